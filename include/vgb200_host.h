@@ -1,0 +1,145 @@
+/*
+ * vgb200_host.h — C view of the C++ host library (libvgb200host.so).
+ *
+ * The reference's host is Rust (FontManager / FontWrapper / GlyphBlock / Writer / Renderer,
+ * reference src/lib.rs:8-13) and there is no Rust toolchain in this image, so the host side above
+ * the device ABI (b200sdf.h) is written in C++ with the same names, argument meaning and error
+ * behaviour; this header exposes it to C / ctypes.  Each function cites what it mirrors.
+ * Conventions: handles are opaque pointers; functions returning int give 0 on success and a
+ * negative value on error with a message retrievable through vgb_last_error() (thread-local).
+ */
+#ifndef VGB200_HOST_H
+#define VGB200_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "b200sdf.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vgb_font vgb_font;         /* FontFileEntry  (src/font/file_entry.rs:13) */
+typedef struct vgb_renderer vgb_renderer; /* Renderer       (src/render/renderer.rs:17) */
+typedef struct vgb_batch vgb_batch;       /* flat segment buffer of one GlyphBlock (new) */
+typedef struct vgb_manager vgb_manager;   /* FontManager    (src/font/manager.rs:18)    */
+typedef struct vgb_writer vgb_writer;     /* Writer         (src/writer/mod.rs:21)      */
+
+const char *vgb_last_error(void);
+void vgb_free(void *p);
+
+/* ---- PbfGlyph (src/protobuf/glyph.rs:10-41) ---- */
+typedef struct {
+	uint32_t id;
+	int32_t has_bitmap;
+	uint32_t width, height;
+	int32_t left, top;
+	uint32_t advance;
+	uint8_t *bitmap;     /* malloc'd, (width+6)*(height+6) bytes when has_bitmap; free with vgb_free */
+	uint64_t bitmap_len;
+	uint32_t n_segments; /* segments handed to the SDF pass */
+} vgb_glyph;
+
+/* ---- FontFileEntry / Face ---- */
+vgb_font *vgb_font_from_bytes(const uint8_t *data, size_t len);           /* FontFileEntry::new, file_entry.rs:32 */
+vgb_font *vgb_font_from_path(const char *path);
+void vgb_font_free(vgb_font *f);
+uint32_t vgb_font_units_per_em(const vgb_font *f);                         /* renderer.rs:107 */
+uint32_t vgb_font_number_of_glyphs(const vgb_font *f);                     /* file_entry.rs:66-71 */
+int32_t vgb_font_glyph_index(const vgb_font *f, uint32_t codepoint);       /* renderer.rs:106; -1 = None */
+int32_t vgb_font_hor_advance(const vgb_font *f, uint32_t glyph_id);        /* renderer.rs:115; -1 = None */
+size_t vgb_font_codepoints(const vgb_font *f, uint32_t *out, size_t cap);  /* metadata.rs:104-118 */
+/* RingBuilder over outline_glyph (ring_builder.rs): flattened rings in font units.
+ * xy: malloc'd 2*n_points doubles; ring_start: malloc'd n_rings+1 offsets.  Returns n_rings. */
+int32_t vgb_font_outline_rings(const vgb_font *f, uint32_t glyph_id, double **xy, uint32_t **ring_start,
+                               uint32_t *n_points);
+
+/* ---- geometry (src/geometry/ring.rs:119-187, segment.rs:96-99) ---- */
+size_t vgb_flatten_quad(const double s[2], const double c[2], const double e[2], double tol_sq, double *out_xy, size_t cap);
+size_t vgb_flatten_cubic(const double s[2], const double c1[2], const double c2[2], const double e[2], double tol_sq,
+                         double *out_xy, size_t cap);
+double vgb_segment_sqdist(double vx, double vy, double wx, double wy, double px, double py);
+const char *vgb_name_to_id(const char *name, char *buf, size_t cap);        /* manager.rs:141-147 */
+
+/* ---- Renderer ---- */
+/* Renderer::new(dummy) (renderer.rs:25-31).  dummy=0 -> the CUDA renderer on `device` with
+ * n_slots batches in flight (0 = default); NULL when no B200 is usable (no CPU fallback). */
+vgb_renderer *vgb_renderer_new(int dummy, int device, uint32_t n_slots);
+void vgb_renderer_free(vgb_renderer *r);
+int vgb_renderer_is_dummy(const vgb_renderer *r);
+b200sdf_ctx *vgb_renderer_context(const vgb_renderer *r); /* NULL for the dummy renderer */
+/* Renderer::render_glyph (renderer.rs:103-149): 1 = Some(glyph), 0 = None, <0 = error */
+int vgb_renderer_render_glyph(const vgb_renderer *r, const vgb_font *f, uint32_t codepoint, vgb_glyph *out);
+
+/* ---- GlyphBatch ---- */
+typedef struct {
+	uint32_t id, advance;
+	int32_t has_bitmap;
+	int32_t x0, y0;          /* integer origin of the bitmap (RenderResult.x0/.y0) */
+	uint32_t bm_width, bm_height; /* RenderResult.width/.height (buffer included) */
+	uint32_t width, height;  /* PbfGlyph fields */
+	int32_t left, top;
+	uint32_t seg_off, seg_cnt;
+	uint64_t out_off;
+} vgb_batch_glyph;
+
+vgb_batch *vgb_batch_new(const vgb_renderer *r);
+void vgb_batch_free(vgb_batch *b);
+void vgb_batch_clear(vgb_batch *b);
+int vgb_batch_add_glyph(vgb_batch *b, const vgb_font *f, uint32_t codepoint); /* 1 added, 0 None */
+/* renderer_precise's own inputs: frame + closed rings in pixel space (renderer_precise.rs:8) */
+int vgb_batch_add_rings(vgb_batch *b, uint32_t id, int32_t x0, int32_t y0, uint32_t width, uint32_t height,
+                        const double *xy, const uint32_t *ring_start, uint32_t n_rings);
+uint32_t vgb_batch_glyph_count(const vgb_batch *b);
+int vgb_batch_glyph_info(const vgb_batch *b, uint32_t i, vgb_batch_glyph *out);
+const b200sdf_segment *vgb_batch_segments(const vgb_batch *b, uint32_t *n_seg);
+const b200sdf_glyph_job *vgb_batch_jobs(const vgb_batch *b, uint32_t *n_jobs);
+const uint8_t *vgb_batch_bitmaps(const vgb_batch *b, uint64_t *bytes);
+uint64_t vgb_batch_pairs(const vgb_batch *b);
+int vgb_renderer_render_batch(const vgb_renderer *r, vgb_batch *b);
+int vgb_renderer_submit_batch(const vgb_renderer *r, vgb_batch *b, uint64_t *ticket);
+int vgb_renderer_wait_batch(const vgb_renderer *r, uint64_t ticket);
+
+/* ---- Writer ---- */
+vgb_writer *vgb_writer_new_file(const char *folder); /* Writer::new_file, writer/mod.rs:35 */
+vgb_writer *vgb_writer_new_memory(void);             /* Writer::new_dummy + contents, writer/mod.rs:44 */
+void vgb_writer_free(vgb_writer *w);
+uint32_t vgb_writer_entry_count(const vgb_writer *w);
+int vgb_writer_entry(const vgb_writer *w, uint32_t i, const char **name, int32_t *is_dir, const uint8_t **bytes,
+                     uint64_t *len);
+
+/* ---- FontManager ---- */
+typedef struct {
+	uint64_t glyphs, bitmaps, pixels, segments, pairs, pbf_bytes, blocks;
+} vgb_stats;
+
+vgb_manager *vgb_manager_new(int parallel);                                        /* manager.rs:28-33 */
+void vgb_manager_free(vgb_manager *m);
+int vgb_manager_add_path(vgb_manager *m, const char *path);                        /* manager.rs:39-53 */
+int vgb_manager_add_font_with_name(vgb_manager *m, const char *name, const char *const *sources, uint32_t n); /* :66-75 */
+int vgb_manager_add_font_bytes_with_name(vgb_manager *m, const char *name, const uint8_t *data, size_t len);
+uint32_t vgb_manager_font_count(const vgb_manager *m);
+const char *vgb_manager_font_id(const vgb_manager *m, uint32_t i);
+/* FontWrapper::get_blocks populations (wrapper.rs:53-76): out[256] = glyphs per block */
+int vgb_manager_block_population(const vgb_manager *m, const char *font_id, uint32_t out[256]);
+/* GlyphBlock::render (glyph_block.rs:69-80): malloc'd PBF bytes of one block */
+int vgb_manager_render_block(const vgb_manager *m, const char *font_id, uint32_t block, const vgb_renderer *r,
+                             uint8_t **pbf, uint64_t *len);
+/* FontManager::render_glyphs (manager.rs:81-125).  shard/n_shards select every n-th (font, block)
+ * task — the multi-GPU sharding; threads = host workers (0 = all cores, 1 = the reference's
+ * --single-thread). */
+int vgb_manager_render_glyphs(const vgb_manager *m, vgb_writer *w, const vgb_renderer *r, uint32_t shard,
+                              uint32_t n_shards, int threads, vgb_stats *stats);
+int vgb_manager_write_index_json(const vgb_manager *m, vgb_writer *w);             /* manager.rs:128-131 */
+
+/* ---- PBF decode (commands/debug.rs:60-79) ---- */
+/* Decodes one glyphs PBF; glyphs: malloc'd array (each bitmap malloc'd); returns count or <0. */
+int32_t vgb_pbf_decode(const uint8_t *data, size_t len, char *name, size_t name_cap, char *range, size_t range_cap,
+                       vgb_glyph **glyphs);
+void vgb_glyphs_free(vgb_glyph *glyphs, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,268 @@
+"""CPU tests (no GPU): the C++ host side of the product against the oracle.
+
+Everything that decides a metric or feeds the kernel is produced on the host, so it can be
+checked bit-for-bit here: cmap / hmtx / outline flattening, glyph frames, the f32 segment buffer,
+and — with the reference's own `Renderer::new_dummy()` fake (src/render/renderer.rs:39-43) — the
+complete PBF byte stream of every block, incl. the reference's golden sizes.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import versatiles_glyphs_rs_b200 as V
+from versatiles_glyphs_rs_b200 import _native as N
+
+
+@pytest.fixture(scope="module")
+def fira():
+    return V.FontFileEntry(path=O.FIRA), O.Font(O.FIRA)
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function declared in include/*.h must be exported (and nothing is called here)."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for header, lib, table in (("b200sdf.h", N.sdf, N.SDF_SYMBOLS), ("vgb200_host.h", N.host, N.HOST_SYMBOLS)):
+        text = open(os.path.join(root, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared = set(re.findall(r"\b((?:b200sdf|vgb)_[a-z0-9_]+)\s*\(", text))
+        assert declared, header
+        for name in declared:
+            assert hasattr(lib, name), f"{header}: {name} not exported"
+        assert declared == set(table), (header, declared ^ set(table))
+    assert N.sdf.b200sdf_abi_version() == 1
+
+
+def test_no_cuda_device_fails_loudly():
+    """No CPU fallback: without a GPU the precise renderer refuses to exist (the dummy one works)."""
+    if V.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(V.B200Error):
+        V.Renderer(dummy=False)
+    with pytest.raises(V.B200Error):
+        V.SdfContext()
+    assert V.Renderer(dummy=True).dummy
+
+
+def test_face_basics_match_reference_goldens(fira):
+    f, _ = fira
+    # reference src/font/metadata.rs:136-153, src/font/file_entry.rs:66-71
+    assert len(f.codepoints()) == 1686
+    assert f.number_of_glyphs == 2677
+    assert f.units_per_em == 1000
+    noto = V.FontFileEntry(path=os.path.join(O.NOTO_DIR, "Noto Sans - Regular.ttf"))
+    assert len(noto.codepoints()) == 3094
+    assert f.glyph_index(0xD800) is None
+
+
+@pytest.mark.parametrize("path", [O.FIRA] + O.noto_paths())
+def test_cmap_hmtx_outline_match_oracle(path):
+    """cmap enumeration, glyph ids, advances and flattened rings (font units, f64) are identical."""
+    f, o = V.FontFileEntry(path=path), O.Font(path)
+    cps = f.codepoints()
+    assert cps.tolist() == o.codepoints()
+    step = max(1, len(cps) // 400)  # every glyph of small fonts, a stride through the large ones
+    for cp in cps[::step].tolist():
+        gid = f.glyph_index(cp)
+        assert gid == o.glyph_index(cp)
+        assert f.glyph_hor_advance(gid) == o.hor_advance(gid)
+        pts, starts = f.outline_rings(gid)
+        rings = o.outline_rings(gid)
+        assert len(rings) == len(starts) - 1
+        for i, r in enumerate(rings):
+            assert np.array_equal(pts[starts[i] : starts[i + 1]], r), (path, cp)
+
+
+def test_flatten_point_counts():
+    """reference src/render/ring_builder.rs:197-229: quad and cubic at precision 0.01 give 17 points."""
+    arr = lambda p: (C.c_double * 2)(*p)
+    out = (C.c_double * 4096)()
+    n = N.host.vgb_flatten_quad(arr((0, 0)), arr((10, 10)), arr((20, 0)), 0.01, out, 2048)
+    assert n + 1 == 17
+    got = np.array(out[: 2 * n]).reshape(-1, 2)
+    assert np.array_equal(got, O.flatten_quad((0, 0), (10, 10), (20, 0)))
+    n = N.host.vgb_flatten_cubic(arr((0, 0)), arr((10, 10)), arr((20, 10)), arr((30, 0)), 0.01, out, 2048)
+    assert n + 1 == 17
+    got = np.array(out[: 2 * n]).reshape(-1, 2)
+    assert np.array_equal(got, O.flatten_cubic((0, 0), (10, 10), (20, 10), (30, 0)))
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        p = rng.integers(-2000, 2000, size=(4, 2)).astype(float)
+        n = N.host.vgb_flatten_cubic(arr(p[0]), arr(p[1]), arr(p[2]), arr(p[3]), 0.01, out, 2048)
+        assert np.array_equal(np.array(out[: 2 * n]).reshape(-1, 2), O.flatten_cubic(p[0], p[1], p[2], p[3]))
+
+
+def test_segment_distance_cases():
+    """reference src/geometry/segment.rs:117-198 (projection / clamp cases)."""
+    d = N.host.vgb_segment_sqdist
+    assert d(0, 0, 10, 0, 5, 3) == 9.0
+    assert d(0, 0, 10, 0, -3, 4) == 25.0  # clamps to start
+    assert d(0, 0, 10, 0, 13, 4) == 25.0  # clamps to end
+    assert d(2, 2, 2, 2, 5, 6) == 25.0  # zero-length segment -> distance to the point
+    rng = np.random.default_rng(3)
+    for _ in range(500):
+        a = rng.normal(size=6) * 10
+        assert d(*a) == O.segment_sqdist(a[0:2], a[2:4], a[4:6])
+
+
+def test_name_to_id():
+    """reference src/font/manager.rs:141-147 and its tests (:224-232)."""
+    assert V.name_to_id("Fira Sans - Regular") == "fira_sans_regular"
+    assert V.name_to_id("  Noto--Sans__Bold  Italic ") == "noto_sans_bold_italic"
+    assert V.name_to_id("Noto Sans Regular") == "noto_sans_regular"
+
+
+def test_frames_and_segments_match_oracle_fira(fira):
+    """Glyph frames bit-exact; the f32 segment buffer is the oracle's f64 segments, origin-relative."""
+    f, o = fira
+    r = V.Renderer(dummy=True)
+    batch = r.new_batch()
+    cps = f.codepoints().tolist()
+    for cp in cps:
+        assert batch.add_glyph(f, cp)
+    assert not batch.add_glyph(f, 0xD800) and not batch.add_glyph(f, 0x110000) and not batch.add_glyph(f, 0x0378)
+    assert len(batch) == len(cps)
+    segs = batch.segments()
+    n_bitmaps = 0
+    for i, cp in enumerate(cps):
+        g = batch.glyph_info(i)
+        osegs, (x0, y0, W, H) = o.glyph_segments(cp)
+        assert g.id == cp
+        if len(osegs) == 0:
+            assert not g.has_bitmap
+            continue
+        n_bitmaps += 1
+        assert (g.x0, g.y0, g.bm_width, g.bm_height) == (x0, y0, W, H), cp
+        assert g.seg_cnt == len(osegs)
+        want = (osegs - np.array([x0, y0, x0, y0], dtype=np.float64)).astype(np.float32)
+        assert np.array_equal(segs[g.seg_off : g.seg_off + g.seg_cnt], want), cp
+    assert n_bitmaps == 1679
+    assert batch.pairs == sum(
+        int(batch.glyph_info(i).bm_width) * batch.glyph_info(i).bm_height * batch.glyph_info(i).seg_cnt for i in range(len(cps))
+    )
+
+
+def test_render_glyph_metrics_goldens_dummy(fira):
+    """reference src/render/renderer.rs:176-287 metrics (bitmaps need the GPU: tests/test_gpu_parity.py)."""
+    f, _ = fira
+    r = V.Renderer.new_dummy()
+    g = r.render_glyph(f, 0x20)
+    assert (g.width, g.height, g.left, g.top, g.advance, g.bitmap) == (0, 0, 0, 0, 6, None)
+    g = r.render_glyph(f, 0x41)
+    assert (g.width, g.height, g.left, g.top, g.advance) == (14, 17, 0, -7, 13)
+    assert len(g.bitmap) == (14 + 6) * (17 + 6) and not any(g.bitmap)
+    g = r.render_glyph(f, 0xE6)
+    assert (g.width, g.height, g.left, g.top, g.advance) == (19, 14, 0, -11, 19)
+    g = r.render_glyph(f, 0x60)
+    assert (g.width, g.height, g.left, g.top, g.advance) == (7, 5, 0, -4, 7)
+    assert r.render_glyph(f, 0xD800) is None and r.render_glyph(f, 0x0378) is None
+
+
+# reference src/commands/recurse.rs:341-367 — golden per-block PBF sizes of Fira Sans (dummy == precise sizes)
+FIRA_PBF_SIZES = {
+    0: 80022, 1024: 118037, 11264: 3579, 1280: 26296, 256: 130750, 3584: 592, 42752: 5761, 43776: 487,
+    512: 92634, 64256: 1032, 65024: 50, 7424: 7260, 768: 63760, 7680: 87078, 7936: 124520, 8192: 20301,
+    8448: 17395, 8704: 6511, 8960: 4375, 9472: 853,
+}
+
+
+def test_fira_dummy_pipeline_matches_oracle_bytes_and_golden_sizes():
+    m = V.FontManager(parallel=True)
+    m.add_font_with_name("Fira Sans - Regular", [O.FIRA])
+    assert m.font_ids() == ["fira_sans_regular"]
+    pop = m.block_population("fira_sans_regular")
+    oset = O.FontSet("Fira Sans - Regular", [O.FIRA])
+    assert pop.tolist() == oset.block_population()
+    # reference src/font/wrapper.rs:197-220 (first entries)
+    assert pop[:3].tolist() == [192, 256, 219]
+    w = V.Writer.new_memory()
+    st = m.render_glyphs(w, V.Renderer.new_dummy())
+    entries = w.entries()
+    assert entries[0] == ("fira_sans_regular/", True, b"")
+    files = {n: d for n, is_dir, d in entries if not is_dir}
+    assert len(files) == 256 and st.blocks == 256 and st.glyphs == 1686 and st.bitmaps == 1679
+    assert st.segments == 600952 and st.pixels == 758736
+    for start, size in FIRA_PBF_SIZES.items():
+        assert len(files[f"fira_sans_regular/{start}-{start + 255}.pbf"]) == size
+    nonempty = [n for n, d in files.items() if len(d) > 40]
+    assert len(nonempty) == len(FIRA_PBF_SIZES)
+    for b in range(256):
+        assert files[f"fira_sans_regular/{b * 256}-{b * 256 + 255}.pbf"] == oset.render_block(b, O.MODE_DUMMY), b
+    assert st.pbf_bytes == sum(len(d) for d in files.values())
+
+
+def test_noto_merge_dummy_pipeline_matches_oracle():
+    """C2: 20 Noto Sans files merged into one glyph set, first file wins (glyph_block.rs:34-36)."""
+    paths = O.noto_paths()
+    m = V.FontManager(parallel=True)
+    m.add_font_with_name("Noto Sans Regular", paths)
+    oset = O.FontSet("Noto Sans Regular", paths)
+    assert m.block_population("noto_sans_regular").tolist() == oset.block_population()
+    w = V.Writer.new_memory()
+    st = m.render_glyphs(w, V.Renderer.new_dummy(), threads=4)
+    assert (st.glyphs, st.bitmaps, st.segments, st.pixels) == (6480, 6445, 3956999, 3295280)
+    files = {n: d for n, is_dir, d in w.entries() if not is_dir}
+    for b in range(256):
+        assert files[f"noto_sans_regular/{b * 256}-{b * 256 + 255}.pbf"] == oset.render_block(b, O.MODE_DUMMY), b
+    # single block API = GlyphBlock::render
+    assert m.render_block("noto_sans_regular", 9, V.Renderer.new_dummy()) == oset.render_block(9, O.MODE_DUMMY)
+
+
+def test_sharded_render_covers_every_task_once():
+    """font x block sharding (multi-GPU): shards are disjoint and their union is the full job."""
+    m = V.FontManager(parallel=False)
+    m.add_font_with_name("Fira Sans - Regular", [O.FIRA])
+    m.add_font_with_name("Noto Sans Regular", O.noto_paths()[:2])
+    full = V.Writer.new_memory()
+    r = V.Renderer.new_dummy()
+    m.render_glyphs(full, r)
+    want = {n: d for n, is_dir, d in full.entries() if not is_dir}
+    assert len(want) == 512
+    got = {}
+    for s in range(3):
+        w = V.Writer.new_memory()
+        m.render_glyphs(w, r, shard=s, n_shards=3)
+        part = {n: d for n, is_dir, d in w.entries() if not is_dir}
+        assert not set(part) & set(got)
+        got.update(part)
+    assert got == want
+
+
+def test_pbf_roundtrip_and_index_json():
+    m = V.FontManager(parallel=False)
+    m.add_font_with_name("Fira Sans - Regular", [O.FIRA])
+    data = m.render_block("fira_sans_regular", 0, V.Renderer.new_dummy())
+    name, rng, glyphs = V.decode_pbf(data)
+    oname, orng, oglyphs = O.decode_pbf(data)
+    assert (name, rng) == (oname, orng) == ("fira_sans_regular", "0-255")
+    assert len(glyphs) == len(oglyphs) == 192
+    for a, b in zip(glyphs, oglyphs):
+        assert (a.id, a.width, a.height, a.left, a.top, a.advance) == (
+            b["id"], b["width"], b["height"], b["left"], b["top"], b["advance"])
+        assert (a.bitmap is None) == (b["bitmap"] is None)
+    w = V.Writer.new_memory()
+    m.write_index_json(w)
+    assert w.entries() == [("index.json", False, b'[\n  "fira_sans_regular"\n]')]
+
+
+def test_file_writer(tmp_path):
+    m = V.FontManager(parallel=False)
+    m.add_font_with_name("Fira Sans - Regular", [O.FIRA])
+    out = tmp_path / "glyphs"
+    out.mkdir()
+    m.render_glyphs(V.Writer.new_file(str(out)), V.Renderer.new_dummy())
+    names = sorted(os.listdir(out / "fira_sans_regular"))
+    assert len(names) == 256
+    assert os.path.getsize(out / "fira_sans_regular" / "0-255.pbf") == 80022  # recurse.rs:345
+
+
+def test_bad_font_errors():
+    with pytest.raises(V.B200Error, match="Could not parse font data"):
+        V.FontFileEntry(data=b"not a font")
+    m = V.FontManager()
+    with pytest.raises(V.B200Error):
+        m.add_font_with_name("x", ["/nonexistent/font.ttf"])

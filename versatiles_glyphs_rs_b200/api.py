@@ -1,0 +1,405 @@
+"""Python mirror of the reference's public Rust API for the rendering path
+(reference src/lib.rs:8-13: FontManager, FontWrapper, GlyphBlock, Writer, Renderer, PbfGlyph).
+
+Thin ctypes wrappers over libvgb200host.so / libb200sdf.so — all work happens in native code.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from . import _native as N
+
+GLYPH_SIZE = 24  # reference src/render/mod.rs:52
+BUFFER = 3  # reference src/render/mod.rs:58
+GLYPH_BLOCK_SIZE = 256  # reference src/font/glyph_block.rs:7
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+@dataclass
+class PbfGlyph:
+    """reference src/protobuf/glyph.rs:10-41"""
+
+    id: int
+    bitmap: Optional[bytes]
+    width: int
+    height: int
+    left: int
+    top: int
+    advance: int
+    n_segments: int = 0
+
+
+def _glyph_from_c(g: N.Glyph) -> PbfGlyph:
+    bm = C.string_at(g.bitmap, g.bitmap_len) if g.has_bitmap else None
+    return PbfGlyph(g.id, bm, g.width, g.height, g.left, g.top, g.advance, g.n_segments)
+
+
+class FontFileEntry:
+    """reference src/font/file_entry.rs:13-56 (Face + code point set)."""
+
+    def __init__(self, data: Optional[bytes] = None, path: Optional[str] = None):
+        if data is not None:
+            self._h = N.host.vgb_font_from_bytes(data, len(data))
+        else:
+            self._h = N.host.vgb_font_from_path(path.encode())
+        if not self._h:
+            raise B200Error(N.host_error())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            N.host.vgb_font_free(self._h)
+            self._h = None
+
+    @property
+    def units_per_em(self) -> int:
+        return N.host.vgb_font_units_per_em(self._h)
+
+    @property
+    def number_of_glyphs(self) -> int:
+        return N.host.vgb_font_number_of_glyphs(self._h)
+
+    def glyph_index(self, cp: int) -> Optional[int]:
+        g = N.host.vgb_font_glyph_index(self._h, cp)
+        return None if g < 0 else g
+
+    def glyph_hor_advance(self, gid: int) -> Optional[int]:
+        a = N.host.vgb_font_hor_advance(self._h, gid)
+        return None if a < 0 else a
+
+    def codepoints(self) -> np.ndarray:
+        n = N.host.vgb_font_codepoints(self._h, None, 0)
+        out = np.zeros(n, dtype=np.uint32)
+        N.host.vgb_font_codepoints(self._h, out.ctypes.data_as(N.u32p), n)
+        return out
+
+    def outline_rings(self, gid: int):
+        """RingBuilder over outline_glyph: (xy float64 [n,2], ring_start uint32 [n_rings+1]) in font units."""
+        xy = N.f64p()
+        rs = N.u32p()
+        npts = C.c_uint32()
+        nr = N.host.vgb_font_outline_rings(self._h, gid, C.byref(xy), C.byref(rs), C.byref(npts))
+        pts = np.ctypeslib.as_array(xy, shape=(max(npts.value, 1) * 2,))[: npts.value * 2].copy().reshape(-1, 2)
+        starts = np.ctypeslib.as_array(rs, shape=(nr + 1,)).copy()
+        N.host.vgb_free(xy)
+        N.host.vgb_free(rs)
+        return pts, starts
+
+
+class Renderer:
+    """reference src/render/renderer.rs:17-43.  ``Renderer(dummy=False)`` is the CUDA renderer
+    (the reference's ``Precise`` arm replaced by the sm_100a kernel); ``Renderer(dummy=True)`` is the
+    zero-bitmap fake of renderer_dummy.rs.  Raises when no B200 is usable: there is no CPU path."""
+
+    def __init__(self, dummy: bool = False, device: int = 0, n_slots: int = 0):
+        self._h = N.host.vgb_renderer_new(1 if dummy else 0, device, n_slots)
+        if not self._h:
+            raise B200Error(N.host_error())
+        self.dummy = dummy
+
+    @classmethod
+    def new_precise(cls, device: int = 0, n_slots: int = 0):
+        return cls(False, device, n_slots)
+
+    @classmethod
+    def new_dummy(cls):
+        return cls(True)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            N.host.vgb_renderer_free(self._h)
+            self._h = None
+
+    @property
+    def context(self):
+        """b200sdf_ctx* of the CUDA renderer (None for dummy)."""
+        return N.host.vgb_renderer_context(self._h)
+
+    def render_glyph(self, font: FontFileEntry, index: int) -> Optional[PbfGlyph]:
+        """reference src/render/renderer.rs:103-149"""
+        g = N.Glyph()
+        rc = N.host.vgb_renderer_render_glyph(self._h, font._h, index, C.byref(g))
+        if rc < 0:
+            raise B200Error(N.host_error())
+        if rc == 0:
+            return None
+        out = _glyph_from_c(g)
+        N.host.vgb_free(g.bitmap)
+        return out
+
+    def new_batch(self) -> "GlyphBatch":
+        return GlyphBatch(self)
+
+    def render_batch(self, batch: "GlyphBatch"):
+        if N.host.vgb_renderer_render_batch(self._h, batch._h) != 0:
+            raise B200Error(N.host_error())
+
+    def submit_batch(self, batch: "GlyphBatch") -> int:
+        t = C.c_uint64()
+        if N.host.vgb_renderer_submit_batch(self._h, batch._h, C.byref(t)) != 0:
+            raise B200Error(N.host_error())
+        return t.value
+
+    def wait_batch(self, ticket: int):
+        if N.host.vgb_renderer_wait_batch(self._h, ticket) != 0:
+            raise B200Error(N.host_error())
+
+
+class GlyphBatch:
+    """The flat segment buffer of one GlyphBlock (north star: "packed into a flat SoA segment buffer
+    per GlyphBlock and uploaded once")."""
+
+    def __init__(self, renderer: Renderer):
+        self._h = N.host.vgb_batch_new(renderer._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            N.host.vgb_batch_free(self._h)
+            self._h = None
+
+    def clear(self):
+        N.host.vgb_batch_clear(self._h)
+
+    def add_glyph(self, font: FontFileEntry, cp: int) -> bool:
+        return N.host.vgb_batch_add_glyph(self._h, font._h, cp) == 1
+
+    def add_rings(self, gid: int, x0: int, y0: int, width: int, height: int, xy: np.ndarray, ring_start: np.ndarray):
+        xy = np.ascontiguousarray(xy, dtype=np.float64)
+        rs = np.ascontiguousarray(ring_start, dtype=np.uint32)
+        rc = N.host.vgb_batch_add_rings(
+            self._h, gid, x0, y0, width, height, xy.ctypes.data_as(N.f64p), rs.ctypes.data_as(N.u32p), len(rs) - 1
+        )
+        if rc != 1:
+            raise B200Error(N.host_error())
+
+    def __len__(self):
+        return N.host.vgb_batch_glyph_count(self._h)
+
+    def glyph_info(self, i: int) -> N.BatchGlyph:
+        g = N.BatchGlyph()
+        if N.host.vgb_batch_glyph_info(self._h, i, C.byref(g)) != 0:
+            raise B200Error(N.host_error())
+        return g
+
+    def segments(self) -> np.ndarray:
+        n = C.c_uint32()
+        p = N.host.vgb_batch_segments(self._h, C.byref(n))
+        if n.value == 0:
+            return np.zeros((0, 4), dtype=np.float32)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n.value, 4))
+
+    def jobs(self) -> np.ndarray:
+        n = C.c_uint32()
+        p = N.host.vgb_batch_jobs(self._h, C.byref(n))
+        dt = np.dtype(
+            [("seg_off", "<u4"), ("seg_cnt", "<u4"), ("width", "<u4"), ("height", "<u4"), ("out_off", "<u8")]
+        )
+        if n.value == 0:
+            return np.zeros(0, dtype=dt)
+        buf = C.string_at(p, n.value * C.sizeof(N.GlyphJob))
+        return np.frombuffer(buf, dtype=dt).copy()
+
+    def bitmaps(self) -> np.ndarray:
+        n = C.c_uint64()
+        p = N.host.vgb_batch_bitmaps(self._h, C.byref(n))
+        if n.value == 0 or not p:
+            return np.zeros(0, dtype=np.uint8)
+        return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    @property
+    def pairs(self) -> int:
+        return N.host.vgb_batch_pairs(self._h)
+
+    def bitmap_of(self, i: int) -> Optional[np.ndarray]:
+        g = self.glyph_info(i)
+        if not g.has_bitmap:
+            return None
+        n = g.bm_width * g.bm_height
+        return self.bitmaps()[g.out_off : g.out_off + n].reshape(g.bm_height, g.bm_width)
+
+
+class Writer:
+    """reference src/writer/mod.rs:27-96 (directory sink and in-memory recorder)."""
+
+    def __init__(self, folder: Optional[str] = None):
+        self._h = N.host.vgb_writer_new_file(folder.encode()) if folder else N.host.vgb_writer_new_memory()
+
+    @classmethod
+    def new_file(cls, folder: str):
+        return cls(folder)
+
+    @classmethod
+    def new_memory(cls):
+        return cls(None)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            N.host.vgb_writer_free(self._h)
+            self._h = None
+
+    def entries(self):
+        """[(name, is_dir, bytes)] recorded by the in-memory writer."""
+        out = []
+        for i in range(N.host.vgb_writer_entry_count(self._h)):
+            name = C.c_char_p()
+            is_dir = C.c_int32()
+            data = N.u8p()
+            n = C.c_uint64()
+            N.host.vgb_writer_entry(self._h, i, C.byref(name), C.byref(is_dir), C.byref(data), C.byref(n))
+            out.append((name.value.decode(), bool(is_dir.value), C.string_at(data, n.value) if n.value else b""))
+        return out
+
+
+@dataclass
+class RenderStats:
+    glyphs: int
+    bitmaps: int
+    pixels: int
+    segments: int
+    pairs: int
+    pbf_bytes: int
+    blocks: int
+
+
+class FontManager:
+    """reference src/font/manager.rs:18-147."""
+
+    def __init__(self, parallel: bool = True):
+        self._h = N.host.vgb_manager_new(1 if parallel else 0)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            N.host.vgb_manager_free(self._h)
+            self._h = None
+
+    def add_path(self, path: str):
+        if N.host.vgb_manager_add_path(self._h, path.encode()) != 0:
+            raise B200Error(N.host_error())
+
+    def add_paths(self, paths: List[str]):
+        for p in paths:
+            self.add_path(p)
+
+    def add_font_with_name(self, name: str, sources: List[str]):
+        arr = (C.c_char_p * len(sources))(*[s.encode() for s in sources])
+        if N.host.vgb_manager_add_font_with_name(self._h, name.encode(), arr, len(sources)) != 0:
+            raise B200Error(N.host_error())
+
+    def add_font_bytes_with_name(self, name: str, data: bytes):
+        if N.host.vgb_manager_add_font_bytes_with_name(self._h, name.encode(), data, len(data)) != 0:
+            raise B200Error(N.host_error())
+
+    def font_ids(self) -> List[str]:
+        return [N.host.vgb_manager_font_id(self._h, i).decode() for i in range(N.host.vgb_manager_font_count(self._h))]
+
+    def block_population(self, font_id: str) -> np.ndarray:
+        out = np.zeros(256, dtype=np.uint32)
+        if N.host.vgb_manager_block_population(self._h, font_id.encode(), out.ctypes.data_as(N.u32p)) != 0:
+            raise B200Error(N.host_error())
+        return out
+
+    def render_block(self, font_id: str, block: int, renderer: Renderer) -> bytes:
+        """GlyphBlock::render (reference src/font/glyph_block.rs:69-80), glyphs in ascending id order."""
+        p = N.u8p()
+        n = C.c_uint64()
+        if N.host.vgb_manager_render_block(self._h, font_id.encode(), block, renderer._h, C.byref(p), C.byref(n)) != 0:
+            raise B200Error(N.host_error())
+        out = C.string_at(p, n.value)
+        N.host.vgb_free(p)
+        return out
+
+    def render_glyphs(self, writer: Writer, renderer: Renderer, shard: int = 0, n_shards: int = 1, threads: int = 0) -> RenderStats:
+        """reference src/font/manager.rs:81-125 as an async batch pipeline over CUDA streams."""
+        st = N.Stats()
+        if N.host.vgb_manager_render_glyphs(self._h, writer._h, renderer._h, shard, n_shards, threads, C.byref(st)) != 0:
+            raise B200Error(N.host_error())
+        return RenderStats(st.glyphs, st.bitmaps, st.pixels, st.segments, st.pairs, st.pbf_bytes, st.blocks)
+
+    def write_index_json(self, writer: Writer):
+        if N.host.vgb_manager_write_index_json(self._h, writer._h) != 0:
+            raise B200Error(N.host_error())
+
+
+def name_to_id(name: str) -> str:
+    buf = C.create_string_buffer(4 * len(name) + 8)
+    return N.host.vgb_name_to_id(name.encode(), buf, len(buf)).decode()
+
+
+def decode_pbf(data: bytes):
+    """(name, range, [PbfGlyph]) — mirror of the prost decode in reference src/commands/debug.rs:60-79."""
+    name = C.create_string_buffer(512)
+    rng = C.create_string_buffer(64)
+    gl = C.POINTER(N.Glyph)()
+    n = N.host.vgb_pbf_decode(data, len(data), name, len(name), rng, len(rng), C.byref(gl))
+    if n < 0:
+        raise B200Error(N.host_error())
+    out = [_glyph_from_c(gl[i]) for i in range(n)]
+    N.host.vgb_glyphs_free(gl, n)
+    return name.value.decode(), rng.value.decode(), out
+
+
+class SdfContext:
+    """Direct view of the device ABI (include/b200sdf.h) over numpy buffers."""
+
+    def __init__(self, device: int = 0, n_slots: int = 2):
+        h = C.c_void_p()
+        rc = N.sdf.b200sdf_create(device, n_slots, C.byref(h))
+        if rc != 0:
+            raise B200Error(f"b200sdf_create failed with code {rc}: a B200 (sm_100) GPU is required; there is no CPU fallback")
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            N.sdf.b200sdf_destroy(self._h)
+            self._h = None
+
+    def last_error(self) -> str:
+        return (N.sdf.b200sdf_last_error(self._h) or b"").decode()
+
+    def render(self, segs: np.ndarray, jobs: np.ndarray, out_bytes: int) -> np.ndarray:
+        """b200sdf_render over host buffers: segs float32 [n,4], jobs structured (see GlyphBatch.jobs)."""
+        segs = np.ascontiguousarray(segs, dtype=np.float32).reshape(-1, 4)
+        jobs = np.ascontiguousarray(jobs)
+        out = np.zeros(max(out_bytes, 1), dtype=np.uint8)
+        rc = N.sdf.b200sdf_render(self._h, segs.ctypes.data, len(segs), jobs.ctypes.data, len(jobs), out.ctypes.data, out_bytes)
+        if rc != 0:
+            raise B200Error(f"b200sdf_render: {rc}: {self.last_error()}")
+        return out[:out_bytes]
+
+    def plan_tiles(self, jobs: np.ndarray, n_seg: int, out_bytes: int):
+        jobs = np.ascontiguousarray(jobs)
+        n = C.c_uint32()
+        pairs = C.c_uint64()
+        rc = N.sdf.b200sdf_plan_tiles(jobs.ctypes.data, len(jobs), n_seg, out_bytes, None, 0, C.byref(n), C.byref(pairs))
+        if rc != 0:
+            raise B200Error(f"b200sdf_plan_tiles: {rc}")
+        tiles = np.zeros(n.value * C.sizeof(N.TileJob), dtype=np.uint8)
+        rc = N.sdf.b200sdf_plan_tiles(jobs.ctypes.data, len(jobs), n_seg, out_bytes, tiles.ctypes.data, n.value, C.byref(n), C.byref(pairs))
+        if rc != 0:
+            raise B200Error(f"b200sdf_plan_tiles: {rc}")
+        return tiles, n.value, pairs.value
+
+    def render_device(self, d_segs: int, d_tiles: int, n_tiles: int, d_out: int, stream: int = 0):
+        rc = N.sdf.b200sdf_render_device(self._h, d_segs, d_tiles, n_tiles, d_out, stream)
+        if rc != 0:
+            raise B200Error(f"b200sdf_render_device: {rc}: {self.last_error()}")
+
+    def measure_fp32_peak(self, reps: int = 5):
+        t = C.c_double()
+        ms = C.c_double()
+        rc = N.sdf.b200sdf_measure_fp32_peak(self._h, reps, C.byref(t), C.byref(ms))
+        if rc != 0:
+            raise B200Error(f"b200sdf_measure_fp32_peak: {rc}: {self.last_error()}")
+        return t.value, ms.value
+
+    @property
+    def launch_count(self) -> int:
+        return N.sdf.b200sdf_launch_count(self._h)
+
+
+def device_count() -> int:
+    return N.sdf.b200sdf_device_count()

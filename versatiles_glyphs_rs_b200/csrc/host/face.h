@@ -1,0 +1,85 @@
+// face.h — the subset of ttf-parser 0.25.1's `Face` that the reference's rendering path calls
+// (crate not vendored in the reference; call sites: src/render/renderer.rs:106,107,110,115,
+// src/font/file_entry.rs:48, src/font/metadata.rs:91-116).  TrueType `glyf` outlines, cmap
+// formats 0/4/6/12, hmtx advances, name table strings.  No CFF, no variations (none of the
+// reference's fixtures use them; SURVEY.md §8(f) rank 3 lists them as "next").
+#pragma once
+
+#include <cstdint>
+#include <memory>
+#include <optional>
+#include <string>
+#include <vector>
+
+namespace vgb {
+
+// ttf_parser::OutlineBuilder — coordinates arrive as f32 font units
+class OutlineBuilder {
+  public:
+	virtual ~OutlineBuilder() = default;
+	virtual void move_to(float x, float y) = 0;
+	virtual void line_to(float x, float y) = 0;
+	virtual void quad_to(float x1, float y1, float x, float y) = 0;
+	virtual void curve_to(float x1, float y1, float x2, float y2, float x, float y) = 0;
+	virtual void close() = 0;
+};
+
+class Face {
+  public:
+	// Face::parse(data, 0): nullptr when the mandatory tables are missing / truncated
+	static std::unique_ptr<Face> parse(std::vector<uint8_t> data);
+
+	uint16_t units_per_em() const { return upm_; }
+	uint16_t number_of_glyphs() const { return num_glyphs_; }
+	// first unicode cmap subtable (table order) that maps the code point
+	std::optional<uint16_t> glyph_index(uint32_t codepoint) const;
+	std::optional<uint16_t> glyph_hor_advance(uint16_t glyph_id) const;
+	// returns false when the glyph has no outline (no callbacks were made)
+	bool outline_glyph(uint16_t glyph_id, OutlineBuilder &builder) const;
+	// sorted union over unicode cmap subtables of the code points they map (metadata.rs:104-118)
+	std::vector<uint32_t> codepoints() const;
+	// name table entry (first record with that id that decodes; UTF-16BE / Mac Roman), "" if none
+	std::string name(uint16_t name_id) const;
+
+  private:
+	struct Span {
+		size_t off = 0, len = 0;
+	};
+	struct CmapSubtable {
+		uint16_t platform, encoding, format;
+		Span data;
+		bool is_unicode() const
+		{
+			return platform == 0 || (platform == 3 && encoding == 1) ||
+			       (platform == 3 && encoding == 10 && (format == 12 || format == 13));
+		}
+	};
+	struct Transform {
+		float a = 1.f, b = 0.f, c = 0.f, d = 1.f, e = 0.f, f = 0.f;
+		bool is_default() const { return a == 1.f && b == 0.f && c == 0.f && d == 1.f && e == 0.f && f == 0.f; }
+		static Transform combine(const Transform &t1, const Transform &t2);
+		void apply_to(float &x, float &y) const;
+	};
+	class ContourEmitter;
+
+	bool table(const char tag[4], Span &out) const;
+	uint16_t u16(size_t off) const { return (uint16_t)((data_[off] << 8) | data_[off + 1]); }
+	int16_t i16(size_t off) const { return (int16_t)u16(off); }
+	uint32_t u32(size_t off) const
+	{
+		return ((uint32_t)data_[off] << 24) | ((uint32_t)data_[off + 1] << 16) | ((uint32_t)data_[off + 2] << 8) |
+		       (uint32_t)data_[off + 3];
+	}
+	std::optional<uint16_t> lookup(const CmapSubtable &s, uint32_t cp) const;
+	template <typename F> void enumerate(const CmapSubtable &s, F &&f) const;
+	bool glyph_range(uint16_t gid, Span &out) const;
+	void outline_impl(Span glyph, int depth, const Transform &t, OutlineBuilder &b) const;
+
+	std::vector<uint8_t> data_;
+	uint16_t upm_ = 0, num_glyphs_ = 0, num_hmetrics_ = 0;
+	bool loca_long_ = false;
+	Span hmtx_, loca_, glyf_, cmap_, name_;
+	std::vector<CmapSubtable> subtables_;
+};
+
+} // namespace vgb

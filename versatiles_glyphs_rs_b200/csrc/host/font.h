@@ -1,0 +1,131 @@
+// font.h — block / font / manager orchestration (mirror of reference src/font/*.rs) and the
+// writer facade (src/writer/mod.rs).
+//
+//   FontFileEntry  = font/file_entry.rs:13-56     owned font bytes + parsed Face + code point set
+//   GlyphBlock     = font/glyph_block.rs:9-89     <= 256 code points, first file wins
+//   FontWrapper    = font/wrapper.rs:15-76        files of one font id -> 256 BMP blocks
+//   FontManager    = font/manager.rs:18-147       fonts by id; render_glyphs = the batch pipeline
+//   Writer         = writer/mod.rs:27-96          directory / in-memory sink
+#pragma once
+
+#include <array>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "face.h"
+#include "pbf.h"
+#include "render.h"
+
+namespace vgb {
+
+constexpr uint32_t GLYPH_BLOCK_SIZE = 256; // glyph_block.rs:7
+
+struct FontFileEntry {
+	std::unique_ptr<Face> face;
+	std::vector<uint32_t> codepoints; // FontMetadata.codepoints (metadata.rs:104-118)
+	std::string family;               // name id 1 (metadata.rs:97)
+	// file_entry.rs:32-56; nullptr + *err on unparsable data
+	static std::unique_ptr<FontFileEntry> from_bytes(std::vector<uint8_t> data, std::string *err);
+	static std::unique_ptr<FontFileEntry> from_path(const std::string &path, std::string *err);
+};
+
+class GlyphBlock {
+  public:
+	explicit GlyphBlock(uint32_t start_index = 0) : start_index_(start_index) { fonts_.fill(nullptr); }
+	uint32_t start_index() const { return start_index_; }
+	// glyph_block.rs:34-36 — entry().or_insert(): the first file that has the code point keeps it
+	void set_glyph_font(uint8_t char_index, const FontFileEntry *font)
+	{
+		if (!fonts_[char_index]) {
+			fonts_[char_index] = font;
+			++len_;
+		}
+	}
+	size_t len() const { return len_; }
+	bool is_empty() const { return len_ == 0; }
+	const FontFileEntry *font_of(uint8_t char_index) const { return fonts_[char_index]; }
+	std::string range() const;    // "{start}-{start+255}"            glyph_block.rs:52-58
+	std::string filename() const; // "{range}.pbf"                     glyph_block.rs:85-87
+	// glyph_block.rs:69-80.  Glyphs are emitted in ascending code point order (the reference
+	// iterates a HashMap, i.e. in unspecified order).
+	bool render(const std::string &font_name, const Renderer &renderer, std::vector<uint8_t> &out, std::string *err) const;
+	// Split form used by the pipeline: fill a batch, later turn the rendered batch into the PBF.
+	bool fill_batch(GlyphBatch &batch) const;
+	std::vector<uint8_t> encode_batch(const std::string &font_name, const GlyphBatch &batch) const;
+
+  private:
+	uint32_t start_index_;
+	std::array<const FontFileEntry *, GLYPH_BLOCK_SIZE> fonts_;
+	size_t len_ = 0;
+};
+
+class FontWrapper {
+  public:
+	void add_file(std::unique_ptr<FontFileEntry> file) { files_.push_back(std::move(file)); }
+	bool add_paths(const std::vector<std::string> &sources, std::string *err);
+	const std::vector<std::unique_ptr<FontFileEntry>> &files() const { return files_; }
+	// wrapper.rs:53-76 — always 256 BMP blocks, code points > 0xFFFF ignored
+	std::vector<GlyphBlock> get_blocks() const;
+
+  private:
+	std::vector<std::unique_ptr<FontFileEntry>> files_;
+};
+
+// writer/mod.rs.  kinds: directory on disk (file.rs), in-memory recorder (dummy.rs + content).
+class Writer {
+  public:
+	static Writer new_file(const std::string &folder);
+	static Writer new_memory();
+	bool write_file(const std::string &filename, const uint8_t *bytes, size_t len, std::string *err);
+	bool write_directory(const std::string &dirname, std::string *err);
+	bool finish(std::string *err);
+	struct Entry {
+		std::string name;
+		bool is_dir = false;
+		std::vector<uint8_t> bytes;
+	};
+	const std::vector<Entry> &entries() const { return entries_; } // memory writer only
+	uint64_t bytes_written() const { return bytes_written_; }
+
+  private:
+	bool to_disk_ = false;
+	std::string folder_;
+	std::vector<Entry> entries_;
+	uint64_t bytes_written_ = 0;
+	bool finished_ = false;
+};
+
+struct RenderStats {
+	uint64_t glyphs = 0, bitmaps = 0, pixels = 0, segments = 0, pairs = 0, pbf_bytes = 0, blocks = 0;
+};
+
+class FontManager {
+  public:
+	explicit FontManager(bool parallel) : parallel_(parallel) {}
+	// manager.rs:39-53: id = name_to_id(family name); see DESIGN.md for the naming subset
+	bool add_path(const std::string &path, std::string *err);
+	bool add_paths(const std::vector<std::string> &paths, std::string *err);
+	// manager.rs:66-75
+	bool add_font_with_name(const std::string &name, const std::vector<std::string> &sources, std::string *err);
+	bool add_font_bytes_with_name(const std::string &name, std::vector<uint8_t> data, std::string *err);
+	const std::map<std::string, FontWrapper> &fonts() const { return fonts_; }
+	// manager.rs:81-125.  Blocks are flattened by host workers, rendered on the renderer's CUDA
+	// streams and encoded while later blocks are in flight; writes go through one mutex.
+	// shard/n_shards: render only tasks with (task_index % n_shards == shard) — the font x block
+	// sharding used across GPUs (every shard still writes its own directories).
+	bool render_glyphs(Writer &writer, const Renderer &renderer, std::string *err, RenderStats *stats = nullptr,
+	                   uint32_t shard = 0, uint32_t n_shards = 1, int threads = 0) const;
+	// manager.rs:128-131 (font ids as a JSON array)
+	bool write_index_json(Writer &writer, std::string *err) const;
+	static std::string name_to_id(const std::string &name); // manager.rs:141-147
+
+  private:
+	std::map<std::string, FontWrapper> fonts_; // ordered: deterministic task order
+	bool parallel_;
+};
+
+} // namespace vgb
