@@ -1441,7 +1441,7 @@ int vgo_fontset_render_block(vgo_fontset *s, uint32_t block, int mode, uint8_t *
 typedef struct {
 	vgo_fontset *s;
 	int mode;
-	uint32_t lo, hi;
+	uint32_t lo, hi, stride;
 	uint32_t next;
 	pthread_mutex_t mu;
 	bvec *outs; /* per block */
@@ -1458,7 +1458,8 @@ static void *worker(void *p)
 	job_ctx *c = a->c;
 	for (;;) {
 		pthread_mutex_lock(&c->mu);
-		uint32_t b = c->next++;
+		uint32_t b = c->next;
+		c->next += c->stride;
 		pthread_mutex_unlock(&c->mu);
 		if (b >= c->hi)
 			break;
@@ -1470,6 +1471,15 @@ static void *worker(void *p)
 /* FontManager::render_glyphs — src/font/manager.rs:81-125: one task per block, worker pool */
 int vgo_fontset_render_all(vgo_fontset *s, int mode, int threads, uint32_t block_lo, uint32_t block_hi, vgo_stats *st)
 {
+	return vgo_fontset_render_strided(s, mode, threads, block_lo, block_hi, 1, st);
+}
+
+/* Same, visiting only blocks block_lo, block_lo+stride, ... (< block_hi): bounded samples for bench.py. */
+int vgo_fontset_render_strided(vgo_fontset *s, int mode, int threads, uint32_t block_lo, uint32_t block_hi, uint32_t stride,
+                               vgo_stats *st)
+{
+	if (stride < 1)
+		stride = 1;
 	if (block_hi > 256)
 		block_hi = 256;
 	if (block_lo > block_hi)
@@ -1479,7 +1489,7 @@ int vgo_fontset_render_all(vgo_fontset *s, int mode, int threads, uint32_t block
 	fontset_index(s);
 	job_ctx c;
 	memset(&c, 0, sizeof(c));
-	c.s = s, c.mode = mode, c.lo = block_lo, c.hi = block_hi, c.next = block_lo;
+	c.s = s, c.mode = mode, c.lo = block_lo, c.hi = block_hi, c.next = block_lo, c.stride = stride;
 	pthread_mutex_init(&c.mu, NULL);
 	c.outs = (bvec *)calloc(block_hi - block_lo + 1, sizeof(bvec));
 	c.per_thread = (vgo_stats *)calloc((size_t)threads, sizeof(vgo_stats));
@@ -1502,7 +1512,7 @@ int vgo_fontset_render_all(vgo_fontset *s, int mode, int threads, uint32_t block
 		st->pairs += c.per_thread[i].pairs;
 	}
 	uint64_t h = 1469598103934665603ull;
-	for (uint32_t b = block_lo; b < block_hi; b++) {
+	for (uint32_t b = block_lo; b < block_hi; b += stride) {
 		bvec *o = &c.outs[b - block_lo];
 		st->pbf_bytes += o->n;
 		for (size_t i = 0; i < o->n; i++)

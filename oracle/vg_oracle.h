@@ -102,6 +102,9 @@ typedef struct {
 /* FontManager::render_glyphs restated: all 256 blocks, `threads` workers pulling blocks
  * (rayon par_iter granularity, src/font/manager.rs:117-121). block_lo/hi restrict to a sub-range. */
 int vgo_fontset_render_all(vgo_fontset *s, int mode, int threads, uint32_t block_lo, uint32_t block_hi, vgo_stats *st);
+/* Same over blocks block_lo, block_lo+stride, ... : bounded samples of a workload for bench.py's CPU legs. */
+int vgo_fontset_render_strided(vgo_fontset *s, int mode, int threads, uint32_t block_lo, uint32_t block_hi, uint32_t stride,
+                               vgo_stats *st);
 
 const char *vgo_name_to_id(const char *name, char *buf, size_t cap);
 

@@ -85,6 +85,7 @@ def lib():
         "vgo_fontset_block_population": (None, [vp, C.POINTER(u32 * 256)]),
         "vgo_fontset_render_block": (C.c_int, [vp, u32, C.c_int, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(u64)]),
         "vgo_fontset_render_all": (C.c_int, [vp, C.c_int, C.c_int, u32, u32, C.POINTER(Stats)]),
+        "vgo_fontset_render_strided": (C.c_int, [vp, C.c_int, C.c_int, u32, u32, u32, C.POINTER(Stats)]),
         "vgo_name_to_id": (C.c_char_p, [C.c_char_p, C.c_char_p, C.c_size_t]),
     }
     for name, (res, args) in sig.items():
@@ -195,9 +196,9 @@ class FontSet:
         lib().vgo_free(p)
         return data
 
-    def render_all(self, mode=MODE_PRECISE, threads=1, block_lo=0, block_hi=256):
+    def render_all(self, mode=MODE_PRECISE, threads=1, block_lo=0, block_hi=256, stride=1):
         st = Stats()
-        lib().vgo_fontset_render_all(self._h, mode, threads, block_lo, block_hi, C.byref(st))
+        lib().vgo_fontset_render_strided(self._h, mode, threads, block_lo, block_hi, stride, C.byref(st))
         return st.as_dict()
 
 

@@ -1,0 +1,332 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar (BASELINE.json): glyph metrics and PBF structure bit-exact; SDF bitmaps within +-1 u8 per pixel
+with >= 99.9 % of pixels identical.  Floating point tolerance is therefore stated in u8 steps:
+MAX_DIFF = 1, MIN_IDENTICAL = 0.999.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import synth_font
+import versatiles_glyphs_rs_b200 as V
+
+pytestmark = pytest.mark.gpu
+
+MAX_DIFF = 1
+MIN_IDENTICAL = 0.999
+
+
+@pytest.fixture(scope="module")
+def renderer():
+    return V.Renderer.new_precise(device=0)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return V.SdfContext(device=0, n_slots=2)
+
+
+JOB_DT = np.dtype([("seg_off", "<u4"), ("seg_cnt", "<u4"), ("width", "<u4"), ("height", "<u4"), ("out_off", "<u8")])
+
+
+def compare_bitmaps(got, want, what=""):
+    d = np.abs(got.astype(np.int16).reshape(-1) - want.astype(np.int16).reshape(-1))
+    assert d.max(initial=0) <= MAX_DIFF, (what, int(d.max()))
+    return d.size, int((d == 0).sum())
+
+
+def check_pbf_block(got_bytes, want_bytes, what):
+    """PBF structure + metrics bit-exact, bitmaps within tolerance; returns (pixels, identical)."""
+    gname, grange, gg = O.decode_pbf(got_bytes)
+    wname, wrange, wg = O.decode_pbf(want_bytes)
+    assert (gname, grange) == (wname, wrange), what
+    assert len(got_bytes) == len(want_bytes), what
+    assert [g["id"] for g in gg] == [g["id"] for g in wg], what
+    px = same = 0
+    for a, b in zip(gg, wg):
+        for k in ("width", "height", "left", "top", "advance"):
+            assert a[k] == b[k], (what, a["id"], k)
+        assert (a["bitmap"] is None) == (b["bitmap"] is None)
+        if a["bitmap"] is not None:
+            assert len(a["bitmap"]) == (a["width"] + 6) * (a["height"] + 6)  # renderer.rs:164-166
+            p, s = compare_bitmaps(a["bitmap"], b["bitmap"], (what, a["id"]))
+            px += p
+            same += s
+    return px, same
+
+
+# ---- reference golden tests, now through the CUDA path ---------------------------------------------------
+def test_square_golden(ctx):
+    """reference src/render/renderer_precise.rs:91-135: axis-aligned square in a 10x10 bitmap."""
+    ring = np.array([(1, 2), (5, 2), (5, 6), (1, 6), (1, 2)], dtype=np.float64)
+    x0, y0, W, H = -2, -1, 10, 10
+    segs = np.concatenate([ring[:-1], ring[1:]], axis=1) - np.array([x0, y0, x0, y0])
+    jobs = np.array([(0, 4, W, H, 0)], dtype=JOB_DT)
+    bm = ctx.render(segs.astype(np.float32), jobs, W * H)
+    want = O.renderer_precise(x0, y0, W, H, [ring.tolist()])
+    assert np.array_equal(bm, want)
+    assert O.bitmap_as_digit_art(bm, W) == [
+        "30 38 42 43 43 43 43 42 38 30",
+        "38 48 54 55 55 55 55 54 48 38",
+        "42 54 65 68 68 68 68 65 54 42",
+        "43 55 68 80 80 80 80 68 55 43",
+        "43 55 68 80 93 93 80 68 55 43",
+        "43 55 68 80 93 93 80 68 55 43",
+        "43 55 68 80 80 80 80 68 55 43",
+        "42 54 65 68 68 68 68 65 54 42",
+        "38 48 54 55 55 55 55 54 48 38",
+        "30 38 42 43 43 43 43 42 38 30",
+    ]
+
+
+def test_render_glyph_goldens(renderer):
+    """reference src/render/renderer.rs:176-287 — metrics exact, art bands as in the reference."""
+    font, ofont = V.FontFileEntry(path=O.FIRA), O.Font(O.FIRA)
+    g = renderer.render_glyph(font, 0x20)
+    assert (g.width, g.height, g.left, g.top, g.advance, g.bitmap) == (0, 0, 0, 0, 6, None)
+    for cp, metrics in ((0x41, (14, 17, 0, -7, 13)), (0xE6, (19, 14, 0, -11, 19)), (0x60, (7, 5, 0, -4, 7))):
+        g = renderer.render_glyph(font, cp)
+        assert (g.width, g.height, g.left, g.top, g.advance) == metrics
+        assert len(g.bitmap) == (g.width + 6) * (g.height + 6)
+        want = ofont.render_glyph(cp)
+        compare_bitmaps(np.frombuffer(g.bitmap, dtype=np.uint8), want["bitmap"], hex(cp))
+    assert renderer.render_glyph(font, 0xD800) is None
+    g = renderer.render_glyph(font, 0x41)
+    art = O.bitmap_as_ascii_art(np.frombuffer(g.bitmap, dtype=np.uint8), g.width + 6)
+    want = O.bitmap_as_ascii_art(ofont.render_glyph(0x41)["bitmap"], g.width + 6)
+    assert art == want
+
+
+# ---- C1 / C2: whole fonts through FontManager::render_glyphs ---------------------------------------------
+def _render_all(name, paths, renderer, **kw):
+    m = V.FontManager(parallel=True)
+    m.add_font_with_name(name, paths)
+    w = V.Writer.new_memory()
+    st = m.render_glyphs(w, renderer, **kw)
+    return {n: d for n, is_dir, d in w.entries() if not is_dir}, st, m
+
+
+def test_c1_fira_recurse_parity(renderer):
+    files, st, _ = _render_all("Fira Sans - Regular", [O.FIRA], renderer)
+    oset = O.FontSet("Fira Sans - Regular", [O.FIRA])
+    assert (st.glyphs, st.bitmaps, st.segments, st.pixels) == (1686, 1679, 600952, 758736)
+    px = same = 0
+    for b in range(256):
+        p, s = check_pbf_block(files[f"fira_sans_regular/{b * 256}-{b * 256 + 255}.pbf"], oset.render_block(b), b)
+        px += p
+        same += s
+    assert px == 758736
+    assert same / px >= MIN_IDENTICAL, same / px
+    print(f"C1 Fira: {px} px, {px - same} differ by 1 ({100 * same / px:.4f}% identical)")
+
+
+def test_c2_noto_merge_parity(renderer):
+    paths = O.noto_paths()
+    files, st, _ = _render_all("Noto Sans Regular", paths, renderer)
+    oset = O.FontSet("Noto Sans Regular", paths)
+    assert (st.glyphs, st.bitmaps, st.segments, st.pixels) == (6480, 6445, 3956999, 3295280)
+    pop = oset.block_population()
+    px = same = 0
+    for b in range(256):
+        if pop[b] == 0:
+            assert files[f"noto_sans_regular/{b * 256}-{b * 256 + 255}.pbf"] == oset.render_block(b)
+            continue
+        p, s = check_pbf_block(files[f"noto_sans_regular/{b * 256}-{b * 256 + 255}.pbf"], oset.render_block(b), b)
+        px += p
+        same += s
+    assert px == 3295280
+    assert same / px >= MIN_IDENTICAL, same / px
+    print(f"C2 Noto merge: {px} px, {px - same} differ by 1 ({100 * same / px:.4f}% identical)")
+
+
+def test_single_thread_and_sharded_runs_are_identical(renderer):
+    """--single-thread (recurse.rs:52-53) and the multi-GPU sharding give byte-identical PBFs: the
+    kernel is deterministic (min and integer adds only)."""
+    full, _, m = _render_all("Fira Sans - Regular", [O.FIRA], renderer)
+    w = V.Writer.new_memory()
+    m.render_glyphs(w, renderer, threads=1)
+    assert {n: d for n, is_dir, d in w.entries() if not is_dir} == full
+    got = {}
+    for s in range(4):
+        w = V.Writer.new_memory()
+        m.render_glyphs(w, renderer, shard=s, n_shards=4)
+        got.update({n: d for n, is_dir, d in w.entries() if not is_dir})
+    assert got == full
+
+
+# ---- C3 / C4: synthetic fonts ---------------------------------------------------------------------------
+def _font_parity(data, renderer, name, blocks):
+    m = V.FontManager(parallel=True)
+    m.add_font_bytes_with_name(name, data)
+    fid = V.name_to_id(name)
+    path = f"/tmp/_synth_{fid}.ttf"
+    open(path, "wb").write(data)
+    oset = O.FontSet(name, [path])
+    assert m.block_population(fid).tolist() == oset.block_population()
+    px = same = 0
+    for b in blocks:
+        p, s = check_pbf_block(m.render_block(fid, b, renderer), oset.render_block(b), (name, b))
+        px += p
+        same += s
+    os.unlink(path)
+    assert px > 0
+    assert same / px >= MIN_IDENTICAL, (name, same / px)
+    return px, same
+
+
+def test_c3_dense_outlines_parity(renderer):
+    """Synthetic dense outlines (K = 8..64 strokes, up to ~10 k segments per glyph, overlapping and
+    counter-wound rings): segment staging over many chunks + winding numbers beyond 0/1."""
+    data = synth_font.dense_font(n_glyphs=96, first_cp=0x4E00)
+    px, same = _font_parity(data, renderer, "Synth Dense", [0x4E])
+    print(f"C3 dense: {px} px, {100 * same / px:.4f}% identical")
+
+
+def test_c4_full_bmp_subset_parity(renderer):
+    """Every 97th BMP code point of the C4 font: all block ranges, surrogate gap, format-4 cmap."""
+    data = synth_font.full_bmp_font(stride=97)
+    px, same = _font_parity(data, renderer, "Synth Full", list(range(0, 256, 5)) + [0xD7, 0xD8, 0xDF, 0xE0, 0xFF])
+    print(f"C4 subset: {px} px, {100 * same / px:.4f}% identical")
+
+
+# ---- edge cases through the raw C ABI ---------------------------------------------------------------------
+def test_empty_and_degenerate_batches(ctx):
+    # empty batch
+    out = ctx.render(np.zeros((0, 4), np.float32), np.zeros(0, JOB_DT), 0)
+    assert out.size == 0
+    # a glyph with zero segments renders as "infinitely far outside" = 0 everywhere
+    out = ctx.render(np.zeros((0, 4), np.float32), np.array([(0, 0, 7, 9, 0)], JOB_DT), 63)
+    assert not out.any()
+    # zero-length segment = distance to a point (segment.rs:58-61); one-segment glyph
+    segs = np.array([[5.5, 5.5, 5.5, 5.5]], np.float32)
+    out = ctx.render(segs, np.array([(0, 1, 11, 11, 0)], JOB_DT), 121).reshape(11, 11)
+    want = O.renderer_precise(0, 0, 11, 11, [[(5.5, 5.5), (5.5, 5.5)]]).reshape(11, 11)
+    assert np.abs(out.astype(int) - want.astype(int)).max() <= 1
+    assert out[5, 5] == 191  # on the point: 255 - 64
+
+
+def test_bad_arguments_are_rejected(ctx):
+    segs = np.zeros((4, 4), np.float32)
+    for job in [(0, 5, 8, 8, 0), (0, 4, 0, 8, 0), (0, 4, 8, 8, 1), (0, 4, 70000, 8, 0)]:
+        with pytest.raises(V.B200Error):
+            ctx.render(segs, np.array([job], JOB_DT), 64)
+
+
+def test_unaligned_and_sparse_output_offsets(ctx):
+    """out_off may have any alignment (vectorised stores must handle head/tail bytes)."""
+    rng = np.random.default_rng(5)
+    jobs, segs, rings, off = [], [], [], 3
+    for i in range(40):
+        W, H = int(rng.integers(7, 40)), int(rng.integers(7, 40))
+        cx, cy = W / 2 + rng.normal() * 0.3, H / 2 + rng.normal() * 0.3
+        r = min(W, H) / 2 - 3
+        n = int(rng.integers(3, 40))
+        ang = np.linspace(0, 2 * np.pi, n + 1)
+        ring = np.stack([cx + r * np.cos(ang), cy + r * np.sin(ang)], axis=1)
+        ring[-1] = ring[0]
+        s = np.concatenate([ring[:-1], ring[1:]], axis=1)
+        jobs.append((len(np.concatenate(segs)) if segs else 0, n, W, H, off))
+        segs.append(s)
+        rings.append(ring)
+        off += W * H + int(rng.integers(0, 7))
+    allsegs = np.concatenate(segs).astype(np.float32)
+    jobs = np.array(jobs, JOB_DT)
+    out = ctx.render(allsegs, jobs, off)
+    px = same = 0
+    for j, ring in zip(jobs, rings):
+        W, H = int(j["width"]), int(j["height"])
+        got = out[int(j["out_off"]) : int(j["out_off"]) + W * H]
+        ring32 = ring.astype(np.float32).astype(np.float64)  # the oracle sees what the kernel sees
+        want = O.renderer_precise(0, 0, W, H, [ring32.tolist()])
+        p, s = compare_bitmaps(got, want, (W, H))
+        px += p
+        same += s
+    assert same / px >= MIN_IDENTICAL
+    # bytes between bitmaps are never written
+    mask = np.ones(off, bool)
+    for j in jobs:
+        mask[int(j["out_off"]) : int(j["out_off"]) + int(j["width"]) * int(j["height"])] = False
+    assert not out[mask].any()
+
+
+def test_large_glyph_is_tiled_over_several_ctas(ctx):
+    """A 300x200 px glyph (one CTA covers at most 128 4x4 tiles) incl. a counter-wound hole and a
+    self-overlapping second ring: winding prefix across tile-rectangle boundaries, column strips."""
+    W, H = 300, 200
+    def circle(cx, cy, r, n, rev=False):
+        a = np.linspace(0, 2 * np.pi, n + 1)
+        if rev:
+            a = a[::-1]
+        p = np.stack([cx + r * np.cos(a), cy + r * np.sin(a)], axis=1)
+        p[-1] = p[0]
+        return p.astype(np.float32).astype(np.float64)
+    rings = [circle(150.3, 100.2, 90.0, 700), circle(150.3, 100.2, 60.0, 500, rev=True), circle(200.1, 120.4, 70.5, 300)]
+    segs = np.concatenate([np.concatenate([r[:-1], r[1:]], axis=1) for r in rings]).astype(np.float32)
+    jobs = np.array([(0, len(segs), W, H, 5)], JOB_DT)
+    tiles, n_tiles, pairs = ctx.plan_tiles(jobs, len(segs), W * H + 5)
+    assert n_tiles > 20 and pairs == W * H * len(segs)
+    out = ctx.render(segs, jobs, W * H + 5)[5:]
+    want = O.renderer_precise(0, 0, W, H, [r.tolist() for r in rings])
+    px, same = compare_bitmaps(out, want, "large")
+    assert same / px >= MIN_IDENTICAL
+    assert {0, 255} <= set(np.unique(out).tolist())
+
+
+def test_many_batches_in_flight_from_threads(renderer):
+    """submit/wait from several host threads on one context (reference: rayon workers, manager.rs:117-118)."""
+    import threading
+
+    font = V.FontFileEntry(path=O.FIRA)
+    cps = font.codepoints().tolist()
+    ref_batch = renderer.new_batch()
+    for cp in cps[:300]:
+        ref_batch.add_glyph(font, cp)
+    renderer.render_batch(ref_batch)
+    want = ref_batch.bitmaps().copy()
+    errors = []
+
+    def work():
+        try:
+            for _ in range(5):
+                b = renderer.new_batch()
+                for cp in cps[:300]:
+                    b.add_glyph(font, cp)
+                t = renderer.submit_batch(b)
+                renderer.wait_batch(t)
+                if not np.array_equal(b.bitmaps(), want):
+                    errors.append("mismatch")
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work) for _ in range(6)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+
+
+def test_device_resident_path_matches_host_path(ctx):
+    """b200sdf_render_device over torch-owned HBM buffers on a torch stream = b200sdf_render."""
+    import torch
+
+    font = V.FontFileEntry(path=O.FIRA)
+    r = V.Renderer.new_dummy()  # only used to build the batch (host side)
+    batch = r.new_batch()
+    for cp in font.codepoints().tolist()[:500]:
+        batch.add_glyph(font, cp)
+    segs, jobs = batch.segments().copy(), batch.jobs()
+    out_bytes = int(jobs["out_off"][-1] + jobs["width"][-1] * jobs["height"][-1])
+    want = ctx.render(segs, jobs, out_bytes)
+    tiles, n_tiles, pairs = ctx.plan_tiles(jobs, len(segs), out_bytes)
+    assert pairs == batch.pairs
+    dev = torch.device("cuda:0")
+    d_segs = torch.from_numpy(segs).to(dev)
+    d_tiles = torch.from_numpy(tiles).to(dev)
+    d_out = torch.zeros(out_bytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        ctx.render_device(d_segs.data_ptr(), d_tiles.data_ptr(), n_tiles, d_out.data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), want)
