@@ -227,22 +227,31 @@ def main():
     for cp in sorted(owner):
         batch.add_glyph(owner[cp], cp)
     n_glyphs = len(batch)
-    segs = batch.segments().copy()
+    segs = batch.segments().copy()  # only glyphs that cannot be flattened exactly on the device (scaled composites)
+    curves = batch.curves()
     jobs = batch.jobs()
     n_bitmaps = len(jobs)
+    n_segments = batch.total_segments
     out_bytes = int(jobs["out_off"][-1] + jobs["width"][-1].astype(np.uint64) * jobs["height"][-1]) if n_bitmaps else 0
-    tiles, n_tiles, pairs = ctx.plan_tiles(jobs, len(segs), out_bytes)
+    tiles, n_tiles, pairs = ctx.plan_outline_tiles(jobs, len(curves), len(segs), out_bytes)
 
-    d_segs = torch.from_numpy(segs).to(dev)
+    def to_dev(a):
+        return torch.from_numpy(np.frombuffer(a.tobytes() or b"\0" * 16, dtype=np.uint8).copy()).to(dev)
+
+    d_segs = to_dev(segs)
+    d_curves = to_dev(curves)
+    d_jobs = to_dev(jobs)
     d_tiles = torch.from_numpy(tiles).to(dev)
     d_out = torch.zeros(max(out_bytes, 1), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.Stream(device=dev)
 
     fp32_peak_tflops, _ = ctx.measure_fp32_peak(5)
+    fp32x2_peak_tflops, _ = ctx.measure_fp32_peak(5, packed=True)
 
     def launch():
-        ctx.render_device(d_segs.data_ptr(), d_tiles.data_ptr(), n_tiles, d_out.data_ptr(), stream.cuda_stream)
+        ctx.render_outlines_device(d_curves.data_ptr(), d_segs.data_ptr(), d_jobs.data_ptr(), d_tiles.data_ptr(), n_tiles,
+                                   d_out.data_ptr(), stream.cuda_stream)
 
     # ---- value: device-resident kernel time ----
     sampler = ClockSampler(local_rank)
@@ -276,7 +285,8 @@ def main():
     value = world * n_bitmaps / (ms_per_step * 1e-3)
     kernel_s = statistics.mean(kernel_ms) * 1e-3
     achieved_tflops = FLOP_PER_PAIR * pairs / kernel_s / 1e12
-    alg_bytes = len(segs) * 16 + n_tiles * 32 + out_bytes
+    in_bytes = len(segs) * 16 + len(curves) * 32 + len(jobs) * 56 + n_tiles * 32
+    alg_bytes = in_bytes + out_bytes
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -288,7 +298,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "testdata fonts" if args.workload in ("noto", "fira") else "synthetic",
         "config": {
-            "workload": label, "glyphs": n_glyphs, "bitmaps": n_bitmaps, "segments": int(len(segs)), "pixels": out_bytes,
+            "workload": label, "glyphs": n_glyphs, "bitmaps": n_bitmaps, "segments": int(n_segments), "curve_records": int(len(curves)), "host_flattened_segments": int(len(segs)), "pixels": out_bytes,
             "pairs": int(pairs), "ctas": int(n_tiles), "l2": "flushed between timed launches (256 MiB memset)",
             "value_counts": "glyphs with a bitmap; per rank the same workload (font x block shards are independent)",
             "bitmap_checksum": checksum,
@@ -298,6 +308,7 @@ def main():
             "frac": achieved_tflops / fp32_peak_tflops, "traffic": None,
             "peak_source": "FFMA-chain microbenchmark in this run (b200sdf_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
             "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": int(pairs), "kernel_ms": kernel_s * 1e3,
+            "peak_ffma2_tflops": fp32x2_peak_tflops,
             "pairs_per_s": pairs / kernel_s,
             "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / kernel_s / 1e9,
                     "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json (measured copy)"},
@@ -318,7 +329,7 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         result["e2e"] = {
             "value": world * st.glyphs * e2e_steps / e2e_s, "unit": "glyphs/s",
-            "h2d_bytes_per_step": int(st.segments * 16 + n_tiles * 32), "d2h_bytes_per_step": int(st.pixels),
+            "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(st.pixels),
             "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "pbf_bytes_per_step": int(st.pbf_bytes),
             "api": "FontManager.render_glyphs(Writer.new_memory(), Renderer.new_precise()): flatten -> H2D -> kernel -> D2H -> PBF",
         }

@@ -66,22 +66,65 @@ typedef struct {
 } b200sdf_glyph_job;
 
 /*
+ * Outline-level input (the seam one step earlier: the RingBuilder callbacks of
+ * src/render/ring_builder.rs:67-117 BEFORE flattening).  One record = one line or one quadratic
+ * Bezier of a closed ring, control points in FONT UNITS exactly as the outline callbacks deliver
+ * them (f32).  The device flattens it the way Ring::add_quadratic_bezier does
+ * (src/geometry/ring.rs:119-144): `depth` = k means 2^k segments at t = j/2^k, evaluated in f64.
+ * For inputs whose coordinates are small dyadic rationals (every TrueType outline without scaled
+ * components) the reference's midpoint recursion is exact in f64 and has uniform depth, so the
+ * device points equal the reference's points bit for bit; the host decides k with the reference's
+ * own flatness test and falls back to uploading explicit segments otherwise.
+ */
+typedef struct {
+	float sx, sy, cx, cy, ex, ey; /* start, control, end; for a line cx,cy = sx,sy and depth = 0 */
+	uint32_t seg_off;             /* index of this record's first segment within its glyph */
+	uint32_t depth;               /* k */
+} b200sdf_curve;
+
+enum { B200SDF_KIND_CURVES = 0, B200SDF_KIND_SEGMENTS = 1 };
+
+/*
+ * One glyph of a mixed batch.  kind = CURVES: src_off/src_cnt index the curve array, the device
+ * applies rings.scale(scale); rings.translate((dx, 0)) (src/render/renderer.rs:122-131) in f64 and
+ * subtracts the integer origin (x0, y0) before narrowing to f32.  kind = SEGMENTS: src_off/src_cnt
+ * index the segment array (already origin-relative pixel units; scale/dx/x0/y0 unused) and
+ * seg_cnt = src_cnt.
+ */
+typedef struct {
+	uint32_t kind;
+	uint32_t src_off, src_cnt;
+	uint32_t seg_cnt; /* total flattened segments of the glyph */
+	uint32_t width, height;
+	int32_t x0, y0;
+	double scale, dx;
+	uint64_t out_off;
+} b200sdf_outline_job;
+
+/*
  * Device-side work item: a rectangle of pixel tiles of one glyph, rendered by one CTA
  * ("each CTA owns one glyph, or a pixel tile of a large glyph").  Produced by b200sdf_plan_tiles.
  */
 typedef struct {
-	uint32_t seg_off;
-	uint32_t seg_cnt;
+	uint32_t seg_off;       /* first segment (segment array), or first curve record when `job` is set */
+	uint32_t seg_cnt;       /* flattened segments of the glyph */
 	uint64_t out_off;
 	uint16_t width, height; /* whole-glyph bitmap size */
 	uint16_t tx0, ty0;      /* first tile column / row (tiles are B200SDF_TILE_W x B200SDF_TILE_H pixels, y upward) */
 	uint16_t ntx, nty;      /* tile columns / rows in this rectangle; ntx*nty <= B200SDF_MAX_ITEMS */
-	uint32_t reserved;
+	uint32_t job;           /* B200SDF_NO_JOB = raw segments; else index of the b200sdf_outline_job (curves) */
 } b200sdf_tile_job;
+#define B200SDF_NO_JOB 0xFFFFFFFFu
 
+#ifndef B200SDF_TILE_W
 #define B200SDF_TILE_W 4
+#endif
+#ifndef B200SDF_TILE_H
 #define B200SDF_TILE_H 4
-#define B200SDF_MAX_ITEMS 128
+#endif
+#ifndef B200SDF_MAX_ITEMS
+#define B200SDF_MAX_ITEMS 64
+#endif
 #define B200SDF_MAX_DIM 16384 /* largest accepted glyph width/height in pixels */
 
 /* ---- context --------------------------------------------------------------------------------- */
@@ -110,6 +153,18 @@ int b200sdf_wait(b200sdf_ctx *ctx, uint64_t ticket);
 int b200sdf_render(b200sdf_ctx *ctx, const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_glyph_job *jobs,
                    uint32_t n_jobs, uint8_t *out, uint64_t out_bytes);
 
+/* ---- outline-level path: flattening happens on the device ------------------------------------- */
+/* Like b200sdf_submit, but glyphs are given as curve records (kind CURVES) and/or explicit
+ * segments (kind SEGMENTS).  H2D shrinks from 16 B per flattened segment to 32 B per curve. */
+int b200sdf_submit_outlines(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint32_t n_curves,
+                            const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_outline_job *jobs,
+                            uint32_t n_jobs, uint8_t *out, uint64_t out_bytes, uint64_t *ticket);
+/* Device flattening only: writes the f32 origin-relative segments of every CURVES glyph, glyph
+ * after glyph in job order, into out_segs (host buffer, n_out = sum of seg_cnt).  Blocking. */
+int b200sdf_flatten_outlines(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint32_t n_curves,
+                             const b200sdf_outline_job *jobs, uint32_t n_jobs, b200sdf_segment *out_segs,
+                             uint64_t n_out);
+
 /* ---- device-resident path (segments and bitmaps stay in HBM) ----------------------------------- */
 /* Split glyph jobs into CTA work items, largest first.  tiles may be NULL to query the count.
  * pairs (optional) receives sum(width*height*seg_cnt), the algorithmic pixel x segment pairs. */
@@ -119,10 +174,18 @@ int b200sdf_plan_tiles(const b200sdf_glyph_job *jobs, uint32_t n_jobs, uint32_t 
  * pointers.  Asynchronous; exactly one kernel launch. */
 int b200sdf_render_device(b200sdf_ctx *ctx, const b200sdf_segment *d_segs, const b200sdf_tile_job *d_tiles,
                           uint32_t n_tiles, uint8_t *d_out, void *stream);
+/* Same for a mixed batch: tiles from b200sdf_plan_outline_tiles, d_jobs = the outline jobs in HBM. */
+int b200sdf_plan_outline_tiles(const b200sdf_outline_job *jobs, uint32_t n_jobs, uint32_t n_curves, uint32_t n_seg,
+                               uint64_t out_bytes, b200sdf_tile_job *tiles, uint32_t cap, uint32_t *n_tiles,
+                               uint64_t *pairs);
+int b200sdf_render_outlines_device(b200sdf_ctx *ctx, const b200sdf_curve *d_curves, const b200sdf_segment *d_segs,
+                                   const b200sdf_outline_job *d_jobs, const b200sdf_tile_job *d_tiles,
+                                   uint32_t n_tiles, uint8_t *d_out, void *stream);
 
 /* ---- measurement helpers ----------------------------------------------------------------------- */
 /* Dependent-FFMA-chain microbenchmark: measured FP32 (non-tensor) peak of this device in TFLOP/s
- * (2 flop per FFMA), best of `reps`.  Roofline denominator for the SDF kernel. */
+ * (2 flop per FFMA), best of |reps|.  Roofline denominator for the SDF kernel.  reps < 0 runs the
+ * packed FFMA2 variant (two FMAs per lane per instruction) instead. */
 int b200sdf_measure_fp32_peak(b200sdf_ctx *ctx, int reps, double *tflops, double *ms);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 uint64_t b200sdf_launch_count(const b200sdf_ctx *ctx);

@@ -68,6 +68,9 @@ const char *vgb_name_to_id(const char *name, char *buf, size_t cap);        /* m
 vgb_renderer *vgb_renderer_new(int dummy, int device, uint32_t n_slots);
 void vgb_renderer_free(vgb_renderer *r);
 int vgb_renderer_is_dummy(const vgb_renderer *r);
+/* Where new batches flatten Bezier curves: 1 = on the device from curve records (default), 0 = on the
+ * host (upload b200sdf_segment: the literal renderer_precise seam, src/render/renderer_precise.rs:8) */
+void vgb_renderer_set_flatten(vgb_renderer *r, int on_device);
 b200sdf_ctx *vgb_renderer_context(const vgb_renderer *r); /* NULL for the dummy renderer */
 /* Renderer::render_glyph (renderer.rs:103-149): 1 = Some(glyph), 0 = None, <0 = error */
 int vgb_renderer_render_glyph(const vgb_renderer *r, const vgb_font *f, uint32_t codepoint, vgb_glyph *out);
@@ -80,7 +83,9 @@ typedef struct {
 	uint32_t bm_width, bm_height; /* RenderResult.width/.height (buffer included) */
 	uint32_t width, height;  /* PbfGlyph fields */
 	int32_t left, top;
-	uint32_t seg_off, seg_cnt;
+	uint32_t kind;            /* B200SDF_KIND_CURVES / B200SDF_KIND_SEGMENTS */
+	uint32_t src_off, src_cnt; /* range in the batch's curve or segment array */
+	uint32_t seg_cnt;          /* flattened segments */
 	uint64_t out_off;
 } vgb_batch_glyph;
 
@@ -94,7 +99,10 @@ int vgb_batch_add_rings(vgb_batch *b, uint32_t id, int32_t x0, int32_t y0, uint3
 uint32_t vgb_batch_glyph_count(const vgb_batch *b);
 int vgb_batch_glyph_info(const vgb_batch *b, uint32_t i, vgb_batch_glyph *out);
 const b200sdf_segment *vgb_batch_segments(const vgb_batch *b, uint32_t *n_seg);
-const b200sdf_glyph_job *vgb_batch_jobs(const vgb_batch *b, uint32_t *n_jobs);
+const b200sdf_outline_job *vgb_batch_jobs(const vgb_batch *b, uint32_t *n_jobs);
+const b200sdf_curve *vgb_batch_curves(const vgb_batch *b, uint32_t *n_curves);
+uint64_t vgb_batch_total_segments(const vgb_batch *b);   /* flattened segments of all glyphs, either source */
+uint32_t vgb_batch_fallback_glyphs(const vgb_batch *b);  /* device-flatten glyphs that had to be flattened on the host */
 const uint8_t *vgb_batch_bitmaps(const vgb_batch *b, uint64_t *bytes);
 uint64_t vgb_batch_pairs(const vgb_batch *b);
 int vgb_renderer_render_batch(const vgb_renderer *r, vgb_batch *b);

@@ -313,10 +313,11 @@ def test_device_resident_path_matches_host_path(ctx):
 
     font = V.FontFileEntry(path=O.FIRA)
     r = V.Renderer.new_dummy()  # only used to build the batch (host side)
+    r.set_flatten(on_device=False)
     batch = r.new_batch()
     for cp in font.codepoints().tolist()[:500]:
         batch.add_glyph(font, cp)
-    segs, jobs = batch.segments().copy(), batch.jobs()
+    segs, jobs = batch.segments().copy(), batch.glyph_jobs()
     out_bytes = int(jobs["out_off"][-1] + jobs["width"][-1] * jobs["height"][-1])
     want = ctx.render(segs, jobs, out_bytes)
     tiles, n_tiles, pairs = ctx.plan_tiles(jobs, len(segs), out_bytes)
@@ -330,3 +331,70 @@ def test_device_resident_path_matches_host_path(ctx):
         ctx.render_device(d_segs.data_ptr(), d_tiles.data_ptr(), n_tiles, d_out.data_ptr(), stream.cuda_stream)
     stream.synchronize()
     assert np.array_equal(d_out.cpu().numpy(), want)
+
+
+# ---- outline-level path: flattening on the device ---------------------------------------------------------
+def _both_batches(font, cps):
+    r = V.Renderer.new_dummy()  # host side only: builds the batches
+    dev_batch = r.new_batch()
+    r.set_flatten(on_device=False)
+    host_batch = r.new_batch()
+    for cp in cps:
+        assert dev_batch.add_glyph(font, cp) == host_batch.add_glyph(font, cp)
+    return dev_batch, host_batch
+
+
+@pytest.mark.parametrize("path", [O.FIRA] + O.noto_paths())
+def test_device_flattening_is_bit_identical_to_host_flattening(ctx, path):
+    """The device regenerates Ring::add_quadratic_bezier's points (ring.rs:119-144) from curve records:
+    every f32 segment equals the host's literal flattening bit for bit, for every glyph of every fixture."""
+    font = V.FontFileEntry(path=path)
+    cps = [cp for cp in font.codepoints().tolist() if cp <= 0xFFFF]
+    dev_batch, host_batch = _both_batches(font, cps)
+    jobs = dev_batch.jobs()
+    curve_jobs = jobs[jobs["kind"] == 0]
+    got = ctx.flatten_outlines(dev_batch.curves(), curve_jobs)
+    hsegs = host_batch.segments()
+    hjobs = host_batch.jobs()
+    assert len(jobs) == len(hjobs)
+    pos = 0
+    for dj, hj in zip(jobs, hjobs):
+        assert (dj["width"], dj["height"], dj["x0"], dj["y0"], dj["seg_cnt"], dj["out_off"]) == (
+            hj["width"], hj["height"], hj["x0"], hj["y0"], hj["seg_cnt"], hj["out_off"])
+        if dj["kind"] != 0:
+            continue
+        n = int(dj["seg_cnt"])
+        want = hsegs[int(hj["src_off"]) : int(hj["src_off"]) + n]
+        assert np.array_equal(got[pos : pos + n], want), (path, int(dj["src_off"]))
+        pos += n
+    assert pos == len(got)
+
+
+def test_outline_path_bitmaps_equal_segment_path_bitmaps(ctx):
+    """Same segments in, same bytes out: b200sdf_submit_outlines == b200sdf_submit, byte for byte."""
+    font = V.FontFileEntry(path=os.path.join(O.NOTO_DIR, "Noto Sans - Regular.ttf"))
+    cps = [cp for cp in font.codepoints().tolist() if cp <= 0xFFFF][:1500]
+    dev_batch, host_batch = _both_batches(font, cps)
+    jobs = dev_batch.jobs()
+    out_bytes = int(jobs["out_off"][-1] + jobs["width"][-1].astype(np.uint64) * jobs["height"][-1])
+    a = ctx.render_outlines(dev_batch.curves(), dev_batch.segments(), jobs, out_bytes)
+    b = ctx.render(host_batch.segments(), host_batch.glyph_jobs(), out_bytes)
+    assert np.array_equal(a, b)
+    assert (jobs["kind"] == 0).sum() > 1400
+
+
+def test_outline_jobs_are_validated(ctx):
+    curves = np.zeros(2, dtype=V.api.CURVE_DT)
+    curves["depth"] = [1, 2]
+    curves["seg_off"] = [0, 2]
+    good = np.zeros(1, dtype=V.api.OUTLINE_JOB_DT)
+    good[0] = (0, 0, 2, 6, 8, 8, 0, 0, 1.0, 0.0, 0)
+    ctx.render_outlines(curves, np.zeros((0, 4), np.float32), good, 64)
+    for field, value in (("seg_cnt", 5), ("src_cnt", 3), ("kind", 7), ("width", 0)):
+        bad = good.copy()
+        bad[field] = value
+        with pytest.raises(V.B200Error):
+            ctx.render_outlines(curves, np.zeros((0, 4), np.float32), bad, 64)
+    curves["seg_off"] = [0, 3]
+    with pytest.raises(V.B200Error):
+        ctx.render_outlines(curves, np.zeros((0, 4), np.float32), good, 64)

@@ -117,9 +117,10 @@ def test_name_to_id():
 
 
 def test_frames_and_segments_match_oracle_fira(fira):
-    """Glyph frames bit-exact; the f32 segment buffer is the oracle's f64 segments, origin-relative."""
+    """Host flattening: glyph frames bit-exact; the f32 segment buffer is the oracle's f64 segments, origin-relative."""
     f, o = fira
     r = V.Renderer(dummy=True)
+    r.set_flatten(on_device=False)
     batch = r.new_batch()
     cps = f.codepoints().tolist()
     for cp in cps:
@@ -137,13 +138,45 @@ def test_frames_and_segments_match_oracle_fira(fira):
             continue
         n_bitmaps += 1
         assert (g.x0, g.y0, g.bm_width, g.bm_height) == (x0, y0, W, H), cp
-        assert g.seg_cnt == len(osegs)
+        assert g.kind == N.KIND_SEGMENTS and g.seg_cnt == g.src_cnt == len(osegs)
         want = (osegs - np.array([x0, y0, x0, y0], dtype=np.float64)).astype(np.float32)
-        assert np.array_equal(segs[g.seg_off : g.seg_off + g.seg_cnt], want), cp
+        assert np.array_equal(segs[g.src_off : g.src_off + g.seg_cnt], want), cp
     assert n_bitmaps == 1679
     assert batch.pairs == sum(
         int(batch.glyph_info(i).bm_width) * batch.glyph_info(i).bm_height * batch.glyph_info(i).seg_cnt for i in range(len(cps))
     )
+    assert len(batch.glyph_jobs()) == n_bitmaps and len(batch.curves()) == 0
+
+
+@pytest.mark.parametrize("path", [O.FIRA] + O.noto_paths())
+def test_outline_records_give_exact_frames_and_counts(path):
+    """Device-flatten mode: the frame comes from the analytic bounding box of the curve records and the
+    segment count from the root flatness test — both must equal the literal flattening for EVERY glyph."""
+    f, o = V.FontFileEntry(path=path), O.Font(path)
+    r = V.Renderer(dummy=True)
+    batch = r.new_batch()  # default: flatten on the device
+    cps = [cp for cp in f.codepoints().tolist() if cp <= 0xFFFF]
+    for cp in cps:
+        assert batch.add_glyph(f, cp)
+    curves = batch.curves()
+    n_curve_glyphs = 0
+    for i, cp in enumerate(cps):
+        g = batch.glyph_info(i)
+        want = o.render_glyph(cp, O.MODE_DUMMY)
+        assert (g.id, g.advance) == (cp, want["advance"])
+        if want["bitmap"] is None:
+            assert not g.has_bitmap
+            continue
+        assert (g.width, g.height, g.left, g.top) == (want["width"], want["height"], want["left"], want["top"]), hex(cp)
+        assert g.seg_cnt == want["n_segments"], hex(cp)
+        if g.kind == N.KIND_CURVES:
+            n_curve_glyphs += 1
+            rec = curves[g.src_off : g.src_off + g.src_cnt]
+            assert rec["seg_off"][0] == 0 and np.array_equal(np.cumsum(1 << rec["depth"])[:-1], rec["seg_off"][1:])
+            assert int((1 << rec["depth"].astype(np.int64)).sum()) == g.seg_cnt
+    # only glyphs with scaled composite components cannot be represented exactly (SURVEY.md Appendix C: 6 in all fixtures)
+    assert batch.fallback_glyphs <= 6
+    assert n_curve_glyphs > 0
 
 
 def test_render_glyph_metrics_goldens_dummy(fira):

@@ -61,8 +61,31 @@ class TileJob(C.Structure):
         ("ty0", C.c_uint16),
         ("ntx", C.c_uint16),
         ("nty", C.c_uint16),
-        ("reserved", C.c_uint32),
+        ("job", C.c_uint32),
     ]
+
+
+class Curve(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("sx", "sy", "cx", "cy", "ex", "ey")] + [("seg_off", C.c_uint32), ("depth", C.c_uint32)]
+
+
+class OutlineJob(C.Structure):
+    _fields_ = [
+        ("kind", C.c_uint32),
+        ("src_off", C.c_uint32),
+        ("src_cnt", C.c_uint32),
+        ("seg_cnt", C.c_uint32),
+        ("width", C.c_uint32),
+        ("height", C.c_uint32),
+        ("x0", C.c_int32),
+        ("y0", C.c_int32),
+        ("scale", C.c_double),
+        ("dx", C.c_double),
+        ("out_off", C.c_uint64),
+    ]
+
+
+KIND_CURVES, KIND_SEGMENTS = 0, 1
 
 
 class Glyph(C.Structure):
@@ -93,7 +116,9 @@ class BatchGlyph(C.Structure):
         ("height", C.c_uint32),
         ("left", C.c_int32),
         ("top", C.c_int32),
-        ("seg_off", C.c_uint32),
+        ("kind", C.c_uint32),
+        ("src_off", C.c_uint32),
+        ("src_cnt", C.c_uint32),
         ("seg_cnt", C.c_uint32),
         ("out_off", C.c_uint64),
     ]
@@ -118,6 +143,10 @@ SDF_SYMBOLS = {
     "b200sdf_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
     "b200sdf_plan_tiles": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, u32p, u64p]),
     "b200sdf_render_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "b200sdf_submit_outlines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, u64p]),
+    "b200sdf_flatten_outlines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "b200sdf_plan_outline_tiles": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, u32p, u64p]),
+    "b200sdf_render_outlines_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "b200sdf_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, f64p, f64p]),
     "b200sdf_launch_count": (C.c_uint64, [C.c_void_p]),
 }
@@ -151,7 +180,11 @@ HOST_SYMBOLS = {
     "vgb_batch_glyph_count": (C.c_uint32, [C.c_void_p]),
     "vgb_batch_glyph_info": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(BatchGlyph)]),
     "vgb_batch_segments": (C.POINTER(Segment), [C.c_void_p, u32p]),
-    "vgb_batch_jobs": (C.POINTER(GlyphJob), [C.c_void_p, u32p]),
+    "vgb_batch_jobs": (C.POINTER(OutlineJob), [C.c_void_p, u32p]),
+    "vgb_batch_curves": (C.POINTER(Curve), [C.c_void_p, u32p]),
+    "vgb_batch_total_segments": (C.c_uint64, [C.c_void_p]),
+    "vgb_batch_fallback_glyphs": (C.c_uint32, [C.c_void_p]),
+    "vgb_renderer_set_flatten": (None, [C.c_void_p, C.c_int]),
     "vgb_batch_bitmaps": (u8p, [C.c_void_p, u64p]),
     "vgb_batch_pairs": (C.c_uint64, [C.c_void_p]),
     "vgb_renderer_render_batch": (C.c_int, [C.c_void_p, C.c_void_p]),

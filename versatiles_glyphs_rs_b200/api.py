@@ -16,6 +16,17 @@ BUFFER = 3  # reference src/render/mod.rs:58
 GLYPH_BLOCK_SIZE = 256  # reference src/font/glyph_block.rs:7
 
 
+GLYPH_JOB_DT = np.dtype([("seg_off", "<u4"), ("seg_cnt", "<u4"), ("width", "<u4"), ("height", "<u4"), ("out_off", "<u8")])
+OUTLINE_JOB_DT = np.dtype(
+    [("kind", "<u4"), ("src_off", "<u4"), ("src_cnt", "<u4"), ("seg_cnt", "<u4"), ("width", "<u4"), ("height", "<u4"),
+     ("x0", "<i4"), ("y0", "<i4"), ("scale", "<f8"), ("dx", "<f8"), ("out_off", "<u8")]
+)
+CURVE_DT = np.dtype(
+    [("sx", "<f4"), ("sy", "<f4"), ("cx", "<f4"), ("cy", "<f4"), ("ex", "<f4"), ("ey", "<f4"), ("seg_off", "<u4"), ("depth", "<u4")]
+)
+assert OUTLINE_JOB_DT.itemsize == C.sizeof(N.OutlineJob) and CURVE_DT.itemsize == C.sizeof(N.Curve)
+
+
 class B200Error(RuntimeError):
     pass
 
@@ -119,6 +130,11 @@ class Renderer:
         """b200sdf_ctx* of the CUDA renderer (None for dummy)."""
         return N.host.vgb_renderer_context(self._h)
 
+    def set_flatten(self, on_device: bool):
+        """Where batches created from now on flatten curves: on the device from curve records
+        (default) or on the host (upload flattened segments — the literal renderer_precise seam)."""
+        N.host.vgb_renderer_set_flatten(self._h, 1 if on_device else 0)
+
     def render_glyph(self, font: FontFileEntry, index: int) -> Optional[PbfGlyph]:
         """reference src/render/renderer.rs:103-149"""
         g = N.Glyph()
@@ -193,15 +209,37 @@ class GlyphBatch:
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n.value, 4))
 
     def jobs(self) -> np.ndarray:
+        """b200sdf_outline_job records (one per bitmap)."""
         n = C.c_uint32()
         p = N.host.vgb_batch_jobs(self._h, C.byref(n))
-        dt = np.dtype(
-            [("seg_off", "<u4"), ("seg_cnt", "<u4"), ("width", "<u4"), ("height", "<u4"), ("out_off", "<u8")]
-        )
         if n.value == 0:
-            return np.zeros(0, dtype=dt)
-        buf = C.string_at(p, n.value * C.sizeof(N.GlyphJob))
-        return np.frombuffer(buf, dtype=dt).copy()
+            return np.zeros(0, dtype=OUTLINE_JOB_DT)
+        buf = C.string_at(p, n.value * C.sizeof(N.OutlineJob))
+        return np.frombuffer(buf, dtype=OUTLINE_JOB_DT).copy()
+
+    def glyph_jobs(self) -> np.ndarray:
+        """The same jobs as b200sdf_glyph_job records (only valid when every glyph is a SEGMENTS glyph)."""
+        j = self.jobs()
+        assert (j["kind"] == N.KIND_SEGMENTS).all()
+        out = np.zeros(len(j), dtype=GLYPH_JOB_DT)
+        out["seg_off"], out["seg_cnt"] = j["src_off"], j["seg_cnt"]
+        out["width"], out["height"], out["out_off"] = j["width"], j["height"], j["out_off"]
+        return out
+
+    def curves(self) -> np.ndarray:
+        n = C.c_uint32()
+        p = N.host.vgb_batch_curves(self._h, C.byref(n))
+        if n.value == 0:
+            return np.zeros(0, dtype=CURVE_DT)
+        return np.frombuffer(C.string_at(p, n.value * C.sizeof(N.Curve)), dtype=CURVE_DT).copy()
+
+    @property
+    def total_segments(self) -> int:
+        return N.host.vgb_batch_total_segments(self._h)
+
+    @property
+    def fallback_glyphs(self) -> int:
+        return N.host.vgb_batch_fallback_glyphs(self._h)
 
     def bitmaps(self) -> np.ndarray:
         n = C.c_uint64()
@@ -388,10 +426,57 @@ class SdfContext:
         if rc != 0:
             raise B200Error(f"b200sdf_render_device: {rc}: {self.last_error()}")
 
-    def measure_fp32_peak(self, reps: int = 5):
+    # ---- outline-level path (device flattening) ----
+    def render_outlines(self, curves: np.ndarray, segs: np.ndarray, jobs: np.ndarray, out_bytes: int) -> np.ndarray:
+        """b200sdf_submit_outlines + b200sdf_wait over host buffers."""
+        curves = np.ascontiguousarray(curves, dtype=CURVE_DT)
+        segs = np.ascontiguousarray(segs, dtype=np.float32).reshape(-1, 4)
+        jobs = np.ascontiguousarray(jobs, dtype=OUTLINE_JOB_DT)
+        out = np.zeros(max(out_bytes, 1), dtype=np.uint8)
+        t = C.c_uint64()
+        rc = N.sdf.b200sdf_submit_outlines(self._h, curves.ctypes.data, len(curves), segs.ctypes.data, len(segs),
+                                           jobs.ctypes.data, len(jobs), out.ctypes.data, out_bytes, C.byref(t))
+        if rc == 0:
+            rc = N.sdf.b200sdf_wait(self._h, t.value)
+        if rc != 0:
+            raise B200Error(f"b200sdf_submit_outlines: {rc}: {self.last_error()}")
+        return out[:out_bytes]
+
+    def flatten_outlines(self, curves: np.ndarray, jobs: np.ndarray) -> np.ndarray:
+        """Device flattening only: float32 [sum seg_cnt, 4] origin-relative segments, glyph after glyph."""
+        curves = np.ascontiguousarray(curves, dtype=CURVE_DT)
+        jobs = np.ascontiguousarray(jobs, dtype=OUTLINE_JOB_DT)
+        n = int(jobs["seg_cnt"].sum())
+        out = np.zeros((max(n, 1), 4), dtype=np.float32)
+        rc = N.sdf.b200sdf_flatten_outlines(self._h, curves.ctypes.data, len(curves), jobs.ctypes.data, len(jobs), out.ctypes.data, n)
+        if rc != 0:
+            raise B200Error(f"b200sdf_flatten_outlines: {rc}: {self.last_error()}")
+        return out[:n]
+
+    def plan_outline_tiles(self, jobs: np.ndarray, n_curves: int, n_seg: int, out_bytes: int):
+        jobs = np.ascontiguousarray(jobs, dtype=OUTLINE_JOB_DT)
+        n = C.c_uint32()
+        pairs = C.c_uint64()
+        args = (jobs.ctypes.data, len(jobs), n_curves, n_seg, out_bytes)
+        rc = N.sdf.b200sdf_plan_outline_tiles(*args, None, 0, C.byref(n), C.byref(pairs))
+        if rc != 0:
+            raise B200Error(f"b200sdf_plan_outline_tiles: {rc}")
+        tiles = np.zeros(n.value * C.sizeof(N.TileJob), dtype=np.uint8)
+        rc = N.sdf.b200sdf_plan_outline_tiles(*args, tiles.ctypes.data, n.value, C.byref(n), C.byref(pairs))
+        if rc != 0:
+            raise B200Error(f"b200sdf_plan_outline_tiles: {rc}")
+        return tiles, n.value, pairs.value
+
+    def render_outlines_device(self, d_curves: int, d_segs: int, d_jobs: int, d_tiles: int, n_tiles: int, d_out: int, stream: int = 0):
+        rc = N.sdf.b200sdf_render_outlines_device(self._h, d_curves, d_segs, d_jobs, d_tiles, n_tiles, d_out, stream)
+        if rc != 0:
+            raise B200Error(f"b200sdf_render_outlines_device: {rc}: {self.last_error()}")
+
+    def measure_fp32_peak(self, reps: int = 5, packed: bool = False):
+        """FFMA-chain microbenchmark -> (TFLOP/s, ms); packed=True uses FFMA2 (two FMAs per instruction)."""
         t = C.c_double()
         ms = C.c_double()
-        rc = N.sdf.b200sdf_measure_fp32_peak(self._h, reps, C.byref(t), C.byref(ms))
+        rc = N.sdf.b200sdf_measure_fp32_peak(self._h, -reps if packed else reps, C.byref(t), C.byref(ms))
         if rc != 0:
             raise B200Error(f"b200sdf_measure_fp32_peak: {rc}: {self.last_error()}")
         return t.value, ms.value

@@ -2,8 +2,8 @@
 //
 // Context = one GPU + a pool of slots; a slot = one CUDA stream + device buffers + pinned staging
 // for the tile-job list + one completion event.  submit() plans tiles on the host, then enqueues
-// H2D(segments) -> H2D(tiles) -> kernel -> D2H(bitmaps) on the slot's stream and returns.
-// This is the async batch pipeline that replaces the serial per-block loop of
+// H2D(curves / segments / jobs) -> H2D(tiles) -> kernel -> D2H(bitmaps) on the slot's stream and
+// returns.  This is the async batch pipeline that replaces the serial per-block loop of
 // FontManager::render_glyphs (reference src/font/manager.rs:104-121).
 #include <algorithm>
 #include <condition_variable>
@@ -18,16 +18,16 @@
 
 namespace {
 
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
 struct Slot {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t done = nullptr;
-	void *d_segs = nullptr;
-	size_t segs_cap = 0;
-	void *d_tiles = nullptr;
-	size_t tiles_cap = 0;
-	void *d_out = nullptr;
-	size_t out_cap = 0;
-	b200sdf_tile_job *h_tiles = nullptr; // pinned
+	DevBuf segs, curves, ojobs, tiles, out, seg_base;
+	void *h_tiles = nullptr; // pinned staging: tile jobs
 	size_t h_tiles_cap = 0;
 	bool busy = false;
 	uint64_t generation = 0;
@@ -62,62 +62,63 @@ int fail_arg(b200sdf_ctx *ctx, const char *what)
 	return B200SDF_E_ARG;
 }
 
-#define CU_TRY(ctx, call)                                  \
-	do {                                                   \
-		cudaError_t e_ = (call);                           \
-		if (e_ != cudaSuccess)                             \
-			return fail_cuda((ctx), e_, #call);            \
+#define CU_TRY(ctx, call)                       \
+	do {                                        \
+		cudaError_t e_ = (call);                \
+		if (e_ != cudaSuccess)                  \
+			return fail_cuda((ctx), e_, #call); \
 	} while (0)
 
-template <typename F> int grow(b200sdf_ctx *ctx, void **p, size_t *cap, size_t need, F alloc_free)
+size_t grown(size_t need, size_t cap)
 {
-	if (need <= *cap)
-		return 0;
-	size_t n = std::max(need, *cap + *cap / 2);
-	n = (n + 255) & ~size_t(255);
-	return alloc_free(ctx, p, cap, n);
+	size_t n = std::max(need, cap + cap / 2);
+	return (n + 255) & ~size_t(255);
 }
 
-int grow_device(b200sdf_ctx *ctx, void **p, size_t *cap, size_t need)
+int grow_device(b200sdf_ctx *ctx, DevBuf &b, size_t need)
 {
-	return grow(ctx, p, cap, need, [](b200sdf_ctx *c, void **pp, size_t *cc, size_t n) -> int {
-		if (*pp)
-			cudaFree(*pp);
-		*pp = nullptr;
-		*cc = 0;
-		cudaError_t e = cudaMalloc(pp, n);
-		if (e != cudaSuccess)
-			return fail_cuda(c, e, "cudaMalloc");
-		*cc = n;
+	if (need <= b.cap)
 		return 0;
-	});
+	const size_t n = grown(need, b.cap);
+	if (b.p)
+		cudaFree(b.p);
+	b.p = nullptr;
+	b.cap = 0;
+	cudaError_t e = cudaMalloc(&b.p, n);
+	if (e != cudaSuccess)
+		return fail_cuda(ctx, e, "cudaMalloc");
+	b.cap = n;
+	return 0;
 }
 
 int grow_pinned(b200sdf_ctx *ctx, void **p, size_t *cap, size_t need)
 {
-	return grow(ctx, p, cap, need, [](b200sdf_ctx *c, void **pp, size_t *cc, size_t n) -> int {
-		if (*pp)
-			cudaFreeHost(*pp);
-		*pp = nullptr;
-		*cc = 0;
-		cudaError_t e = cudaMallocHost(pp, n);
-		if (e != cudaSuccess)
-			return fail_cuda(c, e, "cudaMallocHost");
-		*cc = n;
+	if (need <= *cap)
 		return 0;
-	});
+	if (*p)
+		cudaFreeHost(*p);
+	*p = nullptr;
+	const size_t n = grown(need, *cap);
+	*cap = 0;
+	cudaError_t e = cudaMallocHost(p, n);
+	if (e != cudaSuccess)
+		return fail_cuda(ctx, e, "cudaMallocHost");
+	*cap = n;
+	return 0;
 }
 
-// Split one glyph into rectangles of tiles with at most kMaxItems items each.
+// ---- tile planning ---------------------------------------------------------------------------------
 struct Planned {
 	b200sdf_tile_job t;
 	uint64_t cost;
 };
 
-void plan_glyph(const b200sdf_glyph_job &j, std::vector<Planned> &out)
+// Split one glyph into rectangles of tiles with at most kMaxItems items each.
+void plan_glyph(uint32_t src_off, uint32_t seg_cnt, uint32_t width, uint32_t height, uint64_t out_off, uint32_t job,
+                std::vector<Planned> &out)
 {
 	using namespace b200sdf;
-	const uint32_t nx = (j.width + kTileW - 1) / kTileW, ny = (j.height + kTileH - 1) / kTileH;
+	const uint32_t nx = (width + kTileW - 1) / kTileW, ny = (height + kTileH - 1) / kTileH;
 	// column strips only when one tile row alone exceeds the item budget
 	const uint32_t col_parts = (nx + kMaxItems - 1) / kMaxItems;
 	const uint32_t cols_per = (nx + col_parts - 1) / col_parts;
@@ -127,48 +128,211 @@ void plan_glyph(const b200sdf_glyph_job &j, std::vector<Planned> &out)
 	for (uint32_t ty = 0; ty < ny; ty += rows_per)
 		for (uint32_t tx = 0; tx < nx; tx += cols_per) {
 			Planned p;
-			p.t.seg_off = j.seg_off;
-			p.t.seg_cnt = j.seg_cnt;
-			p.t.out_off = j.out_off;
-			p.t.width = (uint16_t)j.width;
-			p.t.height = (uint16_t)j.height;
+			p.t.seg_off = src_off;
+			p.t.seg_cnt = seg_cnt;
+			p.t.out_off = out_off;
+			p.t.width = (uint16_t)width;
+			p.t.height = (uint16_t)height;
 			p.t.tx0 = (uint16_t)tx;
 			p.t.ty0 = (uint16_t)ty;
 			p.t.ntx = (uint16_t)std::min(cols_per, nx - tx);
 			p.t.nty = (uint16_t)std::min(rows_per, ny - ty);
-			p.t.reserved = 0;
-			p.cost = (uint64_t)p.t.ntx * p.t.nty * (uint64_t)(j.seg_cnt + 8);
+			p.t.job = job;
+			p.cost = (uint64_t)p.t.ntx * p.t.nty * (uint64_t)(seg_cnt + 8);
 			out.push_back(p);
 		}
 }
 
-int plan_impl(const b200sdf_glyph_job *jobs, uint32_t n_jobs, uint32_t n_seg, uint64_t out_bytes, std::vector<Planned> &v,
-              uint64_t *pairs, const char **why)
+bool frame_ok(uint32_t w, uint32_t h, uint64_t out_off, uint64_t out_bytes, const char **why)
+{
+	if (w == 0 || h == 0 || w > B200SDF_MAX_DIM || h > B200SDF_MAX_DIM) {
+		*why = "glyph job with zero or oversized width/height";
+		return false;
+	}
+	if (out_off + (uint64_t)w * h > out_bytes) {
+		*why = "glyph job bitmap exceeds out_bytes";
+		return false;
+	}
+	return true;
+}
+
+void sort_plan(std::vector<Planned> &v)
+{
+	// largest first: the hardware CTA scheduler then approximates longest-processing-time-first
+	std::stable_sort(v.begin(), v.end(), [](const Planned &a, const Planned &b) { return a.cost > b.cost; });
+}
+
+int plan_segments(const b200sdf_glyph_job *jobs, uint32_t n_jobs, uint32_t n_seg, uint64_t out_bytes, std::vector<Planned> &v,
+                  uint64_t *pairs, const char **why)
 {
 	uint64_t pr = 0;
 	v.clear();
 	v.reserve(n_jobs + n_jobs / 8 + 4);
 	for (uint32_t i = 0; i < n_jobs; ++i) {
 		const b200sdf_glyph_job &j = jobs[i];
-		if (j.width == 0 || j.height == 0 || j.width > B200SDF_MAX_DIM || j.height > B200SDF_MAX_DIM) {
-			*why = "glyph job with zero or oversized width/height";
+		if (!frame_ok(j.width, j.height, j.out_off, out_bytes, why))
 			return B200SDF_E_ARG;
-		}
 		if ((uint64_t)j.seg_off + j.seg_cnt > n_seg) {
 			*why = "glyph job segment range exceeds n_seg";
 			return B200SDF_E_ARG;
 		}
-		if (j.out_off + (uint64_t)j.width * j.height > out_bytes) {
-			*why = "glyph job bitmap exceeds out_bytes";
+		pr += (uint64_t)j.width * j.height * j.seg_cnt;
+		plan_glyph(j.seg_off, j.seg_cnt, j.width, j.height, j.out_off, B200SDF_NO_JOB, v);
+	}
+	sort_plan(v);
+	if (pairs)
+		*pairs = pr;
+	return 0;
+}
+
+// curves may be null (device-resident planning): then the per-record consistency check is skipped
+int plan_outlines(const b200sdf_outline_job *jobs, uint32_t n_jobs, const b200sdf_curve *curves, uint32_t n_curves,
+                  uint32_t n_seg, uint64_t out_bytes, std::vector<Planned> &v, uint64_t *pairs, const char **why)
+{
+	uint64_t pr = 0;
+	v.clear();
+	v.reserve(n_jobs + n_jobs / 8 + 4);
+	for (uint32_t i = 0; i < n_jobs; ++i) {
+		const b200sdf_outline_job &j = jobs[i];
+		if (!frame_ok(j.width, j.height, j.out_off, out_bytes, why))
+			return B200SDF_E_ARG;
+		if (j.kind == B200SDF_KIND_SEGMENTS) {
+			if ((uint64_t)j.src_off + j.src_cnt > n_seg || j.seg_cnt != j.src_cnt) {
+				*why = "outline job (segments) range exceeds n_seg or seg_cnt != src_cnt";
+				return B200SDF_E_ARG;
+			}
+			plan_glyph(j.src_off, j.seg_cnt, j.width, j.height, j.out_off, B200SDF_NO_JOB, v);
+		} else if (j.kind == B200SDF_KIND_CURVES) {
+			if ((uint64_t)j.src_off + j.src_cnt > n_curves || (j.src_cnt == 0 && j.seg_cnt != 0)) {
+				*why = "outline job (curves) range exceeds n_curves";
+				return B200SDF_E_ARG;
+			}
+			if (curves) {
+				// the device's binary search needs seg_off = running sum of 2^depth starting at 0
+				uint64_t run = 0;
+				for (uint32_t c = 0; c < j.src_cnt; ++c) {
+					const b200sdf_curve &cv = curves[j.src_off + c];
+					if (cv.depth > 20 || cv.seg_off != run) {
+						*why = "curve record with depth > 20 or inconsistent seg_off";
+						return B200SDF_E_ARG;
+					}
+					run += 1ull << cv.depth;
+				}
+				if (run != j.seg_cnt) {
+					*why = "outline job seg_cnt does not match its curve records";
+					return B200SDF_E_ARG;
+				}
+			}
+			plan_glyph(j.src_off, j.seg_cnt, j.width, j.height, j.out_off, i, v);
+		} else {
+			*why = "outline job with unknown kind";
 			return B200SDF_E_ARG;
 		}
 		pr += (uint64_t)j.width * j.height * j.seg_cnt;
-		plan_glyph(j, v);
 	}
-	// largest first: the hardware CTA scheduler then approximates longest-processing-time-first
-	std::stable_sort(v.begin(), v.end(), [](const Planned &a, const Planned &b) { return a.cost > b.cost; });
+	sort_plan(v);
 	if (pairs)
 		*pairs = pr;
+	return 0;
+}
+
+int copy_plan(const std::vector<Planned> &v, b200sdf_tile_job *tiles, uint32_t cap, uint32_t *n_tiles)
+{
+	*n_tiles = (uint32_t)v.size();
+	if (tiles) {
+		if (cap < v.size())
+			return B200SDF_E_ARG;
+		for (size_t i = 0; i < v.size(); ++i)
+			tiles[i] = v[i].t;
+	}
+	return 0;
+}
+
+void launch_sdf(const void *d_segs, const void *d_curves, const void *d_ojobs, const void *d_tiles, uint32_t n_tiles,
+                void *d_out, cudaStream_t stream)
+{
+	b200sdf::sdf_tiles_kernel<<<n_tiles, b200sdf::kThreads, 0, stream>>>(
+	    reinterpret_cast<const float4 *>(d_segs), reinterpret_cast<const b200sdf_curve *>(d_curves),
+	    reinterpret_cast<const b200sdf_outline_job *>(d_ojobs), reinterpret_cast<const b200sdf_tile_job *>(d_tiles),
+	    reinterpret_cast<uint8_t *>(d_out));
+}
+
+// ---- slots -----------------------------------------------------------------------------------------
+size_t acquire_slot(b200sdf_ctx *ctx)
+{
+	std::unique_lock<std::mutex> lk(ctx->mu);
+	size_t si;
+	for (;;) {
+		for (si = 0; si < ctx->slots.size(); ++si)
+			if (!ctx->slots[si].busy)
+				break;
+		if (si < ctx->slots.size())
+			break;
+		ctx->cv.wait(lk);
+	}
+	ctx->slots[si].busy = true;
+	ctx->slots[si].generation++;
+	return si;
+}
+
+int release_slot(b200sdf_ctx *ctx, Slot &s, int code)
+{
+	std::lock_guard<std::mutex> g(ctx->mu);
+	s.busy = false;
+	ctx->cv.notify_one();
+	return code;
+}
+
+// The common submit path: everything already validated and planned.
+int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b200sdf_curve *curves, uint32_t n_curves,
+                   const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_outline_job *ojobs, uint32_t n_ojobs,
+                   uint8_t *out, uint64_t out_bytes, uint64_t *ticket)
+{
+	const size_t si = acquire_slot(ctx);
+	Slot &s = ctx->slots[si];
+	cudaError_t e = cudaSetDevice(ctx->device);
+	if (e != cudaSuccess)
+		return release_slot(ctx, s, fail_cuda(ctx, e, "cudaSetDevice"));
+	const size_t n_tiles = plan.size();
+	int rc;
+	if ((rc = grow_device(ctx, s.segs, (size_t)n_seg * sizeof(b200sdf_segment))) ||
+	    (rc = grow_device(ctx, s.curves, (size_t)n_curves * sizeof(b200sdf_curve))) ||
+	    (rc = grow_device(ctx, s.ojobs, (size_t)n_ojobs * sizeof(b200sdf_outline_job))) ||
+	    (rc = grow_device(ctx, s.tiles, n_tiles * sizeof(b200sdf_tile_job))) ||
+	    (rc = grow_device(ctx, s.out, (size_t)out_bytes)) ||
+	    (rc = grow_pinned(ctx, &s.h_tiles, &s.h_tiles_cap, n_tiles * sizeof(b200sdf_tile_job))))
+		return release_slot(ctx, s, rc);
+	b200sdf_tile_job *ht = reinterpret_cast<b200sdf_tile_job *>(s.h_tiles);
+	for (size_t i = 0; i < n_tiles; ++i)
+		ht[i] = plan[i].t;
+
+#define SUB_TRY(call)                                                \
+	do {                                                             \
+		cudaError_t e_ = (call);                                     \
+		if (e_ != cudaSuccess)                                       \
+			return release_slot(ctx, s, fail_cuda(ctx, e_, #call));  \
+	} while (0)
+	if (n_seg)
+		SUB_TRY(cudaMemcpyAsync(s.segs.p, segs, (size_t)n_seg * sizeof(b200sdf_segment), cudaMemcpyHostToDevice, s.stream));
+	if (n_curves)
+		SUB_TRY(cudaMemcpyAsync(s.curves.p, curves, (size_t)n_curves * sizeof(b200sdf_curve), cudaMemcpyHostToDevice, s.stream));
+	if (n_ojobs)
+		SUB_TRY(cudaMemcpyAsync(s.ojobs.p, ojobs, (size_t)n_ojobs * sizeof(b200sdf_outline_job), cudaMemcpyHostToDevice, s.stream));
+	if (n_tiles) {
+		SUB_TRY(cudaMemcpyAsync(s.tiles.p, ht, n_tiles * sizeof(b200sdf_tile_job), cudaMemcpyHostToDevice, s.stream));
+		launch_sdf(s.segs.p, s.curves.p, s.ojobs.p, s.tiles.p, (uint32_t)n_tiles, s.out.p, s.stream);
+		SUB_TRY(cudaGetLastError());
+		// bitmaps may be sparse in `out` (caller-chosen out_off); the device buffer mirrors the layout
+		SUB_TRY(cudaMemcpyAsync(out, s.out.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, s.stream));
+	}
+	SUB_TRY(cudaEventRecord(s.done, s.stream));
+#undef SUB_TRY
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		if (n_tiles)
+			ctx->launches++;
+		*ticket = ((uint64_t)s.generation << 8) | (uint64_t)si;
+	}
 	return 0;
 }
 
@@ -236,12 +400,9 @@ void b200sdf_destroy(b200sdf_ctx *ctx)
 	for (auto &s : ctx->slots) {
 		if (s.stream)
 			cudaStreamSynchronize(s.stream);
-		if (s.d_segs)
-			cudaFree(s.d_segs);
-		if (s.d_tiles)
-			cudaFree(s.d_tiles);
-		if (s.d_out)
-			cudaFree(s.d_out);
+		for (DevBuf *b : {&s.segs, &s.curves, &s.ojobs, &s.tiles, &s.out, &s.seg_base})
+			if (b->p)
+				cudaFree(b->p);
 		if (s.h_tiles)
 			cudaFreeHost(s.h_tiles);
 		if (s.done)
@@ -280,21 +441,24 @@ int b200sdf_plan_tiles(const b200sdf_glyph_job *jobs, uint32_t n_jobs, uint32_t 
 		return B200SDF_E_ARG;
 	std::vector<Planned> v;
 	const char *why = "";
-	int rc = plan_impl(jobs, n_jobs, n_seg, out_bytes, v, pairs, &why);
-	if (rc)
-		return rc;
-	*n_tiles = (uint32_t)v.size();
-	if (tiles) {
-		if (cap < v.size())
-			return B200SDF_E_ARG;
-		for (size_t i = 0; i < v.size(); ++i)
-			tiles[i] = v[i].t;
-	}
-	return 0;
+	int rc = plan_segments(jobs, n_jobs, n_seg, out_bytes, v, pairs, &why);
+	return rc ? rc : copy_plan(v, tiles, cap, n_tiles);
 }
 
-int b200sdf_render_device(b200sdf_ctx *ctx, const b200sdf_segment *d_segs, const b200sdf_tile_job *d_tiles,
-                          uint32_t n_tiles, uint8_t *d_out, void *stream)
+int b200sdf_plan_outline_tiles(const b200sdf_outline_job *jobs, uint32_t n_jobs, uint32_t n_curves, uint32_t n_seg,
+                               uint64_t out_bytes, b200sdf_tile_job *tiles, uint32_t cap, uint32_t *n_tiles, uint64_t *pairs)
+{
+	if ((!jobs && n_jobs) || !n_tiles)
+		return B200SDF_E_ARG;
+	std::vector<Planned> v;
+	const char *why = "";
+	int rc = plan_outlines(jobs, n_jobs, nullptr, n_curves, n_seg, out_bytes, v, pairs, &why);
+	return rc ? rc : copy_plan(v, tiles, cap, n_tiles);
+}
+
+int b200sdf_render_outlines_device(b200sdf_ctx *ctx, const b200sdf_curve *d_curves, const b200sdf_segment *d_segs,
+                                   const b200sdf_outline_job *d_jobs, const b200sdf_tile_job *d_tiles, uint32_t n_tiles,
+                                   uint8_t *d_out, void *stream)
 {
 	if (!ctx)
 		return B200SDF_E_ARG;
@@ -302,16 +466,21 @@ int b200sdf_render_device(b200sdf_ctx *ctx, const b200sdf_segment *d_segs, const
 		return 0;
 	if (!d_tiles || !d_out)
 		return fail_arg(ctx, "render_device: null device pointer");
-	if (((uintptr_t)d_segs & 15u) != 0)
-		return fail_arg(ctx, "render_device: segment array must be 16-byte aligned");
-	b200sdf::sdf_tiles_kernel<<<n_tiles, b200sdf::kThreads, 0, (cudaStream_t)stream>>>(
-	    reinterpret_cast<const float4 *>(d_segs), d_tiles, d_out);
+	if ((((uintptr_t)d_segs) & 15u) != 0 || (((uintptr_t)d_curves) & 15u) != 0)
+		return fail_arg(ctx, "render_device: segment / curve arrays must be 16-byte aligned");
+	launch_sdf(d_segs, d_curves, d_jobs, d_tiles, n_tiles, d_out, (cudaStream_t)stream);
 	CU_TRY(ctx, cudaGetLastError());
 	{
 		std::lock_guard<std::mutex> g(ctx->mu);
 		ctx->launches++;
 	}
 	return 0;
+}
+
+int b200sdf_render_device(b200sdf_ctx *ctx, const b200sdf_segment *d_segs, const b200sdf_tile_job *d_tiles,
+                          uint32_t n_tiles, uint8_t *d_out, void *stream)
+{
+	return b200sdf_render_outlines_device(ctx, nullptr, d_segs, nullptr, d_tiles, n_tiles, d_out, stream);
 }
 
 int b200sdf_submit(b200sdf_ctx *ctx, const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_glyph_job *jobs,
@@ -323,73 +492,26 @@ int b200sdf_submit(b200sdf_ctx *ctx, const b200sdf_segment *segs, uint32_t n_seg
 		return fail_arg(ctx, "submit: null buffer");
 	std::vector<Planned> plan;
 	const char *why = "";
-	int rc = plan_impl(jobs, n_jobs, n_seg, out_bytes, plan, nullptr, &why);
+	int rc = plan_segments(jobs, n_jobs, n_seg, out_bytes, plan, nullptr, &why);
 	if (rc)
 		return fail_arg(ctx, why);
+	return submit_planned(ctx, plan, nullptr, 0, segs, n_seg, nullptr, 0, out, out_bytes, ticket);
+}
 
-	size_t si;
-	{
-		std::unique_lock<std::mutex> lk(ctx->mu);
-		for (;;) {
-			for (si = 0; si < ctx->slots.size(); ++si)
-				if (!ctx->slots[si].busy)
-					break;
-			if (si < ctx->slots.size())
-				break;
-			ctx->cv.wait(lk);
-		}
-		ctx->slots[si].busy = true;
-		ctx->slots[si].generation++;
-	}
-	Slot &s = ctx->slots[si];
-	auto release = [&](int code) {
-		std::lock_guard<std::mutex> g(ctx->mu);
-		s.busy = false;
-		ctx->cv.notify_one();
-		return code;
-	};
-	cudaError_t e = cudaSetDevice(ctx->device);
-	if (e != cudaSuccess)
-		return release(fail_cuda(ctx, e, "cudaSetDevice"));
-	const size_t n_tiles = plan.size();
-	void *ht = s.h_tiles;
-	if ((rc = grow_device(ctx, &s.d_segs, &s.segs_cap, (size_t)n_seg * sizeof(b200sdf_segment))) ||
-	    (rc = grow_device(ctx, &s.d_tiles, &s.tiles_cap, n_tiles * sizeof(b200sdf_tile_job))) ||
-	    (rc = grow_device(ctx, &s.d_out, &s.out_cap, (size_t)out_bytes)) ||
-	    (rc = grow_pinned(ctx, &ht, &s.h_tiles_cap, n_tiles * sizeof(b200sdf_tile_job)))) {
-		s.h_tiles = (b200sdf_tile_job *)ht;
-		return release(rc);
-	}
-	s.h_tiles = (b200sdf_tile_job *)ht;
-	for (size_t i = 0; i < n_tiles; ++i)
-		s.h_tiles[i] = plan[i].t;
-
-#define SUB_TRY(call)                                        \
-	do {                                                     \
-		cudaError_t e_ = (call);                             \
-		if (e_ != cudaSuccess)                               \
-			return release(fail_cuda(ctx, e_, #call));       \
-	} while (0)
-	if (n_seg)
-		SUB_TRY(cudaMemcpyAsync(s.d_segs, segs, (size_t)n_seg * sizeof(b200sdf_segment), cudaMemcpyHostToDevice, s.stream));
-	if (n_tiles) {
-		SUB_TRY(cudaMemcpyAsync(s.d_tiles, s.h_tiles, n_tiles * sizeof(b200sdf_tile_job), cudaMemcpyHostToDevice, s.stream));
-		b200sdf::sdf_tiles_kernel<<<(unsigned)n_tiles, b200sdf::kThreads, 0, s.stream>>>(
-		    reinterpret_cast<const float4 *>(s.d_segs), reinterpret_cast<const b200sdf_tile_job *>(s.d_tiles),
-		    reinterpret_cast<uint8_t *>(s.d_out));
-		SUB_TRY(cudaGetLastError());
-		// bitmaps may be sparse in `out` (caller-chosen out_off); the device buffer mirrors the layout
-		SUB_TRY(cudaMemcpyAsync(out, s.d_out, (size_t)out_bytes, cudaMemcpyDeviceToHost, s.stream));
-	}
-	SUB_TRY(cudaEventRecord(s.done, s.stream));
-#undef SUB_TRY
-	{
-		std::lock_guard<std::mutex> g(ctx->mu);
-		if (n_tiles)
-			ctx->launches++;
-		*ticket = ((uint64_t)s.generation << 8) | (uint64_t)si;
-	}
-	return 0;
+int b200sdf_submit_outlines(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint32_t n_curves, const b200sdf_segment *segs,
+                            uint32_t n_seg, const b200sdf_outline_job *jobs, uint32_t n_jobs, uint8_t *out,
+                            uint64_t out_bytes, uint64_t *ticket)
+{
+	if (!ctx || !ticket)
+		return B200SDF_E_ARG;
+	if ((n_seg && !segs) || (n_curves && !curves) || (n_jobs && !jobs) || (out_bytes && !out))
+		return fail_arg(ctx, "submit_outlines: null buffer");
+	std::vector<Planned> plan;
+	const char *why = "";
+	int rc = plan_outlines(jobs, n_jobs, curves, n_curves, n_seg, out_bytes, plan, nullptr, &why);
+	if (rc)
+		return fail_arg(ctx, why);
+	return submit_planned(ctx, plan, curves, n_curves, segs, n_seg, jobs, n_jobs, out, out_bytes, ticket);
 }
 
 int b200sdf_wait(b200sdf_ctx *ctx, uint64_t ticket)
@@ -406,11 +528,7 @@ int b200sdf_wait(b200sdf_ctx *ctx, uint64_t ticket)
 	}
 	Slot &s = ctx->slots[si];
 	cudaError_t e = cudaEventSynchronize(s.done);
-	{
-		std::lock_guard<std::mutex> g(ctx->mu);
-		s.busy = false;
-		ctx->cv.notify_one();
-	}
+	release_slot(ctx, s, 0);
 	if (e != cudaSuccess)
 		return fail_cuda(ctx, e, "cudaEventSynchronize");
 	return 0;
@@ -426,6 +544,69 @@ int b200sdf_render(b200sdf_ctx *ctx, const b200sdf_segment *segs, uint32_t n_seg
 	return b200sdf_wait(ctx, t);
 }
 
+int b200sdf_flatten_outlines(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint32_t n_curves, const b200sdf_outline_job *jobs,
+                             uint32_t n_jobs, b200sdf_segment *out_segs, uint64_t n_out)
+{
+	if (!ctx)
+		return B200SDF_E_ARG;
+	if ((n_curves && !curves) || (n_jobs && !jobs) || (n_out && !out_segs))
+		return fail_arg(ctx, "flatten_outlines: null buffer");
+	// validate exactly like submit (bitmap frames are irrelevant here: give each job a fake 1x1 frame check)
+	std::vector<uint64_t> base(n_jobs + 1, 0);
+	for (uint32_t i = 0; i < n_jobs; ++i) {
+		const b200sdf_outline_job &j = jobs[i];
+		if (j.kind != B200SDF_KIND_CURVES || (uint64_t)j.src_off + j.src_cnt > n_curves)
+			return fail_arg(ctx, "flatten_outlines: only CURVES jobs with valid ranges");
+		uint64_t run = 0;
+		for (uint32_t c = 0; c < j.src_cnt; ++c) {
+			const b200sdf_curve &cv = curves[j.src_off + c];
+			if (cv.depth > 20 || cv.seg_off != run)
+				return fail_arg(ctx, "curve record with depth > 20 or inconsistent seg_off");
+			run += 1ull << cv.depth;
+		}
+		if (run != j.seg_cnt)
+			return fail_arg(ctx, "outline job seg_cnt does not match its curve records");
+		base[i + 1] = base[i] + run;
+	}
+	if (base[n_jobs] != n_out)
+		return fail_arg(ctx, "flatten_outlines: n_out != sum of seg_cnt");
+	if (n_jobs == 0 || n_out == 0)
+		return 0;
+	const size_t si = acquire_slot(ctx);
+	Slot &s = ctx->slots[si];
+	int rc;
+	if ((rc = grow_device(ctx, s.curves, (size_t)n_curves * sizeof(b200sdf_curve))) ||
+	    (rc = grow_device(ctx, s.ojobs, (size_t)n_jobs * sizeof(b200sdf_outline_job))) ||
+	    (rc = grow_device(ctx, s.seg_base, (size_t)(n_jobs + 1) * sizeof(uint64_t))) ||
+	    (rc = grow_device(ctx, s.segs, (size_t)n_out * sizeof(b200sdf_segment))))
+		return release_slot(ctx, s, rc);
+	cudaError_t e = cudaSetDevice(ctx->device);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(s.curves.p, curves, (size_t)n_curves * sizeof(b200sdf_curve), cudaMemcpyHostToDevice, s.stream);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(s.ojobs.p, jobs, (size_t)n_jobs * sizeof(b200sdf_outline_job), cudaMemcpyHostToDevice, s.stream);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(s.seg_base.p, base.data(), (size_t)(n_jobs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream);
+	if (e == cudaSuccess) {
+		b200sdf::flatten_kernel<<<n_jobs, 256, 0, s.stream>>>(
+		    reinterpret_cast<const b200sdf_curve *>(s.curves.p), reinterpret_cast<const b200sdf_outline_job *>(s.ojobs.p),
+		    reinterpret_cast<const uint64_t *>(s.seg_base.p), reinterpret_cast<float4 *>(s.segs.p));
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(out_segs, s.segs.p, (size_t)n_out * sizeof(b200sdf_segment), cudaMemcpyDeviceToHost, s.stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(s.stream);
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		ctx->launches++;
+	}
+	release_slot(ctx, s, 0);
+	if (e != cudaSuccess)
+		return fail_cuda(ctx, e, "flatten_outlines");
+	return 0;
+}
+
 int b200sdf_measure_fp32_peak(b200sdf_ctx *ctx, int reps, double *tflops, double *ms_out)
 {
 	if (!ctx || !tflops)
@@ -439,12 +620,15 @@ int b200sdf_measure_fp32_peak(b200sdf_ctx *ctx, int reps, double *tflops, double
 	cudaEvent_t a, b;
 	CU_TRY(ctx, cudaEventCreate(&a));
 	CU_TRY(ctx, cudaEventCreate(&b));
-	if (reps < 1)
-		reps = 1;
+	const bool packed = reps < 0; // negative reps: measure the packed FFMA2 variant instead
+	reps = std::max(1, reps < 0 ? -reps : reps);
 	double best = 1e30;
 	for (int r = 0; r < reps + 2; ++r) {
 		cudaEventRecord(a, 0);
-		b200sdf::fp32_peak_kernel<<<blocks, threads>>>(ctx->d_peak, iters, 0.999f, 0.001f);
+		if (packed)
+			b200sdf::fp32x2_peak_kernel<<<blocks, threads>>>(ctx->d_peak, iters, 0.999f, 0.001f);
+		else
+			b200sdf::fp32_peak_kernel<<<blocks, threads>>>(ctx->d_peak, iters, 0.999f, 0.001f);
 		cudaEventRecord(b, 0);
 		cudaError_t e = cudaEventSynchronize(b);
 		if (e != cudaSuccess) {

@@ -190,7 +190,7 @@ int vgb_renderer_render_glyph(const vgb_renderer *r, const vgb_font *f, uint32_t
 	std::string err;
 	if (!r->r->render_batch(*batch, &err))
 		return fail(err);
-	fill_glyph(batch->take_glyph(0), batch->segment_count(), out);
+	fill_glyph(batch->take_glyph(0), (uint32_t)batch->total_segments(), out);
 	return 1;
 }
 
@@ -231,7 +231,7 @@ int vgb_batch_glyph_info(const vgb_batch *b, uint32_t i, vgb_batch_glyph *out)
 	out->advance = g.advance;
 	out->has_bitmap = g.has_bitmap ? 1 : 0;
 	if (g.has_bitmap) {
-		const b200sdf_glyph_job &j = b->b->jobs()[g.job];
+		const b200sdf_outline_job &j = b->b->jobs()[g.job];
 		const PbfGlyph p = g.frame.into_pbf_glyph(g.id, g.advance);
 		out->x0 = g.frame.x0;
 		out->y0 = g.frame.y0;
@@ -241,7 +241,9 @@ int vgb_batch_glyph_info(const vgb_batch *b, uint32_t i, vgb_batch_glyph *out)
 		out->height = p.height;
 		out->left = p.left;
 		out->top = p.top;
-		out->seg_off = j.seg_off;
+		out->kind = j.kind;
+		out->src_off = j.src_off;
+		out->src_cnt = j.src_cnt;
 		out->seg_cnt = j.seg_cnt;
 		out->out_off = j.out_off;
 	}
@@ -252,11 +254,19 @@ const b200sdf_segment *vgb_batch_segments(const vgb_batch *b, uint32_t *n_seg)
 	*n_seg = b->b->segment_count();
 	return b->b->segments();
 }
-const b200sdf_glyph_job *vgb_batch_jobs(const vgb_batch *b, uint32_t *n_jobs)
+const b200sdf_outline_job *vgb_batch_jobs(const vgb_batch *b, uint32_t *n_jobs)
 {
-	*n_jobs = (uint32_t)b->b->jobs().size();
-	return b->b->jobs().data();
+	*n_jobs = b->b->job_count();
+	return b->b->jobs();
 }
+const b200sdf_curve *vgb_batch_curves(const vgb_batch *b, uint32_t *n_curves)
+{
+	*n_curves = b->b->curve_count();
+	return b->b->curves();
+}
+uint64_t vgb_batch_total_segments(const vgb_batch *b) { return b->b->total_segments(); }
+uint32_t vgb_batch_fallback_glyphs(const vgb_batch *b) { return b->b->fallback_glyphs(); }
+void vgb_renderer_set_flatten(vgb_renderer *r, int on_device) { r->r->set_flatten(on_device ? Flatten::Device : Flatten::Host); }
 const uint8_t *vgb_batch_bitmaps(const vgb_batch *b, uint64_t *bytes)
 {
 	*bytes = b->b->bitmap_bytes();

@@ -69,12 +69,13 @@ std::vector<uint8_t> GlyphBlock::encode_batch(const std::string &font_name, cons
 bool GlyphBlock::render(const std::string &font_name, const Renderer &renderer, std::vector<uint8_t> &out,
                         std::string *err) const
 {
-	std::unique_ptr<GlyphBatch> batch = renderer.new_batch();
+	std::unique_ptr<GlyphBatch> batch = renderer.acquire_batch();
 	fill_batch(*batch);
-	if (!renderer.render_batch(*batch, err))
-		return false;
-	out = encode_batch(font_name, *batch);
-	return true;
+	const bool ok = renderer.render_batch(*batch, err);
+	if (ok)
+		out = encode_batch(font_name, *batch);
+	renderer.release_batch(std::move(batch));
+	return ok;
 }
 
 // ---- FontWrapper -------------------------------------------------------------------------------------
@@ -300,7 +301,13 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 
 	auto work = [&](int wid) {
 		// Two batches per worker: while batch A is on the GPU, batch B is being flattened.
-		std::unique_ptr<GlyphBatch> batches[2] = {renderer.new_batch(), renderer.new_batch()};
+		// (batches come from the renderer's pool: their pinned buffers survive across calls)
+		struct Lease {
+			const Renderer &r;
+			std::unique_ptr<GlyphBatch> b[2];
+			explicit Lease(const Renderer &rr) : r(rr) { b[0] = r.acquire_batch(), b[1] = r.acquire_batch(); }
+			~Lease() { r.release_batch(std::move(b[0])), r.release_batch(std::move(b[1])); }
+		} batches(renderer);
 		struct InFlight {
 			const Todo *todo = nullptr;
 			GlyphBatch *batch = nullptr;
@@ -329,13 +336,13 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			if (ti >= tasks.size())
 				break;
 			const Todo &todo = tasks[ti];
-			GlyphBatch *cur = batches[k].get();
+			GlyphBatch *cur = batches.b[k].get();
 			k ^= 1;
 			todo.block.fill_batch(*cur);
 			st.glyphs += cur->glyphs().size();
-			st.bitmaps += cur->jobs().size();
+			st.bitmaps += cur->job_count();
 			st.pixels += cur->bitmap_bytes();
-			st.segments += cur->segment_count();
+			st.segments += cur->total_segments();
 			st.pairs += cur->pairs();
 			InFlight now;
 			now.todo = &todo;

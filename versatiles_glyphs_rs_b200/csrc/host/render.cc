@@ -1,11 +1,11 @@
-// render.cc — RingBuilder, GlyphBatch, Renderer (see render.h for the reference map).
+// render.cc — RingBuilder, OutlineRecorder, GlyphBatch, Renderer (see render.h for the reference map).
 #include "render.h"
 
 #include <algorithm>
 #include <cmath>
-#include <thread>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace vgb {
 
@@ -53,6 +53,169 @@ void RingBuilder::curve_to(float x1, float y1, float x2, float y2, float x, floa
 void RingBuilder::close() { save_ring(); }
 void RingBuilder::finish() { save_ring(); }
 
+// ---- OutlineRecorder -----------------------------------------------------------------------------------
+namespace {
+
+constexpr uint32_t MAX_DEPTH = 12;
+
+// |v| <= 2^15 and v is a multiple of 2^-10: with depth <= 12 every intermediate of the midpoint
+// recursion needs at most 17 + 10 + 24 = 51 significant bits, i.e. f64 arithmetic is exact.
+inline bool dyadic_ok(float v)
+{
+	const double w = (double)v * 1024.0;
+	return std::fabs((double)v) <= 32768.0 && w == std::floor(w);
+}
+
+inline double lerp_exact(double a, double b, double t) { return a + t * (b - a); }
+
+// B(i / 2^k) of one coordinate — the same expression the device evaluates (sdf_kernel.cuh curve_point)
+inline double curve_coord(double s, double c, double e, uint32_t i, uint32_t k)
+{
+	const double t = std::ldexp((double)i, -(int)k);
+	return lerp_exact(lerp_exact(s, c, t), lerp_exact(c, e, t), t);
+}
+
+} // namespace
+
+void OutlineRecorder::begin()
+{
+	recs_.clear();
+	ring_first_rec_ = 0;
+	ring_points_ = 0;
+	ring_bbox_ = BBox();
+	bbox_ = BBox();
+	n_seg_ = 0;
+	rings_ = 0;
+	exact_ = true;
+}
+
+void OutlineRecorder::add_line(P a, P b)
+{
+	b200sdf_curve r;
+	r.sx = a.x, r.sy = a.y, r.cx = a.x, r.cy = a.y, r.ex = b.x, r.ey = b.y;
+	r.seg_off = 0;
+	r.depth = 0;
+	recs_.push_back(r);
+	ring_bbox_.include_point(Point::from_f32(b.x, b.y));
+	ring_points_ += 1;
+	ring_last_ = b;
+}
+
+void OutlineRecorder::move_to(float x, float y)
+{
+	save_ring();
+	if (!dyadic_ok(x) || !dyadic_ok(y))
+		exact_ = false;
+	ring_first_ = ring_last_ = P{x, y};
+	ring_points_ = 1;
+	ring_bbox_.include_point(Point::from_f32(x, y));
+}
+
+void OutlineRecorder::line_to(float x, float y)
+{
+	if (!dyadic_ok(x) || !dyadic_ok(y))
+		exact_ = false;
+	if (ring_points_ == 0) { // Ring::add_point on an empty ring: the ring starts here (ring_builder.rs:75-77)
+		ring_first_ = ring_last_ = P{x, y};
+		ring_points_ = 1;
+		ring_bbox_.include_point(Point::from_f32(x, y));
+		return;
+	}
+	add_line(ring_last_, P{x, y});
+}
+
+// Extremes over the grid points i/2^k, 0 < i < 2^k, of one coordinate of a quadratic: a quadratic is
+// monotone either side of its vertex t* = (s-c)/(s-2c+e), so only the grid points next to t* matter.
+void OutlineRecorder::axis_extrema(double s, double c, double e, uint32_t k, double &lo, double &hi) const
+{
+	const double a = s - c * 2.0 + e;
+	if (k == 0 || a == 0.0)
+		return;
+	const double ts = (s - c) / a;
+	if (!(ts > 0.0 && ts < 1.0))
+		return;
+	const int64_t n = (int64_t)1 << k;
+	const int64_t i0 = (int64_t)std::floor(ts * (double)n);
+	for (int64_t i = i0 - 1; i <= i0 + 2; ++i) { // one extra point each side absorbs the rounding of t*
+		if (i < 1 || i > n - 1)
+			continue;
+		const double v = curve_coord(s, c, e, (uint32_t)i, k);
+		lo = std::fmin(lo, v);
+		hi = std::fmax(hi, v);
+	}
+}
+
+void OutlineRecorder::quad_to(float x1, float y1, float x, float y)
+{
+	if (ring_points_ == 0)
+		return; // ring_builder.rs:83
+	if (!dyadic_ok(x1) || !dyadic_ok(y1) || !dyadic_ok(x) || !dyadic_ok(y)) {
+		exact_ = false;
+		return;
+	}
+	const double sx = ring_last_.x, sy = ring_last_.y, cx = x1, cy = y1, ex = x, ey = y;
+	// Ring::add_quadratic_bezier's test at the root (ring.rs:128-131); at depth j both differences are
+	// exactly 4^-j times the root's, so the tested value is exactly 16^-j times this one.
+	const double dx = sx + ex - cx * 2.0;
+	const double dy = sy + ey - cy * 2.0;
+	double v = dx * dx + dy * dy;
+	uint32_t k = 0;
+	while (v > PRECISION) {
+		v *= 0.0625;
+		if (++k > MAX_DEPTH) {
+			exact_ = false;
+			return;
+		}
+	}
+	b200sdf_curve r;
+	r.sx = ring_last_.x, r.sy = ring_last_.y, r.cx = x1, r.cy = y1, r.ex = x, r.ey = y;
+	r.seg_off = 0;
+	r.depth = k;
+	recs_.push_back(r);
+	ring_bbox_.include_point(Point::from_f32(x, y));
+	axis_extrema(sx, cx, ex, k, ring_bbox_.min.x, ring_bbox_.max.x);
+	axis_extrema(sy, cy, ey, k, ring_bbox_.min.y, ring_bbox_.max.y);
+	ring_points_ += 1u << k;
+	ring_last_ = P{x, y};
+}
+
+void OutlineRecorder::curve_to(float, float, float, float, float, float)
+{
+	// Cubic flattening (ring.rs:159-187) is adaptive, not uniform: flatten literally on the host.
+	exact_ = false;
+}
+
+void OutlineRecorder::close() { save_ring(); }
+void OutlineRecorder::finish() { save_ring(); }
+
+void OutlineRecorder::save_ring()
+{
+	// ring_builder.rs:33-54 on point counts
+	if (ring_points_ >= 3) {
+		// Ring::close — ring.rs:53-63
+		const double eps = std::numeric_limits<double>::epsilon();
+		if (std::fabs((double)ring_first_.x - (double)ring_last_.x) > eps ||
+		    std::fabs((double)ring_first_.y - (double)ring_last_.y) > eps)
+			add_line(ring_last_, ring_first_);
+	}
+	if (ring_points_ >= 4) {
+		uint32_t off = n_seg_;
+		for (size_t i = ring_first_rec_; i < recs_.size(); ++i) {
+			recs_[i].seg_off = off;
+			off += 1u << recs_[i].depth;
+		}
+		n_seg_ = off;
+		bbox_.include_point(ring_bbox_.min);
+		bbox_.include_point(ring_bbox_.max);
+		rings_++;
+	} else {
+		recs_.resize(ring_first_rec_);
+	}
+	ring_first_rec_ = recs_.size();
+	ring_points_ = 0;
+	ring_bbox_ = BBox();
+}
+
 // ---- HostBuffer ------------------------------------------------------------------------------------
 HostBuffer::~HostBuffer()
 {
@@ -68,9 +231,9 @@ bool HostBuffer::reserve(size_t bytes, size_t keep)
 {
 	if (bytes <= cap_)
 		return true;
-	size_t n = cap_ ? cap_ : 4096;
+	size_t n = cap_ ? cap_ : 16384;
 	while (n < bytes)
-		n += n / 2 + 4096;
+		n += n / 2 + 16384;
 	n = (n + 4095) & ~size_t(4095);
 	uint8_t *q = pinned_ ? (uint8_t *)b200sdf_alloc_pinned(n) : (uint8_t *)std::malloc(n);
 	if (!q)
@@ -89,15 +252,24 @@ bool HostBuffer::reserve(size_t bytes, size_t keep)
 }
 
 // ---- GlyphBatch ------------------------------------------------------------------------------------
-GlyphBatch::GlyphBatch(bool pinned) : segs_(pinned), out_(pinned) {}
+GlyphBatch::GlyphBatch(bool pinned, Flatten mode) : mode_(mode), jobs_(pinned), segs_(pinned), curves_(pinned), out_(pinned) {}
 
 void GlyphBatch::clear()
 {
 	glyphs_.clear();
-	jobs_.clear();
-	n_seg_ = 0;
-	out_bytes_ = 0;
-	pairs_ = 0;
+	n_jobs_ = n_seg_ = n_curves_ = n_fallback_ = 0;
+	total_seg_ = out_bytes_ = pairs_ = 0;
+}
+
+bool GlyphBatch::push_job(const b200sdf_outline_job &j)
+{
+	if (!jobs_.reserve(((size_t)n_jobs_ + 1) * sizeof(j), (size_t)n_jobs_ * sizeof(j)))
+		return false;
+	reinterpret_cast<b200sdf_outline_job *>(jobs_.data())[n_jobs_++] = j;
+	out_bytes_ += (uint64_t)j.width * j.height;
+	pairs_ += (uint64_t)j.width * j.height * j.seg_cnt;
+	total_seg_ += j.seg_cnt;
+	return true;
 }
 
 // Rings::get_segments (rings.rs:75-81) narrowed to f32 relative to the integer origin (ox, oy).
@@ -124,11 +296,15 @@ bool GlyphBatch::append_segments(const RingSet &rings, double ox, double oy)
 
 bool GlyphBatch::add_rings(uint32_t id, uint32_t advance, const RenderResult &frame, const RingSet &rings)
 {
-	b200sdf_glyph_job job;
-	job.seg_off = n_seg_;
-	job.seg_cnt = (uint32_t)rings.segment_count();
+	b200sdf_outline_job job;
+	std::memset(&job, 0, sizeof(job));
+	job.kind = B200SDF_KIND_SEGMENTS;
+	job.src_off = n_seg_;
+	job.src_cnt = job.seg_cnt = (uint32_t)rings.segment_count();
 	job.width = frame.width;
 	job.height = frame.height;
+	job.x0 = frame.x0;
+	job.y0 = frame.y0;
 	job.out_off = out_bytes_;
 	if (!append_segments(rings, (double)frame.x0, (double)frame.y0))
 		return false;
@@ -137,11 +313,51 @@ bool GlyphBatch::add_rings(uint32_t id, uint32_t advance, const RenderResult &fr
 	g.advance = advance;
 	g.has_bitmap = true;
 	g.frame = frame;
-	g.job = (uint32_t)jobs_.size();
-	jobs_.push_back(job);
+	g.job = n_jobs_;
+	if (!push_job(job))
+		return false;
 	glyphs_.push_back(g);
-	out_bytes_ += (uint64_t)frame.width * frame.height;
-	pairs_ += (uint64_t)frame.width * frame.height * job.seg_cnt;
+	return true;
+}
+
+namespace {
+
+// prepare_glyph — renderer.rs:64-91
+inline RenderResult frame_of(const BBox &bbox)
+{
+	RenderResult fr;
+	fr.x0 = (int32_t)std::floor(bbox.min.x) - BUFFER;
+	fr.y0 = (int32_t)std::floor(bbox.min.y) - BUFFER;
+	fr.x1 = (int32_t)std::ceil(bbox.max.x) + BUFFER;
+	fr.y1 = (int32_t)std::ceil(bbox.max.y) + BUFFER;
+	fr.width = (uint32_t)(fr.x1 - fr.x0);
+	fr.height = (uint32_t)(fr.y1 - fr.y0);
+	return fr;
+}
+
+} // namespace
+
+// Literal host flattening of the glyph whose rings (font units) are in scratch_: renderer.rs:122-146
+bool GlyphBatch::add_flattened(uint32_t index, uint32_t advance, double advance_float, double scale)
+{
+	BatchGlyph g;
+	g.id = index;
+	g.advance = advance;
+	if (scratch_.is_empty()) { // :118-120
+		glyphs_.push_back(g);
+		return true;
+	}
+	// :122-131 — scale, then shift by half the advance rounding error
+	const double dx = ((double)advance - advance_float) / 2.0;
+	scratch_.scale_translate(scale, dx, 0.0);
+	const BBox bbox = scratch_.get_bbox();
+	if (bbox.is_empty()) { // :133-137
+		glyphs_.push_back(g);
+		return true;
+	}
+	if (!add_rings(index, advance, frame_of(bbox), scratch_))
+		return false;
+	glyphs_.back().frame.y1 -= GLYPH_SIZE; // :146
 	return true;
 }
 
@@ -154,45 +370,71 @@ bool GlyphBatch::add_glyph(const Face &face, uint32_t index)
 	if (!glyph_id)
 		return false;
 	const double scale = (double)GLYPH_SIZE / (double)face.units_per_em(); // :107
-
-	scratch_.clear();
-	RingBuilder builder(scratch_);
-	face.outline_glyph(*glyph_id, builder); // :109-110
-	builder.finish();                       // into_rings, :111
-
 	// :115-116 — (adv * scale) * 0.95, round half away from zero, saturating cast
 	const double advance_float = (double)face.glyph_hor_advance(*glyph_id).value_or(0) * scale * 0.95;
 	const double rounded = std::round(advance_float);
 	const uint32_t advance = rounded <= 0.0 ? 0u : (rounded >= 4294967295.0 ? 4294967295u : (uint32_t)rounded);
 
-	BatchGlyph g;
-	g.id = index;
-	g.advance = advance;
-	if (scratch_.is_empty()) { // :118-120
-		glyphs_.push_back(g);
-		return true;
+	if (mode_ == Flatten::Device) {
+		recorder_.begin();
+		face.outline_glyph(*glyph_id, recorder_); // :109-110
+		recorder_.finish();                       // into_rings, :111
+		if (recorder_.exact()) {
+			BatchGlyph g;
+			g.id = index;
+			g.advance = advance;
+			if (recorder_.is_empty()) { // :118-120
+				glyphs_.push_back(g);
+				return true;
+			}
+			// :122-131 applied to the font-unit box: x*scale then +dx is monotone, so the box of the
+			// transformed points is the transformed box
+			const double dx = ((double)advance - advance_float) / 2.0;
+			BBox bbox;
+			Point lo = recorder_.bbox().min, hi = recorder_.bbox().max;
+			lo.x *= scale, lo.y *= scale, hi.x *= scale, hi.y *= scale;
+			lo.x += dx, lo.y += 0.0, hi.x += dx, hi.y += 0.0;
+			bbox.include_point(lo);
+			bbox.include_point(hi);
+			if (bbox.is_empty()) { // :133-137
+				glyphs_.push_back(g);
+				return true;
+			}
+			const RenderResult fr = frame_of(bbox);
+			const std::vector<b200sdf_curve> &recs = recorder_.records();
+			if (!curves_.reserve(((size_t)n_curves_ + recs.size()) * sizeof(b200sdf_curve), (size_t)n_curves_ * sizeof(b200sdf_curve)))
+				return false;
+			std::memcpy(curves_.data() + (size_t)n_curves_ * sizeof(b200sdf_curve), recs.data(), recs.size() * sizeof(b200sdf_curve));
+			b200sdf_outline_job job;
+			std::memset(&job, 0, sizeof(job));
+			job.kind = B200SDF_KIND_CURVES;
+			job.src_off = n_curves_;
+			job.src_cnt = (uint32_t)recs.size();
+			job.seg_cnt = recorder_.segment_count();
+			job.width = fr.width;
+			job.height = fr.height;
+			job.x0 = fr.x0;
+			job.y0 = fr.y0;
+			job.scale = scale;
+			job.dx = dx;
+			job.out_off = out_bytes_;
+			n_curves_ += (uint32_t)recs.size();
+			g.has_bitmap = true;
+			g.frame = fr;
+			g.frame.y1 -= GLYPH_SIZE; // :146
+			g.job = n_jobs_;
+			if (!push_job(job))
+				return false;
+			glyphs_.push_back(g);
+			return true;
+		}
+		n_fallback_++;
 	}
-	// :122-131 — scale, then shift by half the advance rounding error
-	const double dx = ((double)advance - advance_float) / 2.0;
-	scratch_.scale_translate(scale, dx, 0.0);
-
-	// prepare_glyph — :64-91
-	const BBox bbox = scratch_.get_bbox();
-	if (bbox.is_empty()) { // :133-137
-		glyphs_.push_back(g);
-		return true;
-	}
-	RenderResult fr;
-	fr.x0 = (int32_t)std::floor(bbox.min.x) - BUFFER;
-	fr.y0 = (int32_t)std::floor(bbox.min.y) - BUFFER;
-	fr.x1 = (int32_t)std::ceil(bbox.max.x) + BUFFER;
-	fr.y1 = (int32_t)std::ceil(bbox.max.y) + BUFFER;
-	fr.width = (uint32_t)(fr.x1 - fr.x0);
-	fr.height = (uint32_t)(fr.y1 - fr.y0);
-	if (!add_rings(index, advance, fr, scratch_))
-		return false;
-	glyphs_.back().frame.y1 -= GLYPH_SIZE; // :146
-	return true;
+	scratch_.clear();
+	RingBuilder builder(scratch_);
+	face.outline_glyph(*glyph_id, builder); // :109-110
+	builder.finish();                       // into_rings, :111
+	return add_flattened(index, advance, advance_float, scale);
 }
 
 bool GlyphBatch::ensure_output() { return out_.reserve((size_t)out_bytes_ + 16, 0); }
@@ -203,7 +445,7 @@ PbfGlyph GlyphBatch::take_glyph(size_t i) const
 	if (!b.has_bitmap)
 		return PbfGlyph::empty(b.id, b.advance);
 	PbfGlyph g = b.frame.into_pbf_glyph(b.id, b.advance);
-	const b200sdf_glyph_job &j = jobs_[b.job];
+	const b200sdf_outline_job &j = jobs()[b.job];
 	const size_t n = (size_t)j.width * j.height;
 	g.bitmap.assign(out_.data() + j.out_off, out_.data() + j.out_off + n);
 	return g;
@@ -244,8 +486,32 @@ std::unique_ptr<Renderer> Renderer::new_precise(int device, uint32_t n_slots, st
 
 Renderer::~Renderer()
 {
+	pool_.clear(); // pinned buffers go before the context
 	if (ctx_)
 		b200sdf_destroy(ctx_);
+}
+
+std::unique_ptr<GlyphBatch> Renderer::acquire_batch() const
+{
+	{
+		std::lock_guard<std::mutex> g(pool_mu_);
+		while (!pool_.empty()) {
+			std::unique_ptr<GlyphBatch> b = std::move(pool_.back());
+			pool_.pop_back();
+			if (b->mode() == flatten_) {
+				b->clear();
+				return b;
+			}
+		}
+	}
+	return new_batch();
+}
+
+void Renderer::release_batch(std::unique_ptr<GlyphBatch> b) const
+{
+	std::lock_guard<std::mutex> g(pool_mu_);
+	if (pool_.size() < 128)
+		pool_.push_back(std::move(b));
 }
 
 bool Renderer::submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *err) const
@@ -261,11 +527,11 @@ bool Renderer::submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *er
 		*ticket = ~0ull;
 		return true;
 	}
-	const int rc = b200sdf_submit(ctx_, batch.segments(), batch.segment_count(), batch.jobs().data(),
-	                              (uint32_t)batch.jobs().size(), batch.bitmaps(), batch.bitmap_bytes(), ticket);
+	const int rc = b200sdf_submit_outlines(ctx_, batch.curves(), batch.curve_count(), batch.segments(), batch.segment_count(),
+	                                       batch.jobs(), batch.job_count(), batch.bitmaps(), batch.bitmap_bytes(), ticket);
 	if (rc != 0) {
 		if (err)
-			*err = std::string("b200sdf_submit: ") + b200sdf_last_error(ctx_);
+			*err = std::string("b200sdf_submit_outlines: ") + b200sdf_last_error(ctx_);
 		return false;
 	}
 	return true;
@@ -292,12 +558,12 @@ bool Renderer::render_batch(GlyphBatch &batch, std::string *err) const
 
 std::optional<PbfGlyph> Renderer::render_glyph(const Face &face, uint32_t index, std::string *err) const
 {
-	GlyphBatch batch(mode_ == Mode::Cuda);
-	if (!batch.add_glyph(face, index))
-		return std::nullopt;
-	if (!render_batch(batch, err))
-		return std::nullopt;
-	return batch.take_glyph(0);
+	std::unique_ptr<GlyphBatch> batch = acquire_batch();
+	std::optional<PbfGlyph> out;
+	if (batch->add_glyph(face, index) && render_batch(*batch, err))
+		out = batch->take_glyph(0);
+	release_batch(std::move(batch));
+	return out;
 }
 
 } // namespace vgb

@@ -1,17 +1,21 @@
 // render.h — host side of the rendering path (mirror of reference src/render/*.rs).
 //
-//   RingBuilder   = src/render/ring_builder.rs        outline callbacks -> flattened closed rings
-//   RenderResult  = src/render/result.rs              integer frame of a glyph (+ bitmap)
-//   Renderer      = src/render/renderer.rs            render_glyph(face, codepoint) -> Option<PbfGlyph>
-//   GlyphBatch    = NEW: the flat segment buffer of one GlyphBlock, uploaded once (north star)
+//   RingBuilder     = src/render/ring_builder.rs      outline callbacks -> flattened closed rings (literal)
+//   OutlineRecorder = the same callbacks recorded as curve records for on-device flattening,
+//                     with the exact glyph bounding box computed analytically
+//   RenderResult    = src/render/result.rs            integer frame of a glyph (+ bitmap)
+//   Renderer        = src/render/renderer.rs          render_glyph(face, codepoint) -> Option<PbfGlyph>
+//   GlyphBatch      = NEW: the flat outline buffer of one GlyphBlock, uploaded once (north star)
 //
 // Everything that decides a METRIC (advance, bbox, floor/ceil, width/height/left/top) is computed
-// here in f64 with the reference's operation order; only the per-pixel SDF work goes to the GPU
-// through include/b200sdf.h.  There is no CPU rasteriser in this library.
+// here in f64 with the reference's operation order; only the per-pixel SDF work (and, in outline
+// mode, the flattening that feeds it) goes to the GPU through include/b200sdf.h.  There is no CPU
+// rasteriser in this library.
 #pragma once
 
 #include <cstdint>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <string>
 #include <vector>
@@ -27,6 +31,7 @@ constexpr int32_t GLYPH_SIZE = 24;
 constexpr int32_t BUFFER = 3;
 constexpr double SDF_RADIUS = 8.0;
 constexpr double CUTOFF = 0.25 * 256.0;
+constexpr double PRECISION = 0.01; // ring_builder.rs:62 (tolerance_sq, font units squared)
 
 // protobuf/glyph.rs:10-41
 struct PbfGlyph {
@@ -65,10 +70,10 @@ struct RenderResult {
 	}
 };
 
-// render/ring_builder.rs:8-117
+// render/ring_builder.rs:8-117 — literal flattening on the host
 class RingBuilder : public OutlineBuilder {
   public:
-	explicit RingBuilder(RingSet &rings, double precision = 0.01) : rings_(rings), precision_(precision) {}
+	explicit RingBuilder(RingSet &rings, double precision = PRECISION) : rings_(rings), precision_(precision) {}
 	void move_to(float x, float y) override;
 	void line_to(float x, float y) override;
 	void quad_to(float x1, float y1, float x, float y) override;
@@ -79,6 +84,52 @@ class RingBuilder : public OutlineBuilder {
 	void save_ring();
 	RingSet &rings_;
 	double precision_;
+};
+
+// The same callbacks, recorded instead of flattened.  For outlines whose coordinates are small
+// dyadic rationals (|v| <= 2^15, v * 2^10 integral — every TrueType glyph without scaled
+// components), Ring::add_quadratic_bezier's midpoint recursion (ring.rs:119-144) is exact in f64:
+// the second difference quarters at every level, so the recursion depth k is uniform and the
+// emitted points are exactly B(j / 2^k).  Then
+//   * k follows from the reference's own flatness test evaluated at the root,
+//   * the bounding box of the flattened points is the box of the end points plus the grid points
+//     next to each coordinate's vertex (a quadratic is monotone either side of it),
+//   * ring bookkeeping (save_ring's 3 / 4 point rules, Ring::close) needs only point counts,
+// and the device can regenerate every flattened point bit-for-bit.  Anything else (non-dyadic
+// coordinates, cubic curves, absurd depth) clears exact() and the caller flattens literally.
+class OutlineRecorder : public OutlineBuilder {
+  public:
+	void begin();
+	void move_to(float x, float y) override;
+	void line_to(float x, float y) override;
+	void quad_to(float x1, float y1, float x, float y) override;
+	void curve_to(float x1, float y1, float x2, float y2, float x, float y) override;
+	void close() override;
+	void finish();
+
+	bool exact() const { return exact_; }
+	bool is_empty() const { return rings_ == 0; } // Rings::is_empty
+	const std::vector<b200sdf_curve> &records() const { return recs_; }
+	uint32_t segment_count() const { return n_seg_; }
+	const BBox &bbox() const { return bbox_; } // font units, over every flattened point of the kept rings
+
+  private:
+	struct P {
+		float x, y;
+	};
+	void add_line(P a, P b);
+	void save_ring();
+	void axis_extrema(double s, double c, double e, uint32_t k, double &lo, double &hi) const;
+
+	std::vector<b200sdf_curve> recs_;
+	size_t ring_first_rec_ = 0;
+	uint32_t ring_points_ = 0;
+	P ring_first_{0, 0}, ring_last_{0, 0};
+	BBox ring_bbox_;
+	BBox bbox_;
+	uint32_t n_seg_ = 0;
+	size_t rings_ = 0;
+	bool exact_ = true;
 };
 
 // Growable host buffer, pinned when a CUDA renderer owns it.
@@ -109,24 +160,36 @@ struct BatchGlyph {
 	uint32_t job = 0;        // index into jobs when has_bitmap
 };
 
-// The flat segment buffer of one GlyphBlock (or of any group of glyphs): segments of all glyphs
-// back to back as b200sdf_segment, one b200sdf_glyph_job per bitmap, bitmaps packed back to back.
+// Where flattening happens for a batch.
+enum class Flatten {
+	Device, // upload curve records, flatten on the GPU (glyphs that are not exactly representable fall back per glyph)
+	Host    // flatten on the host, upload b200sdf_segment (the literal renderer_precise seam)
+};
+
+// The flat outline buffer of one GlyphBlock (or of any group of glyphs): curve records and/or
+// segments of all glyphs back to back, one b200sdf_outline_job per bitmap, bitmaps packed back to back.
 class GlyphBatch {
   public:
-	explicit GlyphBatch(bool pinned);
+	GlyphBatch(bool pinned, Flatten mode);
 	void clear();
-	// First half of Renderer::render_glyph (renderer.rs:103-137): cmap lookup, outline, flatten,
-	// advance, scale+shift, integer frame; appends the glyph's segments.  Returns false for
+	Flatten mode() const { return mode_; }
+	// First half of Renderer::render_glyph (renderer.rs:103-137): cmap lookup, outline, advance,
+	// scale+shift, integer frame; appends the glyph's curve records or segments.  Returns false for
 	// "None" (code point not a char / not in the font), true otherwise.
 	bool add_glyph(const Face &face, uint32_t codepoint);
-	// Same from explicit rings already in pixel space (renderer_precise's own signature; used by
-	// tests with synthetic outlines).  Always has a bitmap.
+	// From explicit rings already in pixel space (renderer_precise's own signature; used by tests
+	// with synthetic outlines).  Always has a bitmap, always uploaded as segments.
 	bool add_rings(uint32_t id, uint32_t advance, const RenderResult &frame, const RingSet &rings);
 
 	const std::vector<BatchGlyph> &glyphs() const { return glyphs_; }
-	const std::vector<b200sdf_glyph_job> &jobs() const { return jobs_; }
+	const b200sdf_outline_job *jobs() const { return reinterpret_cast<const b200sdf_outline_job *>(jobs_.data()); }
+	uint32_t job_count() const { return n_jobs_; }
 	const b200sdf_segment *segments() const { return reinterpret_cast<const b200sdf_segment *>(segs_.data()); }
-	uint32_t segment_count() const { return n_seg_; }
+	uint32_t segment_count() const { return n_seg_; }       // host-flattened segments uploaded as such
+	const b200sdf_curve *curves() const { return reinterpret_cast<const b200sdf_curve *>(curves_.data()); }
+	uint32_t curve_count() const { return n_curves_; }
+	uint64_t total_segments() const { return total_seg_; }  // flattened segments of all glyphs (either source)
+	uint32_t fallback_glyphs() const { return n_fallback_; } // Device-mode glyphs that had to be flattened on the host
 	uint8_t *bitmaps() { return out_.data(); }
 	const uint8_t *bitmaps() const { return out_.data(); }
 	uint64_t bitmap_bytes() const { return out_bytes_; }
@@ -137,14 +200,15 @@ class GlyphBatch {
 
   private:
 	bool append_segments(const RingSet &rings, double ox, double oy);
+	bool push_job(const b200sdf_outline_job &j);
+	bool add_flattened(uint32_t index, uint32_t advance, double advance_float, double scale);
+	Flatten mode_;
 	RingSet scratch_;
+	OutlineRecorder recorder_;
 	std::vector<BatchGlyph> glyphs_;
-	std::vector<b200sdf_glyph_job> jobs_;
-	HostBuffer segs_;
-	HostBuffer out_;
-	uint32_t n_seg_ = 0;
-	uint64_t out_bytes_ = 0;
-	uint64_t pairs_ = 0;
+	HostBuffer jobs_, segs_, curves_, out_;
+	uint32_t n_jobs_ = 0, n_seg_ = 0, n_curves_ = 0, n_fallback_ = 0;
+	uint64_t total_seg_ = 0, out_bytes_ = 0, pairs_ = 0;
 };
 
 // render/renderer.rs:17-43.  `Precise` in the reference is the CPU loop; here the precise
@@ -162,7 +226,12 @@ class Renderer {
 	Mode mode() const { return mode_; }
 	uint32_t slots() const { return slots_; }
 	b200sdf_ctx *context() const { return ctx_; }
-	std::unique_ptr<GlyphBatch> new_batch() const { return std::make_unique<GlyphBatch>(mode_ == Mode::Cuda); }
+	Flatten flatten() const { return flatten_; }
+	void set_flatten(Flatten f) { flatten_ = f; }
+	std::unique_ptr<GlyphBatch> new_batch() const { return std::make_unique<GlyphBatch>(mode_ == Mode::Cuda, flatten_); }
+	// Batch pool: pinned buffers are expensive to allocate, so the pipeline recycles batches.
+	std::unique_ptr<GlyphBatch> acquire_batch() const;
+	void release_batch(std::unique_ptr<GlyphBatch> b) const;
 
 	// renderer.rs:103-149 — a batch of one.  nullopt = None.
 	std::optional<PbfGlyph> render_glyph(const Face &face, uint32_t index, std::string *err = nullptr) const;
@@ -177,6 +246,9 @@ class Renderer {
 	Mode mode_ = Mode::Dummy;
 	b200sdf_ctx *ctx_ = nullptr;
 	uint32_t slots_ = 0;
+	Flatten flatten_ = Flatten::Device;
+	mutable std::mutex pool_mu_;
+	mutable std::vector<std::unique_ptr<GlyphBatch>> pool_;
 };
 
 } // namespace vgb

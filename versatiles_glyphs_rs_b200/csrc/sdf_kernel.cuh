@@ -1,25 +1,37 @@
 // sdf_kernel.cuh — the batched SDF kernel for sm_100a (B200).
 //
 // Replaces the hot loops of renderer_precise (reference src/render/renderer_precise.rs:33-81):
-//   loop 2  (row x segment crossing collection, :41-51)      -> crossing scatter in stage_chunk()
+//   loop 2  (row x segment crossing collection, :41-51)      -> crossing scatter in stage_segment()
 //   loop 3  (winding sweep per pixel, :61-67)                 -> prefix sum of the scattered deltas
 //   loop 4  (min_distance_to_line_segment, rtree_segments.rs:40-68 over
 //            Segment::squared_distance_to_point, geometry/segment.rs:54-99) -> the FP32 pair loop
 //   quantisation (:75-79)                                     -> epilogue
+// and, for outline-level jobs, Ring::add_quadratic_bezier (src/geometry/ring.rs:119-144) plus
+// rings.scale/translate (src/render/renderer.rs:122-131): flattening happens while staging, in
+// f64, so flattened segments never touch HBM.
 //
 // One CTA (128 threads) renders one tile job = a rectangle of TW x TH pixel tiles of one glyph.
-// The glyph's segments stream HBM -> shared memory in chunks through the TMA unit
-// (cp.async.bulk + mbarrier, double buffered); each chunk is turned into per-segment records
-// (origin, direction, direction / |direction|^2) once, then every thread evaluates its TW x TH
-// pixels against the chunk.  Threads that would idle because the rectangle has fewer than 128
-// items instead take a slice of the chunk's segments (warp slices and lane slices); slices are
-// merged with shared-memory atomicMin on the non-negative float bit patterns.
+// Segment source A (raw segments): the glyph's segments stream HBM -> shared memory in chunks
+// through the TMA unit (cp.async.bulk + mbarrier, double buffered).  Source B (curve records):
+// the glyph's curve list is bulk-copied once and each thread evaluates its segment's end points.
+// Either way each chunk becomes per-segment records (origin, direction, direction / |direction|^2)
+// once, then every thread evaluates its TW x TH pixels against the chunk.  Threads that would idle
+// because the rectangle has fewer than 128 items take a slice of the chunk's segments instead
+// (warp slices and lane slices); slices are merged with shared-memory atomicMin on the
+// non-negative float bit patterns.
 #pragma once
 
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/b200sdf.h"
+
+#ifndef B200SDF_CHUNK
+#define B200SDF_CHUNK 256
+#endif
+#ifndef B200SDF_FFMA2
+#define B200SDF_FFMA2 1
+#endif
 
 namespace b200sdf {
 
@@ -29,7 +41,9 @@ constexpr int kTileW = B200SDF_TILE_W;
 constexpr int kTileH = B200SDF_TILE_H;
 constexpr int kMaxItems = B200SDF_MAX_ITEMS;
 constexpr int kMaxPix = kMaxItems * kTileW * kTileH;
-constexpr int kChunk = 256; // segments per staged chunk
+constexpr int kChunk = B200SDF_CHUNK;        // segments per staged chunk
+constexpr int kCurveSmem = 2 * kChunk / 2;   // curve records (32 B) that fit the raw staging area
+static_assert(kTileW % 2 == 0, "FFMA2 path pairs pixels along x");
 
 // ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA unit; SASS: UBLKCP / SYNCS) ----------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -63,71 +77,118 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 	             "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
 	             : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async()
-{
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void fence_mbar_init()
-{
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-struct __align__(16) SegA {
-	float vx, vy, dx, dy; // start point, direction (end - start)
+// Per-segment records, laid out for the packed-FP32 pair loop: every value the loop needs as a
+// (v, v) pair is stored duplicated so one LDS.128 yields two ready-made 64-bit register pairs.
+struct __align__(16) SegX {
+	float nvx0, nvx1, ndx0, ndx1; // (-vx, -vx, -dx, -dx)
 };
-struct __align__(8) SegB {
+struct __align__(16) SegY {
+	float nvy0, nvy1, ndy0, ndy1; // (-vy, -vy, -dy, -dy)
+};
+struct __align__(8) SegN {
 	float dxn, dyn; // direction / |direction|^2  (0,0 for a zero-length segment: segment.rs:58-61)
 };
 
 struct SharedStorage {
-	float4 raw[2][kChunk];  // staged b200sdf_segment chunks (TMA destination)
-	SegA recA[2][kChunk];
-	SegB recB[2][kChunk];
-	int delta[kMaxPix];     // signed crossing deltas per pixel of the rectangle (winding sweep)
-	unsigned d2[kMaxPix];   // min squared distance per pixel, float bits
+	float4 raw[2][kChunk]; // staged b200sdf_segment chunks (TMA destination) / the glyph's curve list
+	SegX recX[2][kChunk];
+	SegY recY[2][kChunk];
+	SegN recN[2][kChunk];
+	int delta[kMaxPix];    // signed crossing deltas per pixel of the rectangle (winding sweep)
+	unsigned d2[kMaxPix];  // min squared distance per pixel, float bits
 	uint8_t obuf[kMaxPix + 32];
 	uint64_t bar[2];
 };
 
-// Turn one staged chunk into records and scatter its row crossings.
+struct Rect {
+	int rx0, ry0, rw, rh;
+};
+
+// Turn one segment (origin-relative pixel units) into its records and scatter its row crossings.
 // Crossing rule = renderer_precise.rs:44-50: upward  s.y <= py <  e.y -> sign +1
 //                                             downward s.y >  py >= e.y -> sign -1
 // and the sweep (:63-66) subtracts the sign of every crossing with x_c <= px, so a crossing adds
-// -sign to the first pixel column whose centre is >= x_c; pixels left of the rectangle clamp to
-// its first column, pixels right of it are dropped.
-__device__ __forceinline__ void stage_chunk(const float4 *raw, SegA *recA, SegB *recB, int n, int *delta, int rx0, int ry0,
-                                            int rw, int rh, int tid)
+// -sign to the first pixel column whose centre is >= x_c; columns left of the rectangle clamp to
+// its first column, columns right of it are dropped.
+__device__ __forceinline__ void stage_segment(const float4 s, SegX &rx, SegY &ry, SegN &rn, int *delta, const Rect &R)
 {
-	for (int i = tid; i < n; i += kThreads) {
-		const float4 s = raw[i];
-		const float dx = s.z - s.x, dy = s.w - s.y;
-		const float l2 = dx * dx + dy * dy;
-		const float inv = l2 > 0.0f ? __frcp_rn(l2) : 0.0f;
-		recA[i] = SegA{s.x, s.y, dx, dy};
-		recB[i] = SegB{dx * inv, dy * inv};
+	const float dx = s.z - s.x, dy = s.w - s.y;
+	const float l2 = dx * dx + dy * dy;
+	const float inv = l2 > 0.0f ? __frcp_rn(l2) : 0.0f;
+	rx = SegX{-s.x, -s.x, -dx, -dx};
+	ry = SegY{-s.y, -s.y, -dy, -dy};
+	rn = SegN{dx * inv, dy * inv};
 
-		const float lo = fminf(s.y, s.w), hi = fmaxf(s.y, s.w);
-		// rows r (glyph space) whose centre r+0.5 lies in [lo, hi)
-		int r0 = (int)ceilf(lo - 0.5f), r1 = (int)ceilf(hi - 0.5f);
-		r0 = max(r0, ry0);
-		r1 = min(r1, ry0 + rh);
-		for (int r = r0; r < r1; ++r) {
-			const float py = (float)r + 0.5f;
-			const bool up = (s.y <= py) && (s.w > py);
-			const bool down = (s.y > py) && (s.w <= py);
-			if (!(up || down))
-				continue;
-			const float t = (py - s.y) / dy;
-			const float xc = s.x + t * dx;
-			int c = (int)ceilf(xc - 0.5f) - rx0; // first column with centre >= x_c
-			c = max(c, 0);
-			if (c < rw)
-				atomicAdd(&delta[(r - ry0) * rw + c], up ? -1 : 1);
-		}
+	const float lo = fminf(s.y, s.w), hi = fmaxf(s.y, s.w);
+	// rows r (glyph space) whose centre r+0.5 lies in [lo, hi)
+	int r0 = (int)ceilf(lo - 0.5f), r1 = (int)ceilf(hi - 0.5f);
+	r0 = max(r0, R.ry0);
+	r1 = min(r1, R.ry0 + R.rh);
+#pragma unroll 1
+	for (int r = r0; r < r1; ++r) {
+		const float py = (float)r + 0.5f;
+		const bool up = (s.y <= py) && (s.w > py);
+		const bool down = (s.y > py) && (s.w <= py);
+		if (!(up || down))
+			continue;
+		const float t = (py - s.y) / dy;
+		const float xc = s.x + t * dx;
+		int c = (int)ceilf(xc - 0.5f) - R.rx0; // first column with centre >= x_c
+		c = max(c, 0);
+		if (c < R.rw)
+			atomicAdd(&delta[(r - R.ry0) * R.rw + c], up ? -1 : 1);
 	}
 }
 
+// ---- device flattening (ring.rs:119-144 in closed form, exact for dyadic inputs) --------------------
+__device__ __forceinline__ double lerp_rn(double a, double b, double t)
+{
+	return __dadd_rn(a, __dmul_rn(t, __dsub_rn(b, a))); // never contracted into an FMA
+}
+
+// Point j (0..2^k) of a curve record, in font units.
+__device__ __forceinline__ void curve_point(const b200sdf_curve &c, uint32_t j, double &x, double &y)
+{
+	// t = j / 2^k, exact
+	const double t = (double)j * __longlong_as_double((long long)(1023 - (int)c.depth) << 52);
+	const double sx = c.sx, sy = c.sy, cx = c.cx, cy = c.cy, ex = c.ex, ey = c.ey;
+	x = lerp_rn(lerp_rn(sx, cx, t), lerp_rn(cx, ex, t), t);
+	y = lerp_rn(lerp_rn(sy, cy, t), lerp_rn(cy, ey, t), t);
+}
+
+// Segment g of a CURVES glyph as origin-relative f32 pixel coordinates — the same arithmetic, in
+// the same order, as the host path: p*scale, +dx (renderer.rs:122-131), -origin, narrow to f32.
+__device__ __forceinline__ float4 flatten_segment(const b200sdf_curve *__restrict__ curves, uint32_t n_curves, uint32_t g,
+                                                  double scale, double dx, double ox, double oy)
+{
+	// binary search: last record with seg_off <= g
+	uint32_t lo = 0, hi = n_curves;
+	while (hi - lo > 1) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (curves[mid].seg_off <= g)
+			lo = mid;
+		else
+			hi = mid;
+	}
+	const b200sdf_curve c = curves[lo];
+	const uint32_t j = g - c.seg_off;
+	double x0, y0, x1, y1;
+	curve_point(c, j, x0, y0);
+	curve_point(c, j + 1, x1, y1);
+	float4 s;
+	s.x = (float)__dsub_rn(__dadd_rn(__dmul_rn(x0, scale), dx), ox);
+	s.y = (float)__dsub_rn(__dadd_rn(__dmul_rn(y0, scale), 0.0), oy);
+	s.z = (float)__dsub_rn(__dadd_rn(__dmul_rn(x1, scale), dx), ox);
+	s.w = (float)__dsub_rn(__dadd_rn(__dmul_rn(y1, scale), 0.0), oy);
+	return s;
+}
+
 __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__restrict__ segs,
+                                                             const b200sdf_curve *__restrict__ curves,
+                                                             const b200sdf_outline_job *__restrict__ ojobs,
                                                              const b200sdf_tile_job *__restrict__ jobs,
                                                              uint8_t *__restrict__ out)
 {
@@ -140,14 +201,31 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 	// 32-byte job record, uniform across the CTA
 	const b200sdf_tile_job job = jobs[blockIdx.x];
 	const int W = job.width, H = job.height;
-	const int rx0 = job.tx0 * kTileW, ry0 = job.ty0 * kTileH; // rectangle origin (pixels, y upward)
-	const int rw = min((int)job.ntx * kTileW, W - rx0);
-	const int rh = min((int)job.nty * kTileH, H - ry0);
-	const int rpix = rw * rh;
+	Rect R;
+	R.rx0 = job.tx0 * kTileW;
+	R.ry0 = job.ty0 * kTileH; // rectangle origin (pixels, y upward)
+	R.rw = min((int)job.ntx * kTileW, W - R.rx0);
+	R.rh = min((int)job.nty * kTileH, H - R.ry0);
+	const int rpix = R.rw * R.rh;
 	const int n_items = (int)job.ntx * (int)job.nty;
 	const uint32_t S = job.seg_cnt;
-	const float4 *gsegs = segs + job.seg_off;
 	const int n_chunks = (int)((S + kChunk - 1) / kChunk);
+	const bool from_curves = job.job != B200SDF_NO_JOB;
+
+	// source A: raw segments; source B: curve records of this glyph
+	const float4 *gsegs = segs + job.seg_off;
+	const b200sdf_curve *gcurves = curves + job.seg_off;
+	uint32_t n_curves = 0;
+	double g_scale = 0.0, g_dx = 0.0, g_ox = 0.0, g_oy = 0.0;
+	if (from_curves) {
+		const b200sdf_outline_job oj = ojobs[job.job];
+		n_curves = oj.src_cnt;
+		g_scale = oj.scale;
+		g_dx = oj.dx;
+		g_ox = (double)oj.x0;
+		g_oy = (double)oj.y0;
+	}
+	const bool curves_in_smem = from_curves && n_curves <= (uint32_t)kCurveSmem;
 
 	if (tid == 0) {
 		mbar_init(&sm.bar[0], 1);
@@ -160,15 +238,24 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 	}
 	__syncthreads();
 	if (tid == 0) {
-		for (int c = 0; c < 2 && c < n_chunks; ++c) {
-			const uint32_t n = min((uint32_t)kChunk, S - (uint32_t)c * kChunk);
-			mbar_expect_tx(&sm.bar[c], n * 16u);
-			bulk_g2s(sm.raw[c], gsegs + (size_t)c * kChunk, n * 16u, &sm.bar[c]);
+		if (!from_curves) {
+			for (int c = 0; c < 2 && c < n_chunks; ++c) {
+				const uint32_t n = min((uint32_t)kChunk, S - (uint32_t)c * kChunk);
+				mbar_expect_tx(&sm.bar[c], n * 16u);
+				bulk_g2s(sm.raw[c], gsegs + (size_t)c * kChunk, n * 16u, &sm.bar[c]);
+			}
+		} else if (curves_in_smem && n_curves) {
+			mbar_expect_tx(&sm.bar[0], n_curves * 32u);
+			bulk_g2s(&sm.raw[0][0], gcurves, n_curves * 32u, &sm.bar[0]);
 		}
+	}
+	if (curves_in_smem && n_curves) {
+		mbar_wait(&sm.bar[0], 0);
+		gcurves = reinterpret_cast<const b200sdf_curve *>(&sm.raw[0][0]);
 	}
 
 	// ---- work split: item group per warp, then warp slices x lane slices over the segments ----
-	const int n_groups = (n_items + 31) >> 5;              // 1..4
+	const int n_groups = (n_items + 31) >> 5; // 1..4
 	const int wslices = n_groups == 1 ? 4 : (n_groups == 2 ? 2 : 1);
 	const int group = n_groups == 1 ? 0 : (n_groups == 2 ? (warp & 1) : warp);
 	const int wslice = n_groups == 1 ? warp : (n_groups == 2 ? (warp >> 1) : 0);
@@ -177,13 +264,13 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 	const int lslices = 32 / g_items;
 	const int item = group * 32 + lane % g_items;
 	const int lslice = (lane / g_items) % lslices;
-	const int T = wslices * lslices;             // total segment slices for my item
-	const int sid = wslice * lslices + lslice;   // my slice
+	const int T = wslices * lslices;           // total segment slices for my item
+	const int sid = wslice * lslices + lslice; // my slice
 
 	const int tx = item % (int)job.ntx, ty = item / (int)job.ntx;
 	// pixel block origin relative to the glyph origin; pixel centres at +0.5
-	const float px0 = (float)(rx0 + tx * kTileW) + 0.5f;
-	const float py0 = (float)(ry0 + ty * kTileH) + 0.5f;
+	const float px0 = (float)(R.rx0 + tx * kTileW) + 0.5f;
+	const float py0 = (float)(R.ry0 + ty * kTileH) + 0.5f;
 
 	float mn[kTileH][kTileW];
 #pragma unroll
@@ -192,42 +279,91 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 		for (int j = 0; j < kTileW; ++j)
 			mn[r][j] = __int_as_float(0x7f800000);
 
+#if B200SDF_FFMA2
+	float2 pxp[kTileW / 2], pyp[kTileH];
+#pragma unroll
+	for (int j = 0; j < kTileW / 2; ++j)
+		pxp[j] = make_float2(px0 + (float)(2 * j), px0 + (float)(2 * j + 1));
+#pragma unroll
+	for (int r = 0; r < kTileH; ++r)
+		pyp[r] = make_float2(py0 + (float)r, py0 + (float)r);
+#endif
+
 	for (int c = 0; c < n_chunks; ++c) {
 		const int b = c & 1;
 		const int n = (int)min((uint32_t)kChunk, S - (uint32_t)c * kChunk);
-		mbar_wait(&sm.bar[b], (uint32_t)((c >> 1) & 1));
-		stage_chunk(sm.raw[b], sm.recA[b], sm.recB[b], n, sm.delta, rx0, ry0, rw, rh, tid);
+		if (!from_curves) {
+			mbar_wait(&sm.bar[b], (uint32_t)((c >> 1) & 1));
+			for (int i = tid; i < n; i += kThreads)
+				stage_segment(sm.raw[b][i], sm.recX[b][i], sm.recY[b][i], sm.recN[b][i], sm.delta, R);
+		} else {
+			for (int i = tid; i < n; i += kThreads) {
+				const float4 s = flatten_segment(gcurves, n_curves, (uint32_t)(c * kChunk + i), g_scale, g_dx, g_ox, g_oy);
+				stage_segment(s, sm.recX[b][i], sm.recY[b][i], sm.recN[b][i], sm.delta, R);
+			}
+		}
 		__syncthreads(); // records of chunk c visible; raw[b] consumed; everyone is past chunk c-1
-		if (tid == 0 && c + 2 < n_chunks) {
+		if (!from_curves && tid == 0 && c + 2 < n_chunks) {
 			const uint32_t n2 = min((uint32_t)kChunk, S - (uint32_t)(c + 2) * kChunk);
 			fence_proxy_async();
 			mbar_expect_tx(&sm.bar[b], n2 * 16u);
 			bulk_g2s(sm.raw[b], gsegs + (size_t)(c + 2) * kChunk, n2 * 16u, &sm.bar[b]);
 		}
 		if (warp_active) {
-			const SegA *__restrict__ A = sm.recA[b];
-			const SegB *__restrict__ B = sm.recB[b];
+			const SegX *__restrict__ X = sm.recX[b];
+			const SegY *__restrict__ Y = sm.recY[b];
+			const SegN *__restrict__ Nn = sm.recN[b];
 #pragma unroll 2
 			for (int i = sid; i < n; i += T) {
-				const SegA a = A[i];
-				const SegB q = B[i];
+#if B200SDF_FFMA2
+				// Packed-FP32 (FFMA2/FADD2/FMUL2) form: two horizontally adjacent pixels per instruction.
+				const float4 xr = *reinterpret_cast<const float4 *>(&X[i]);
+				const float4 yr = *reinterpret_cast<const float4 *>(&Y[i]);
+				const SegN q = Nn[i];
+				const float2 nvx = make_float2(xr.x, xr.y), ndx = make_float2(xr.z, xr.w);
+				const float2 nvy = make_float2(yr.x, yr.y), ndy = make_float2(yr.z, yr.w);
+				float2 pax[kTileW / 2];
+#pragma unroll
+				for (int j = 0; j < kTileW / 2; ++j)
+					pax[j] = __fadd2_rn(pxp[j], nvx);
+#pragma unroll
+				for (int r = 0; r < kTileH; ++r) {
+					const float2 pay = __fadd2_rn(pyp[r], nvy);
+					const float cr = pay.x * q.dyn;
+#pragma unroll
+					for (int j = 0; j < kTileW / 2; ++j) {
+						float2 t;
+						t.x = __saturatef(fmaf(pax[j].x, q.dxn, cr));
+						t.y = __saturatef(fmaf(pax[j].y, q.dxn, cr));
+						const float2 qx = __ffma2_rn(t, ndx, pax[j]);
+						const float2 qy = __ffma2_rn(t, ndy, pay);
+						const float2 d2 = __ffma2_rn(qx, qx, __fmul2_rn(qy, qy));
+						mn[r][2 * j] = fminf(mn[r][2 * j], d2.x);
+						mn[r][2 * j + 1] = fminf(mn[r][2 * j + 1], d2.y);
+					}
+				}
+#else
+				const SegX xr = X[i];
+				const SegY yr = Y[i];
+				const SegN q = Nn[i];
 				float pax[kTileW];
 #pragma unroll
 				for (int j = 0; j < kTileW; ++j)
-					pax[j] = (px0 + (float)j) - a.vx;
+					pax[j] = (px0 + (float)j) + xr.nvx0;
 #pragma unroll
 				for (int r = 0; r < kTileH; ++r) {
-					const float pay = (py0 + (float)r) - a.vy;
+					const float pay = (py0 + (float)r) + yr.nvy0;
 					const float cr = pay * q.dyn;
 #pragma unroll
 					for (int j = 0; j < kTileW; ++j) {
 						const float t = __saturatef(fmaf(pax[j], q.dxn, cr));
-						const float qx = fmaf(-t, a.dx, pax[j]);
-						const float qy = fmaf(-t, a.dy, pay);
+						const float qx = fmaf(t, xr.ndx0, pax[j]);
+						const float qy = fmaf(t, yr.ndy0, pay);
 						const float d2 = fmaf(qx, qx, qy * qy);
 						mn[r][j] = fminf(mn[r][j], d2);
 					}
 				}
+#endif
 			}
 		}
 	}
@@ -240,8 +376,8 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 #pragma unroll
 			for (int j = 0; j < kTileW; ++j) {
 				const int x = tx * kTileW + j;
-				if (x < rw && y < rh)
-					atomicMin(&sm.d2[y * rw + x], __float_as_uint(mn[r][j]));
+				if (x < R.rw && y < R.rh)
+					atomicMin(&sm.d2[y * R.rw + x], __float_as_uint(mn[r][j]));
 			}
 		}
 	}
@@ -250,24 +386,24 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 	// ---- epilogue: winding prefix, quantise (renderer_precise.rs:67-79), stage in output order ----
 	// Output rows run top (largest y) to bottom; the rectangle's rows [ry0, ry0+rh) map to output
 	// rows H-1-y.  For a full-width rectangle they form one contiguous byte range.
-	const bool full_width = (rx0 == 0 && rw == W);
-	const size_t gbase = (size_t)job.out_off + (size_t)(H - ry0 - rh) * (size_t)W; // first byte (full-width case)
+	const bool full_width = (R.rx0 == 0 && R.rw == W);
+	const size_t gbase = (size_t)job.out_off + (size_t)(H - R.ry0 - R.rh) * (size_t)W; // first byte (full-width case)
 	const uint32_t mis = full_width ? (uint32_t)((uintptr_t)(out + gbase) & 15u) : 0u;
 	for (int p = tid; p < rpix; p += kThreads) {
-		const int y = p / rw, x = p - y * rw;
+		const int y = p / R.rw, x = p - y * R.rw;
 		int wn = 0;
-		const int *drow = &sm.delta[y * rw];
+		const int *drow = &sm.delta[y * R.rw];
 		for (int k = 0; k <= x; ++k)
 			wn += drow[k];
 		const float d = sqrtf(__uint_as_float(sm.d2[p]));
-		// value = 255 - (±d * 32 + 64), clamped, rounded half away from zero
+		// value = 255 - (+-d * 32 + 64), clamped, rounded half away from zero
 		float v = wn != 0 ? fmaf(d, 32.0f, 191.0f) : fmaf(d, -32.0f, 191.0f);
 		v = fminf(fmaxf(v, 0.0f), 255.0f);
 		const uint8_t q = (uint8_t)(int)floorf(v + 0.5f);
 		if (full_width)
-			sm.obuf[mis + (uint32_t)((rh - 1 - y) * rw + x)] = q;
+			sm.obuf[mis + (uint32_t)((R.rh - 1 - y) * R.rw + x)] = q;
 		else
-			out[(size_t)job.out_off + (size_t)(H - 1 - (ry0 + y)) * (size_t)W + (size_t)(rx0 + x)] = q;
+			out[(size_t)job.out_off + (size_t)(H - 1 - (R.ry0 + y)) * (size_t)W + (size_t)(R.rx0 + x)] = q;
 	}
 	if (!full_width)
 		return;
@@ -285,6 +421,19 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 				gdst[k] = sm.obuf[k];
 		}
 	}
+}
+
+// Device flattening only (b200sdf_flatten_outlines): one CTA per glyph, one thread per segment.
+__global__ void __launch_bounds__(256) flatten_kernel(const b200sdf_curve *__restrict__ curves,
+                                                      const b200sdf_outline_job *__restrict__ ojobs,
+                                                      const uint64_t *__restrict__ seg_base, float4 *__restrict__ out)
+{
+	const b200sdf_outline_job oj = ojobs[blockIdx.x];
+	if (oj.kind != B200SDF_KIND_CURVES)
+		return;
+	for (uint32_t g = threadIdx.x; g < oj.seg_cnt; g += blockDim.x)
+		out[seg_base[blockIdx.x] + g] =
+		    flatten_segment(curves + oj.src_off, oj.src_cnt, g, oj.scale, oj.dx, (double)oj.x0, (double)oj.y0);
 }
 
 // ---- FP32 peak microbenchmark: 8 independent dependent-FFMA chains per thread ----------------------
@@ -306,6 +455,31 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, f
 		}
 	}
 	out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+// Same with packed FFMA2 (2 FMAs per lane per instruction): tells whether packed FP32 raises the
+// FLOP ceiling or only halves the issue slots.
+__global__ void __launch_bounds__(256) fp32x2_peak_kernel(float *out, int iters, float a, float b)
+{
+	float2 x0 = make_float2(threadIdx.x * 1e-3f, 0.5f), x1 = x0, x2 = x0, x3 = x0, x4 = x0, x5 = x0, x6 = x0, x7 = x0;
+	x1.x += 1.f, x2.x += 2.f, x3.x += 3.f, x4.x += 4.f, x5.x += 5.f, x6.x += 6.f, x7.x += 7.f;
+	const float2 aa = make_float2(a, a), bb = make_float2(b, b);
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			x0 = __ffma2_rn(x0, aa, bb);
+			x1 = __ffma2_rn(x1, aa, bb);
+			x2 = __ffma2_rn(x2, aa, bb);
+			x3 = __ffma2_rn(x3, aa, bb);
+			x4 = __ffma2_rn(x4, aa, bb);
+			x5 = __ffma2_rn(x5, aa, bb);
+			x6 = __ffma2_rn(x6, aa, bb);
+			x7 = __ffma2_rn(x7, aa, bb);
+		}
+	}
+	out[blockIdx.x * blockDim.x + threadIdx.x] =
+	    ((x0.x + x1.x) + (x2.x + x3.x)) + ((x4.x + x5.x) + (x6.x + x7.x)) + ((x0.y + x1.y) + (x2.y + x3.y)) +
+	    ((x4.y + x5.y) + (x6.y + x7.y));
 }
 
 } // namespace b200sdf
