@@ -331,7 +331,13 @@ def main():
             "value": world * st.glyphs * e2e_steps / e2e_s, "unit": "glyphs/s",
             "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(st.pixels),
             "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "pbf_bytes_per_step": int(st.pbf_bytes),
-            "api": "FontManager.render_glyphs(Writer.new_memory(), Renderer.new_precise()): flatten -> H2D -> kernel -> D2H -> PBF",
+            "api": "FontManager.render_glyphs(Writer.new_memory(), Renderer.new_precise()): outlines -> H2D -> flatten+SDF kernel -> D2H -> PBF",
+            "host_phases_ms_last_step": {
+                "workers": st.workers, "submits": st.submits, "wall": st.wall_ns / 1e6,
+                "outline_per_worker": st.outline_ns / 1e6 / max(1, st.workers), "submit_per_worker": st.submit_ns / 1e6 / max(1, st.workers),
+                "wait_per_worker": st.wait_ns / 1e6 / max(1, st.workers), "encode_per_worker": st.encode_ns / 1e6 / max(1, st.workers),
+                "write_per_worker": st.write_ns / 1e6 / max(1, st.workers),
+            },
         }
         if rank == 0 and world == 1:
             import oracle_lib as O

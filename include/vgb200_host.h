@@ -120,6 +120,9 @@ int vgb_writer_entry(const vgb_writer *w, uint32_t i, const char **name, int32_t
 /* ---- FontManager ---- */
 typedef struct {
 	uint64_t glyphs, bitmaps, pixels, segments, pairs, pbf_bytes, blocks;
+	/* host time per phase, ns summed over workers; wall_ns = the whole call */
+	uint64_t outline_ns, submit_ns, wait_ns, encode_ns, write_ns, wall_ns;
+	uint64_t submits, workers;
 } vgb_stats;
 
 vgb_manager *vgb_manager_new(int parallel);                                        /* manager.rs:28-33 */

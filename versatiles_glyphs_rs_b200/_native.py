@@ -125,7 +125,9 @@ class BatchGlyph(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("glyphs", "bitmaps", "pixels", "segments", "pairs", "pbf_bytes", "blocks")]
+    _fields_ = [(n, C.c_uint64) for n in (
+        "glyphs", "bitmaps", "pixels", "segments", "pairs", "pbf_bytes", "blocks",
+        "outline_ns", "submit_ns", "wait_ns", "encode_ns", "write_ns", "wall_ns", "submits", "workers")]
 
 
 # name -> (restype, argtypes); the single source of truth for "every symbol the headers declare"

@@ -301,6 +301,15 @@ class RenderStats:
     pairs: int
     pbf_bytes: int
     blocks: int
+    # host time per phase in ns, summed over workers (wall_ns: the whole call)
+    outline_ns: int = 0
+    submit_ns: int = 0
+    wait_ns: int = 0
+    encode_ns: int = 0
+    write_ns: int = 0
+    wall_ns: int = 0
+    submits: int = 0
+    workers: int = 0
 
 
 class FontManager:
@@ -355,7 +364,7 @@ class FontManager:
         st = N.Stats()
         if N.host.vgb_manager_render_glyphs(self._h, writer._h, renderer._h, shard, n_shards, threads, C.byref(st)) != 0:
             raise B200Error(N.host_error())
-        return RenderStats(st.glyphs, st.bitmaps, st.pixels, st.segments, st.pairs, st.pbf_bytes, st.blocks)
+        return RenderStats(*[int(getattr(st, n)) for n, _ in N.Stats._fields_])
 
     def write_index_json(self, writer: Writer):
         if N.host.vgb_manager_write_index_json(self._h, writer._h) != 0:

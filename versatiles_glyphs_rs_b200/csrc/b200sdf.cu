@@ -320,6 +320,14 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 		SUB_TRY(cudaMemcpyAsync(s.ojobs.p, ojobs, (size_t)n_ojobs * sizeof(b200sdf_outline_job), cudaMemcpyHostToDevice, s.stream));
 	if (n_tiles) {
 		SUB_TRY(cudaMemcpyAsync(s.tiles.p, ht, n_tiles * sizeof(b200sdf_tile_job), cudaMemcpyHostToDevice, s.stream));
+		// Bitmaps may be sparse in `out` (caller-chosen out_off); the device buffer mirrors the layout and
+		// is copied back whole, so bytes between bitmaps are defined (zero) rather than stale device memory.
+		uint64_t covered = 0;
+		for (const Planned &p : plan)
+			if (p.t.tx0 == 0 && p.t.ty0 == 0)
+				covered += (uint64_t)p.t.width * p.t.height;
+		if (covered < out_bytes)
+			SUB_TRY(cudaMemsetAsync(s.out.p, 0, (size_t)out_bytes, s.stream));
 		launch_sdf(s.segs.p, s.curves.p, s.ojobs.p, s.tiles.p, (uint32_t)n_tiles, s.out.p, s.stream);
 		SUB_TRY(cudaGetLastError());
 		// bitmaps may be sparse in `out` (caller-chosen out_off); the device buffer mirrors the layout

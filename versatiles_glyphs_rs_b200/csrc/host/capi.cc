@@ -379,6 +379,14 @@ int vgb_manager_render_glyphs(const vgb_manager *m, vgb_writer *w, const vgb_ren
 		stats->pairs = st.pairs;
 		stats->pbf_bytes = st.pbf_bytes;
 		stats->blocks = st.blocks;
+		stats->outline_ns = st.outline_ns;
+		stats->submit_ns = st.submit_ns;
+		stats->wait_ns = st.wait_ns;
+		stats->encode_ns = st.encode_ns;
+		stats->write_ns = st.write_ns;
+		stats->wall_ns = st.wall_ns;
+		stats->submits = st.submits;
+		stats->workers = st.workers;
 	}
 	return 0;
 }

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cerrno>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -47,15 +48,25 @@ std::string GlyphBlock::range() const
 }
 std::string GlyphBlock::filename() const { return range() + ".pbf"; }
 
-bool GlyphBlock::fill_batch(GlyphBatch &batch) const
+void GlyphBlock::append_to_batch(GlyphBatch &batch) const
 {
-	batch.clear();
 	for (uint32_t i = 0; i < GLYPH_BLOCK_SIZE; ++i) {
 		const FontFileEntry *f = fonts_[i];
 		if (f)
 			batch.add_glyph(*f->face, start_index_ + i); // false = None = skipped (glyph_block.rs:74-76)
 	}
+}
+
+bool GlyphBlock::fill_batch(GlyphBatch &batch) const
+{
+	batch.clear();
+	append_to_batch(batch);
 	return true;
+}
+
+std::vector<uint8_t> GlyphBlock::encode_range(const std::string &font_name, const GlyphBatch &batch, size_t g0, size_t g1) const
+{
+	return encode_batch_range(font_name, range(), batch, g0, g1);
 }
 
 std::vector<uint8_t> GlyphBlock::encode_batch(const std::string &font_name, const GlyphBatch &batch) const
@@ -155,6 +166,18 @@ bool Writer::write_file(const std::string &filename, const uint8_t *bytes, size_
 	if (!ok && err)
 		*err = "write " + path + " failed";
 	return ok;
+}
+
+bool Writer::write_file(const std::string &filename, std::vector<uint8_t> &&bytes, std::string *err)
+{
+	if (to_disk_)
+		return write_file(filename, bytes.data(), bytes.size(), err);
+	bytes_written_ += bytes.size();
+	Entry e;
+	e.name = filename;
+	e.bytes = std::move(bytes);
+	entries_.push_back(std::move(e));
+	return true;
 }
 
 bool Writer::write_directory(const std::string &dirname, std::string *err)
@@ -260,6 +283,14 @@ bool FontManager::write_index_json(Writer &writer, std::string *err) const
 	return writer.write_file("index.json", (const uint8_t *)s.data(), s.size(), err);
 }
 
+namespace {
+inline uint64_t now_ns()
+{
+	return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
+	    .count();
+}
+} // namespace
+
 bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::string *err, RenderStats *stats,
                                 uint32_t shard, uint32_t n_shards, int threads) const
 {
@@ -267,18 +298,26 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		const std::string *name;
 		GlyphBlock block;
 	};
+	const uint64_t t_begin = now_ns();
 	if (n_shards == 0)
 		n_shards = 1;
 	std::vector<Todo> tasks;
 	uint32_t index = 0;
+	size_t total_glyphs = 0;
 	for (const auto &kv : fonts_) {
 		if (!writer.write_directory(kv.first + "/", err))
 			return false;
 		for (GlyphBlock &b : kv.second.get_blocks()) {
-			if (index++ % n_shards == shard)
+			if (index++ % n_shards == shard) {
+				total_glyphs += b.len();
 				tasks.push_back(Todo{&kv.first, std::move(b)});
+			}
 		}
 	}
+
+	// Fullest blocks first: dynamic scheduling then ends with the cheap ones (the reference's rayon
+	// par_iter makes no order promise either, manager.rs:117-118).
+	std::stable_sort(tasks.begin(), tasks.end(), [](const Todo &a, const Todo &b) { return a.block.len() > b.block.len(); });
 
 	int workers = 1;
 	if (parallel_) {
@@ -288,6 +327,9 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		if (renderer.mode() == Renderer::Mode::Cuda)
 			workers = std::max(1, std::min(workers, (int)renderer.slots() / 2));
 	}
+	// One submission carries whole blocks until it holds about `target` glyphs: small jobs keep one
+	// block per submission (parallelism), big jobs amortise the per-submission cost.
+	const size_t target = std::min<size_t>(2048, std::max<size_t>(1, total_glyphs / ((size_t)workers * 4)));
 	std::atomic<size_t> next{0};
 	std::atomic<bool> failed{false};
 	std::mutex writer_mutex, err_mutex;
@@ -300,67 +342,118 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	};
 
 	auto work = [&](int wid) {
-		// Two batches per worker: while batch A is on the GPU, batch B is being flattened.
-		// (batches come from the renderer's pool: their pinned buffers survive across calls)
-		struct Lease {
-			const Renderer &r;
-			std::unique_ptr<GlyphBatch> b[2];
-			explicit Lease(const Renderer &rr) : r(rr) { b[0] = r.acquire_batch(), b[1] = r.acquire_batch(); }
-			~Lease() { r.release_batch(std::move(b[0])), r.release_batch(std::move(b[1])); }
-		} batches(renderer);
-		struct InFlight {
-			const Todo *todo = nullptr;
-			GlyphBatch *batch = nullptr;
-			uint64_t ticket = 0;
-		} pending;
 		RenderStats &st = per_worker[(size_t)wid];
-		auto retire = [&](InFlight &p) -> bool {
+		auto emit = [&](const Todo &todo, std::vector<uint8_t> &&data) -> bool {
+			st.pbf_bytes += data.size();
+			st.blocks++;
+			const uint64_t t0 = now_ns();
 			std::string e;
-			if (!renderer.wait_batch(p.ticket, &e)) {
+			bool ok;
+			{
+				std::lock_guard<std::mutex> g(writer_mutex);
+				ok = writer.write_file(*todo.name + "/" + todo.block.filename(), std::move(data), &e);
+			}
+			st.write_ns += now_ns() - t0;
+			if (!ok)
+				fail(e);
+			return ok;
+		};
+		// Two batches per worker: while batch A is on the GPU, batch B is being filled.
+		// (batches come from the renderer's pool: their pinned buffers survive across calls)
+		struct Part {
+			const Todo *todo;
+			size_t g0, g1;
+		};
+		struct Flight {
+			std::unique_ptr<GlyphBatch> batch;
+			std::vector<Part> parts;
+			uint64_t ticket = 0;
+			bool active = false;
+		} flights[2];
+		flights[0].batch = renderer.acquire_batch();
+		flights[1].batch = renderer.acquire_batch();
+		auto retire = [&](Flight &f) -> bool {
+			if (!f.active)
+				return true;
+			f.active = false;
+			std::string e;
+			uint64_t t0 = now_ns();
+			const bool waited = renderer.wait_batch(f.ticket, &e);
+			st.wait_ns += now_ns() - t0;
+			if (!waited) {
 				fail(e);
 				return false;
 			}
-			const std::vector<uint8_t> data = p.todo->block.encode_batch(*p.todo->name, *p.batch);
-			st.pbf_bytes += data.size();
-			st.blocks++;
-			std::lock_guard<std::mutex> g(writer_mutex);
-			if (!writer.write_file(*p.todo->name + "/" + p.todo->block.filename(), data.data(), data.size(), &e)) {
-				fail(e);
-				return false;
+			for (const Part &p : f.parts) {
+				t0 = now_ns();
+				std::vector<uint8_t> data = p.todo->block.encode_range(*p.todo->name, *f.batch, p.g0, p.g1);
+				st.encode_ns += now_ns() - t0;
+				if (!emit(*p.todo, std::move(data)))
+					return false;
 			}
 			return true;
 		};
 		int k = 0;
-		while (!failed.load()) {
-			const size_t ti = next.fetch_add(1);
-			if (ti >= tasks.size())
+		bool more = true;
+		while (more && !failed.load()) {
+			Flight &cur = flights[k];
+			cur.batch->clear();
+			cur.parts.clear();
+			uint64_t t0 = now_ns();
+			while (cur.batch->glyphs().size() < target) {
+				const size_t ti = next.fetch_add(1);
+				if (ti >= tasks.size()) {
+					more = false;
+					break;
+				}
+				const Todo &todo = tasks[ti];
+				const size_t g0 = cur.batch->glyphs().size();
+				todo.block.append_to_batch(*cur.batch);
+				cur.parts.push_back(Part{&todo, g0, cur.batch->glyphs().size()});
+			}
+			st.outline_ns += now_ns() - t0;
+			if (cur.parts.empty())
 				break;
-			const Todo &todo = tasks[ti];
-			GlyphBatch *cur = batches.b[k].get();
-			k ^= 1;
-			todo.block.fill_batch(*cur);
-			st.glyphs += cur->glyphs().size();
-			st.bitmaps += cur->job_count();
-			st.pixels += cur->bitmap_bytes();
-			st.segments += cur->total_segments();
-			st.pairs += cur->pairs();
-			InFlight now;
-			now.todo = &todo;
-			now.batch = cur;
+			st.glyphs += cur.batch->glyphs().size();
+			st.bitmaps += cur.batch->job_count();
+			st.pixels += cur.batch->bitmap_bytes();
+			st.segments += cur.batch->total_segments();
+			st.pairs += cur.batch->pairs();
+			if (cur.batch->job_count() == 0) {
+				// nothing to rasterise (empty blocks, or only bitmap-less glyphs): no GPU round trip
+				cur.ticket = ~0ull;
+				cur.active = false;
+				for (const Part &p : cur.parts) {
+					t0 = now_ns();
+					std::vector<uint8_t> data = p.todo->block.encode_range(*p.todo->name, *cur.batch, p.g0, p.g1);
+					st.encode_ns += now_ns() - t0;
+					if (!emit(*p.todo, std::move(data)))
+						break;
+				}
+				continue;
+			}
+			t0 = now_ns();
 			std::string e;
-			if (!renderer.submit_batch(*cur, &now.ticket, &e)) {
+			const bool submitted = renderer.submit_batch(*cur.batch, &cur.ticket, &e);
+			st.submit_ns += now_ns() - t0;
+			st.submits++;
+			if (!submitted) {
 				fail(e);
 				break;
 			}
-			if (pending.todo && !retire(pending)) {
-				pending.todo = nullptr;
-				renderer.wait_batch(now.ticket, nullptr);
-				return;
-			}
-			pending = now;
+			cur.active = true;
+			k ^= 1;
+			if (!retire(flights[k]))
+				break;
 		}
-		if (pending.todo)
-			retire(pending);
+		for (Flight &f : flights) {
+			if (f.active && failed.load()) {
+				renderer.wait_batch(f.ticket, nullptr); // drain; results are dropped
+				f.active = false;
+			}
+			retire(f);
+			renderer.release_batch(std::move(f.batch));
+		}
 	};
 
 	if (workers == 1) {
@@ -382,7 +475,15 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			stats->pairs += s.pairs;
 			stats->pbf_bytes += s.pbf_bytes;
 			stats->blocks += s.blocks;
+			stats->outline_ns += s.outline_ns;
+			stats->submit_ns += s.submit_ns;
+			stats->wait_ns += s.wait_ns;
+			stats->encode_ns += s.encode_ns;
+			stats->write_ns += s.write_ns;
+			stats->submits += s.submits;
 		}
+		stats->workers = (uint64_t)workers;
+		stats->wall_ns = now_ns() - t_begin;
 	}
 	return !failed.load();
 }

@@ -56,6 +56,10 @@ class GlyphBlock {
 	// Split form used by the pipeline: fill a batch, later turn the rendered batch into the PBF.
 	bool fill_batch(GlyphBatch &batch) const;
 	std::vector<uint8_t> encode_batch(const std::string &font_name, const GlyphBatch &batch) const;
+	// Several blocks may share one batch: append this block's glyphs (no clear) / encode glyphs [g0, g1)
+	// straight from the batch's bitmap buffer (no intermediate PbfGlyph copies).
+	void append_to_batch(GlyphBatch &batch) const;
+	std::vector<uint8_t> encode_range(const std::string &font_name, const GlyphBatch &batch, size_t g0, size_t g1) const;
 
   private:
 	uint32_t start_index_;
@@ -81,6 +85,7 @@ class Writer {
 	static Writer new_file(const std::string &folder);
 	static Writer new_memory();
 	bool write_file(const std::string &filename, const uint8_t *bytes, size_t len, std::string *err);
+	bool write_file(const std::string &filename, std::vector<uint8_t> &&bytes, std::string *err); // no copy for the memory writer
 	bool write_directory(const std::string &dirname, std::string *err);
 	bool finish(std::string *err);
 	struct Entry {
@@ -101,6 +106,9 @@ class Writer {
 
 struct RenderStats {
 	uint64_t glyphs = 0, bitmaps = 0, pixels = 0, segments = 0, pairs = 0, pbf_bytes = 0, blocks = 0;
+	// where the host time went, nanoseconds summed over workers (wall_ns: the whole call)
+	uint64_t outline_ns = 0, submit_ns = 0, wait_ns = 0, encode_ns = 0, write_ns = 0, wall_ns = 0;
+	uint64_t submits = 0, workers = 0;
 };
 
 class FontManager {

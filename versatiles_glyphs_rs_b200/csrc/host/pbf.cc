@@ -89,6 +89,78 @@ std::vector<uint8_t> PbfGlyphs::into_vec() const
 	return out;
 }
 
+std::vector<uint8_t> encode_batch_range(const std::string &name, const std::string &range, const GlyphBatch &batch, size_t g0,
+                                        size_t g1)
+{
+	struct Item {
+		uint32_t id, width, height, left_zz, top_zz, advance;
+		const uint8_t *bitmap; // nullptr = None
+		size_t bitmap_len, body;
+	};
+	std::vector<Item> items;
+	items.reserve(g1 - g0);
+	size_t stack = 1 + varint_size(name.size()) + name.size() + 1 + varint_size(range.size()) + range.size();
+	for (size_t i = g0; i < g1; ++i) {
+		const BatchGlyph &b = batch.glyphs()[i];
+		Item it;
+		it.id = b.id;
+		it.advance = b.advance;
+		if (b.has_bitmap) {
+			const PbfGlyph m = b.frame.into_pbf_glyph(b.id, b.advance); // metrics only (result.rs:66-76)
+			const b200sdf_outline_job &j = batch.jobs()[b.job];
+			it.width = m.width, it.height = m.height;
+			it.left_zz = zigzag32(m.left), it.top_zz = zigzag32(m.top);
+			it.bitmap = batch.bitmaps() + j.out_off;
+			it.bitmap_len = (size_t)j.width * j.height;
+		} else {
+			it.width = it.height = 0;
+			it.left_zz = it.top_zz = 0;
+			it.bitmap = nullptr;
+			it.bitmap_len = 0;
+		}
+		it.body = 1 + varint_size(it.id) + (it.bitmap ? 1 + varint_size(it.bitmap_len) + it.bitmap_len : 0) + 1 +
+		          varint_size(it.width) + 1 + varint_size(it.height) + 1 + varint_size(it.left_zz) + 1 + varint_size(it.top_zz) +
+		          1 + varint_size(it.advance);
+		stack += 1 + varint_size(it.body) + it.body;
+		items.push_back(it);
+	}
+	std::vector<uint8_t> out(1 + varint_size(stack) + stack);
+	uint8_t *p = out.data();
+	*p++ = 0x0A;
+	p = put_varint(p, stack);
+	*p++ = 0x0A;
+	p = put_varint(p, name.size());
+	std::memcpy(p, name.data(), name.size());
+	p += name.size();
+	*p++ = 0x12;
+	p = put_varint(p, range.size());
+	std::memcpy(p, range.data(), range.size());
+	p += range.size();
+	for (const Item &it : items) {
+		*p++ = 0x1A;
+		p = put_varint(p, it.body);
+		*p++ = 0x08;
+		p = put_varint(p, it.id);
+		if (it.bitmap) {
+			*p++ = 0x12;
+			p = put_varint(p, it.bitmap_len);
+			std::memcpy(p, it.bitmap, it.bitmap_len);
+			p += it.bitmap_len;
+		}
+		*p++ = 0x18;
+		p = put_varint(p, it.width);
+		*p++ = 0x20;
+		p = put_varint(p, it.height);
+		*p++ = 0x28;
+		p = put_varint(p, it.left_zz);
+		*p++ = 0x30;
+		p = put_varint(p, it.top_zz);
+		*p++ = 0x38;
+		p = put_varint(p, it.advance);
+	}
+	return out;
+}
+
 // ---- decoder ----------------------------------------------------------------------------------------
 namespace {
 

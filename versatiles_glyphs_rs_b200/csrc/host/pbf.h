@@ -30,6 +30,11 @@ class PbfGlyphs {
 	std::vector<PbfGlyph> glyphs_;
 };
 
+// Same bytes as PbfGlyphs(name, range) + push(batch.take_glyph(i)) for i in [g0, g1) + into_vec(),
+// written straight from the batch's bitmap buffer (one allocation, one copy per bitmap).
+std::vector<uint8_t> encode_batch_range(const std::string &name, const std::string &range, const GlyphBatch &batch, size_t g0,
+                                        size_t g1);
+
 // Decoder for tests / the debug differ (mirror of commands/debug.rs:38-98's prost decode).
 bool pbf_decode(const uint8_t *data, size_t len, std::string &name, std::string &range, std::vector<PbfGlyph> &glyphs);
 
