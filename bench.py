@@ -319,12 +319,15 @@ def main():
     # ---- e2e: the reference-facing host API, host buffers in, PBF bytes out ----
     if not args.kernel_only:
         e2e_steps = args.e2e_steps or min(args.steps, 20)
-        for _ in range(2):
+        for _ in range(max(3, args.warmup)):
             manager.render_glyphs(V.Writer.new_memory(), renderer)
         barrier()
         t0 = time.perf_counter()
+        step_ms = []
         for _ in range(e2e_steps):
+            ts = time.perf_counter()
             st = manager.render_glyphs(V.Writer.new_memory(), renderer)
+            step_ms.append(1e3 * (time.perf_counter() - ts))
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         result["e2e"] = {
@@ -332,6 +335,7 @@ def main():
             "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(st.pixels),
             "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "pbf_bytes_per_step": int(st.pbf_bytes),
             "api": "FontManager.render_glyphs(Writer.new_memory(), Renderer.new_precise()): outlines -> H2D -> flatten+SDF kernel -> D2H -> PBF",
+            "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
             "host_phases_ms_last_step": {
                 "workers": st.workers, "submits": st.submits, "wall": st.wall_ns / 1e6,
                 "outline_per_worker": st.outline_ns / 1e6 / max(1, st.workers), "submit_per_worker": st.submit_ns / 1e6 / max(1, st.workers),

@@ -9,7 +9,7 @@ Loading fails loudly when they are missing: there is no Python or CPU fallback f
 import ctypes as C
 import os
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
+_HERE = os.environ.get("VGB200_LIBDIR") or os.path.dirname(os.path.abspath(__file__))  # override: kernel-variant experiments
 SDF_LIB_PATH = os.path.join(_HERE, "libb200sdf.so")
 HOST_LIB_PATH = os.path.join(_HERE, "libvgb200host.so")
 

@@ -113,16 +113,39 @@ struct Planned {
 	uint64_t cost;
 };
 
-// Split one glyph into rectangles of tiles with at most kMaxItems items each.
+// Work model: one item (tile) x one segment = one unit.  A CTA's latency is what bounds the kernel
+// when a batch has a few very heavy glyphs (thousands of segments), so no tile job may cost more
+// than its fair share of the batch: heavy glyphs are cut into smaller rectangles (never below
+// kMinItems items, so that staging — which every rectangle repeats — stays a small fraction).
+constexpr uint32_t kSMs = 148;          // B200
+constexpr uint32_t kJobsPerSM = 8;      // target number of equal-cost jobs per SM
+constexpr uint32_t kMinItems = 16;
+constexpr uint64_t kMinJobCost = 16384; // item x segment units
+
+inline uint64_t glyph_cost(uint32_t seg_cnt, uint32_t width, uint32_t height)
+{
+	using namespace b200sdf;
+	const uint64_t nx = (width + kTileW - 1) / kTileW, ny = (height + kTileH - 1) / kTileH;
+	return nx * ny * (uint64_t)(seg_cnt + 8);
+}
+
+inline uint32_t items_cap(uint64_t total_cost, uint32_t seg_cnt)
+{
+	const uint64_t cap = std::max<uint64_t>(total_cost / (kSMs * kJobsPerSM), kMinJobCost);
+	const uint64_t items = cap / (uint64_t)(seg_cnt + 8);
+	return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(items, kMinItems), (uint64_t)b200sdf::kMaxItems);
+}
+
+// Split one glyph into rectangles of tiles with at most max_items items each.
 void plan_glyph(uint32_t src_off, uint32_t seg_cnt, uint32_t width, uint32_t height, uint64_t out_off, uint32_t job,
-                std::vector<Planned> &out)
+                uint32_t max_items, std::vector<Planned> &out)
 {
 	using namespace b200sdf;
 	const uint32_t nx = (width + kTileW - 1) / kTileW, ny = (height + kTileH - 1) / kTileH;
 	// column strips only when one tile row alone exceeds the item budget
-	const uint32_t col_parts = (nx + kMaxItems - 1) / kMaxItems;
+	const uint32_t col_parts = (nx + max_items - 1) / max_items;
 	const uint32_t cols_per = (nx + col_parts - 1) / col_parts;
-	const uint32_t max_rows = std::max<uint32_t>(1, kMaxItems / cols_per);
+	const uint32_t max_rows = std::max<uint32_t>(1, max_items / cols_per);
 	const uint32_t row_parts = (ny + max_rows - 1) / max_rows;
 	const uint32_t rows_per = (ny + row_parts - 1) / row_parts;
 	for (uint32_t ty = 0; ty < ny; ty += rows_per)
@@ -165,9 +188,11 @@ void sort_plan(std::vector<Planned> &v)
 int plan_segments(const b200sdf_glyph_job *jobs, uint32_t n_jobs, uint32_t n_seg, uint64_t out_bytes, std::vector<Planned> &v,
                   uint64_t *pairs, const char **why)
 {
-	uint64_t pr = 0;
+	uint64_t pr = 0, total = 0;
 	v.clear();
 	v.reserve(n_jobs + n_jobs / 8 + 4);
+	for (uint32_t i = 0; i < n_jobs; ++i)
+		total += glyph_cost(jobs[i].seg_cnt, jobs[i].width, jobs[i].height);
 	for (uint32_t i = 0; i < n_jobs; ++i) {
 		const b200sdf_glyph_job &j = jobs[i];
 		if (!frame_ok(j.width, j.height, j.out_off, out_bytes, why))
@@ -177,7 +202,7 @@ int plan_segments(const b200sdf_glyph_job *jobs, uint32_t n_jobs, uint32_t n_seg
 			return B200SDF_E_ARG;
 		}
 		pr += (uint64_t)j.width * j.height * j.seg_cnt;
-		plan_glyph(j.seg_off, j.seg_cnt, j.width, j.height, j.out_off, B200SDF_NO_JOB, v);
+		plan_glyph(j.seg_off, j.seg_cnt, j.width, j.height, j.out_off, B200SDF_NO_JOB, items_cap(total, j.seg_cnt), v);
 	}
 	sort_plan(v);
 	if (pairs)
@@ -189,9 +214,11 @@ int plan_segments(const b200sdf_glyph_job *jobs, uint32_t n_jobs, uint32_t n_seg
 int plan_outlines(const b200sdf_outline_job *jobs, uint32_t n_jobs, const b200sdf_curve *curves, uint32_t n_curves,
                   uint32_t n_seg, uint64_t out_bytes, std::vector<Planned> &v, uint64_t *pairs, const char **why)
 {
-	uint64_t pr = 0;
+	uint64_t pr = 0, total = 0;
 	v.clear();
 	v.reserve(n_jobs + n_jobs / 8 + 4);
+	for (uint32_t i = 0; i < n_jobs; ++i)
+		total += glyph_cost(jobs[i].seg_cnt, jobs[i].width, jobs[i].height);
 	for (uint32_t i = 0; i < n_jobs; ++i) {
 		const b200sdf_outline_job &j = jobs[i];
 		if (!frame_ok(j.width, j.height, j.out_off, out_bytes, why))
@@ -201,7 +228,7 @@ int plan_outlines(const b200sdf_outline_job *jobs, uint32_t n_jobs, const b200sd
 				*why = "outline job (segments) range exceeds n_seg or seg_cnt != src_cnt";
 				return B200SDF_E_ARG;
 			}
-			plan_glyph(j.src_off, j.seg_cnt, j.width, j.height, j.out_off, B200SDF_NO_JOB, v);
+			plan_glyph(j.src_off, j.seg_cnt, j.width, j.height, j.out_off, B200SDF_NO_JOB, items_cap(total, j.seg_cnt), v);
 		} else if (j.kind == B200SDF_KIND_CURVES) {
 			if ((uint64_t)j.src_off + j.src_cnt > n_curves || (j.src_cnt == 0 && j.seg_cnt != 0)) {
 				*why = "outline job (curves) range exceeds n_curves";
@@ -223,7 +250,7 @@ int plan_outlines(const b200sdf_outline_job *jobs, uint32_t n_jobs, const b200sd
 					return B200SDF_E_ARG;
 				}
 			}
-			plan_glyph(j.src_off, j.seg_cnt, j.width, j.height, j.out_off, i, v);
+			plan_glyph(j.src_off, j.seg_cnt, j.width, j.height, j.out_off, i, items_cap(total, j.seg_cnt), v);
 		} else {
 			*why = "outline job with unknown kind";
 			return B200SDF_E_ARG;

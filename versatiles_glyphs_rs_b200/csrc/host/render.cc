@@ -231,9 +231,12 @@ bool HostBuffer::reserve(size_t bytes, size_t keep)
 {
 	if (bytes <= cap_)
 		return true;
-	size_t n = cap_ ? cap_ : 16384;
+	// Pinned allocations are slow and stall the whole CUDA context, so grow them in big steps: a pooled
+	// batch reaches its steady-state size after one or two uses.
+	const size_t step = pinned_ ? (size_t)256 << 10 : (size_t)16 << 10;
+	size_t n = cap_ ? cap_ : step;
 	while (n < bytes)
-		n += n / 2 + 16384;
+		n += n + step;
 	n = (n + 4095) & ~size_t(4095);
 	uint8_t *q = pinned_ ? (uint8_t *)b200sdf_alloc_pinned(n) : (uint8_t *)std::malloc(n);
 	if (!q)

@@ -11,14 +11,20 @@
 // f64, so flattened segments never touch HBM.
 //
 // One CTA (128 threads) renders one tile job = a rectangle of TW x TH pixel tiles of one glyph.
-// Segment source A (raw segments): the glyph's segments stream HBM -> shared memory in chunks
-// through the TMA unit (cp.async.bulk + mbarrier, double buffered).  Source B (curve records):
-// the glyph's curve list is bulk-copied once and each thread evaluates its segment's end points.
-// Either way each chunk becomes per-segment records (origin, direction, direction / |direction|^2)
-// once, then every thread evaluates its TW x TH pixels against the chunk.  Threads that would idle
-// because the rectangle has fewer than 128 items take a slice of the chunk's segments instead
-// (warp slices and lane slices); slices are merged with shared-memory atomicMin on the
-// non-negative float bit patterns.
+// Every thread owns one tile (TW x TH pixels, "item"); a warp owns a group of up to 32 items.
+// When the rectangle has fewer than 4 groups the warps split the glyph's segments between them
+// (warp slices), and lanes left over inside a group split a warp's segments further (lane
+// slices); slices are merged at the end with shared-memory atomicMin on the float bit patterns.
+//
+// Each WARP stages its own contiguous range of segments, 64 at a time, into a private shared
+// memory buffer — no CTA-wide barrier in the main loop:
+//   source A (raw segments): the TMA unit streams the warp's range HBM -> shared memory
+//            (cp.async.bulk + per-warp mbarrier, double buffered);
+//   source B (curve records): the glyph's curve list is bulk-copied once per CTA and each lane
+//            evaluates the end points of its segments in f64.
+// A staged segment becomes a record (negated origin and direction, direction / |direction|^2) and
+// scatters its row crossings; then the warp evaluates its pixels against the 64 records with
+// packed FP32 (FFMA2 / FADD2 / FMUL2: two horizontally adjacent pixels per instruction).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -26,11 +32,17 @@
 
 #include "../../include/b200sdf.h"
 
-#ifndef B200SDF_CHUNK
-#define B200SDF_CHUNK 256
+#ifndef B200SDF_MINI
+#define B200SDF_MINI 64 // segments a warp stages at a time
 #endif
-#ifndef B200SDF_FFMA2
-#define B200SDF_FFMA2 1
+#ifndef B200SDF_PACK
+#define B200SDF_PACK 2 // 0 = scalar FP32 pair loop, 1 = FFMA2 for the projection only, 2 = FFMA2/FMUL2 throughout
+#endif
+#ifndef B200SDF_UNROLL
+#define B200SDF_UNROLL 1 // pair-loop unroll over segments (measured: 1 beats 2 and 4 — register pressure)
+#endif
+#ifndef B200SDF_CURVE_SMEM
+#define B200SDF_CURVE_SMEM 256 // curve records (32 B) kept in shared memory per CTA
 #endif
 
 namespace b200sdf {
@@ -41,9 +53,11 @@ constexpr int kTileW = B200SDF_TILE_W;
 constexpr int kTileH = B200SDF_TILE_H;
 constexpr int kMaxItems = B200SDF_MAX_ITEMS;
 constexpr int kMaxPix = kMaxItems * kTileW * kTileH;
-constexpr int kChunk = B200SDF_CHUNK;        // segments per staged chunk
-constexpr int kCurveSmem = 2 * kChunk / 2;   // curve records (32 B) that fit the raw staging area
-static_assert(kTileW % 2 == 0, "FFMA2 path pairs pixels along x");
+constexpr int kMini = B200SDF_MINI;
+constexpr int kCurveSmem = B200SDF_CURVE_SMEM;
+constexpr int kUnroll = B200SDF_UNROLL;
+static_assert(kTileW % 2 == 0, "the packed-FP32 loop pairs pixels along x");
+static_assert(kMaxItems <= 32 * kWarps, "one item per thread");
 
 // ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA unit; SASS: UBLKCP / SYNCS) ----------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,48 +94,51 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// Per-segment records, laid out for the packed-FP32 pair loop: every value the loop needs as a
-// (v, v) pair is stored duplicated so one LDS.128 yields two ready-made 64-bit register pairs.
-struct __align__(16) SegX {
-	float nvx0, nvx1, ndx0, ndx1; // (-vx, -vx, -dx, -dx)
-};
-struct __align__(16) SegY {
-	float nvy0, nvy1, ndy0, ndy1; // (-vy, -vy, -dy, -dy)
+// Per-segment record of the pair loop (24 bytes).  Origin and direction are stored negated so the
+// loop needs only adds and fused multiply-adds.
+struct __align__(16) SegA {
+	float nvx, nvy, ndx, ndy; // -start, -(end - start)
 };
 struct __align__(8) SegN {
 	float dxn, dyn; // direction / |direction|^2  (0,0 for a zero-length segment: segment.rs:58-61)
 };
 
+struct WarpStage {
+	float4 raw[2][kMini]; // source A: TMA destination, double buffered
+	SegA recA[kMini];
+	SegN recN[kMini];
+};
+
 struct SharedStorage {
-	float4 raw[2][kChunk]; // staged b200sdf_segment chunks (TMA destination) / the glyph's curve list
-	SegX recX[2][kChunk];
-	SegY recY[2][kChunk];
-	SegN recN[2][kChunk];
-	int delta[kMaxPix];    // signed crossing deltas per pixel of the rectangle (winding sweep)
-	unsigned d2[kMaxPix];  // min squared distance per pixel, float bits
+	WarpStage warp[kWarps];
+	b200sdf_curve curves[kCurveSmem]; // source B: the glyph's curve list
+	int delta[kMaxPix];               // signed crossing deltas per pixel of the rectangle (winding sweep)
+	unsigned d2[kMaxPix];             // min squared distance per pixel, float bits
 	uint8_t obuf[kMaxPix + 32];
-	uint64_t bar[2];
+	uint64_t bar[kWarps][2];          // per-warp mbarriers of the raw double buffer
+	uint64_t curve_bar;
 };
 
 struct Rect {
 	int rx0, ry0, rw, rh;
 };
 
-// Turn one segment (origin-relative pixel units) into its records and scatter its row crossings.
+// Turn one segment (origin-relative pixel units) into its record and, if `scatter`, add its row
+// crossings to the winding deltas.
 // Crossing rule = renderer_precise.rs:44-50: upward  s.y <= py <  e.y -> sign +1
 //                                             downward s.y >  py >= e.y -> sign -1
 // and the sweep (:63-66) subtracts the sign of every crossing with x_c <= px, so a crossing adds
 // -sign to the first pixel column whose centre is >= x_c; columns left of the rectangle clamp to
 // its first column, columns right of it are dropped.
-__device__ __forceinline__ void stage_segment(const float4 s, SegX &rx, SegY &ry, SegN &rn, int *delta, const Rect &R)
+__device__ __forceinline__ void stage_segment(const float4 s, SegA &ra, SegN &rn, int *delta, const Rect &R, bool scatter)
 {
 	const float dx = s.z - s.x, dy = s.w - s.y;
 	const float l2 = dx * dx + dy * dy;
 	const float inv = l2 > 0.0f ? __frcp_rn(l2) : 0.0f;
-	rx = SegX{-s.x, -s.x, -dx, -dx};
-	ry = SegY{-s.y, -s.y, -dy, -dy};
+	ra = SegA{-s.x, -s.y, -dx, -dy};
 	rn = SegN{dx * inv, dy * inv};
-
+	if (!scatter)
+		return;
 	const float lo = fminf(s.y, s.w), hi = fmaxf(s.y, s.w);
 	// rows r (glyph space) whose centre r+0.5 lies in [lo, hi)
 	int r0 = (int)ceilf(lo - 0.5f), r1 = (int)ceilf(hi - 0.5f);
@@ -209,7 +226,6 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 	const int rpix = R.rw * R.rh;
 	const int n_items = (int)job.ntx * (int)job.nty;
 	const uint32_t S = job.seg_cnt;
-	const int n_chunks = (int)((S + kChunk - 1) / kChunk);
 	const bool from_curves = job.job != B200SDF_NO_JOB;
 
 	// source A: raw segments; source B: curve records of this glyph
@@ -225,11 +241,15 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 		g_ox = (double)oj.x0;
 		g_oy = (double)oj.y0;
 	}
-	const bool curves_in_smem = from_curves && n_curves <= (uint32_t)kCurveSmem;
+	const bool curves_in_smem = from_curves && n_curves != 0 && n_curves <= (uint32_t)kCurveSmem;
 
 	if (tid == 0) {
-		mbar_init(&sm.bar[0], 1);
-		mbar_init(&sm.bar[1], 1);
+		mbar_init(&sm.curve_bar, 1);
+		fence_mbar_init();
+	}
+	if (lane == 0) {
+		mbar_init(&sm.bar[warp][0], 1);
+		mbar_init(&sm.bar[warp][1], 1);
 		fence_mbar_init();
 	}
 	for (int i = tid; i < rpix; i += kThreads) {
@@ -237,35 +257,44 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 		sm.d2[i] = 0x7f800000u; // +inf
 	}
 	__syncthreads();
-	if (tid == 0) {
-		if (!from_curves) {
-			for (int c = 0; c < 2 && c < n_chunks; ++c) {
-				const uint32_t n = min((uint32_t)kChunk, S - (uint32_t)c * kChunk);
-				mbar_expect_tx(&sm.bar[c], n * 16u);
-				bulk_g2s(sm.raw[c], gsegs + (size_t)c * kChunk, n * 16u, &sm.bar[c]);
-			}
-		} else if (curves_in_smem && n_curves) {
-			mbar_expect_tx(&sm.bar[0], n_curves * 32u);
-			bulk_g2s(&sm.raw[0][0], gcurves, n_curves * 32u, &sm.bar[0]);
-		}
-	}
-	if (curves_in_smem && n_curves) {
-		mbar_wait(&sm.bar[0], 0);
-		gcurves = reinterpret_cast<const b200sdf_curve *>(&sm.raw[0][0]);
+	if (tid == 0 && curves_in_smem) {
+		mbar_expect_tx(&sm.curve_bar, n_curves * 32u);
+		bulk_g2s(sm.curves, gcurves, n_curves * 32u, &sm.curve_bar);
 	}
 
 	// ---- work split: item group per warp, then warp slices x lane slices over the segments ----
+	// A warp's scheduler (SM sub-partition) is fixed by its index, and so would be the role it plays if
+	// roles followed the index: rotate roles by the CTA index so that heavy and light roles of the CTAs
+	// resident on one SM spread over all four sub-partitions.
+	const int vw = (warp + (int)blockIdx.x) & 3;
 	const int n_groups = (n_items + 31) >> 5; // 1..4
-	const int wslices = n_groups == 1 ? 4 : (n_groups == 2 ? 2 : 1);
-	const int group = n_groups == 1 ? 0 : (n_groups == 2 ? (warp & 1) : warp);
-	const int wslice = n_groups == 1 ? warp : (n_groups == 2 ? (warp >> 1) : 0);
+	int wslices, group, wslice;
+	if (n_groups == 1) {
+		wslices = 4, group = 0, wslice = vw;
+	} else if (n_groups == 2) {
+		// the second group is a remainder; if it is small enough to run >= 3 lane slices, one warp
+		// takes it with all segments and the full group gets three warps (work 1/3 : <= 1/3 each)
+		const int rem = n_items - 32;
+		if (32 / rem >= 3) {
+			group = vw == 3 ? 1 : 0;
+			wslices = vw == 3 ? 1 : 3;
+			wslice = vw == 3 ? 0 : vw;
+		} else {
+			wslices = 2, group = vw & 1, wslice = vw >> 1;
+		}
+	} else {
+		wslices = 1, group = vw, wslice = 0;
+	}
 	const bool warp_active = group < n_groups;
 	const int g_items = warp_active ? min(32, n_items - group * 32) : 1; // items in my group
 	const int lslices = 32 / g_items;
 	const int item = group * 32 + lane % g_items;
 	const int lslice = (lane / g_items) % lslices;
-	const int T = wslices * lslices;           // total segment slices for my item
-	const int sid = wslice * lslices + lslice; // my slice
+	// this warp's contiguous share of the glyph's segments
+	const uint32_t s_begin = (uint32_t)(((uint64_t)S * (uint32_t)wslice) / (uint32_t)wslices);
+	const uint32_t s_end = (uint32_t)(((uint64_t)S * (uint32_t)(wslice + 1)) / (uint32_t)wslices);
+	// warps of different groups that share a slice stage the same segments; only group 0 scatters crossings
+	const bool scatter = group == 0;
 
 	const int tx = item % (int)job.ntx, ty = item / (int)job.ntx;
 	// pixel block origin relative to the glyph origin; pixel centres at +0.5
@@ -279,57 +308,66 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 		for (int j = 0; j < kTileW; ++j)
 			mn[r][j] = __int_as_float(0x7f800000);
 
-#if B200SDF_FFMA2
-	float2 pxp[kTileW / 2], pyp[kTileH];
+	float2 pxp[kTileW / 2];
 #pragma unroll
 	for (int j = 0; j < kTileW / 2; ++j)
 		pxp[j] = make_float2(px0 + (float)(2 * j), px0 + (float)(2 * j + 1));
-#pragma unroll
-	for (int r = 0; r < kTileH; ++r)
-		pyp[r] = make_float2(py0 + (float)r, py0 + (float)r);
-#endif
 
-	for (int c = 0; c < n_chunks; ++c) {
-		const int b = c & 1;
-		const int n = (int)min((uint32_t)kChunk, S - (uint32_t)c * kChunk);
-		if (!from_curves) {
-			mbar_wait(&sm.bar[b], (uint32_t)((c >> 1) & 1));
-			for (int i = tid; i < n; i += kThreads)
-				stage_segment(sm.raw[b][i], sm.recX[b][i], sm.recY[b][i], sm.recN[b][i], sm.delta, R);
-		} else {
-			for (int i = tid; i < n; i += kThreads) {
-				const float4 s = flatten_segment(gcurves, n_curves, (uint32_t)(c * kChunk + i), g_scale, g_dx, g_ox, g_oy);
-				stage_segment(s, sm.recX[b][i], sm.recY[b][i], sm.recN[b][i], sm.delta, R);
+	if (curves_in_smem) {
+		mbar_wait(&sm.curve_bar, 0);
+		gcurves = sm.curves;
+	}
+
+	if (warp_active && s_end > s_begin) {
+		WarpStage &ws = sm.warp[warp];
+		const uint32_t n_mini = (s_end - s_begin + kMini - 1) / kMini;
+		if (!from_curves && lane == 0) {
+			for (uint32_t m = 0; m < 2 && m < n_mini; ++m) {
+				const uint32_t n = min((uint32_t)kMini, s_end - (s_begin + m * kMini));
+				mbar_expect_tx(&sm.bar[warp][m], n * 16u);
+				bulk_g2s(ws.raw[m], gsegs + s_begin + m * kMini, n * 16u, &sm.bar[warp][m]);
 			}
 		}
-		__syncthreads(); // records of chunk c visible; raw[b] consumed; everyone is past chunk c-1
-		if (!from_curves && tid == 0 && c + 2 < n_chunks) {
-			const uint32_t n2 = min((uint32_t)kChunk, S - (uint32_t)(c + 2) * kChunk);
-			fence_proxy_async();
-			mbar_expect_tx(&sm.bar[b], n2 * 16u);
-			bulk_g2s(sm.raw[b], gsegs + (size_t)(c + 2) * kChunk, n2 * 16u, &sm.bar[b]);
-		}
-		if (warp_active) {
-			const SegX *__restrict__ X = sm.recX[b];
-			const SegY *__restrict__ Y = sm.recY[b];
-			const SegN *__restrict__ Nn = sm.recN[b];
-#pragma unroll 2
-			for (int i = sid; i < n; i += T) {
-#if B200SDF_FFMA2
-				// Packed-FP32 (FFMA2/FADD2/FMUL2) form: two horizontally adjacent pixels per instruction.
-				const float4 xr = *reinterpret_cast<const float4 *>(&X[i]);
-				const float4 yr = *reinterpret_cast<const float4 *>(&Y[i]);
+		for (uint32_t m = 0; m < n_mini; ++m) {
+			const uint32_t base = s_begin + m * kMini;
+			const int n = (int)min((uint32_t)kMini, s_end - base);
+			const int b = (int)(m & 1);
+			// ---- stage: every lane turns up to kMini/32 segments into records ----
+			if (!from_curves) {
+				mbar_wait(&sm.bar[warp][b], (m >> 1) & 1);
+				for (int i = lane; i < n; i += 32)
+					stage_segment(ws.raw[b][i], ws.recA[i], ws.recN[i], sm.delta, R, scatter);
+			} else {
+				for (int i = lane; i < n; i += 32) {
+					const float4 s = flatten_segment(gcurves, n_curves, base + (uint32_t)i, g_scale, g_dx, g_ox, g_oy);
+					stage_segment(s, ws.recA[i], ws.recN[i], sm.delta, R, scatter);
+				}
+			}
+			__syncwarp();
+			if (!from_curves && lane == 0 && m + 2 < n_mini) {
+				const uint32_t n2 = min((uint32_t)kMini, s_end - (base + 2 * kMini));
+				fence_proxy_async();
+				mbar_expect_tx(&sm.bar[warp][b], n2 * 16u);
+				bulk_g2s(ws.raw[b], gsegs + base + 2 * kMini, n2 * 16u, &sm.bar[warp][b]);
+			}
+			// ---- pair loop: my pixels x the staged records of my lane slice ----
+			const SegA *__restrict__ A = ws.recA;
+			const SegN *__restrict__ Nn = ws.recN;
+#pragma unroll kUnroll
+			for (int i = lslice; i < n; i += lslices) {
+				const float4 a = *reinterpret_cast<const float4 *>(&A[i]);
 				const SegN q = Nn[i];
-				const float2 nvx = make_float2(xr.x, xr.y), ndx = make_float2(xr.z, xr.w);
-				const float2 nvy = make_float2(yr.x, yr.y), ndy = make_float2(yr.z, yr.w);
+#if B200SDF_PACK >= 1
+				const float2 nvx = make_float2(a.x, a.x), ndx = make_float2(a.z, a.z), ndy = make_float2(a.w, a.w);
 				float2 pax[kTileW / 2];
 #pragma unroll
 				for (int j = 0; j < kTileW / 2; ++j)
 					pax[j] = __fadd2_rn(pxp[j], nvx);
 #pragma unroll
 				for (int r = 0; r < kTileH; ++r) {
-					const float2 pay = __fadd2_rn(pyp[r], nvy);
-					const float cr = pay.x * q.dyn;
+					const float pay1 = (py0 + (float)r) + a.y;
+					const float2 pay = make_float2(pay1, pay1);
+					const float cr = pay1 * q.dyn;
 #pragma unroll
 					for (int j = 0; j < kTileW / 2; ++j) {
 						float2 t;
@@ -337,34 +375,38 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 						t.y = __saturatef(fmaf(pax[j].y, q.dxn, cr));
 						const float2 qx = __ffma2_rn(t, ndx, pax[j]);
 						const float2 qy = __ffma2_rn(t, ndy, pay);
+#if B200SDF_PACK >= 2
 						const float2 d2 = __ffma2_rn(qx, qx, __fmul2_rn(qy, qy));
+#else
+						float2 d2;
+						d2.x = fmaf(qx.x, qx.x, qy.x * qy.x);
+						d2.y = fmaf(qx.y, qx.y, qy.y * qy.y);
+#endif
 						mn[r][2 * j] = fminf(mn[r][2 * j], d2.x);
 						mn[r][2 * j + 1] = fminf(mn[r][2 * j + 1], d2.y);
 					}
 				}
 #else
-				const SegX xr = X[i];
-				const SegY yr = Y[i];
-				const SegN q = Nn[i];
 				float pax[kTileW];
 #pragma unroll
 				for (int j = 0; j < kTileW; ++j)
-					pax[j] = (px0 + (float)j) + xr.nvx0;
+					pax[j] = (px0 + (float)j) + a.x;
 #pragma unroll
 				for (int r = 0; r < kTileH; ++r) {
-					const float pay = (py0 + (float)r) + yr.nvy0;
+					const float pay = (py0 + (float)r) + a.y;
 					const float cr = pay * q.dyn;
 #pragma unroll
 					for (int j = 0; j < kTileW; ++j) {
 						const float t = __saturatef(fmaf(pax[j], q.dxn, cr));
-						const float qx = fmaf(t, xr.ndx0, pax[j]);
-						const float qy = fmaf(t, yr.ndy0, pay);
+						const float qx = fmaf(t, a.z, pax[j]);
+						const float qy = fmaf(t, a.w, pay);
 						const float d2 = fmaf(qx, qx, qy * qy);
 						mn[r][j] = fminf(mn[r][j], d2);
 					}
 				}
 #endif
 			}
+			__syncwarp(); // records are overwritten by the next staging pass
 		}
 	}
 
