@@ -319,14 +319,16 @@ def main():
     # ---- e2e: the reference-facing host API, host buffers in, PBF bytes out ----
     if not args.kernel_only:
         e2e_steps = args.e2e_steps or min(args.steps, 20)
+        # the ranks of one box share its host cores: give each rank its share instead of oversubscribing
+        host_threads = max(1, (os.cpu_count() or 1) // world)
         for _ in range(max(3, args.warmup)):
-            manager.render_glyphs(V.Writer.new_memory(), renderer)
+            manager.render_glyphs(V.Writer.new_memory(), renderer, threads=host_threads)
         barrier()
         t0 = time.perf_counter()
         step_ms = []
         for _ in range(e2e_steps):
             ts = time.perf_counter()
-            st = manager.render_glyphs(V.Writer.new_memory(), renderer)
+            st = manager.render_glyphs(V.Writer.new_memory(), renderer, threads=host_threads)
             step_ms.append(1e3 * (time.perf_counter() - ts))
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -336,6 +338,7 @@ def main():
             "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "pbf_bytes_per_step": int(st.pbf_bytes),
             "api": "FontManager.render_glyphs(Writer.new_memory(), Renderer.new_precise()): outlines -> H2D -> flatten+SDF kernel -> D2H -> PBF",
             "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
+            "host_threads_per_rank": host_threads,
             "host_phases_ms_last_step": {
                 "workers": st.workers, "submits": st.submits, "wall": st.wall_ns / 1e6,
                 "outline_per_worker": st.outline_ns / 1e6 / max(1, st.workers), "submit_per_worker": st.submit_ns / 1e6 / max(1, st.workers),

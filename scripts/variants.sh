@@ -7,15 +7,15 @@ declare -A V=(
   [base]=""
   [pack0]="-DB200SDF_PACK=0"
   [pack1]="-DB200SDF_PACK=1"
-  [unroll1]="-DB200SDF_UNROLL=1"
-  [unroll4]="-DB200SDF_UNROLL=4"
+  [unroll2]="-DB200SDF_UNROLL=2"
   [mini32]="-DB200SDF_MINI=32"
   [mini128]="-DB200SDF_MINI=128"
+  [mini128p1]="-DB200SDF_MINI=128 -DB200SDF_PACK=1"
+  [mini96]="-DB200SDF_MINI=96"
   [t4x2]="-DB200SDF_TILE_W=4 -DB200SDF_TILE_H=2 -DB200SDF_MAX_ITEMS=128"
+  [t4x2p1]="-DB200SDF_TILE_W=4 -DB200SDF_TILE_H=2 -DB200SDF_MAX_ITEMS=128 -DB200SDF_PACK=1"
   [t8x2]="-DB200SDF_TILE_W=8 -DB200SDF_TILE_H=2"
-  [t2x4]="-DB200SDF_TILE_W=2 -DB200SDF_TILE_H=4 -DB200SDF_MAX_ITEMS=128"
-  [t4x4i128]="-DB200SDF_MAX_ITEMS=128"
-  [t4x4p0i128]="-DB200SDF_MAX_ITEMS=128 -DB200SDF_PACK=0"
+  [csm128]="-DB200SDF_CURVE_SMEM=128"
 )
 if [ "${1:-}" = "build" ]; then
   for n in "${!V[@]}"; do

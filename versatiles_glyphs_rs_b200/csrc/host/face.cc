@@ -466,7 +466,8 @@ void Face::outline_impl(Span g, int depth, const Transform &t, OutlineBuilder &b
 		if (pos > end)
 			return;
 		// expand flags (REPEAT 0x08)
-		std::vector<uint8_t> flags(n_points);
+		thread_local std::vector<uint8_t> flags; // scratch: no allocation per glyph (simple glyphs do not recurse)
+		flags.resize(n_points);
 		for (uint32_t k = 0; k < n_points;) {
 			if (pos >= end)
 				return;

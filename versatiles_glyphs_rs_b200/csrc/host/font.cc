@@ -7,7 +7,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <fstream>
+#include <functional>
 #include <sys/stat.h>
 #include <thread>
 
@@ -289,6 +291,64 @@ inline uint64_t now_ns()
 	return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
 	    .count();
 }
+
+// Persistent host workers (the reference keeps a rayon pool alive the same way): creating and joining
+// 16 threads costs more than rendering the whole Noto merge on the GPU.  run() is not re-entrant across
+// concurrent callers; they serialise on run_mu_.
+class WorkerPool {
+  public:
+	static WorkerPool &instance()
+	{
+		static WorkerPool *p = new WorkerPool(); // intentionally leaked: workers must outlive static destructors
+		return *p;
+	}
+	void run(int n, const std::function<void(int)> &fn)
+	{
+		std::lock_guard<std::mutex> serial(run_mu_);
+		{
+			std::unique_lock<std::mutex> lk(mu_);
+			while ((int)threads_.size() < n) {
+				const int id = (int)threads_.size();
+				threads_.emplace_back([this, id] { loop(id); });
+			}
+			fn_ = &fn;
+			want_ = n;
+			remaining_ = n;
+			++generation_;
+		}
+		cv_.notify_all();
+		std::unique_lock<std::mutex> lk(mu_);
+		done_cv_.wait(lk, [this] { return remaining_ == 0; });
+		fn_ = nullptr;
+	}
+
+  private:
+	void loop(int id)
+	{
+		uint64_t seen = 0;
+		for (;;) {
+			const std::function<void(int)> *fn;
+			{
+				std::unique_lock<std::mutex> lk(mu_);
+				cv_.wait(lk, [&] { return generation_ != seen && id < want_; });
+				seen = generation_;
+				fn = fn_;
+			}
+			(*fn)(id);
+			{
+				std::lock_guard<std::mutex> lk(mu_);
+				if (--remaining_ == 0)
+					done_cv_.notify_all();
+			}
+		}
+	}
+	std::mutex mu_, run_mu_;
+	std::condition_variable cv_, done_cv_;
+	std::vector<std::thread> threads_;
+	const std::function<void(int)> *fn_ = nullptr;
+	int want_ = 0, remaining_ = 0;
+	uint64_t generation_ = 0;
+};
 } // namespace
 
 bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::string *err, RenderStats *stats,
@@ -459,11 +519,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	if (workers == 1) {
 		work(0);
 	} else {
-		std::vector<std::thread> pool;
-		for (int w = 0; w < workers; ++w)
-			pool.emplace_back(work, w);
-		for (auto &t : pool)
-			t.join();
+		WorkerPool::instance().run(workers, work);
 	}
 	if (stats) {
 		*stats = RenderStats();

@@ -36,10 +36,12 @@ struct BBox {
 	Point max{-std::numeric_limits<double>::infinity(), -std::numeric_limits<double>::infinity()};
 	void include_point(const Point &p)
 	{
-		min.x = std::fmin(min.x, p.x);
-		min.y = std::fmin(min.y, p.y);
-		max.x = std::fmax(max.x, p.x);
-		max.y = std::fmax(max.y, p.y);
+		// f64::min / f64::max for non-NaN inputs (coordinates are never NaN); plain compares compile to
+		// minsd/maxsd instead of a libm call
+		min.x = p.x < min.x ? p.x : min.x;
+		min.y = p.y < min.y ? p.y : min.y;
+		max.x = p.x > max.x ? p.x : max.x;
+		max.y = p.y > max.y ? p.y : max.y;
 	}
 	// bbox.rs:56-58: empty only when there is no extent in BOTH axes
 	bool is_empty() const { return max.x <= min.x && max.y <= min.y; }

@@ -62,8 +62,10 @@ constexpr uint32_t MAX_DEPTH = 12;
 // recursion needs at most 17 + 10 + 24 = 51 significant bits, i.e. f64 arithmetic is exact.
 inline bool dyadic_ok(float v)
 {
-	const double w = (double)v * 1024.0;
-	return std::fabs((double)v) <= 32768.0 && w == std::floor(w);
+	if (!(v >= -32768.0f && v <= 32768.0f))
+		return false;                 // also rejects NaN
+	const float w = v * 1024.0f;      // exact (power of two), |w| <= 2^25 fits int32
+	return (float)(int32_t)w == w;
 }
 
 inline double lerp_exact(double a, double b, double t) { return a + t * (b - a); }
@@ -128,8 +130,11 @@ void OutlineRecorder::line_to(float x, float y)
 // monotone either side of its vertex t* = (s-c)/(s-2c+e), so only the grid points next to t* matter.
 void OutlineRecorder::axis_extrema(double s, double c, double e, uint32_t k, double &lo, double &hi) const
 {
+	// control point between the end points: the coordinate is monotone on [0,1], the end points bound it
+	if (k == 0 || (c >= std::fmin(s, e) && c <= std::fmax(s, e)))
+		return;
 	const double a = s - c * 2.0 + e;
-	if (k == 0 || a == 0.0)
+	if (a == 0.0)
 		return;
 	const double ts = (s - c) / a;
 	if (!(ts > 0.0 && ts < 1.0))

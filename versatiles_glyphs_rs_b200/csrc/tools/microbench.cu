@@ -34,6 +34,24 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float *out, const f
 					x[i] = fmaf(y[i], z[i], x[i]);
 				else if (MODE == 3) // FFMA two regs + uniform
 					x[i] = fmaf(x[i], y[i], b);
+				else if (MODE == 4) // FFMA, the two other operands shared by all 8 chains (operand reuse cache)
+					x[i] = fmaf(x[i], y[0], z[0]);
+				else if (MODE == 5) // FFMA x = x*y + x (2 distinct registers)
+					x[i] = fmaf(x[i], y[i], x[i]);
+				else if (MODE == 6) // FFMA reg, reg, immediate
+					x[i] = fmaf(x[i], y[i], 0.25f);
+				else if (MODE == 7) // FFMA reg, immediate, reg
+					x[i] = fmaf(x[i], 0.999f, z[i]);
+				else if (MODE == 8) // FMUL reg, reg
+					x[i] = x[i] * y[i];
+				else if (MODE == 9) // FADD reg, reg
+					x[i] = x[i] + y[i];
+				else if (MODE == 10) // FMNMX reg, reg (ALU pipe)
+					x[i] = fminf(x[i], y[i]);
+				else if (MODE == 11) // FFMA.SAT three registers
+					x[i] = __saturatef(fmaf(x[i], y[i], z[i]));
+				else if (MODE == 12) // FFMA one shared operand: x = x*y0 + z_i
+					x[i] = fmaf(x[i], y[0], z[i]);
 			}
 		}
 	}
@@ -208,6 +226,15 @@ int main()
 	RUN1(1, "FFMA  reg, reg, reg (3 distinct)");
 	RUN1(2, "FFMA  d = y*z + d");
 	RUN1(3, "FFMA  reg, reg, uniform");
+	RUN1(4, "FFMA  x*y0+z0 (two operands shared by chains)");
+	RUN1(12, "FFMA  x*y0+z_i (one operand shared)");
+	RUN1(5, "FFMA  x*y+x (2 distinct regs)");
+	RUN1(6, "FFMA  reg, reg, imm");
+	RUN1(7, "FFMA  reg, imm, reg");
+	RUN1(8, "FMUL  reg, reg");
+	RUN1(9, "FADD  reg, reg");
+	RUN1(10, "FMNMX reg, reg (ALU pipe)");
+	RUN1(11, "FFMA.SAT reg, reg, reg");
 	RUN2(0, "FFMA2 pair, uniform, uniform", 4);
 	RUN2(1, "FFMA2 pair, pair, pair", 4);
 	RUN2(2, "FFMA2 pair, scalar reg, pair", 4);
