@@ -292,6 +292,13 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
+    traffic = None  # DRAM bytes per launch of the SDF kernel from the committed ncu --set full capture (same workload only)
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if t.get("workload") == args.workload:
+            traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        pass
 
     result = {
         "metric": METRIC, "value": value, "unit": "glyphs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -305,7 +312,7 @@ def main():
         },
         "roofline": {
             "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-            "frac": achieved_tflops / fp32_peak_tflops, "traffic": None,
+            "frac": achieved_tflops / fp32_peak_tflops, "traffic": traffic,
             "peak_source": "FFMA-chain microbenchmark in this run (b200sdf_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
             "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": int(pairs), "kernel_ms": kernel_s * 1e3,
             "peak_ffma2_tflops": fp32x2_peak_tflops,
@@ -338,7 +345,7 @@ def main():
             "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "pbf_bytes_per_step": int(st.pbf_bytes),
             "api": "FontManager.render_glyphs(Writer.new_memory(), Renderer.new_precise()): outlines -> H2D -> flatten+SDF kernel -> D2H -> PBF",
             "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
-            "host_threads_per_rank": host_threads,
+            "host_threads_per_rank": host_threads, "step_ms": [round(x, 3) for x in step_ms],
             "host_phases_ms_last_step": {
                 "workers": st.workers, "submits": st.submits, "wall": st.wall_ns / 1e6,
                 "outline_per_worker": st.outline_ns / 1e6 / max(1, st.workers), "submit_per_worker": st.submit_ns / 1e6 / max(1, st.workers),

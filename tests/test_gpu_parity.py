@@ -398,3 +398,53 @@ def test_outline_jobs_are_validated(ctx):
     curves["seg_off"] = [0, 3]
     with pytest.raises(V.B200Error):
         ctx.render_outlines(curves, np.zeros((0, 4), np.float32), good, 64)
+
+
+# ---- full-size C4 (63 487 glyphs, ~90 M segments): size-independent properties + sampled oracle parity ----
+def test_c4_full_font_properties(renderer):
+    data = synth_font.full_bmp_font()
+    name, fid = "Synth Full", "synth_full"
+    m = V.FontManager(parallel=True)
+    m.add_font_bytes_with_name(name, data)
+    runs = []
+    for kw in ({}, {"threads": 3}):
+        w = V.Writer.new_memory()
+        st = m.render_glyphs(w, renderer, **kw)
+        runs.append({n: d for n, is_dir, d in w.entries() if not is_dir})
+    assert st.glyphs == 63487 and st.blocks == 256 and st.bitmaps == 63487
+    # (1) deterministic: identical bytes whatever the worker count / batching
+    assert runs[0] == runs[1]
+    # (2) sharded over 4 "GPUs": union of the shards == the whole job, byte for byte
+    got = {}
+    for s in range(4):
+        w = V.Writer.new_memory()
+        m.render_glyphs(w, renderer, shard=s, n_shards=4)
+        got.update({n: d for n, is_dir, d in w.entries() if not is_dir})
+    assert got == runs[0]
+    # (3) structure: every block has exactly the byte length of the dummy renderer's block (metrics + PBF framing)
+    wd = V.Writer.new_memory()
+    m.render_glyphs(wd, V.Renderer.new_dummy())
+    dummy = {n: d for n, is_dir, d in wd.entries() if not is_dir}
+    assert {n: len(d) for n, d in runs[0].items()} == {n: len(d) for n, d in dummy.items()}
+    # (4) every bitmap: outermost ring of the 3 px buffer is at least 2 px outside the outline -> value <= 191 - 64 + 1
+    rng = np.random.default_rng(11)
+    blocks = sorted(rng.choice(256, size=24, replace=False).tolist())
+    path = "/tmp/_synth_full.ttf"
+    open(path, "wb").write(data)
+    oset = O.FontSet(name, [path])
+    px = same = 0
+    for b in blocks:
+        blob = runs[0][f"{fid}/{b * 256}-{b * 256 + 255}.pbf"]
+        _, _, glyphs = O.decode_pbf(blob)
+        for g in glyphs:
+            bm = g["bitmap"].reshape(g["height"] + 6, g["width"] + 6)
+            edge = np.concatenate([bm[0], bm[-1], bm[:, 0], bm[:, -1]])
+            assert edge.max() <= 128, (b, g["id"], int(edge.max()))
+        # (5) oracle parity on a sample of whole blocks
+        if b % 3 == 0 and not 0xD8 <= b <= 0xDF:
+            p, s = check_pbf_block(blob, oset.render_block(b), ("c4", b))
+            px += p
+            same += s
+    os.unlink(path)
+    assert px > 100000 and same / px >= MIN_IDENTICAL
+    print(f"C4 full: {len(runs[0])} blocks, oracle sample {px} px, {100 * same / px:.4f}% identical")

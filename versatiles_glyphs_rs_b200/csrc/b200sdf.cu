@@ -43,6 +43,7 @@ struct b200sdf_ctx {
 	std::string err;
 	uint64_t launches = 0;
 	float *d_peak = nullptr;
+	size_t hwm[5] = {0, 0, 0, 0, 0}; // largest per-batch buffer sizes seen (segments, curves, jobs, tiles, bitmaps)
 };
 
 namespace {
@@ -321,13 +322,22 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 	if (e != cudaSuccess)
 		return release_slot(ctx, s, fail_cuda(ctx, e, "cudaSetDevice"));
 	const size_t n_tiles = plan.size();
+	// Size a slot's buffers to the largest request any slot of this context has seen: a slot then
+	// (re)allocates at most once after the workload's largest batch has shown up, instead of stalling
+	// the context with cudaFree/cudaMalloc whenever it first meets a bigger batch.
+	size_t need[5] = {(size_t)n_seg * sizeof(b200sdf_segment), (size_t)n_curves * sizeof(b200sdf_curve),
+	                  (size_t)n_ojobs * sizeof(b200sdf_outline_job), n_tiles * sizeof(b200sdf_tile_job), (size_t)out_bytes};
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		for (int k = 0; k < 5; ++k) {
+			ctx->hwm[k] = std::max(ctx->hwm[k], need[k]);
+			need[k] = ctx->hwm[k];
+		}
+	}
 	int rc;
-	if ((rc = grow_device(ctx, s.segs, (size_t)n_seg * sizeof(b200sdf_segment))) ||
-	    (rc = grow_device(ctx, s.curves, (size_t)n_curves * sizeof(b200sdf_curve))) ||
-	    (rc = grow_device(ctx, s.ojobs, (size_t)n_ojobs * sizeof(b200sdf_outline_job))) ||
-	    (rc = grow_device(ctx, s.tiles, n_tiles * sizeof(b200sdf_tile_job))) ||
-	    (rc = grow_device(ctx, s.out, (size_t)out_bytes)) ||
-	    (rc = grow_pinned(ctx, &s.h_tiles, &s.h_tiles_cap, n_tiles * sizeof(b200sdf_tile_job))))
+	if ((rc = grow_device(ctx, s.segs, need[0])) || (rc = grow_device(ctx, s.curves, need[1])) ||
+	    (rc = grow_device(ctx, s.ojobs, need[2])) || (rc = grow_device(ctx, s.tiles, need[3])) ||
+	    (rc = grow_device(ctx, s.out, need[4])) || (rc = grow_pinned(ctx, &s.h_tiles, &s.h_tiles_cap, need[3])))
 		return release_slot(ctx, s, rc);
 	b200sdf_tile_job *ht = reinterpret_cast<b200sdf_tile_job *>(s.h_tiles);
 	for (size_t i = 0; i < n_tiles; ++i)

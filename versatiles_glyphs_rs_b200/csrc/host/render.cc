@@ -232,16 +232,18 @@ HostBuffer::~HostBuffer()
 		std::free(p_);
 }
 
-bool HostBuffer::reserve(size_t bytes, size_t keep)
+bool HostBuffer::reserve(size_t bytes, size_t keep, bool exact)
 {
 	if (bytes <= cap_)
 		return true;
 	// Pinned allocations are slow and stall the whole CUDA context, so grow them in big steps: a pooled
-	// batch reaches its steady-state size after one or two uses.
+	// batch reaches its steady-state size after one or two uses.  (exact: sizing to a known capacity.)
 	const size_t step = pinned_ ? (size_t)256 << 10 : (size_t)16 << 10;
 	size_t n = cap_ ? cap_ : step;
 	while (n < bytes)
 		n += n + step;
+	if (exact)
+		n = bytes;
 	n = (n + 4095) & ~size_t(4095);
 	uint8_t *q = pinned_ ? (uint8_t *)b200sdf_alloc_pinned(n) : (uint8_t *)std::malloc(n);
 	if (!q)
@@ -447,6 +449,18 @@ bool GlyphBatch::add_glyph(const Face &face, uint32_t index)
 
 bool GlyphBatch::ensure_output() { return out_.reserve((size_t)out_bytes_ + 16, 0); }
 
+void GlyphBatch::capacities(size_t caps[4]) const
+{
+	caps[0] = jobs_.capacity(), caps[1] = segs_.capacity(), caps[2] = curves_.capacity(), caps[3] = out_.capacity();
+}
+
+void GlyphBatch::reserve_capacity(const size_t caps[4])
+{
+	// only called on an empty batch: nothing to keep
+	jobs_.reserve(caps[0], 0, true), segs_.reserve(caps[1], 0, true), curves_.reserve(caps[2], 0, true),
+	    out_.reserve(caps[3], 0, true);
+}
+
 PbfGlyph GlyphBatch::take_glyph(size_t i) const
 {
 	const BatchGlyph &b = glyphs_[i];
@@ -501,23 +515,35 @@ Renderer::~Renderer()
 
 std::unique_ptr<GlyphBatch> Renderer::acquire_batch() const
 {
+	std::unique_ptr<GlyphBatch> b;
+	size_t caps[4];
 	{
 		std::lock_guard<std::mutex> g(pool_mu_);
-		while (!pool_.empty()) {
-			std::unique_ptr<GlyphBatch> b = std::move(pool_.back());
+		while (!pool_.empty() && !b) {
+			b = std::move(pool_.back());
 			pool_.pop_back();
-			if (b->mode() == flatten_) {
-				b->clear();
-				return b;
-			}
+			if (b->mode() != flatten_)
+				b.reset();
 		}
+		for (int i = 0; i < 4; ++i)
+			caps[i] = hwm_[i];
 	}
-	return new_batch();
+	if (!b)
+		b = new_batch();
+	b->clear();
+	// Size every buffer to the largest any batch of this renderer ever needed: (pinned) allocations then
+	// happen once per pooled batch, up front, instead of whenever a batch first meets a big block.
+	b->reserve_capacity(caps);
+	return b;
 }
 
 void Renderer::release_batch(std::unique_ptr<GlyphBatch> b) const
 {
+	size_t caps[4];
+	b->capacities(caps);
 	std::lock_guard<std::mutex> g(pool_mu_);
+	for (int i = 0; i < 4; ++i)
+		hwm_[i] = std::max(hwm_[i], caps[i]);
 	if (pool_.size() < 128)
 		pool_.push_back(std::move(b));
 }

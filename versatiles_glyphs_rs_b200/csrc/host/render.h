@@ -140,7 +140,7 @@ class HostBuffer {
 	HostBuffer(const HostBuffer &) = delete;
 	HostBuffer &operator=(const HostBuffer &) = delete;
 	// keeps the first `keep` bytes
-	bool reserve(size_t bytes, size_t keep);
+	bool reserve(size_t bytes, size_t keep, bool exact = false);
 	uint8_t *data() { return p_; }
 	const uint8_t *data() const { return p_; }
 	size_t capacity() const { return cap_; }
@@ -195,6 +195,9 @@ class GlyphBatch {
 	uint64_t bitmap_bytes() const { return out_bytes_; }
 	uint64_t pairs() const { return pairs_; }
 	bool ensure_output(); // allocate the bitmap area (after the last add)
+	// buffer capacities in bytes (jobs, segments, curves, bitmaps) — the pool sizes new leases from them
+	void capacities(size_t caps[4]) const;
+	void reserve_capacity(const size_t caps[4]);
 	// PbfGlyph i with its bitmap copied out of the batch (valid after the batch was rendered)
 	PbfGlyph take_glyph(size_t i) const;
 
@@ -249,6 +252,7 @@ class Renderer {
 	Flatten flatten_ = Flatten::Device;
 	mutable std::mutex pool_mu_;
 	mutable std::vector<std::unique_ptr<GlyphBatch>> pool_;
+	mutable size_t hwm_[4] = {0, 0, 0, 0}; // largest buffer capacities any batch of this renderer reached
 };
 
 } // namespace vgb
