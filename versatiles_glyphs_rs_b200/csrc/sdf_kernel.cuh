@@ -41,6 +41,10 @@
 #ifndef B200SDF_UNROLL
 #define B200SDF_UNROLL 1 // pair-loop unroll over segments (measured: 1 beats 2 and 4 — register pressure)
 #endif
+#ifndef B200SDF_MIN_CTAS
+#define B200SDF_MIN_CTAS 7 // __launch_bounds__ minimum CTAs per SM: 72 registers (measured best of 4..9)
+#endif
+#define B200SDF_BOUNDS __launch_bounds__(128, B200SDF_MIN_CTAS)
 #ifndef B200SDF_CURVE_SMEM
 #define B200SDF_CURVE_SMEM 256 // curve records (32 B) kept in shared memory per CTA
 #endif
@@ -104,14 +108,19 @@ struct __align__(8) SegN {
 };
 
 struct WarpStage {
-	float4 raw[2][kMini]; // source A: TMA destination, double buffered
 	SegA recA[kMini];
 	SegN recN[kMini];
 };
 
+// A CTA reads either raw segments or curve records, never both: the two staging areas share storage.
+union SourceStage {
+	float4 raw[kWarps][2][kMini];     // source A: per-warp TMA destinations, double buffered
+	b200sdf_curve curves[kCurveSmem]; // source B: the glyph's curve list
+};
+
 struct SharedStorage {
 	WarpStage warp[kWarps];
-	b200sdf_curve curves[kCurveSmem]; // source B: the glyph's curve list
+	SourceStage src;
 	int delta[kMaxPix];               // signed crossing deltas per pixel of the rectangle (winding sweep)
 	unsigned d2[kMaxPix];             // min squared distance per pixel, float bits
 	uint8_t obuf[kMaxPix + 32];
@@ -203,7 +212,8 @@ __device__ __forceinline__ float4 flatten_segment(const b200sdf_curve *__restric
 	return s;
 }
 
-__global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__restrict__ segs,
+static_assert(kThreads == 128, "B200SDF_BOUNDS");
+__global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
                                                              const b200sdf_curve *__restrict__ curves,
                                                              const b200sdf_outline_job *__restrict__ ojobs,
                                                              const b200sdf_tile_job *__restrict__ jobs,
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 	__syncthreads();
 	if (tid == 0 && curves_in_smem) {
 		mbar_expect_tx(&sm.curve_bar, n_curves * 32u);
-		bulk_g2s(sm.curves, gcurves, n_curves * 32u, &sm.curve_bar);
+		bulk_g2s(sm.src.curves, gcurves, n_curves * 32u, &sm.curve_bar);
 	}
 
 	// ---- work split: item group per warp, then warp slices x lane slices over the segments ----
@@ -315,17 +325,18 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 
 	if (curves_in_smem) {
 		mbar_wait(&sm.curve_bar, 0);
-		gcurves = sm.curves;
+		gcurves = sm.src.curves;
 	}
 
 	if (warp_active && s_end > s_begin) {
 		WarpStage &ws = sm.warp[warp];
+		float4(*raw)[kMini] = sm.src.raw[warp];
 		const uint32_t n_mini = (s_end - s_begin + kMini - 1) / kMini;
 		if (!from_curves && lane == 0) {
 			for (uint32_t m = 0; m < 2 && m < n_mini; ++m) {
 				const uint32_t n = min((uint32_t)kMini, s_end - (s_begin + m * kMini));
 				mbar_expect_tx(&sm.bar[warp][m], n * 16u);
-				bulk_g2s(ws.raw[m], gsegs + s_begin + m * kMini, n * 16u, &sm.bar[warp][m]);
+				bulk_g2s(raw[m], gsegs + s_begin + m * kMini, n * 16u, &sm.bar[warp][m]);
 			}
 		}
 		for (uint32_t m = 0; m < n_mini; ++m) {
@@ -336,7 +347,7 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 			if (!from_curves) {
 				mbar_wait(&sm.bar[warp][b], (m >> 1) & 1);
 				for (int i = lane; i < n; i += 32)
-					stage_segment(ws.raw[b][i], ws.recA[i], ws.recN[i], sm.delta, R, scatter);
+					stage_segment(raw[b][i], ws.recA[i], ws.recN[i], sm.delta, R, scatter);
 			} else {
 				for (int i = lane; i < n; i += 32) {
 					const float4 s = flatten_segment(gcurves, n_curves, base + (uint32_t)i, g_scale, g_dx, g_ox, g_oy);
@@ -348,7 +359,7 @@ __global__ void __launch_bounds__(kThreads) sdf_tiles_kernel(const float4 *__res
 				const uint32_t n2 = min((uint32_t)kMini, s_end - (base + 2 * kMini));
 				fence_proxy_async();
 				mbar_expect_tx(&sm.bar[warp][b], n2 * 16u);
-				bulk_g2s(ws.raw[b], gsegs + base + 2 * kMini, n2 * 16u, &sm.bar[warp][b]);
+				bulk_g2s(raw[b], gsegs + base + 2 * kMini, n2 * 16u, &sm.bar[warp][b]);
 			}
 			// ---- pair loop: my pixels x the staged records of my lane slice ----
 			const SegA *__restrict__ A = ws.recA;

@@ -117,7 +117,34 @@ template <int PACK> __global__ void __launch_bounds__(128) body(float *out, cons
 	const float step = in[(tid + 8) & 1023] * 1e-3f;
 	for (int it = 0; it < iters; ++it) {
 		nvx += step, nvy -= step, ndx += step, ndy -= step; // 4 extra FADD per segment (a real kernel has 2 LDS instead)
-		if (PACK == 0) {
+		if (PACK == 10) {
+			// scalar, "operation-major": instructions that share two operands are emitted back to back
+			// (t and qy row by row, qx column by column) so only d2 reads two fresh registers
+			float pax[4], pay[4], t[4][4], m[4][4];
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				pax[j] = (px0 + (float)j) + nvx;
+#pragma unroll
+			for (int r = 0; r < 4; ++r) {
+				pay[r] = (py0 + (float)r) + nvy;
+				const float cr = pay[r] * dyn;
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+					t[r][j] = __saturatef(fmaf(pax[j], dxn, cr));
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const float qy = fmaf(t[r][j], ndy, pay[r]);
+					m[r][j] = qy * qy;
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+#pragma unroll
+				for (int r = 0; r < 4; ++r) {
+					const float qx = fmaf(t[r][j], ndx, pax[j]);
+					mn[r][j] = fminf(mn[r][j], fmaf(qx, qx, m[r][j]));
+				}
+		} else if (PACK == 0) {
 			float pax[4];
 #pragma unroll
 			for (int j = 0; j < 4; ++j)
@@ -251,6 +278,7 @@ int main()
 		       cyc * sms * 4 / (pairs / 32), pairs * 11 / (ms * 1e-3) / 1e12, pairs / (ms * 1e-3));
 	};
 	body_report("pair-loop body, scalar (PACK 0)", time_ms([&] { body<0><<<bblocks, 128>>>(d_out, d_in, it); }));
+	body_report("pair-loop body, scalar operation-major", time_ms([&] { body<10><<<bblocks, 128>>>(d_out, d_in, it); }));
 	body_report("pair-loop body, FFMA2 projection (PACK 1)", time_ms([&] { body<1><<<bblocks, 128>>>(d_out, d_in, it); }));
 	body_report("pair-loop body, FFMA2 throughout (PACK 2)", time_ms([&] { body<2><<<bblocks, 128>>>(d_out, d_in, it); }));
 	return 0;
