@@ -62,6 +62,17 @@ size_t vgb_flatten_cubic(const double s[2], const double c1[2], const double c2[
 double vgb_segment_sqdist(double vx, double vy, double wx, double wy, double px, double py);
 const char *vgb_name_to_id(const char *name, char *buf, size_t cap);        /* manager.rs:141-147 */
 
+/* ---- font naming + index files (not on the accelerated path; they name the output files) ---- */
+/* parse_font_name (font/parse_font_name.rs:214-293): family/style/width are written NUL-terminated
+ * into caller buffers of `cap` bytes each; returns 0, or -1 when a buffer is too small. */
+int vgb_parse_font_name(const char *family, const char *ps_name, char *out_family, char *out_style, uint16_t *out_weight,
+                        char *out_width, size_t cap);
+/* encode_codeblocks (font/index_files.rs:60-95): returns the length needed (excluding NUL) */
+size_t vgb_encode_codeblocks(const uint32_t *codepoints, size_t n, char *buf, size_t cap);
+/* FontMetadata (font/metadata.rs:20-64,84-129) of a parsed file; generate_name() in `generated` */
+int vgb_font_metadata(const vgb_font *f, char *name, char *family, char *style, uint16_t *weight, char *width,
+                      char *generated, size_t cap);
+
 /* ---- Renderer ---- */
 /* Renderer::new(dummy) (renderer.rs:25-31).  dummy=0 -> the CUDA renderer on `device` with
  * n_slots batches in flight (0 = default); NULL when no B200 is usable (no CPU fallback). */
@@ -112,6 +123,12 @@ int vgb_renderer_wait_batch(const vgb_renderer *r, uint64_t ticket);
 /* ---- Writer ---- */
 vgb_writer *vgb_writer_new_file(const char *folder); /* Writer::new_file, writer/mod.rs:35 */
 vgb_writer *vgb_writer_new_memory(void);             /* Writer::new_dummy + contents, writer/mod.rs:44 */
+vgb_writer *vgb_writer_new_tar(const char *path);    /* Writer::new_tar over a file, writer/mod.rs:27-33, writer/tar.rs */
+vgb_writer *vgb_writer_new_tar_memory(void);         /* TarWriter over a Vec<u8> (tar.rs tests) */
+int vgb_writer_write_file(vgb_writer *w, const char *filename, const uint8_t *bytes, uint64_t len); /* mod.rs:51-56 */
+int vgb_writer_write_directory(vgb_writer *w, const char *dirname);                                /* mod.rs:58-63 */
+int vgb_writer_finish(vgb_writer *w);                                                               /* mod.rs:67-73 */
+const uint8_t *vgb_writer_tar_bytes(const vgb_writer *w, uint64_t *len); /* the ustar stream of new_tar_memory */
 void vgb_writer_free(vgb_writer *w);
 uint32_t vgb_writer_entry_count(const vgb_writer *w);
 int vgb_writer_entry(const vgb_writer *w, uint32_t i, const char **name, int32_t *is_dir, const uint8_t **bytes,
@@ -143,6 +160,7 @@ int vgb_manager_render_block(const vgb_manager *m, const char *font_id, uint32_t
 int vgb_manager_render_glyphs(const vgb_manager *m, vgb_writer *w, const vgb_renderer *r, uint32_t shard,
                               uint32_t n_shards, int threads, vgb_stats *stats);
 int vgb_manager_write_index_json(const vgb_manager *m, vgb_writer *w);             /* manager.rs:128-131 */
+int vgb_manager_write_families_json(const vgb_manager *m, vgb_writer *w);          /* manager.rs:134-137 */
 
 /* ---- PBF decode (commands/debug.rs:60-79) ---- */
 /* Decodes one glyphs PBF; glyphs: malloc'd array (each bitmap malloc'd); returns count or <0. */

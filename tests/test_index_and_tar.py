@@ -1,0 +1,211 @@
+"""CPU tests (no GPU): the sink side of the path against the reference's own
+known-answer tests — parse_font_name vectors (tests/golden/, extracted from
+src/font/parse_font_name.rs), FontMetadata (src/font/metadata.rs:134-153), encode_codeblocks and
+font_families.json / index.json (src/font/index_files.rs:139-228, src/font/manager.rs:225-262), and
+the ustar writer (src/writer/tar.rs:180-300)."""
+import io
+import json
+import os
+import tarfile
+
+import pytest
+
+import oracle_lib as O
+import versatiles_glyphs_rs_b200 as V
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NOTO_REGULAR = os.path.join(O.NOTO_DIR, "Noto Sans - Regular.ttf")
+
+
+def test_parse_font_name_reference_vectors():
+    doc = json.load(open(os.path.join(GOLDEN, "parse_font_name_vectors.json")))
+    vectors = doc["vectors"]
+    assert len(vectors) == 243
+    for v in vectors:
+        got = V.parse_font_name(v["family"], v["ps_name"])
+        assert list(got) == v["expect"], (v, got)
+
+
+def test_parse_font_name_doc_example():
+    # parse_font_name.rs:203-212
+    assert V.parse_font_name("Open Sans SemiCondensed Light", "OpenSansSemiCondensed-LightItalic") == (
+        "Open Sans", "italic", 300, "semi-condensed")
+    assert V.parse_font_name("Foo Extra Condensed", "Foo") == ("Foo", "normal", 400, "extra-condensed")
+
+
+def test_font_metadata_goldens():
+    # metadata.rs:134-153
+    m = V.FontFileEntry(path=O.FIRA).metadata
+    assert (m["family"], m["generated_name"]) == ("Fira Sans", "Fira Sans Regular")
+    m = V.FontFileEntry(path=NOTO_REGULAR).metadata
+    assert (m["family"], m["generated_name"]) == ("Noto Sans", "Noto Sans Regular")
+    assert (m["style"], m["weight"], m["width"]) == ("normal", 400, "normal")
+
+
+def test_encode_codeblocks_goldens():
+    # index_files.rs:209-227
+    assert V.encode_codeblocks([]) == ""
+    assert V.encode_codeblocks([0xA3]) == "A"
+    assert V.encode_codeblocks([0x0, 0x1, 0x2, 0xF, 0x10]) == "0-1"
+    assert V.encode_codeblocks([0x0, 0x2, 0x1F, 0x40, 0xA0]) == "0-1,4,A"
+
+
+FAMILIES_GOLDEN = [  # index_files.rs:170-205
+    "[",
+    "  {",
+    "    \"name\": \"Fira Sans\",",
+    "    \"faces\": [",
+    "      {",
+    "        \"id\": \"fira_sans_regular\",",
+    "        \"style\": \"normal\",",
+    "        \"weight\": 400,",
+    "        \"width\": \"normal\",",
+    "        \"codeblocks\": \"0,2-7,A-2E,30-52,E3,1D4,1D6-1D7,1D9,1DB-1DC,1E0-204,207-208,20A-20B,210-212,215,219,21E,220-222,224,226,22C,232,23C,25A,25C,2C6-2C7,A78,A7A-A7B,AB5,FB0,FEF\"",
+    "      }",
+    "    ]",
+    "  },",
+    "  {",
+    "    \"name\": \"Noto Sans\",",
+    "    \"faces\": [",
+    "      {",
+    "        \"id\": \"noto_sans_regular\",",
+    "        \"style\": \"normal\",",
+    "        \"weight\": 400,",
+    "        \"width\": \"normal\",",
+    "        \"codeblocks\": \"0,2-7,A-52,90-97,10F,1AB-1AC,1C8,1D0-20C,20F-215,218,221,25C,2C6-2C7,2DE-2E5,A64-A69,A70-A7D,A7F,A8F,A92,AB3-AB6,FB0,FE0,FE2,FEF,FFF,1078-107B,1DF0-1DF1\"",
+    "      }",
+    "    ]",
+    "  }",
+    "]",
+]
+
+
+def _two_font_manager():
+    m = V.FontManager(parallel=False)
+    m.add_paths([O.FIRA, NOTO_REGULAR])  # add_path derives the id with parse_font_name (manager.rs:39-53)
+    assert m.font_ids() == ["fira_sans_regular", "noto_sans_regular"]
+    return m
+
+
+def test_families_and_index_json_goldens():
+    m = _two_font_manager()
+    w = V.Writer.new_memory()
+    m.write_families_json(w)
+    m.write_index_json(w)
+    files = {name: data for name, is_dir, data in w.entries()}
+    assert sorted(files) == ["font_families.json", "index.json"]
+    assert files["font_families.json"].decode().split("\n") == FAMILIES_GOLDEN
+    # index_files.rs:152-160
+    assert files["index.json"].decode().split("\n") == ["[", "  \"fira_sans_regular\",", "  \"noto_sans_regular\"", "]"]
+    # manager.rs:239-242 compares the dummy writer's whitespace-collapsed record
+    flat = "font_families.json: " + files["font_families.json"].decode().replace("\n", "").replace("  ", "")
+    assert flat[:64] == "font_families.json: [{\"name\": \"Fira Sans\",\"faces\": [{\"id\": \"fira"
+
+
+def test_families_json_groups_faces_by_family():
+    m = V.FontManager(parallel=False)
+    names = [n for n in sorted(os.listdir(O.NOTO_DIR)) if n.endswith(".ttf")][:4]
+    for n in names:
+        m.add_font_with_name(n[:-4], [os.path.join(O.NOTO_DIR, n)])
+    w = V.Writer.new_memory()
+    m.write_families_json(w)
+    doc = json.loads(w.entries()[0][2])
+    assert [f["name"] for f in doc] == sorted(f["name"] for f in doc)
+    assert sum(len(f["faces"]) for f in doc) == len(names)
+    for fam in doc:
+        for face in fam["faces"]:
+            assert set(face) == {"id", "style", "weight", "width", "codeblocks"}
+
+
+def _until_nul(b):
+    return b.split(b"\0", 1)[0].decode()
+
+
+def test_tar_long_filename_errors():
+    w = V.Writer.new_tar_memory()
+    with pytest.raises(V.B200Error, match="tar header field overflow"):
+        w.write_file("a" * 101, b"x")
+
+
+def test_tar_write_file():
+    w = V.Writer.new_tar_memory()
+    w.write_file("testfile.txt", b"hello tar")
+    w.finish()
+    out = w.tar_bytes()
+    assert len(out) == 2048
+    assert _until_nul(out[0:100]) == "testfile.txt"
+    assert out[156:157] == b"0"
+    assert out[512:521] == b"hello tar"
+    assert out[521:1024] == bytes(503)
+    w.finish()  # idempotent (writer/mod.rs:67-73)
+    assert len(w.tar_bytes()) == 2048
+
+
+def test_tar_write_directory():
+    w = V.Writer.new_tar_memory()
+    w.write_directory("testdir/")
+    w.finish()
+    out = w.tar_bytes()
+    assert len(out) == 1536
+    assert _until_nul(out[0:100]) == "testdir/"
+    assert out[156:157] == b"5"
+    assert out[512:] == bytes(1024)
+    with pytest.raises(V.B200Error, match="must end with a slash"):
+        V.Writer.new_tar_memory().write_directory("nodash")
+
+
+def test_tar_multiple_files_and_finish():
+    w = V.Writer.new_tar_memory()
+    w.write_file("file1.txt", b"foo")
+    w.write_file("file2.txt", b"barbaz")
+    w.finish()
+    out = w.tar_bytes()
+    assert len(out) == 3072
+    assert _until_nul(out[0:100]) == "file1.txt"
+    assert _until_nul(out[1024:1124]) == "file2.txt"
+    assert out[512:515] == b"foo" and out[1536:1542] == b"barbaz"
+
+
+def test_tar_real_decoder():
+    """tar.rs:259-289 with Python's tarfile in place of the `tar` crate."""
+    w = V.Writer.new_tar_memory()
+    w.write_file("file1.txt", b"content 1")
+    w.write_directory("folder/")
+    w.write_file("file2.txt", b"content 2")
+    w.write_file("folder/file3.txt", b"content 3")
+    w.finish()
+    out = w.tar_bytes()
+    tf = tarfile.open(fileobj=io.BytesIO(out))
+    members = tf.getmembers()
+    got = [(("Directory" if m.isdir() else "Regular"), m.name + ("/" if m.isdir() else ""), m.offset, m.offset_data, m.size)
+           for m in members]
+    assert got == [
+        ("Regular", "file1.txt", 0, 512, 9),
+        ("Directory", "folder/", 1024, 1536, 0),
+        ("Regular", "file2.txt", 1536, 2048, 9),
+        ("Regular", "folder/file3.txt", 2560, 3072, 9),
+    ]
+    assert [tf.extractfile(m).read() for m in members if m.isfile()] == [b"content 1", b"content 2", b"content 3"]
+    for m in members:
+        assert (m.mode, m.uid, m.gid) == (0o755 if m.isdir() else 0o644, 0, 0)
+
+
+def test_render_glyphs_into_tar_matches_directory_sink(tmp_path):
+    """The whole sink: dummy renderer -> tar file, every member equal to the in-memory writer's entry."""
+    m = _two_font_manager()
+    r = V.Renderer.new_dummy()
+    mem = V.Writer.new_memory()
+    m.render_glyphs(mem, r)
+    m.write_index_json(mem)
+    m.write_families_json(mem)
+    path = str(tmp_path / "glyphs.tar")
+    tw = V.Writer.new_tar(path)
+    m.render_glyphs(tw, r)
+    m.write_index_json(tw)
+    m.write_families_json(tw)
+    tw.finish()
+    want = {name: data for name, is_dir, data in mem.entries() if not is_dir}
+    tf = tarfile.open(path)
+    got = {mm.name: tf.extractfile(mm).read() for mm in tf.getmembers() if mm.isfile()}
+    assert got == want
+    assert sum(1 for n in got if n.endswith(".pbf")) == 512  # manager.rs:199: all 256 ranges per font

@@ -20,5 +20,7 @@ from .api import (  # noqa: F401
     Writer,
     decode_pbf,
     device_count,
+    encode_codeblocks,
     name_to_id,
+    parse_font_name,
 )

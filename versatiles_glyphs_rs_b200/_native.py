@@ -169,6 +169,9 @@ HOST_SYMBOLS = {
     "vgb_flatten_cubic": (C.c_size_t, [f64p, f64p, f64p, f64p, C.c_double, f64p, C.c_size_t]),
     "vgb_segment_sqdist": (C.c_double, [C.c_double] * 6),
     "vgb_name_to_id": (C.c_char_p, [C.c_char_p, C.c_char_p, C.c_size_t]),
+    "vgb_parse_font_name": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint16), C.c_char_p, C.c_size_t]),
+    "vgb_encode_codeblocks": (C.c_size_t, [u32p, C.c_size_t, C.c_char_p, C.c_size_t]),
+    "vgb_font_metadata": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint16), C.c_char_p, C.c_char_p, C.c_size_t]),
     "vgb_renderer_new": (C.c_void_p, [C.c_int, C.c_int, C.c_uint32]),
     "vgb_renderer_free": (None, [C.c_void_p]),
     "vgb_renderer_is_dummy": (C.c_int, [C.c_void_p]),
@@ -194,6 +197,12 @@ HOST_SYMBOLS = {
     "vgb_renderer_wait_batch": (C.c_int, [C.c_void_p, C.c_uint64]),
     "vgb_writer_new_file": (C.c_void_p, [C.c_char_p]),
     "vgb_writer_new_memory": (C.c_void_p, []),
+    "vgb_writer_new_tar": (C.c_void_p, [C.c_char_p]),
+    "vgb_writer_new_tar_memory": (C.c_void_p, []),
+    "vgb_writer_write_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint64]),
+    "vgb_writer_write_directory": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "vgb_writer_finish": (C.c_int, [C.c_void_p]),
+    "vgb_writer_tar_bytes": (u8p, [C.c_void_p, u64p]),
     "vgb_writer_free": (None, [C.c_void_p]),
     "vgb_writer_entry_count": (C.c_uint32, [C.c_void_p]),
     "vgb_writer_entry": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(u8p), u64p]),
@@ -208,6 +217,7 @@ HOST_SYMBOLS = {
     "vgb_manager_render_block": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.POINTER(u8p), u64p]),
     "vgb_manager_render_glyphs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(Stats)]),
     "vgb_manager_write_index_json": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vgb_manager_write_families_json": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vgb_pbf_decode": (C.c_int32, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.POINTER(Glyph))]),
     "vgb_glyphs_free": (None, [C.POINTER(Glyph), C.c_int32]),
 }

@@ -67,6 +67,17 @@ class FontFileEntry:
             self._h = None
 
     @property
+    def metadata(self) -> dict:
+        """FontMetadata (reference src/font/metadata.rs:20-64,84-129) + generate_name()."""
+        cap = 1024
+        bufs = [C.create_string_buffer(cap) for _ in range(5)]
+        weight = C.c_uint16()
+        if N.host.vgb_font_metadata(self._h, bufs[0], bufs[1], bufs[2], C.byref(weight), bufs[3], bufs[4], cap) != 0:
+            raise B200Error(N.host_error())
+        name, family, style, width, generated = (b.value.decode() for b in bufs)
+        return {"name": name, "family": family, "style": style, "weight": int(weight.value), "width": width,
+                "generated_name": generated}
+
     def units_per_em(self) -> int:
         return N.host.vgb_font_units_per_em(self._h)
 
@@ -263,8 +274,11 @@ class GlyphBatch:
 class Writer:
     """reference src/writer/mod.rs:27-96 (directory sink and in-memory recorder)."""
 
-    def __init__(self, folder: Optional[str] = None):
-        self._h = N.host.vgb_writer_new_file(folder.encode()) if folder else N.host.vgb_writer_new_memory()
+    def __init__(self, folder: Optional[str] = None, _handle=None):
+        if _handle is not None:
+            self._h = _handle
+        else:
+            self._h = N.host.vgb_writer_new_file(folder.encode()) if folder else N.host.vgb_writer_new_memory()
 
     @classmethod
     def new_file(cls, folder: str):
@@ -273,6 +287,33 @@ class Writer:
     @classmethod
     def new_memory(cls):
         return cls(None)
+
+    @classmethod
+    def new_tar(cls, path: str):
+        """reference src/writer/mod.rs:27-33 — a ustar stream (src/writer/tar.rs) written to `path`."""
+        return cls(_handle=N.host.vgb_writer_new_tar(path.encode()))
+
+    @classmethod
+    def new_tar_memory(cls):
+        """TarWriter over an in-memory buffer, as in the reference's src/writer/tar.rs tests."""
+        return cls(_handle=N.host.vgb_writer_new_tar_memory())
+
+    def write_file(self, filename: str, data: bytes):
+        if N.host.vgb_writer_write_file(self._h, filename.encode(), data, len(data)) != 0:
+            raise B200Error(N.host_error())
+
+    def write_directory(self, dirname: str):
+        if N.host.vgb_writer_write_directory(self._h, dirname.encode()) != 0:
+            raise B200Error(N.host_error())
+
+    def finish(self):
+        if N.host.vgb_writer_finish(self._h) != 0:
+            raise B200Error(N.host_error())
+
+    def tar_bytes(self) -> bytes:
+        n = C.c_uint64()
+        p = N.host.vgb_writer_tar_bytes(self._h, C.byref(n))
+        return C.string_at(p, n.value) if n.value else b""
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -369,6 +410,32 @@ class FontManager:
     def write_index_json(self, writer: Writer):
         if N.host.vgb_manager_write_index_json(self._h, writer._h) != 0:
             raise B200Error(N.host_error())
+
+
+    def write_families_json(self, writer: Writer):
+        """reference src/font/manager.rs:134-137 (font_families.json, src/font/index_files.rs:115-139)."""
+        if N.host.vgb_manager_write_families_json(self._h, writer._h) != 0:
+            raise B200Error(N.host_error())
+
+
+def parse_font_name(family: str, ps_name: str):
+    """(family, style, weight, width) — reference src/font/parse_font_name.rs:214-293."""
+    cap = 4 * (len(family) + len(ps_name)) + 64
+    fam, style, width = (C.create_string_buffer(cap) for _ in range(3))
+    weight = C.c_uint16()
+    if N.host.vgb_parse_font_name(family.encode(), ps_name.encode(), fam, style, C.byref(weight), width, cap) != 0:
+        raise B200Error(N.host_error())
+    return fam.value.decode(), style.value.decode(), int(weight.value), width.value.decode()
+
+
+def encode_codeblocks(codepoints) -> str:
+    """reference src/font/index_files.rs:60-95."""
+    cps = np.ascontiguousarray(codepoints, dtype=np.uint32)
+    p = cps.ctypes.data_as(N.u32p)
+    n = N.host.vgb_encode_codeblocks(p, cps.size, None, 0)
+    buf = C.create_string_buffer(n + 1)
+    N.host.vgb_encode_codeblocks(p, cps.size, buf, n + 1)
+    return buf.value.decode()
 
 
 def name_to_id(name: str) -> str:

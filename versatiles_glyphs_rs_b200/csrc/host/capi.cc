@@ -1,5 +1,6 @@
 // capi.cc — extern "C" surface of the host library (include/vgb200_host.h).
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <string>
 
@@ -167,6 +168,46 @@ const char *vgb_name_to_id(const char *name, char *buf, size_t cap)
 	return buf;
 }
 
+// ---- font naming + index files --------------------------------------------------------------------
+static bool put_str(char *buf, size_t cap, const std::string &v)
+{
+	if (!buf || v.size() + 1 > cap)
+		return false;
+	std::memcpy(buf, v.c_str(), v.size() + 1);
+	return true;
+}
+int vgb_parse_font_name(const char *family, const char *ps_name, char *out_family, char *out_style, uint16_t *out_weight,
+                        char *out_width, size_t cap)
+{
+	std::string fam, style, width;
+	uint16_t weight = 400;
+	parse_font_name(family, ps_name, fam, style, weight, width);
+	if (!put_str(out_family, cap, fam) || !put_str(out_style, cap, style) || !put_str(out_width, cap, width))
+		return fail("buffer too small");
+	*out_weight = weight;
+	return 0;
+}
+size_t vgb_encode_codeblocks(const uint32_t *codepoints, size_t n, char *buf, size_t cap)
+{
+	const std::string s = encode_codeblocks(std::vector<uint32_t>(codepoints, codepoints + n));
+	if (buf && cap) {
+		const size_t k = std::min(s.size(), cap - 1);
+		std::memcpy(buf, s.data(), k);
+		buf[k] = 0;
+	}
+	return s.size();
+}
+int vgb_font_metadata(const vgb_font *f, char *name, char *family, char *style, uint16_t *weight, char *width, char *generated,
+                      size_t cap)
+{
+	const FontMetadata &m = f->e->metadata;
+	if (!put_str(name, cap, m.name) || !put_str(family, cap, m.family) || !put_str(style, cap, m.style) ||
+	    !put_str(width, cap, m.width) || !put_str(generated, cap, m.generate_name()))
+		return fail("buffer too small");
+	*weight = m.weight;
+	return 0;
+}
+
 // ---- renderer --------------------------------------------------------------------------------------
 vgb_renderer *vgb_renderer_new(int dummy, int device, uint32_t n_slots)
 {
@@ -292,7 +333,37 @@ int vgb_renderer_wait_batch(const vgb_renderer *r, uint64_t ticket)
 // ---- writer ----------------------------------------------------------------------------------------
 vgb_writer *vgb_writer_new_file(const char *folder) { return new vgb_writer(Writer::new_file(folder)); }
 vgb_writer *vgb_writer_new_memory(void) { return new vgb_writer(Writer::new_memory()); }
-void vgb_writer_free(vgb_writer *w) { delete w; }
+vgb_writer *vgb_writer_new_tar(const char *path) { return new vgb_writer(Writer::new_tar(path)); }
+vgb_writer *vgb_writer_new_tar_memory(void) { return new vgb_writer(Writer::new_tar_memory()); }
+int vgb_writer_write_file(vgb_writer *w, const char *filename, const uint8_t *bytes, uint64_t len)
+{
+	std::string err;
+	return w->w.write_file(filename, bytes, (size_t)len, &err) ? 0 : fail(err);
+}
+int vgb_writer_write_directory(vgb_writer *w, const char *dirname)
+{
+	std::string err;
+	return w->w.write_directory(dirname, &err) ? 0 : fail(err);
+}
+int vgb_writer_finish(vgb_writer *w)
+{
+	std::string err;
+	return w->w.finish(&err) ? 0 : fail(err);
+}
+const uint8_t *vgb_writer_tar_bytes(const vgb_writer *w, uint64_t *len)
+{
+	*len = w->w.tar_bytes().size();
+	return w->w.tar_bytes().data();
+}
+void vgb_writer_free(vgb_writer *w)
+{
+	if (w) { // Drop for Writer (writer/mod.rs:83-96): best-effort finalisation
+		std::string err;
+		if (!w->w.finish(&err))
+			std::fprintf(stderr, "warning: writer finalize failed during drop: %s\n", err.c_str());
+	}
+	delete w;
+}
 uint32_t vgb_writer_entry_count(const vgb_writer *w) { return (uint32_t)w->w.entries().size(); }
 int vgb_writer_entry(const vgb_writer *w, uint32_t i, const char **name, int32_t *is_dir, const uint8_t **bytes, uint64_t *len)
 {
@@ -394,6 +465,12 @@ int vgb_manager_write_index_json(const vgb_manager *m, vgb_writer *w)
 {
 	std::string err;
 	return m->m.write_index_json(w->w, &err) ? 0 : fail(err);
+}
+
+int vgb_manager_write_families_json(const vgb_manager *m, vgb_writer *w)
+{
+	std::string err;
+	return m->m.write_families_json(w->w, &err) ? 0 : fail(err);
 }
 
 // ---- pbf decode ------------------------------------------------------------------------------------

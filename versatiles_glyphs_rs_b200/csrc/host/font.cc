@@ -25,8 +25,9 @@ std::unique_ptr<FontFileEntry> FontFileEntry::from_bytes(std::vector<uint8_t> da
 		return nullptr;
 	}
 	std::unique_ptr<FontFileEntry> e(new FontFileEntry());
-	e->codepoints = face->codepoints();
-	e->family = face->name(1);
+	e->metadata = FontMetadata::from_face(*face);
+	e->codepoints = e->metadata.codepoints;
+	e->family = e->metadata.name;
 	e->face = std::move(face);
 	return e;
 }
@@ -129,6 +130,72 @@ Writer Writer::new_file(const std::string &folder)
 }
 Writer Writer::new_memory() { return Writer(); }
 
+Writer Writer::new_tar_memory()
+{
+	Writer w;
+	w.to_tar_ = true;
+	return w;
+}
+
+Writer Writer::new_tar(const std::string &path)
+{
+	Writer w;
+	w.to_tar_ = true;
+	w.folder_ = path;
+	std::FILE *f = std::fopen(path.c_str(), "wb");
+	if (f)
+		w.tar_file_ = std::shared_ptr<std::FILE>(f, [](std::FILE *p) { std::fclose(p); });
+	return w;
+}
+
+bool Writer::tar_put(const uint8_t *p, size_t n, std::string *err)
+{
+	if (!folder_.empty()) {
+		if (!tar_file_ || (n && std::fwrite(p, 1, n, tar_file_.get()) != n)) {
+			if (err)
+				*err = "writing tar \"" + folder_ + "\" failed";
+			return false;
+		}
+		return true;
+	}
+	tar_.insert(tar_.end(), p, p + n);
+	return true;
+}
+
+// writer/tar.rs:49-99 — one 512-byte ustar header; octal fields are zero-filled and end with a space
+bool Writer::tar_header(const std::string &path, uint64_t size, uint64_t mode, char typeflag, std::string *err)
+{
+	uint8_t h[512];
+	std::memset(h, 0, sizeof(h));
+	if (path.size() > 100) { // tar.rs:160-172
+		if (err)
+			*err = "tar header field overflow: \"" + path + "\" is " + std::to_string(path.size()) + " bytes, max 100";
+		return false;
+	}
+	std::memcpy(h, path.data(), path.size());
+	auto octal = [&](size_t off, size_t len, uint64_t v) { // tar.rs:147-156
+		h[off + len - 1] = ' ';
+		for (size_t i = len - 1; i-- > 0;) {
+			h[off + i] = (uint8_t)('0' + (v & 7));
+			v >>= 3;
+		}
+	};
+	octal(100, 8, mode);
+	octal(108, 8, 0);
+	octal(116, 8, 0);
+	octal(124, 12, size);
+	octal(136, 12, (uint64_t)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::system_clock::now().time_since_epoch()).count());
+	h[156] = (uint8_t)typeflag;
+	std::memcpy(h + 257, "ustar\0", 6);
+	std::memcpy(h + 263, "00", 2);
+	std::memset(h + 148, ' ', 8);
+	uint32_t sum = 0;
+	for (uint8_t b : h)
+		sum += b;
+	octal(148, 8, sum);
+	return tar_put(h, sizeof(h), err);
+}
+
 static bool mkdirs(const std::string &path, std::string *err)
 {
 	std::string cur;
@@ -149,6 +216,13 @@ static bool mkdirs(const std::string &path, std::string *err)
 bool Writer::write_file(const std::string &filename, const uint8_t *bytes, size_t len, std::string *err)
 {
 	bytes_written_ += len;
+	if (to_tar_) { // writer/tar.rs:101-120
+		static const uint8_t zeros[512] = {0};
+		if (!tar_header(filename, len, 0644, '0', err) || !tar_put(bytes, len, err))
+			return false;
+		const size_t rem = len % 512;
+		return rem == 0 || tar_put(zeros, 512 - rem, err);
+	}
 	if (!to_disk_) {
 		Entry e;
 		e.name = filename;
@@ -172,7 +246,7 @@ bool Writer::write_file(const std::string &filename, const uint8_t *bytes, size_
 
 bool Writer::write_file(const std::string &filename, std::vector<uint8_t> &&bytes, std::string *err)
 {
-	if (to_disk_)
+	if (to_disk_ || to_tar_)
 		return write_file(filename, bytes.data(), bytes.size(), err);
 	bytes_written_ += bytes.size();
 	Entry e;
@@ -184,6 +258,14 @@ bool Writer::write_file(const std::string &filename, std::vector<uint8_t> &&byte
 
 bool Writer::write_directory(const std::string &dirname, std::string *err)
 {
+	if (to_tar_) { // writer/tar.rs:122-126
+		if (dirname.empty() || dirname.back() != '/') {
+			if (err)
+				*err = "dirname must end with a slash";
+			return false;
+		}
+		return tar_header(dirname, 0, 0755, '5', err);
+	}
 	if (!to_disk_) {
 		Entry e;
 		e.name = dirname;
@@ -194,9 +276,18 @@ bool Writer::write_directory(const std::string &dirname, std::string *err)
 	return mkdirs(folder_ + "/" + dirname, err);
 }
 
-bool Writer::finish(std::string *)
+bool Writer::finish(std::string *err)
 {
+	if (finished_) // writer/mod.rs:67-73
+		return true;
 	finished_ = true;
+	if (to_tar_) { // writer/tar.rs:133-137: two zero blocks
+		static const uint8_t zeros[1024] = {0};
+		if (!tar_put(zeros, sizeof(zeros), err))
+			return false;
+		if (tar_file_)
+			std::fflush(tar_file_.get());
+	}
 	return true;
 }
 
@@ -241,20 +332,8 @@ bool FontManager::add_path(const std::string &path, std::string *err)
 	std::unique_ptr<FontFileEntry> e = FontFileEntry::from_path(path, err);
 	if (!e)
 		return false;
-	// The reference derives "<family> [<width>] <weight> [<style>]" with the heuristics of
-	// font/parse_font_name.rs (out of this path's scope).  Subset: family name + "Regular" unless
-	// the family already ends in a weight word — enough for the fixtures; use
-	// add_font_with_name() (what `recurse` does with fonts.json) for exact control.
-	std::string name = e->family.empty() ? path.substr(path.find_last_of('/') + 1) : e->family;
-	static const char *weights[] = {"Thin", "ExtraLight", "Light", "Regular", "Medium", "SemiBold", "Bold", "ExtraBold", "Black"};
-	bool has_weight = false;
-	for (const char *w : weights) {
-		const size_t n = std::strlen(w);
-		if (name.size() > n && name.compare(name.size() - n, n, w) == 0 && name[name.size() - n - 1] == ' ')
-			has_weight = true;
-	}
-	if (!has_weight)
-		name += " Regular";
+	// manager.rs:42: id = name_to_id(metadata.generate_name())
+	const std::string name = e->metadata.generate_name();
 	fonts_[name_to_id(name)].add_file(std::move(e));
 	return true;
 }
@@ -283,6 +362,18 @@ bool FontManager::write_index_json(Writer &writer, std::string *err) const
 		s += "]";
 	}
 	return writer.write_file("index.json", (const uint8_t *)s.data(), s.size(), err);
+}
+
+bool FontManager::write_families_json(Writer &writer, std::string *err) const
+{
+	std::string e;
+	const std::string s = build_font_families_json(fonts_, &e);
+	if (s.empty()) {
+		if (err)
+			*err = e;
+		return false;
+	}
+	return writer.write_file("font_families.json", (const uint8_t *)s.data(), s.size(), err);
 }
 
 namespace {

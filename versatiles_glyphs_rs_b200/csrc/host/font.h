@@ -9,6 +9,7 @@
 #pragma once
 
 #include <array>
+#include <cstdio>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -24,10 +25,31 @@ namespace vgb {
 
 constexpr uint32_t GLYPH_BLOCK_SIZE = 256; // glyph_block.rs:7
 
+// font/metadata.rs:20-64
+struct FontMetadata {
+	std::string name;   // name id 1 as stored in the font
+	std::string family; // after parse_font_name stripped width / weight / script words
+	std::vector<uint32_t> codepoints;
+	std::string style = "normal";
+	uint16_t weight = 400;
+	std::string width = "normal";
+	std::string generate_name() const;              // "<family> [<width>] <Weight> [<style>]", metadata.rs:29-55
+	static FontMetadata from_face(const Face &face); // metadata.rs:84-129
+};
+// font/parse_font_name.rs:214-293
+void parse_font_name(const std::string &family, const std::string &ps_name, std::string &out_family, std::string &style,
+                     uint16_t &weight, std::string &width);
+// font/index_files.rs:60-95
+std::string encode_codeblocks(const std::vector<uint32_t> &codepoints);
+class FontWrapper;
+// font/index_files.rs:115-139; empty string + *err when a font has no files
+std::string build_font_families_json(const std::map<std::string, FontWrapper> &fonts, std::string *err);
+
 struct FontFileEntry {
 	std::unique_ptr<Face> face;
-	std::vector<uint32_t> codepoints; // FontMetadata.codepoints (metadata.rs:104-118)
-	std::string family;               // name id 1 (metadata.rs:97)
+	FontMetadata metadata;
+	std::vector<uint32_t> codepoints; // = metadata.codepoints (metadata.rs:104-118)
+	std::string family;               // = metadata.name, name id 1 (metadata.rs:97)
 	// file_entry.rs:32-56; nullptr + *err on unparsable data
 	static std::unique_ptr<FontFileEntry> from_bytes(std::vector<uint8_t> data, std::string *err);
 	static std::unique_ptr<FontFileEntry> from_path(const std::string &path, std::string *err);
@@ -84,6 +106,10 @@ class Writer {
   public:
 	static Writer new_file(const std::string &folder);
 	static Writer new_memory();
+	// Writer::new_tar (writer/mod.rs:27-33, writer/tar.rs): a ustar stream, to a file (path) or kept in memory
+	static Writer new_tar(const std::string &path);
+	static Writer new_tar_memory();
+	const std::vector<uint8_t> &tar_bytes() const { return tar_; } // new_tar_memory only
 	bool write_file(const std::string &filename, const uint8_t *bytes, size_t len, std::string *err);
 	bool write_file(const std::string &filename, std::vector<uint8_t> &&bytes, std::string *err); // no copy for the memory writer
 	bool write_directory(const std::string &dirname, std::string *err);
@@ -97,8 +123,12 @@ class Writer {
 	uint64_t bytes_written() const { return bytes_written_; }
 
   private:
-	bool to_disk_ = false;
+	bool tar_header(const std::string &path, uint64_t size, uint64_t mode, char typeflag, std::string *err);
+	bool tar_put(const uint8_t *p, size_t n, std::string *err);
+	bool to_disk_ = false, to_tar_ = false;
 	std::string folder_;
+	std::vector<uint8_t> tar_;
+	std::shared_ptr<std::FILE> tar_file_;
 	std::vector<Entry> entries_;
 	uint64_t bytes_written_ = 0;
 	bool finished_ = false;
@@ -129,6 +159,8 @@ class FontManager {
 	                   uint32_t shard = 0, uint32_t n_shards = 1, int threads = 0) const;
 	// manager.rs:128-131 (font ids as a JSON array)
 	bool write_index_json(Writer &writer, std::string *err) const;
+	// manager.rs:134-137 (font_families.json, index_files.rs:115-139)
+	bool write_families_json(Writer &writer, std::string *err) const;
 	static std::string name_to_id(const std::string &name); // manager.rs:141-147
 
   private:
