@@ -78,6 +78,7 @@ class FontFileEntry:
         return {"name": name, "family": family, "style": style, "weight": int(weight.value), "width": width,
                 "generated_name": generated}
 
+    @property
     def units_per_em(self) -> int:
         return N.host.vgb_font_units_per_em(self._h)
 
