@@ -45,6 +45,13 @@
 #define B200SDF_MIN_CTAS 7 // __launch_bounds__ minimum CTAs per SM: 72 registers (measured best of 4..9)
 #endif
 #define B200SDF_BOUNDS __launch_bounds__(128, B200SDF_MIN_CTAS)
+#ifndef B200SDF_ALGO
+// 1 = every pixel x every segment through the clamped projection (11 flop per pair);
+// 2 = the same minimum split into   min over vertices  (one FFMA + half an FMNMX3 per pair)
+//                                 + interiors of short segments, rasterised as bands
+//                                 + long segments (> 0.5 px) through the clamped projection.
+#define B200SDF_ALGO 2
+#endif
 #ifndef B200SDF_CURVE_SMEM
 #define B200SDF_CURVE_SMEM 256 // curve records (32 B) kept in shared memory per CTA
 #endif
@@ -95,6 +102,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 	             "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
 	             : "memory");
 }
+// three-input minimum (sm_100+: one FMNMX3 on the ALU pipe instead of two FMNMX)
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+	float r;
+	asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+	return r;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -107,10 +121,15 @@ struct __align__(8) SegN {
 	float dxn, dyn; // direction / |direction|^2  (0,0 for a zero-length segment: segment.rs:58-61)
 };
 
+constexpr int kVtx = 2 * kMini + 2; // source A stages both end points of a segment
 struct WarpStage {
-	SegA recA[kMini];
+	SegA recA[kMini]; // ALGO 2: only the long segments, compacted
 	SegN recN[kMini];
+#if B200SDF_ALGO == 2
+	float2 vtx[kVtx]; // negated vertices, read two at a time (LDS.128)
+#endif
 };
+constexpr float kLongL2 = 0.25f; // squared length above which a segment takes the clamped-projection loop
 
 // A CTA reads either raw segments or curve records, never both: the two staging areas share storage.
 union SourceStage {
@@ -139,15 +158,8 @@ struct Rect {
 // and the sweep (:63-66) subtracts the sign of every crossing with x_c <= px, so a crossing adds
 // -sign to the first pixel column whose centre is >= x_c; columns left of the rectangle clamp to
 // its first column, columns right of it are dropped.
-__device__ __forceinline__ void stage_segment(const float4 s, SegA &ra, SegN &rn, int *delta, const Rect &R, bool scatter)
+__device__ __forceinline__ void scatter_crossings(const float4 s, const float dx, const float dy, int *delta, const Rect &R)
 {
-	const float dx = s.z - s.x, dy = s.w - s.y;
-	const float l2 = dx * dx + dy * dy;
-	const float inv = l2 > 0.0f ? __frcp_rn(l2) : 0.0f;
-	ra = SegA{-s.x, -s.y, -dx, -dy};
-	rn = SegN{dx * inv, dy * inv};
-	if (!scatter)
-		return;
 	const float lo = fminf(s.y, s.w), hi = fmaxf(s.y, s.w);
 	// rows r (glyph space) whose centre r+0.5 lies in [lo, hi)
 	int r0 = (int)ceilf(lo - 0.5f), r1 = (int)ceilf(hi - 0.5f);
@@ -168,6 +180,61 @@ __device__ __forceinline__ void stage_segment(const float4 s, SegA &ra, SegN &rn
 			atomicAdd(&delta[(r - R.ry0) * R.rw + c], up ? -1 : 1);
 	}
 }
+
+__device__ __forceinline__ void stage_segment(const float4 s, SegA &ra, SegN &rn, int *delta, const Rect &R, bool scatter)
+{
+	const float dx = s.z - s.x, dy = s.w - s.y;
+	const float l2 = dx * dx + dy * dy;
+	const float inv = l2 > 0.0f ? __frcp_rn(l2) : 0.0f;
+	ra = SegA{-s.x, -s.y, -dx, -dy};
+	rn = SegN{dx * inv, dy * inv};
+	if (scatter)
+		scatter_crossings(s, dx, dy, delta, R);
+}
+
+#if B200SDF_ALGO == 2
+// Interior of a SHORT segment (0 < |d|^2 <= kLongL2).  A pixel p is nearer to the interior of the
+// segment than to its end points iff 0 < u < |d|^2 with u = (p - s).d  (segment.rs:62-70, 0 < t < 1);
+// its squared distance is then ((p - s) x d)^2 / |d|^2.  Those pixels form a band of width |d|
+// perpendicular to the segment: walk it along its major axis (rows for a flat segment, columns for a
+// steep one).  |d| <= 0.5 px makes the band at most 0.7072 px wide along the minor axis, so at most
+// ONE pixel centre per row (column) can lie in it.  A band pixel at perpendicular distance D sits
+// D |d_c| / |d| <= D beyond its foot point along the major axis, so rows (columns) whose centre is more
+// than 6 px past the segment hold only distances > 6 px, which saturate the output (191 - 32 d < 0.5).
+__device__ __forceinline__ void band_scatter(const float4 s, float dx, float dy, const float l2, const float inv, unsigned *d2,
+                                             const Rect &R)
+{
+	// minor axis "c" (x for a flat segment), major axis "m" (the band runs along it)
+	const bool steep = fabsf(dy) > fabsf(dx);
+	const float sc = steep ? s.y : s.x, sm_ = steep ? s.x : s.y;
+	const float ec_m = steep ? s.z : s.w; // end point, major coordinate
+	const float dc = steep ? dy : dx, dm = steep ? dx : dy;
+	const int c0 = steep ? R.ry0 : R.rx0, cn = steep ? R.rh : R.rw;
+	const int m0 = steep ? R.rx0 : R.ry0, mn = steep ? R.rw : R.rh;
+	const int stride_c = steep ? R.rw : 1, stride_m = steep ? 1 : R.rw;
+	const float slope = dm / dc;  // |slope| <= 1
+	const float w = l2 / dc;      // signed band width along c, |w| <= sqrt(2) |d|
+	const float wlo = fminf(w, 0.0f);
+	int ma = (int)ceilf(fminf(sm_, ec_m) - 6.5f), mb = (int)floorf(fmaxf(sm_, ec_m) + 5.5f); // centres within 6 px
+	ma = max(ma, m0);
+	mb = min(mb, m0 + mn - 1);
+#pragma unroll 1
+	for (int m = ma; m <= mb; ++m) {
+		const float pam = ((float)m + 0.5f) - sm_;
+		// u = pac * dc + pam * dm in (0, l2)  <=>  pac between -pam * slope and -pam * slope + w
+		const float lo = fmaf(-pam, slope, wlo);        // lower end of the pac interval
+		const float cf = ceilf(lo + (sc - 0.5f) - 1e-4f); // first centre at or after it (with slack)
+		const float pac = (cf + 0.5f) - sc;
+		const float u = fmaf(pac, dc, pam * dm);
+		const int c = (int)cf;
+		if (u > 0.0f && u < l2 && c >= c0 && c < c0 + cn) {
+			const float cr = fmaf(pac, dm, -(pam * dc));
+			const float v = (cr * cr) * inv;
+			atomicMin(&d2[(m - m0) * stride_m + (c - c0) * stride_c], __float_as_uint(v));
+		}
+	}
+}
+#endif
 
 // ---- device flattening (ring.rs:119-144 in closed form, exact for dyadic inputs) --------------------
 __device__ __forceinline__ double lerp_rn(double a, double b, double t)
@@ -344,6 +411,48 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 			const int n = (int)min((uint32_t)kMini, s_end - base);
 			const int b = (int)(m & 1);
 			// ---- stage: every lane turns up to kMini/32 segments into records ----
+#if B200SDF_ALGO == 2
+			if (!from_curves)
+				mbar_wait(&sm.bar[warp][b], (m >> 1) & 1);
+			int n_long = 0;
+			for (int i0 = 0; i0 < n; i0 += 32) { // uniform trip count: the long list is compacted by ballot
+				const int i = i0 + lane;
+				bool is_long = false;
+				float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+				float dx = 0.f, dy = 0.f, inv = 0.f;
+				if (i < n) {
+					s = from_curves ? flatten_segment(gcurves, n_curves, base + (uint32_t)i, g_scale, g_dx, g_ox, g_oy) : raw[b][i];
+					dx = s.z - s.x, dy = s.w - s.y;
+					const float l2 = dx * dx + dy * dy;
+					inv = l2 > 0.0f ? __frcp_rn(l2) : 0.0f;
+					is_long = l2 > kLongL2;
+					if (from_curves) {
+						ws.vtx[i] = make_float2(-s.x, -s.y); // rings are closed: every end is another segment's start
+					} else {
+						ws.vtx[2 * i] = make_float2(-s.x, -s.y);
+						ws.vtx[2 * i + 1] = make_float2(-s.z, -s.w);
+					}
+					if (scatter) {
+						scatter_crossings(s, dx, dy, sm.delta, R);
+						if (!is_long && l2 > 0.0f)
+							band_scatter(s, dx, dy, l2, inv, sm.d2, R);
+					}
+				}
+				const unsigned mask = __ballot_sync(0xffffffffu, is_long);
+				if (is_long) {
+					const int k = n_long + __popc(mask & ((1u << lane) - 1u));
+					ws.recA[k] = SegA{-s.x, -s.y, -dx, -dy};
+					ws.recN[k] = SegN{dx * inv, dy * inv};
+				}
+				n_long += __popc(mask);
+			}
+			int nv = from_curves ? n : 2 * n;
+			__syncwarp();
+			if ((nv & 1) && lane == 0)
+				ws.vtx[nv] = ws.vtx[nv - 1]; // pad to a whole pair
+			nv = (nv + 1) & ~1;
+#else
+			const int n_long = n;
 			if (!from_curves) {
 				mbar_wait(&sm.bar[warp][b], (m >> 1) & 1);
 				for (int i = lane; i < n; i += 32)
@@ -354,6 +463,7 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 					stage_segment(s, ws.recA[i], ws.recN[i], sm.delta, R, scatter);
 				}
 			}
+#endif
 			__syncwarp();
 			if (!from_curves && lane == 0 && m + 2 < n_mini) {
 				const uint32_t n2 = min((uint32_t)kMini, s_end - (base + 2 * kMini));
@@ -361,11 +471,51 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 				mbar_expect_tx(&sm.bar[warp][b], n2 * 16u);
 				bulk_g2s(raw[b], gsegs + base + 2 * kMini, n2 * 16u, &sm.bar[warp][b]);
 			}
+#if B200SDF_ALGO == 2
+			// ---- vertex loop: my pixels x the staged vertices of my lane slice, two vertices per step ----
+			{
+				const float4 *__restrict__ V4 = reinterpret_cast<const float4 *>(ws.vtx);
+				const int npair = nv >> 1;
+#pragma unroll 1
+				for (int i = lslice; i < npair; i += lslices) {
+					const float4 v = V4[i];
+					float d2a[kTileH][kTileW];
+					{
+						float pax[kTileW];
+#pragma unroll
+						for (int j = 0; j < kTileW; ++j)
+							pax[j] = (px0 + (float)j) + v.x;
+#pragma unroll
+						for (int r = 0; r < kTileH; ++r) {
+							const float pay = (py0 + (float)r) + v.y;
+							const float sy = pay * pay;
+#pragma unroll
+							for (int j = 0; j < kTileW; ++j)
+								d2a[r][j] = fmaf(pax[j], pax[j], sy);
+						}
+					}
+					{
+						float pax[kTileW];
+#pragma unroll
+						for (int j = 0; j < kTileW; ++j)
+							pax[j] = (px0 + (float)j) + v.z;
+#pragma unroll
+						for (int r = 0; r < kTileH; ++r) {
+							const float pay = (py0 + (float)r) + v.w;
+							const float sy = pay * pay;
+#pragma unroll
+							for (int j = 0; j < kTileW; ++j)
+								mn[r][j] = fmin3(mn[r][j], d2a[r][j], fmaf(pax[j], pax[j], sy));
+						}
+					}
+				}
+			}
+#endif
 			// ---- pair loop: my pixels x the staged records of my lane slice ----
 			const SegA *__restrict__ A = ws.recA;
 			const SegN *__restrict__ Nn = ws.recN;
 #pragma unroll kUnroll
-			for (int i = lslice; i < n; i += lslices) {
+			for (int i = lslice; i < n_long; i += lslices) {
 				const float4 a = *reinterpret_cast<const float4 *>(&A[i]);
 				const SegN q = Nn[i];
 #if B200SDF_PACK >= 1
