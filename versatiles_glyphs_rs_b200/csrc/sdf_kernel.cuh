@@ -52,6 +52,9 @@
 //                                 + long segments (> 0.5 px) through the clamped projection.
 #define B200SDF_ALGO 2
 #endif
+#ifndef B200SDF_VUNROLL
+#define B200SDF_VUNROLL 2 // vertex-loop unroll (pairs of vertices per trip)
+#endif
 #ifndef B200SDF_CURVE_SMEM
 #define B200SDF_CURVE_SMEM 256 // curve records (32 B) kept in shared memory per CTA
 #endif
@@ -67,7 +70,8 @@ constexpr int kMaxPix = kMaxItems * kTileW * kTileH;
 constexpr int kMini = B200SDF_MINI;
 constexpr int kCurveSmem = B200SDF_CURVE_SMEM;
 constexpr int kUnroll = B200SDF_UNROLL;
-static_assert(kTileW % 2 == 0, "the packed-FP32 loop pairs pixels along x");
+constexpr int kVUnroll = B200SDF_VUNROLL;
+static_assert(kTileW % 2 == 0 && kTileH % 2 == 0, "the packed-FP32 loops pair pixels along x and rows along y");
 static_assert(kMaxItems <= 32 * kWarps, "one item per thread");
 
 // ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA unit; SASS: UBLKCP / SYNCS) ----------------
@@ -214,23 +218,24 @@ __device__ __forceinline__ void band_scatter(const float4 s, float dx, float dy,
 	const int stride_c = steep ? R.rw : 1, stride_m = steep ? 1 : R.rw;
 	const float slope = dm / dc;  // |slope| <= 1
 	const float w = l2 / dc;      // signed band width along c, |w| <= sqrt(2) |d|
-	const float wlo = fminf(w, 0.0f);
 	int ma = (int)ceilf(fminf(sm_, ec_m) - 6.5f), mb = (int)floorf(fmaxf(sm_, ec_m) + 5.5f); // centres within 6 px
 	ma = max(ma, m0);
 	mb = min(mb, m0 + mn - 1);
+	// u = pac * dc + pam * dm in (0, l2)  <=>  pac between -pam * slope and -pam * slope + w;
+	// the first centre at or after the lower end (with slack) is  ceil(k0 - pam * slope)
+	const float k0 = (fminf(w, 0.0f) + (sc - 0.5f)) - 1e-4f;
+	float mf = (float)ma + 0.5f;
+	unsigned *cell = d2 + (ma - m0) * stride_m - c0 * stride_c;
 #pragma unroll 1
-	for (int m = ma; m <= mb; ++m) {
-		const float pam = ((float)m + 0.5f) - sm_;
-		// u = pac * dc + pam * dm in (0, l2)  <=>  pac between -pam * slope and -pam * slope + w
-		const float lo = fmaf(-pam, slope, wlo);        // lower end of the pac interval
-		const float cf = ceilf(lo + (sc - 0.5f) - 1e-4f); // first centre at or after it (with slack)
+	for (int m = ma; m <= mb; ++m, mf += 1.0f, cell += stride_m) {
+		const float pam = mf - sm_;
+		const float cf = ceilf(fmaf(-pam, slope, k0));
 		const float pac = (cf + 0.5f) - sc;
 		const float u = fmaf(pac, dc, pam * dm);
 		const int c = (int)cf;
-		if (u > 0.0f && u < l2 && c >= c0 && c < c0 + cn) {
+		if (u > 0.0f && u < l2 && (unsigned)(c - c0) < (unsigned)cn) {
 			const float cr = fmaf(pac, dm, -(pam * dc));
-			const float v = (cr * cr) * inv;
-			atomicMin(&d2[(m - m0) * stride_m + (c - c0) * stride_c], __float_as_uint(v));
+			atomicMin(cell + c * stride_c, __float_as_uint((cr * cr) * inv));
 		}
 	}
 }
@@ -389,6 +394,12 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 #pragma unroll
 	for (int j = 0; j < kTileW / 2; ++j)
 		pxp[j] = make_float2(px0 + (float)(2 * j), px0 + (float)(2 * j + 1));
+#if B200SDF_ALGO == 2
+	float2 pyp[kTileH / 2];
+#pragma unroll
+	for (int r = 0; r < kTileH / 2; ++r)
+		pyp[r] = make_float2(py0 + (float)(2 * r), py0 + (float)(2 * r + 1));
+#endif
 
 	if (curves_in_smem) {
 		mbar_wait(&sm.curve_bar, 0);
@@ -476,36 +487,33 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 			{
 				const float4 *__restrict__ V4 = reinterpret_cast<const float4 *>(ws.vtx);
 				const int npair = nv >> 1;
-#pragma unroll 1
+#pragma unroll kVUnroll
 				for (int i = lslice; i < npair; i += lslices) {
 					const float4 v = V4[i];
-					float d2a[kTileH][kTileW];
-					{
-						float pax[kTileW];
+					// two vertices a = (v.x, v.y), b = (v.z, v.w): the per-column / per-row terms with packed
+					// FP32 (half the issue slots), the 16 + 16 squared distances with scalar FFMA
+					float2 paxa[kTileW / 2], paxb[kTileW / 2], sya[kTileH / 2], syb[kTileH / 2];
 #pragma unroll
-						for (int j = 0; j < kTileW; ++j)
-							pax[j] = (px0 + (float)j) + v.x;
-#pragma unroll
-						for (int r = 0; r < kTileH; ++r) {
-							const float pay = (py0 + (float)r) + v.y;
-							const float sy = pay * pay;
-#pragma unroll
-							for (int j = 0; j < kTileW; ++j)
-								d2a[r][j] = fmaf(pax[j], pax[j], sy);
-						}
+					for (int j = 0; j < kTileW / 2; ++j) {
+						paxa[j] = __fadd2_rn(pxp[j], make_float2(v.x, v.x));
+						paxb[j] = __fadd2_rn(pxp[j], make_float2(v.z, v.z));
 					}
-					{
-						float pax[kTileW];
 #pragma unroll
-						for (int j = 0; j < kTileW; ++j)
-							pax[j] = (px0 + (float)j) + v.z;
+					for (int r = 0; r < kTileH / 2; ++r) {
+						const float2 pa = __fadd2_rn(pyp[r], make_float2(v.y, v.y));
+						const float2 pb = __fadd2_rn(pyp[r], make_float2(v.w, v.w));
+						sya[r] = __fmul2_rn(pa, pa);
+						syb[r] = __fmul2_rn(pb, pb);
+					}
 #pragma unroll
-						for (int r = 0; r < kTileH; ++r) {
-							const float pay = (py0 + (float)r) + v.w;
-							const float sy = pay * pay;
+					for (int r = 0; r < kTileH; ++r) {
+						const float ya = (r & 1) ? sya[r >> 1].y : sya[r >> 1].x;
+						const float yb = (r & 1) ? syb[r >> 1].y : syb[r >> 1].x;
 #pragma unroll
-							for (int j = 0; j < kTileW; ++j)
-								mn[r][j] = fmin3(mn[r][j], d2a[r][j], fmaf(pax[j], pax[j], sy));
+						for (int j = 0; j < kTileW; ++j) {
+							const float xa = (j & 1) ? paxa[j >> 1].y : paxa[j >> 1].x;
+							const float xb = (j & 1) ? paxb[j >> 1].y : paxb[j >> 1].x;
+							mn[r][j] = fmin3(mn[r][j], fmaf(xa, xa, ya), fmaf(xb, xb, yb));
 						}
 					}
 				}
