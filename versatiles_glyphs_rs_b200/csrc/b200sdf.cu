@@ -330,7 +330,12 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 	{
 		std::lock_guard<std::mutex> g(ctx->mu);
 		for (int k = 0; k < 5; ++k) {
-			ctx->hwm[k] = std::max(ctx->hwm[k], need[k]);
+			// ... rounded up to a power of two (>= 64 KiB): batch composition varies from call to call
+			// (dynamic scheduling), and a mark that creeps up by a few bytes would stall the device again
+			size_t r = (size_t)64 << 10;
+			while (r < need[k])
+				r <<= 1;
+			ctx->hwm[k] = std::max(ctx->hwm[k], r);
 			need[k] = ctx->hwm[k];
 		}
 	}

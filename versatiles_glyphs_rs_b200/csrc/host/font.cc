@@ -6,6 +6,7 @@
 #include <cerrno>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <condition_variable>
 #include <fstream>
@@ -51,10 +52,10 @@ std::string GlyphBlock::range() const
 }
 std::string GlyphBlock::filename() const { return range() + ".pbf"; }
 
-void GlyphBlock::append_to_batch(GlyphBatch &batch) const
+void GlyphBlock::append_to_batch(GlyphBatch &batch, uint32_t slot0, uint32_t slot1) const
 {
-	for (uint32_t i = 0; i < GLYPH_BLOCK_SIZE; ++i) {
-		const FontFileEntry *f = fonts_[i];
+	for (uint32_t i = slot0; i < slot1 && i < GLYPH_BLOCK_SIZE; ++i) {
+		const FontFileEntry *f = font_of((uint8_t)i);
 		if (f)
 			batch.add_glyph(*f->face, start_index_ + i); // false = None = skipped (glyph_block.rs:74-76)
 	}
@@ -111,13 +112,21 @@ std::vector<GlyphBlock> FontWrapper::get_blocks() const
 	blocks.reserve(BMP_BLOCK_COUNT);
 	for (uint32_t i = 0; i < BMP_BLOCK_COUNT; ++i)
 		blocks.emplace_back(i * GLYPH_BLOCK_SIZE);
+	std::vector<GlyphBlock *> ptrs(BMP_BLOCK_COUNT);
+	for (uint32_t i = 0; i < BMP_BLOCK_COUNT; ++i)
+		ptrs[i] = &blocks[i];
+	assign_blocks(ptrs.data());
+	return blocks;
+}
+
+void FontWrapper::assign_blocks(GlyphBlock *const *blocks) const
+{
 	for (const auto &file : files_)
 		for (uint32_t cp : file->codepoints) {
 			if (cp > 0xFFFF)
 				continue;
-			blocks[cp / GLYPH_BLOCK_SIZE].set_glyph_font((uint8_t)(cp % GLYPH_BLOCK_SIZE), file.get());
+			blocks[cp / GLYPH_BLOCK_SIZE]->set_glyph_font((uint8_t)(cp % GLYPH_BLOCK_SIZE), file.get());
 		}
-	return blocks;
 }
 
 // ---- Writer ------------------------------------------------------------------------------------------
@@ -445,30 +454,70 @@ class WorkerPool {
 bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::string *err, RenderStats *stats,
                                 uint32_t shard, uint32_t n_shards, int threads) const
 {
-	struct Todo {
-		const std::string *name;
+	// A task is a slot range of one block holding at most kPartGlyphs glyphs: full blocks are split so that
+	// no worker is stuck recording 256 outlines while the others (and the GPU) run dry.  The parts of a
+	// block are encoded independently (Fontstack.glyphs entries) and the worker that finishes the last
+	// one assembles and writes the file.
+	constexpr size_t kPartGlyphs = 32;
+	struct BlockState {
+		const std::string *name = nullptr;
 		GlyphBlock block;
+		std::vector<std::vector<uint8_t>> parts;
+		std::atomic<uint32_t> remaining{0};
+	};
+	struct Todo {
+		BlockState *bs;
+		uint32_t part, slot0, slot1, glyphs;
 	};
 	const uint64_t t_begin = now_ns();
 	if (n_shards == 0)
 		n_shards = 1;
+	constexpr uint32_t kBlocks = 0x10000 / GLYPH_BLOCK_SIZE; // wrapper.rs:53-76: always 256 BMP blocks per font
+	std::vector<std::unique_ptr<BlockState[]>> fonts_blocks;
 	std::vector<Todo> tasks;
+	tasks.reserve(fonts_.size() * kBlocks + 64);
 	uint32_t index = 0;
 	size_t total_glyphs = 0;
 	for (const auto &kv : fonts_) {
 		if (!writer.write_directory(kv.first + "/", err))
 			return false;
-		for (GlyphBlock &b : kv.second.get_blocks()) {
-			if (index++ % n_shards == shard) {
-				total_glyphs += b.len();
-				tasks.push_back(Todo{&kv.first, std::move(b)});
+		fonts_blocks.emplace_back(new BlockState[kBlocks]);
+		BlockState *bsv = fonts_blocks.back().get();
+		GlyphBlock *ptrs[kBlocks];
+		for (uint32_t i = 0; i < kBlocks; ++i) {
+			bsv[i].name = &kv.first;
+			bsv[i].block.reset(i * GLYPH_BLOCK_SIZE);
+			ptrs[i] = &bsv[i].block;
+		}
+		kv.second.assign_blocks(ptrs); // = get_blocks(), written in place
+		for (uint32_t i = 0; i < kBlocks; ++i) {
+			if (index++ % n_shards != shard)
+				continue;
+			BlockState *bs = &bsv[i];
+			total_glyphs += bs->block.len();
+			uint32_t part = 0, slot0 = 0, count = 0;
+			if (bs->block.len() > kPartGlyphs) {
+				for (uint32_t k = 0; k < GLYPH_BLOCK_SIZE; ++k) {
+					if (!bs->block.font_of((uint8_t)k))
+						continue;
+					if (count == kPartGlyphs) {
+						tasks.push_back(Todo{bs, part++, slot0, k, count});
+						slot0 = k, count = 0;
+					}
+					++count;
+				}
+			} else {
+				count = (uint32_t)bs->block.len(); // small and empty blocks: one part
 			}
+			tasks.push_back(Todo{bs, part++, slot0, GLYPH_BLOCK_SIZE, count});
+			bs->parts.resize(part);
+			bs->remaining.store(part, std::memory_order_relaxed);
 		}
 	}
 
-	// Fullest blocks first: dynamic scheduling then ends with the cheap ones (the reference's rayon
+	// Fullest parts first: dynamic scheduling then ends with the cheap ones (the reference's rayon
 	// par_iter makes no order promise either, manager.rs:117-118).
-	std::stable_sort(tasks.begin(), tasks.end(), [](const Todo &a, const Todo &b) { return a.block.len() > b.block.len(); });
+	std::stable_sort(tasks.begin(), tasks.end(), [](const Todo &a, const Todo &b) { return a.glyphs > b.glyphs; });
 
 	int workers = 1;
 	if (parallel_) {
@@ -492,17 +541,44 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			*err = msg;
 	};
 
+	// VGB_TRACE=1: print a per-worker timeline (us since the call began) to stderr — diagnostics only
+	const bool trace = std::getenv("VGB_TRACE") != nullptr;
+	std::vector<std::vector<std::pair<char, uint64_t>>> events((size_t)workers);
+	const uint64_t t_setup = now_ns();
+
 	auto work = [&](int wid) {
 		RenderStats &st = per_worker[(size_t)wid];
-		auto emit = [&](const Todo &todo, std::vector<uint8_t> &&data) -> bool {
+		auto &ev = events[(size_t)wid];
+		auto mark = [&](char what) {
+			if (trace)
+				ev.emplace_back(what, now_ns() - t_begin);
+		};
+		mark('B');
+		// one finished part: encode its glyph entries; the last part of a block assembles and writes the file
+		auto finish_part = [&](const Todo &todo, const GlyphBatch &batch, size_t g0, size_t g1) -> bool {
+			BlockState &bs = *todo.bs;
+			uint64_t t0 = now_ns();
+			std::vector<uint8_t> data;
+			const bool whole = bs.parts.size() == 1;
+			if (whole)
+				data = bs.block.encode_range(*bs.name, batch, g0, g1);
+			else
+				bs.parts[todo.part] = encode_glyph_entries(batch, g0, g1);
+			if (!whole && bs.remaining.fetch_sub(1, std::memory_order_acq_rel) != 1) {
+				st.encode_ns += now_ns() - t0;
+				return true;
+			}
+			if (!whole)
+				data = assemble_glyphs_pbf(*bs.name, bs.block.range(), bs.parts);
+			st.encode_ns += now_ns() - t0;
 			st.pbf_bytes += data.size();
 			st.blocks++;
-			const uint64_t t0 = now_ns();
+			t0 = now_ns();
 			std::string e;
 			bool ok;
 			{
 				std::lock_guard<std::mutex> g(writer_mutex);
-				ok = writer.write_file(*todo.name + "/" + todo.block.filename(), std::move(data), &e);
+				ok = writer.write_file(*bs.name + "/" + bs.block.filename(), std::move(data), &e);
 			}
 			st.write_ns += now_ns() - t0;
 			if (!ok)
@@ -529,19 +605,17 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			f.active = false;
 			std::string e;
 			uint64_t t0 = now_ns();
+			mark('w');
 			const bool waited = renderer.wait_batch(f.ticket, &e);
+			mark('W');
 			st.wait_ns += now_ns() - t0;
 			if (!waited) {
 				fail(e);
 				return false;
 			}
-			for (const Part &p : f.parts) {
-				t0 = now_ns();
-				std::vector<uint8_t> data = p.todo->block.encode_range(*p.todo->name, *f.batch, p.g0, p.g1);
-				st.encode_ns += now_ns() - t0;
-				if (!emit(*p.todo, std::move(data)))
+			for (const Part &p : f.parts)
+				if (!finish_part(*p.todo, *f.batch, p.g0, p.g1))
 					return false;
-			}
 			return true;
 		};
 		int k = 0;
@@ -550,6 +624,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			Flight &cur = flights[k];
 			cur.batch->clear();
 			cur.parts.clear();
+			mark('o');
 			uint64_t t0 = now_ns();
 			while (cur.batch->glyphs().size() < target) {
 				const size_t ti = next.fetch_add(1);
@@ -559,7 +634,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				}
 				const Todo &todo = tasks[ti];
 				const size_t g0 = cur.batch->glyphs().size();
-				todo.block.append_to_batch(*cur.batch);
+				todo.bs->block.append_to_batch(*cur.batch, todo.slot0, todo.slot1);
 				cur.parts.push_back(Part{&todo, g0, cur.batch->glyphs().size()});
 			}
 			st.outline_ns += now_ns() - t0;
@@ -574,18 +649,16 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				// nothing to rasterise (empty blocks, or only bitmap-less glyphs): no GPU round trip
 				cur.ticket = ~0ull;
 				cur.active = false;
-				for (const Part &p : cur.parts) {
-					t0 = now_ns();
-					std::vector<uint8_t> data = p.todo->block.encode_range(*p.todo->name, *cur.batch, p.g0, p.g1);
-					st.encode_ns += now_ns() - t0;
-					if (!emit(*p.todo, std::move(data)))
+				for (const Part &p : cur.parts)
+					if (!finish_part(*p.todo, *cur.batch, p.g0, p.g1))
 						break;
-				}
 				continue;
 			}
 			t0 = now_ns();
 			std::string e;
+			mark('s');
 			const bool submitted = renderer.submit_batch(*cur.batch, &cur.ticket, &e);
+			mark('S');
 			st.submit_ns += now_ns() - t0;
 			st.submits++;
 			if (!submitted) {
@@ -605,12 +678,23 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			retire(f);
 			renderer.release_batch(std::move(f.batch));
 		}
+		mark('E');
 	};
 
 	if (workers == 1) {
 		work(0);
 	} else {
 		WorkerPool::instance().run(workers, work);
+	}
+	if (trace) {
+		std::fprintf(stderr, "[vgb trace] setup %.1f us, %d workers, %zu tasks, target %zu glyphs, total %.1f us\n",
+		             (double)(t_setup - t_begin) * 1e-3, workers, tasks.size(), target, (double)(now_ns() - t_begin) * 1e-3);
+		for (int w = 0; w < workers; ++w) {
+			std::fprintf(stderr, "[vgb trace] w%02d", w);
+			for (const auto &e : events[(size_t)w])
+				std::fprintf(stderr, " %c%.0f", e.first, (double)e.second * 1e-3);
+			std::fprintf(stderr, "\n");
+		}
 	}
 	if (stats) {
 		*stats = RenderStats();

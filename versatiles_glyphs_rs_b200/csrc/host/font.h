@@ -57,19 +57,35 @@ struct FontFileEntry {
 
 class GlyphBlock {
   public:
-	explicit GlyphBlock(uint32_t start_index = 0) : start_index_(start_index) { fonts_.fill(nullptr); }
+	explicit GlyphBlock(uint32_t start_index = 0) : start_index_(start_index) { slot_.fill(0); }
 	uint32_t start_index() const { return start_index_; }
+	void reset(uint32_t start_index)
+	{
+		start_index_ = start_index;
+		slot_.fill(0);
+		owners_.clear();
+		len_ = 0;
+	}
 	// glyph_block.rs:34-36 — entry().or_insert(): the first file that has the code point keeps it
 	void set_glyph_font(uint8_t char_index, const FontFileEntry *font)
 	{
-		if (!fonts_[char_index]) {
-			fonts_[char_index] = font;
-			++len_;
-		}
+		if (slot_[char_index])
+			return;
+		size_t k = 0;
+		while (k < owners_.size() && owners_[k] != font)
+			++k;
+		if (k == owners_.size())
+			owners_.push_back(font);
+		slot_[char_index] = (uint16_t)(k + 1);
+		++len_;
 	}
 	size_t len() const { return len_; }
 	bool is_empty() const { return len_ == 0; }
-	const FontFileEntry *font_of(uint8_t char_index) const { return fonts_[char_index]; }
+	const FontFileEntry *font_of(uint8_t char_index) const
+	{
+		const uint16_t k = slot_[char_index];
+		return k ? owners_[k - 1u] : nullptr;
+	}
 	std::string range() const;    // "{start}-{start+255}"            glyph_block.rs:52-58
 	std::string filename() const; // "{range}.pbf"                     glyph_block.rs:85-87
 	// glyph_block.rs:69-80.  Glyphs are emitted in ascending code point order (the reference
@@ -80,12 +96,15 @@ class GlyphBlock {
 	std::vector<uint8_t> encode_batch(const std::string &font_name, const GlyphBatch &batch) const;
 	// Several blocks may share one batch: append this block's glyphs (no clear) / encode glyphs [g0, g1)
 	// straight from the batch's bitmap buffer (no intermediate PbfGlyph copies).
-	void append_to_batch(GlyphBatch &batch) const;
+	void append_to_batch(GlyphBatch &batch, uint32_t slot0 = 0, uint32_t slot1 = GLYPH_BLOCK_SIZE) const;
 	std::vector<uint8_t> encode_range(const std::string &font_name, const GlyphBatch &batch, size_t g0, size_t g1) const;
 
   private:
 	uint32_t start_index_;
-	std::array<const FontFileEntry *, GLYPH_BLOCK_SIZE> fonts_;
+	// slot -> 1 + index into owners_ (0 = no glyph): a block is 512 bytes, so building the 256 blocks of a
+	// font on every render_glyphs call (as the reference does) touches 128 KiB instead of 512 KiB
+	std::array<uint16_t, GLYPH_BLOCK_SIZE> slot_;
+	std::vector<const FontFileEntry *> owners_; // the files that own at least one slot, in first-seen order
 	size_t len_ = 0;
 };
 
@@ -96,6 +115,8 @@ class FontWrapper {
 	const std::vector<std::unique_ptr<FontFileEntry>> &files() const { return files_; }
 	// wrapper.rs:53-76 — always 256 BMP blocks, code points > 0xFFFF ignored
 	std::vector<GlyphBlock> get_blocks() const;
+	// the same assignment written into 256 caller-owned blocks (block i must start at i * 256)
+	void assign_blocks(GlyphBlock *const *blocks) const;
 
   private:
 	std::vector<std::unique_ptr<FontFileEntry>> files_;

@@ -89,20 +89,20 @@ std::vector<uint8_t> PbfGlyphs::into_vec() const
 	return out;
 }
 
-std::vector<uint8_t> encode_batch_range(const std::string &name, const std::string &range, const GlyphBatch &batch, size_t g0,
-                                        size_t g1)
+namespace {
+struct RangeItem {
+	uint32_t id, width, height, left_zz, top_zz, advance;
+	const uint8_t *bitmap; // nullptr = None
+	size_t bitmap_len, body;
+};
+// gathers glyphs [g0, g1) and returns the encoded size of their Fontstack.glyphs entries
+size_t gather_items(const GlyphBatch &batch, size_t g0, size_t g1, std::vector<RangeItem> &items)
 {
-	struct Item {
-		uint32_t id, width, height, left_zz, top_zz, advance;
-		const uint8_t *bitmap; // nullptr = None
-		size_t bitmap_len, body;
-	};
-	std::vector<Item> items;
 	items.reserve(g1 - g0);
-	size_t stack = 1 + varint_size(name.size()) + name.size() + 1 + varint_size(range.size()) + range.size();
+	size_t bytes = 0;
 	for (size_t i = g0; i < g1; ++i) {
 		const BatchGlyph &b = batch.glyphs()[i];
-		Item it;
+		RangeItem it;
 		it.id = b.id;
 		it.advance = b.advance;
 		if (b.has_bitmap) {
@@ -121,22 +121,14 @@ std::vector<uint8_t> encode_batch_range(const std::string &name, const std::stri
 		it.body = 1 + varint_size(it.id) + (it.bitmap ? 1 + varint_size(it.bitmap_len) + it.bitmap_len : 0) + 1 +
 		          varint_size(it.width) + 1 + varint_size(it.height) + 1 + varint_size(it.left_zz) + 1 + varint_size(it.top_zz) +
 		          1 + varint_size(it.advance);
-		stack += 1 + varint_size(it.body) + it.body;
+		bytes += 1 + varint_size(it.body) + it.body;
 		items.push_back(it);
 	}
-	std::vector<uint8_t> out(1 + varint_size(stack) + stack);
-	uint8_t *p = out.data();
-	*p++ = 0x0A;
-	p = put_varint(p, stack);
-	*p++ = 0x0A;
-	p = put_varint(p, name.size());
-	std::memcpy(p, name.data(), name.size());
-	p += name.size();
-	*p++ = 0x12;
-	p = put_varint(p, range.size());
-	std::memcpy(p, range.data(), range.size());
-	p += range.size();
-	for (const Item &it : items) {
+	return bytes;
+}
+uint8_t *put_items(uint8_t *p, const std::vector<RangeItem> &items)
+{
+	for (const RangeItem &it : items) {
 		*p++ = 0x1A;
 		p = put_varint(p, it.body);
 		*p++ = 0x08;
@@ -157,6 +149,58 @@ std::vector<uint8_t> encode_batch_range(const std::string &name, const std::stri
 		p = put_varint(p, it.top_zz);
 		*p++ = 0x38;
 		p = put_varint(p, it.advance);
+	}
+	return p;
+}
+size_t stack_header_size(const std::string &name, const std::string &range)
+{
+	return 1 + varint_size(name.size()) + name.size() + 1 + varint_size(range.size()) + range.size();
+}
+uint8_t *put_headers(uint8_t *p, const std::string &name, const std::string &range, size_t stack)
+{
+	*p++ = 0x0A;
+	p = put_varint(p, stack);
+	*p++ = 0x0A;
+	p = put_varint(p, name.size());
+	std::memcpy(p, name.data(), name.size());
+	p += name.size();
+	*p++ = 0x12;
+	p = put_varint(p, range.size());
+	std::memcpy(p, range.data(), range.size());
+	return p + range.size();
+}
+} // namespace
+
+std::vector<uint8_t> encode_batch_range(const std::string &name, const std::string &range, const GlyphBatch &batch, size_t g0,
+                                        size_t g1)
+{
+	std::vector<RangeItem> items;
+	const size_t stack = stack_header_size(name, range) + gather_items(batch, g0, g1, items);
+	std::vector<uint8_t> out(1 + varint_size(stack) + stack);
+	put_items(put_headers(out.data(), name, range, stack), items);
+	return out;
+}
+
+std::vector<uint8_t> encode_glyph_entries(const GlyphBatch &batch, size_t g0, size_t g1)
+{
+	std::vector<RangeItem> items;
+	std::vector<uint8_t> out(gather_items(batch, g0, g1, items));
+	put_items(out.data(), items);
+	return out;
+}
+
+std::vector<uint8_t> assemble_glyphs_pbf(const std::string &name, const std::string &range,
+                                         const std::vector<std::vector<uint8_t>> &parts)
+{
+	size_t stack = stack_header_size(name, range);
+	for (const auto &part : parts)
+		stack += part.size();
+	std::vector<uint8_t> out(1 + varint_size(stack) + stack);
+	uint8_t *p = put_headers(out.data(), name, range, stack);
+	for (const auto &part : parts) {
+		if (!part.empty())
+			std::memcpy(p, part.data(), part.size());
+		p += part.size();
 	}
 	return out;
 }

@@ -35,6 +35,13 @@ class PbfGlyphs {
 std::vector<uint8_t> encode_batch_range(const std::string &name, const std::string &range, const GlyphBatch &batch, size_t g0,
                                         size_t g1);
 
+// A block rendered in several parts (FontManager::render_glyphs splits full blocks so that no worker is
+// stuck with 256 glyphs): the Fontstack.glyphs entries of glyphs [g0, g1) alone, and the final message
+// built from the parts in code point order — byte-identical to encode_batch_range over the whole block.
+std::vector<uint8_t> encode_glyph_entries(const GlyphBatch &batch, size_t g0, size_t g1);
+std::vector<uint8_t> assemble_glyphs_pbf(const std::string &name, const std::string &range,
+                                         const std::vector<std::vector<uint8_t>> &parts);
+
 // Decoder for tests / the debug differ (mirror of commands/debug.rs:38-98's prost decode).
 bool pbf_decode(const uint8_t *data, size_t len, std::string &name, std::string &range, std::vector<PbfGlyph> &glyphs);
 
