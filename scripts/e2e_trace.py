@@ -17,6 +17,8 @@ r = V.Renderer.new_precise(device=0)
 ts = []
 for i in range(30):
     w = V.Writer.new_memory()
+    if os.environ.get("B200SDF_TRACE"):
+        print(f"--- step {i}", file=sys.stderr, flush=True)
     t = time.perf_counter()
     st = m.render_glyphs(w, r, threads=threads)
     ts.append((time.perf_counter() - t) * 1e3)

@@ -6,9 +6,13 @@
 // returns.  This is the async batch pipeline that replaces the serial per-block loop of
 // FontManager::render_glyphs (reference src/font/manager.rs:104-121).
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -22,6 +26,51 @@ struct DevBuf {
 	void *p = nullptr;
 	size_t cap = 0;
 };
+
+// Pinned host memory handed out by b200sdf_alloc_pinned: [start, start + bytes) -> device-side address.
+// A batch whose job list and bitmap buffer live in such memory is rendered without staging copies for
+// them: the kernel reads the (small) job records and writes the bitmaps straight over PCIe, so the slot's
+// stream carries one H2D copy and one kernel instead of four copies, a kernel and a copy back.
+struct PinnedRegistry {
+	std::mutex mu;
+	std::map<uintptr_t, std::pair<size_t, uintptr_t>> ranges; // start -> (bytes, device address)
+	void add(void *p, size_t bytes, void *dev)
+	{
+		std::lock_guard<std::mutex> g(mu);
+		ranges[(uintptr_t)p] = std::make_pair(bytes, (uintptr_t)dev);
+	}
+	void remove(void *p)
+	{
+		std::lock_guard<std::mutex> g(mu);
+		ranges.erase((uintptr_t)p);
+	}
+	// device address of host range [p, p + bytes) if it lies inside one pinned allocation, else nullptr
+	void *device_ptr(const void *p, size_t bytes)
+	{
+		std::lock_guard<std::mutex> g(mu);
+		auto it = ranges.upper_bound((uintptr_t)p);
+		if (it == ranges.begin())
+			return nullptr;
+		--it;
+		const uintptr_t off = (uintptr_t)p - it->first;
+		if (off > it->second.first || bytes > it->second.first - off)
+			return nullptr;
+		return (void *)(it->second.second + off);
+	}
+};
+PinnedRegistry &pinned_registry()
+{
+	static PinnedRegistry *r = new PinnedRegistry(); // leaked on purpose: outlives static destructors
+	return *r;
+}
+bool zero_copy_enabled()
+{
+	static const bool on = [] {
+		const char *e = std::getenv("B200SDF_ZEROCOPY");
+		return !(e && e[0] == '0');
+	}();
+	return on;
+}
 
 struct Slot {
 	cudaStream_t stream = nullptr;
@@ -76,18 +125,22 @@ size_t grown(size_t need, size_t cap)
 	return (n + 255) & ~size_t(255);
 }
 
-int grow_device(b200sdf_ctx *ctx, DevBuf &b, size_t need)
+// Stream-ordered (re)allocation on the slot's own stream: unlike cudaFree / cudaMalloc it does not
+// synchronise the device, so a slot that meets a bigger batch does not stall the other slots' work.
+int grow_device(b200sdf_ctx *ctx, DevBuf &b, size_t need, cudaStream_t stream)
 {
 	if (need <= b.cap)
 		return 0;
 	const size_t n = grown(need, b.cap);
 	if (b.p)
-		cudaFree(b.p);
+		cudaFreeAsync(b.p, stream);
 	b.p = nullptr;
 	b.cap = 0;
-	cudaError_t e = cudaMalloc(&b.p, n);
+	if (std::getenv("B200SDF_TRACE"))
+		std::fprintf(stderr, "[b200sdf trace] grow_device %zu -> %zu bytes\n", need, n);
+	cudaError_t e = cudaMallocAsync(&b.p, n, stream);
 	if (e != cudaSuccess)
-		return fail_cuda(ctx, e, "cudaMalloc");
+		return fail_cuda(ctx, e, "cudaMallocAsync");
 	b.cap = n;
 	return 0;
 }
@@ -97,13 +150,13 @@ int grow_pinned(b200sdf_ctx *ctx, void **p, size_t *cap, size_t need)
 	if (need <= *cap)
 		return 0;
 	if (*p)
-		cudaFreeHost(*p);
+		b200sdf_free_pinned(*p);
 	*p = nullptr;
 	const size_t n = grown(need, *cap);
 	*cap = 0;
-	cudaError_t e = cudaMallocHost(p, n);
-	if (e != cudaSuccess)
-		return fail_cuda(ctx, e, "cudaMallocHost");
+	*p = b200sdf_alloc_pinned(n);
+	if (!*p)
+		return fail_cuda(ctx, cudaErrorMemoryAllocation, "cudaHostAlloc");
 	*cap = n;
 	return 0;
 }
@@ -316,7 +369,19 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
                    const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_outline_job *ojobs, uint32_t n_ojobs,
                    uint8_t *out, uint64_t out_bytes, uint64_t *ticket)
 {
+	// B200SDF_TRACE=1: report submissions slower than 200 us with per-phase timestamps (diagnostics)
+	static const bool trace = std::getenv("B200SDF_TRACE") != nullptr;
+	uint64_t tt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	auto now = [] {
+		timespec ts;
+		clock_gettime(CLOCK_MONOTONIC, &ts);
+		return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+	};
+	if (trace)
+		tt[0] = now();
 	const size_t si = acquire_slot(ctx);
+	if (trace)
+		tt[1] = now();
 	Slot &s = ctx->slots[si];
 	cudaError_t e = cudaSetDevice(ctx->device);
 	if (e != cudaSuccess)
@@ -327,11 +392,22 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 	// the context with cudaFree/cudaMalloc whenever it first meets a bigger batch.
 	size_t need[5] = {(size_t)n_seg * sizeof(b200sdf_segment), (size_t)n_curves * sizeof(b200sdf_curve),
 	                  (size_t)n_ojobs * sizeof(b200sdf_outline_job), n_tiles * sizeof(b200sdf_tile_job), (size_t)out_bytes};
+	// zero-copy legs (see PinnedRegistry): job records read, bitmaps written, in place in pinned host memory
+	const bool zc = zero_copy_enabled();
+	const void *k_ojobs = zc && n_ojobs ? pinned_registry().device_ptr(ojobs, need[2]) : nullptr;
+	void *k_out = zc && out_bytes ? pinned_registry().device_ptr(out, need[4]) : nullptr;
+	if (k_ojobs)
+		need[2] = 0; // no device mirror needed
+	if (k_out)
+		need[4] = 0;
+	const size_t tiles_bytes = need[3];
 	{
 		std::lock_guard<std::mutex> g(ctx->mu);
 		for (int k = 0; k < 5; ++k) {
 			// ... rounded up to a power of two (>= 64 KiB): batch composition varies from call to call
 			// (dynamic scheduling), and a mark that creeps up by a few bytes would stall the device again
+			if (need[k] == 0)
+				continue;
 			size_t r = (size_t)64 << 10;
 			while (r < need[k])
 				r <<= 1;
@@ -340,14 +416,45 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 		}
 	}
 	int rc;
-	if ((rc = grow_device(ctx, s.segs, need[0])) || (rc = grow_device(ctx, s.curves, need[1])) ||
-	    (rc = grow_device(ctx, s.ojobs, need[2])) || (rc = grow_device(ctx, s.tiles, need[3])) ||
-	    (rc = grow_device(ctx, s.out, need[4])) || (rc = grow_pinned(ctx, &s.h_tiles, &s.h_tiles_cap, need[3])))
+	if ((rc = grow_device(ctx, s.segs, need[0], s.stream)) || (rc = grow_device(ctx, s.curves, need[1], s.stream)) ||
+	    (rc = grow_device(ctx, s.ojobs, need[2], s.stream)) || (rc = grow_device(ctx, s.tiles, need[3], s.stream)) ||
+	    (rc = grow_device(ctx, s.out, need[4], s.stream)) || (rc = grow_pinned(ctx, &s.h_tiles, &s.h_tiles_cap, need[3])))
 		return release_slot(ctx, s, rc);
+	(void)tiles_bytes;
+	if (trace)
+		tt[2] = now();
 	b200sdf_tile_job *ht = reinterpret_cast<b200sdf_tile_job *>(s.h_tiles);
 	for (size_t i = 0; i < n_tiles; ++i)
 		ht[i] = plan[i].t;
 
+	// B200SDF_SERIALIZE=1|2: enqueue under a process-wide spin lock (experiment: driver-side contention)
+	static const int serialize = [] {
+		const char *e = std::getenv("B200SDF_SERIALIZE");
+		return e ? std::atoi(e) : 0;
+	}();
+	struct SpinGuard {
+		static std::atomic<int> &flag()
+		{
+			static std::atomic<int> f{0};
+			return f;
+		}
+		bool on;
+		explicit SpinGuard(bool o) : on(o)
+		{
+			if (!on)
+				return;
+			int z = 0;
+			while (!flag().compare_exchange_weak(z, 1, std::memory_order_acquire)) {
+				z = 0;
+				__builtin_ia32_pause();
+			}
+		}
+		~SpinGuard()
+		{
+			if (on)
+				flag().store(0, std::memory_order_release);
+		}
+	} spin_guard(serialize != 0);
 #define SUB_TRY(call)                                                \
 	do {                                                             \
 		cudaError_t e_ = (call);                                     \
@@ -358,25 +465,48 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 		SUB_TRY(cudaMemcpyAsync(s.segs.p, segs, (size_t)n_seg * sizeof(b200sdf_segment), cudaMemcpyHostToDevice, s.stream));
 	if (n_curves)
 		SUB_TRY(cudaMemcpyAsync(s.curves.p, curves, (size_t)n_curves * sizeof(b200sdf_curve), cudaMemcpyHostToDevice, s.stream));
-	if (n_ojobs)
+	if (trace)
+		tt[3] = now();
+	const void *k_tiles = zc && n_tiles ? pinned_registry().device_ptr(ht, n_tiles * sizeof(b200sdf_tile_job)) : nullptr;
+	if (n_ojobs && !k_ojobs) {
 		SUB_TRY(cudaMemcpyAsync(s.ojobs.p, ojobs, (size_t)n_ojobs * sizeof(b200sdf_outline_job), cudaMemcpyHostToDevice, s.stream));
+		k_ojobs = s.ojobs.p;
+	}
 	if (n_tiles) {
-		SUB_TRY(cudaMemcpyAsync(s.tiles.p, ht, n_tiles * sizeof(b200sdf_tile_job), cudaMemcpyHostToDevice, s.stream));
-		// Bitmaps may be sparse in `out` (caller-chosen out_off); the device buffer mirrors the layout and
-		// is copied back whole, so bytes between bitmaps are defined (zero) rather than stale device memory.
+		if (!k_tiles) {
+			SUB_TRY(cudaMemcpyAsync(s.tiles.p, ht, n_tiles * sizeof(b200sdf_tile_job), cudaMemcpyHostToDevice, s.stream));
+			k_tiles = s.tiles.p;
+		}
+		// Bitmaps may be sparse in `out` (caller-chosen out_off): bytes between bitmaps are defined (zero).
 		uint64_t covered = 0;
 		for (const Planned &p : plan)
 			if (p.t.tx0 == 0 && p.t.ty0 == 0)
 				covered += (uint64_t)p.t.width * p.t.height;
-		if (covered < out_bytes)
-			SUB_TRY(cudaMemsetAsync(s.out.p, 0, (size_t)out_bytes, s.stream));
-		launch_sdf(s.segs.p, s.curves.p, s.ojobs.p, s.tiles.p, (uint32_t)n_tiles, s.out.p, s.stream);
-		SUB_TRY(cudaGetLastError());
-		// bitmaps may be sparse in `out` (caller-chosen out_off); the device buffer mirrors the layout
-		SUB_TRY(cudaMemcpyAsync(out, s.out.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, s.stream));
+		if (k_out) {
+			if (covered < out_bytes)
+				std::memset(out, 0, (size_t)out_bytes); // the caller's buffer is ours until wait()
+			launch_sdf(s.segs.p, s.curves.p, k_ojobs, k_tiles, (uint32_t)n_tiles, k_out, s.stream);
+			SUB_TRY(cudaGetLastError());
+		} else {
+			// staged: the device buffer mirrors the layout and is copied back whole
+			if (covered < out_bytes)
+				SUB_TRY(cudaMemsetAsync(s.out.p, 0, (size_t)out_bytes, s.stream));
+			launch_sdf(s.segs.p, s.curves.p, k_ojobs, k_tiles, (uint32_t)n_tiles, s.out.p, s.stream);
+			SUB_TRY(cudaGetLastError());
+			SUB_TRY(cudaMemcpyAsync(out, s.out.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, s.stream));
+		}
 	}
+	if (trace)
+		tt[4] = now();
 	SUB_TRY(cudaEventRecord(s.done, s.stream));
 #undef SUB_TRY
+	if (trace) {
+		tt[5] = now();
+		if (tt[5] - tt[0] > 200000)
+			std::fprintf(stderr, "[b200sdf trace] slow submit slot %zu: acquire %.0f grow %.0f tiles+h2d %.0f launch %.0f event %.0f us (curves %u tiles %zu)\n",
+			             si, (tt[1] - tt[0]) * 1e-3, (tt[2] - tt[1]) * 1e-3, (tt[3] - tt[2]) * 1e-3, (tt[4] - tt[3]) * 1e-3,
+			             (tt[5] - tt[4]) * 1e-3, n_curves, n_tiles);
+	}
 	{
 		std::lock_guard<std::mutex> g(ctx->mu);
 		if (n_tiles)
@@ -430,6 +560,15 @@ int b200sdf_create(int device, uint32_t n_slots, b200sdf_ctx **out)
 		delete ctx;
 		return B200SDF_E_NODEVICE;
 	}
+	// keep freed stream-ordered allocations in the pool (grow_device): no trimming at synchronisation points
+	{
+		cudaMemPool_t pool = nullptr;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+			uint64_t keep = ~0ull;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+		cudaGetLastError();
+	}
 	ctx->slots.resize(n_slots);
 	for (auto &s : ctx->slots) {
 		if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -454,7 +593,7 @@ void b200sdf_destroy(b200sdf_ctx *ctx)
 			if (b->p)
 				cudaFree(b->p);
 		if (s.h_tiles)
-			cudaFreeHost(s.h_tiles);
+			b200sdf_free_pinned(s.h_tiles);
 		if (s.done)
 			cudaEventDestroy(s.done);
 		if (s.stream)
@@ -472,16 +611,25 @@ uint64_t b200sdf_launch_count(const b200sdf_ctx *ctx) { return ctx ? ctx->launch
 void *b200sdf_alloc_pinned(size_t bytes)
 {
 	void *p = nullptr;
-	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+	if (std::getenv("B200SDF_TRACE"))
+		std::fprintf(stderr, "[b200sdf trace] alloc_pinned %zu bytes\n", bytes);
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
 		cudaGetLastError();
 		return nullptr;
 	}
+	void *dev = nullptr;
+	if (cudaHostGetDevicePointer(&dev, p, 0) == cudaSuccess && dev)
+		pinned_registry().add(p, bytes ? bytes : 1, dev);
+	else
+		cudaGetLastError(); // not mapped: the staged path is used for this buffer
 	return p;
 }
 void b200sdf_free_pinned(void *p)
 {
-	if (p)
-		cudaFreeHost(p);
+	if (!p)
+		return;
+	pinned_registry().remove(p);
+	cudaFreeHost(p);
 }
 
 int b200sdf_plan_tiles(const b200sdf_glyph_job *jobs, uint32_t n_jobs, uint32_t n_seg, uint64_t out_bytes,
@@ -577,7 +725,18 @@ int b200sdf_wait(b200sdf_ctx *ctx, uint64_t ticket)
 		}
 	}
 	Slot &s = ctx->slots[si];
-	cudaError_t e = cudaEventSynchronize(s.done);
+	static const bool poll = [] {
+		const char *v = std::getenv("B200SDF_SERIALIZE");
+		return v && std::atoi(v) >= 2;
+	}();
+	cudaError_t e;
+	if (poll) {
+		while ((e = cudaEventQuery(s.done)) == cudaErrorNotReady)
+			for (int k = 0; k < 64; ++k)
+				__builtin_ia32_pause();
+	} else {
+		e = cudaEventSynchronize(s.done);
+	}
 	release_slot(ctx, s, 0);
 	if (e != cudaSuccess)
 		return fail_cuda(ctx, e, "cudaEventSynchronize");
@@ -625,10 +784,10 @@ int b200sdf_flatten_outlines(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint
 	const size_t si = acquire_slot(ctx);
 	Slot &s = ctx->slots[si];
 	int rc;
-	if ((rc = grow_device(ctx, s.curves, (size_t)n_curves * sizeof(b200sdf_curve))) ||
-	    (rc = grow_device(ctx, s.ojobs, (size_t)n_jobs * sizeof(b200sdf_outline_job))) ||
-	    (rc = grow_device(ctx, s.seg_base, (size_t)(n_jobs + 1) * sizeof(uint64_t))) ||
-	    (rc = grow_device(ctx, s.segs, (size_t)n_out * sizeof(b200sdf_segment))))
+	if ((rc = grow_device(ctx, s.curves, (size_t)n_curves * sizeof(b200sdf_curve), s.stream)) ||
+	    (rc = grow_device(ctx, s.ojobs, (size_t)n_jobs * sizeof(b200sdf_outline_job), s.stream)) ||
+	    (rc = grow_device(ctx, s.seg_base, (size_t)(n_jobs + 1) * sizeof(uint64_t), s.stream)) ||
+	    (rc = grow_device(ctx, s.segs, (size_t)n_out * sizeof(b200sdf_segment), s.stream)))
 		return release_slot(ctx, s, rc);
 	cudaError_t e = cudaSetDevice(ctx->device);
 	if (e == cudaSuccess)

@@ -454,11 +454,15 @@ class WorkerPool {
 bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::string *err, RenderStats *stats,
                                 uint32_t shard, uint32_t n_shards, int threads) const
 {
-	// A task is a slot range of one block holding at most kPartGlyphs glyphs: full blocks are split so that
+	// A task is a slot range of one block holding at most kPartGlyphs (64) glyphs: full blocks are split so that
 	// no worker is stuck recording 256 outlines while the others (and the GPU) run dry.  The parts of a
 	// block are encoded independently (Fontstack.glyphs entries) and the worker that finishes the last
 	// one assembles and writes the file.
-	constexpr size_t kPartGlyphs = 32;
+	static const size_t kPartGlyphs = [] { // tuning knob (default 64; measured 16 / 32 / 64 on C2)
+		const char *e = std::getenv("VGB_PART_GLYPHS");
+		const long v = e ? std::atol(e) : 0;
+		return (size_t)(v >= 1 && v <= 256 ? v : 64);
+	}();
 	struct BlockState {
 		const std::string *name = nullptr;
 		GlyphBlock block;
@@ -515,9 +519,13 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		}
 	}
 
-	// Fullest parts first: dynamic scheduling then ends with the cheap ones (the reference's rayon
-	// par_iter makes no order promise either, manager.rs:117-118).
-	std::stable_sort(tasks.begin(), tasks.end(), [](const Todo &a, const Todo &b) { return a.glyphs > b.glyphs; });
+	// Empty blocks first (they need no GPU and would otherwise all be written after the last wait), then the
+	// fullest parts: dynamic scheduling ends with the cheap ones (the reference's rayon par_iter makes no
+	// order promise either, manager.rs:117-118).
+	std::stable_sort(tasks.begin(), tasks.end(), [](const Todo &a, const Todo &b) {
+		const uint32_t ka = a.glyphs ? a.glyphs : 0xffffffffu, kb = b.glyphs ? b.glyphs : 0xffffffffu;
+		return ka > kb;
+	});
 
 	int workers = 1;
 	if (parallel_) {
@@ -529,8 +537,14 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	}
 	// One submission carries whole blocks until it holds about `target` glyphs: small jobs keep one
 	// block per submission (parallelism), big jobs amortise the per-submission cost.
-	const size_t target = std::min<size_t>(2048, std::max<size_t>(1, total_glyphs / ((size_t)workers * 4)));
+	static const size_t kBatchesPerWorker = [] { // tuning knob (default 4)
+		const char *e = std::getenv("VGB_BATCHES_PER_WORKER");
+		const long v = e ? std::atol(e) : 0;
+		return (size_t)(v >= 1 && v <= 64 ? v : 4);
+	}();
+	const size_t target = std::min<size_t>(2048, std::max<size_t>(1, total_glyphs / ((size_t)workers * kBatchesPerWorker)));
 	std::atomic<size_t> next{0};
+	std::atomic<size_t> glyphs_taken{0};
 	std::atomic<bool> failed{false};
 	std::mutex writer_mutex, err_mutex;
 	std::vector<RenderStats> per_worker((size_t)workers);
@@ -554,6 +568,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				ev.emplace_back(what, now_ns() - t_begin);
 		};
 		mark('B');
+		std::vector<std::pair<std::string, std::vector<uint8_t>>> pending;
 		// one finished part: encode its glyph entries; the last part of a block assembles and writes the file
 		auto finish_part = [&](const Todo &todo, const GlyphBatch &batch, size_t g0, size_t g1) -> bool {
 			BlockState &bs = *todo.bs;
@@ -568,19 +583,34 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				st.encode_ns += now_ns() - t0;
 				return true;
 			}
-			if (!whole)
+			if (!whole) {
+				mark('a');
 				data = assemble_glyphs_pbf(*bs.name, bs.block.range(), bs.parts);
+				mark('A');
+			}
 			st.encode_ns += now_ns() - t0;
 			st.pbf_bytes += data.size();
 			st.blocks++;
-			t0 = now_ns();
+			pending.emplace_back(*bs.name + "/" + bs.block.filename(), std::move(data));
+			return true;
+		};
+		// finished files are handed to the writer in groups: one lock acquisition per retired batch instead
+		// of one per file (512 files per font pair, most of them tiny, would otherwise queue on the mutex)
+		auto flush = [&]() -> bool {
+			if (pending.empty())
+				return true;
+			const uint64_t t0 = now_ns();
 			std::string e;
-			bool ok;
+			bool ok = true;
 			{
 				std::lock_guard<std::mutex> g(writer_mutex);
-				ok = writer.write_file(*bs.name + "/" + bs.block.filename(), std::move(data), &e);
+				for (auto &f : pending)
+					if (ok)
+						ok = writer.write_file(f.first, std::move(f.second), &e);
 			}
+			pending.clear();
 			st.write_ns += now_ns() - t0;
+			mark('F');
 			if (!ok)
 				fail(e);
 			return ok;
@@ -616,9 +646,10 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			for (const Part &p : f.parts)
 				if (!finish_part(*p.todo, *f.batch, p.g0, p.g1))
 					return false;
-			return true;
+			return flush();
 		};
 		int k = 0;
+		unsigned n_batches = 0;
 		bool more = true;
 		while (more && !failed.load()) {
 			Flight &cur = flights[k];
@@ -626,7 +657,14 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			cur.parts.clear();
 			mark('o');
 			uint64_t t0 = now_ns();
-			while (cur.batch->glyphs().size() < target) {
+			// Batch size: small first batches (the GPU starts early), the steady-state target, then a taper —
+			// the last batches of all workers are submitted together and their latency is the tail of the call.
+			const size_t left = total_glyphs - std::min(total_glyphs, glyphs_taken.load(std::memory_order_relaxed));
+			size_t want = std::min(target, std::max<size_t>(kPartGlyphs, left / ((size_t)workers * 2)));
+			if (n_batches < 2)
+				want = std::min(want, std::max<size_t>(kPartGlyphs, target >> (2 - n_batches)));
+			++n_batches;
+			while (cur.batch->glyphs().size() < want) {
 				const size_t ti = next.fetch_add(1);
 				if (ti >= tasks.size()) {
 					more = false;
@@ -634,6 +672,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				}
 				const Todo &todo = tasks[ti];
 				const size_t g0 = cur.batch->glyphs().size();
+				glyphs_taken.fetch_add(todo.glyphs, std::memory_order_relaxed);
 				todo.bs->block.append_to_batch(*cur.batch, todo.slot0, todo.slot1);
 				cur.parts.push_back(Part{&todo, g0, cur.batch->glyphs().size()});
 			}
@@ -652,6 +691,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				for (const Part &p : cur.parts)
 					if (!finish_part(*p.todo, *cur.batch, p.g0, p.g1))
 						break;
+				if (!flush())
+					break;
 				continue;
 			}
 			t0 = now_ns();
