@@ -149,6 +149,10 @@ void b200sdf_free_pinned(void *p);
 int b200sdf_submit(b200sdf_ctx *ctx, const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_glyph_job *jobs,
                    uint32_t n_jobs, uint8_t *out, uint64_t out_bytes, uint64_t *ticket);
 int b200sdf_wait(b200sdf_ctx *ctx, uint64_t ticket);
+/* Non-blocking form of b200sdf_wait: 1 = the batch has finished (ticket consumed, as by wait),
+ * 0 = still running (ticket stays valid), < 0 = error.  Lets ONE thread own all CUDA traffic of a
+ * pipeline (submit + completion polling) while the others only produce and consume batches. */
+int b200sdf_poll(b200sdf_ctx *ctx, uint64_t ticket);
 /* submit + wait */
 int b200sdf_render(b200sdf_ctx *ctx, const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_glyph_job *jobs,
                    uint32_t n_jobs, uint8_t *out, uint64_t out_bytes);
@@ -159,6 +163,13 @@ int b200sdf_render(b200sdf_ctx *ctx, const b200sdf_segment *segs, uint32_t n_seg
 int b200sdf_submit_outlines(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint32_t n_curves,
                             const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_outline_job *jobs,
                             uint32_t n_jobs, uint8_t *out, uint64_t out_bytes, uint64_t *ticket);
+/* The same with the tile planning done by the caller beforehand (b200sdf_plan_outline_tiles over the
+ * SAME job array; the tile list is trusted, not re-validated): a pipeline can then plan in its worker
+ * threads and keep the thread that talks to CUDA down to one copy, one launch and one event. */
+int b200sdf_submit_planned(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint32_t n_curves,
+                           const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_outline_job *jobs,
+                           uint32_t n_jobs, const b200sdf_tile_job *tiles, uint32_t n_tiles, uint8_t *out,
+                           uint64_t out_bytes, uint64_t *ticket);
 /* Device flattening only: writes the f32 origin-relative segments of every CURVES glyph, glyph
  * after glyph in job order, into out_segs (host buffer, n_out = sum of seg_cnt).  Blocking. */
 int b200sdf_flatten_outlines(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint32_t n_curves,

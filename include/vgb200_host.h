@@ -119,6 +119,11 @@ uint64_t vgb_batch_pairs(const vgb_batch *b);
 int vgb_renderer_render_batch(const vgb_renderer *r, vgb_batch *b);
 int vgb_renderer_submit_batch(const vgb_renderer *r, vgb_batch *b, uint64_t *ticket);
 int vgb_renderer_wait_batch(const vgb_renderer *r, uint64_t ticket);
+/* Two-step submission (pipelines with one CUDA thread): prepare in any thread (bitmap buffer, job validation,
+ * tile planning), then vgb_renderer_submit_batch only enqueues.  poll: 1 = finished (ticket consumed like
+ * wait), 0 = still running, < 0 = error. */
+int vgb_renderer_prepare_batch(const vgb_renderer *r, vgb_batch *b);
+int vgb_renderer_poll_batch(const vgb_renderer *r, uint64_t ticket);
 
 /* ---- Writer ---- */
 vgb_writer *vgb_writer_new_file(const char *folder); /* Writer::new_file, writer/mod.rs:35 */

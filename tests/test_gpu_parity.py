@@ -307,6 +307,29 @@ def test_many_batches_in_flight_from_threads(renderer):
     assert not errors, errors
 
 
+def test_prepared_submission_and_polling(renderer):
+    """b200sdf_submit_planned (tiles planned beforehand) + b200sdf_poll give the bitmaps of submit + wait."""
+    import time
+
+    font = V.FontFileEntry(path=O.FIRA)
+    cps = font.codepoints().tolist()[:400]
+    a, b = renderer.new_batch(), renderer.new_batch()
+    for cp in cps:
+        a.add_glyph(font, cp)
+        b.add_glyph(font, cp)
+    renderer.render_batch(a)
+    renderer.prepare_batch(b)
+    t = renderer.submit_batch(b)
+    deadline = time.time() + 30
+    while not renderer.poll_batch(t):
+        assert time.time() < deadline
+    assert np.array_equal(a.bitmaps(), b.bitmaps())
+    with pytest.raises(V.B200Error):
+        renderer.poll_batch(t)  # the ticket was consumed
+    with pytest.raises(V.B200Error):
+        renderer.wait_batch(t)
+
+
 def test_device_resident_path_matches_host_path(ctx):
     """b200sdf_render_device over torch-owned HBM buffers on a torch stream = b200sdf_render."""
     import torch

@@ -142,6 +142,9 @@ SDF_SYMBOLS = {
     "b200sdf_free_pinned": (None, [C.c_void_p]),
     "b200sdf_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, u64p]),
     "b200sdf_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "b200sdf_poll": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "b200sdf_submit_planned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                         C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, u64p]),
     "b200sdf_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
     "b200sdf_plan_tiles": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, u32p, u64p]),
     "b200sdf_render_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
@@ -195,6 +198,8 @@ HOST_SYMBOLS = {
     "vgb_renderer_render_batch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vgb_renderer_submit_batch": (C.c_int, [C.c_void_p, C.c_void_p, u64p]),
     "vgb_renderer_wait_batch": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "vgb_renderer_prepare_batch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vgb_renderer_poll_batch": (C.c_int, [C.c_void_p, C.c_uint64]),
     "vgb_writer_new_file": (C.c_void_p, [C.c_char_p]),
     "vgb_writer_new_memory": (C.c_void_p, []),
     "vgb_writer_new_tar": (C.c_void_p, [C.c_char_p]),

@@ -176,6 +176,18 @@ class Renderer:
         if N.host.vgb_renderer_wait_batch(self._h, ticket) != 0:
             raise B200Error(N.host_error())
 
+    def prepare_batch(self, batch: "GlyphBatch"):
+        """Plan the batch's tiles now (any thread); submit_batch then only enqueues (b200sdf_submit_planned)."""
+        if N.host.vgb_renderer_prepare_batch(self._h, batch._h) != 0:
+            raise B200Error(N.host_error())
+
+    def poll_batch(self, ticket: int) -> bool:
+        """Non-blocking wait_batch: True = finished (the ticket is consumed), False = still running."""
+        rc = N.host.vgb_renderer_poll_batch(self._h, ticket)
+        if rc < 0:
+            raise B200Error(N.host_error())
+        return rc == 1
+
 
 class GlyphBatch:
     """The flat segment buffer of one GlyphBlock (north star: "packed into a flat SoA segment buffer

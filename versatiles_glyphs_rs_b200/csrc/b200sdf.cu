@@ -63,6 +63,9 @@ PinnedRegistry &pinned_registry()
 	static PinnedRegistry *r = new PinnedRegistry(); // leaked on purpose: outlives static destructors
 	return *r;
 }
+#ifndef B200SDF_ZEROCOPY_CURVES
+#define B200SDF_ZEROCOPY_CURVES 1
+#endif
 bool zero_copy_enabled()
 {
 	static const bool on = [] {
@@ -367,7 +370,8 @@ int release_slot(b200sdf_ctx *ctx, Slot &s, int code)
 // The common submit path: everything already validated and planned.
 int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b200sdf_curve *curves, uint32_t n_curves,
                    const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_outline_job *ojobs, uint32_t n_ojobs,
-                   uint8_t *out, uint64_t out_bytes, uint64_t *ticket)
+                   uint8_t *out, uint64_t out_bytes, uint64_t *ticket, const b200sdf_tile_job *ext_tiles = nullptr,
+                   size_t n_ext_tiles = 0)
 {
 	// B200SDF_TRACE=1: report submissions slower than 200 us with per-phase timestamps (diagnostics)
 	static const bool trace = std::getenv("B200SDF_TRACE") != nullptr;
@@ -386,7 +390,7 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 	cudaError_t e = cudaSetDevice(ctx->device);
 	if (e != cudaSuccess)
 		return release_slot(ctx, s, fail_cuda(ctx, e, "cudaSetDevice"));
-	const size_t n_tiles = plan.size();
+	const size_t n_tiles = ext_tiles ? n_ext_tiles : plan.size();
 	// Size a slot's buffers to the largest request any slot of this context has seen: a slot then
 	// (re)allocates at most once after the workload's largest batch has shown up, instead of stalling
 	// the context with cudaFree/cudaMalloc whenever it first meets a bigger batch.
@@ -396,10 +400,24 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 	const bool zc = zero_copy_enabled();
 	const void *k_ojobs = zc && n_ojobs ? pinned_registry().device_ptr(ojobs, need[2]) : nullptr;
 	void *k_out = zc && out_bytes ? pinned_registry().device_ptr(out, need[4]) : nullptr;
+	// Curve lists are read ONCE per CTA with a bulk copy into shared memory when they fit there; only then
+	// is reading them in place (over PCIe) as good as a staged copy.  A glyph with more curve records than
+	// the kernel keeps in shared memory searches them in global memory: such a batch is staged.
+	const void *k_curves = nullptr;
+	if (zc && n_curves && B200SDF_ZEROCOPY_CURVES) {
+		uint32_t most = 0;
+		for (uint32_t i = 0; i < n_ojobs; ++i)
+			if (ojobs[i].kind == B200SDF_KIND_CURVES)
+				most = std::max(most, ojobs[i].src_cnt);
+		if (most <= (uint32_t)B200SDF_CURVE_SMEM)
+			k_curves = pinned_registry().device_ptr(curves, need[1]);
+	}
 	if (k_ojobs)
 		need[2] = 0; // no device mirror needed
 	if (k_out)
 		need[4] = 0;
+	if (k_curves)
+		need[1] = 0;
 	const size_t tiles_bytes = need[3];
 	{
 		std::lock_guard<std::mutex> g(ctx->mu);
@@ -418,43 +436,19 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 	int rc;
 	if ((rc = grow_device(ctx, s.segs, need[0], s.stream)) || (rc = grow_device(ctx, s.curves, need[1], s.stream)) ||
 	    (rc = grow_device(ctx, s.ojobs, need[2], s.stream)) || (rc = grow_device(ctx, s.tiles, need[3], s.stream)) ||
-	    (rc = grow_device(ctx, s.out, need[4], s.stream)) || (rc = grow_pinned(ctx, &s.h_tiles, &s.h_tiles_cap, need[3])))
+	    (rc = grow_device(ctx, s.out, need[4], s.stream)) || (rc = ext_tiles ? 0 : grow_pinned(ctx, &s.h_tiles, &s.h_tiles_cap, need[3])))
 		return release_slot(ctx, s, rc);
 	(void)tiles_bytes;
 	if (trace)
 		tt[2] = now();
-	b200sdf_tile_job *ht = reinterpret_cast<b200sdf_tile_job *>(s.h_tiles);
-	for (size_t i = 0; i < n_tiles; ++i)
-		ht[i] = plan[i].t;
+	const b200sdf_tile_job *ht = ext_tiles;
+	if (!ext_tiles) {
+		b200sdf_tile_job *mine = reinterpret_cast<b200sdf_tile_job *>(s.h_tiles);
+		for (size_t i = 0; i < n_tiles; ++i)
+			mine[i] = plan[i].t;
+		ht = mine;
+	}
 
-	// B200SDF_SERIALIZE=1|2: enqueue under a process-wide spin lock (experiment: driver-side contention)
-	static const int serialize = [] {
-		const char *e = std::getenv("B200SDF_SERIALIZE");
-		return e ? std::atoi(e) : 0;
-	}();
-	struct SpinGuard {
-		static std::atomic<int> &flag()
-		{
-			static std::atomic<int> f{0};
-			return f;
-		}
-		bool on;
-		explicit SpinGuard(bool o) : on(o)
-		{
-			if (!on)
-				return;
-			int z = 0;
-			while (!flag().compare_exchange_weak(z, 1, std::memory_order_acquire)) {
-				z = 0;
-				__builtin_ia32_pause();
-			}
-		}
-		~SpinGuard()
-		{
-			if (on)
-				flag().store(0, std::memory_order_release);
-		}
-	} spin_guard(serialize != 0);
 #define SUB_TRY(call)                                                \
 	do {                                                             \
 		cudaError_t e_ = (call);                                     \
@@ -463,8 +457,10 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 	} while (0)
 	if (n_seg)
 		SUB_TRY(cudaMemcpyAsync(s.segs.p, segs, (size_t)n_seg * sizeof(b200sdf_segment), cudaMemcpyHostToDevice, s.stream));
-	if (n_curves)
+	if (n_curves && !k_curves) {
 		SUB_TRY(cudaMemcpyAsync(s.curves.p, curves, (size_t)n_curves * sizeof(b200sdf_curve), cudaMemcpyHostToDevice, s.stream));
+		k_curves = s.curves.p;
+	}
 	if (trace)
 		tt[3] = now();
 	const void *k_tiles = zc && n_tiles ? pinned_registry().device_ptr(ht, n_tiles * sizeof(b200sdf_tile_job)) : nullptr;
@@ -479,19 +475,19 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 		}
 		// Bitmaps may be sparse in `out` (caller-chosen out_off): bytes between bitmaps are defined (zero).
 		uint64_t covered = 0;
-		for (const Planned &p : plan)
-			if (p.t.tx0 == 0 && p.t.ty0 == 0)
-				covered += (uint64_t)p.t.width * p.t.height;
+		for (size_t i = 0; i < n_tiles; ++i)
+			if (ht[i].tx0 == 0 && ht[i].ty0 == 0)
+				covered += (uint64_t)ht[i].width * ht[i].height;
 		if (k_out) {
 			if (covered < out_bytes)
 				std::memset(out, 0, (size_t)out_bytes); // the caller's buffer is ours until wait()
-			launch_sdf(s.segs.p, s.curves.p, k_ojobs, k_tiles, (uint32_t)n_tiles, k_out, s.stream);
+			launch_sdf(s.segs.p, k_curves, k_ojobs, k_tiles, (uint32_t)n_tiles, k_out, s.stream);
 			SUB_TRY(cudaGetLastError());
 		} else {
 			// staged: the device buffer mirrors the layout and is copied back whole
 			if (covered < out_bytes)
 				SUB_TRY(cudaMemsetAsync(s.out.p, 0, (size_t)out_bytes, s.stream));
-			launch_sdf(s.segs.p, s.curves.p, k_ojobs, k_tiles, (uint32_t)n_tiles, s.out.p, s.stream);
+			launch_sdf(s.segs.p, k_curves, k_ojobs, k_tiles, (uint32_t)n_tiles, s.out.p, s.stream);
 			SUB_TRY(cudaGetLastError());
 			SUB_TRY(cudaMemcpyAsync(out, s.out.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, s.stream));
 		}
@@ -712,6 +708,18 @@ int b200sdf_submit_outlines(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint3
 	return submit_planned(ctx, plan, curves, n_curves, segs, n_seg, jobs, n_jobs, out, out_bytes, ticket);
 }
 
+int b200sdf_submit_planned(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint32_t n_curves, const b200sdf_segment *segs,
+                           uint32_t n_seg, const b200sdf_outline_job *jobs, uint32_t n_jobs, const b200sdf_tile_job *tiles,
+                           uint32_t n_tiles, uint8_t *out, uint64_t out_bytes, uint64_t *ticket)
+{
+	if (!ctx || !ticket)
+		return B200SDF_E_ARG;
+	if ((n_seg && !segs) || (n_curves && !curves) || (n_jobs && !jobs) || (out_bytes && !out) || (n_tiles && !tiles))
+		return fail_arg(ctx, "submit_planned: null buffer");
+	static const std::vector<Planned> none;
+	return submit_planned(ctx, none, curves, n_curves, segs, n_seg, jobs, n_jobs, out, out_bytes, ticket, tiles, n_tiles);
+}
+
 int b200sdf_wait(b200sdf_ctx *ctx, uint64_t ticket)
 {
 	if (!ctx)
@@ -725,22 +733,33 @@ int b200sdf_wait(b200sdf_ctx *ctx, uint64_t ticket)
 		}
 	}
 	Slot &s = ctx->slots[si];
-	static const bool poll = [] {
-		const char *v = std::getenv("B200SDF_SERIALIZE");
-		return v && std::atoi(v) >= 2;
-	}();
-	cudaError_t e;
-	if (poll) {
-		while ((e = cudaEventQuery(s.done)) == cudaErrorNotReady)
-			for (int k = 0; k < 64; ++k)
-				__builtin_ia32_pause();
-	} else {
-		e = cudaEventSynchronize(s.done);
-	}
+	const cudaError_t e = cudaEventSynchronize(s.done);
 	release_slot(ctx, s, 0);
 	if (e != cudaSuccess)
 		return fail_cuda(ctx, e, "cudaEventSynchronize");
 	return 0;
+}
+
+int b200sdf_poll(b200sdf_ctx *ctx, uint64_t ticket)
+{
+	if (!ctx)
+		return B200SDF_E_ARG;
+	const size_t si = (size_t)(ticket & 0xff);
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		if (si >= ctx->slots.size() || !ctx->slots[si].busy || ctx->slots[si].generation != (ticket >> 8)) {
+			ctx->err = "poll: unknown ticket";
+			return B200SDF_E_TICKET;
+		}
+	}
+	Slot &s = ctx->slots[si];
+	const cudaError_t e = cudaEventQuery(s.done);
+	if (e == cudaErrorNotReady)
+		return 0;
+	release_slot(ctx, s, 0);
+	if (e != cudaSuccess)
+		return fail_cuda(ctx, e, "cudaEventQuery");
+	return 1;
 }
 
 int b200sdf_render(b200sdf_ctx *ctx, const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_glyph_job *jobs,

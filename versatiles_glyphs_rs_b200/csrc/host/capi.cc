@@ -324,6 +324,19 @@ int vgb_renderer_submit_batch(const vgb_renderer *r, vgb_batch *b, uint64_t *tic
 	std::string err;
 	return r->r->submit_batch(*b->b, ticket, &err) ? 0 : fail(err);
 }
+int vgb_renderer_prepare_batch(const vgb_renderer *r, vgb_batch *b)
+{
+	std::string err;
+	return r->r->prepare_batch(*b->b, &err) ? 0 : fail(err);
+}
+int vgb_renderer_poll_batch(const vgb_renderer *r, uint64_t ticket)
+{
+	std::string err;
+	bool done = false;
+	if (!r->r->poll_batch(ticket, &done, &err))
+		return fail(err);
+	return done ? 1 : 0;
+}
 int vgb_renderer_wait_batch(const vgb_renderer *r, uint64_t ticket)
 {
 	std::string err;

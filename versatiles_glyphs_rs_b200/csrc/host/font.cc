@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <condition_variable>
 #include <fstream>
 #include <functional>
@@ -386,6 +387,14 @@ bool FontManager::write_families_json(Writer &writer, std::string *err) const
 }
 
 namespace {
+inline void cpu_pause()
+{
+#if defined(__x86_64__) || defined(__i386__)
+	__builtin_ia32_pause();
+#else
+	std::this_thread::yield();
+#endif
+}
 inline uint64_t now_ns()
 {
 	return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
@@ -402,7 +411,9 @@ class WorkerPool {
 		static WorkerPool *p = new WorkerPool(); // intentionally leaked: workers must outlive static destructors
 		return *p;
 	}
-	void run(int n, const std::function<void(int)> &fn)
+	// run fn(0..n-1) on the pool and, meanwhile, `here` on the calling thread (which is already running on a
+	// core: the pipeline's submitter must not wait for a sleeping pool thread to be scheduled)
+	void run(int n, const std::function<void(int)> &fn, const std::function<void()> &here = nullptr)
 	{
 		std::lock_guard<std::mutex> serial(run_mu_);
 		{
@@ -417,6 +428,8 @@ class WorkerPool {
 			++generation_;
 		}
 		cv_.notify_all();
+		if (here)
+			here();
 		std::unique_lock<std::mutex> lk(mu_);
 		done_cv_.wait(lk, [this] { return remaining_ == 0; });
 		fn_ = nullptr;
@@ -531,17 +544,19 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	if (parallel_) {
 		workers = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
 		workers = std::max(1, std::min(workers, 32));
-		// each worker keeps two batches in flight; never more than the renderer has slots for
-		if (renderer.mode() == Renderer::Mode::Cuda)
-			workers = std::max(1, std::min(workers, (int)renderer.slots() / 2));
+		// the CUDA pipeline runs one extra thread that owns all CUDA traffic (see below): by default it gets
+		// a core of its own
+		if (renderer.mode() == Renderer::Mode::Cuda && threads <= 0 && workers > 2)
+			workers -= 1;
 	}
 	// One submission carries whole blocks until it holds about `target` glyphs: small jobs keep one
 	// block per submission (parallelism), big jobs amortise the per-submission cost.
-	static const size_t kBatchesPerWorker = [] { // tuning knob (default 4)
+	static const size_t kBatchesPerWorker = [] { // tuning knob (default 4; measured 1..6 on C2)
 		const char *e = std::getenv("VGB_BATCHES_PER_WORKER");
 		const long v = e ? std::atol(e) : 0;
 		return (size_t)(v >= 1 && v <= 64 ? v : 4);
 	}();
+	constexpr int kEarlyWorkers = 4;
 	const size_t target = std::min<size_t>(2048, std::max<size_t>(1, total_glyphs / ((size_t)workers * kBatchesPerWorker)));
 	std::atomic<size_t> next{0};
 	std::atomic<size_t> glyphs_taken{0};
@@ -557,8 +572,29 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 
 	// VGB_TRACE=1: print a per-worker timeline (us since the call began) to stderr — diagnostics only
 	const bool trace = std::getenv("VGB_TRACE") != nullptr;
-	std::vector<std::vector<std::pair<char, uint64_t>>> events((size_t)workers);
+	std::vector<std::vector<std::pair<char, uint64_t>>> events((size_t)workers + 1); // [workers] = the submitter
 	const uint64_t t_setup = now_ns();
+
+	struct Part {
+		const Todo *todo;
+		size_t g0, g1;
+	};
+	struct Flight {
+		std::unique_ptr<GlyphBatch> batch;
+		std::vector<Part> parts;
+		uint64_t ticket = 0;
+	};
+	std::mutex qm;
+	std::condition_variable qcv;
+	std::deque<Flight *> submit_q, done_q;
+	size_t outstanding = 0; // batches submitted (or queued for it) and not yet encoded
+	int workers_done = 0;
+	std::atomic<uint64_t> submit_ns{0};
+	const bool inline_pump = workers == 1;
+	// never more batches on their way than the renderer has slots for (submit would block the submitter)
+	const size_t max_outstanding =
+	    renderer.mode() == Renderer::Mode::Cuda ? std::max<size_t>(2, renderer.slots()) : (size_t)(2 * workers + 2);
+	std::function<void(bool)> pump;
 
 	auto work = [&](int wid) {
 		RenderStats &st = per_worker[(size_t)wid];
@@ -615,123 +651,294 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				fail(e);
 			return ok;
 		};
-		// Two batches per worker: while batch A is on the GPU, batch B is being filled.
-		// (batches come from the renderer's pool: their pinned buffers survive across calls)
-		struct Part {
-			const Todo *todo;
-			size_t g0, g1;
-		};
-		struct Flight {
-			std::unique_ptr<GlyphBatch> batch;
-			std::vector<Part> parts;
-			uint64_t ticket = 0;
-			bool active = false;
-		} flights[2];
-		flights[0].batch = renderer.acquire_batch();
-		flights[1].batch = renderer.acquire_batch();
-		auto retire = [&](Flight &f) -> bool {
-			if (!f.active)
-				return true;
-			f.active = false;
-			std::string e;
-			uint64_t t0 = now_ns();
-			mark('w');
-			const bool waited = renderer.wait_batch(f.ticket, &e);
-			mark('W');
-			st.wait_ns += now_ns() - t0;
-			if (!waited) {
-				fail(e);
-				return false;
-			}
-			for (const Part &p : f.parts)
-				if (!finish_part(*p.todo, *f.batch, p.g0, p.g1))
-					return false;
-			return flush();
-		};
-		int k = 0;
+		// ---- the pipeline ------------------------------------------------------------------------------
+		// Workers only record outlines and encode results.  Every CUDA call (submit, completion polling) is
+		// made by ONE thread — the submitter: 16 threads entering the driver concurrently were measured to
+		// stall each other's launches for hundreds of microseconds.  Batches travel through two queues:
+		//   worker --submit_q--> submitter --(GPU)--> submitter --done_q--> any worker (encode, write)
+		// With a single worker (the reference's --single-thread) the worker pumps the queues itself.
 		unsigned n_batches = 0;
 		bool more = true;
-		while (more && !failed.load()) {
-			Flight &cur = flights[k];
-			cur.batch->clear();
-			cur.parts.clear();
-			mark('o');
-			uint64_t t0 = now_ns();
-			// Batch size: small first batches (the GPU starts early), the steady-state target, then a taper —
-			// the last batches of all workers are submitted together and their latency is the tail of the call.
-			const size_t left = total_glyphs - std::min(total_glyphs, glyphs_taken.load(std::memory_order_relaxed));
-			size_t want = std::min(target, std::max<size_t>(kPartGlyphs, left / ((size_t)workers * 2)));
-			if (n_batches < 2)
-				want = std::min(want, std::max<size_t>(kPartGlyphs, target >> (2 - n_batches)));
-			++n_batches;
-			while (cur.batch->glyphs().size() < want) {
-				const size_t ti = next.fetch_add(1);
-				if (ti >= tasks.size()) {
-					more = false;
-					break;
-				}
-				const Todo &todo = tasks[ti];
-				const size_t g0 = cur.batch->glyphs().size();
-				glyphs_taken.fetch_add(todo.glyphs, std::memory_order_relaxed);
-				todo.bs->block.append_to_batch(*cur.batch, todo.slot0, todo.slot1);
-				cur.parts.push_back(Part{&todo, g0, cur.batch->glyphs().size()});
-			}
-			st.outline_ns += now_ns() - t0;
-			if (cur.parts.empty())
+		for (;;) {
+			if (failed.load())
 				break;
-			st.glyphs += cur.batch->glyphs().size();
-			st.bitmaps += cur.batch->job_count();
-			st.pixels += cur.batch->bitmap_bytes();
-			st.segments += cur.batch->total_segments();
-			st.pairs += cur.batch->pairs();
-			if (cur.batch->job_count() == 0) {
-				// nothing to rasterise (empty blocks, or only bitmap-less glyphs): no GPU round trip
-				cur.ticket = ~0ull;
-				cur.active = false;
-				for (const Part &p : cur.parts)
-					if (!finish_part(*p.todo, *cur.batch, p.g0, p.g1))
-						break;
-				if (!flush())
+			// 1. finished batches first: encoding frees the batch and gets files out early
+			Flight *done = nullptr;
+			{
+				std::lock_guard<std::mutex> g(qm);
+				if (!done_q.empty()) {
+					done = done_q.front();
+					done_q.pop_front();
+				}
+			}
+			if (done) {
+				mark('e');
+				bool ok = true;
+				for (const Part &p : done->parts)
+					if (ok)
+						ok = finish_part(*p.todo, *done->batch, p.g0, p.g1);
+				ok = ok && flush();
+				renderer.release_batch(std::move(done->batch));
+				delete done;
+				{
+					std::lock_guard<std::mutex> g(qm);
+					--outstanding;
+				}
+				qcv.notify_all();
+				if (!ok)
 					break;
 				continue;
 			}
-			t0 = now_ns();
-			std::string e;
-			mark('s');
-			const bool submitted = renderer.submit_batch(*cur.batch, &cur.ticket, &e);
-			mark('S');
-			st.submit_ns += now_ns() - t0;
-			st.submits++;
-			if (!submitted) {
-				fail(e);
-				break;
+			// 2. record the next batch
+			if (more) {
+				{
+					std::unique_lock<std::mutex> lk(qm);
+					if (outstanding >= max_outstanding) { // back-pressure: wait for a completion
+						if (inline_pump)
+							lk.unlock(), pump(true);
+						else
+							qcv.wait_for(lk, std::chrono::milliseconds(50),
+							             [&] { return !done_q.empty() || outstanding < max_outstanding || failed.load(); });
+						continue;
+					}
+					++outstanding; // reserve the place now: several workers pass this check at the same time
+				}
+				std::unique_ptr<Flight> cur(new Flight());
+				cur->batch = renderer.acquire_batch();
+				mark('o');
+				uint64_t t0 = now_ns();
+				// Batch size.  One thread enqueues every batch (about 10 us each), so batches are as large as the
+				// pipeline allows: a few workers open with a single part so that the GPU starts early, the rest
+				// record `target` glyphs at a time, and the size tapers with the work that is left — the last
+				// batches of all workers are submitted together and their latency is the tail of the call.
+				const size_t left = total_glyphs - std::min(total_glyphs, glyphs_taken.load(std::memory_order_relaxed));
+				// (half of each worker's share of what is left: sizes fall geometrically towards the end)
+				size_t want = std::max<size_t>(kPartGlyphs, std::min(target, left / ((size_t)workers * 2)));
+				if (n_batches == 0) // staggered openings: the workers do not all submit at the same moments
+					want = wid < kEarlyWorkers ? kPartGlyphs : std::min(target, kPartGlyphs * (size_t)(1 + wid % 4));
+				++n_batches;
+				while (cur->batch->glyphs().size() < want) {
+					const size_t ti = next.fetch_add(1);
+					if (ti >= tasks.size()) {
+						more = false;
+						break;
+					}
+					const Todo &todo = tasks[ti];
+					const size_t g0 = cur->batch->glyphs().size();
+					glyphs_taken.fetch_add(todo.glyphs, std::memory_order_relaxed);
+					todo.bs->block.append_to_batch(*cur->batch, todo.slot0, todo.slot1);
+					cur->parts.push_back(Part{&todo, g0, cur->batch->glyphs().size()});
+				}
+				st.outline_ns += now_ns() - t0;
+				if (cur->parts.empty()) {
+					renderer.release_batch(std::move(cur->batch));
+					std::lock_guard<std::mutex> g(qm);
+					--outstanding;
+					continue;
+				}
+				st.glyphs += cur->batch->glyphs().size();
+				st.bitmaps += cur->batch->job_count();
+				st.pixels += cur->batch->bitmap_bytes();
+				st.segments += cur->batch->total_segments();
+				st.pairs += cur->batch->pairs();
+				if (cur->batch->job_count() == 0) {
+					// nothing to rasterise (empty blocks, or only bitmap-less glyphs): no GPU round trip
+					bool ok = true;
+					for (const Part &p : cur->parts)
+						if (ok)
+							ok = finish_part(*p.todo, *cur->batch, p.g0, p.g1);
+					ok = ok && flush();
+					renderer.release_batch(std::move(cur->batch));
+					{
+						std::lock_guard<std::mutex> g(qm);
+						--outstanding;
+					}
+					qcv.notify_all();
+					if (!ok)
+						break;
+					continue;
+				}
+				st.submits++;
+				{
+					// everything that is not a CUDA call happens here, in the worker: bitmap buffer, tile planning
+					std::string e;
+					t0 = now_ns();
+					const bool prepared = renderer.prepare_batch(*cur->batch, &e);
+					st.submit_ns += now_ns() - t0;
+					if (!prepared) {
+						fail(e);
+						renderer.release_batch(std::move(cur->batch));
+						std::lock_guard<std::mutex> g(qm);
+						--outstanding;
+						break;
+					}
+				}
+				mark('s');
+				{
+					std::lock_guard<std::mutex> g(qm);
+					submit_q.push_back(cur.release());
+				}
+				if (inline_pump)
+					pump(false);
+				continue;
 			}
-			cur.active = true;
-			k ^= 1;
-			if (!retire(flights[k]))
-				break;
-		}
-		for (Flight &f : flights) {
-			if (f.active && failed.load()) {
-				renderer.wait_batch(f.ticket, nullptr); // drain; results are dropped
-				f.active = false;
+			// 3. nothing left to record: help until every batch has come back
+			{
+				std::unique_lock<std::mutex> lk(qm);
+				if (outstanding == 0)
+					break;
+				if (!done_q.empty())
+					continue;
+				const uint64_t t0 = now_ns();
+				if (inline_pump)
+					lk.unlock(), pump(true);
+				else
+					qcv.wait_for(lk, std::chrono::milliseconds(50), [&] { return !done_q.empty() || outstanding == 0 || failed.load(); });
+				st.wait_ns += now_ns() - t0;
 			}
-			retire(f);
-			renderer.release_batch(std::move(f.batch));
 		}
+		flush();
 		mark('E');
 	};
 
-	if (workers == 1) {
+	// The submitter: submit whatever the workers queued, poll what is in flight, hand back what finished.
+	// (With one worker it is called inline: `block` = nothing else to do, wait for the oldest batch.)
+	std::deque<Flight *> inflight; // touched by the pumping thread only
+	pump = [&](bool block) {
+		bool progressed = false;
+		for (;;) {
+			Flight *f = nullptr;
+			{
+				std::lock_guard<std::mutex> g(qm);
+				if (!submit_q.empty()) {
+					f = submit_q.front();
+					submit_q.pop_front();
+				}
+			}
+			if (f) {
+				std::string e;
+				const uint64_t t0 = now_ns();
+				if (trace)
+					events[(size_t)workers].emplace_back('s', t0 - t_begin);
+				const bool ok = renderer.submit_batch(*f->batch, &f->ticket, &e);
+				submit_ns.fetch_add(now_ns() - t0, std::memory_order_relaxed);
+				if (trace)
+					events[(size_t)workers].emplace_back('S', now_ns() - t_begin);
+				if (ok) {
+					inflight.push_back(f);
+				} else {
+					fail(e);
+					f->parts.clear(); // results are dropped
+					{
+						std::lock_guard<std::mutex> g(qm);
+						done_q.push_back(f);
+					}
+					qcv.notify_all();
+				}
+			}
+			// a polling sweep after every submission: slots come back only through here.  Batches finish
+			// roughly in submission order, so only the oldest few are asked (a query costs about a microsecond).
+			const size_t sweep = f ? 2 : 6;
+			for (size_t i = 0; i < inflight.size() && i < sweep;) {
+				Flight *q = inflight[i];
+				bool finished = false;
+				std::string e;
+				bool ok;
+				if (block && !f && i == 0 && !progressed) {
+					ok = renderer.wait_batch(q->ticket, &e);
+					finished = true;
+				} else {
+					ok = renderer.poll_batch(q->ticket, &finished, &e);
+				}
+				if (!ok) {
+					fail(e);
+					q->parts.clear();
+					finished = true;
+				}
+				if (!finished) {
+					++i;
+					continue;
+				}
+				progressed = true;
+				if (trace)
+					events[(size_t)workers].emplace_back('d', now_ns() - t_begin);
+				inflight.erase(inflight.begin() + (long)i);
+				{
+					std::lock_guard<std::mutex> g(qm);
+					done_q.push_back(q);
+				}
+				qcv.notify_one();
+			}
+			if (!f)
+				break;
+		}
+	};
+	auto submitter = [&]() {
+		// watchdog: a pipeline that makes no progress for this long is reported as an error instead of hanging
+		static const uint64_t stall_ns = [] {
+			const char *e = std::getenv("VGB_STALL_SECONDS");
+			const double v = e ? std::atof(e) : 0.0;
+			return (uint64_t)((v > 0.0 ? v : 60.0) * 1e9);
+		}();
+		uint64_t last_progress = now_ns();
+		size_t last_state = ~(size_t)0;
+		for (;;) {
+			pump(false);
+			size_t state;
+			{
+				std::lock_guard<std::mutex> g(qm);
+				if (workers_done == workers && submit_q.empty() && inflight.empty())
+					break;
+				state = next.load() * 131 + outstanding * 17 + done_q.size() * 7 + inflight.size() + (size_t)workers_done * 1000003;
+			}
+			const uint64_t t = now_ns();
+			if (state != last_state) {
+				last_state = state;
+				last_progress = t;
+			} else if (t - last_progress > stall_ns && !failed.load()) {
+				std::lock_guard<std::mutex> g(qm);
+				fail("render_glyphs pipeline stalled: tasks " + std::to_string(next.load()) + "/" + std::to_string(tasks.size()) +
+				     ", outstanding " + std::to_string(outstanding) + ", in flight " + std::to_string(inflight.size()) +
+				     ", to submit " + std::to_string(submit_q.size()) + ", done " + std::to_string(done_q.size()) +
+				     ", workers done " + std::to_string(workers_done) + "/" + std::to_string(workers));
+				qcv.notify_all();
+				last_progress = t;
+			}
+			for (int k = 0; k < 16; ++k)
+				cpu_pause();
+		}
+	};
+
+	if (inline_pump) {
 		work(0);
 	} else {
-		WorkerPool::instance().run(workers, work);
+		WorkerPool::instance().run(
+		    workers,
+		    [&](int id) {
+			    work(id);
+			    std::lock_guard<std::mutex> g(qm);
+			    ++workers_done;
+		    },
+		    submitter); // the calling thread is the submitter
 	}
+	// error paths leave batches behind: nothing is in flight any more (the submitter drained), free them
+	if (inline_pump)
+		while (!inflight.empty()) {
+			renderer.wait_batch(inflight.front()->ticket, nullptr);
+			done_q.push_back(inflight.front());
+			inflight.pop_front();
+		}
+	for (std::deque<Flight *> *q : {&submit_q, &done_q})
+		for (Flight *f : *q) {
+			if (f->batch)
+				renderer.release_batch(std::move(f->batch));
+			delete f;
+		}
 	if (trace) {
 		std::fprintf(stderr, "[vgb trace] setup %.1f us, %d workers, %zu tasks, target %zu glyphs, total %.1f us\n",
 		             (double)(t_setup - t_begin) * 1e-3, workers, tasks.size(), target, (double)(now_ns() - t_begin) * 1e-3);
-		for (int w = 0; w < workers; ++w) {
-			std::fprintf(stderr, "[vgb trace] w%02d", w);
+		for (int w = 0; w <= workers; ++w) {
+			std::fprintf(stderr, "[vgb trace] %c%02d", w == workers ? 'S' : 'w', w);
 			for (const auto &e : events[(size_t)w])
 				std::fprintf(stderr, " %c%.0f", e.first, (double)e.second * 1e-3);
 			std::fprintf(stderr, "\n");
@@ -754,6 +961,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			stats->write_ns += s.write_ns;
 			stats->submits += s.submits;
 		}
+		stats->submit_ns += submit_ns.load();
 		stats->workers = (uint64_t)workers;
 		stats->wall_ns = now_ns() - t_begin;
 	}

@@ -2,6 +2,7 @@
 #include "render.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -262,13 +263,46 @@ bool HostBuffer::reserve(size_t bytes, size_t keep, bool exact)
 }
 
 // ---- GlyphBatch ------------------------------------------------------------------------------------
-GlyphBatch::GlyphBatch(bool pinned, Flatten mode) : mode_(mode), jobs_(pinned), segs_(pinned), curves_(pinned), out_(pinned) {}
+GlyphBatch::GlyphBatch(bool pinned, Flatten mode)
+    : mode_(mode), jobs_(pinned), segs_(pinned), curves_(pinned), out_(pinned), tiles_(pinned)
+{
+}
 
 void GlyphBatch::clear()
 {
 	glyphs_.clear();
 	n_jobs_ = n_seg_ = n_curves_ = n_fallback_ = 0;
 	total_seg_ = out_bytes_ = pairs_ = 0;
+	n_tiles_ = 0;
+	prepared_ = false;
+}
+
+bool GlyphBatch::plan_tiles(const char **why)
+{
+	*why = "";
+	// most glyphs are one tile job; heavy ones are cut into several: start generous, retry once if short
+	uint32_t cap = std::max<uint32_t>(64u, n_jobs_ * 2u + 64u);
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		if (!tiles_.reserve((size_t)cap * sizeof(b200sdf_tile_job), 0)) {
+			*why = "out of host memory for the tile list";
+			return false;
+		}
+		uint32_t n = 0;
+		const int rc = b200sdf_plan_outline_tiles(jobs(), n_jobs_, n_curves_, n_seg_, out_bytes_,
+		                                          reinterpret_cast<b200sdf_tile_job *>(tiles_.data()), cap, &n, nullptr);
+		if (rc != 0 && n <= cap) { // (a short buffer also answers non-zero, with the needed count in n)
+			*why = "invalid outline job (b200sdf_plan_outline_tiles)";
+			return false;
+		}
+		if (rc == 0 && n <= cap) {
+			n_tiles_ = n;
+			prepared_ = true;
+			return true;
+		}
+		cap = n;
+	}
+	*why = "tile planning did not converge";
+	return false;
 }
 
 bool GlyphBatch::push_job(const b200sdf_outline_job &j)
@@ -548,6 +582,24 @@ void Renderer::release_batch(std::unique_ptr<GlyphBatch> b) const
 		pool_.push_back(std::move(b));
 }
 
+bool Renderer::prepare_batch(GlyphBatch &batch, std::string *err) const
+{
+	if (!batch.ensure_output()) {
+		if (err)
+			*err = "out of host memory for the bitmap buffer";
+		return false;
+	}
+	if (mode_ == Mode::Dummy)
+		return true;
+	const char *why = "";
+	if (!batch.plan_tiles(&why)) {
+		if (err)
+			*err = why;
+		return false;
+	}
+	return true;
+}
+
 bool Renderer::submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *err) const
 {
 	if (!batch.ensure_output()) {
@@ -561,11 +613,16 @@ bool Renderer::submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *er
 		*ticket = ~0ull;
 		return true;
 	}
-	const int rc = b200sdf_submit_outlines(ctx_, batch.curves(), batch.curve_count(), batch.segments(), batch.segment_count(),
-	                                       batch.jobs(), batch.job_count(), batch.bitmaps(), batch.bitmap_bytes(), ticket);
+	const int rc =
+	    batch.prepared()
+	        ? b200sdf_submit_planned(ctx_, batch.curves(), batch.curve_count(), batch.segments(), batch.segment_count(),
+	                                 batch.jobs(), batch.job_count(), batch.tiles(), batch.tile_count(), batch.bitmaps(),
+	                                 batch.bitmap_bytes(), ticket)
+	        : b200sdf_submit_outlines(ctx_, batch.curves(), batch.curve_count(), batch.segments(), batch.segment_count(),
+	                                  batch.jobs(), batch.job_count(), batch.bitmaps(), batch.bitmap_bytes(), ticket);
 	if (rc != 0) {
 		if (err)
-			*err = std::string("b200sdf_submit_outlines: ") + b200sdf_last_error(ctx_);
+			*err = std::string("b200sdf_submit: ") + b200sdf_last_error(ctx_);
 		return false;
 	}
 	return true;
@@ -581,6 +638,28 @@ bool Renderer::wait_batch(uint64_t ticket, std::string *err) const
 			*err = std::string("b200sdf_wait: ") + b200sdf_last_error(ctx_);
 		return false;
 	}
+	return true;
+}
+
+bool Renderer::poll_batch(uint64_t ticket, bool *done, std::string *err) const
+{
+	*done = true;
+	if (mode_ == Mode::Dummy) {
+		// test hook: VGB_FAKE_LATENCY makes the dummy renderer report "still running" most of the time, so the
+		// CPU tests exercise the asynchronous paths of the pipeline (tests/test_host_vs_oracle.py)
+		static const bool fake = std::getenv("VGB_FAKE_LATENCY") != nullptr;
+		static std::atomic<unsigned> n{0};
+		if (fake && (n.fetch_add(1) % 7) != 0)
+			*done = false;
+		return true;
+	}
+	const int rc = b200sdf_poll(ctx_, ticket);
+	if (rc < 0) {
+		if (err)
+			*err = std::string("b200sdf_poll: ") + b200sdf_last_error(ctx_);
+		return false;
+	}
+	*done = rc == 1;
 	return true;
 }
 

@@ -195,6 +195,12 @@ class GlyphBatch {
 	uint64_t bitmap_bytes() const { return out_bytes_; }
 	uint64_t pairs() const { return pairs_; }
 	bool ensure_output(); // allocate the bitmap area (after the last add)
+	// plan the CTA work items of the recorded jobs into the batch's own (pinned) tile buffer; false + *why
+	// when a job is invalid.  After this, tiles()/tile_count() feed b200sdf_submit_planned.
+	bool plan_tiles(const char **why);
+	bool prepared() const { return prepared_; }
+	const b200sdf_tile_job *tiles() const { return reinterpret_cast<const b200sdf_tile_job *>(tiles_.data()); }
+	uint32_t tile_count() const { return n_tiles_; }
 	// buffer capacities in bytes (jobs, segments, curves, bitmaps) — the pool sizes new leases from them
 	void capacities(size_t caps[4]) const;
 	void reserve_capacity(const size_t caps[4]);
@@ -210,6 +216,9 @@ class GlyphBatch {
 	OutlineRecorder recorder_;
 	std::vector<BatchGlyph> glyphs_;
 	HostBuffer jobs_, segs_, curves_, out_;
+	HostBuffer tiles_;       // CTA work items planned by prepare() (pipeline: planned in the worker thread)
+	uint32_t n_tiles_ = 0;
+	bool prepared_ = false;
 	uint32_t n_jobs_ = 0, n_seg_ = 0, n_curves_ = 0, n_fallback_ = 0;
 	uint64_t total_seg_ = 0, out_bytes_ = 0, pairs_ = 0;
 };
@@ -243,6 +252,11 @@ class Renderer {
 	// Asynchronous form: several batches in flight on the context's streams.
 	bool submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *err = nullptr) const;
 	bool wait_batch(uint64_t ticket, std::string *err = nullptr) const;
+	// Two-step submission for pipelines with one CUDA thread: prepare_batch (any thread: sizes the bitmap
+	// buffer, validates the jobs and plans the tiles) then submit_batch (enqueue only).
+	bool prepare_batch(GlyphBatch &batch, std::string *err = nullptr) const;
+	// non-blocking: *done = the batch has finished (the ticket is consumed, as by wait_batch)
+	bool poll_batch(uint64_t ticket, bool *done, std::string *err = nullptr) const;
 
   private:
 	Renderer() = default;
