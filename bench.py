@@ -11,10 +11,18 @@ configs[1], the 20-file Noto Sans `merge`, 6480 glyphs / 6445 bitmaps / 3.96 M s
   value      glyphs/s with segments, tile jobs and bitmaps resident in HBM: K kernel launches, each
              timed with CUDA events on the launching stream; L2 is flushed between launches.
   e2e        glyphs/s through the reference-facing host API (FontManager.render_glyphs: parsed fonts
-             in host memory -> PBF bytes in host memory): flattening, H2D, kernel, D2H, PBF encode.
-  roofline   FP32-ALU bound (north star): achieved = 11 flop x executed pixel x segment pairs / kernel
-             time, peak = FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no
-             FP32 figure); HBM figures for the same launch are reported beside it.
+             in host memory -> PBF bytes in host memory): outline recording, host->device transfer of
+             the records, kernel, device->host transfer of the bitmaps, PBF encode.  The transfers are
+             in the timed region; with pinned buffers they are zero-copy (the kernel reads the records
+             and writes the bitmaps across PCIe itself), h2d/d2h_bytes_per_step are those bytes.
+  roofline   FP32-ALU bound (north star).  The kernel computes min over segments as
+             min(vertices) + band interiors of short segments + clamped projection of long segments
+             (DESIGN.md §3.3), so `achieved` counts the flops of THAT formulation:
+             3 flop per pixel x vertex (one FFMA + one min) + 11 flop per pixel x long segment, over kernel
+             time; `bruteforce_equivalent` restates the same launch as SURVEY.md §8(d)'s 11 flop x
+             pixel x segment pairs (what a brute-force kernel would have to sustain for this time).
+             peak = FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32
+             figure); HBM figures for the same launch are reported beside it.
   cpu_baseline  the oracle (C port of the reference's CPU algorithm) on the box's host cores.
 
 Under torchrun each rank renders the same workload on its own GPU (font x block shards are
@@ -33,7 +41,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-FLOP_PER_PAIR = 11  # pax 1, t 2, qx 2, qy 2, d2 3, min 1
+FLOP_PER_PAIR = 11  # pax 1, t 2, qx 2, qy 2, d2 3, min 1 (brute force / long segments)
+FLOP_PER_VERTEX_PAIR = 3  # fma(pax, pax, pay^2) 2, min 1
+LONG_L2 = 0.25  # sdf_kernel.cuh kLongL2: squared length above which a segment takes the clamped projection
 METRIC = "SDF glyphs/sec (24px, buffer 3)"
 
 
@@ -284,7 +294,29 @@ def main():
 
     value = world * n_bitmaps / (ms_per_step * 1e-3)
     kernel_s = statistics.mean(kernel_ms) * 1e-3
-    achieved_tflops = FLOP_PER_PAIR * pairs / kernel_s / 1e12
+    # executed flops of the kernel's formulation (computed outside the timed region, from the device's own
+    # flattening): per glyph W*H * (3 * vertices + 11 * long segments); SEGMENTS glyphs stage both end points
+    flat = ctx.flatten_outlines(curves, jobs) if len(curves) else np.zeros((0, 4), np.float32)
+    l2 = (flat[:, 2] - flat[:, 0]) ** 2 + (flat[:, 3] - flat[:, 1]) ** 2
+    is_curves = (jobs["kind"] == 0) if n_bitmaps else np.zeros(0, bool)  # B200SDF_KIND_CURVES
+    seg_cnt = jobs["seg_cnt"].astype(np.int64)
+    px = jobs["width"].astype(np.int64) * jobs["height"].astype(np.int64)
+    starts = np.concatenate([[0], np.cumsum(np.where(is_curves, seg_cnt, 0))])[:-1]
+    long_per_job = np.zeros(n_bitmaps, np.int64)
+    long_mask = (l2 > LONG_L2).astype(np.int64)
+    csum = np.concatenate([[0], np.cumsum(long_mask)])
+    long_per_job[is_curves] = (csum[(starts + seg_cnt)[is_curves]] - csum[starts[is_curves]])
+    if len(segs) and (~is_curves).any():  # host-flattened glyphs: classify their uploaded segments
+        sl2 = (segs[:, 2] - segs[:, 0]) ** 2 + (segs[:, 3] - segs[:, 1]) ** 2
+        scs = np.concatenate([[0], np.cumsum((sl2 > LONG_L2).astype(np.int64))])
+        so = jobs["src_off"].astype(np.int64)
+        long_per_job[~is_curves] = (scs[(so + seg_cnt)[~is_curves]] - scs[so[~is_curves]])
+    vertices = np.where(is_curves, seg_cnt, 2 * seg_cnt)
+    vertex_pairs = int((px * vertices).sum())
+    long_pairs = int((px * long_per_job).sum())
+    executed_flop = FLOP_PER_VERTEX_PAIR * vertex_pairs + FLOP_PER_PAIR * long_pairs
+    achieved_tflops = executed_flop / kernel_s / 1e12
+    equivalent_tflops = FLOP_PER_PAIR * pairs / kernel_s / 1e12
     in_bytes = len(segs) * 16 + len(curves) * 32 + len(jobs) * 56 + n_tiles * 32
     alg_bytes = in_bytes + out_bytes
     peaks = {}
@@ -314,7 +346,15 @@ def main():
             "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
             "frac": achieved_tflops / fp32_peak_tflops, "traffic": traffic,
             "peak_source": "FFMA-chain microbenchmark in this run (b200sdf_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
-            "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": int(pairs), "kernel_ms": kernel_s * 1e3,
+            "flop_model": "3 flop x pixel x vertex (FFMA + min) + 11 flop x pixel x long segment (|d| > 0.5 px); band "
+                          "rasterisation and staging not credited",
+            "vertex_pairs_per_launch": vertex_pairs, "long_segment_pairs_per_launch": long_pairs,
+            "flop_per_launch": int(executed_flop),
+            "bruteforce_equivalent": {"flop_per_pair": FLOP_PER_PAIR, "tflops": equivalent_tflops,
+                                      "frac_of_peak": equivalent_tflops / fp32_peak_tflops,
+                                      "note": "SURVEY.md 8(d) accounting: what a brute-force pixel x segment kernel would "
+                                              "have to sustain to match this launch time"},
+            "pairs_per_launch": int(pairs), "kernel_ms": kernel_s * 1e3,
             "peak_ffma2_tflops": fp32x2_peak_tflops,
             "pairs_per_s": pairs / kernel_s,
             "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / kernel_s / 1e9,
@@ -327,7 +367,8 @@ def main():
     if not args.kernel_only:
         e2e_steps = args.e2e_steps or min(args.steps, 20)
         # the ranks of one box share its host cores: give each rank its share instead of oversubscribing
-        host_threads = max(1, (os.cpu_count() or 1) // world)
+        # (the calling thread is the pipeline's CUDA thread, so a rank runs its share minus one as workers)
+        host_threads = max(1, (os.cpu_count() or 1) // world - 1)
         for _ in range(max(3, args.warmup)):
             manager.render_glyphs(V.Writer.new_memory(), renderer, threads=host_threads)
         barrier()
@@ -343,7 +384,8 @@ def main():
             "value": world * st.glyphs * e2e_steps / e2e_s, "unit": "glyphs/s",
             "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(st.pixels),
             "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "pbf_bytes_per_step": int(st.pbf_bytes),
-            "api": "FontManager.render_glyphs(Writer.new_memory(), Renderer.new_precise()): outlines -> H2D -> flatten+SDF kernel -> D2H -> PBF",
+            "api": "FontManager.render_glyphs(Writer.new_memory(), Renderer.new_precise()): outline records in pinned host memory -> "
+                   "flatten+SDF kernel (reads them and writes the bitmaps over PCIe) -> PBF",
             "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
             "host_threads_per_rank": host_threads, "step_ms": [round(x, 3) for x in step_ms],
             "host_phases_ms_last_step": {

@@ -5,12 +5,12 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/gpu.csv 2>&1
 nproc > gpurun_out/nproc.txt
-python -m pytest tests -x -q -m gpu -s > gpurun_out/pytest_gpu.log 2>&1; rc=$?
+timeout 600 python -m pytest tests -x -q -m gpu -s > gpurun_out/pytest_gpu.log 2>&1; rc=$?
 tail -25 gpurun_out/pytest_gpu.log
 [ $rc -ne 0 ] && { echo "GPU TESTS FAILED rc=$rc"; exit $rc; }
-python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 || { cat gpurun_out/smoke.log; echo "SMOKE FAILED"; exit 1; }
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 || { cat gpurun_out/smoke.log; echo "SMOKE FAILED"; exit 1; }
 cat gpurun_out/smoke.log
-python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err || { tail -20 gpurun_out/bench.err; echo "BENCH FAILED"; exit 1; }
+timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err || { tail -20 gpurun_out/bench.err; echo "BENCH FAILED"; exit 1; }
 cat gpurun_out/bench.json
 if [ "${1:-}" = "ncu" ]; then
   python bench.py --kernel-only --steps 3 --warmup 3 > gpurun_out/plain.log 2>&1 &&
