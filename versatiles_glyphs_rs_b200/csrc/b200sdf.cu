@@ -66,13 +66,14 @@ PinnedRegistry &pinned_registry()
 #ifndef B200SDF_ZEROCOPY_CURVES
 #define B200SDF_ZEROCOPY_CURVES 1
 #endif
-bool zero_copy_enabled()
+// B200SDF_ZEROCOPY: 0 = stage everything, 1 (default) = inputs and bitmaps in place, 2 = bitmaps only
+int zero_copy_mode()
 {
-	static const bool on = [] {
+	static const int mode = [] {
 		const char *e = std::getenv("B200SDF_ZEROCOPY");
-		return !(e && e[0] == '0');
+		return e ? std::atoi(e) : 1;
 	}();
-	return on;
+	return mode;
 }
 
 struct Slot {
@@ -397,9 +398,9 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 	size_t need[5] = {(size_t)n_seg * sizeof(b200sdf_segment), (size_t)n_curves * sizeof(b200sdf_curve),
 	                  (size_t)n_ojobs * sizeof(b200sdf_outline_job), n_tiles * sizeof(b200sdf_tile_job), (size_t)out_bytes};
 	// zero-copy legs (see PinnedRegistry): job records read, bitmaps written, in place in pinned host memory
-	const bool zc = zero_copy_enabled();
+	const bool zc = zero_copy_mode() == 1;
 	const void *k_ojobs = zc && n_ojobs ? pinned_registry().device_ptr(ojobs, need[2]) : nullptr;
-	void *k_out = zc && out_bytes ? pinned_registry().device_ptr(out, need[4]) : nullptr;
+	void *k_out = zero_copy_mode() != 0 && out_bytes ? pinned_registry().device_ptr(out, need[4]) : nullptr;
 	// Curve lists are read ONCE per CTA with a bulk copy into shared memory when they fit there; only then
 	// is reading them in place (over PCIe) as good as a staged copy.  A glyph with more curve records than
 	// the kernel keeps in shared memory searches them in global memory: such a batch is staged.
