@@ -290,8 +290,31 @@ static int32_t sub_lookup(const cmap_sub *s, uint32_t cp)
 			return -1;
 		return (int32_t)rd16(s->data.p + 10 + 2 * (cp - first));
 	}
+	case 10: { /* trimmed array, 32-bit: glyphs[cp - first] as stored (ttf-parser 0.25.1 cmap/format10.rs) */
+		if (s->data.len < 20)
+			return -1;
+		uint32_t first = rd32(s->data.p + 12), cnt = rd32(s->data.p + 16);
+		if (cp < first || cp - first >= cnt || 20 + 2 * (size_t)(cp - first) + 2 > s->data.len)
+			return -1;
+		return (int32_t)rd16(s->data.p + 20 + 2 * (size_t)(cp - first));
+	}
+	case 13: { /* many-to-one ranges: every cp of a group maps to the group's glyph (cmap/format13.rs) */
+		if (s->data.len < 16)
+			return -1;
+		uint32_t n = rd32(s->data.p + 12);
+		if (16 + (size_t)n * 12 > s->data.len)
+			return -1;
+		for (uint32_t i = 0; i < n; i++) {
+			const uint8_t *g = s->data.p + 16 + (size_t)i * 12;
+			if (cp >= rd32(g) && cp <= rd32(g + 4)) {
+				uint32_t gid = rd32(g + 8);
+				return gid > 0xFFFF ? -1 : (int32_t)gid;
+			}
+		}
+		return -1;
+	}
 	default:
-		return -1; /* formats absent from the fixtures; contribute nothing */
+		return -1; /* formats 2, 8 and 14: no fixture and never a unicode lookup in practice; contribute nothing */
 	}
 }
 
@@ -347,7 +370,7 @@ size_t vgo_font_codepoints(const vgo_font *f, uint32_t *out, size_t cap)
 					if (sub_lookup(s, cp) >= 0)
 						uvec_push(&cps, cp);
 			}
-		} else if (s->format == 12 && s->data.len >= 16) {
+		} else if ((s->format == 12 || s->format == 13) && s->data.len >= 16) {
 			uint32_t n = rd32(s->data.p + 12);
 			if (16 + (size_t)n * 12 > s->data.len)
 				continue;
@@ -367,6 +390,11 @@ size_t vgo_font_codepoints(const vgo_font *f, uint32_t *out, size_t cap)
 			for (uint32_t cp = first; cp < first + cnt; cp++)
 				if (sub_lookup(s, cp) >= 0)
 					uvec_push(&cps, cp);
+		} else if (s->format == 10 && s->data.len >= 20) {
+			uint32_t first = rd32(s->data.p + 12), cnt = rd32(s->data.p + 16);
+			for (uint32_t i = 0; i < cnt && first + i >= first; i++)
+				if (sub_lookup(s, first + i) >= 0)
+					uvec_push(&cps, first + i);
 		}
 	}
 	size_t n = 0;

@@ -67,7 +67,7 @@ def make_outline(rng, k_strokes, hole_every=2):
     return contours
 
 
-def build_font(codepoints, strokes_for, seed=0xB200, family="Synth B200"):
+def build_font(codepoints, strokes_for, seed=0xB200, family="Synth B200", cmap_format=4, many_to_one=None):
     """codepoints: ascending BMP code points (no surrogates, no 0xFFFF); strokes_for(cp) -> K.
     Glyph id i+1 belongs to codepoints[i]; glyph 0 is an empty .notdef."""
     cps = [int(c) for c in codepoints]
@@ -103,6 +103,28 @@ def build_font(codepoints, strokes_for, seed=0xB200, family="Synth B200"):
     ranges = b"\0\0" * len(runs)
     sub = struct.pack(">HHHHHHH", 4, 16 + 4 * segx2, 0, segx2, 0, 0, 0) + ends + b"\0\0" + starts + deltas + ranges
     cmap_table = struct.pack(">HH", 0, 1) + struct.pack(">HHI", 3, 1, 12) + sub
+    real_runs = runs[:-1]
+    if cmap_format == 12:  # segmented coverage, (platform 0, encoding 4)
+        groups = b"".join(struct.pack(">III", s0, e0, g0) for s0, e0, g0 in real_runs)
+        sub = struct.pack(">HHIII", 12, 0, 16 + len(groups), 0, len(real_runs)) + groups
+        cmap_table = struct.pack(">HH", 0, 1) + struct.pack(">HHI", 0, 4, 12) + sub
+    elif cmap_format == 13:  # many-to-one: many_to_one = [(first cp, last cp, glyph id)], ascending
+        groups = b"".join(struct.pack(">III", s0, e0, g0) for s0, e0, g0 in many_to_one)
+        sub = struct.pack(">HHIII", 13, 0, 16 + len(groups), 0, len(many_to_one)) + groups
+        cmap_table = struct.pack(">HH", 0, 1) + struct.pack(">HHI", 3, 10, 12) + sub
+    elif cmap_format in (6, 10):  # trimmed arrays over [cps[0], cps[-1]]; holes map to glyph 0
+        first, count = cps[0], cps[-1] - cps[0] + 1
+        gids = np.zeros(count, dtype=">u2")
+        for i, c in enumerate(cps):
+            gids[c - first] = i + 1
+        if cmap_format == 6:
+            sub = struct.pack(">HHHHH", 6, 10 + 2 * count, 0, first, count) + gids.tobytes()
+            cmap_table = struct.pack(">HH", 0, 1) + struct.pack(">HHI", 3, 1, 12) + sub
+        else:
+            sub = struct.pack(">HHIIII", 10, 0, 20 + 2 * count, 0, first, count) + gids.tobytes()
+            cmap_table = struct.pack(">HH", 0, 1) + struct.pack(">HHI", 0, 4, 12) + sub
+    else:
+        assert cmap_format == 4
 
     head = struct.pack(">IIIIHHqqhhhhHHhhh", 0x00010000, 0x00010000, 0, 0x5F0F3CF5, 0, 1000, 0, 0, 0, -200, 1000, 800,
                        0, 8, 2, 1, 0)

@@ -338,3 +338,41 @@ for threads in (1, 2, 3, 8, 0, 5, 1):
     assert len(lines) == 14
     assert {ln[1] for ln in lines} == {"512"} and {ln[2] for ln in lines} == {str(6480 + 1686)}
     assert len({ln[3] for ln in lines}) == 1, lines  # every run produced exactly the same files
+
+
+@pytest.mark.parametrize("fmt", [4, 6, 10, 12, 13])
+def test_cmap_formats_known_answers_and_oracle(fmt):
+    """cmap subtable formats beyond the fixtures' 4 / 12: a synthetic font per format, checked
+    against the mapping it was built with (known answer) and host against oracle (code point set, glyph ids,
+    full dummy pipeline bytes).  Formats 6 / 10 return the stored id as is (0 included), 13 maps whole
+    ranges to one glyph, as ttf-parser 0.25.1 does."""
+    import synth_font
+
+    cps = [0x41, 0x42, 0x43, 0x50, 0x51, 0x60] + list(range(0x4E00, 0x4E10))
+    m2o = [(0x41, 0x5A, 2), (0x100, 0x10F, 5), (0x4E00, 0x4E7F, 7)]
+    data = synth_font.build_font(cps, lambda cp: 3, seed=7, family="Cmap Test", cmap_format=fmt, many_to_one=m2o)
+    f, o = V.FontFileEntry(data=data), O.Font(data)
+    if fmt == 13:
+        expect = {cp: g for s0, e0, g in m2o for cp in range(s0, e0 + 1)}
+    elif fmt in (6, 10):
+        expect = {cp: 0 for cp in range(cps[0], cps[-1] + 1)}  # holes: glyph 0 (.notdef), still "mapped"
+        expect.update({cp: i + 1 for i, cp in enumerate(cps)})
+    else:
+        expect = {cp: i + 1 for i, cp in enumerate(cps)}
+    for cp in list(expect) + [0x20, 0x7F, 0x5B, 0x4DFF, 0x4E80, 0x1F600]:
+        want = expect.get(cp)
+        assert f.glyph_index(cp) == want, (fmt, hex(cp))
+        assert o.glyph_index(cp) == want, (fmt, hex(cp))
+    assert f.codepoints().tolist() == sorted(expect) == list(o.codepoints())
+    # the whole host path on this font equals the oracle's
+    m = V.FontManager(parallel=False)
+    m.add_font_bytes_with_name("Cmap Test", data)
+    path = f"/tmp/_cmap_{fmt}.ttf"
+    open(path, "wb").write(data)
+    try:
+        oset = O.FontSet("Cmap Test", [path])
+        assert m.block_population("cmap_test").tolist() == oset.block_population()
+        for b in (0, 1, 0x4E):
+            assert m.render_block("cmap_test", b, V.Renderer.new_dummy()) == oset.render_block(b, O.MODE_DUMMY), (fmt, b)
+    finally:
+        os.unlink(path)

@@ -173,6 +173,34 @@ std::optional<uint16_t> Face::lookup(const CmapSubtable &s, uint32_t cp) const
 		}
 		return std::nullopt;
 	}
+	case 10: { // trimmed array with 32-bit code points: the stored glyph id as is (ttf-parser cmap/format10.rs)
+		if (len < 20)
+			return std::nullopt;
+		const uint32_t first = u32(base + 12), count = u32(base + 16);
+		if (cp < first || cp - first >= count)
+			return std::nullopt;
+		const size_t pos = base + 20 + 2 * (size_t)(cp - first);
+		if (pos + 2 > base + len)
+			return std::nullopt;
+		return u16(pos);
+	}
+	case 13: { // many-to-one ranges, scanned in order (ttf-parser cmap/format13.rs)
+		if (len < 16)
+			return std::nullopt;
+		const uint32_t n = u32(base + 12);
+		if (16 + (size_t)n * 12 > len)
+			return std::nullopt;
+		for (uint32_t i = 0; i < n; ++i) {
+			const size_t g = base + 16 + (size_t)i * 12;
+			if (cp >= u32(g) && cp <= u32(g + 4)) {
+				const uint32_t gid = u32(g + 8);
+				if (gid > 0xFFFF)
+					return std::nullopt;
+				return (uint16_t)gid;
+			}
+		}
+		return std::nullopt;
+	}
 	default:
 		return std::nullopt;
 	}
@@ -210,7 +238,8 @@ template <typename F> void Face::enumerate(const CmapSubtable &s, F &&f) const
 			f(cp);
 		break;
 	}
-	case 12: {
+	case 12:
+	case 13: {
 		if (len < 16)
 			return;
 		const uint32_t n = u32(base + 12);
@@ -222,6 +251,14 @@ template <typename F> void Face::enumerate(const CmapSubtable &s, F &&f) const
 			for (uint64_t cp = sc; cp <= ec; ++cp)
 				f((uint32_t)cp);
 		}
+		break;
+	}
+	case 10: {
+		if (len < 20)
+			return;
+		const uint64_t first = u32(base + 12), count = u32(base + 16);
+		for (uint64_t i = 0; i < count && first + i <= 0xFFFFFFFFull; ++i)
+			f((uint32_t)(first + i));
 		break;
 	}
 	default:
