@@ -172,7 +172,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = glyphs / dt
     sample = f"every {stride}th GlyphBlock of the workload ({st['glyphs']} glyphs, {st['pairs']} pairs per step)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "glyphs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "testdata fonts" if args.workload in ("noto", "fira") else "synthetic",
@@ -180,11 +180,33 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "glyphs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "glyphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries print to stdout (NCCL: "NCCL version ..."): keep fd 1 for the ONE JSON line, send the rest to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(result):
+    sys.stdout.flush()
+    line = (json.dumps(result) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
     args = parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -410,7 +432,7 @@ def main():
     result["clocks"] = ClockSampler.summary(sampler.window(t_wall0, time.perf_counter()))
     sampler.stop()
     if rank == 0:
-        print(json.dumps(result))
+        emit(result)
     if dist is not None:
         dist.destroy_process_group()
 
