@@ -187,11 +187,29 @@ inline uint64_t glyph_cost(uint32_t seg_cnt, uint32_t width, uint32_t height)
 	return nx * ny * (uint64_t)(seg_cnt + 8);
 }
 
+// A batch too small to fill the GPU (a pipeline's 64..256-glyph batches) is latency-bound: its kernel lasts as
+// long as its heaviest CTA running alone on an SM, so heavy glyphs are cut finer there (down to kMinItemsSmall
+// items per CTA) even though every extra rectangle repeats the staging.
+constexpr uint32_t kMinItemsSmall = 8;
+constexpr uint64_t kSmallBatchCost = (uint64_t)kSMs * kJobsPerSM * kMinJobCost; // ~19 M units, ~1000 median glyphs
+
 inline uint32_t items_cap(uint64_t total_cost, uint32_t seg_cnt)
 {
-	const uint64_t cap = std::max<uint64_t>(total_cost / (kSMs * kJobsPerSM), kMinJobCost);
+	static const uint32_t min_small = [] { // B200SDF_MIN_ITEMS_SMALL: tuning knob
+		const char *e = std::getenv("B200SDF_MIN_ITEMS_SMALL");
+		const int v = e ? std::atoi(e) : 0;
+		return (uint32_t)(v >= 1 && v <= 64 ? v : (int)kMinItemsSmall);
+	}();
+	static const uint64_t min_cost_small = [] { // B200SDF_MIN_COST_SMALL: tuning knob
+		const char *e = std::getenv("B200SDF_MIN_COST_SMALL");
+		const long v = e ? std::atol(e) : 0;
+		return (uint64_t)(v >= 256 ? v : (long)kMinJobCost);
+	}();
+	const bool small = total_cost < kSmallBatchCost;
+	const uint64_t cap = std::max<uint64_t>(total_cost / (kSMs * kJobsPerSM), small ? min_cost_small : kMinJobCost);
 	const uint64_t items = cap / (uint64_t)(seg_cnt + 8);
-	return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(items, kMinItems), (uint64_t)b200sdf::kMaxItems);
+	const uint64_t floor_items = small ? min_small : kMinItems;
+	return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(items, floor_items), (uint64_t)b200sdf::kMaxItems);
 }
 
 // Split one glyph into rectangles of tiles with at most max_items items each.

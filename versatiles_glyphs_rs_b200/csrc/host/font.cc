@@ -12,6 +12,8 @@
 #include <condition_variable>
 #include <fstream>
 #include <functional>
+#include <pthread.h>
+#include <sched.h>
 #include <sys/stat.h>
 #include <thread>
 
@@ -421,6 +423,7 @@ class WorkerPool {
 			while ((int)threads_.size() < n) {
 				const int id = (int)threads_.size();
 				threads_.emplace_back([this, id] { loop(id); });
+				pin(threads_.back(), id);
 			}
 			fn_ = &fn;
 			want_ = n;
@@ -436,6 +439,31 @@ class WorkerPool {
 	}
 
   private:
+	// VGB_PIN_WORKERS=1: worker i stays on the (i+1)-th CPU this process may use (the first is left to the
+	// calling thread, the pipeline's submitter) — fewer migrations, steadier step times.  Off by default.
+	static void pin(std::thread &t, int id)
+	{
+		static const bool on = [] {
+			const char *e = std::getenv("VGB_PIN_WORKERS");
+			return e && e[0] == '1';
+		}();
+		if (!on)
+			return;
+		cpu_set_t allowed;
+		CPU_ZERO(&allowed);
+		if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0)
+			return;
+		std::vector<int> cpus;
+		for (int c = 0; c < CPU_SETSIZE; ++c)
+			if (CPU_ISSET(c, &allowed))
+				cpus.push_back(c);
+		if ((int)cpus.size() < 2)
+			return;
+		cpu_set_t one;
+		CPU_ZERO(&one);
+		CPU_SET(cpus[(size_t)(id + 1) % cpus.size()], &one);
+		pthread_setaffinity_np(t.native_handle(), sizeof(one), &one);
+	}
 	void loop(int id)
 	{
 		uint64_t seen = 0;
