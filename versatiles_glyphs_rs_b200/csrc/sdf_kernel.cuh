@@ -259,10 +259,9 @@ __device__ __forceinline__ void curve_point(const b200sdf_curve &c, uint32_t j, 
 
 // Segment g of a CURVES glyph as origin-relative f32 pixel coordinates — the same arithmetic, in
 // the same order, as the host path: p*scale, +dx (renderer.rs:122-131), -origin, narrow to f32.
-__device__ __forceinline__ float4 flatten_segment(const b200sdf_curve *__restrict__ curves, uint32_t n_curves, uint32_t g,
-                                                  double scale, double dx, double ox, double oy)
+// binary search: last record with seg_off <= g
+__device__ __forceinline__ uint32_t find_curve(const b200sdf_curve *__restrict__ curves, uint32_t n_curves, uint32_t g)
 {
-	// binary search: last record with seg_off <= g
 	uint32_t lo = 0, hi = n_curves;
 	while (hi - lo > 1) {
 		const uint32_t mid = (lo + hi) >> 1;
@@ -271,7 +270,11 @@ __device__ __forceinline__ float4 flatten_segment(const b200sdf_curve *__restric
 		else
 			hi = mid;
 	}
-	const b200sdf_curve c = curves[lo];
+	return lo;
+}
+
+__device__ __forceinline__ float4 flatten_segment_of(const b200sdf_curve c, uint32_t g, double scale, double dx, double ox, double oy)
+{
 	const uint32_t j = g - c.seg_off;
 	double x0, y0, x1, y1;
 	curve_point(c, j, x0, y0);
@@ -282,6 +285,31 @@ __device__ __forceinline__ float4 flatten_segment(const b200sdf_curve *__restric
 	s.z = (float)__dsub_rn(__dadd_rn(__dmul_rn(x1, scale), dx), ox);
 	s.w = (float)__dsub_rn(__dadd_rn(__dmul_rn(y1, scale), 0.0), oy);
 	return s;
+}
+
+__device__ __forceinline__ float4 flatten_segment(const b200sdf_curve *__restrict__ curves, uint32_t n_curves, uint32_t g,
+                                                  double scale, double dx, double ox, double oy)
+{
+	return flatten_segment_of(curves[find_curve(curves, n_curves, g)], g, scale, dx, ox, oy);
+}
+
+// The curve records of 32 CONSECUTIVE segments g0 + lane, without a search per lane: every record holds at least
+// one segment, so they lie in [c_lo, c_lo + 32] where c_lo is the record of g0.  Lane k looks at record c_lo + 1 + k;
+// if it starts at g0 + d (1 <= d <= 31) it sets bit d; the OR of all lanes' bits, counted up to a lane's own
+// position, is how many records that lane is past c_lo.  Returns this lane's record index; c_lo_next receives the
+// record of segment g0 + 32 (the next pass continues from there).
+__device__ __forceinline__ uint32_t curves_of_32(const b200sdf_curve *__restrict__ curves, uint32_t n_curves, uint32_t c_lo,
+                                                 uint32_t g0, int lane, uint32_t &c_lo_next)
+{
+	const uint32_t k = c_lo + 1u + (uint32_t)lane;
+	const uint32_t start = k < n_curves ? curves[k].seg_off : 0xffffffffu;
+	const uint32_t d = start - g0; // >= 1
+	const uint32_t bit = d <= 31u ? (1u << d) : 0u;
+	const uint32_t mask = __reduce_or_sync(0xffffffffu, bit);
+	// records starting exactly at g0 + 32 belong to the next pass
+	const uint32_t starts32 = __ballot_sync(0xffffffffu, d <= 32u); // records starting at or before g0 + 32
+	c_lo_next = c_lo + (uint32_t)__popc(starts32);
+	return c_lo + (uint32_t)__popc(mask & (0xffffffffu >> (31 - lane)));
 }
 
 static_assert(kThreads == 128, "B200SDF_BOUNDS");
@@ -417,6 +445,10 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 				bulk_g2s(raw[m], gsegs + s_begin + m * kMini, n * 16u, &sm.bar[warp][m]);
 			}
 		}
+#if B200SDF_ALGO == 2
+		// record of the warp's first segment; later passes advance it without searching (curves_of_32)
+		uint32_t c_lo = from_curves ? find_curve(gcurves, n_curves, s_begin) : 0u;
+#endif
 		for (uint32_t m = 0; m < n_mini; ++m) {
 			const uint32_t base = s_begin + m * kMini;
 			const int n = (int)min((uint32_t)kMini, s_end - base);
@@ -431,8 +463,15 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 				bool is_long = false;
 				float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 				float dx = 0.f, dy = 0.f, inv = 0.f;
+				uint32_t my_curve = 0;
+				if (from_curves) {
+					uint32_t next_lo;
+					my_curve = curves_of_32(gcurves, n_curves, c_lo, base + (uint32_t)i0, lane, next_lo);
+					c_lo = next_lo;
+				}
 				if (i < n) {
-					s = from_curves ? flatten_segment(gcurves, n_curves, base + (uint32_t)i, g_scale, g_dx, g_ox, g_oy) : raw[b][i];
+					s = from_curves ? flatten_segment_of(gcurves[min(my_curve, n_curves - 1u)], base + (uint32_t)i, g_scale, g_dx, g_ox, g_oy)
+					                : raw[b][i];
 					dx = s.z - s.x, dy = s.w - s.y;
 					const float l2 = dx * dx + dy * dy;
 					inv = l2 > 0.0f ? __frcp_rn(l2) : 0.0f;
