@@ -52,6 +52,9 @@
 //                                 + long segments (> 0.5 px) through the clamped projection.
 #define B200SDF_ALGO 2
 #endif
+#ifndef B200SDF_SHARED_STAGE
+#define B200SDF_SHARED_STAGE 1 // curve glyphs: stage each segment once per CTA, all warps consume all staged lists
+#endif
 #ifndef B200SDF_VUNROLL
 #define B200SDF_VUNROLL 2 // vertex-loop unroll (pairs of vertices per trip)
 #endif
@@ -149,6 +152,7 @@ struct SharedStorage {
 	uint8_t obuf[kMaxPix + 32];
 	uint64_t bar[kWarps][2];          // per-warp mbarriers of the raw double buffer
 	uint64_t curve_bar;
+	int st_nv[kWarps], st_nl[kWarps]; // shared staging: vertices / long records each warp staged this round
 };
 
 struct Rect {
@@ -434,135 +438,13 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 		gcurves = sm.src.curves;
 	}
 
-	if (warp_active && s_end > s_begin) {
-		WarpStage &ws = sm.warp[warp];
-		float4(*raw)[kMini] = sm.src.raw[warp];
-		const uint32_t n_mini = (s_end - s_begin + kMini - 1) / kMini;
-		if (!from_curves && lane == 0) {
-			for (uint32_t m = 0; m < 2 && m < n_mini; ++m) {
-				const uint32_t n = min((uint32_t)kMini, s_end - (s_begin + m * kMini));
-				mbar_expect_tx(&sm.bar[warp][m], n * 16u);
-				bulk_g2s(raw[m], gsegs + s_begin + m * kMini, n * 16u, &sm.bar[warp][m]);
-			}
-		}
-#if B200SDF_ALGO == 2
-		// record of the warp's first segment; later passes advance it without searching (curves_of_32)
-		uint32_t c_lo = from_curves ? find_curve(gcurves, n_curves, s_begin) : 0u;
-#endif
-		for (uint32_t m = 0; m < n_mini; ++m) {
-			const uint32_t base = s_begin + m * kMini;
-			const int n = (int)min((uint32_t)kMini, s_end - base);
-			const int b = (int)(m & 1);
-			// ---- stage: every lane turns up to kMini/32 segments into records ----
-#if B200SDF_ALGO == 2
-			if (!from_curves)
-				mbar_wait(&sm.bar[warp][b], (m >> 1) & 1);
-			int n_long = 0;
-			for (int i0 = 0; i0 < n; i0 += 32) { // uniform trip count: the long list is compacted by ballot
-				const int i = i0 + lane;
-				bool is_long = false;
-				float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-				float dx = 0.f, dy = 0.f, inv = 0.f;
-				uint32_t my_curve = 0;
-				if (from_curves) {
-					uint32_t next_lo;
-					my_curve = curves_of_32(gcurves, n_curves, c_lo, base + (uint32_t)i0, lane, next_lo);
-					c_lo = next_lo;
-				}
-				if (i < n) {
-					s = from_curves ? flatten_segment_of(gcurves[min(my_curve, n_curves - 1u)], base + (uint32_t)i, g_scale, g_dx, g_ox, g_oy)
-					                : raw[b][i];
-					dx = s.z - s.x, dy = s.w - s.y;
-					const float l2 = dx * dx + dy * dy;
-					inv = l2 > 0.0f ? __frcp_rn(l2) : 0.0f;
-					is_long = l2 > kLongL2;
-					if (from_curves) {
-						ws.vtx[i] = make_float2(-s.x, -s.y); // rings are closed: every end is another segment's start
-					} else {
-						ws.vtx[2 * i] = make_float2(-s.x, -s.y);
-						ws.vtx[2 * i + 1] = make_float2(-s.z, -s.w);
-					}
-					if (scatter) {
-						scatter_crossings(s, dx, dy, sm.delta, R);
-						if (!is_long && l2 > 0.0f)
-							band_scatter(s, dx, dy, l2, inv, sm.d2, R);
-					}
-				}
-				const unsigned mask = __ballot_sync(0xffffffffu, is_long);
-				if (is_long) {
-					const int k = n_long + __popc(mask & ((1u << lane) - 1u));
-					ws.recA[k] = SegA{-s.x, -s.y, -dx, -dy};
-					ws.recN[k] = SegN{dx * inv, dy * inv};
-				}
-				n_long += __popc(mask);
-			}
-			int nv = from_curves ? n : 2 * n;
-			__syncwarp();
-			if ((nv & 1) && lane == 0)
-				ws.vtx[nv] = ws.vtx[nv - 1]; // pad to a whole pair
-			nv = (nv + 1) & ~1;
-#else
-			const int n_long = n;
-			if (!from_curves) {
-				mbar_wait(&sm.bar[warp][b], (m >> 1) & 1);
-				for (int i = lane; i < n; i += 32)
-					stage_segment(raw[b][i], ws.recA[i], ws.recN[i], sm.delta, R, scatter);
-			} else {
-				for (int i = lane; i < n; i += 32) {
-					const float4 s = flatten_segment(gcurves, n_curves, base + (uint32_t)i, g_scale, g_dx, g_ox, g_oy);
-					stage_segment(s, ws.recA[i], ws.recN[i], sm.delta, R, scatter);
-				}
-			}
-#endif
-			__syncwarp();
-			if (!from_curves && lane == 0 && m + 2 < n_mini) {
-				const uint32_t n2 = min((uint32_t)kMini, s_end - (base + 2 * kMini));
-				fence_proxy_async();
-				mbar_expect_tx(&sm.bar[warp][b], n2 * 16u);
-				bulk_g2s(raw[b], gsegs + base + 2 * kMini, n2 * 16u, &sm.bar[warp][b]);
-			}
-#if B200SDF_ALGO == 2
-			// ---- vertex loop: my pixels x the staged vertices of my lane slice, two vertices per step ----
-			{
-				const float4 *__restrict__ V4 = reinterpret_cast<const float4 *>(ws.vtx);
-				const int npair = nv >> 1;
-#pragma unroll kVUnroll
-				for (int i = lslice; i < npair; i += lslices) {
-					const float4 v = V4[i];
-					// two vertices a = (v.x, v.y), b = (v.z, v.w): the per-column / per-row terms with packed
-					// FP32 (half the issue slots), the 16 + 16 squared distances with scalar FFMA
-					float2 paxa[kTileW / 2], paxb[kTileW / 2], sya[kTileH / 2], syb[kTileH / 2];
-#pragma unroll
-					for (int j = 0; j < kTileW / 2; ++j) {
-						paxa[j] = __fadd2_rn(pxp[j], make_float2(v.x, v.x));
-						paxb[j] = __fadd2_rn(pxp[j], make_float2(v.z, v.z));
-					}
-#pragma unroll
-					for (int r = 0; r < kTileH / 2; ++r) {
-						const float2 pa = __fadd2_rn(pyp[r], make_float2(v.y, v.y));
-						const float2 pb = __fadd2_rn(pyp[r], make_float2(v.w, v.w));
-						sya[r] = __fmul2_rn(pa, pa);
-						syb[r] = __fmul2_rn(pb, pb);
-					}
-#pragma unroll
-					for (int r = 0; r < kTileH; ++r) {
-						const float ya = (r & 1) ? sya[r >> 1].y : sya[r >> 1].x;
-						const float yb = (r & 1) ? syb[r >> 1].y : syb[r >> 1].x;
-#pragma unroll
-						for (int j = 0; j < kTileW; ++j) {
-							const float xa = (j & 1) ? paxa[j >> 1].y : paxa[j >> 1].x;
-							const float xb = (j & 1) ? paxb[j >> 1].y : paxb[j >> 1].x;
-							mn[r][j] = fmin3(mn[r][j], fmaf(xa, xa, ya), fmaf(xb, xb, yb));
-						}
-					}
-				}
-			}
-#endif
-			// ---- pair loop: my pixels x the staged records of my lane slice ----
-			const SegA *__restrict__ A = ws.recA;
-			const SegN *__restrict__ Nn = ws.recN;
+	// ---- the two halves of a staging pass, shared by both loop structures below ----
+	// long-segment loop: my pixels x records [first, count) step stride of one staged list
+	auto long_loop = [&](const WarpStage &ws, int count, int first, int stride) {
+		const SegA *__restrict__ A = ws.recA;
+		const SegN *__restrict__ Nn = ws.recN;
 #pragma unroll kUnroll
-			for (int i = lslice; i < n_long; i += lslices) {
+		for (int i = first; i < count; i += stride) {
 				const float4 a = *reinterpret_cast<const float4 *>(&A[i]);
 				const SegN q = Nn[i];
 #if B200SDF_PACK >= 1
@@ -613,7 +495,178 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 					}
 				}
 #endif
+		}
+	};
+#if B200SDF_ALGO == 2
+	// stage: one warp turns segments [base, base + n) into the vertex list, the long list, crossings and bands
+	auto stage = [&](WarpStage &ws, const float4 *rawbuf, uint32_t base, int n, uint32_t &c_lo, bool do_scatter,
+	                 int &nv_out) -> int {
+			int n_long = 0;
+			for (int i0 = 0; i0 < n; i0 += 32) { // uniform trip count: the long list is compacted by ballot
+				const int i = i0 + lane;
+				bool is_long = false;
+				float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+				float dx = 0.f, dy = 0.f, inv = 0.f;
+				uint32_t my_curve = 0;
+				if (from_curves) {
+					uint32_t next_lo;
+					my_curve = curves_of_32(gcurves, n_curves, c_lo, base + (uint32_t)i0, lane, next_lo);
+					c_lo = next_lo;
+				}
+				if (i < n) {
+					s = from_curves ? flatten_segment_of(gcurves[min(my_curve, n_curves - 1u)], base + (uint32_t)i, g_scale, g_dx, g_ox, g_oy)
+					                : rawbuf[i];
+					dx = s.z - s.x, dy = s.w - s.y;
+					const float l2 = dx * dx + dy * dy;
+					inv = l2 > 0.0f ? __frcp_rn(l2) : 0.0f;
+					is_long = l2 > kLongL2;
+					if (from_curves) {
+						ws.vtx[i] = make_float2(-s.x, -s.y); // rings are closed: every end is another segment's start
+					} else {
+						ws.vtx[2 * i] = make_float2(-s.x, -s.y);
+						ws.vtx[2 * i + 1] = make_float2(-s.z, -s.w);
+					}
+					if (do_scatter) {
+						scatter_crossings(s, dx, dy, sm.delta, R);
+						if (!is_long && l2 > 0.0f)
+							band_scatter(s, dx, dy, l2, inv, sm.d2, R);
+					}
+				}
+				const unsigned mask = __ballot_sync(0xffffffffu, is_long);
+				if (is_long) {
+					const int k = n_long + __popc(mask & ((1u << lane) - 1u));
+					ws.recA[k] = SegA{-s.x, -s.y, -dx, -dy};
+					ws.recN[k] = SegN{dx * inv, dy * inv};
+				}
+				n_long += __popc(mask);
 			}
+		const int nv = from_curves ? n : 2 * n;
+		__syncwarp();
+		if ((nv & 1) && lane == 0)
+			ws.vtx[nv] = ws.vtx[nv - 1]; // pad to a whole pair
+		nv_out = (nv + 1) & ~1;
+		return n_long;
+	};
+	// vertex loop: my pixels x vertex pairs [first, nv/2) step stride of one staged list
+	auto vertex_loop = [&](const WarpStage &ws, int nv, int first, int stride) {
+				const float4 *__restrict__ V4 = reinterpret_cast<const float4 *>(ws.vtx);
+				const int npair = nv >> 1;
+#pragma unroll kVUnroll
+				for (int i = first; i < npair; i += stride) {
+					const float4 v = V4[i];
+					// two vertices a = (v.x, v.y), b = (v.z, v.w): the per-column / per-row terms with packed
+					// FP32 (half the issue slots), the 16 + 16 squared distances with scalar FFMA
+					float2 paxa[kTileW / 2], paxb[kTileW / 2], sya[kTileH / 2], syb[kTileH / 2];
+#pragma unroll
+					for (int j = 0; j < kTileW / 2; ++j) {
+						paxa[j] = __fadd2_rn(pxp[j], make_float2(v.x, v.x));
+						paxb[j] = __fadd2_rn(pxp[j], make_float2(v.z, v.z));
+					}
+#pragma unroll
+					for (int r = 0; r < kTileH / 2; ++r) {
+						const float2 pa = __fadd2_rn(pyp[r], make_float2(v.y, v.y));
+						const float2 pb = __fadd2_rn(pyp[r], make_float2(v.w, v.w));
+						sya[r] = __fmul2_rn(pa, pa);
+						syb[r] = __fmul2_rn(pb, pb);
+					}
+#pragma unroll
+					for (int r = 0; r < kTileH; ++r) {
+						const float ya = (r & 1) ? sya[r >> 1].y : sya[r >> 1].x;
+						const float yb = (r & 1) ? syb[r >> 1].y : syb[r >> 1].x;
+#pragma unroll
+						for (int j = 0; j < kTileW; ++j) {
+							const float xa = (j & 1) ? paxa[j >> 1].y : paxa[j >> 1].x;
+							const float xb = (j & 1) ? paxb[j >> 1].y : paxb[j >> 1].x;
+							mn[r][j] = fmin3(mn[r][j], fmaf(xa, xa, ya), fmaf(xb, xb, yb));
+						}
+					}
+				}
+	};
+#endif
+
+#if B200SDF_ALGO == 2 && B200SDF_SHARED_STAGE
+	// Curve glyphs: the CTA stages 4 x kMini segments per round — warp w the w-th quarter, every segment exactly
+	// once — and then every warp consumes its share of ALL four staged lists for its own tiles.  (Before, the
+	// warps of different item groups each staged the segments they needed: a glyph of more than 32 tiles, i.e.
+	// most of the work, was staged twice, and in the 3 + 1 split one warp staged everything alone.)
+	if (from_curves) {
+		const int cstride = wslices * lslices;                 // consumers of my item group
+		const int cs = wslice * lslices + lslice;              // my position among them
+		const uint32_t per_round = 4u * (uint32_t)kMini;
+		for (uint32_t r0 = 0; r0 < S; r0 += per_round) {
+			const uint32_t base = r0 + (uint32_t)warp * (uint32_t)kMini;
+			const int n = base < S ? (int)min((uint32_t)kMini, S - base) : 0;
+			int nv = 0, nl = 0;
+			if (n > 0) {
+				uint32_t c_lo = find_curve(gcurves, n_curves, base);
+				nl = stage(sm.warp[warp], nullptr, base, n, c_lo, true, nv);
+			}
+			if (lane == 0) {
+				sm.st_nv[warp] = nv;
+				sm.st_nl[warp] = nl;
+			}
+			__syncthreads();
+			if (warp_active) {
+#pragma unroll 1
+				for (int q = 0; q < kWarps; ++q) {
+					const int first = (cs + q) % cstride; // rotate: list lengths are not multiples of the stride
+					vertex_loop(sm.warp[q], sm.st_nv[q], first, cstride);
+					long_loop(sm.warp[q], sm.st_nl[q], first, cstride);
+				}
+			}
+			__syncthreads(); // the lists are overwritten by the next round
+		}
+	} else
+#endif
+	if (warp_active && s_end > s_begin) {
+		WarpStage &ws = sm.warp[warp];
+		float4(*raw)[kMini] = sm.src.raw[warp];
+		const uint32_t n_mini = (s_end - s_begin + kMini - 1) / kMini;
+		if (!from_curves && lane == 0) {
+			for (uint32_t m = 0; m < 2 && m < n_mini; ++m) {
+				const uint32_t n = min((uint32_t)kMini, s_end - (s_begin + m * kMini));
+				mbar_expect_tx(&sm.bar[warp][m], n * 16u);
+				bulk_g2s(raw[m], gsegs + s_begin + m * kMini, n * 16u, &sm.bar[warp][m]);
+			}
+		}
+#if B200SDF_ALGO == 2
+		// record of the warp's first segment; later passes advance it without searching (curves_of_32)
+		uint32_t c_lo = from_curves ? find_curve(gcurves, n_curves, s_begin) : 0u;
+#endif
+		for (uint32_t m = 0; m < n_mini; ++m) {
+			const uint32_t base = s_begin + m * kMini;
+			const int n = (int)min((uint32_t)kMini, s_end - base);
+			const int b = (int)(m & 1);
+			// ---- stage: every lane turns up to kMini/32 segments into records ----
+#if B200SDF_ALGO == 2
+			if (!from_curves)
+				mbar_wait(&sm.bar[warp][b], (m >> 1) & 1);
+			int nv = 0;
+			const int n_long = stage(ws, raw[b], base, n, c_lo, scatter, nv);
+#else
+			const int n_long = n;
+			if (!from_curves) {
+				mbar_wait(&sm.bar[warp][b], (m >> 1) & 1);
+				for (int i = lane; i < n; i += 32)
+					stage_segment(raw[b][i], ws.recA[i], ws.recN[i], sm.delta, R, scatter);
+			} else {
+				for (int i = lane; i < n; i += 32) {
+					const float4 s = flatten_segment(gcurves, n_curves, base + (uint32_t)i, g_scale, g_dx, g_ox, g_oy);
+					stage_segment(s, ws.recA[i], ws.recN[i], sm.delta, R, scatter);
+				}
+			}
+#endif
+			__syncwarp();
+			if (!from_curves && lane == 0 && m + 2 < n_mini) {
+				const uint32_t n2 = min((uint32_t)kMini, s_end - (base + 2 * kMini));
+				fence_proxy_async();
+				mbar_expect_tx(&sm.bar[warp][b], n2 * 16u);
+				bulk_g2s(raw[b], gsegs + base + 2 * kMini, n2 * 16u, &sm.bar[warp][b]);
+			}
+#if B200SDF_ALGO == 2
+			vertex_loop(ws, nv, lslice, lslices);
+#endif
+			long_loop(ws, n_long, lslice, lslices);
 			__syncwarp(); // records are overwritten by the next staging pass
 		}
 	}
