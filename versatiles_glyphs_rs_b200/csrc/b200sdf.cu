@@ -191,6 +191,10 @@ inline uint64_t glyph_cost(uint32_t seg_cnt, uint32_t width, uint32_t height)
 // long as its heaviest CTA running alone on an SM, so heavy glyphs are cut finer there (down to kMinItemsSmall
 // items per CTA) even though every extra rectangle repeats the staging.
 constexpr uint32_t kMinItemsSmall = 8;
+// ... but not finer than this per CTA: a pipeline keeps many small batches in flight, so what it needs from each
+// is throughput more than latency, and every extra rectangle repeats the staging of all the glyph's segments
+// (measured, C2 in 128-glyph kernels on 32 streams: 0.99 ms with 16384, 0.62 ms with 65536; one launch: 0.46 ms)
+constexpr uint64_t kMinJobCostSmall = 65536;
 constexpr uint64_t kSmallBatchCost = (uint64_t)kSMs * kJobsPerSM * kMinJobCost; // ~19 M units, ~1000 median glyphs
 
 inline uint32_t items_cap(uint64_t total_cost, uint32_t seg_cnt)
@@ -203,7 +207,7 @@ inline uint32_t items_cap(uint64_t total_cost, uint32_t seg_cnt)
 	static const uint64_t min_cost_small = [] { // B200SDF_MIN_COST_SMALL: tuning knob
 		const char *e = std::getenv("B200SDF_MIN_COST_SMALL");
 		const long v = e ? std::atol(e) : 0;
-		return (uint64_t)(v >= 256 ? v : (long)kMinJobCost);
+		return (uint64_t)(v >= 256 ? v : (long)kMinJobCostSmall);
 	}();
 	const bool small = total_cost < kSmallBatchCost;
 	const uint64_t cap = std::max<uint64_t>(total_cost / (kSMs * kJobsPerSM), small ? min_cost_small : kMinJobCost);
