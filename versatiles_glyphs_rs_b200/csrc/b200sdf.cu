@@ -84,6 +84,10 @@ struct Slot {
 	size_t h_tiles_cap = 0;
 	bool busy = false;
 	uint64_t generation = 0;
+	// B200SDF_GPU_TRACE=1: device-side timeline of every batch (kernel start / stop relative to the context's epoch)
+	cudaEvent_t t0 = nullptr, t1 = nullptr;
+	uint64_t host_submit_ns = 0;
+	uint32_t traced_tiles = 0;
 };
 
 } // namespace
@@ -96,6 +100,8 @@ struct b200sdf_ctx {
 	std::string err;
 	uint64_t launches = 0;
 	float *d_peak = nullptr;
+	cudaEvent_t epoch = nullptr; // B200SDF_GPU_TRACE
+	uint64_t epoch_host_ns = 0;
 	size_t hwm[5] = {0, 0, 0, 0, 0}; // largest per-batch buffer sizes seen (segments, curves, jobs, tiles, bitmaps)
 };
 
@@ -382,6 +388,17 @@ size_t acquire_slot(b200sdf_ctx *ctx)
 	return si;
 }
 
+void report_gpu_trace(b200sdf_ctx *ctx, Slot &s)
+{
+	if (!s.t1 || !s.traced_tiles || !ctx->epoch)
+		return;
+	float a = 0.f, b = 0.f;
+	if (cudaEventElapsedTime(&a, ctx->epoch, s.t0) == cudaSuccess && cudaEventElapsedTime(&b, ctx->epoch, s.t1) == cudaSuccess)
+		std::fprintf(stderr, "[b200sdf gpu] submit %.1f us  kernel %.1f .. %.1f us (%.1f us, %u CTAs)\n",
+		             (double)(s.host_submit_ns - ctx->epoch_host_ns) * 1e-3, a * 1e3, b * 1e3, (b - a) * 1e3, s.traced_tiles);
+	s.traced_tiles = 0;
+}
+
 int release_slot(b200sdf_ctx *ctx, Slot &s, int code)
 {
 	std::lock_guard<std::mutex> g(ctx->mu);
@@ -501,6 +518,24 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 		for (size_t i = 0; i < n_tiles; ++i)
 			if (ht[i].tx0 == 0 && ht[i].ty0 == 0)
 				covered += (uint64_t)ht[i].width * ht[i].height;
+		static const bool gpu_trace = std::getenv("B200SDF_GPU_TRACE") != nullptr;
+		if (gpu_trace) {
+			if (!s.t0) {
+				cudaEventCreate(&s.t0);
+				cudaEventCreate(&s.t1);
+			}
+			{
+				std::lock_guard<std::mutex> g(ctx->mu);
+				if (!ctx->epoch) {
+					cudaEventCreate(&ctx->epoch);
+					cudaEventRecord(ctx->epoch, s.stream);
+					ctx->epoch_host_ns = now();
+				}
+			}
+			s.host_submit_ns = now();
+			s.traced_tiles = (uint32_t)n_tiles;
+			cudaEventRecord(s.t0, s.stream);
+		}
 		if (k_out) {
 			if (covered < out_bytes)
 				std::memset(out, 0, (size_t)out_bytes); // the caller's buffer is ours until wait()
@@ -517,6 +552,8 @@ int submit_planned(b200sdf_ctx *ctx, const std::vector<Planned> &plan, const b20
 	}
 	if (trace)
 		tt[4] = now();
+	if (s.t1 && s.traced_tiles)
+		cudaEventRecord(s.t1, s.stream);
 	SUB_TRY(cudaEventRecord(s.done, s.stream));
 #undef SUB_TRY
 	if (trace) {
@@ -757,6 +794,7 @@ int b200sdf_wait(b200sdf_ctx *ctx, uint64_t ticket)
 	}
 	Slot &s = ctx->slots[si];
 	const cudaError_t e = cudaEventSynchronize(s.done);
+	report_gpu_trace(ctx, s);
 	release_slot(ctx, s, 0);
 	if (e != cudaSuccess)
 		return fail_cuda(ctx, e, "cudaEventSynchronize");
@@ -779,6 +817,7 @@ int b200sdf_poll(b200sdf_ctx *ctx, uint64_t ticket)
 	const cudaError_t e = cudaEventQuery(s.done);
 	if (e == cudaErrorNotReady)
 		return 0;
+	report_gpu_trace(ctx, s);
 	release_slot(ctx, s, 0);
 	if (e != cudaSuccess)
 		return fail_cuda(ctx, e, "cudaEventQuery");
