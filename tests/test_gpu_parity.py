@@ -252,6 +252,96 @@ def test_unaligned_and_sparse_output_offsets(ctx):
     assert not out[mask].any()
 
 
+def test_vertex_band_long_decomposition_edge_cases(ctx):
+    """The kernel takes min over segments as vertices + band interiors of short segments + clamped projection of
+    long ones.  Shapes chosen to sit on its seams: segment lengths at and around the 0.5 px
+    threshold, tiny segments (0.01..0.3 px) in every direction incl. exactly axis-aligned and 45 degrees, end points and
+    whole segments exactly on pixel centres, repeated points (zero length), open polylines (raw segments need both
+    end points as vertices), bands crossing tile-rectangle boundaries of a glyph that is cut into several CTAs."""
+    rng = np.random.default_rng(20261018)
+    jobs, segs, rings_per_job, off = [], [], [], 0
+
+    def add(W, H, rings):
+        nonlocal off
+        s = [np.concatenate([np.asarray(r)[:-1], np.asarray(r)[1:]], axis=1) for r in rings]
+        s = np.concatenate(s).astype(np.float32)
+        jobs.append((sum(len(x) for x in segs), len(s), W, H, off))
+        segs.append(s)
+        rings_per_job.append([np.asarray(r, np.float32).astype(np.float64).tolist() for r in rings])
+        off += W * H
+
+    # 1. polygons whose edges are chains of equal steps of a given length (incl. exactly 0.5 and its neighbours)
+    for step in (0.01, 0.05, 0.3, 0.4999, 0.5, 0.5001, 0.75, 3.0):
+        W, H = 31, 27
+        corners = np.array([[5.5, 5.5], [25.5, 6.0], [24.0, 21.5], [12.25, 19.0], [6.0, 22.0]])
+        pts = []
+        for a, b in zip(corners, np.roll(corners, -1, axis=0)):
+            n = max(1, int(np.ceil(np.linalg.norm(b - a) / step)))
+            d = (b - a) / np.linalg.norm(b - a)
+            for k in range(n):
+                pts.append(a + d * min(k * step, np.linalg.norm(b - a)))
+        pts.append(pts[0])
+        add(W, H, [pts])
+    # 2. axis-aligned and diagonal staircases through pixel centres, with repeated points
+    stair = [(4.5, 4.5), (4.5, 4.5), (14.5, 4.5), (14.5, 9.5), (14.5, 9.5), (19.5, 14.5), (19.5, 20.5), (9.5, 20.5),
+             (4.5, 15.5), (4.5, 4.5)]
+    add(25, 25, [stair])
+    fine = []
+    for a, b in zip(stair[:-1], stair[1:]):  # the same outline in 0.125 px steps (exact in binary)
+        a, b = np.array(a), np.array(b)
+        n = int(round(np.abs(b - a).max() / 0.125))
+        for k in range(max(n, 1)):
+            fine.append(a + (b - a) * (k / max(n, 1)))
+    fine.append(fine[0])
+    add(25, 25, [fine])
+    # 3. random smooth blobs: thousands of tiny segments in every direction
+    for _ in range(12):
+        W, H = int(rng.integers(12, 60)), int(rng.integers(12, 60))
+        n = int(rng.integers(200, 3000))
+        t = np.linspace(0, 2 * np.pi, n + 1)
+        r = (min(W, H) / 2 - 4) * (1 + 0.25 * np.sin(3 * t + rng.uniform(0, 6)) + 0.1 * np.sin(7 * t + rng.uniform(0, 6)))
+        ring = np.stack([W / 2 + r * np.cos(t), H / 2 + r * np.sin(t)], axis=1)
+        ring[-1] = ring[0]
+        hole = np.stack([W / 2 + 2.2 * np.cos(-t[::8]), H / 2 + 2.2 * np.sin(-t[::8])], axis=1)
+        hole[-1] = hole[0]
+        add(W, H, [ring, hole])
+    # 4. a glyph large enough to be cut into many rectangles, outline in 0.07 px steps
+    W, H = 150, 110
+    t = np.linspace(0, 2 * np.pi, 5001)
+    ring = np.stack([75 + 60 * np.cos(t) + 6 * np.cos(9 * t), 55 + 42 * np.sin(t) + 5 * np.sin(11 * t)], axis=1)
+    ring[-1] = ring[0]
+    add(W, H, [ring])
+    allsegs = np.concatenate(segs)
+    jb = np.array(jobs, JOB_DT)
+    out = ctx.render(allsegs, jb, off)
+    px = same = 0
+    for j, rings in zip(jb, rings_per_job):
+        Wj, Hj = int(j["width"]), int(j["height"])
+        got = out[int(j["out_off"]) : int(j["out_off"]) + Wj * Hj]
+        want = O.renderer_precise(0, 0, Wj, Hj, rings)
+        p, sm = compare_bitmaps(got, want, (Wj, Hj))
+        px += p
+        same += sm
+    print(f"decomposition edge cases: {px} px, {100.0 * same / px:.4f}% identical")
+    assert same / px >= MIN_IDENTICAL
+    # 5. an OPEN polyline through the raw-segment seam: distances only (no interior), both end points count
+    open_pts = np.array([[3.2, 3.7], [9.9, 4.1], [10.0, 4.1], [10.05, 4.15], [16.5, 12.25]], np.float32)
+    s = np.concatenate([open_pts[:-1], open_pts[1:]], axis=1)
+    got = ctx.render(s, np.array([(0, len(s), 20, 16, 0)], JOB_DT), 320).reshape(16, 20).astype(int)
+    yy, xx = np.mgrid[0:16, 0:20]
+    pxc, pyc = xx + 0.5, (15 - yy) + 0.5  # row 0 = top
+    d2 = np.full((16, 20), np.inf)
+    for x0, y0, x1, y1 in s.astype(np.float64):
+        dx, dy = x1 - x0, y1 - y0
+        tt = np.clip(((pxc - x0) * dx + (pyc - y0) * dy) / (dx * dx + dy * dy), 0, 1)
+        d2 = np.minimum(d2, (pxc - x0 - tt * dx) ** 2 + (pyc - y0 - tt * dy) ** 2)
+    want = np.rint(np.clip(191 - 32 * np.sqrt(d2), 0, 255)).astype(int)  # winding 0 everywhere: outside
+    # (an open polyline has no inside; crossings of its segments still toggle the reference's winding sum on some
+    # rows, so compare only where no segment is crossed to the left: rows above and below the polyline)
+    rows_clear = [r for r in range(16) if (15 - r) + 0.5 > 12.25 or (15 - r) + 0.5 < 3.7]
+    assert np.abs(got[rows_clear] - want[rows_clear]).max() <= 1
+
+
 def test_large_glyph_is_tiled_over_several_ctas(ctx):
     """A 300x200 px glyph (one CTA covers at most 128 4x4 tiles) incl. a counter-wound hole and a
     self-overlapping second ring: winding prefix across tile-rectangle boundaries, column strips."""
