@@ -62,6 +62,14 @@
 #define B200SDF_CURVE_SMEM 256 // curve records (32 B) kept in shared memory per CTA
 #endif
 
+// -DB200SDF_DEBUG_BOUNDS: trap on any shared-memory index outside its array (compute-sanitizer stand-in)
+#ifdef B200SDF_DEBUG_BOUNDS
+#include <assert.h>
+#define B200SDF_CHECK(cond) assert(cond)
+#else
+#define B200SDF_CHECK(cond) ((void)0)
+#endif
+
 namespace b200sdf {
 
 constexpr int kThreads = 128;
@@ -184,8 +192,10 @@ __device__ __forceinline__ void scatter_crossings(const float4 s, const float dx
 		const float xc = s.x + t * dx;
 		int c = (int)ceilf(xc - 0.5f) - R.rx0; // first column with centre >= x_c
 		c = max(c, 0);
-		if (c < R.rw)
+		if (c < R.rw) {
+			B200SDF_CHECK(r >= R.ry0 && r < R.ry0 + R.rh && c >= 0 && (r - R.ry0) * R.rw + c < kMaxPix);
 			atomicAdd(&delta[(r - R.ry0) * R.rw + c], up ? -1 : 1);
+		}
 	}
 }
 
@@ -239,6 +249,7 @@ __device__ __forceinline__ void band_scatter(const float4 s, float dx, float dy,
 		const int c = (int)cf;
 		if (u > 0.0f && u < l2 && (unsigned)(c - c0) < (unsigned)cn) {
 			const float cr = fmaf(pac, dm, -(pam * dc));
+			B200SDF_CHECK((cell + c * stride_c) >= d2 && (cell + c * stride_c) < d2 + R.rw * R.rh && R.rw * R.rh <= kMaxPix);
 			atomicMin(cell + c * stride_c, __float_as_uint((cr * cr) * inv));
 		}
 	}
@@ -520,6 +531,7 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 					const float l2 = dx * dx + dy * dy;
 					inv = l2 > 0.0f ? __frcp_rn(l2) : 0.0f;
 					is_long = l2 > kLongL2;
+					B200SDF_CHECK(i >= 0 && 2 * i + 1 < kVtx);
 					if (from_curves) {
 						ws.vtx[i] = make_float2(-s.x, -s.y); // rings are closed: every end is another segment's start
 					} else {
@@ -535,6 +547,7 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 				const unsigned mask = __ballot_sync(0xffffffffu, is_long);
 				if (is_long) {
 					const int k = n_long + __popc(mask & ((1u << lane) - 1u));
+					B200SDF_CHECK(k >= 0 && k < kMini);
 					ws.recA[k] = SegA{-s.x, -s.y, -dx, -dy};
 					ws.recN[k] = SegN{dx * inv, dy * inv};
 				}
@@ -679,8 +692,10 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 #pragma unroll
 			for (int j = 0; j < kTileW; ++j) {
 				const int x = tx * kTileW + j;
-				if (x < R.rw && y < R.rh)
+				if (x < R.rw && y < R.rh) {
+					B200SDF_CHECK(y * R.rw + x < kMaxPix);
 					atomicMin(&sm.d2[y * R.rw + x], __float_as_uint(mn[r][j]));
+				}
 			}
 		}
 	}
