@@ -209,3 +209,19 @@ def test_render_glyphs_into_tar_matches_directory_sink(tmp_path):
     got = {mm.name: tf.extractfile(mm).read() for mm in tf.getmembers() if mm.isfile()}
     assert got == want
     assert sum(1 for n in got if n.endswith(".pbf")) == 512  # manager.rs:199: all 256 ranges per font
+
+
+def test_writer_failure_mid_pipeline_is_an_error_not_a_hang():
+    """A sink that starts failing after the first flush (/dev/full): render_glyphs reports the error from every
+    worker configuration, leaves no thread stuck, and the manager renders normally afterwards."""
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full")
+    m = V.FontManager(parallel=True)
+    m.add_font_with_name("Fira Sans - Regular", [O.FIRA])
+    r = V.Renderer.new_dummy()
+    for threads in (1, 3, 0):
+        with pytest.raises(V.B200Error, match="writing tar"):
+            m.render_glyphs(V.Writer.new_tar("/dev/full"), r, threads=threads)
+    w = V.Writer.new_memory()
+    st = m.render_glyphs(w, r)
+    assert st.blocks == 256 and st.glyphs == 1686
