@@ -388,14 +388,22 @@ size_t acquire_slot(b200sdf_ctx *ctx)
 	return si;
 }
 
+uint64_t now_ns_mono()
+{
+	timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+
 void report_gpu_trace(b200sdf_ctx *ctx, Slot &s)
 {
 	if (!s.t1 || !s.traced_tiles || !ctx->epoch)
 		return;
 	float a = 0.f, b = 0.f;
 	if (cudaEventElapsedTime(&a, ctx->epoch, s.t0) == cudaSuccess && cudaEventElapsedTime(&b, ctx->epoch, s.t1) == cudaSuccess)
-		std::fprintf(stderr, "[b200sdf gpu] submit %.1f us  kernel %.1f .. %.1f us (%.1f us, %u CTAs)\n",
-		             (double)(s.host_submit_ns - ctx->epoch_host_ns) * 1e-3, a * 1e3, b * 1e3, (b - a) * 1e3, s.traced_tiles);
+		std::fprintf(stderr, "[b200sdf gpu] submit %.1f us  kernel %.1f .. %.1f us (%.1f us, %u CTAs)  seen %.1f us  abs0 %llu\n",
+		             (double)(s.host_submit_ns - ctx->epoch_host_ns) * 1e-3, a * 1e3, b * 1e3, (b - a) * 1e3, s.traced_tiles,
+		             (double)(now_ns_mono() - ctx->epoch_host_ns) * 1e-3, (unsigned long long)ctx->epoch_host_ns);
 	s.traced_tiles = 0;
 }
 

@@ -618,6 +618,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	size_t outstanding = 0; // batches submitted (or queued for it) and not yet encoded
 	int workers_done = 0;
 	std::atomic<uint64_t> submit_ns{0};
+	std::atomic<uint64_t> done_seq{0}; // batches handed back so far (workers spin on it before they sleep)
+	std::atomic<int> sleepers{0};      // workers blocked in qcv.wait (the submitter only pays for a wake-up then)
 	const bool inline_pump = workers == 1;
 	// never more batches on their way than the renderer has slots for (submit would block the submitter)
 	const size_t max_outstanding =
@@ -724,9 +726,12 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					if (outstanding >= max_outstanding) { // back-pressure: wait for a completion
 						if (inline_pump)
 							lk.unlock(), pump(true);
-						else
+						else {
+							sleepers.fetch_add(1, std::memory_order_acq_rel);
 							qcv.wait_for(lk, std::chrono::milliseconds(50),
 							             [&] { return !done_q.empty() || outstanding < max_outstanding || failed.load(); });
+							sleepers.fetch_sub(1, std::memory_order_acq_rel);
+						}
 						continue;
 					}
 					++outstanding; // reserve the place now: several workers pass this check at the same time
@@ -818,10 +823,25 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				if (!done_q.empty())
 					continue;
 				const uint64_t t0 = now_ns();
-				if (inline_pump)
+				if (inline_pump) {
 					lk.unlock(), pump(true);
-				else
-					qcv.wait_for(lk, std::chrono::milliseconds(50), [&] { return !done_q.empty() || outstanding == 0 || failed.load(); });
+				} else {
+					// spin briefly on the hand-back counter before sleeping: at the end of a call the next batch is
+					// usually tens of microseconds away, less than a sleep / wake-up round trip
+					const uint64_t seen = done_seq.load(std::memory_order_acquire);
+					lk.unlock();
+					bool changed = false;
+					for (int spin = 0; spin < 4000 && !changed; ++spin) {
+						cpu_pause();
+						changed = done_seq.load(std::memory_order_acquire) != seen || failed.load(std::memory_order_relaxed);
+					}
+					lk.lock();
+					if (!changed && done_q.empty() && outstanding != 0 && !failed.load()) {
+						sleepers.fetch_add(1, std::memory_order_acq_rel);
+						qcv.wait_for(lk, std::chrono::milliseconds(50), [&] { return !done_q.empty() || outstanding == 0 || failed.load(); });
+						sleepers.fetch_sub(1, std::memory_order_acq_rel);
+					}
+				}
 				st.wait_ns += now_ns() - t0;
 			}
 		}
@@ -832,6 +852,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	// The submitter: submit whatever the workers queued, poll what is in flight, hand back what finished.
 	// (With one worker it is called inline: `block` = nothing else to do, wait for the oldest batch.)
 	std::deque<Flight *> inflight; // touched by the pumping thread only
+	std::vector<Flight *> finished_now;
 	pump = [&](bool block) {
 		bool progressed = false;
 		for (;;) {
@@ -861,12 +882,14 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 						std::lock_guard<std::mutex> g(qm);
 						done_q.push_back(f);
 					}
+					done_seq.fetch_add(1, std::memory_order_release);
 					qcv.notify_all();
 				}
 			}
 			// a polling sweep after every submission: slots come back only through here.  Batches finish
 			// roughly in submission order, so only the oldest few are asked (a query costs about a microsecond).
-			const size_t sweep = f ? 2 : 6;
+			const size_t sweep = f ? 2 : 8;
+			finished_now.clear();
 			for (size_t i = 0; i < inflight.size() && i < sweep;) {
 				Flight *q = inflight[i];
 				bool finished = false;
@@ -891,11 +914,19 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				if (trace)
 					events[(size_t)workers].emplace_back('d', now_ns() - t_begin);
 				inflight.erase(inflight.begin() + (long)i);
+				finished_now.push_back(q);
+			}
+			if (!finished_now.empty()) {
+				// hand everything that finished in this sweep over at once: one lock, one wake-up (a futex wake per
+				// batch cost the submitter ~10 us each and completions queued up behind it at the end of a call)
 				{
 					std::lock_guard<std::mutex> g(qm);
-					done_q.push_back(q);
+					for (Flight *q : finished_now)
+						done_q.push_back(q);
 				}
-				qcv.notify_one();
+				done_seq.fetch_add((uint64_t)finished_now.size(), std::memory_order_release);
+				if (sleepers.load(std::memory_order_acquire) > 0)
+					qcv.notify_all();
 			}
 			if (!f)
 				break;
