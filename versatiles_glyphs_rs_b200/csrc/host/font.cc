@@ -12,6 +12,7 @@
 #include <condition_variable>
 #include <fstream>
 #include <functional>
+#include <malloc.h>
 #include <pthread.h>
 #include <sched.h>
 #include <sys/stat.h>
@@ -495,6 +496,21 @@ class WorkerPool {
 bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::string *err, RenderStats *stats,
                                 uint32_t shard, uint32_t n_shards, int threads) const
 {
+	// glibc serves allocations >= 128 KiB (every full block's PBF) with mmap: fresh pages, i.e. ~30 page faults per
+	// file, every call.  Keep such blocks on the heap, where the pages freed after one call are reused by the next.
+	// (Process-wide malloc tuning; VGB_KEEP_MALLOC_DEFAULTS=1 leaves the allocator alone.)
+	static const bool malloc_tuned = [] {
+		if (std::getenv("VGB_KEEP_MALLOC_DEFAULTS"))
+			return false;
+#if defined(__GLIBC__)
+		mallopt(M_MMAP_THRESHOLD, 64 << 20);
+		mallopt(M_TRIM_THRESHOLD, 512 << 20);
+		return true;
+#else
+		return false;
+#endif
+	}();
+	(void)malloc_tuned;
 	// A task is a slot range of one block holding at most kPartGlyphs (64) glyphs: full blocks are split so that
 	// no worker is stuck recording 256 outlines while the others (and the GPU) run dry.  The parts of a
 	// block are encoded independently (Fontstack.glyphs entries) and the worker that finishes the last
