@@ -226,7 +226,16 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        cpus_before = os.sched_getaffinity(0)
         dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()  # NCCL communicator is built here
+        # NCCL pins the calling thread to the GPU's NUMA-local cores while it initialises; threads created later
+        # (the pipeline's workers) would inherit a narrowed mask.  Restore what the launcher gave this process.
+        cpus_after = os.sched_getaffinity(0)
+        if cpus_after != cpus_before:
+            os.sched_setaffinity(0, cpus_before)
+        print(f"[bench] rank {rank}: cpu affinity {len(cpus_before)} cpus at start, {len(cpus_after)} after NCCL init",
+              file=sys.stderr)
 
     def barrier():
         if dist is not None:
@@ -400,7 +409,11 @@ def main():
             ts = time.perf_counter()
             st = manager.render_glyphs(V.Writer.new_memory(), renderer, threads=host_threads)
             step_ms.append(1e3 * (time.perf_counter() - ts))
+        t_loop = time.perf_counter() - t0
+        tb = time.perf_counter()
         barrier()
+        print(f"[bench] rank {rank}: e2e loop {1e3 * t_loop:.1f} ms, closing barrier {1e3 * (time.perf_counter() - tb):.1f} ms, "
+              f"steps min/median/max {min(step_ms):.2f}/{statistics.median(step_ms):.2f}/{max(step_ms):.2f} ms", file=sys.stderr)
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         result["e2e"] = {
             "value": world * st.glyphs * e2e_steps / e2e_s, "unit": "glyphs/s",

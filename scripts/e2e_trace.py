@@ -13,7 +13,7 @@ import versatiles_glyphs_rs_b200 as V  # noqa: E402
 threads = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 m = V.FontManager(parallel=True)
 m.add_font_with_name("Noto Sans Regular", O.noto_paths())
-r = V.Renderer.new_precise(device=0)
+r = V.Renderer.new_precise(device=int(os.environ.get("VGB_DEVICE", "0")))
 ts = []
 for i in range(30):
     w = V.Writer.new_memory()

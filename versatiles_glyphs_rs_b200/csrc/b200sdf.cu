@@ -67,6 +67,11 @@ PinnedRegistry &pinned_registry()
 #define B200SDF_ZEROCOPY_CURVES 1
 #endif
 // B200SDF_ZEROCOPY: 0 = stage everything, 1 (default) = inputs and bitmaps in place, 2 = bitmaps only
+// Device of the most recently created context: threads that only allocate pinned memory (a pipeline's workers never
+// call cudaSetDevice themselves) must not touch — and thereby create a CUDA context on — device 0 in a process that
+// renders on another GPU.
+std::atomic<int> g_home_device{-1};
+
 int zero_copy_mode()
 {
 	static const int mode = [] {
@@ -618,6 +623,7 @@ int b200sdf_create(int device, uint32_t n_slots, b200sdf_ctx **out)
 		delete ctx;
 		return B200SDF_E_CUDA;
 	}
+	g_home_device.store(device, std::memory_order_relaxed);
 	cudaDeviceProp prop;
 	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
 		// sm_100a code only: refuse anything else instead of failing at the first launch
@@ -675,6 +681,12 @@ uint64_t b200sdf_launch_count(const b200sdf_ctx *ctx) { return ctx ? ctx->launch
 void *b200sdf_alloc_pinned(size_t bytes)
 {
 	void *p = nullptr;
+	const int home = g_home_device.load(std::memory_order_relaxed);
+	if (home >= 0) {
+		int cur = -1;
+		if (cudaGetDevice(&cur) != cudaSuccess || cur != home)
+			cudaSetDevice(home);
+	}
 	if (std::getenv("B200SDF_TRACE"))
 		std::fprintf(stderr, "[b200sdf trace] alloc_pinned %zu bytes\n", bytes);
 	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
