@@ -303,7 +303,7 @@ def test_bad_font_errors():
 
 def test_pipeline_with_asynchronous_completion_is_byte_identical():
     """The submitter / worker queues of FontManager::render_glyphs under out-of-order, delayed completion
-    (VGB_FAKE_LATENCY makes the dummy renderer answer "still running" to most polls): split blocks are
+    (VGB_FAKE_LATENCY: a dummy batch finishes only 400 us after its submission): split blocks are
     reassembled byte-identically, for many worker counts and for the inline single-thread pump."""
     import subprocess
     import sys
@@ -316,9 +316,14 @@ m = V.FontManager(parallel=True)
 m.add_font_with_name("Noto Sans Regular", O.noto_paths())
 m.add_font_with_name("Fira Sans - Regular", [O.FIRA])
 r = V.Renderer.new_dummy()
-for threads in (1, 2, 3, 8, 0, 5, 1):
+import time
+for threads in (1, 2, 3, 8, 0, 5, 1) * 3:
     w = V.Writer.new_memory()
+    t0 = time.perf_counter()
     st = m.render_glyphs(w, r, threads=threads)
+    # the workers' condition waits have a safety-net timeout (VGB_WAIT_MS, 3 s here): a lost wake-up would show
+    # up as a call that takes that long instead of milliseconds
+    assert time.perf_counter() - t0 < 2.0, (threads, time.perf_counter() - t0)
     files = sorted((n, d) for n, is_dir, d in w.entries() if not is_dir)
     h = hashlib.sha256()
     for n, d in files:
@@ -329,13 +334,14 @@ for threads in (1, 2, 3, 8, 0, 5, 1):
     for fake in (False, True):
         env = dict(os.environ)
         env.pop("VGB_FAKE_LATENCY", None)
+        env["VGB_WAIT_MS"] = "3000"
         if fake:
-            env["VGB_FAKE_LATENCY"] = "1"
+            env["VGB_FAKE_LATENCY"] = "400"  # microseconds per batch: long enough for idle workers to go to sleep
         res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert res.returncode == 0, res.stderr[-2000:]
         outs.append([ln.split() for ln in res.stdout.strip().splitlines()])
     lines = outs[0] + outs[1]
-    assert len(lines) == 14
+    assert len(lines) == 42
     assert {ln[1] for ln in lines} == {"512"} and {ln[2] for ln in lines} == {str(6480 + 1686)}
     assert len({ln[3] for ln in lines}) == 1, lines  # every run produced exactly the same files
 

@@ -634,6 +634,11 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	size_t outstanding = 0; // batches submitted (or queued for it) and not yet encoded
 	int workers_done = 0;
 	std::atomic<uint64_t> submit_ns{0};
+	static const int kWaitMs = [] { // safety-net timeout of the workers' condition waits (diagnostics knob)
+		const char *e = std::getenv("VGB_WAIT_MS");
+		const int v = e ? std::atoi(e) : 0;
+		return v > 0 ? v : 50;
+	}();
 	std::atomic<uint64_t> done_seq{0}; // batches handed back so far (workers spin on it before they sleep)
 	std::atomic<int> sleepers{0};      // workers blocked in qcv.wait (the submitter only pays for a wake-up then)
 	const bool inline_pump = workers == 1;
@@ -744,7 +749,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 							lk.unlock(), pump(true);
 						else {
 							sleepers.fetch_add(1, std::memory_order_acq_rel);
-							qcv.wait_for(lk, std::chrono::milliseconds(50),
+							qcv.wait_for(lk, std::chrono::milliseconds(kWaitMs),
 							             [&] { return !done_q.empty() || outstanding < max_outstanding || failed.load(); });
 							sleepers.fetch_sub(1, std::memory_order_acq_rel);
 						}
@@ -781,8 +786,11 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				st.outline_ns += now_ns() - t0;
 				if (cur->parts.empty()) {
 					renderer.release_batch(std::move(cur->batch));
-					std::lock_guard<std::mutex> g(qm);
-					--outstanding;
+					{
+						std::lock_guard<std::mutex> g(qm);
+						--outstanding;
+					}
+					qcv.notify_all(); // a worker may be asleep waiting for exactly this reservation to go away
 					continue;
 				}
 				st.glyphs += cur->batch->glyphs().size();
@@ -854,7 +862,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					lk.lock();
 					if (!changed && done_q.empty() && outstanding != 0 && !failed.load()) {
 						sleepers.fetch_add(1, std::memory_order_acq_rel);
-						qcv.wait_for(lk, std::chrono::milliseconds(50), [&] { return !done_q.empty() || outstanding == 0 || failed.load(); });
+						qcv.wait_for(lk, std::chrono::milliseconds(kWaitMs), [&] { return !done_q.empty() || outstanding == 0 || failed.load(); });
 						sleepers.fetch_sub(1, std::memory_order_acq_rel);
 					}
 				}
@@ -862,6 +870,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			}
 		}
 		flush();
+		if (failed.load())
+			qcv.notify_all(); // sleepers look at `failed`
 		mark('E');
 	};
 

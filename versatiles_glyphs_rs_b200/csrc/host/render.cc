@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <thread>
 
@@ -582,6 +583,22 @@ void Renderer::release_batch(std::unique_ptr<GlyphBatch> b) const
 		pool_.push_back(std::move(b));
 }
 
+namespace {
+uint64_t fake_now_ns()
+{
+	return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+uint64_t fake_latency_ns()
+{
+	static const uint64_t ns = [] {
+		const char *e = std::getenv("VGB_FAKE_LATENCY");
+		const long us = e ? std::atol(e) : 0;
+		return (uint64_t)(us > 0 ? us : 0) * 1000ull;
+	}();
+	return ns;
+}
+} // namespace
+
 bool Renderer::prepare_batch(GlyphBatch &batch, std::string *err) const
 {
 	if (!batch.ensure_output()) {
@@ -610,7 +627,7 @@ bool Renderer::submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *er
 	if (mode_ == Mode::Dummy) {
 		// renderer_dummy.rs:3-5 — zero-filled bitmaps of the right size
 		std::memset(batch.bitmaps(), 0, (size_t)batch.bitmap_bytes());
-		*ticket = ~0ull;
+		*ticket = fake_latency_ns() ? fake_now_ns() + fake_latency_ns() : ~0ull; // (test hook, see poll_batch)
 		return true;
 	}
 	const int rc =
@@ -630,8 +647,11 @@ bool Renderer::submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *er
 
 bool Renderer::wait_batch(uint64_t ticket, std::string *err) const
 {
-	if (mode_ == Mode::Dummy)
+	if (mode_ == Mode::Dummy) {
+		while (ticket != ~0ull && fake_now_ns() < ticket)
+			std::this_thread::yield();
 		return true;
+	}
 	const int rc = b200sdf_wait(ctx_, ticket);
 	if (rc != 0) {
 		if (err)
@@ -645,12 +665,11 @@ bool Renderer::poll_batch(uint64_t ticket, bool *done, std::string *err) const
 {
 	*done = true;
 	if (mode_ == Mode::Dummy) {
-		// test hook: VGB_FAKE_LATENCY makes the dummy renderer report "still running" most of the time, so the
-		// CPU tests exercise the asynchronous paths of the pipeline (tests/test_host_vs_oracle.py)
-		static const bool fake = std::getenv("VGB_FAKE_LATENCY") != nullptr;
-		static std::atomic<unsigned> n{0};
-		if (fake && (n.fetch_add(1) % 7) != 0)
-			*done = false;
+		// test hook: VGB_FAKE_LATENCY=<microseconds> makes a dummy batch "finish" only that long after its
+		// submission (the ticket carries the submission time), so the CPU tests exercise the asynchronous paths of
+		// the pipeline: polling, sleeping workers, out-of-order hand-back (tests/test_host_vs_oracle.py)
+		if (ticket != ~0ull)
+			*done = fake_now_ns() >= ticket;
 		return true;
 	}
 	const int rc = b200sdf_poll(ctx_, ticket);
