@@ -104,7 +104,7 @@ bool FontWrapper::add_paths(const std::vector<std::string> &sources, std::string
 		std::unique_ptr<FontFileEntry> e = FontFileEntry::from_path(p, err);
 		if (!e)
 			return false;
-		files_.push_back(std::move(e));
+		add_file(std::move(e));
 	}
 	return true;
 }
@@ -121,6 +121,14 @@ std::vector<GlyphBlock> FontWrapper::get_blocks() const
 		ptrs[i] = &blocks[i];
 	assign_blocks(ptrs.data());
 	return blocks;
+}
+
+const std::vector<GlyphBlock> &FontWrapper::blocks() const
+{
+	std::lock_guard<std::mutex> g(blocks_mu_);
+	if (blocks_.empty())
+		blocks_ = get_blocks();
+	return blocks_;
 }
 
 void FontWrapper::assign_blocks(GlyphBlock *const *blocks) const
@@ -522,7 +530,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	}();
 	struct BlockState {
 		const std::string *name = nullptr;
-		GlyphBlock block;
+		const GlyphBlock *blk = nullptr;
 		std::vector<std::vector<uint8_t>> parts;
 		std::atomic<uint32_t> remaining{0};
 	};
@@ -544,22 +552,20 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			return false;
 		fonts_blocks.emplace_back(new BlockState[kBlocks]);
 		BlockState *bsv = fonts_blocks.back().get();
-		GlyphBlock *ptrs[kBlocks];
+		const std::vector<GlyphBlock> &table = kv.second.blocks(); // = get_blocks(), built once per font set
 		for (uint32_t i = 0; i < kBlocks; ++i) {
 			bsv[i].name = &kv.first;
-			bsv[i].block.reset(i * GLYPH_BLOCK_SIZE);
-			ptrs[i] = &bsv[i].block;
+			bsv[i].blk = &table[i];
 		}
-		kv.second.assign_blocks(ptrs); // = get_blocks(), written in place
 		for (uint32_t i = 0; i < kBlocks; ++i) {
 			if (index++ % n_shards != shard)
 				continue;
 			BlockState *bs = &bsv[i];
-			total_glyphs += bs->block.len();
+			total_glyphs += bs->blk->len();
 			uint32_t part = 0, slot0 = 0, count = 0;
-			if (bs->block.len() > kPartGlyphs) {
+			if (bs->blk->len() > kPartGlyphs) {
 				for (uint32_t k = 0; k < GLYPH_BLOCK_SIZE; ++k) {
-					if (!bs->block.font_of((uint8_t)k))
+					if (!bs->blk->font_of((uint8_t)k))
 						continue;
 					if (count == kPartGlyphs) {
 						tasks.push_back(Todo{bs, part++, slot0, k, count});
@@ -568,7 +574,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					++count;
 				}
 			} else {
-				count = (uint32_t)bs->block.len(); // small and empty blocks: one part
+				count = (uint32_t)bs->blk->len(); // small and empty blocks: one part
 			}
 			tasks.push_back(Todo{bs, part++, slot0, GLYPH_BLOCK_SIZE, count});
 			bs->parts.resize(part);
@@ -663,7 +669,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			std::vector<uint8_t> data;
 			const bool whole = bs.parts.size() == 1;
 			if (whole)
-				data = bs.block.encode_range(*bs.name, batch, g0, g1);
+				data = bs.blk->encode_range(*bs.name, batch, g0, g1);
 			else
 				bs.parts[todo.part] = encode_glyph_entries(batch, g0, g1);
 			if (!whole && bs.remaining.fetch_sub(1, std::memory_order_acq_rel) != 1) {
@@ -672,13 +678,13 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			}
 			if (!whole) {
 				mark('a');
-				data = assemble_glyphs_pbf(*bs.name, bs.block.range(), bs.parts);
+				data = assemble_glyphs_pbf(*bs.name, bs.blk->range(), bs.parts);
 				mark('A');
 			}
 			st.encode_ns += now_ns() - t0;
 			st.pbf_bytes += data.size();
 			st.blocks++;
-			pending.emplace_back(*bs.name + "/" + bs.block.filename(), std::move(data));
+			pending.emplace_back(*bs.name + "/" + bs.blk->filename(), std::move(data));
 			return true;
 		};
 		// finished files are handed to the writer in groups: one lock acquisition per retired batch instead
@@ -780,7 +786,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					const Todo &todo = tasks[ti];
 					const size_t g0 = cur->batch->glyphs().size();
 					glyphs_taken.fetch_add(todo.glyphs, std::memory_order_relaxed);
-					todo.bs->block.append_to_batch(*cur->batch, todo.slot0, todo.slot1);
+					todo.bs->blk->append_to_batch(*cur->batch, todo.slot0, todo.slot1);
 					cur->parts.push_back(Part{&todo, g0, cur->batch->glyphs().size()});
 				}
 				st.outline_ns += now_ns() - t0;

@@ -110,16 +110,25 @@ class GlyphBlock {
 
 class FontWrapper {
   public:
-	void add_file(std::unique_ptr<FontFileEntry> file) { files_.push_back(std::move(file)); }
+	void add_file(std::unique_ptr<FontFileEntry> file)
+	{
+		files_.push_back(std::move(file));
+		blocks_.clear(); // the block table is rebuilt on next use
+	}
 	bool add_paths(const std::vector<std::string> &sources, std::string *err);
 	const std::vector<std::unique_ptr<FontFileEntry>> &files() const { return files_; }
 	// wrapper.rs:53-76 — always 256 BMP blocks, code points > 0xFFFF ignored
 	std::vector<GlyphBlock> get_blocks() const;
 	// the same assignment written into 256 caller-owned blocks (block i must start at i * 256)
 	void assign_blocks(GlyphBlock *const *blocks) const;
+	// get_blocks() as a table owned by the wrapper: a pure function of the files, so it is built when first
+	// needed after the last add_file (i.e. at load time, like the parsed cmap) and reused by every render_glyphs
+	const std::vector<GlyphBlock> &blocks() const;
 
   private:
 	std::vector<std::unique_ptr<FontFileEntry>> files_;
+	mutable std::vector<GlyphBlock> blocks_;
+	mutable std::mutex blocks_mu_;
 };
 
 // writer/mod.rs.  kinds: directory on disk (file.rs), in-memory recorder (dummy.rs + content).
