@@ -189,6 +189,13 @@ int b200sdf_render_device(b200sdf_ctx *ctx, const b200sdf_segment *d_segs, const
 int b200sdf_plan_outline_tiles(const b200sdf_outline_job *jobs, uint32_t n_jobs, uint32_t n_curves, uint32_t n_seg,
                                uint64_t out_bytes, b200sdf_tile_job *tiles, uint32_t cap, uint32_t *n_tiles,
                                uint64_t *pairs);
+/* The same with planning flags.  B200SDF_PLAN_LATENCY: the caller will wait for this batch alone (the last batches
+ * of a pipeline) — heavy glyphs are cut as finely as allowed, which shortens the kernel at the price of repeated
+ * staging; without it small batches are planned for throughput. */
+#define B200SDF_PLAN_LATENCY 1u
+int b200sdf_plan_outline_tiles_ex(const b200sdf_outline_job *jobs, uint32_t n_jobs, uint32_t n_curves, uint32_t n_seg,
+                                  uint64_t out_bytes, uint32_t flags, b200sdf_tile_job *tiles, uint32_t cap,
+                                  uint32_t *n_tiles, uint64_t *pairs);
 int b200sdf_render_outlines_device(b200sdf_ctx *ctx, const b200sdf_curve *d_curves, const b200sdf_segment *d_segs,
                                    const b200sdf_outline_job *d_jobs, const b200sdf_tile_job *d_tiles,
                                    uint32_t n_tiles, uint8_t *d_out, void *stream);

@@ -151,6 +151,8 @@ SDF_SYMBOLS = {
     "b200sdf_submit_outlines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, u64p]),
     "b200sdf_flatten_outlines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
     "b200sdf_plan_outline_tiles": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, u32p, u64p]),
+    "b200sdf_plan_outline_tiles_ex": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p,
+                                                C.c_uint32, u32p, u64p]),
     "b200sdf_render_outlines_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "b200sdf_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, f64p, f64p]),
     "b200sdf_launch_count": (C.c_uint64, [C.c_void_p]),

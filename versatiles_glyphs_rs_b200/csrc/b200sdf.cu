@@ -208,7 +208,7 @@ constexpr uint32_t kMinItemsSmall = 8;
 constexpr uint64_t kMinJobCostSmall = 65536;
 constexpr uint64_t kSmallBatchCost = (uint64_t)kSMs * kJobsPerSM * kMinJobCost; // ~19 M units, ~1000 median glyphs
 
-inline uint32_t items_cap(uint64_t total_cost, uint32_t seg_cnt)
+inline uint32_t items_cap(uint64_t total_cost, uint32_t seg_cnt, bool latency = false)
 {
 	static const uint32_t min_small = [] { // B200SDF_MIN_ITEMS_SMALL: tuning knob
 		const char *e = std::getenv("B200SDF_MIN_ITEMS_SMALL");
@@ -221,9 +221,12 @@ inline uint32_t items_cap(uint64_t total_cost, uint32_t seg_cnt)
 		return (uint64_t)(v >= 256 ? v : (long)kMinJobCostSmall);
 	}();
 	const bool small = total_cost < kSmallBatchCost;
-	const uint64_t cap = std::max<uint64_t>(total_cost / (kSMs * kJobsPerSM), small ? min_cost_small : kMinJobCost);
+	// latency: the caller waits for THIS batch alone (the last batches of a pipeline): cut as finely as allowed, so the
+	// kernel's critical path — its heaviest CTA — is short, whatever that costs in repeated staging
+	const uint64_t floor_cost = !small ? kMinJobCost : latency ? kMinJobCost : min_cost_small;
+	const uint64_t cap = std::max<uint64_t>(total_cost / (kSMs * kJobsPerSM), floor_cost);
 	const uint64_t items = cap / (uint64_t)(seg_cnt + 8);
-	const uint64_t floor_items = small ? min_small : kMinItems;
+	const uint64_t floor_items = small ? (latency ? std::min<uint64_t>(4, min_small) : min_small) : kMinItems;
 	return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(items, floor_items), (uint64_t)b200sdf::kMaxItems);
 }
 
@@ -303,7 +306,8 @@ int plan_segments(const b200sdf_glyph_job *jobs, uint32_t n_jobs, uint32_t n_seg
 
 // curves may be null (device-resident planning): then the per-record consistency check is skipped
 int plan_outlines(const b200sdf_outline_job *jobs, uint32_t n_jobs, const b200sdf_curve *curves, uint32_t n_curves,
-                  uint32_t n_seg, uint64_t out_bytes, std::vector<Planned> &v, uint64_t *pairs, const char **why)
+                  uint32_t n_seg, uint64_t out_bytes, std::vector<Planned> &v, uint64_t *pairs, const char **why,
+                  bool latency = false)
 {
 	uint64_t pr = 0, total = 0;
 	v.clear();
@@ -319,7 +323,7 @@ int plan_outlines(const b200sdf_outline_job *jobs, uint32_t n_jobs, const b200sd
 				*why = "outline job (segments) range exceeds n_seg or seg_cnt != src_cnt";
 				return B200SDF_E_ARG;
 			}
-			plan_glyph(j.src_off, j.seg_cnt, j.width, j.height, j.out_off, B200SDF_NO_JOB, items_cap(total, j.seg_cnt), v);
+			plan_glyph(j.src_off, j.seg_cnt, j.width, j.height, j.out_off, B200SDF_NO_JOB, items_cap(total, j.seg_cnt, latency), v);
 		} else if (j.kind == B200SDF_KIND_CURVES) {
 			if ((uint64_t)j.src_off + j.src_cnt > n_curves || (j.src_cnt == 0 && j.seg_cnt != 0)) {
 				*why = "outline job (curves) range exceeds n_curves";
@@ -341,7 +345,7 @@ int plan_outlines(const b200sdf_outline_job *jobs, uint32_t n_jobs, const b200sd
 					return B200SDF_E_ARG;
 				}
 			}
-			plan_glyph(j.src_off, j.seg_cnt, j.width, j.height, j.out_off, i, items_cap(total, j.seg_cnt), v);
+			plan_glyph(j.src_off, j.seg_cnt, j.width, j.height, j.out_off, i, items_cap(total, j.seg_cnt, latency), v);
 		} else {
 			*why = "outline job with unknown kind";
 			return B200SDF_E_ARG;
@@ -727,6 +731,18 @@ int b200sdf_plan_outline_tiles(const b200sdf_outline_job *jobs, uint32_t n_jobs,
 	std::vector<Planned> v;
 	const char *why = "";
 	int rc = plan_outlines(jobs, n_jobs, nullptr, n_curves, n_seg, out_bytes, v, pairs, &why);
+	return rc ? rc : copy_plan(v, tiles, cap, n_tiles);
+}
+
+int b200sdf_plan_outline_tiles_ex(const b200sdf_outline_job *jobs, uint32_t n_jobs, uint32_t n_curves, uint32_t n_seg,
+                                  uint64_t out_bytes, uint32_t flags, b200sdf_tile_job *tiles, uint32_t cap, uint32_t *n_tiles,
+                                  uint64_t *pairs)
+{
+	if ((!jobs && n_jobs) || !n_tiles)
+		return B200SDF_E_ARG;
+	std::vector<Planned> v;
+	const char *why = "";
+	int rc = plan_outlines(jobs, n_jobs, nullptr, n_curves, n_seg, out_bytes, v, pairs, &why, (flags & B200SDF_PLAN_LATENCY) != 0);
 	return rc ? rc : copy_plan(v, tiles, cap, n_tiles);
 }
 

@@ -278,7 +278,7 @@ void GlyphBatch::clear()
 	prepared_ = false;
 }
 
-bool GlyphBatch::plan_tiles(const char **why)
+bool GlyphBatch::plan_tiles(const char **why, bool latency)
 {
 	*why = "";
 	// most glyphs are one tile job; heavy ones are cut into several: start generous, retry once if short
@@ -289,8 +289,9 @@ bool GlyphBatch::plan_tiles(const char **why)
 			return false;
 		}
 		uint32_t n = 0;
-		const int rc = b200sdf_plan_outline_tiles(jobs(), n_jobs_, n_curves_, n_seg_, out_bytes_,
-		                                          reinterpret_cast<b200sdf_tile_job *>(tiles_.data()), cap, &n, nullptr);
+		const int rc = b200sdf_plan_outline_tiles_ex(jobs(), n_jobs_, n_curves_, n_seg_, out_bytes_,
+		                                             latency ? B200SDF_PLAN_LATENCY : 0u,
+		                                             reinterpret_cast<b200sdf_tile_job *>(tiles_.data()), cap, &n, nullptr);
 		if (rc != 0 && n <= cap) { // (a short buffer also answers non-zero, with the needed count in n)
 			*why = "invalid outline job (b200sdf_plan_outline_tiles)";
 			return false;
@@ -599,7 +600,7 @@ uint64_t fake_latency_ns()
 }
 } // namespace
 
-bool Renderer::prepare_batch(GlyphBatch &batch, std::string *err) const
+bool Renderer::prepare_batch(GlyphBatch &batch, std::string *err, bool latency) const
 {
 	if (!batch.ensure_output()) {
 		if (err)
@@ -609,7 +610,7 @@ bool Renderer::prepare_batch(GlyphBatch &batch, std::string *err) const
 	if (mode_ == Mode::Dummy)
 		return true;
 	const char *why = "";
-	if (!batch.plan_tiles(&why)) {
+	if (!batch.plan_tiles(&why, latency)) {
 		if (err)
 			*err = why;
 		return false;

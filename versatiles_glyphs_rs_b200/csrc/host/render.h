@@ -197,7 +197,7 @@ class GlyphBatch {
 	bool ensure_output(); // allocate the bitmap area (after the last add)
 	// plan the CTA work items of the recorded jobs into the batch's own (pinned) tile buffer; false + *why
 	// when a job is invalid.  After this, tiles()/tile_count() feed b200sdf_submit_planned.
-	bool plan_tiles(const char **why);
+	bool plan_tiles(const char **why, bool latency = false);
 	bool prepared() const { return prepared_; }
 	const b200sdf_tile_job *tiles() const { return reinterpret_cast<const b200sdf_tile_job *>(tiles_.data()); }
 	uint32_t tile_count() const { return n_tiles_; }
@@ -254,7 +254,7 @@ class Renderer {
 	bool wait_batch(uint64_t ticket, std::string *err = nullptr) const;
 	// Two-step submission for pipelines with one CUDA thread: prepare_batch (any thread: sizes the bitmap
 	// buffer, validates the jobs and plans the tiles) then submit_batch (enqueue only).
-	bool prepare_batch(GlyphBatch &batch, std::string *err = nullptr) const;
+	bool prepare_batch(GlyphBatch &batch, std::string *err = nullptr, bool latency = false) const;
 	// non-blocking: *done = the batch has finished (the ticket is consumed, as by wait_batch)
 	bool poll_batch(uint64_t ticket, bool *done, std::string *err = nullptr) const;
 
