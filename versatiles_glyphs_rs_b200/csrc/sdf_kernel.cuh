@@ -42,7 +42,7 @@
 #define B200SDF_UNROLL 1 // pair-loop unroll over segments (measured: 1 beats 2 and 4 — register pressure)
 #endif
 #ifndef B200SDF_MIN_CTAS
-#define B200SDF_MIN_CTAS 7 // __launch_bounds__ minimum CTAs per SM: 72 registers (measured best of 4..9)
+#define B200SDF_MIN_CTAS 8 // __launch_bounds__ minimum CTAs per SM: 64 registers (measured 6 / 7 / 8 with the shared-staging loop: 0.475 / 0.459 / 0.442 ms)
 #endif
 #define B200SDF_BOUNDS __launch_bounds__(128, B200SDF_MIN_CTAS)
 #ifndef B200SDF_ALGO
@@ -56,7 +56,7 @@
 #define B200SDF_SHARED_STAGE 1 // curve glyphs: stage each segment once per CTA, all warps consume all staged lists
 #endif
 #ifndef B200SDF_VUNROLL
-#define B200SDF_VUNROLL 2 // vertex-loop unroll (pairs of vertices per trip)
+#define B200SDF_VUNROLL 1 // vertex-loop unroll (pairs of vertices per trip); 1 beats 2 and 4 at 64 registers
 #endif
 #ifndef B200SDF_CURVE_SMEM
 #define B200SDF_CURVE_SMEM 256 // curve records (32 B) kept in shared memory per CTA
