@@ -142,6 +142,41 @@ def test_c2_noto_merge_parity(renderer):
     print(f"C2 Noto merge: {px} px, {px - same} differ by 1 ({100 * same / px:.4f}% identical)")
 
 
+def test_c5_every_fixture_font_on_its_own_parity(renderer):
+    """C5-like: the 21 fixture fonts as 21 separate fonts of ONE FontManager (recurse over a directory without
+    fonts.json, recurse.rs:127-133), so that every glyph of every file is rendered — the merge of C2 hides the code
+    points a later file shares with an earlier one (14 k glyphs here against 6.5 k there).  Compared block by block
+    with the oracle rendering each file alone."""
+    paths = [O.FIRA] + O.noto_paths()
+    m = V.FontManager(parallel=True)
+    names = []
+    for p in paths:
+        name = os.path.basename(p)[:-4]
+        names.append(name)
+        m.add_font_with_name(name, [p])
+    w = V.Writer.new_memory()
+    st = m.render_glyphs(w, renderer)
+    files = {n: d for n, is_dir, d in w.entries() if not is_dir}
+    assert len(files) == 256 * len(paths) and st.blocks == 256 * len(paths)
+    px = same = glyphs = 0
+    for name, p in zip(names, paths):
+        fid = V.name_to_id(name)
+        oset = O.FontSet(name, [p])
+        pop = oset.block_population()
+        glyphs += sum(pop)
+        for b in range(256):
+            got = files[f"{fid}/{b * 256}-{b * 256 + 255}.pbf"]
+            if pop[b] == 0:
+                assert got == oset.render_block(b)
+                continue
+            a, c = check_pbf_block(got, oset.render_block(b), (name, b))
+            px += a
+            same += c
+    assert st.glyphs == glyphs
+    assert same / px >= MIN_IDENTICAL, same / px
+    print(f"C5 every fixture font alone: {glyphs} glyphs, {px} px, {px - same} differ by 1 ({100 * same / px:.4f}% identical)")
+
+
 def test_single_thread_and_sharded_runs_are_identical(renderer):
     """--single-thread (recurse.rs:52-53) and the multi-GPU sharding give byte-identical PBFs: the
     kernel is deterministic (min and integer adds only)."""
