@@ -151,9 +151,14 @@ vgb_manager *vgb_manager_new(int parallel);                                     
 void vgb_manager_free(vgb_manager *m);
 int vgb_manager_add_path(vgb_manager *m, const char *path);                        /* manager.rs:39-53 */
 int vgb_manager_add_font_with_name(vgb_manager *m, const char *name, const char *const *sources, uint32_t n); /* :66-75 */
+/* `scan` of the recurse command (commands/recurse.rs:104-133): font files, fonts.json manifests, recursion */
+int vgb_manager_scan(vgb_manager *m, const char *path);
 int vgb_manager_add_font_bytes_with_name(vgb_manager *m, const char *name, const uint8_t *data, size_t len);
 uint32_t vgb_manager_font_count(const vgb_manager *m);
 const char *vgb_manager_font_id(const vgb_manager *m, uint32_t i);
+/* metadata.name (name id 1) of the font's files, in the order they were added, '\n'-separated; returns the length
+ * needed (excluding NUL) */
+size_t vgb_manager_font_file_names(const vgb_manager *m, const char *font_id, char *buf, size_t cap);
 /* FontWrapper::get_blocks populations (wrapper.rs:53-76): out[256] = glyphs per block */
 int vgb_manager_block_population(const vgb_manager *m, const char *font_id, uint32_t out[256]);
 /* GlyphBlock::render (glyph_block.rs:69-80): malloc'd PBF bytes of one block */

@@ -225,3 +225,55 @@ def test_writer_failure_mid_pipeline_is_an_error_not_a_hang():
     w = V.Writer.new_memory()
     st = m.render_glyphs(w, r)
     assert st.blocks == 256 and st.glyphs == 1686
+
+
+# ---- `scan` of the recurse command (commands/recurse.rs:104-133 and its tests :150-330) -------------------
+def test_scan_testdata_like_the_reference():
+    """recurse.rs test_scan: without a fonts.json every file is added by path, and parse_font_name strips the script
+    word, so all Noto Sans files merge into noto_sans_regular (20 here: JP / KR / SC are not in this checkout)."""
+    m = V.FontManager(parallel=False)
+    m.scan(O.TESTDATA)
+    assert m.font_ids() == ["fira_sans_regular", "noto_sans_regular"]
+    assert sorted(m.font_file_names("noto_sans_regular")) == [
+        "Noto Sans", "Noto Sans Arabic", "Noto Sans Armenian", "Noto Sans Balinese", "Noto Sans Bengali",
+        "Noto Sans Devanagari", "Noto Sans Ethiopic", "Noto Sans Georgian", "Noto Sans Gujarati", "Noto Sans Gurmukhi",
+        "Noto Sans Hebrew", "Noto Sans Javanese", "Noto Sans Kannada", "Noto Sans Khmer", "Noto Sans Lao",
+        "Noto Sans Myanmar", "Noto Sans Oriya", "Noto Sans Sinhala", "Noto Sans Tamil", "Noto Sans Thai"]
+    assert m.font_file_names("fira_sans_regular") == ["Fira Sans"]
+    # entries are visited in byte-wise name order: "Noto Sans - Regular.ttf" first, so it owns the shared code points
+    assert m.font_file_names("noto_sans_regular")[0] == "Noto Sans"
+
+
+def test_scan_fonts_json_manifest_and_non_font_files(tmp_path):
+    import shutil
+
+    # recurse.rs test_run_with_fonts_json_manifest + test_scan_skips_non_font_files
+    d = tmp_path / "input"
+    d.mkdir()
+    shutil.copy(O.FIRA, d / "font.ttf")
+    shutil.copy(O.FIRA, d / "ignored because of the manifest.ttf")
+    (d / "fonts.json").write_text('[{"name": "Custom Merged Sans", "sources": ["font.ttf"], "comment": {"x": [1, 2]}}]')
+    plain = tmp_path / "plain"
+    (plain / "sub").mkdir(parents=True)
+    (plain / "README.txt").write_text("this is not a font")
+    (plain / "UPPER.TTF").write_bytes(open(O.FIRA, "rb").read())  # the extension test is case-sensitive
+    shutil.copy(O.FIRA, plain / "sub" / "deep.otf")
+    m = V.FontManager(parallel=False)
+    m.scan(str(d))
+    m.scan(str(plain))
+    m.scan(str(tmp_path / "does not exist"))
+    assert m.font_ids() == ["custom_merged_sans", "fira_sans_regular"]
+    assert m.font_file_names("custom_merged_sans") == ["Fira Sans"]
+    w = V.Writer.new_file(str(tmp_path / "glyphs"))
+    m.render_glyphs(w, V.Renderer.new_dummy())
+    m.write_index_json(w)
+    m.write_families_json(w)
+    out = tmp_path / "glyphs"
+    assert (out / "custom_merged_sans" / "0-255.pbf").is_file() and (out / "fira_sans_regular" / "65280-65535.pbf").is_file()
+    assert "custom_merged_sans" in (out / "index.json").read_text() and (out / "font_families.json").is_file()
+    # a broken manifest is an error, not a silent skip
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    (bad / "fonts.json").write_text('[{"name": "No sources"}]')
+    with pytest.raises(V.B200Error, match="fonts.json"):
+        V.FontManager(parallel=False).scan(str(bad))

@@ -216,6 +216,8 @@ HOST_SYMBOLS = {
     "vgb_manager_new": (C.c_void_p, [C.c_int]),
     "vgb_manager_free": (None, [C.c_void_p]),
     "vgb_manager_add_path": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "vgb_manager_scan": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "vgb_manager_font_file_names": (C.c_size_t, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     "vgb_manager_add_font_with_name": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32]),
     "vgb_manager_add_font_bytes_with_name": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     "vgb_manager_font_count": (C.c_uint32, [C.c_void_p]),

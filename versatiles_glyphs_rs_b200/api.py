@@ -381,6 +381,18 @@ class FontManager:
         if N.host.vgb_manager_add_path(self._h, path.encode()) != 0:
             raise B200Error(N.host_error())
 
+    def font_file_names(self, font_id: str) -> List[str]:
+        """metadata.name of the files merged into one font, in the order they were added."""
+        n = N.host.vgb_manager_font_file_names(self._h, font_id.encode(), None, 0)
+        buf = C.create_string_buffer(n + 1)
+        N.host.vgb_manager_font_file_names(self._h, font_id.encode(), buf, n + 1)
+        return buf.value.decode().split("\n") if n else []
+
+    def scan(self, path: str):
+        """reference src/commands/recurse.rs:104-133: font files, fonts.json manifests, recursion into directories."""
+        if N.host.vgb_manager_scan(self._h, path.encode()) != 0:
+            raise B200Error(N.host_error())
+
     def add_paths(self, paths: List[str]):
         for p in paths:
             self.add_path(p)

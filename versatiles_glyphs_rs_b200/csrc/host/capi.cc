@@ -398,6 +398,29 @@ int vgb_manager_add_path(vgb_manager *m, const char *path)
 	std::string err;
 	return m->m.add_path(path, &err) ? 0 : fail(err);
 }
+size_t vgb_manager_font_file_names(const vgb_manager *m, const char *font_id, char *buf, size_t cap)
+{
+	std::string out;
+	const auto &fonts = m->m.fonts();
+	const auto it = fonts.find(font_id);
+	if (it != fonts.end())
+		for (const auto &f : it->second.files()) {
+			if (!out.empty())
+				out.push_back('\n');
+			out += f->metadata.name;
+		}
+	if (buf && cap) {
+		const size_t k = std::min(out.size(), cap - 1);
+		std::memcpy(buf, out.data(), k);
+		buf[k] = 0;
+	}
+	return out.size();
+}
+int vgb_manager_scan(vgb_manager *m, const char *path)
+{
+	std::string err;
+	return m->m.scan(path, &err) ? 0 : fail(err);
+}
 int vgb_manager_add_font_with_name(vgb_manager *m, const char *name, const char *const *sources, uint32_t n)
 {
 	std::vector<std::string> v;

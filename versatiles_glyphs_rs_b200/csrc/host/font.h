@@ -179,6 +179,11 @@ class FontManager {
 	bool add_paths(const std::vector<std::string> &paths, std::string *err);
 	// manager.rs:66-75
 	bool add_font_with_name(const std::string &name, const std::vector<std::string> &sources, std::string *err);
+	// commands/recurse.rs:104-133 (`scan`): a .ttf / .otf file is added by path; a directory holding a fonts.json
+	// contributes exactly the merged fonts that file lists ([{"name": ..., "sources": [...]}], sources relative to the
+	// directory); any other directory is searched recursively.  Directory entries are visited in byte-wise name order
+	// (the reference takes fs::read_dir order, i.e. unspecified — the order decides which file owns a shared code point).
+	bool scan(const std::string &path, std::string *err);
 	bool add_font_bytes_with_name(const std::string &name, std::vector<uint8_t> data, std::string *err);
 	const std::map<std::string, FontWrapper> &fonts() const { return fonts_; }
 	// manager.rs:81-125.  Blocks are flattened by host workers, rendered on the renderer's CUDA
