@@ -398,8 +398,9 @@ def main():
     if not args.kernel_only:
         e2e_steps = args.e2e_steps or min(args.steps, 20)
         # the ranks of one box share its host cores: give each rank its share instead of oversubscribing
-        # (the calling thread is the pipeline's CUDA thread, so a rank runs its share minus one as workers)
-        host_threads = max(1, (os.cpu_count() or 1) // world - 1)
+        # (threads = the rank's total, the calling thread included: with >= 14 the caller is the pipeline's dedicated CUDA
+        # thread and the rest record / encode; with fewer every thread works and whoever is free talks to CUDA)
+        host_threads = max(1, (os.cpu_count() or 1) // world)
         for _ in range(max(3, args.warmup)):
             manager.render_glyphs(V.Writer.new_memory(), renderer, threads=host_threads)
         barrier()

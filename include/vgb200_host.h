@@ -165,9 +165,10 @@ int vgb_manager_block_population(const vgb_manager *m, const char *font_id, uint
 int vgb_manager_render_block(const vgb_manager *m, const char *font_id, uint32_t block, const vgb_renderer *r,
                              uint8_t **pbf, uint64_t *len);
 /* FontManager::render_glyphs (manager.rs:81-125).  shard/n_shards select every n-th (font, block)
- * task — the multi-GPU sharding; threads = host workers recording outlines and encoding PBFs
- * (0 = one per core minus one: the CALLING thread is the pipeline's only CUDA thread and works for the
- * whole call; 1 = the reference's --single-thread, everything on the calling thread). */
+ * task — the multi-GPU sharding; threads = host threads the call may use, the calling thread included
+ * (0 = one per core).  With 14 or more the CALLING thread is the pipeline's only CUDA thread and the others record
+ * outlines and encode PBFs; with 2..13 every thread does that and whichever is free submits / polls; 1 = the
+ * reference's --single-thread, everything on the calling thread. */
 int vgb_manager_render_glyphs(const vgb_manager *m, vgb_writer *w, const vgb_renderer *r, uint32_t shard,
                               uint32_t n_shards, int threads, vgb_stats *stats);
 int vgb_manager_write_index_json(const vgb_manager *m, vgb_writer *w);             /* manager.rs:128-131 */

@@ -863,15 +863,22 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		return ka > kb;
 	});
 
-	int workers = 1;
+	// `threads` = host threads this call may use, the calling thread included (0 = one per core).  With fourteen or more,
+	// the calling thread becomes the dedicated submitter (all CUDA traffic, see below) and the rest are workers; with
+	// fewer — several ranks sharing a box's cores — a spinning submitter would burn a large share of them, so every
+	// thread is a worker and whoever is free pumps the queues (one at a time); with one, everything runs inline.
+	static const int kDedicatedMin = [] { // VGB_DEDICATED_MIN: tuning knob
+		const char *e = std::getenv("VGB_DEDICATED_MIN");
+		const int v = e ? std::atoi(e) : 0;
+		return v >= 2 ? v : 14; // measured on C2: cooperative 2.36 / 1.53 ms at 6 / 12 threads against 2.62 / 1.66 dedicated; 16: 1.40 against 1.31
+	}();
+	int total_threads = 1;
 	if (parallel_) {
-		workers = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
-		workers = std::max(1, std::min(workers, 32));
-		// the CUDA pipeline runs one extra thread that owns all CUDA traffic (see below): by default it gets
-		// a core of its own
-		if (renderer.mode() == Renderer::Mode::Cuda && threads <= 0 && workers > 2)
-			workers -= 1;
+		total_threads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+		total_threads = std::max(1, std::min(total_threads, 33));
 	}
+	const bool dedicated = total_threads >= kDedicatedMin;
+	const int workers = dedicated ? total_threads - 1 : total_threads;
 	// One submission carries whole blocks until it holds about `target` glyphs: small jobs keep one
 	// block per submission (parallelism), big jobs amortise the per-submission cost.
 	static const size_t kBatchesPerWorker = [] { // tuning knob (default 4; measured 1..6 on C2)
@@ -924,11 +931,26 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	}();
 	std::atomic<uint64_t> done_seq{0}; // batches handed back so far (workers spin on it before they sleep)
 	std::atomic<int> sleepers{0};      // workers blocked in qcv.wait (the submitter only pays for a wake-up then)
-	const bool inline_pump = workers == 1;
+	std::function<void(bool)> pump;
+	const bool inline_pump = workers == 1;      // single thread: the worker pumps, and may block in the pump
+	const bool coop_pump = !dedicated && !inline_pump; // few threads: whoever is free pumps (never blocking)
+	std::mutex pump_mu;                         // cooperative mode: one pumping thread at a time
+	// pump from a worker (inline / cooperative modes); `idle` = the caller has nothing else to do
+	auto worker_pump = [&](bool idle) {
+		if (inline_pump) {
+			pump(idle);
+			return;
+		}
+		std::unique_lock<std::mutex> pl(pump_mu, std::try_to_lock);
+		if (pl.owns_lock())
+			pump(false);
+		else if (idle)
+			for (int k = 0; k < 64; ++k)
+				cpu_pause();
+	};
 	// never more batches on their way than the renderer has slots for (submit would block the submitter)
 	const size_t max_outstanding =
 	    renderer.mode() == Renderer::Mode::Cuda ? std::max<size_t>(2, renderer.slots()) : (size_t)(2 * workers + 2);
-	std::function<void(bool)> pump;
 
 	auto work = [&](int wid) {
 		RenderStats &st = per_worker[(size_t)wid];
@@ -997,6 +1019,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			if (failed.load())
 				break;
 			// 1. finished batches first: encoding frees the batch and gets files out early
+			if (coop_pump)
+				worker_pump(false);
 			Flight *done = nullptr;
 			{
 				std::lock_guard<std::mutex> g(qm);
@@ -1028,8 +1052,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				{
 					std::unique_lock<std::mutex> lk(qm);
 					if (outstanding >= max_outstanding) { // back-pressure: wait for a completion
-						if (inline_pump)
-							lk.unlock(), pump(true);
+						if (inline_pump || coop_pump)
+							lk.unlock(), worker_pump(true);
 						else {
 							sleepers.fetch_add(1, std::memory_order_acq_rel);
 							qcv.wait_for(lk, std::chrono::milliseconds(kWaitMs),
@@ -1120,8 +1144,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					std::lock_guard<std::mutex> g(qm);
 					submit_q.push_back(cur.release());
 				}
-				if (inline_pump)
-					pump(false);
+				if (inline_pump || coop_pump)
+					worker_pump(false);
 				continue;
 			}
 			// 3. nothing left to record: help until every batch has come back
@@ -1132,8 +1156,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				if (!done_q.empty())
 					continue;
 				const uint64_t t0 = now_ns();
-				if (inline_pump) {
-					lk.unlock(), pump(true);
+				if (inline_pump || coop_pump) {
+					lk.unlock(), worker_pump(true);
 				} else {
 					// spin briefly on the hand-back counter before sleeping: at the end of a call the next batch is
 					// usually tens of microseconds away, less than a sleep / wake-up round trip
@@ -1281,6 +1305,9 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 
 	if (inline_pump) {
 		work(0);
+	} else if (coop_pump) {
+		// the calling thread is worker 0
+		WorkerPool::instance().run(workers - 1, [&](int id) { work(id + 1); }, [&] { work(0); });
 	} else {
 		WorkerPool::instance().run(
 		    workers,
@@ -1292,7 +1319,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		    submitter); // the calling thread is the submitter
 	}
 	// error paths leave batches behind: nothing is in flight any more (the submitter drained), free them
-	if (inline_pump)
+	if (inline_pump || coop_pump)
 		while (!inflight.empty()) {
 			renderer.wait_batch(inflight.front()->ticket, nullptr);
 			done_q.push_back(inflight.front());
