@@ -403,6 +403,10 @@ def main():
         host_threads = max(1, (os.cpu_count() or 1) // world)
         for _ in range(max(3, args.warmup)):
             manager.render_glyphs(V.Writer.new_memory(), renderer, threads=host_threads)
+        import gc
+
+        gc.collect()
+        gc.disable()  # a generational collection of the interpreter's heap (torch, numpy, ...) is a 50 ms pause between steps
         barrier()
         t0 = time.perf_counter()
         step_ms = []
@@ -411,6 +415,7 @@ def main():
             st = manager.render_glyphs(V.Writer.new_memory(), renderer, threads=host_threads)
             step_ms.append(1e3 * (time.perf_counter() - ts))
         t_loop = time.perf_counter() - t0
+        gc.enable()
         tb = time.perf_counter()
         barrier()
         print(f"[bench] rank {rank}: e2e loop {1e3 * t_loop:.1f} ms, closing barrier {1e3 * (time.perf_counter() - tb):.1f} ms, "
