@@ -936,15 +936,27 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	const bool coop_pump = !dedicated && !inline_pump; // few threads: whoever is free pumps (never blocking)
 	std::mutex pump_mu;                         // cooperative mode: one pumping thread at a time
 	// pump from a worker (inline / cooperative modes); `idle` = the caller has nothing else to do
-	auto worker_pump = [&](bool idle) {
+	// (idle_spins: the caller's count of consecutive idle calls.  Idle workers must not spin forever: with every core
+	// busy spinning, the one thread that holds pump_mu or qm can be pre-empted for a whole scheduler slice — a 70 ms
+	// step was measured — so they yield after a while and then nap.)
+	auto worker_pump = [&](bool idle, unsigned *idle_spins) {
 		if (inline_pump) {
 			pump(idle);
 			return;
 		}
-		std::unique_lock<std::mutex> pl(pump_mu, std::try_to_lock);
-		if (pl.owns_lock())
-			pump(false);
-		else if (idle)
+		{
+			std::unique_lock<std::mutex> pl(pump_mu, std::try_to_lock);
+			if (pl.owns_lock())
+				pump(false);
+		}
+		if (!idle)
+			return;
+		const unsigned n = idle_spins ? ++*idle_spins : 0;
+		if (n > 2000)
+			std::this_thread::sleep_for(std::chrono::microseconds(50));
+		else if (n > 200)
+			std::this_thread::yield();
+		else
 			for (int k = 0; k < 64; ++k)
 				cpu_pause();
 	};
@@ -1014,13 +1026,14 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		//   worker --submit_q--> submitter --(GPU)--> submitter --done_q--> any worker (encode, write)
 		// With a single worker (the reference's --single-thread) the worker pumps the queues itself.
 		unsigned n_batches = 0;
+		unsigned idle_spins = 0;
 		bool more = true;
 		for (;;) {
 			if (failed.load())
 				break;
 			// 1. finished batches first: encoding frees the batch and gets files out early
 			if (coop_pump)
-				worker_pump(false);
+				worker_pump(false, nullptr);
 			Flight *done = nullptr;
 			{
 				std::lock_guard<std::mutex> g(qm);
@@ -1030,6 +1043,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				}
 			}
 			if (done) {
+				idle_spins = 0;
 				mark('e');
 				bool ok = true;
 				for (const Part &p : done->parts)
@@ -1053,7 +1067,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					std::unique_lock<std::mutex> lk(qm);
 					if (outstanding >= max_outstanding) { // back-pressure: wait for a completion
 						if (inline_pump || coop_pump)
-							lk.unlock(), worker_pump(true);
+							lk.unlock(), worker_pump(true, &idle_spins);
 						else {
 							sleepers.fetch_add(1, std::memory_order_acq_rel);
 							qcv.wait_for(lk, std::chrono::milliseconds(kWaitMs),
@@ -1145,7 +1159,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					submit_q.push_back(cur.release());
 				}
 				if (inline_pump || coop_pump)
-					worker_pump(false);
+					worker_pump(false, nullptr);
 				continue;
 			}
 			// 3. nothing left to record: help until every batch has come back
@@ -1157,7 +1171,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					continue;
 				const uint64_t t0 = now_ns();
 				if (inline_pump || coop_pump) {
-					lk.unlock(), worker_pump(true);
+					lk.unlock(), worker_pump(true, &idle_spins);
 				} else {
 					// spin briefly on the hand-back counter before sleeping: at the end of a call the next batch is
 					// usually tens of microseconds away, less than a sleep / wake-up round trip
