@@ -213,6 +213,8 @@ def main():
     import numpy as np
     import torch
 
+    torch.set_num_threads(1)  # torch is plumbing here: no intra-op pool competing with the pipeline's workers for cores
+
     import versatiles_glyphs_rs_b200 as V
 
     rank = int(os.environ.get("RANK", "0"))
