@@ -272,6 +272,11 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	size_t outstanding = 0; // batches submitted (or queued for it) and not yet encoded
 	int workers_done = 0;
 	std::atomic<uint64_t> submit_ns{0};
+	static const int kSpinBudget = [] { // pause iterations an idle worker spins before it sleeps (VGB_SPIN: tuning knob)
+		const char *e = std::getenv("VGB_SPIN");
+		const int v = e ? std::atoi(e) : 0;
+		return v > 0 ? v : 4000;
+	}();
 	static const int kWaitMs = [] { // safety-net timeout of the workers' condition waits (diagnostics knob)
 		const char *e = std::getenv("VGB_WAIT_MS");
 		const int v = e ? std::atoi(e) : 0;
@@ -526,7 +531,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					const uint64_t seen = done_seq.load(std::memory_order_acquire);
 					lk.unlock();
 					bool changed = false;
-					for (int spin = 0; spin < 4000 && !changed; ++spin) {
+					for (int spin = 0; spin < kSpinBudget && !changed; ++spin) {
 						cpu_pause();
 						changed = done_seq.load(std::memory_order_acquire) != seen || failed.load(std::memory_order_relaxed);
 					}
