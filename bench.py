@@ -159,7 +159,7 @@ def run_reference(args):
     import oracle_lib as O
 
     label, font_name, blobs = workload_fonts(args.workload)
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0)) or 1
     budget = max(0.05, 150.0 / max(1, args.steps + args.warmup))
     fs, stride = cpu_sample(font_name, blobs, budget, threads)
     glyphs = 0
@@ -402,7 +402,7 @@ def main():
         # the ranks of one box share its host cores: give each rank its share instead of oversubscribing
         # (threads = the rank's total, the calling thread included: with >= 14 the caller is the pipeline's dedicated CUDA
         # thread and the rest record / encode; with fewer every thread works and whoever is free talks to CUDA)
-        host_threads = max(1, (os.cpu_count() or 1) // world)
+        host_threads = max(1, len(os.sched_getaffinity(0)) // world)
         for _ in range(max(3, args.warmup)):
             manager.render_glyphs(V.Writer.new_memory(), renderer, threads=host_threads)
         import gc
@@ -441,7 +441,7 @@ def main():
         if rank == 0 and world == 1:
             import oracle_lib as O
 
-            threads = os.cpu_count() or 1
+            threads = len(os.sched_getaffinity(0)) or 1
             fs, stride = cpu_sample(font_name, blobs, args.cpu_seconds, threads)
             t0 = time.perf_counter()
             cst = fs.render_all(O.MODE_PRECISE, threads=threads, stride=stride)

@@ -27,6 +27,18 @@ inline void cpu_pause()
 	std::this_thread::yield();
 #endif
 }
+// CPUs this process may run on (a cpuset / taskset can be narrower than the machine)
+inline int usable_cpus()
+{
+	cpu_set_t set;
+	CPU_ZERO(&set);
+	if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+		const int n = CPU_COUNT(&set);
+		if (n > 0)
+			return n;
+	}
+	return (int)std::max(1u, std::thread::hardware_concurrency());
+}
 inline uint64_t now_ns()
 {
 	return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
@@ -222,7 +234,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	}();
 	int total_threads = 1;
 	if (parallel_) {
-		total_threads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+		total_threads = threads > 0 ? threads : usable_cpus();
 		total_threads = std::max(1, std::min(total_threads, 33));
 	}
 	const bool dedicated = total_threads >= kDedicatedMin;
