@@ -94,6 +94,9 @@ typedef struct {
 	span data;
 } cmap_sub;
 
+typedef struct vgo_cff vgo_cff;
+static vgo_cff *cff_parse(span t);
+
 struct vgo_font {
 	uint8_t *data;
 	size_t len;
@@ -104,6 +107,7 @@ struct vgo_font {
 	span hmtx, loca, glyf, cmap;
 	cmap_sub *subs;
 	uint32_t n_subs;
+	struct vgo_cff *cff; /* parsed `CFF ` table, NULL if absent or rejected */
 };
 
 static inline uint16_t rd16(const uint8_t *p) { return (uint16_t)((p[0] << 8) | p[1]); }
@@ -169,6 +173,9 @@ vgo_font *vgo_font_parse(const uint8_t *data, size_t len)
 		f->loca.len = 0;
 	if (!find_table(f, "glyf", &f->glyf))
 		f->glyf.len = 0;
+	span cff;
+	if (find_table(f, "CFF ", &cff))
+		f->cff = cff_parse(cff);
 	/* cmap subtable records, in table order */
 	if (f->cmap.len >= 4) {
 		uint16_t n = rd16(f->cmap.p + 2);
@@ -196,6 +203,7 @@ void vgo_font_free(vgo_font *f)
 	if (!f)
 		return;
 	free(f->subs);
+	free(f->cff);
 	free(f->data);
 	free(f);
 }
@@ -813,13 +821,645 @@ static void outline_impl(const vgo_font *f, span g, int depth, xform t, ring_bui
 	}
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* CFF 1 outlines → callbacks (restated ttf-parser 0.25.1 cff1.rs / charstring.rs / dict.rs /   */
+/* index.rs; reached from renderer.rs:110 when the face has no glyf + loca).  Parity unpinned:  */
+/* no fixture of the reference is CFF; tests use synthetic known-answer fonts.  `seac` is not   */
+/* restated (the glyph ends with an error before any callback).                                 */
+/* ------------------------------------------------------------------------------------------ */
+static void rb_curve_to(ring_builder *b, float x1, float y1, float x2, float y2, float x, float y)
+{
+	if (b->ring.n == 0) /* ring_builder.rs:99 */
+		return;
+	double s[2] = {b->ring.v[b->ring.n - 2], b->ring.v[b->ring.n - 1]};
+	double c1[2] = {(double)x1, (double)y1}, c2[2] = {(double)x2, (double)y2}, e[2] = {(double)x, (double)y};
+	flatten_cubic(&b->ring, s, c1, c2, e, PRECISION);
+}
+
+typedef struct {
+	uint32_t count;
+	uint32_t osz;
+	const uint8_t *offs;
+	span data;
+} cff_index;
+
+static uint32_t cff_off(const uint8_t *p, uint32_t osz)
+{
+	uint32_t v = 0;
+	while (osz--)
+		v = (v << 8) | *p++;
+	return v;
+}
+
+/* parse_index at *pos of s; advances *pos; 0 = None */
+static int cff_read_index(span s, size_t *pos, cff_index *ix)
+{
+	memset(ix, 0, sizeof(*ix));
+	if (*pos > s.len || s.len - *pos < 2)
+		return 0;
+	uint32_t count = rd16(s.p + *pos);
+	*pos += 2;
+	if (count == 0)
+		return 1;
+	if (s.len - *pos < 1)
+		return 0;
+	uint32_t osz = s.p[(*pos)++];
+	if (osz < 1 || osz > 4)
+		return 0;
+	size_t olen = ((size_t)count + 1) * osz;
+	if (s.len - *pos < olen)
+		return 0;
+	const uint8_t *offs = s.p + *pos;
+	*pos += olen;
+	uint32_t last = cff_off(offs + (size_t)count * osz, osz);
+	if (last == 0)
+		return 1; /* empty index */
+	if (s.len - *pos < (size_t)last - 1)
+		return 0;
+	ix->count = count, ix->osz = osz, ix->offs = offs;
+	ix->data.p = s.p + *pos, ix->data.len = (size_t)last - 1;
+	*pos += (size_t)last - 1;
+	return 1;
+}
+
+static int cff_index_get(const cff_index *ix, uint32_t i, span *out)
+{
+	if (i >= ix->count)
+		return 0;
+	uint32_t a = cff_off(ix->offs + (size_t)i * ix->osz, ix->osz), b = cff_off(ix->offs + ((size_t)i + 1) * ix->osz, ix->osz);
+	if (a == 0 || b == 0 || a > b || (size_t)b - 1 > ix->data.len)
+		return 0;
+	out->p = ix->data.p + (a - 1), out->len = b - a;
+	return 1;
+}
+
+/* DICT walker: returns the next operator (two-byte: 1200 + b) or -1; operands in ops[0..*n) (at most 48 kept) */
+static int cff_dict_next(span d, size_t *pos, double *ops, int *n)
+{
+	*n = 0;
+	while (*pos < d.len) {
+		uint8_t b = d.p[(*pos)++];
+		if (b <= 27 || b == 31 || b == 255) {
+			if (b != 12)
+				return b;
+			if (*pos >= d.len)
+				return -1;
+			return 1200 + d.p[(*pos)++];
+		}
+		double v = 0.0;
+		if (b == 28) {
+			if (d.len - *pos < 2)
+				return -1;
+			v = rds16(d.p + *pos), *pos += 2;
+		} else if (b == 29) {
+			if (d.len - *pos < 4)
+				return -1;
+			v = (int32_t)rd32(d.p + *pos), *pos += 4;
+		} else if (b == 30) { /* packed-BCD real */
+			char txt[80];
+			int k = 0, end = 0;
+			while (!end) {
+				if (*pos >= d.len)
+					return -1;
+				uint8_t q = d.p[(*pos)++];
+				for (int h = 1; h >= 0 && !end; h--) {
+					int nib = (q >> (4 * h)) & 15;
+					if (nib == 15) {
+						end = 1;
+					} else if (k > 70 || nib == 13) {
+						return -1;
+					} else if (nib < 10) {
+						txt[k++] = (char)('0' + nib);
+					} else if (nib == 10) {
+						txt[k++] = '.';
+					} else if (nib == 14) {
+						txt[k++] = '-';
+					} else {
+						txt[k++] = 'e';
+						if (nib == 12)
+							txt[k++] = '-';
+					}
+				}
+			}
+			txt[k] = 0;
+			char *stop;
+			v = strtod(txt, &stop);
+			if (k == 0 || *stop)
+				return -1;
+		} else if (b <= 246) {
+			v = (int)b - 139;
+		} else {
+			if (*pos >= d.len)
+				return -1;
+			int w = d.p[(*pos)++];
+			v = b <= 250 ? (b - 247) * 256 + w + 108 : -(b - 251) * 256 - w - 108;
+		}
+		if (*n < 48)
+			ops[(*n)++] = v;
+	}
+	return -1;
+}
+
+static int cff_as_offset(const double *ops, int n, size_t *out)
+{
+	if (n != 1 || (int32_t)ops[0] < 0)
+		return 0;
+	*out = (size_t)(int32_t)ops[0];
+	return 1;
+}
+static int cff_as_range(const double *ops, int n, size_t *start, size_t *len)
+{
+	if (n != 2 || (int32_t)ops[0] < 0 || (int32_t)ops[1] < 0)
+		return 0;
+	*len = (size_t)(int32_t)ops[0], *start = (size_t)(int32_t)ops[1];
+	return 1;
+}
+
+struct vgo_cff {
+	span table;
+	cff_index gsubrs, charstrings, lsubrs, fdarray;
+	int cid, fdsel_format;
+	span fdsel;
+};
+
+/* Subrs INDEX of the Private DICT at [start, start + len) of the table; 1 = found and parsed, 0 = none, -1 = malformed */
+static int cff_private_subrs(span table, size_t start, size_t len, cff_index *out)
+{
+	if (start > table.len || table.len - start < len)
+		return -1;
+	span priv = {table.p + start, len};
+	size_t pos = 0, off = 0;
+	double ops[48];
+	int n, op, have = 0;
+	while ((op = cff_dict_next(priv, &pos, ops, &n)) >= 0)
+		if (op == 19)
+			have = cff_as_offset(ops, n, &off);
+	if (!have)
+		return 0;
+	size_t at = start + off;
+	if (at > table.len)
+		return -1;
+	return cff_read_index(table, &at, out) ? 1 : -1;
+}
+
+static vgo_cff *cff_parse(span t)
+{
+	if (t.len < 4 || t.p[0] != 1)
+		return NULL;
+	size_t pos = t.p[2] > 4 ? t.p[2] : 4;
+	cff_index names, top, strings;
+	vgo_cff c;
+	memset(&c, 0, sizeof(c));
+	c.table = t;
+	if (!cff_read_index(t, &pos, &names) || !cff_read_index(t, &pos, &top))
+		return NULL;
+	span td;
+	if (!cff_index_get(&top, 0, &td))
+		return NULL;
+	size_t charset = 0, encoding = 0, cs = 0, pstart = 0, plen = 0, fda = 0, fds = 0, dpos = 0;
+	int has_charset = 0, has_encoding = 0, has_priv = 0, ros = 0, has_fda = 0, has_fds = 0, n, op;
+	double ops[48];
+	while ((op = cff_dict_next(td, &dpos, ops, &n)) >= 0) {
+		if (op == 15)
+			has_charset = cff_as_offset(ops, n, &charset);
+		else if (op == 16)
+			has_encoding = cff_as_offset(ops, n, &encoding);
+		else if (op == 17) {
+			if (!cff_as_offset(ops, n, &cs))
+				return NULL;
+		} else if (op == 18)
+			has_priv = cff_as_range(ops, n, &pstart, &plen);
+		else if (op == 1230)
+			ros = 1;
+		else if (op == 1236)
+			has_fda = cff_as_offset(ops, n, &fda);
+		else if (op == 1237)
+			has_fds = cff_as_offset(ops, n, &fds);
+	}
+	if (cs == 0)
+		return NULL;
+	if (!cff_read_index(t, &pos, &strings) || !cff_read_index(t, &pos, &c.gsubrs))
+		return NULL;
+	if (cs > t.len || !cff_read_index(t, &cs, &c.charstrings) || c.charstrings.count == 0)
+		return NULL;
+	uint32_t ng = c.charstrings.count;
+	if (has_charset && charset > 2) { /* parse_charset must succeed */
+		if (charset >= t.len)
+			return NULL;
+		size_t p = charset + 1;
+		uint8_t fmt = t.p[charset];
+		if (fmt == 0) {
+			if (t.len - p < ((size_t)ng - 1) * 2)
+				return NULL;
+		} else if (fmt == 1 || fmt == 2) {
+			uint32_t left = ng - 1;
+			size_t rec = fmt == 1 ? 3 : 4;
+			while (left > 0) {
+				if (t.len - p < rec)
+					return NULL;
+				uint32_t cnt = (fmt == 1 ? t.p[p + 2] : rd16(t.p + p + 2)) + 1u;
+				p += rec;
+				if (cnt > left)
+					return NULL;
+				left -= cnt;
+			}
+		} else
+			return NULL;
+	}
+	if (ros) {
+		if (!has_charset || !has_fda || !has_fds || charset == 0 || fda == 0 || fds == 0)
+			return NULL;
+		c.cid = 1;
+		if (fda > t.len || !cff_read_index(t, &fda, &c.fdarray))
+			return NULL;
+		if (fds >= t.len)
+			return NULL;
+		c.fdsel_format = t.p[fds];
+		c.fdsel.p = t.p + fds + 1, c.fdsel.len = t.len - fds - 1;
+		if (c.fdsel_format == 0) {
+			if (c.fdsel.len < ng)
+				return NULL;
+			c.fdsel.len = ng;
+		} else if (c.fdsel_format != 3)
+			return NULL;
+	} else {
+		if (has_encoding && encoding > 1) { /* parse_encoding must succeed */
+			size_t p = encoding;
+			if (t.len < 2 || p > t.len - 2)
+				return NULL;
+			uint8_t fmt = t.p[p], cnt = t.p[p + 1];
+			p += 2;
+			size_t body = (fmt & 0x7f) == 0 ? cnt : (fmt & 0x7f) == 1 ? (size_t)cnt * 2 : (size_t)-1;
+			if (body == (size_t)-1 || t.len - p < body)
+				return NULL;
+			p += body;
+			if (fmt & 0x80) {
+				if (p >= t.len || t.len - p - 1 < (size_t)t.p[p] * 3)
+					return NULL;
+			}
+		}
+		if (has_priv && cff_private_subrs(t, pstart, plen, &c.lsubrs) < 0)
+			return NULL;
+	}
+	vgo_cff *out = (vgo_cff *)malloc(sizeof(c));
+	*out = c;
+	return out;
+}
+
+/* local subroutines of a CID glyph: FDSelect → FDArray[fd] → Private → Subrs */
+static int cff_cid_lsubrs(const vgo_cff *c, uint32_t gid, cff_index *out)
+{
+	uint32_t fd;
+	if (c->fdsel_format == 0) {
+		if (gid >= c->fdsel.len)
+			return 0;
+		fd = c->fdsel.p[gid];
+	} else {
+		span s = c->fdsel;
+		if (s.len < 2)
+			return 0;
+		uint32_t nr = rd16(s.p);
+		if (nr == 0 || nr == 0xffff)
+			return 0;
+		/* nr records of (first u16, fd u8) followed by a sentinel u16 */
+		size_t p = 2;
+		int hit = 0;
+		fd = 0;
+		for (uint32_t i = 0; i < nr; i++, p += 3) {
+			if (s.len - p < 5)
+				return 0;
+			uint32_t first = rd16(s.p + p), next = rd16(s.p + p + 3);
+			if (gid >= first && gid < next) {
+				fd = s.p[p + 2];
+				hit = 1;
+				break;
+			}
+		}
+		if (!hit)
+			return 0;
+	}
+	span fdict;
+	if (!cff_index_get(&c->fdarray, fd, &fdict))
+		return 0;
+	size_t pos = 0, start = 0, len = 0;
+	double ops[48];
+	int n, op, have = 0;
+	while ((op = cff_dict_next(fdict, &pos, ops, &n)) >= 0)
+		if (op == 18) {
+			have = cff_as_range(ops, n, &start, &len);
+			break;
+		}
+	if (!have)
+		return 0;
+	return cff_private_subrs(c->table, start, len, out) == 1;
+}
+
+typedef struct {
+	const vgo_cff *c;
+	ring_builder *rb;
+	uint32_t gid;
+	float st[48];
+	int n;
+	float x, y;
+	int moved, first_move, width_seen, endchar, stems;
+	int lsubrs_ready;
+	cff_index lsubrs;
+} cs_state;
+
+static void cs_curve(cs_state *s, float x1, float y1, float x2, float y2, float x, float y)
+{
+	s->x = x, s->y = y;
+	rb_curve_to(s->rb, x1, y1, x2, y2, x, y);
+}
+static void cs_rrcurve(cs_state *s, const float *a)
+{
+	float x1 = s->x + a[0], y1 = s->y + a[1], x2 = x1 + a[2], y2 = y1 + a[3];
+	cs_curve(s, x1, y1, x2, y2, x2 + a[4], y2 + a[5]);
+}
+static void cs_rline(cs_state *s, float dx, float dy)
+{
+	s->x += dx, s->y += dy;
+	rb_line_to(s->rb, s->x, s->y);
+}
+
+/* 1 = keep going / finished normally, 0 = error (CFFError) */
+static int cs_exec(cs_state *s, span code, int depth)
+{
+	size_t pc = 0;
+	while (pc < code.len) {
+		uint8_t op = code.p[pc++];
+		float *a = s->st;
+		int n = s->n;
+		if (op >= 32 || op == 28) { /* operands */
+			float v;
+			if (op == 28) {
+				if (code.len - pc < 2)
+					return 0;
+				v = (float)rds16(code.p + pc), pc += 2;
+			} else if (op == 255) {
+				if (code.len - pc < 4)
+					return 0;
+				v = (float)(int32_t)rd32(code.p + pc) / 65536.0f, pc += 4;
+			} else if (op <= 246) {
+				v = (float)((int)op - 139);
+			} else {
+				if (pc >= code.len)
+					return 0;
+				int w = code.p[pc++];
+				v = (float)(op <= 250 ? (op - 247) * 256 + w + 108 : -(op - 251) * 256 - w - 108);
+			}
+			if (s->n == 48)
+				return 0;
+			s->st[s->n++] = v;
+			continue;
+		}
+		switch (op) {
+		case 1: case 3: case 18: case 23: /* h/vstem(hm) */
+			if ((n & 1) && !s->width_seen)
+				s->width_seen = 1, n--;
+			s->stems += n >> 1;
+			s->n = 0;
+			break;
+		case 19: case 20: /* hintmask, cntrmask */
+			s->n = 0;
+			if (n & 1)
+				s->width_seen = 1, n--;
+			s->stems += n >> 1;
+			if (code.len - pc < (size_t)((s->stems + 7) >> 3))
+				return 0;
+			pc += (size_t)((s->stems + 7) >> 3);
+			break;
+		case 21: case 22: case 4: { /* rmoveto, hmoveto, vmoveto */
+			int want = op == 21 ? 2 : 1, i = 0;
+			if (n == want + 1 && !s->width_seen)
+				s->width_seen = 1, i = 1;
+			if (n != want + i)
+				return 0;
+			if (s->first_move)
+				s->first_move = 0;
+			else
+				rb_close(s->rb);
+			s->moved = 1;
+			if (op == 21)
+				s->x += a[i], s->y += a[i + 1];
+			else if (op == 22)
+				s->x += a[i];
+			else
+				s->y += a[i];
+			rb_move_to(s->rb, s->x, s->y);
+			s->n = 0;
+			break;
+		}
+		case 5: /* rlineto */
+			if (!s->moved || (n & 1))
+				return 0;
+			for (int i = 0; i < n; i += 2)
+				cs_rline(s, a[i], a[i + 1]);
+			s->n = 0;
+			break;
+		case 6: case 7: /* hlineto, vlineto: alternate */
+			if (!s->moved || n == 0)
+				return 0;
+			for (int i = 0; i < n; i++) {
+				if (((i & 1) == 0) == (op == 6))
+					cs_rline(s, a[i], 0.0f);
+				else
+					cs_rline(s, 0.0f, a[i]);
+			}
+			s->n = 0;
+			break;
+		case 8: /* rrcurveto */
+			if (!s->moved || n % 6)
+				return 0;
+			for (int i = 0; i < n; i += 6)
+				cs_rrcurve(s, a + i);
+			s->n = 0;
+			break;
+		case 24: { /* rcurveline */
+			if (!s->moved || n < 8 || (n - 2) % 6)
+				return 0;
+			int i = 0;
+			for (; i < n - 2; i += 6)
+				cs_rrcurve(s, a + i);
+			cs_rline(s, a[i], a[i + 1]);
+			s->n = 0;
+			break;
+		}
+		case 25: { /* rlinecurve */
+			if (!s->moved || n < 8 || ((n - 6) & 1))
+				return 0;
+			int i = 0;
+			for (; i < n - 6; i += 2)
+				cs_rline(s, a[i], a[i + 1]);
+			cs_rrcurve(s, a + i);
+			s->n = 0;
+			break;
+		}
+		case 26: case 27: { /* vvcurveto, hhcurveto */
+			if (!s->moved)
+				return 0;
+			int i = 0;
+			if (n & 1) {
+				if (op == 27)
+					s->y += a[0];
+				else
+					s->x += a[0];
+				i = 1;
+			}
+			if ((n - i) % 4)
+				return 0;
+			for (; i < n; i += 4) {
+				if (op == 27) {
+					float x1 = s->x + a[i], y1 = s->y, x2 = x1 + a[i + 1], y2 = y1 + a[i + 2];
+					cs_curve(s, x1, y1, x2, y2, x2 + a[i + 3], y2);
+				} else {
+					float x1 = s->x, y1 = s->y + a[i], x2 = x1 + a[i + 1], y2 = y1 + a[i + 2];
+					cs_curve(s, x1, y1, x2, y2, x2, y2 + a[i + 3]);
+				}
+			}
+			s->n = 0;
+			break;
+		}
+		case 30: case 31: { /* vhcurveto, hvcurveto */
+			if (!s->moved || n < 4)
+				return 0;
+			int i = 0, horiz = op == 31;
+			while (i < n) {
+				int rest = n - i;
+				if (rest < 4)
+					return 0;
+				float extra = rest == 5 ? a[i + 4] : 0.0f;
+				if (horiz) {
+					float x1 = s->x + a[i], y1 = s->y, x2 = x1 + a[i + 1], y2 = y1 + a[i + 2];
+					float ex = rest == 5 ? x2 + extra : x2;
+					cs_curve(s, x1, y1, x2, y2, ex, y2 + a[i + 3]);
+				} else {
+					float x1 = s->x, y1 = s->y + a[i], x2 = x1 + a[i + 1], y2 = y1 + a[i + 2];
+					float ey = rest == 5 ? y2 + extra : y2;
+					cs_curve(s, x1, y1, x2, y2, x2 + a[i + 3], ey);
+				}
+				i += rest == 5 ? 5 : 4;
+				horiz = !horiz;
+			}
+			s->n = 0;
+			break;
+		}
+		case 12: { /* flex family */
+			if (pc >= code.len)
+				return 0;
+			uint8_t op2 = code.p[pc++];
+			if (op2 < 34 || op2 > 37 || !s->moved)
+				return 0;
+			float sx = s->x, sy = s->y;
+			if (op2 == 35) {
+				if (n != 13)
+					return 0;
+				cs_rrcurve(s, a);
+				cs_rrcurve(s, a + 6);
+			} else if (op2 == 34) {
+				if (n != 7)
+					return 0;
+				float x1 = sx + a[0], x2 = x1 + a[1], y2 = sy + a[2], x3 = x2 + a[3];
+				cs_curve(s, x1, sy, x2, y2, x3, y2);
+				float x4 = x3 + a[4], x5 = x4 + a[5];
+				cs_curve(s, x4, y2, x5, sy, x5 + a[6], sy);
+			} else if (op2 == 36) {
+				if (n != 9)
+					return 0;
+				float x1 = sx + a[0], y1 = sy + a[1], x2 = x1 + a[2], y2 = y1 + a[3], x3 = x2 + a[4];
+				cs_curve(s, x1, y1, x2, y2, x3, y2);
+				float x4 = x3 + a[5], x5 = x4 + a[6], y5 = y2 + a[7];
+				cs_curve(s, x4, y2, x5, y5, x5 + a[8], sy);
+			} else {
+				if (n != 11)
+					return 0;
+				float px[6], py[6];
+				px[0] = sx, py[0] = sy;
+				for (int k = 1; k <= 5; k++)
+					px[k] = px[k - 1] + a[2 * k - 2], py[k] = py[k - 1] + a[2 * k - 1];
+				float ex = sx, ey = sy;
+				if (fabsf(px[5] - sx) > fabsf(py[5] - sy))
+					ex = px[5] + a[10];
+				else
+					ey = py[5] + a[10];
+				cs_curve(s, px[1], py[1], px[2], py[2], px[3], py[3]);
+				cs_curve(s, px[4], py[4], px[5], py[5], ex, ey);
+			}
+			s->n = 0;
+			break;
+		}
+		case 10: case 29: { /* callsubr, callgsubr */
+			if (n == 0 || depth == 10)
+				return 0;
+			const cff_index *ix = &s->c->gsubrs;
+			if (op == 10) {
+				if (!s->lsubrs_ready) {
+					if (!s->c->cid)
+						s->lsubrs = s->c->lsubrs, s->lsubrs_ready = 1;
+					else if (cff_cid_lsubrs(s->c, s->gid, &s->lsubrs))
+						s->lsubrs_ready = 1;
+					else
+						return 0;
+				}
+				ix = &s->lsubrs;
+			}
+			int bias = ix->count < 1240 ? 107 : ix->count < 33900 ? 1131 : 32768;
+			double v = (double)s->st[--s->n];
+			if (!(v > -2147483649.0 && v < 2147483648.0))
+				return 0;
+			int64_t k = (int64_t)(int32_t)v + bias;
+			span body;
+			if (k < 0 || !cff_index_get(ix, (uint32_t)k, &body))
+				return 0;
+			if (!cs_exec(s, body, depth + 1))
+				return 0;
+			if (s->endchar)
+				return pc >= code.len;
+			break;
+		}
+		case 11: /* return */
+			return 1;
+		case 14: /* endchar */
+			if (n == 4 || (n == 5 && !s->width_seen))
+				return 0; /* seac */
+			if (n == 1 && !s->width_seen)
+				s->width_seen = 1, s->n = 0;
+			if (!s->first_move) {
+				s->first_move = 1;
+				rb_close(s->rb);
+			}
+			if (pc < code.len)
+				return 0;
+			s->endchar = 1;
+			return 1;
+		default: /* 0, 2, 9, 13, 15, 16, 17: reserved */
+			return 0;
+		}
+	}
+	return 1;
+}
+
+static void cff_outline(const vgo_cff *c, uint32_t gid, ring_builder *rb)
+{
+	span code;
+	if (!cff_index_get(&c->charstrings, gid, &code))
+		return;
+	cs_state s;
+	memset(&s, 0, sizeof(s));
+	s.c = c, s.rb = rb, s.gid = gid, s.first_move = 1;
+	cs_exec(&s, code, 0); /* the reference ignores outline_glyph's result: what was emitted stays */
+}
+
 /* face.outline_glyph(gid, &mut RingBuilder) + into_rings — src/render/renderer.rs:109-111 */
 int vgo_outline_rings(const vgo_font *f, uint32_t gid, vgo_rings *out)
 {
 	ring_builder rb;
 	memset(&rb, 0, sizeof(rb));
 	span g;
-	if (glyph_span(f, gid, &g))
+	if (f->glyf.len == 0 || f->loca.len == 0) { /* ttf-parser: glyf first, then cff */
+		if (f->cff)
+			cff_outline(f->cff, gid, &rb);
+	} else if (glyph_span(f, gid, &g))
 		outline_impl(f, g, 0, XF_ID, &rb);
 	rb_save_ring(&rb); /* into_rings — ring_builder.rs:26-29 */
 	free(rb.ring.v);

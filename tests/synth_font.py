@@ -164,3 +164,409 @@ def full_bmp_font(seed=0xB200, stride=1):
     stride > 1 keeps every stride-th code point (smaller fixture for tests)."""
     cps = [c for c in range(0, 0xFFFF, stride) if not 0xD800 <= c <= 0xDFFF]
     return build_font(cps, lambda cp: 2 + ((cp * 2654435761) >> 7) % 14, seed=seed, family="Synth Full")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Synthetic CFF (.otf) fonts — SURVEY.md §8(f) rank 3.  Glyphs are given as absolute path commands
+# ('M', x, y) / ('L', x, y) / ('C', x1, y1, x2, y2, x, y) with integer coordinates; the encoder below turns them
+# into Type 2 charstrings and deliberately spreads them over every operator and number encoding, so the
+# absolute commands are the known answer for both CFF interpreters (host C++ and oracle C).
+# ---------------------------------------------------------------------------------------------------------------
+def _t2_num(v, style=0):
+    """Type 2 charstring operand.  style 1 forces the 3-byte form (28), style 2 the 16.16 form (255)."""
+    v = int(v)
+    if style == 2:
+        return b"\xff" + struct.pack(">i", v << 16)
+    if style == 1 or not -1131 <= v <= 1131:
+        return b"\x1c" + struct.pack(">h", v)
+    if -107 <= v <= 107:
+        return bytes([v + 139])
+    if v > 0:
+        v -= 108
+        return bytes([247 + (v >> 8), v & 255])
+    v = -v - 108
+    return bytes([251 + (v >> 8), v & 255])
+
+
+def _dict_int5(v):
+    return b"\x1d" + struct.pack(">i", int(v))
+
+
+def _dict_real(text):
+    nib = {".": 0xA, "E": 0xB, "-": 0xE}
+    out = []
+    i = 0
+    while i < len(text):
+        if text[i : i + 2] == "E-":
+            out.append(0xC)
+            i += 2
+        else:
+            out.append(nib.get(text[i], int(text[i]) if text[i].isdigit() else None))
+            i += 1
+    out.append(0xF)
+    if len(out) & 1:
+        out.append(0xF)
+    return b"\x1e" + bytes((out[k] << 4) | out[k + 1] for k in range(0, len(out), 2))
+
+
+def _cff_index(items):
+    if not items:
+        return b"\0\0"
+    offs = [1]
+    for it in items:
+        offs.append(offs[-1] + len(it))
+    osz = 1 if offs[-1] < 256 else 2 if offs[-1] < 65536 else 4
+    enc = b"".join(o.to_bytes(osz, "big") for o in offs)
+    return struct.pack(">HB", len(items), osz) + enc + b"".join(items)
+
+
+def _subr_bias(n):
+    return 107 if n < 1240 else 1131 if n < 33900 else 32768
+
+
+def encode_charstring(cmds, variant=0, width=None, hints=False, call=None):
+    """Absolute commands -> Type 2 charstring.  `variant` rotates which of the equivalent operators is used;
+    `call` = (operator byte 10 / 29, biased index) is issued right after the first moveto (the subroutine
+    draws a closed square relative to the current point and returns to it, see cff_test_font)."""
+    out = b""
+    x = y = 0
+    first = True
+    stack_w = [] if width is None else [_t2_num(width)]
+    if hints:  # hstemhm (+ width), then hintmask with two implied vstems: 3 stems -> one mask byte
+        out += b"".join(stack_w) + _t2_num(10) + _t2_num(20) + b"\x12"
+        stack_w = []
+        out += _t2_num(30) + _t2_num(40) + _t2_num(50) + _t2_num(60) + b"\x13\xe0"
+    i = 0
+    k = variant
+    while i < len(cmds):
+        c = cmds[i]
+        k += 1
+        style = (0, 0, 1, 0, 2)[k % 5]
+        num = lambda v: _t2_num(v, style)
+        if c[0] == "M":
+            dx, dy = c[1] - x, c[2] - y
+            w = b"".join(stack_w)
+            stack_w = []
+            if dy == 0 and k % 2:
+                out += w + num(dx) + b"\x16"
+            elif dx == 0 and k % 2:
+                out += w + num(dy) + b"\x04"
+            else:
+                out += w + num(dx) + num(dy) + b"\x15"
+            x, y = c[1], c[2]
+            if first and call is not None:
+                out += _t2_num(call[1]) + bytes([call[0]])
+            first = False
+            i += 1
+        elif c[0] == "L":
+            run = []
+            while i < len(cmds) and cmds[i][0] == "L":
+                run.append(cmds[i])
+                i += 1
+            # alternating horizontal / vertical runs use hlineto / vlineto, the rest rlineto; a run that is
+            # followed by a curve may become rlinecurve
+            j = 0
+            while j < len(run):
+                dx, dy = run[j][1] - x, run[j][2] - y
+                if (dx == 0) != (dy == 0):
+                    horiz = dy == 0
+                    args, h, xx, yy, jj = [], horiz, x, y, j
+                    while jj < len(run):
+                        ddx, ddy = run[jj][1] - xx, run[jj][2] - yy
+                        if h and ddy == 0 and ddx != 0:
+                            args.append(ddx)
+                        elif not h and ddx == 0 and ddy != 0:
+                            args.append(ddy)
+                        else:
+                            break
+                        xx, yy = run[jj][1], run[jj][2]
+                        h = not h
+                        jj += 1
+                    out += b"".join(num(a) for a in args) + (b"\x06" if horiz else b"\x07")
+                    x, y, j = xx, yy, jj
+                else:
+                    args = []
+                    while j < len(run):
+                        dx, dy = run[j][1] - x, run[j][2] - y
+                        if (dx == 0) != (dy == 0) and args:
+                            break
+                        args += [dx, dy]
+                        x, y = run[j][1], run[j][2]
+                        j += 1
+                    if j == len(run) and i < len(cmds) and cmds[i][0] == "C" and k % 3 == 0 and len(args) <= 30:
+                        cc = cmds[i]
+                        args += [cc[1] - x, cc[2] - y, cc[3] - cc[1], cc[4] - cc[2], cc[5] - cc[3], cc[6] - cc[4]]
+                        x, y = cc[5], cc[6]
+                        i += 1
+                        out += b"".join(num(a) for a in args) + b"\x19"  # rlinecurve
+                    else:
+                        out += b"".join(num(a) for a in args) + b"\x05"
+        else:
+            d = [c[1] - x, c[2] - y, c[3] - c[1], c[4] - c[2], c[5] - c[3], c[6] - c[4]]
+            nxt = cmds[i + 1] if i + 1 < len(cmds) else None
+            if nxt is not None and nxt[0] == "C" and k % 4 == 0:  # two curves as flex (depth argument unused)
+                d2 = [nxt[1] - c[5], nxt[2] - c[6], nxt[3] - nxt[1], nxt[4] - nxt[2], nxt[5] - nxt[3], nxt[6] - nxt[4]]
+                out += b"".join(num(a) for a in d + d2) + num(50) + b"\x0c\x23"
+                x, y = nxt[5], nxt[6]
+                i += 2
+                continue
+            delta = lambda c0, px, py: [c0[1] - px, c0[2] - py, c0[3] - c0[1], c0[4] - c0[2], c0[5] - c0[3], c0[6] - c0[4]]
+            hv = lambda q: q[1] == 0 and q[4] == 0  # horizontal start, vertical end
+            vh = lambda q: q[0] == 0 and q[5] == 0  # vertical start, horizontal end
+            if hv(d) or vh(d):
+                # hvcurveto / vhcurveto: following curves join the same operator while they keep alternating
+                args, horiz, op = [], hv(d), (b"\x1f" if hv(d) else b"\x1e")
+                while True:
+                    args += [d[0], d[2], d[3], d[5]] if horiz else [d[1], d[2], d[3], d[4]]
+                    x, y = c[5], c[6]
+                    i += 1
+                    horiz = not horiz
+                    if i >= len(cmds) or cmds[i][0] != "C" or len(args) > 36:
+                        break
+                    c = cmds[i]
+                    d = delta(c, x, y)
+                    if not (hv(d) if horiz else vh(d)):
+                        break
+                out += b"".join(num(a) for a in args) + op
+                continue
+            elif d[1] == 0 and d[5] == 0:
+                out += b"".join(num(a) for a in (d[0], d[2], d[3], d[4])) + b"\x1b"  # hhcurveto
+            elif d[0] == 0 and d[4] == 0:
+                out += b"".join(num(a) for a in (d[1], d[2], d[3], d[5])) + b"\x1a"  # vvcurveto
+            elif d[5] == 0 and k % 2:
+                out += b"".join(num(a) for a in (d[1], d[0], d[2], d[3], d[4])) + b"\x1b"  # hhcurveto with dy1
+            elif d[4] == 0 and k % 2:
+                out += b"".join(num(a) for a in (d[0], d[1], d[2], d[3], d[5])) + b"\x1a"  # vvcurveto with dx1
+            elif d[1] == 0 and k % 2:
+                out += b"".join(num(a) for a in (d[0], d[2], d[3], d[5], d[4])) + b"\x1f"  # hvcurveto, 5 arguments
+            elif d[0] == 0 and k % 2:
+                out += b"".join(num(a) for a in (d[1], d[2], d[3], d[4], d[5])) + b"\x1e"  # vhcurveto, 5 arguments
+            elif nxt is not None and nxt[0] == "L" and k % 3 == 1:
+                out += b"".join(num(a) for a in d + [nxt[1] - c[5], nxt[2] - c[6]]) + b"\x18"  # rcurveline
+                x, y = nxt[1], nxt[2]
+                i += 2
+                continue
+            elif nxt is not None and nxt[0] == "C" and k % 2 == 0:  # two general curves in one rrcurveto
+                out += b"".join(num(a) for a in d + delta(nxt, c[5], c[6])) + b"\x08"
+                x, y = nxt[5], nxt[6]
+                i += 2
+                continue
+            else:
+                out += b"".join(num(a) for a in d) + b"\x08"
+            x, y = c[5], c[6]
+            i += 1
+    return out + b"".join(stack_w) + b"\x0e"
+
+
+def _blob(x, y, w, h, r):
+    """Closed contour with cubic corners and axis-parallel edges, absolute integer coordinates."""
+    kx = (r * 11) // 20
+    return [
+        ("M", x + r, y), ("L", x + w - r, y), ("C", x + w - r + kx, y, x + w, y + r - kx, x + w, y + r),
+        ("L", x + w, y + h - r), ("C", x + w, y + h - r + kx, x + w - r + kx, y + h, x + w - r, y + h),
+        ("L", x + r, y + h), ("C", x + r - kx, y + h, x, y + h - r + kx, x, y + h - r),
+        ("L", x, y + r), ("C", x, y + r - kx, x + r - kx, y, x + r, y),
+    ]
+
+
+def _wave(x, y, w, h, rng):
+    """Closed contour of general cubics and slanted lines (exercises rrcurveto / rlineto / flex / rcurveline)."""
+    p = lambda fx, fy: (x + int(fx * w) + int(rng.integers(-9, 10)), y + int(fy * h) + int(rng.integers(-9, 10)))
+    a, b, c, d, e, f, g = p(0, 0), p(0.3, 0.25), p(0.6, -0.2), p(1, 0.1), p(0.9, 0.6), p(0.5, 1.0), p(0.1, 0.8)
+    m1, m2, m3, m4 = p(0.95, 0.3), p(1.05, 0.45), p(0.75, 0.9), p(0.6, 1.1)
+    return [("M",) + a, ("C",) + b + c + d, ("C",) + m1 + m2 + e, ("L",) + m3, ("C",) + m4 + p(0.55, 1.05) + f,
+            ("L",) + g, ("L",) + p(0.05, 0.5), ("L",) + a]
+
+
+def _raw(*items):
+    return b"".join(it if isinstance(it, bytes) else _t2_num(it) for it in items)
+
+
+# hand-assembled charstrings for the three flex forms the encoder does not produce: (charstring, expected contours)
+_FLEX_CASES = [
+    (_raw(100, 100, b"\x15", 10, 20, 30, 40, 50, 60, 70, b"\x0c\x22", b"\x0e"),  # hflex
+     [[("M", 100, 100), ("C", 110, 100, 130, 130, 170, 130), ("C", 220, 130, 280, 100, 350, 100)]]),
+    (_raw(100, 100, b"\x15", 10, 5, 20, 30, 40, 50, 60, -30, 70, b"\x0c\x24", b"\x0e"),  # hflex1
+     [[("M", 100, 100), ("C", 110, 105, 130, 135, 170, 135), ("C", 220, 135, 280, 105, 350, 100)]]),
+    (_raw(100, 100, b"\x15", 10, 5, 20, 30, 40, 0, 50, 0, 60, -30, 70, b"\x0c\x25", b"\x0e"),  # flex1, horizontal
+     [[("M", 100, 100), ("C", 110, 105, 130, 135, 170, 135), ("C", 220, 135, 280, 105, 350, 100)]]),
+    (_raw(100, 100, b"\x15", 5, 10, 30, 20, 0, 40, 0, 50, -30, 60, 70, b"\x0c\x25", b"\x0e"),  # flex1, vertical
+     [[("M", 100, 100), ("C", 105, 110, 135, 130, 135, 170), ("C", 135, 220, 105, 280, 100, 350)]]),
+]
+
+
+def _specials(x, y):
+    """Contours built to reach the operators random shapes rarely hit: multi-argument hlineto / vlineto, hmoveto /
+    vmoveto (consecutive contours share a coordinate), hhcurveto / vvcurveto with and without the leading argument,
+    the 5-argument hvcurveto, chained hv / vh curves, and two general curves in a row (flex or 12-argument rrcurveto)."""
+    stair_h = [("M", x, y), ("L", x + 60, y), ("L", x + 60, y + 50), ("L", x + 130, y + 50), ("L", x + 130, y + 120),
+               ("L", x, y + 120), ("L", x, y)]
+    bx = x + 300
+    stair_v = [("M", bx, y), ("L", bx, y + 70), ("L", bx + 40, y + 70), ("L", bx + 40, y + 150), ("L", bx + 110, y + 150),
+               ("L", bx + 110, y), ("L", bx, y)]
+    cy = y + 200
+    curvy = [("M", bx, cy), ("C", bx + 40, cy, bx + 60, cy + 60, bx + 100, cy + 60),
+             ("C", bx + 100, cy + 100, bx + 130, cy + 120, bx + 130, cy + 160),
+             ("C", bx + 80, cy + 190, bx + 20, cy + 210, bx - 20, cy + 210),
+             ("C", bx - 40, cy + 170, bx - 70, cy + 120, bx - 70, cy + 60),
+             ("C", bx - 50, cy + 60, bx - 30, cy + 30, bx, cy)]
+    ox, oy = bx, cy + 300  # quarter arcs: hv, vh, hv, vh in one operator
+    ring = [("M", ox + 50, oy), ("C", ox + 78, oy, ox + 100, oy + 22, ox + 100, oy + 50),
+            ("C", ox + 100, oy + 78, ox + 78, oy + 100, ox + 50, oy + 100),
+            ("C", ox + 22, oy + 100, ox, oy + 78, ox, oy + 50), ("C", ox, oy + 22, ox + 22, oy, ox + 50, oy)]
+    lx, ly = x, y + 400
+    lens = [("M", lx, ly), ("C", lx + 30, ly + 60, lx + 90, ly + 80, lx + 150, ly + 20),
+            ("C", lx + 110, ly - 50, lx + 40, ly - 45, lx, ly)]
+    return [stair_h, stair_v, curvy, ring, lens]
+
+
+_SUBR_RING = [(20, 0), (0, 20), (-20, 0), (0, -20)]  # relative square drawn by the shared subroutines (returns to its start)
+
+
+def cff_test_font(n_glyphs=40, first_cp=0x41, seed=5, cid=False, fd_select_format=3):
+    """Returns (font bytes, code points, expected) where expected[i] = list of contours (absolute commands) of
+    the glyph of cps[i], subroutine-drawn parts included."""
+    rng = np.random.default_rng(seed)
+    cps = list(range(first_cp, first_cp + n_glyphs + len(_FLEX_CASES)))
+    n_all = len(cps) + 1
+    # subroutines: draw the small square relative to the current point, come back to it, open a new contour
+    # there.  Global subr 0 nests local subr 0 (or, in a CID font, the glyph's own FD's local subr 0).
+    def tri(scale):
+        s = b""
+        for dx, dy in _SUBR_RING:
+            s += _t2_num(dx * scale) + _t2_num(dy * scale) + b"\x05"
+        return s
+    n_fd = 2 if cid else 1
+    fd_of = lambda g: g * n_fd // n_all
+    local_subrs = [[tri(1 + fd) + b"\x0b", tri(3 + fd) + _t2_num(0) + _t2_num(0) + b"\x15" + b"\x0b"] for fd in range(n_fd)]
+    global_subrs = [_t2_num(0 - 107) + b"\x0a" + b"\x0b", tri(2) + b"\x0b"]
+
+    def tri_contour(x, y, scale):
+        pts, out = (x, y), [("M", x, y)]
+        for dx, dy in _SUBR_RING:
+            pts = (pts[0] + dx * scale, pts[1] + dy * scale)
+            out.append(("L",) + pts)
+        return out
+
+    charstrings = [b"\x0e"]  # .notdef: endchar only -> no outline
+    expected, advances = [], [500]
+    for gi, cp in enumerate(cps[:n_glyphs]):
+        contours = []
+        for s in range(1 + gi % 3):
+            w, h = int(rng.integers(120, 600)), int(rng.integers(100, 500))
+            x, y = int(rng.integers(0, 1000 - w)), int(rng.integers(-200, 800 - h))
+            contours.append(_blob(x, y, w, h, int(rng.integers(20, 50))) if (gi + s) % 2 == 0 else _wave(x, y, w, h, rng))
+        if gi % 3 == 1:
+            contours += _specials(int(rng.integers(0, 500)), int(rng.integers(-150, 100)))
+        fd = fd_of(gi + 1)
+        call = None
+        kind = gi % 5
+        first = contours[0][0]
+        cmds = [c for ct in contours for c in ct]
+        exp = [list(ct) for ct in contours]
+        if kind == 1:  # local subr 0: triangle appended to the first contour's start, before its own segments
+            call = (10, 0 - 107)
+            exp[0] = tri_contour(first[1], first[2], 1 + fd) + contours[0][1:]
+        elif kind == 2:  # global subr 0 -> local subr 0
+            call = (29, 0 - 107)
+            exp[0] = tri_contour(first[1], first[2], 1 + fd) + contours[0][1:]
+        elif kind == 3:  # global subr 1
+            call = (29, 1 - 107)
+            exp[0] = tri_contour(first[1], first[2], 2) + contours[0][1:]
+        elif kind == 4:  # local subr 1: a triangle contour of its own, then a fresh moveto at the same point
+            call = (10, 1 - 107)
+            exp = [tri_contour(first[1], first[2], 3 + fd), [("M", first[1] + 0, first[2] + 0)] + contours[0][1:]] + exp[1:]
+        charstrings.append(encode_charstring(cmds, variant=gi, width=(300 + gi) if gi % 2 else None, hints=gi % 4 == 2,
+                                             call=call))
+        expected.append(exp)
+        advances.append(int(rng.integers(400, 1101)))
+    for code, exp in _FLEX_CASES:
+        charstrings.append(code)
+        expected.append(exp)
+        advances.append(600)
+    assert n_all == len(charstrings)
+
+    # ---- CFF table: header, Name, Top DICT, String, Global Subrs | charset | FDSelect | CharStrings | FDArray |
+    # Private DICTs + Local Subrs.  Offsets in DICTs use the fixed 5-byte form so sizes do not depend on them.
+    header = bytes([1, 0, 4, 4])
+    name_index = _cff_index([b"SynthCFF"])
+    string_index = _cff_index([b"Adobe", b"Identity"]) if cid else _cff_index([])
+    gsubr_index = _cff_index(global_subrs)
+    font_matrix = b"".join(_dict_real(t) for t in ("0.001", "0", "0", "1E-3", "0", "0")) + b"\x0c\x07"
+
+    def top_dict(o):
+        d = b""
+        if cid:
+            d += _dict_int5(391) + _dict_int5(392) + _dict_int5(0) + b"\x0c\x1e"
+        d += font_matrix
+        if cid:
+            d += _dict_int5(o["charset"]) + b"\x0f" + _dict_int5(o["fdarray"]) + b"\x0c\x24" + _dict_int5(o["fdselect"]) + b"\x0c\x25"
+        else:
+            d += _dict_int5(o["priv_size"][0]) + _dict_int5(o["priv"][0]) + b"\x12"
+        return d + _dict_int5(o["charstrings"]) + b"\x11"
+
+    def private_dict(subrs_off):
+        return _dict_real("0.039625") + b"\x0c\x09" + _dict_int5(500) + b"\x14" + _dict_int5(subrs_off) + b"\x13"
+
+    priv_len = len(private_dict(0))
+    zero = {"charset": 0, "fdarray": 0, "fdselect": 0, "charstrings": 0, "priv": [0] * n_fd, "priv_size": [priv_len] * n_fd}
+    top_len = len(_cff_index([top_dict(zero)]))
+    pos = len(header) + len(name_index) + top_len + len(string_index) + len(gsubr_index)
+    o = dict(zero)
+    charset = struct.pack(">BHH", 2, 1, n_all - 2) if cid else b""
+    o["charset"] = pos
+    pos += len(charset)
+    if fd_select_format == 3:
+        bounds = [g for g in range(n_all) if g == 0 or fd_of(g) != fd_of(g - 1)]
+        fdselect = struct.pack(">BH", 3, len(bounds)) + b"".join(struct.pack(">HB", g, fd_of(g)) for g in bounds)
+        fdselect += struct.pack(">H", n_all)
+    else:
+        fdselect = b"\0" + bytes(fd_of(g) for g in range(n_all))
+    if not cid:
+        fdselect = b""
+    o["fdselect"] = pos
+    pos += len(fdselect)
+    cs_index = _cff_index(charstrings)
+    o["charstrings"] = pos
+    pos += len(cs_index)
+    font_dict = lambda off: _dict_int5(priv_len) + _dict_int5(off) + b"\x12"
+    fdarray = _cff_index([font_dict(0)] * n_fd) if cid else b""
+    o["fdarray"] = pos
+    pos += len(fdarray)
+    privs = b""
+    o["priv"] = []
+    for fd in range(n_fd):
+        o["priv"].append(pos)
+        blob = private_dict(priv_len) + _cff_index(local_subrs[fd])  # Subrs right behind the Private DICT
+        privs += blob
+        pos += len(blob)
+    if cid:
+        fdarray = _cff_index([font_dict(off) for off in o["priv"]])
+    cff = header + name_index + _cff_index([top_dict(o)]) + string_index + gsubr_index + charset + fdselect + cs_index + fdarray + privs
+    assert len(_cff_index([top_dict(o)])) == top_len and len(cff) == pos
+
+    # ---- sfnt wrapper ('OTTO'): cmap format 4 with one segment, hmtx, head, hhea, maxp 0.5, name
+    sub = struct.pack(">HHHHHHH", 4, 16 + 16, 0, 4, 0, 0, 0) + struct.pack(">HH", cps[-1], 0xFFFF) + b"\0\0" + \
+        struct.pack(">HH", cps[0], 0xFFFF) + struct.pack(">HH", (1 - cps[0]) & 0xFFFF, 1) + b"\0\0\0\0"
+    cmap_table = struct.pack(">HH", 0, 1) + struct.pack(">HHI", 3, 1, 12) + sub
+    head = struct.pack(">IIIIHHqqhhhhHHhhh", 0x00010000, 0x00010000, 0, 0x5F0F3CF5, 0, 1000, 0, 0, 0, -200, 1000, 800,
+                       0, 8, 2, 0, 0)
+    hhea = struct.pack(">IhhhHhhhhhhhhhhhH", 0x00010000, 800, -200, 0, 1100, 0, 0, 1000, 1, 0, 0, 0, 0, 0, 0, 0, n_all)
+    maxp = struct.pack(">IH", 0x00005000, n_all)
+    hm = np.zeros((n_all, 2), dtype=">u2")
+    hm[:, 0] = advances
+    fam = ("Synth CFF CID" if cid else "Synth CFF").encode("utf-16-be")
+    name = struct.pack(">HHH", 0, 1, 6 + 12) + struct.pack(">HHHHHH", 3, 1, 0x409, 1, len(fam), 0) + fam
+    tables = {b"CFF ": cff, b"cmap": cmap_table, b"head": head, b"hhea": hhea, b"hmtx": hm.tobytes(), b"maxp": maxp,
+              b"name": name}
+    tags = sorted(tables)
+    out = struct.pack(">4sHHHH", b"OTTO", len(tags), 64, 2, len(tags) * 16 - 64)
+    offset = 12 + 16 * len(tags)
+    records, blobs = b"", b""
+    for tag in tags:
+        data = tables[tag]
+        records += tag + struct.pack(">III", _table_checksum(data), offset, len(data))
+        padded = data + b"\0" * ((-len(data)) % 4)
+        blobs += padded
+        offset += len(padded)
+    return out + records + blobs, cps, expected

@@ -227,6 +227,16 @@ def test_c4_full_bmp_subset_parity(renderer):
     print(f"C4 subset: {px} px, {100 * same / px:.4f}% identical")
 
 
+@pytest.mark.parametrize("cid", [False, True])
+def test_cff_font_parity(renderer, cid):
+    """CFF (.otf) outlines, name-keyed and CID-keyed: Type 2 charstrings -> cubic flattening on the host
+    (ring.rs:159-187, adaptive, so these glyphs take the segment-level jobs) -> SDF kernel, against the oracle's
+    own CFF interpreter and f64 renderer."""
+    data, cps, _ = synth_font.cff_test_font(n_glyphs=60, cid=cid)
+    px, same = _font_parity(data, renderer, "Synth CFF CID" if cid else "Synth CFF", [0])
+    print(f"CFF cid={cid}: {px} px, {100 * same / px:.4f}% identical")
+
+
 # ---- edge cases through the raw C ABI ---------------------------------------------------------------------
 def test_empty_and_degenerate_batches(ctx):
     # empty batch

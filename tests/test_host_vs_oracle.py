@@ -382,3 +382,94 @@ def test_cmap_formats_known_answers_and_oracle(fmt):
             assert m.render_block("cmap_test", b, V.Renderer.new_dummy()) == oset.render_block(b, O.MODE_DUMMY), (fmt, b)
     finally:
         os.unlink(path)
+
+
+def _expected_rings(contours):
+    """RingBuilder (ring_builder.rs:33-117) over absolute path commands: cubics flattened by the pinned
+    add_cubic_bezier restatement, rings closed, rings with < 3 points (< 4 closed) dropped."""
+    rings = []
+    for ct in contours:
+        pts = []
+        for c in ct:
+            if c[0] == "M":
+                pts = [(float(c[1]), float(c[2]))]
+            elif c[0] == "L":
+                pts.append((float(c[1]), float(c[2])))
+            else:
+                pts += [tuple(p) for p in O.flatten_cubic(pts[-1], c[1:3], c[3:5], c[5:7]).tolist()]
+        if len(pts) < 3:
+            continue
+        if pts[0] != pts[-1]:
+            pts.append(pts[0])
+        if len(pts) >= 4:
+            rings.append(np.array(pts))
+    return rings
+
+
+@pytest.mark.parametrize("cid,fdsel", [(False, 3), (True, 3), (True, 0)])
+def test_cff_charstrings_known_answers_and_oracle(cid, fdsel):
+    """CFF 1 outlines: a synthetic .otf whose Type 2 charstrings are generated from absolute path
+    commands (every path operator, every number encoding, hint operators, width prefixes, local / global / nested
+    subroutines; name-keyed and CID-keyed with FDSelect formats 0 and 3).  Host and oracle interpreters must both
+    reproduce the commands they were generated from, and the whole dummy pipeline must agree byte for byte."""
+    import synth_font
+
+    data, cps, expected = synth_font.cff_test_font(cid=cid, fd_select_format=fdsel)
+    f, o = V.FontFileEntry(data=data), O.Font(data)
+    assert f.codepoints().tolist() == cps == list(o.codepoints())
+    n_rings = 0
+    for cp, contours in zip(cps, expected):
+        gid = f.glyph_index(cp)
+        assert gid == o.glyph_index(cp) == cp - cps[0] + 1
+        want = _expected_rings(contours)
+        pts, starts = f.outline_rings(gid)
+        got_o = o.outline_rings(gid)
+        assert len(want) == len(starts) - 1 == len(got_o), (hex(cp), len(want), len(starts) - 1, len(got_o))
+        for i, r in enumerate(want):
+            assert np.array_equal(pts[starts[i] : starts[i + 1]], r), (hex(cp), i)
+            assert np.array_equal(got_o[i], r), (hex(cp), i)
+        n_rings += len(want)
+    assert n_rings > len(cps)
+    # .notdef is `endchar` only: no outline, no error
+    assert len(f.outline_rings(0)[1]) == 1 and len(o.outline_rings(0)) == 0
+    # frames, metrics and PBF bytes of the whole block through the dummy renderer
+    m = V.FontManager(parallel=False)
+    m.add_font_bytes_with_name("Synth CFF", data)
+    path = f"/tmp/_cff_{int(cid)}_{fdsel}.otf"
+    open(path, "wb").write(data)
+    try:
+        oset = O.FontSet("Synth CFF", [path])
+        assert m.block_population("synth_cff").tolist() == oset.block_population()
+        assert m.render_block("synth_cff", 0, V.Renderer.new_dummy()) == oset.render_block(0, O.MODE_DUMMY)
+    finally:
+        os.unlink(path)
+
+
+def test_cff_malformed_inputs_do_not_crash():
+    """Truncations and byte flips of the CFF table: both parsers must stay in bounds and agree on what comes out
+    (a rejected table = a face without outlines; a charstring error keeps the callbacks made before it)."""
+    import synth_font
+
+    data, cps, _ = synth_font.cff_test_font(n_glyphs=12, cid=True)
+    n_tables = int.from_bytes(data[4:6], "big")
+    rec = next(12 + 16 * i for i in range(n_tables) if data[12 + 16 * i : 16 + 16 * i] == b"CFF ")
+    off, length = int.from_bytes(data[rec + 8 : rec + 12], "big"), int.from_bytes(data[rec + 12 : rec + 16], "big")
+    rng = np.random.default_rng(3)
+    variants = []
+    for cut in (3, 10, 40, length // 2, length - 7):
+        b = bytearray(data)
+        b[rec + 12 : rec + 16] = cut.to_bytes(4, "big")
+        variants.append(bytes(b))
+    for _ in range(150):
+        b = bytearray(data)
+        for _ in range(int(rng.integers(1, 4))):
+            b[off + int(rng.integers(0, length))] = int(rng.integers(0, 256))
+        variants.append(bytes(b))
+    for v in variants:
+        f, o = V.FontFileEntry(data=v), O.Font(v)
+        for gid in range(0, len(cps) + 1):
+            pts, starts = f.outline_rings(gid)
+            rings = o.outline_rings(gid)
+            assert len(rings) == len(starts) - 1
+            for i, r in enumerate(rings):
+                assert np.array_equal(pts[starts[i] : starts[i + 1]], r, equal_nan=True)

@@ -2,6 +2,8 @@
 // SURVEY.md Appendix C; anchored on the reference's call sites, see face.h).
 #include "face.h"
 
+#include "cff.h"
+
 #include <algorithm>
 #include <cstring>
 
@@ -49,6 +51,9 @@ bool Face::table(const char tag[4], Span &out) const
 	return false;
 }
 
+Face::Face() = default;
+Face::~Face() = default;
+
 std::unique_ptr<Face> Face::parse(std::vector<uint8_t> data)
 {
 	std::unique_ptr<Face> f(new Face());
@@ -68,6 +73,9 @@ std::unique_ptr<Face> Face::parse(std::vector<uint8_t> data)
 	f->table("loca", f->loca_);
 	f->table("glyf", f->glyf_);
 	f->table("name", f->name_);
+	Span cff;
+	if (f->table("CFF ", cff))
+		f->cff_ = CffTable::parse(f->data_.data() + cff.off, cff.len);
 	if (f->table("cmap", f->cmap_) && f->cmap_.len >= 4) {
 		const uint16_t n = f->u16(f->cmap_.off + 2);
 		for (uint16_t i = 0; i < n; ++i) {
@@ -622,6 +630,9 @@ void Face::outline_impl(Span g, int depth, const Transform &t, OutlineBuilder &b
 
 bool Face::outline_glyph(uint16_t gid, OutlineBuilder &builder) const
 {
+	// ttf-parser's order (lib.rs, Face::outline_glyph): a face with glyf + loca never looks at `CFF `
+	if (glyf_.len == 0 || loca_.len == 0)
+		return cff_ ? cff_->outline(gid, builder) : false;
 	Span g;
 	if (!glyph_range(gid, g))
 		return false;

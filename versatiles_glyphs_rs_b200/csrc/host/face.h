@@ -1,8 +1,9 @@
 // face.h — the subset of ttf-parser 0.25.1's `Face` that the reference's rendering path calls
 // (crate not vendored in the reference; call sites: src/render/renderer.rs:106,107,110,115,
 // src/font/file_entry.rs:48, src/font/metadata.rs:91-116).  TrueType `glyf` outlines, cmap
-// formats 0/4/6/12, hmtx advances, name table strings.  No CFF, no variations (none of the
-// reference's fixtures use them; SURVEY.md §8(f) rank 3 lists them as "next").
+// formats 0/4/6/10/12/13, hmtx advances, name table strings; `CFF ` outlines through cff.h when the face
+// has no usable glyf / loca pair (ttf-parser's order: glyf, then cff).  No CFF2, no variations (none of
+// the reference's fixtures use them).
 #pragma once
 
 #include <cstdint>
@@ -12,6 +13,8 @@
 #include <vector>
 
 namespace vgb {
+
+class CffTable;
 
 // ttf_parser::OutlineBuilder — coordinates arrive as f32 font units
 class OutlineBuilder {
@@ -28,6 +31,7 @@ class Face {
   public:
 	// Face::parse(data, 0): nullptr when the mandatory tables are missing / truncated
 	static std::unique_ptr<Face> parse(std::vector<uint8_t> data);
+	~Face();
 
 	uint16_t units_per_em() const { return upm_; }
 	uint16_t number_of_glyphs() const { return num_glyphs_; }
@@ -80,6 +84,8 @@ class Face {
 	bool loca_long_ = false;
 	Span hmtx_, loca_, glyf_, cmap_, name_;
 	std::vector<CmapSubtable> subtables_;
+	std::unique_ptr<CffTable> cff_;
+	Face();
 };
 
 } // namespace vgb
