@@ -8,8 +8,9 @@
  *
  * Parity pin: every known-answer test the reference holds for this path is reproduced by
  * tests/test_oracle_goldens.py.  Still unpinned (no reference golden
- * exists): scaled / nested composite glyphs, the cubic path beyond the 17-point count, and
- * exact u8 values of real glyphs — see DESIGN.md "Oracle".
+ * exists): scaled / nested composite glyphs, the cubic path beyond the 17-point count, CFF
+ * charstring interpretation (no CFF fixture; synthetic known-answer fonts only), and exact u8
+ * values of real glyphs — see DESIGN.md "Oracle".
  */
 #ifndef VG_ORACLE_H
 #define VG_ORACLE_H
