@@ -824,8 +824,7 @@ static void outline_impl(const vgo_font *f, span g, int depth, xform t, ring_bui
 /* ------------------------------------------------------------------------------------------ */
 /* CFF 1 outlines → callbacks (restated ttf-parser 0.25.1 cff1.rs / charstring.rs / dict.rs /   */
 /* index.rs; reached from renderer.rs:110 when the face has no glyf + loca).  Parity unpinned:  */
-/* no fixture of the reference is CFF; tests use synthetic known-answer fonts.  `seac` is not   */
-/* restated (the glyph ends with an error before any callback).                                 */
+/* no fixture of the reference is CFF; tests use synthetic known-answer fonts.                  */
 /* ------------------------------------------------------------------------------------------ */
 static void rb_curve_to(ring_builder *b, float x1, float y1, float x2, float y2, float x, float y)
 {
@@ -980,7 +979,48 @@ struct vgo_cff {
 	cff_index gsubrs, charstrings, lsubrs, fdarray;
 	int cid, fdsel_format;
 	span fdsel;
+	int charset_format; /* -1 ISOAdobe, -2 Expert, -3 ExpertSubset, else 0 / 1 / 2 with the records in charset */
+	span charset;
+	uint32_t charset_n; /* records */
 };
+
+/* StandardEncoding (Adobe): code -> SID, as runs {first code, last code, first SID} */
+static const uint16_t STD_ENC_RUNS[][3] = {{32, 126, 1},   {161, 175, 96},  {177, 180, 111}, {182, 189, 115}, {191, 191, 123},
+                                           {193, 200, 124}, {202, 203, 132}, {205, 208, 134}, {225, 225, 138}, {227, 227, 139},
+                                           {232, 235, 140}, {241, 241, 144}, {245, 245, 145}, {248, 251, 146}};
+
+/* seac_code_to_glyph_id — cff1.rs; -1 = None */
+static int32_t cff_seac_gid(const struct vgo_cff *c, float code)
+{
+	if (!(code > -1.0f && code < 256.0f))
+		return -1;
+	uint32_t ch = (uint32_t)(int32_t)code, sid = 0;
+	for (size_t i = 0; i < sizeof(STD_ENC_RUNS) / sizeof(STD_ENC_RUNS[0]); i++)
+		if (ch >= STD_ENC_RUNS[i][0] && ch <= STD_ENC_RUNS[i][1])
+			sid = STD_ENC_RUNS[i][2] + (ch - STD_ENC_RUNS[i][0]);
+	if (c->charset_format == -1)
+		return ch <= 228 ? (int32_t)sid : -1;
+	if (c->charset_format < 0)
+		return -1;
+	if (sid == 0)
+		return 0;
+	const uint8_t *r = c->charset.p;
+	if (c->charset_format == 0) {
+		for (uint32_t g = 0; g < c->charset_n; g++)
+			if (rd16(r + 2 * g) == sid)
+				return (int32_t)g + 1;
+		return -1;
+	}
+	uint32_t gid = 1;
+	for (uint32_t i = 0; i < c->charset_n; i++) {
+		uint32_t first = rd16(r), left = c->charset_format == 1 ? r[2] : rd16(r + 2);
+		if (sid >= first && sid - first <= left)
+			return (int32_t)((gid + (sid - first)) & 0xffff);
+		gid += left + 1;
+		r += c->charset_format == 1 ? 3 : 4;
+	}
+	return -1;
+}
 
 /* Subrs INDEX of the Private DICT at [start, start + len) of the table; 1 = found and parsed, 0 = none, -1 = malformed */
 static int cff_private_subrs(span table, size_t start, size_t len, cff_index *out)
@@ -1043,14 +1083,19 @@ static vgo_cff *cff_parse(span t)
 	if (cs > t.len || !cff_read_index(t, &cs, &c.charstrings) || c.charstrings.count == 0)
 		return NULL;
 	uint32_t ng = c.charstrings.count;
-	if (has_charset && charset > 2) { /* parse_charset must succeed */
+	c.charset_format = -1;
+	if (has_charset && charset <= 2)
+		c.charset_format = -1 - (int)charset;
+	else if (has_charset) { /* parse_charset must succeed */
 		if (charset >= t.len)
 			return NULL;
 		size_t p = charset + 1;
 		uint8_t fmt = t.p[charset];
+		c.charset.p = t.p + p;
 		if (fmt == 0) {
 			if (t.len - p < ((size_t)ng - 1) * 2)
 				return NULL;
+			c.charset_n = ng - 1;
 		} else if (fmt == 1 || fmt == 2) {
 			uint32_t left = ng - 1;
 			size_t rec = fmt == 1 ? 3 : 4;
@@ -1062,9 +1107,11 @@ static vgo_cff *cff_parse(span t)
 				if (cnt > left)
 					return NULL;
 				left -= cnt;
+				c.charset_n++;
 			}
 		} else
 			return NULL;
+		c.charset_format = fmt;
 	}
 	if (ros) {
 		if (!has_charset || !has_fda || !has_fds || charset == 0 || fda == 0 || fds == 0)
@@ -1161,7 +1208,7 @@ typedef struct {
 	float st[48];
 	int n;
 	float x, y;
-	int moved, first_move, width_seen, endchar, stems;
+	int moved, first_move, width_seen, endchar, seac, stems;
 	int lsubrs_ready;
 	cff_index lsubrs;
 } cs_state;
@@ -1231,7 +1278,7 @@ static int cs_exec(cs_state *s, span code, int depth)
 			break;
 		case 21: case 22: case 4: { /* rmoveto, hmoveto, vmoveto */
 			int want = op == 21 ? 2 : 1, i = 0;
-			if (n == want + 1 && !s->width_seen)
+			if (n == want + 1) /* a surplus first argument is the width, also in a seac component */
 				s->width_seen = 1, i = 1;
 			if (n != want + i)
 				return 0;
@@ -1413,16 +1460,32 @@ static int cs_exec(cs_state *s, span code, int depth)
 				return 0;
 			if (!cs_exec(s, body, depth + 1))
 				return 0;
-			if (s->endchar)
+			if (s->endchar && !s->seac)
 				return pc >= code.len;
 			break;
 		}
 		case 11: /* return */
 			return 1;
 		case 14: /* endchar */
-			if (n == 4 || (n == 5 && !s->width_seen))
-				return 0; /* seac */
-			if (n == 1 && !s->width_seen)
+			if (n == 4 || (n == 5 && !s->width_seen)) { /* seac: [w] adx ady bchar achar */
+				int32_t accent = cff_seac_gid(s->c, a[n - 1]);
+				int32_t base = accent < 0 ? -1 : cff_seac_gid(s->c, a[n - 2]);
+				if (base < 0)
+					return 0;
+				float ady = a[n - 3], adx = a[n - 4];
+				if (n == 5)
+					s->width_seen = 1;
+				s->n = 0;
+				s->seac = 1;
+				if (depth == 10)
+					return 0;
+				span part;
+				if (!cff_index_get(&s->c->charstrings, (uint32_t)base, &part) || !cs_exec(s, part, depth + 1))
+					return 0;
+				s->x = adx, s->y = ady;
+				if (!cff_index_get(&s->c->charstrings, (uint32_t)accent, &part) || !cs_exec(s, part, depth + 1))
+					return 0;
+			} else if (n == 1 && !s->width_seen)
 				s->width_seen = 1, s->n = 0;
 			if (!s->first_move) {
 				s->first_move = 1;

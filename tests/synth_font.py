@@ -423,11 +423,11 @@ def _specials(x, y):
 _SUBR_RING = [(20, 0), (0, 20), (-20, 0), (0, -20)]  # relative square drawn by the shared subroutines (returns to its start)
 
 
-def cff_test_font(n_glyphs=40, first_cp=0x41, seed=5, cid=False, fd_select_format=3):
+def cff_test_font(n_glyphs=40, first_cp=0x41, seed=5, cid=False, fd_select_format=3, charset_format=None, seac=False):
     """Returns (font bytes, code points, expected) where expected[i] = list of contours (absolute commands) of
     the glyph of cps[i], subroutine-drawn parts included."""
     rng = np.random.default_rng(seed)
-    cps = list(range(first_cp, first_cp + n_glyphs + len(_FLEX_CASES)))
+    cps = list(range(first_cp, first_cp + n_glyphs + len(_FLEX_CASES) + (2 if seac else 0)))
     n_all = len(cps) + 1
     # subroutines: draw the small square relative to the current point, come back to it, open a new contour
     # there.  Global subr 0 nests local subr 0 (or, in a CID font, the glyph's own FD's local subr 0).
@@ -484,6 +484,18 @@ def cff_test_font(n_glyphs=40, first_cp=0x41, seed=5, cid=False, fd_select_forma
         charstrings.append(code)
         expected.append(exp)
         advances.append(600)
+    if seac:
+        # `endchar` with four arguments (five with a width): accent glyph drawn at (adx, ady) over the base glyph, both
+        # named by StandardEncoding codes that go code -> SID -> glyph through the charset.  Predefined ISOAdobe
+        # charset: glyph id = SID = code - 31.  Custom charset (below): glyphs 1..10 have SIDs 30..39, the rest 108 + gid.
+        assert not cid
+        base_gid, accent_gid, base_code, accent_code = (34, 65, 65, 96) if charset_format is None else (5, 16, 65, 193)
+        shift = lambda ct, dx, dy: [(c[0],) + tuple(v + (dx if k % 2 == 0 else dy) for k, v in enumerate(c[1:])) for c in ct]
+        for args in ((450, 30, 40), (-25, 60)):
+            charstrings.append(_raw(*args, base_code, accent_code, b"\x0e"))
+            adx, ady = args[-2:]
+            expected.append([list(ct) for ct in expected[base_gid - 1]] + [shift(ct, adx, ady) for ct in expected[accent_gid - 1]])
+            advances.append(700)
     assert n_all == len(charstrings)
 
     # ---- CFF table: header, Name, Top DICT, String, Global Subrs | charset | FDSelect | CharStrings | FDArray |
@@ -502,6 +514,8 @@ def cff_test_font(n_glyphs=40, first_cp=0x41, seed=5, cid=False, fd_select_forma
         if cid:
             d += _dict_int5(o["charset"]) + b"\x0f" + _dict_int5(o["fdarray"]) + b"\x0c\x24" + _dict_int5(o["fdselect"]) + b"\x0c\x25"
         else:
+            if charset_format is not None:
+                d += _dict_int5(o["charset"]) + b"\x0f"
             d += _dict_int5(o["priv_size"][0]) + _dict_int5(o["priv"][0]) + b"\x12"
         return d + _dict_int5(o["charstrings"]) + b"\x11"
 
@@ -514,6 +528,14 @@ def cff_test_font(n_glyphs=40, first_cp=0x41, seed=5, cid=False, fd_select_forma
     pos = len(header) + len(name_index) + top_len + len(string_index) + len(gsubr_index)
     o = dict(zero)
     charset = struct.pack(">BHH", 2, 1, n_all - 2) if cid else b""
+    if not cid and charset_format is not None:
+        sids = [29 + g if g <= 10 else 108 + g for g in range(1, n_all)]
+        if charset_format == 0:
+            charset = b"\0" + b"".join(struct.pack(">H", v) for v in sids)
+        elif charset_format == 1:
+            charset = b"\1" + struct.pack(">HB", 30, 9) + struct.pack(">HB", 119, n_all - 12)
+        else:
+            charset = b"\2" + struct.pack(">HH", 30, 9) + struct.pack(">HH", 119, n_all - 12)
     o["charset"] = pos
     pos += len(charset)
     if fd_select_format == 3:

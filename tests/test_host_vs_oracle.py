@@ -406,15 +406,20 @@ def _expected_rings(contours):
     return rings
 
 
-@pytest.mark.parametrize("cid,fdsel", [(False, 3), (True, 3), (True, 0)])
-def test_cff_charstrings_known_answers_and_oracle(cid, fdsel):
+@pytest.mark.parametrize("cid,fdsel,charset", [(False, 3, None), (True, 3, None), (True, 0, None), (False, 3, "iso"),
+                                               (False, 3, 0), (False, 3, 1), (False, 3, 2)])
+def test_cff_charstrings_known_answers_and_oracle(cid, fdsel, charset):
     """CFF 1 outlines: a synthetic .otf whose Type 2 charstrings are generated from absolute path
     commands (every path operator, every number encoding, hint operators, width prefixes, local / global / nested
-    subroutines; name-keyed and CID-keyed with FDSelect formats 0 and 3).  Host and oracle interpreters must both
+    subroutines, `seac` composites; name-keyed and CID-keyed with FDSelect formats 0 and 3, charset formats 0 / 1 / 2
+    and the predefined one).  Host and oracle interpreters must both
     reproduce the commands they were generated from, and the whole dummy pipeline must agree byte for byte."""
     import synth_font
 
-    data, cps, expected = synth_font.cff_test_font(cid=cid, fd_select_format=fdsel)
+    if charset is None:
+        data, cps, expected = synth_font.cff_test_font(cid=cid, fd_select_format=fdsel)
+    else:  # `seac` composites through the predefined ISOAdobe charset or a charset table of format 0 / 1 / 2
+        data, cps, expected = synth_font.cff_test_font(n_glyphs=70, seac=True, charset_format=None if charset == "iso" else charset)
     f, o = V.FontFileEntry(data=data), O.Font(data)
     assert f.codepoints().tolist() == cps == list(o.codepoints())
     n_rings = 0
@@ -435,7 +440,7 @@ def test_cff_charstrings_known_answers_and_oracle(cid, fdsel):
     # frames, metrics and PBF bytes of the whole block through the dummy renderer
     m = V.FontManager(parallel=False)
     m.add_font_bytes_with_name("Synth CFF", data)
-    path = f"/tmp/_cff_{int(cid)}_{fdsel}.otf"
+    path = f"/tmp/_cff_{int(cid)}_{fdsel}_{charset}.otf"
     open(path, "wb").write(data)
     try:
         oset = O.FontSet("Synth CFF", [path])

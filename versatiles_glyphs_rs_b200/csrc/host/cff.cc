@@ -224,15 +224,19 @@ bool private_subrs_offset(Bytes priv, size_t &off)
 	return have;
 }
 
-// charset / encoding tables only matter for `seac`, but a malformed one makes cff::Table::parse fail
-bool charset_well_formed(Bytes t, size_t off, uint16_t n_glyphs)
+// parse_charset: the records behind the format byte (format 0: SIDs of glyphs 1.., formats 1 / 2: ranges that
+// together cover every glyph but .notdef); false = malformed, which makes cff::Table::parse fail
+bool parse_charset(Bytes t, size_t off, uint16_t n_glyphs, uint8_t &format, Bytes &records, uint32_t &n_records)
 {
 	Cursor c(t, off);
-	const uint8_t format = c.u8();
+	format = c.u8();
 	if (!c.ok)
 		return false;
+	const size_t begin = c.pos;
+	n_records = 0;
 	if (format == 0) {
-		c.skip(((size_t)n_glyphs - 1) * 2);
+		n_records = (uint32_t)n_glyphs - 1;
+		c.skip((size_t)n_records * 2);
 	} else if (format == 1 || format == 2) {
 		uint32_t left = (uint32_t)n_glyphs - 1;
 		while (left > 0) {
@@ -241,12 +245,28 @@ bool charset_well_formed(Bytes t, size_t off, uint16_t n_glyphs)
 			if (!c.ok || n > left)
 				return false;
 			left -= n;
+			n_records++;
 		}
 	} else {
 		return false;
 	}
-	return c.ok;
+	if (!c.ok)
+		return false;
+	records.p = t.p + begin, records.len = c.pos - begin;
+	return true;
 }
+
+// Adobe StandardEncoding: character code -> SID (0 = .notdef)
+const uint8_t kStandardEncoding[256] = {
+	0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+	1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32,
+	33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63, 64,
+	65, 66, 67, 68, 69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80, 81, 82, 83, 84, 85, 86, 87, 88, 89, 90, 91, 92, 93, 94, 95, 0,
+	0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+	0, 96, 97, 98, 99, 100, 101, 102, 103, 104, 105, 106, 107, 108, 109, 110, 0, 111, 112, 113, 114, 0, 115, 116, 117, 118, 119, 120, 121, 122, 0, 123,
+	0, 124, 125, 126, 127, 128, 129, 130, 131, 0, 132, 133, 0, 134, 135, 136, 137, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+	0, 138, 0, 139, 0, 0, 0, 0, 140, 141, 142, 143, 0, 0, 0, 0, 0, 144, 0, 0, 0, 145, 0, 0, 146, 147, 148, 149, 0, 0, 0, 0,
+};
 
 bool encoding_well_formed(Bytes t, size_t off)
 {
@@ -332,8 +352,14 @@ std::unique_ptr<CffTable> CffTable::parse(const uint8_t *data, size_t len)
 			return nullptr;
 	}
 	const uint16_t n_glyphs = (uint16_t)t->char_strings_.count;
-	if (has_charset && charset_off > 2 && !charset_well_formed(t->table_, charset_off, n_glyphs))
-		return nullptr;
+	if (has_charset && charset_off <= 2) {
+		t->charset_kind_ = (int)charset_off;
+	} else if (has_charset) {
+		uint8_t format;
+		if (!parse_charset(t->table_, charset_off, n_glyphs, format, t->charset_, t->charset_records_))
+			return nullptr;
+		t->charset_kind_ = 3 + format;
+	}
 
 	if (has_ros) {
 		if (!has_charset || !has_fd_array || !has_fd_select || charset_off == 0 || fd_array_off == 0 || fd_select_off == 0)
@@ -372,6 +398,48 @@ std::unique_ptr<CffTable> CffTable::parse(const uint8_t *data, size_t len)
 		}
 	}
 	return t;
+}
+
+// seac_code_to_glyph_id: StandardEncoding code -> SID -> glyph through the charset
+bool CffTable::seac_glyph(float code, uint16_t &glyph_id) const
+{
+	if (!(code > -1.0f && code < 256.0f))
+		return false;
+	const uint8_t ch = (uint8_t)(int)code;
+	const uint16_t sid = kStandardEncoding[ch];
+	if (charset_kind_ == 0) { // ISOAdobe: glyph id = SID, defined up to 228
+		if (ch > 228)
+			return false;
+		glyph_id = sid;
+		return true;
+	}
+	if (charset_kind_ < 3)
+		return false; // Expert, ExpertSubset
+	if (sid == 0) {
+		glyph_id = 0;
+		return true;
+	}
+	const uint8_t *r = charset_.p;
+	if (charset_kind_ == 3) {
+		for (uint32_t i = 0; i < charset_records_; ++i)
+			if ((uint16_t)((r[2 * i] << 8) | r[2 * i + 1]) == sid) {
+				glyph_id = (uint16_t)(i + 1);
+				return true;
+			}
+		return false;
+	}
+	const size_t rec = charset_kind_ == 4 ? 3 : 4;
+	uint32_t gid = 1;
+	for (uint32_t i = 0; i < charset_records_; ++i, r += rec) {
+		const uint32_t first = (uint32_t)((r[0] << 8) | r[1]);
+		const uint32_t left = rec == 3 ? r[2] : (uint32_t)((r[2] << 8) | r[3]);
+		if (first <= sid && sid <= first + left) {
+			glyph_id = (uint16_t)(gid + (sid - first));
+			return true;
+		}
+		gid += left + 1;
+	}
+	return false;
 }
 
 // parse_cid_local_subrs: FDSelect → Font DICT → Private DICT → Subrs
@@ -438,7 +506,7 @@ struct CffTable::Interp {
 	int len = 0;
 	float x = 0.f, y = 0.f;
 	bool has_move_to = false, is_first_move_to = true;
-	bool have_width = false, has_endchar = false, drew = false;
+	bool have_width = false, has_endchar = false, has_seac = false, drew = false;
 	uint32_t stems = 0;
 	bool have_local = false;
 	Index local;
@@ -485,7 +553,7 @@ struct CffTable::Interp {
 	{
 		const int want = op == 21 ? 2 : 1;
 		int i = 0;
-		if (len == want + 1 && !have_width) {
+		if (len == want + 1) { // one argument too many: the first is the width (also inside a seac component)
 			have_width = true;
 			i = 1;
 		}
@@ -752,7 +820,7 @@ bool CffTable::run(Interp &in, Bytes code, int depth) const
 				return false;
 			if (!run(in, body, depth + 1))
 				return false;
-			if (in.has_endchar) {
+			if (in.has_endchar && !in.has_seac) {
 				if (!s.at_end())
 					return false;
 				return true;
@@ -769,9 +837,25 @@ bool CffTable::run(Interp &in, Bytes code, int depth) const
 			break;
 		}
 		case 14: { // endchar
-			if (in.len == 4 || (!in.have_width && in.len == 5))
-				return false; // seac: not implemented (cff.h)
-			if (in.len == 1 && !in.have_width) {
+			if (in.len == 4 || (!in.have_width && in.len == 5)) { // seac: adx ady bchar achar
+				uint16_t accent, base;
+				if (!seac_glyph(in.pop(), accent) || !seac_glyph(in.pop(), base))
+					return false;
+				const float dy = in.pop(), dx = in.pop();
+				if (!in.have_width && in.len != 0) {
+					in.have_width = true;
+					in.len--;
+				}
+				in.has_seac = true;
+				if (depth == kStackLimit)
+					return false;
+				Bytes part;
+				if (!char_strings_.get(base, part) || !run(in, part, depth + 1))
+					return false;
+				in.x = dx, in.y = dy;
+				if (!char_strings_.get(accent, part) || !run(in, part, depth + 1))
+					return false;
+			} else if (in.len == 1 && !in.have_width) {
 				in.have_width = true;
 				in.len = 0;
 			}

@@ -2,9 +2,8 @@
 // (crate not vendored in the reference; call site src/render/renderer.rs:110, which ignores the result, so the
 // callbacks made before a charstring error count).  Type 2 charstrings → move_to / line_to / curve_to / close
 // in f32 font units; name-keyed (SID) and CID-keyed fonts (FDSelect formats 0 / 3), local and global
-// subroutines.  `seac` (accented composites in `endchar`) is not implemented: such a glyph ends with an error
-// before any callback, where ttf-parser would draw base + accent.  FontMatrix is read past but not applied
-// (ttf-parser exposes it through `Table::matrix()` without transforming the outline).
+// subroutines, `seac` (accented composites in `endchar`, through StandardEncoding and the charset).  FontMatrix is
+// read past but not applied (ttf-parser exposes it through `Table::matrix()` without transforming the outline).
 // SURVEY.md §8(f) rank 3.
 #pragma once
 
@@ -41,12 +40,17 @@ class CffTable {
 	struct Interp;
 	bool run(Interp &in, Bytes code, int depth) const;
 	bool cid_local_subrs(uint16_t glyph_id, Index &out) const;
+	bool seac_glyph(float code, uint16_t &glyph_id) const;
 
 	Bytes table_;
 	Index global_subrs_, char_strings_, local_subrs_, fd_array_;
 	bool cid_ = false;
 	uint8_t fd_select_format_ = 0;
 	Bytes fd_select_; // format 0: one byte per glyph; format 3: everything after the format byte
+	// charset: 0 ISOAdobe / 1 Expert / 2 ExpertSubset (predefined), 3 + f for a table of format f (records in charset_)
+	int charset_kind_ = 0;
+	Bytes charset_;
+	uint32_t charset_records_ = 0;
 };
 
 } // namespace vgb
