@@ -72,12 +72,32 @@ inline bool dyadic_ok(float v)
 
 inline double lerp_exact(double a, double b, double t) { return a + t * (b - a); }
 
-// B(i / 2^k) of one coordinate — the same expression the device evaluates (sdf_kernel.cuh curve_point)
-inline double curve_coord(double s, double c, double e, uint32_t i, uint32_t k)
+// B(t) of one coordinate, t = i / 2^k exactly — the same expression the device evaluates (sdf_kernel.cuh curve_point)
+inline double curve_coord(double s, double c, double e, double t)
 {
-	const double t = std::ldexp((double)i, -(int)k);
 	return lerp_exact(lerp_exact(s, c, t), lerp_exact(c, e, t), t);
 }
+
+// 2^-k, exact
+inline double pow2_neg(uint32_t k)
+{
+	const uint64_t bits = (uint64_t)(1023 - k) << 52;
+	double v;
+	std::memcpy(&v, &bits, sizeof(v));
+	return v;
+}
+
+// PRECISION * 16^j: scaling by a power of two is exact, so `v * 16^-j > PRECISION` <=> `v > kDepthThreshold[j]`
+struct DepthThresholds {
+	double t[MAX_DEPTH + 1];
+	DepthThresholds()
+	{
+		double v = PRECISION;
+		for (uint32_t j = 0; j <= MAX_DEPTH; ++j, v *= 16.0)
+			t[j] = v;
+	}
+};
+const DepthThresholds kDepthThreshold;
 
 } // namespace
 
@@ -133,7 +153,9 @@ void OutlineRecorder::line_to(float x, float y)
 void OutlineRecorder::axis_extrema(double s, double c, double e, uint32_t k, double &lo, double &hi) const
 {
 	// control point between the end points: the coordinate is monotone on [0,1], the end points bound it
-	if (k == 0 || (c >= std::fmin(s, e) && c <= std::fmax(s, e)))
+	// (coordinates passed dyadic_ok: no NaN)
+	const double mn = s < e ? s : e, mx = s < e ? e : s;
+	if (k == 0 || (c >= mn && c <= mx))
 		return;
 	const double a = s - c * 2.0 + e;
 	if (a == 0.0)
@@ -142,14 +164,19 @@ void OutlineRecorder::axis_extrema(double s, double c, double e, uint32_t k, dou
 	if (!(ts > 0.0 && ts < 1.0))
 		return;
 	const int64_t n = (int64_t)1 << k;
-	const int64_t i0 = (int64_t)std::floor(ts * (double)n);
-	for (int64_t i = i0 - 1; i <= i0 + 2; ++i) { // one extra point each side absorbs the rounding of t*
-		if (i < 1 || i > n - 1)
-			continue;
-		const double v = curve_coord(s, c, e, (uint32_t)i, k);
-		lo = std::fmin(lo, v);
-		hi = std::fmax(hi, v);
+	const double step = pow2_neg(k);
+	const int64_t i0 = (int64_t)(ts * (double)n); // ts > 0: truncation is floor
+	// one extra point each side absorbs the rounding of t*; candidates outside 1..n-1 are clamped onto grid points
+	// of the polyline, which belong into the box anyway
+	double l = lo, h = hi;
+	for (int64_t d = -1; d <= 2; ++d) {
+		int64_t i = i0 + d;
+		i = i < 1 ? 1 : (i > n - 1 ? n - 1 : i);
+		const double v = curve_coord(s, c, e, (double)i * step);
+		l = v < l ? v : l;
+		h = v > h ? v : h;
 	}
+	lo = l, hi = h;
 }
 
 void OutlineRecorder::quad_to(float x1, float y1, float x, float y)
@@ -165,14 +192,15 @@ void OutlineRecorder::quad_to(float x1, float y1, float x, float y)
 	// exactly 4^-j times the root's, so the tested value is exactly 16^-j times this one.
 	const double dx = sx + ex - cx * 2.0;
 	const double dy = sy + ey - cy * 2.0;
-	double v = dx * dx + dy * dy;
+	const double v = dx * dx + dy * dy;
+	// depth = how often the tested value has to be divided by 16 to pass: counted against the scaled thresholds
+	// without a data-dependent loop exit (the depth varies from curve to curve and mispredicts)
 	uint32_t k = 0;
-	while (v > PRECISION) {
-		v *= 0.0625;
-		if (++k > MAX_DEPTH) {
-			exact_ = false;
-			return;
-		}
+	for (uint32_t j = 0; j <= MAX_DEPTH; ++j)
+		k += v > kDepthThreshold.t[j] ? 1u : 0u;
+	if (k > MAX_DEPTH) {
+		exact_ = false;
+		return;
 	}
 	b200sdf_curve r;
 	r.sx = ring_last_.x, r.sy = ring_last_.y, r.cx = x1, r.cy = y1, r.ex = x, r.ey = y;
