@@ -710,6 +710,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				renderer.release_batch(std::move(f->batch));
 			delete f;
 		}
+	renderer.top_up_pool();
 	if (trace) {
 		std::fprintf(stderr, "[vgb trace] setup %.1f us, %d workers, %zu tasks, target %zu glyphs, total %.1f us\n",
 		             (double)(t_setup - t_begin) * 1e-3, workers, tasks.size(), target, (double)(now_ns() - t_begin) * 1e-3);

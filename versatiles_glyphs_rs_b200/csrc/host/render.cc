@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
@@ -269,12 +270,18 @@ bool HostBuffer::reserve(size_t bytes, size_t keep, bool exact)
 	// Pinned allocations are slow and stall the whole CUDA context, so grow them in big steps: a pooled
 	// batch reaches its steady-state size after one or two uses.  (exact: sizing to a known capacity.)
 	const size_t step = pinned_ ? (size_t)256 << 10 : (size_t)16 << 10;
+	// ... and with half as much again as is needed now, so that batches a little bigger than any seen so far
+	// (their composition varies from call to call) do not grow the buffer in the middle of a later call.
+	const size_t target = bytes + bytes / 2;
 	size_t n = cap_ ? cap_ : step;
-	while (n < bytes)
+	while (n < target)
 		n += n + step;
 	if (exact)
 		n = bytes;
 	n = (n + 4095) & ~size_t(4095);
+	static const bool trace = std::getenv("VGB_ALLOC_TRACE") != nullptr;
+	if (trace)
+		std::fprintf(stderr, "[vgb alloc] %zu -> %zu bytes (%s%s)\n", cap_, n, pinned_ ? "pinned" : "heap", exact ? ", to the pool's mark" : "");
 	uint8_t *q = pinned_ ? (uint8_t *)b200sdf_alloc_pinned(n) : (uint8_t *)std::malloc(n);
 	if (!q)
 		return false;
@@ -513,16 +520,17 @@ bool GlyphBatch::add_glyph(const Face &face, uint32_t index)
 
 bool GlyphBatch::ensure_output() { return out_.reserve((size_t)out_bytes_ + 16, 0); }
 
-void GlyphBatch::capacities(size_t caps[4]) const
+void GlyphBatch::capacities(size_t caps[kBuffers]) const
 {
 	caps[0] = jobs_.capacity(), caps[1] = segs_.capacity(), caps[2] = curves_.capacity(), caps[3] = out_.capacity();
+	caps[4] = tiles_.capacity();
 }
 
-void GlyphBatch::reserve_capacity(const size_t caps[4])
+void GlyphBatch::reserve_capacity(const size_t caps[kBuffers])
 {
 	// only called on an empty batch: nothing to keep
 	jobs_.reserve(caps[0], 0, true), segs_.reserve(caps[1], 0, true), curves_.reserve(caps[2], 0, true),
-	    out_.reserve(caps[3], 0, true);
+	    out_.reserve(caps[3], 0, true), tiles_.reserve(caps[4], 0, true);
 }
 
 PbfGlyph GlyphBatch::take_glyph(size_t i) const
@@ -577,10 +585,15 @@ Renderer::~Renderer()
 		b200sdf_destroy(ctx_);
 }
 
+namespace {
+constexpr size_t kPoolMax = 128;  // batches kept when they come back
+constexpr size_t kPoolTopUp = 96; // batches allocated ahead of need
+}
+
 std::unique_ptr<GlyphBatch> Renderer::acquire_batch() const
 {
 	std::unique_ptr<GlyphBatch> b;
-	size_t caps[4];
+	size_t caps[GlyphBatch::kBuffers];
 	{
 		std::lock_guard<std::mutex> g(pool_mu_);
 		while (!pool_.empty() && !b) {
@@ -589,8 +602,10 @@ std::unique_ptr<GlyphBatch> Renderer::acquire_batch() const
 			if (b->mode() != flatten_)
 				b.reset();
 		}
-		for (int i = 0; i < 4; ++i)
+		for (int i = 0; i < GlyphBatch::kBuffers; ++i)
 			caps[i] = hwm_[i];
+		out_max_ = std::max(out_max_, ++out_now_);
+		acq_call_++;
 	}
 	if (!b)
 		b = new_batch();
@@ -603,13 +618,47 @@ std::unique_ptr<GlyphBatch> Renderer::acquire_batch() const
 
 void Renderer::release_batch(std::unique_ptr<GlyphBatch> b) const
 {
-	size_t caps[4];
+	size_t caps[GlyphBatch::kBuffers];
 	b->capacities(caps);
 	std::lock_guard<std::mutex> g(pool_mu_);
-	for (int i = 0; i < 4; ++i)
+	for (int i = 0; i < GlyphBatch::kBuffers; ++i)
 		hwm_[i] = std::max(hwm_[i], caps[i]);
-	if (pool_.size() < 128)
+	if (out_now_ > 0)
+		out_now_--;
+	if (pool_.size() < kPoolMax)
 		pool_.push_back(std::move(b));
+}
+
+void Renderer::top_up_pool() const
+{
+	size_t caps[GlyphBatch::kBuffers], want, have;
+	std::vector<std::unique_ptr<GlyphBatch>> mine;
+	static const bool trace = std::getenv("VGB_ALLOC_TRACE") != nullptr;
+	if (trace)
+		std::fprintf(stderr, "[vgb alloc] end of call: pool top-up\n");
+	{
+		std::lock_guard<std::mutex> g(pool_mu_);
+		for (int i = 0; i < GlyphBatch::kBuffers; ++i)
+			caps[i] = hwm_[i];
+		acq_max_ = std::max(acq_max_, acq_call_);
+		acq_call_ = 0;
+		want = std::min(kPoolTopUp, std::max(2 * out_max_, acq_max_ + acq_max_ / 4));
+		have = pool_.size();
+		mine.swap(pool_); // size the pooled batches outside the lock
+	}
+	for (auto &b : mine)
+		if (b->mode() == flatten_)
+			b->reserve_capacity(caps);
+	while (have < want) {
+		std::unique_ptr<GlyphBatch> b = new_batch();
+		b->reserve_capacity(caps);
+		mine.push_back(std::move(b));
+		have++;
+	}
+	std::lock_guard<std::mutex> g(pool_mu_);
+	for (auto &b : mine)
+		if (pool_.size() < kPoolMax)
+			pool_.push_back(std::move(b));
 }
 
 namespace {

@@ -202,8 +202,9 @@ class GlyphBatch {
 	const b200sdf_tile_job *tiles() const { return reinterpret_cast<const b200sdf_tile_job *>(tiles_.data()); }
 	uint32_t tile_count() const { return n_tiles_; }
 	// buffer capacities in bytes (jobs, segments, curves, bitmaps) — the pool sizes new leases from them
-	void capacities(size_t caps[4]) const;
-	void reserve_capacity(const size_t caps[4]);
+	static constexpr int kBuffers = 5; // jobs, segments, curves, bitmaps, tile list
+	void capacities(size_t caps[kBuffers]) const;
+	void reserve_capacity(const size_t caps[kBuffers]);
 	// PbfGlyph i with its bitmap copied out of the batch (valid after the batch was rendered)
 	PbfGlyph take_glyph(size_t i) const;
 
@@ -244,6 +245,12 @@ class Renderer {
 	// Batch pool: pinned buffers are expensive to allocate, so the pipeline recycles batches.
 	std::unique_ptr<GlyphBatch> acquire_batch() const;
 	void release_batch(std::unique_ptr<GlyphBatch> b) const;
+	// Called when a render_glyphs call is over: brings the pool to twice the largest number of batches that were
+	// ever out at once — or, while that is affordable, to 5/4 of the batches one call uses in total, which makes
+	// a later shortage impossible whatever the timing — every one sized to the marks, so that later calls neither
+	// create a batch nor grow one in the middle of their pipeline (a pinned allocation stalls the whole CUDA context, and far longer when eight
+	// ranks allocate on one host).
+	void top_up_pool() const;
 
 	// renderer.rs:103-149 — a batch of one.  nullopt = None.
 	std::optional<PbfGlyph> render_glyph(const Face &face, uint32_t index, std::string *err = nullptr) const;
@@ -266,7 +273,9 @@ class Renderer {
 	Flatten flatten_ = Flatten::Device;
 	mutable std::mutex pool_mu_;
 	mutable std::vector<std::unique_ptr<GlyphBatch>> pool_;
-	mutable size_t hwm_[4] = {0, 0, 0, 0}; // largest buffer capacities any batch of this renderer reached
+	mutable size_t hwm_[GlyphBatch::kBuffers] = {0, 0, 0, 0, 0}; // largest buffer capacities any batch of this renderer reached
+	mutable size_t out_now_ = 0, out_max_ = 0; // batches handed out and not yet returned; the most that ever were
+	mutable size_t acq_call_ = 0, acq_max_ = 0; // batches handed out since the last top-up; the most per call
 };
 
 } // namespace vgb
