@@ -642,8 +642,13 @@ void Renderer::top_up_pool() const
 			caps[i] = hwm_[i];
 		acq_max_ = std::max(acq_max_, acq_call_);
 		acq_call_ = 0;
-		want = std::min(kPoolTopUp, std::max(2 * out_max_, acq_max_ + acq_max_ / 4));
 		have = pool_.size();
+		// A call can never run short while the pool holds as many batches as the call hands out in total.  Top up
+		// only when that is about to stop being true, and then with room to spare, so that calls which use a batch
+		// or two more than any before do not each end with an allocation.
+		const size_t floor = std::max(out_max_ + out_max_ / 2, acq_max_ + 2);
+		want = have < floor ? std::max(2 * out_max_, acq_max_ + acq_max_ / 2) : have;
+		want = std::min(kPoolTopUp, want);
 		mine.swap(pool_); // size the pooled batches outside the lock
 	}
 	for (auto &b : mine)
