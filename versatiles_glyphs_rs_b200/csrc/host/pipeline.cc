@@ -444,7 +444,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					++outstanding; // reserve the place now: several workers pass this check at the same time
 				}
 				std::unique_ptr<Flight> cur(new Flight());
-				cur->batch = renderer.acquire_batch();
+				cur->batch = renderer.acquire_batch(true);
 				mark('o');
 				uint64_t t0 = now_ns();
 				// Batch size.  One thread enqueues every batch (about 10 us each), so batches are as large as the

@@ -590,7 +590,7 @@ constexpr size_t kPoolMax = 128;  // batches kept when they come back
 constexpr size_t kPoolTopUp = 96; // batches allocated ahead of need
 }
 
-std::unique_ptr<GlyphBatch> Renderer::acquire_batch() const
+std::unique_ptr<GlyphBatch> Renderer::acquire_batch(bool in_pipeline) const
 {
 	std::unique_ptr<GlyphBatch> b;
 	size_t caps[GlyphBatch::kBuffers];
@@ -605,7 +605,7 @@ std::unique_ptr<GlyphBatch> Renderer::acquire_batch() const
 		for (int i = 0; i < GlyphBatch::kBuffers; ++i)
 			caps[i] = hwm_[i];
 		out_max_ = std::max(out_max_, ++out_now_);
-		acq_call_++;
+		acq_call_ += in_pipeline ? 1 : 0;
 	}
 	if (!b)
 		b = new_batch();

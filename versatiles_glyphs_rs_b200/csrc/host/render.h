@@ -243,7 +243,8 @@ class Renderer {
 	void set_flatten(Flatten f) { flatten_ = f; }
 	std::unique_ptr<GlyphBatch> new_batch() const { return std::make_unique<GlyphBatch>(mode_ == Mode::Cuda, flatten_); }
 	// Batch pool: pinned buffers are expensive to allocate, so the pipeline recycles batches.
-	std::unique_ptr<GlyphBatch> acquire_batch() const;
+	// in_pipeline: the batch counts towards the per-call total that sizes the pool (top_up_pool)
+	std::unique_ptr<GlyphBatch> acquire_batch(bool in_pipeline = false) const;
 	void release_batch(std::unique_ptr<GlyphBatch> b) const;
 	// Called when a render_glyphs call is over: brings the pool to twice the largest number of batches that were
 	// ever out at once — or, while that is affordable, to 5/4 of the batches one call uses in total, which makes
