@@ -478,3 +478,32 @@ def test_cff_malformed_inputs_do_not_crash():
             assert len(rings) == len(starts) - 1
             for i, r in enumerate(rings):
                 assert np.array_equal(pts[starts[i] : starts[i + 1]], r, equal_nan=True)
+
+
+def test_pipeline_buffers_are_allocated_in_the_first_call_only():
+    """Pooled batch buffers (pinned memory on the GPU, where an allocation stalls the CUDA context): after the first
+    render_glyphs call the pool holds every batch a call needs at the capacity marks, so later calls allocate nothing.
+    Single-threaded and dummy renderer: batch composition is deterministic, the pool logic is the product's."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import versatiles_glyphs_rs_b200 as V, oracle_lib as O\n"
+        "m = V.FontManager(parallel=True); m.add_font_with_name('Noto Sans Regular', O.noto_paths())\n"
+        "r = V.Renderer.new_dummy()\n"
+        "for i in range(6):\n"
+        "    sys.stderr.write('== call %%d\\n' %% i); sys.stderr.flush()\n"
+        "    m.render_glyphs(V.Writer.new_memory(), r, threads=1)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VGB_ALLOC_TRACE="1", VGB_FAKE_LATENCY="100")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    call, per_call = -1, {}
+    for line in res.stderr.splitlines():
+        if line.startswith("== call"):
+            call = int(line.split()[2])
+        elif line.startswith("[vgb alloc]") and "->" in line:
+            per_call[call] = per_call.get(call, 0) + 1
+    assert per_call.get(0, 0) > 0, res.stderr[-2000:]
+    assert set(per_call) == {0}, per_call
