@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B200SDF_ABI_VERSION 1
+#define B200SDF_ABI_VERSION 2
 
 enum {
 	B200SDF_OK = 0,
@@ -126,6 +126,53 @@ typedef struct {
 #define B200SDF_MAX_ITEMS 64
 #endif
 #define B200SDF_MAX_DIM 16384 /* largest accepted glyph width/height in pixels */
+#define B200SDF_TILE_BINS 8   /* cost classes of device-planned tile jobs (heaviest first) */
+
+/*
+ * Glyph-level input (the seam one step earlier still: Face::outline_glyph itself, reference
+ * src/render/renderer.rs:109-111).  The font's `glyf` table lives in HBM (b200sdf_font_upload); a request names the
+ * simple-glyph record(s) of one glyph and the device does what ttf-parser's glyf walker, RingBuilder, Rings::scale /
+ * translate and prepare_glyph (renderer.rs:64-91) do: it decodes flags and coordinate deltas, emits the curve
+ * records, decides the flattening depth, computes the integer frame, plans the tile jobs and renders.  The host keeps
+ * cmap, hmtx, loca and the composite tree (components that are only translated become parts; anything else is
+ * recorded on the host and sent as kind CURVES / SEGMENTS in the same batch).
+ */
+enum { B200SDF_KIND_GLYF = 2 };
+
+typedef struct {
+	uint32_t font;     /* handle from b200sdf_font_upload */
+	uint32_t glyf_off; /* byte range of ONE simple glyph record inside that font's glyf table */
+	uint32_t glyf_len;
+	float ox, oy;      /* translation of the component in font units (0, 0 for a simple glyph) */
+} b200sdf_glyph_part;
+
+typedef struct {
+	uint32_t kind;             /* B200SDF_KIND_GLYF, or _CURVES / _SEGMENTS for a glyph recorded on the host */
+	uint32_t src_off, src_cnt; /* GLYF: parts; CURVES: curve records; SEGMENTS: segments (in the arrays of this call) */
+	uint32_t seg_cnt;          /* CURVES / SEGMENTS: flattened segments (GLYF: computed by the device) */
+	uint32_t width, height;    /* CURVES / SEGMENTS: the frame (GLYF: computed by the device) */
+	int32_t x0, y0;
+	double scale, dx;          /* GLYF / CURVES: rings.scale(scale), rings.translate((dx, 0)) */
+	uint64_t out_off;          /* where the bitmap goes; GLYF: start of a slot of out_cap bytes */
+	uint32_t out_cap;          /* GLYF: bytes reserved for the bitmap (from the glyph header's bounding box) */
+	uint32_t curve_off;        /* GLYF / CURVES: first record of this glyph's slot in the device's curve scratch ... */
+	uint32_t curve_cap;        /* ... and its size in records (GLYF: >= points of all parts) */
+	uint32_t reserved;
+} b200sdf_glyph_req;
+
+enum {
+	B200SDF_GLYPH_OK = 0,         /* rendered: frame valid, bitmap at out_off, row stride = width */
+	B200SDF_GLYPH_EMPTY = 1,      /* no ring survived / empty bounding box: PbfGlyph::empty (renderer.rs:118-120,133-137) */
+	B200SDF_GLYPH_NEEDS_HOST = 2, /* not representable by the device decoder (see glyf_kernel.cuh): record it on the host */
+	B200SDF_GLYPH_BAD_REQUEST = 3 /* request out of range */
+};
+
+typedef struct {
+	int32_t x0, y0;         /* RenderResult.x0 / .y0 */
+	uint32_t width, height; /* RenderResult.width / .height (buffer included) */
+	uint32_t seg_cnt;       /* flattened segments handed to the SDF pass */
+	uint32_t status;
+} b200sdf_glyph_frame;
 
 /* ---- context --------------------------------------------------------------------------------- */
 int b200sdf_abi_version(void);
@@ -199,6 +246,38 @@ int b200sdf_plan_outline_tiles_ex(const b200sdf_outline_job *jobs, uint32_t n_jo
 int b200sdf_render_outlines_device(b200sdf_ctx *ctx, const b200sdf_curve *d_curves, const b200sdf_segment *d_segs,
                                    const b200sdf_outline_job *d_jobs, const b200sdf_tile_job *d_tiles,
                                    uint32_t n_tiles, uint8_t *d_out, void *stream);
+
+/* ---- glyph-level path: glyf decoding, metrics and tile planning on the device ------------------ */
+/* Make a font's `glyf` table resident in HBM for the lifetime of the context (what FontFileEntry::new does for host
+ * memory, reference src/font/file_entry.rs:32-56).  handle indexes b200sdf_glyph_part.font.  Blocking; load time. */
+int b200sdf_font_upload(b200sdf_ctx *ctx, const uint8_t *glyf, uint64_t len, uint32_t *handle);
+/* Upper bound of the tile jobs the device may plan for a glyph whose frame is at most width x height:
+ * tile_cap of a submission = the sum over its requests. */
+uint32_t b200sdf_glyph_tile_bound(uint32_t width, uint32_t height);
+/* Enqueue one batch of glyph requests: decode + frame + tile planning (one kernel), SDF (one persistent kernel).
+ * frames[i] (written by the device) and the bitmaps are valid after b200sdf_wait / b200sdf_poll(ticket).
+ * curves / segs: the arrays CURVES / SEGMENTS requests index (may be NULL / 0).  curve_slots = size of the device's
+ * curve scratch in records (>= every request's curve_off + curve_cap); tile_cap = capacity of each of the
+ * B200SDF_TILE_BINS cost classes of the device's tile list.  A tile list that turns out too short fails the
+ * batch at wait / poll with B200SDF_E_ARG. */
+int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint32_t n_reqs, const b200sdf_glyph_part *parts,
+                          uint32_t n_parts, const b200sdf_curve *curves, uint32_t n_curves, const b200sdf_segment *segs,
+                          uint32_t n_seg, uint32_t curve_slots, uint32_t tile_cap, b200sdf_glyph_frame *frames, uint8_t *out,
+                          uint64_t out_bytes, uint64_t *ticket);
+/* The same over device pointers on `stream` (asynchronous, two kernel launches, scratch owned by the context);
+ * mid_event (a cudaEvent_t or NULL) is recorded between the decode kernel and the SDF kernel. */
+int b200sdf_render_glyphs_device(b200sdf_ctx *ctx, const b200sdf_glyph_req *d_reqs, uint32_t n_reqs,
+                                 const b200sdf_glyph_part *d_parts, uint32_t n_parts, const b200sdf_curve *d_curves,
+                                 uint32_t n_curves, const b200sdf_segment *d_segs, uint32_t n_seg, uint32_t curve_slots,
+                                 uint32_t tile_cap, b200sdf_glyph_frame *d_frames, uint8_t *d_out, uint64_t out_bytes,
+                                 void *stream, void *mid_event);
+/* Decode only (tests, diagnostics): frames, the outline job of every request (src_off / src_cnt locate its records
+ * in curves_out, which must hold curve_slots records) and the number of tile jobs planned per cost class
+ * (tiles_per_bin[B200SDF_TILE_BINS], may be NULL).  Blocking. */
+int b200sdf_decode_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint32_t n_reqs, const b200sdf_glyph_part *parts,
+                          uint32_t n_parts, const b200sdf_curve *curves, uint32_t n_curves, uint32_t n_seg, uint32_t curve_slots,
+                          b200sdf_glyph_frame *frames, b200sdf_outline_job *jobs_out, b200sdf_curve *curves_out,
+                          uint32_t *tiles_per_bin);
 
 /* ---- measurement helpers ----------------------------------------------------------------------- */
 /* Dependent-FFMA-chain microbenchmark: measured FP32 (non-tensor) peak of this device in TFLOP/s

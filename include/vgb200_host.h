@@ -79,9 +79,11 @@ int vgb_font_metadata(const vgb_font *f, char *name, char *family, char *style, 
 vgb_renderer *vgb_renderer_new(int dummy, int device, uint32_t n_slots);
 void vgb_renderer_free(vgb_renderer *r);
 int vgb_renderer_is_dummy(const vgb_renderer *r);
-/* Where new batches flatten Bezier curves: 1 = on the device from curve records (default), 0 = on the
- * host (upload b200sdf_segment: the literal renderer_precise seam, src/render/renderer_precise.rs:8) */
-void vgb_renderer_set_flatten(vgb_renderer *r, int on_device);
+/* What new batches send to the device: 2 = glyf record references — the device decodes, records, measures and plans
+ * (default of the CUDA renderer), 1 = curve records made by the host's OutlineRecorder, flattened on the device,
+ * 0 = segments flattened on the host (the literal renderer_precise seam, src/render/renderer_precise.rs:8) */
+void vgb_renderer_set_flatten(vgb_renderer *r, int mode);
+int vgb_renderer_flatten(const vgb_renderer *r);
 b200sdf_ctx *vgb_renderer_context(const vgb_renderer *r); /* NULL for the dummy renderer */
 /* Renderer::render_glyph (renderer.rs:103-149): 1 = Some(glyph), 0 = None, <0 = error */
 int vgb_renderer_render_glyph(const vgb_renderer *r, const vgb_font *f, uint32_t codepoint, vgb_glyph *out);
@@ -124,6 +126,18 @@ int vgb_renderer_wait_batch(const vgb_renderer *r, uint64_t ticket);
  * wait), 0 = still running, < 0 = error. */
 int vgb_renderer_prepare_batch(const vgb_renderer *r, vgb_batch *b);
 int vgb_renderer_poll_batch(const vgb_renderer *r, uint64_t ticket);
+/* Glyph-level batches (mode 2): after wait / poll reported the batch finished, take frames and bitmap presence from
+ * the device's answers; glyphs the device handed back are recorded on the host and rendered now (blocking).
+ * vgb_renderer_render_batch does this itself.  No-op for the other modes. */
+int vgb_batch_finalize(const vgb_renderer *r, vgb_batch *b);
+/* The request arrays of a glyph-level batch (what b200sdf_submit_glyphs receives) */
+const b200sdf_glyph_req *vgb_batch_requests(const vgb_batch *b, uint32_t *n);
+const b200sdf_glyph_part *vgb_batch_parts(const vgb_batch *b, uint32_t *n);
+uint32_t vgb_batch_curve_slots(const vgb_batch *b);
+uint32_t vgb_batch_tile_cap(const vgb_batch *b);
+uint32_t vgb_batch_handed_back(const vgb_batch *b);
+/* bitmap of glyph i (NULL when it has none); valid after the batch was rendered */
+const uint8_t *vgb_batch_glyph_bitmap(const vgb_batch *b, uint32_t i, uint64_t *len);
 
 /* ---- Writer ---- */
 vgb_writer *vgb_writer_new_file(const char *folder); /* Writer::new_file, writer/mod.rs:35 */
@@ -145,6 +159,9 @@ typedef struct {
 	/* host time per phase, ns summed over workers; wall_ns = the whole call */
 	uint64_t outline_ns, submit_ns, wait_ns, encode_ns, write_ns, wall_ns;
 	uint64_t submits, workers;
+	uint64_t handed_back;            /* glyphs the device decoder returned to the host recorder */
+	uint64_t h2d_bytes;              /* request / record / segment bytes the device read from host memory */
+	uint64_t cost_total, cost_shard; /* estimated cost of the whole job / of this shard (0 when not sharded) */
 } vgb_stats;
 
 vgb_manager *vgb_manager_new(int parallel);                                        /* manager.rs:28-33 */

@@ -27,19 +27,21 @@ def main():
     st = m.render_glyphs(w, r, shard=rank, n_shards=world, threads=2)
     mine = {n: hashlib.sha1(d).hexdigest() for n, is_dir, d in w.entries() if not is_dir}
     gathered = [None] * world
-    dist.all_gather_object(gathered, (mine, st.glyphs, st.blocks))
+    dist.all_gather_object(gathered, (mine, st.glyphs, st.blocks, st.cost_shard, st.cost_total))
     if rank == 0:
         full = V.Writer.new_memory()
         fst = m.render_glyphs(full, r)
         want = {n: hashlib.sha1(d).hexdigest() for n, is_dir, d in full.entries() if not is_dir}
         union = {}
-        for files, _, _ in gathered:
+        for files, *_ in gathered:
             assert not set(files) & set(union), "shards overlap"
             union.update(files)
         assert union == want, "union of shards != whole job"
-        assert sum(g for _, g, _ in gathered) == fst.glyphs and sum(b for _, _, b in gathered) == fst.blocks == 512
+        assert sum(g[1] for g in gathered) == fst.glyphs and sum(g[2] for g in gathered) == fst.blocks == 512
+        # every rank computed the same cost tables and the same longest-processing-time-first assignment
+        assert len({g[4] for g in gathered}) == 1 and sum(g[3] for g in gathered) == gathered[0][4] > 0
         print(json.dumps({"ok": True, "world": world, "files": len(union), "glyphs": fst.glyphs,
-                          "per_rank_blocks": [b for _, _, b in gathered]}))
+                          "per_rank_blocks": [g[2] for g in gathered], "per_rank_cost": [g[3] for g in gathered]}))
     dist.barrier()
     dist.destroy_process_group()
 

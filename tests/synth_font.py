@@ -67,19 +67,102 @@ def make_outline(rng, k_strokes, hole_every=2):
     return contours
 
 
-def build_font(codepoints, strokes_for, seed=0xB200, family="Synth B200", cmap_format=4, many_to_one=None):
+def _glyph_bytes_compact(contours, instructions=b""):
+    """The same record with the compact encodings real fonts use: one-byte deltas (flags 0x02 / 0x04 with the sign
+    bits), "same as previous" coordinates (0x10 / 0x20 without a byte), and runs of equal flags folded with REPEAT (0x08)."""
+    if not contours:
+        return b""
+    pts = [p for c in contours for p in c]
+    ends = np.cumsum([len(c) for c in contours]) - 1
+    flags, xb, yb = [], b"", b""
+    px = py = 0
+    for x, y, on in pts:
+        f = 1 if on else 0
+        dx, dy = x - px, y - py
+        px, py = x, y
+        if dx == 0:
+            f |= 0x10
+        elif -255 <= dx <= 255:
+            f |= 0x02 | (0x10 if dx > 0 else 0)
+            xb += bytes([abs(dx)])
+        else:
+            xb += struct.pack(">h", dx)
+        if dy == 0:
+            f |= 0x20
+        elif -255 <= dy <= 255:
+            f |= 0x04 | (0x20 if dy > 0 else 0)
+            yb += bytes([abs(dy)])
+        else:
+            yb += struct.pack(">h", dy)
+        flags.append(f)
+    fb, i = b"", 0
+    while i < len(flags):
+        j = i
+        while j + 1 < len(flags) and flags[j + 1] == flags[i] and j - i < 255:
+            j += 1
+        if j > i:
+            fb += bytes([flags[i] | 0x08, j - i])
+        else:
+            fb += bytes([flags[i]])
+        i = j + 1
+    xs = [p[0] for p in pts]
+    ys = [p[1] for p in pts]
+    head = struct.pack(">hhhhh", len(contours), min(xs), min(ys), max(xs), max(ys))
+    data = head + ends.astype(">u2").tobytes() + struct.pack(">H", len(instructions)) + instructions + fb + xb + yb
+    return data + b"\0" * ((-len(data)) % 4)
+
+
+def composite_bytes(components, bbox=(0, 0, 1000, 1000)):
+    """Composite glyph record: components = [(glyph id, dx, dy, transform)], transform = None (translation only),
+    a float (uniform scale), (sx, sy) or (a, b, c, d)."""
+    out = struct.pack(">hhhhh", -1, *bbox)
+    for k, (gid, dx, dy, tr) in enumerate(components):
+        fl = 0x0002  # ARGS_ARE_XY
+        words = not (-128 <= dx <= 127 and -128 <= dy <= 127)
+        if words:
+            fl |= 0x0001
+        if k + 1 < len(components):
+            fl |= 0x0020
+        f2 = lambda v: struct.pack(">h", int(round(v * 16384)))
+        tail = b""
+        if tr is not None:
+            if isinstance(tr, (int, float)):
+                fl |= 0x0008
+                tail = f2(tr)
+            elif len(tr) == 2:
+                fl |= 0x0040
+                tail = f2(tr[0]) + f2(tr[1])
+            else:
+                fl |= 0x0080
+                tail = b"".join(f2(v) for v in tr)
+        out += struct.pack(">HH", fl, gid) + (struct.pack(">hh", dx, dy) if words else struct.pack(">bb", dx, dy)) + tail
+    return out + b"\0" * ((-len(out)) % 4)
+
+
+def build_font(codepoints, strokes_for, seed=0xB200, family="Synth B200", cmap_format=4, many_to_one=None, records=None,
+               extra_records=(), compact=False):
     """codepoints: ascending BMP code points (no surrogates, no 0xFFFF); strokes_for(cp) -> K.
-    Glyph id i+1 belongs to codepoints[i]; glyph 0 is an empty .notdef."""
+    Glyph id i+1 belongs to codepoints[i]; glyph 0 is an empty .notdef.
+    records: explicit glyf records for the code points instead of generated strokes; extra_records: further records
+    (components of composites) that get the glyph ids after the mapped ones; compact: generated strokes use the
+    compact glyf encodings."""
     cps = [int(c) for c in codepoints]
     assert cps == sorted(set(cps)) and all(0 <= c < 0xFFFF and not 0xD800 <= c <= 0xDFFF for c in cps)
-    n_glyphs = len(cps) + 1
+    n_glyphs = len(cps) + 1 + len(extra_records)
     assert n_glyphs <= 0xFFFF
     rng = np.random.default_rng(seed)
     glyf = [b""]
     advances = [500]
-    for cp in cps:
-        glyf.append(_glyph_bytes(make_outline(rng, strokes_for(cp))))
+    for i, cp in enumerate(cps):
+        if records is not None:
+            glyf.append(records[i])
+        else:
+            contours = make_outline(rng, strokes_for(cp))
+            glyf.append(_glyph_bytes_compact(contours) if compact else _glyph_bytes(contours))
         advances.append(int(rng.integers(400, 1101)))
+    for rec in extra_records:
+        glyf.append(rec)
+        advances.append(600)
     offsets = np.zeros(n_glyphs + 1, dtype=np.uint64)
     offsets[1:] = np.cumsum([len(g) for g in glyf])
     glyf_table = b"".join(glyf)

@@ -410,6 +410,18 @@ def test_large_glyph_is_tiled_over_several_ctas(ctx):
     assert {0, 255} <= set(np.unique(out).tolist())
 
 
+def _glyph_bitmaps(renderer, batch):
+    """Per-glyph bitmaps of a rendered batch (a glyph-level batch keeps its bitmaps in slots sized on the host: the
+    bytes between them are undefined, so whole buffers are not comparable)."""
+    renderer.finalize_batch(batch)
+    return [None if (bm := batch.bitmap_of(i)) is None else bm.copy() for i in range(len(batch))]
+
+
+def _same_bitmaps(a, b):
+    return len(a) == len(b) and all((x is None and y is None) or (x is not None and y is not None and np.array_equal(x, y))
+                                    for x, y in zip(a, b))
+
+
 def test_many_batches_in_flight_from_threads(renderer):
     """submit/wait from several host threads on one context (reference: rayon workers, manager.rs:117-118)."""
     import threading
@@ -420,7 +432,7 @@ def test_many_batches_in_flight_from_threads(renderer):
     for cp in cps[:300]:
         ref_batch.add_glyph(font, cp)
     renderer.render_batch(ref_batch)
-    want = ref_batch.bitmaps().copy()
+    want = _glyph_bitmaps(renderer, ref_batch)
     errors = []
 
     def work():
@@ -431,7 +443,7 @@ def test_many_batches_in_flight_from_threads(renderer):
                     b.add_glyph(font, cp)
                 t = renderer.submit_batch(b)
                 renderer.wait_batch(t)
-                if not np.array_equal(b.bitmaps(), want):
+                if not _same_bitmaps(_glyph_bitmaps(renderer, b), want):
                     errors.append("mismatch")
         except Exception as e:  # noqa: BLE001
             errors.append(repr(e))
@@ -458,7 +470,7 @@ def test_prepared_submission_and_polling(renderer):
     deadline = time.time() + 30
     while not renderer.poll_batch(t):
         assert time.time() < deadline
-    assert np.array_equal(a.bitmaps(), b.bitmaps())
+    assert _same_bitmaps(_glyph_bitmaps(renderer, a), _glyph_bitmaps(renderer, b))
     with pytest.raises(V.B200Error):
         renderer.poll_batch(t)  # the ticket was consumed
     with pytest.raises(V.B200Error):
@@ -471,7 +483,7 @@ def test_device_resident_path_matches_host_path(ctx):
 
     font = V.FontFileEntry(path=O.FIRA)
     r = V.Renderer.new_dummy()  # only used to build the batch (host side)
-    r.set_flatten(on_device=False)
+    r.set_flatten("host")
     batch = r.new_batch()
     for cp in font.codepoints().tolist()[:500]:
         batch.add_glyph(font, cp)
@@ -495,7 +507,7 @@ def test_device_resident_path_matches_host_path(ctx):
 def _both_batches(font, cps):
     r = V.Renderer.new_dummy()  # host side only: builds the batches
     dev_batch = r.new_batch()
-    r.set_flatten(on_device=False)
+    r.set_flatten("host")
     host_batch = r.new_batch()
     for cp in cps:
         assert dev_batch.add_glyph(font, cp) == host_batch.add_glyph(font, cp)

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
         for name in declared:
             assert hasattr(lib, name), f"{header}: {name} not exported"
         assert declared == set(table), (header, declared ^ set(table))
-    assert N.sdf.b200sdf_abi_version() == 1
+    assert N.sdf.b200sdf_abi_version() == 2
 
 
 def test_no_cuda_device_fails_loudly():
@@ -120,7 +120,7 @@ def test_frames_and_segments_match_oracle_fira(fira):
     """Host flattening: glyph frames bit-exact; the f32 segment buffer is the oracle's f64 segments, origin-relative."""
     f, o = fira
     r = V.Renderer(dummy=True)
-    r.set_flatten(on_device=False)
+    r.set_flatten("host")
     batch = r.new_batch()
     cps = f.codepoints().tolist()
     for cp in cps:

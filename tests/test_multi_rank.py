@@ -18,7 +18,10 @@ def test_sharded_ranks_cover_the_job(world):
     line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
     assert res["ok"] and res["world"] == world and res["files"] == 512
-    assert sum(res["per_rank_blocks"]) == 512 and max(res["per_rank_blocks"]) - min(res["per_rank_blocks"]) <= 1
+    assert sum(res["per_rank_blocks"]) == 512
+    # shards are balanced by estimated cost (LPT over font x block tasks), not by block count
+    costs = res["per_rank_cost"]
+    assert max(costs) <= 1.1 * sum(costs) / world, costs
 
 
 def test_reference_arm_prints_contract_line():

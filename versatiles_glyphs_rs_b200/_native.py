@@ -127,7 +127,31 @@ class BatchGlyph(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "glyphs", "bitmaps", "pixels", "segments", "pairs", "pbf_bytes", "blocks",
-        "outline_ns", "submit_ns", "wait_ns", "encode_ns", "write_ns", "wall_ns", "submits", "workers")]
+        "outline_ns", "submit_ns", "wait_ns", "encode_ns", "write_ns", "wall_ns", "submits", "workers",
+        "handed_back", "h2d_bytes", "cost_total", "cost_shard")]
+
+
+class GlyphPart(C.Structure):
+    _fields_ = [("font", C.c_uint32), ("glyf_off", C.c_uint32), ("glyf_len", C.c_uint32), ("ox", C.c_float), ("oy", C.c_float)]
+
+
+class GlyphReq(C.Structure):
+    _fields_ = [
+        ("kind", C.c_uint32), ("src_off", C.c_uint32), ("src_cnt", C.c_uint32), ("seg_cnt", C.c_uint32),
+        ("width", C.c_uint32), ("height", C.c_uint32), ("x0", C.c_int32), ("y0", C.c_int32),
+        ("scale", C.c_double), ("dx", C.c_double), ("out_off", C.c_uint64),
+        ("out_cap", C.c_uint32), ("curve_off", C.c_uint32), ("curve_cap", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class GlyphFrame(C.Structure):
+    _fields_ = [("x0", C.c_int32), ("y0", C.c_int32), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("seg_cnt", C.c_uint32), ("status", C.c_uint32)]
+
+
+KIND_GLYF = 2
+GLYPH_OK, GLYPH_EMPTY, GLYPH_NEEDS_HOST, GLYPH_BAD_REQUEST = 0, 1, 2, 3
+TILE_BINS = 8
 
 
 # name -> (restype, argtypes); the single source of truth for "every symbol the headers declare"
@@ -154,6 +178,15 @@ SDF_SYMBOLS = {
     "b200sdf_plan_outline_tiles_ex": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p,
                                                 C.c_uint32, u32p, u64p]),
     "b200sdf_render_outlines_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "b200sdf_font_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u32p]),
+    "b200sdf_glyph_tile_bound": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+    "b200sdf_submit_glyphs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                        C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
+    "b200sdf_render_glyphs_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                               C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
+                                               C.c_void_p, C.c_void_p]),
+    "b200sdf_decode_glyphs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
+                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, u32p]),
     "b200sdf_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, f64p, f64p]),
     "b200sdf_launch_count": (C.c_uint64, [C.c_void_p]),
 }
@@ -195,6 +228,14 @@ HOST_SYMBOLS = {
     "vgb_batch_total_segments": (C.c_uint64, [C.c_void_p]),
     "vgb_batch_fallback_glyphs": (C.c_uint32, [C.c_void_p]),
     "vgb_renderer_set_flatten": (None, [C.c_void_p, C.c_int]),
+    "vgb_renderer_flatten": (C.c_int, [C.c_void_p]),
+    "vgb_batch_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vgb_batch_requests": (C.POINTER(GlyphReq), [C.c_void_p, u32p]),
+    "vgb_batch_parts": (C.POINTER(GlyphPart), [C.c_void_p, u32p]),
+    "vgb_batch_curve_slots": (C.c_uint32, [C.c_void_p]),
+    "vgb_batch_tile_cap": (C.c_uint32, [C.c_void_p]),
+    "vgb_batch_handed_back": (C.c_uint32, [C.c_void_p]),
+    "vgb_batch_glyph_bitmap": (u8p, [C.c_void_p, C.c_uint32, u64p]),
     "vgb_batch_bitmaps": (u8p, [C.c_void_p, u64p]),
     "vgb_batch_pairs": (C.c_uint64, [C.c_void_p]),
     "vgb_renderer_render_batch": (C.c_int, [C.c_void_p, C.c_void_p]),

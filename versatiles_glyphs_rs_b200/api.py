@@ -26,6 +26,16 @@ CURVE_DT = np.dtype(
 )
 assert OUTLINE_JOB_DT.itemsize == C.sizeof(N.OutlineJob) and CURVE_DT.itemsize == C.sizeof(N.Curve)
 
+GLYPH_PART_DT = np.dtype([("font", "<u4"), ("glyf_off", "<u4"), ("glyf_len", "<u4"), ("ox", "<f4"), ("oy", "<f4")])
+GLYPH_REQ_DT = np.dtype([
+    ("kind", "<u4"), ("src_off", "<u4"), ("src_cnt", "<u4"), ("seg_cnt", "<u4"), ("width", "<u4"), ("height", "<u4"),
+    ("x0", "<i4"), ("y0", "<i4"), ("scale", "<f8"), ("dx", "<f8"), ("out_off", "<u8"), ("out_cap", "<u4"),
+    ("curve_off", "<u4"), ("curve_cap", "<u4"), ("reserved", "<u4")])
+GLYPH_FRAME_DT = np.dtype([("x0", "<i4"), ("y0", "<i4"), ("width", "<u4"), ("height", "<u4"), ("seg_cnt", "<u4"), ("status", "<u4")])
+assert GLYPH_PART_DT.itemsize == C.sizeof(N.GlyphPart) and GLYPH_REQ_DT.itemsize == C.sizeof(N.GlyphReq) == 72
+assert GLYPH_FRAME_DT.itemsize == C.sizeof(N.GlyphFrame) == 24
+
+
 
 class B200Error(RuntimeError):
     pass
@@ -142,10 +152,17 @@ class Renderer:
         """b200sdf_ctx* of the CUDA renderer (None for dummy)."""
         return N.host.vgb_renderer_context(self._h)
 
-    def set_flatten(self, on_device: bool):
-        """Where batches created from now on flatten curves: on the device from curve records
-        (default) or on the host (upload flattened segments — the literal renderer_precise seam)."""
-        N.host.vgb_renderer_set_flatten(self._h, 1 if on_device else 0)
+    def set_flatten(self, mode):
+        """What batches created from now on send to the device: "glyf" / 2 = glyf record references (the device decodes,
+        records, measures, plans and renders; default of the CUDA renderer), True / "device" / 1 = curve records made on
+        the host, flattened on the device, False / "host" / 0 = segments flattened on the host (the literal
+        renderer_precise seam)."""
+        mode = {"glyf": 2, "device": 1, "host": 0}.get(mode, mode)
+        N.host.vgb_renderer_set_flatten(self._h, int(mode))
+
+    @property
+    def flatten(self) -> int:
+        return N.host.vgb_renderer_flatten(self._h)
 
     def render_glyph(self, font: FontFileEntry, index: int) -> Optional[PbfGlyph]:
         """reference src/render/renderer.rs:103-149"""
@@ -187,6 +204,11 @@ class Renderer:
         if rc < 0:
             raise B200Error(N.host_error())
         return rc == 1
+
+    def finalize_batch(self, batch: "GlyphBatch"):
+        """After wait_batch / poll_batch: take the frames a glyph-level batch got back from the device (no-op otherwise)."""
+        if N.host.vgb_batch_finalize(self._h, batch._h) != 0:
+            raise B200Error(N.host_error())
 
 
 class GlyphBatch:
@@ -280,8 +302,36 @@ class GlyphBatch:
         g = self.glyph_info(i)
         if not g.has_bitmap:
             return None
-        n = g.bm_width * g.bm_height
-        return self.bitmaps()[g.out_off : g.out_off + n].reshape(g.bm_height, g.bm_width)
+        n = C.c_uint64()
+        p = N.host.vgb_batch_glyph_bitmap(self._h, i, C.byref(n))
+        return np.ctypeslib.as_array(p, shape=(n.value,)).reshape(g.bm_height, g.bm_width)
+
+    # ---- glyph-level batches (the device decodes glyf records) ----
+    def requests(self) -> np.ndarray:
+        n = C.c_uint32()
+        p = N.host.vgb_batch_requests(self._h, C.byref(n))
+        if n.value == 0:
+            return np.zeros(0, dtype=GLYPH_REQ_DT)
+        return np.frombuffer(C.string_at(p, n.value * C.sizeof(N.GlyphReq)), dtype=GLYPH_REQ_DT).copy()
+
+    def parts(self) -> np.ndarray:
+        n = C.c_uint32()
+        p = N.host.vgb_batch_parts(self._h, C.byref(n))
+        if n.value == 0:
+            return np.zeros(0, dtype=GLYPH_PART_DT)
+        return np.frombuffer(C.string_at(p, n.value * C.sizeof(N.GlyphPart)), dtype=GLYPH_PART_DT).copy()
+
+    @property
+    def curve_slots(self) -> int:
+        return N.host.vgb_batch_curve_slots(self._h)
+
+    @property
+    def tile_cap(self) -> int:
+        return N.host.vgb_batch_tile_cap(self._h)
+
+    @property
+    def handed_back(self) -> int:
+        return N.host.vgb_batch_handed_back(self._h)
 
 
 class Writer:
@@ -364,6 +414,10 @@ class RenderStats:
     wall_ns: int = 0
     submits: int = 0
     workers: int = 0
+    handed_back: int = 0  # glyphs the device decoder returned to the host recorder
+    h2d_bytes: int = 0    # request / record / segment bytes the device read from host memory
+    cost_total: int = 0   # estimated cost of the whole job (0 when not sharded)
+    cost_shard: int = 0   # ... and of this shard
 
 
 class FontManager:
@@ -484,17 +538,79 @@ def decode_pbf(data: bytes):
 class SdfContext:
     """Direct view of the device ABI (include/b200sdf.h) over numpy buffers."""
 
-    def __init__(self, device: int = 0, n_slots: int = 2):
+    def __init__(self, device: int = 0, n_slots: int = 2, _borrowed=None):
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self._h = C.c_void_p(_borrowed)
+            return
         h = C.c_void_p()
         rc = N.sdf.b200sdf_create(device, n_slots, C.byref(h))
         if rc != 0:
             raise B200Error(f"b200sdf_create failed with code {rc}: a B200 (sm_100) GPU is required; there is no CPU fallback")
         self._h = h
 
+    @classmethod
+    def of_renderer(cls, renderer: "Renderer"):
+        """The renderer's own context (not owned): the fonts it uploaded are resident there."""
+        return cls(_borrowed=renderer.context)
+
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(self, "_owned", False):
             N.sdf.b200sdf_destroy(self._h)
-            self._h = None
+        self._h = None
+
+    # ---- glyph-level path (device glyf decoding) ----
+    def font_upload(self, glyf: bytes) -> int:
+        h = C.c_uint32()
+        buf = np.frombuffer(glyf, dtype=np.uint8)
+        rc = N.sdf.b200sdf_font_upload(self._h, buf.ctypes.data if len(buf) else None, len(buf), C.byref(h))
+        if rc != 0:
+            raise B200Error(f"b200sdf_font_upload: {rc}: {self.last_error()}")
+        return h.value
+
+    def decode_glyphs(self, reqs: np.ndarray, parts: np.ndarray, curve_slots: int, curves: Optional[np.ndarray] = None, n_seg: int = 0):
+        """b200sdf_decode_glyphs -> (frames, outline jobs, curve scratch, tiles per cost class).  curves / n_seg: the
+        host-recorded arrays CURVES / SEGMENTS requests index."""
+        reqs = np.ascontiguousarray(reqs, dtype=GLYPH_REQ_DT)
+        parts = np.ascontiguousarray(parts, dtype=GLYPH_PART_DT)
+        hc = np.zeros(0, dtype=CURVE_DT) if curves is None else np.ascontiguousarray(curves, dtype=CURVE_DT)
+        frames = np.zeros(len(reqs), dtype=GLYPH_FRAME_DT)
+        jobs = np.zeros(len(reqs), dtype=OUTLINE_JOB_DT)
+        curves = np.zeros(max(1, curve_slots), dtype=CURVE_DT)
+        bins = np.zeros(N.TILE_BINS, dtype=np.uint32)
+        rc = N.sdf.b200sdf_decode_glyphs(self._h, reqs.ctypes.data, len(reqs), parts.ctypes.data, len(parts),
+                                         hc.ctypes.data if len(hc) else None, len(hc), n_seg, curve_slots, frames.ctypes.data, jobs.ctypes.data, curves.ctypes.data, bins.ctypes.data_as(N.u32p))
+        if rc != 0:
+            raise B200Error(f"b200sdf_decode_glyphs: {rc}: {self.last_error()}")
+        return frames, jobs, curves[:curve_slots], bins
+
+    def render_glyphs(self, reqs: np.ndarray, parts: np.ndarray, curve_slots: int, tile_cap: int, out_bytes: int,
+                      curves: Optional[np.ndarray] = None, segs: Optional[np.ndarray] = None):
+        """b200sdf_submit_glyphs + b200sdf_wait over (pageable) host buffers -> (frames, bitmaps)."""
+        reqs = np.ascontiguousarray(reqs, dtype=GLYPH_REQ_DT)
+        parts = np.ascontiguousarray(parts, dtype=GLYPH_PART_DT)
+        curves = np.zeros(0, dtype=CURVE_DT) if curves is None else np.ascontiguousarray(curves, dtype=CURVE_DT)
+        segs = np.zeros((0, 4), dtype=np.float32) if segs is None else np.ascontiguousarray(segs, dtype=np.float32).reshape(-1, 4)
+        frames = np.zeros(max(1, len(reqs)), dtype=GLYPH_FRAME_DT)
+        out = np.zeros(max(out_bytes, 1), dtype=np.uint8)
+        t = C.c_uint64()
+        rc = N.sdf.b200sdf_submit_glyphs(self._h, reqs.ctypes.data, len(reqs), parts.ctypes.data, len(parts),
+                                         curves.ctypes.data if len(curves) else None, len(curves),
+                                         segs.ctypes.data if len(segs) else None, len(segs), curve_slots, tile_cap,
+                                         frames.ctypes.data, out.ctypes.data, out_bytes, C.byref(t))
+        if rc == 0:
+            rc = N.sdf.b200sdf_wait(self._h, t.value)
+        if rc != 0:
+            raise B200Error(f"b200sdf_submit_glyphs: {rc}: {self.last_error()}")
+        return frames[: len(reqs)], out[:out_bytes]
+
+    def render_glyphs_device(self, d_reqs: int, n_reqs: int, d_parts: int, n_parts: int, d_curves: int, n_curves: int, d_segs: int,
+                             n_seg: int, curve_slots: int, tile_cap: int, d_frames: int, d_out: int, out_bytes: int, stream: int = 0,
+                             mid_event: int = 0):
+        rc = N.sdf.b200sdf_render_glyphs_device(self._h, d_reqs, n_reqs, d_parts, n_parts, d_curves, n_curves, d_segs, n_seg,
+                                                curve_slots, tile_cap, d_frames, d_out, out_bytes, stream, mid_event)
+        if rc != 0:
+            raise B200Error(f"b200sdf_render_glyphs_device: {rc}: {self.last_error()}")
 
     def last_error(self) -> str:
         return (N.sdf.b200sdf_last_error(self._h) or b"").decode()

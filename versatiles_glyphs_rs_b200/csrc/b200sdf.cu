@@ -85,6 +85,12 @@ struct Slot {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t done = nullptr;
 	DevBuf segs, curves, ojobs, tiles, out, seg_base;
+	// glyph-level submissions (b200sdf_submit_glyphs): staged copies of the request arrays when the caller's memory is
+	// not pinned, the device-written curve scratch, and the batch counters with their pinned mirror
+	DevBuf reqs, parts, frames, gcurves;
+	b200sdf::BatchCounters *counters = nullptr;   // device
+	b200sdf::BatchCounters *h_counters = nullptr; // pinned: copied back after the SDF kernel
+	bool check_overflow = false;
 	void *h_tiles = nullptr; // pinned staging: tile jobs
 	size_t h_tiles_cap = 0;
 	bool busy = false;
@@ -108,7 +114,20 @@ struct b200sdf_ctx {
 	cudaEvent_t epoch = nullptr; // B200SDF_GPU_TRACE
 	uint64_t epoch_host_ns = 0;
 	size_t hwm[5] = {0, 0, 0, 0, 0}; // largest per-batch buffer sizes seen (segments, curves, jobs, tiles, bitmaps)
+	size_t ghwm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // same for glyph-level submissions
+	// fonts resident in HBM (b200sdf_font_upload): glyf tables + the device-side tables the decoder indexes
+	struct FontBlob {
+		void *p = nullptr;
+		uint64_t len = 0;
+	};
+	std::vector<FontBlob> fonts;
+	const uint8_t **d_font_base = nullptr;
+	uint64_t *d_font_len = nullptr;
+	// scratch of the device-resident entry point (b200sdf_render_glyphs_device)
+	DevBuf dv_gcurves, dv_ojobs, dv_tiles;
+	b200sdf::BatchCounters *dv_counters = nullptr;
 };
+constexpr uint32_t kMaxFonts = 8192;
 
 namespace {
 
@@ -663,9 +682,13 @@ void b200sdf_destroy(b200sdf_ctx *ctx)
 	for (auto &s : ctx->slots) {
 		if (s.stream)
 			cudaStreamSynchronize(s.stream);
-		for (DevBuf *b : {&s.segs, &s.curves, &s.ojobs, &s.tiles, &s.out, &s.seg_base})
+		for (DevBuf *b : {&s.segs, &s.curves, &s.ojobs, &s.tiles, &s.out, &s.seg_base, &s.reqs, &s.parts, &s.frames, &s.gcurves})
 			if (b->p)
 				cudaFree(b->p);
+		if (s.counters)
+			cudaFree(s.counters);
+		if (s.h_counters)
+			cudaFreeHost(s.h_counters);
 		if (s.h_tiles)
 			b200sdf_free_pinned(s.h_tiles);
 		if (s.done)
@@ -675,6 +698,18 @@ void b200sdf_destroy(b200sdf_ctx *ctx)
 	}
 	if (ctx->d_peak)
 		cudaFree(ctx->d_peak);
+	for (auto &f : ctx->fonts)
+		if (f.p)
+			cudaFree(f.p);
+	for (DevBuf *b : {&ctx->dv_gcurves, &ctx->dv_ojobs, &ctx->dv_tiles})
+		if (b->p)
+			cudaFree(b->p);
+	if (ctx->d_font_base)
+		cudaFree((void *)ctx->d_font_base);
+	if (ctx->d_font_len)
+		cudaFree(ctx->d_font_len);
+	if (ctx->dv_counters)
+		cudaFree(ctx->dv_counters);
 	delete ctx;
 }
 
@@ -816,6 +851,22 @@ int b200sdf_submit_planned(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint32
 	return submit_planned(ctx, none, curves, n_curves, segs, n_seg, jobs, n_jobs, out, out_bytes, ticket, tiles, n_tiles);
 }
 
+namespace {
+// glyph-level batches: the device reports a tile list that was too short through the counters' mirror
+int finish_slot(b200sdf_ctx *ctx, Slot &s, cudaError_t e, const char *what)
+{
+	const bool overflow = e == cudaSuccess && s.check_overflow && s.h_counters && s.h_counters->overflow != 0;
+	s.check_overflow = false;
+	report_gpu_trace(ctx, s);
+	release_slot(ctx, s, 0);
+	if (e != cudaSuccess)
+		return fail_cuda(ctx, e, what);
+	if (overflow)
+		return fail_arg(ctx, "submit_glyphs: tile_cap too small for this batch (see b200sdf_glyph_tile_bound)");
+	return 0;
+}
+} // namespace
+
 int b200sdf_wait(b200sdf_ctx *ctx, uint64_t ticket)
 {
 	if (!ctx)
@@ -830,11 +881,7 @@ int b200sdf_wait(b200sdf_ctx *ctx, uint64_t ticket)
 	}
 	Slot &s = ctx->slots[si];
 	const cudaError_t e = cudaEventSynchronize(s.done);
-	report_gpu_trace(ctx, s);
-	release_slot(ctx, s, 0);
-	if (e != cudaSuccess)
-		return fail_cuda(ctx, e, "cudaEventSynchronize");
-	return 0;
+	return finish_slot(ctx, s, e, "cudaEventSynchronize");
 }
 
 int b200sdf_poll(b200sdf_ctx *ctx, uint64_t ticket)
@@ -853,11 +900,8 @@ int b200sdf_poll(b200sdf_ctx *ctx, uint64_t ticket)
 	const cudaError_t e = cudaEventQuery(s.done);
 	if (e == cudaErrorNotReady)
 		return 0;
-	report_gpu_trace(ctx, s);
-	release_slot(ctx, s, 0);
-	if (e != cudaSuccess)
-		return fail_cuda(ctx, e, "cudaEventQuery");
-	return 1;
+	const int rc = finish_slot(ctx, s, e, "cudaEventQuery");
+	return rc ? rc : 1;
 }
 
 int b200sdf_render(b200sdf_ctx *ctx, const b200sdf_segment *segs, uint32_t n_seg, const b200sdf_glyph_job *jobs,
@@ -973,6 +1017,410 @@ int b200sdf_measure_fp32_peak(b200sdf_ctx *ctx, int reps, double *tflops, double
 	*tflops = flop / (best * 1e-3) / 1e12;
 	if (ms_out)
 		*ms_out = best;
+	return 0;
+}
+
+/* ---- glyph-level path: glyf decoding, metrics and tile planning on the device ---------------------- */
+namespace {
+
+uint32_t persistent_grid(uint32_t n_reqs)
+{
+	// one wave of resident CTAs at most; small batches do not need the whole machine
+	const uint64_t want = std::max<uint64_t>(kSMs, (uint64_t)n_reqs * 2u);
+	return (uint32_t)std::min<uint64_t>((uint64_t)kSMs * B200SDF_MIN_CTAS, want);
+}
+
+uint32_t glyph_cost_cap()
+{
+	static const uint32_t v = [] { // B200SDF_GLYPH_COST_CAP: tuning knob (item x segment units per tile job)
+		const char *e = std::getenv("B200SDF_GLYPH_COST_CAP");
+		const long x = e ? std::atol(e) : 0;
+		return (uint32_t)(x >= 1024 ? x : 131072);
+	}();
+	return v;
+}
+constexpr uint32_t kGlyphMinItems = 8;
+
+void launch_glyph_pipeline(const b200sdf::DecodeParams &P, const void *d_segs, uint8_t *d_out, cudaStream_t stream,
+                           cudaEvent_t mid)
+{
+	using namespace b200sdf;
+	cudaMemsetAsync(P.counters, 0, sizeof(BatchCounters), stream);
+	glyf_decode_kernel<<<(P.n_reqs + kGlyfWarps - 1) / kGlyfWarps, kGlyfThreads, 0, stream>>>(P);
+	if (mid)
+		cudaEventRecord(mid, stream);
+	sdf_tiles_persistent_kernel<<<persistent_grid(P.n_reqs), kThreads, 0, stream>>>(
+	    reinterpret_cast<const float4 *>(d_segs), P.curves, P.ojobs, P.tiles, P.tile_cap, P.counters, d_out);
+}
+
+int ensure_font_tables(b200sdf_ctx *ctx)
+{
+	if (ctx->d_font_base)
+		return 0;
+	CU_TRY(ctx, cudaMalloc((void **)&ctx->d_font_base, kMaxFonts * sizeof(void *)));
+	CU_TRY(ctx, cudaMalloc((void **)&ctx->d_font_len, kMaxFonts * sizeof(uint64_t)));
+	CU_TRY(ctx, cudaMemset((void *)ctx->d_font_base, 0, kMaxFonts * sizeof(void *)));
+	CU_TRY(ctx, cudaMemset(ctx->d_font_len, 0, kMaxFonts * sizeof(uint64_t)));
+	return 0;
+}
+
+// plain (synchronising) growth for the context-wide scratch of the device-resident entry point
+int grow_plain(b200sdf_ctx *ctx, DevBuf &b, size_t need)
+{
+	if (need <= b.cap)
+		return 0;
+	if (b.p)
+		cudaFree(b.p);
+	b.p = nullptr, b.cap = 0;
+	const size_t n = grown(need, 0);
+	cudaError_t e = cudaMalloc(&b.p, n);
+	if (e != cudaSuccess)
+		return fail_cuda(ctx, e, "cudaMalloc");
+	b.cap = n;
+	return 0;
+}
+
+} // namespace
+
+int b200sdf_font_upload(b200sdf_ctx *ctx, const uint8_t *glyf, uint64_t len, uint32_t *handle)
+{
+	if (!ctx || !handle || (len && !glyf))
+		return B200SDF_E_ARG;
+	CU_TRY(ctx, cudaSetDevice(ctx->device));
+	int rc = ensure_font_tables(ctx);
+	if (rc)
+		return rc;
+	void *d = nullptr;
+	CU_TRY(ctx, cudaMalloc(&d, (size_t)len + 16)); // the decoder reads at most one byte past a checked position
+	if (len)
+		CU_TRY(ctx, cudaMemcpy(d, glyf, (size_t)len, cudaMemcpyHostToDevice));
+	CU_TRY(ctx, cudaMemset((uint8_t *)d + len, 0, 16));
+	uint32_t h;
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		if (ctx->fonts.size() >= kMaxFonts) {
+			cudaFree(d);
+			ctx->err = "font_upload: too many fonts resident on this context";
+			return B200SDF_E_NOMEM;
+		}
+		h = (uint32_t)ctx->fonts.size();
+		b200sdf_ctx::FontBlob fb;
+		fb.p = d, fb.len = len;
+		ctx->fonts.push_back(fb);
+	}
+	const void *dp = d;
+	CU_TRY(ctx, cudaMemcpy((void *)(ctx->d_font_base + h), &dp, sizeof(void *), cudaMemcpyHostToDevice));
+	CU_TRY(ctx, cudaMemcpy(ctx->d_font_len + h, &len, sizeof(uint64_t), cudaMemcpyHostToDevice));
+	*handle = h;
+	return 0;
+}
+
+uint32_t b200sdf_glyph_tile_bound(uint32_t width, uint32_t height)
+{
+	// plan_tiles_dev: at most ceil(nx / min_items) column strips x ny rows of rectangles, whatever the glyph costs
+	const uint32_t nx = (width + B200SDF_TILE_W - 1) / B200SDF_TILE_W, ny = (height + B200SDF_TILE_H - 1) / B200SDF_TILE_H;
+	return std::max(1u, ((nx + kGlyphMinItems - 1) / kGlyphMinItems) * ny);
+}
+
+int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint32_t n_reqs, const b200sdf_glyph_part *parts,
+                          uint32_t n_parts, const b200sdf_curve *curves, uint32_t n_curves, const b200sdf_segment *segs,
+                          uint32_t n_seg, uint32_t curve_slots, uint32_t tile_cap, b200sdf_glyph_frame *frames, uint8_t *out,
+                          uint64_t out_bytes, uint64_t *ticket)
+{
+	using namespace b200sdf;
+	if (!ctx || !ticket)
+		return B200SDF_E_ARG;
+	if ((n_reqs && (!reqs || !frames)) || (n_parts && !parts) || (n_curves && !curves) || (n_seg && !segs) || (out_bytes && !out))
+		return fail_arg(ctx, "submit_glyphs: null buffer");
+	const size_t si = acquire_slot(ctx);
+	Slot &s = ctx->slots[si];
+	cudaError_t e = cudaSetDevice(ctx->device);
+	if (e != cudaSuccess)
+		return release_slot(ctx, s, fail_cuda(ctx, e, "cudaSetDevice"));
+	int rc = ensure_font_tables(ctx);
+	if (rc)
+		return release_slot(ctx, s, rc);
+	if (!s.counters) {
+		if ((e = cudaMalloc((void **)&s.counters, sizeof(BatchCounters))) != cudaSuccess ||
+		    (e = cudaHostAlloc((void **)&s.h_counters, sizeof(BatchCounters), cudaHostAllocPortable)) != cudaSuccess)
+			return release_slot(ctx, s, fail_cuda(ctx, e, "cudaMalloc(counters)"));
+		std::memset(s.h_counters, 0, sizeof(BatchCounters));
+	}
+	if (tile_cap == 0)
+		tile_cap = 1;
+	// what has to exist on the device: [0] segments [1] host curves [2] requests [3] parts [4] frames [5] bitmaps
+	// (each only when the caller's buffer is not pinned + mapped), [6] curve scratch [7] outline jobs, tiles
+	size_t need[9] = {(size_t)n_seg * sizeof(b200sdf_segment), (size_t)n_curves * sizeof(b200sdf_curve),
+	                  (size_t)n_reqs * sizeof(b200sdf_glyph_req), (size_t)n_parts * sizeof(b200sdf_glyph_part),
+	                  (size_t)n_reqs * sizeof(b200sdf_glyph_frame), (size_t)out_bytes,
+	                  (size_t)std::max(1u, curve_slots) * sizeof(b200sdf_curve), (size_t)tile_cap * kTileBins * sizeof(b200sdf_tile_job),
+	                  (size_t)n_reqs * sizeof(b200sdf_outline_job)};
+	const bool zc = zero_copy_mode() == 1;
+	const void *k_reqs = zc && n_reqs ? pinned_registry().device_ptr(reqs, need[2]) : nullptr;
+	const void *k_parts = zc && n_parts ? pinned_registry().device_ptr(parts, need[3]) : nullptr;
+	void *k_frames = zc && n_reqs ? pinned_registry().device_ptr(frames, need[4]) : nullptr;
+	void *k_out = zero_copy_mode() != 0 && out_bytes ? pinned_registry().device_ptr(out, need[5]) : nullptr;
+	const void *k_hcurves = zc && n_curves ? pinned_registry().device_ptr(curves, need[1]) : nullptr;
+	if (k_hcurves)
+		need[1] = 0;
+	if (k_reqs)
+		need[2] = 0;
+	if (k_parts)
+		need[3] = 0;
+	if (k_frames)
+		need[4] = 0;
+	if (k_out)
+		need[5] = 0;
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		for (int k = 0; k < 9; ++k) {
+			if (need[k] == 0)
+				continue;
+			size_t r = (size_t)64 << 10;
+			while (r < need[k])
+				r <<= 1;
+			ctx->ghwm[k] = std::max(ctx->ghwm[k], r);
+			need[k] = ctx->ghwm[k];
+		}
+	}
+	// the tile regions are addressed as bin * tile_cap: keep the stride the caller asked for, the allocation may be larger
+	if ((rc = grow_device(ctx, s.segs, need[0], s.stream)) || (rc = grow_device(ctx, s.curves, need[1], s.stream)) ||
+	    (rc = grow_device(ctx, s.reqs, need[2], s.stream)) || (rc = grow_device(ctx, s.parts, need[3], s.stream)) ||
+	    (rc = grow_device(ctx, s.frames, need[4], s.stream)) || (rc = grow_device(ctx, s.out, need[5], s.stream)) ||
+	    (rc = grow_device(ctx, s.gcurves, need[6], s.stream)) || (rc = grow_device(ctx, s.tiles, need[7], s.stream)) ||
+	    (rc = grow_device(ctx, s.ojobs, need[8], s.stream)))
+		return release_slot(ctx, s, rc);
+#define SUB_TRY(call)                                                \
+	do {                                                             \
+		cudaError_t e_ = (call);                                     \
+		if (e_ != cudaSuccess)                                       \
+			return release_slot(ctx, s, fail_cuda(ctx, e_, #call));  \
+	} while (0)
+	if (n_seg)
+		SUB_TRY(cudaMemcpyAsync(s.segs.p, segs, (size_t)n_seg * sizeof(b200sdf_segment), cudaMemcpyHostToDevice, s.stream));
+	if (n_curves && !k_hcurves) {
+		SUB_TRY(cudaMemcpyAsync(s.curves.p, curves, (size_t)n_curves * sizeof(b200sdf_curve), cudaMemcpyHostToDevice, s.stream));
+		k_hcurves = s.curves.p;
+	}
+	if (n_reqs && !k_reqs) {
+		SUB_TRY(cudaMemcpyAsync(s.reqs.p, reqs, (size_t)n_reqs * sizeof(b200sdf_glyph_req), cudaMemcpyHostToDevice, s.stream));
+		k_reqs = s.reqs.p;
+	}
+	if (n_parts && !k_parts) {
+		SUB_TRY(cudaMemcpyAsync(s.parts.p, parts, (size_t)n_parts * sizeof(b200sdf_glyph_part), cudaMemcpyHostToDevice, s.stream));
+		k_parts = s.parts.p;
+	}
+	static const bool gpu_trace = std::getenv("B200SDF_GPU_TRACE") != nullptr;
+	if (n_reqs) {
+		if (gpu_trace) {
+			if (!s.t0) {
+				cudaEventCreate(&s.t0);
+				cudaEventCreate(&s.t1);
+			}
+			{
+				std::lock_guard<std::mutex> g(ctx->mu);
+				if (!ctx->epoch) {
+					cudaEventCreate(&ctx->epoch);
+					cudaEventRecord(ctx->epoch, s.stream);
+					ctx->epoch_host_ns = now_ns_mono();
+				}
+			}
+			s.host_submit_ns = now_ns_mono();
+			s.traced_tiles = n_reqs;
+			cudaEventRecord(s.t0, s.stream);
+		}
+		DecodeParams P;
+		P.reqs = reinterpret_cast<const b200sdf_glyph_req *>(k_reqs);
+		P.n_reqs = n_reqs;
+		P.parts = reinterpret_cast<const b200sdf_glyph_part *>(k_parts);
+		P.n_parts = n_parts;
+		P.font_base = ctx->d_font_base;
+		P.font_len = ctx->d_font_len;
+		{
+			std::lock_guard<std::mutex> g(ctx->mu);
+			P.n_fonts = (uint32_t)ctx->fonts.size();
+		}
+		P.host_curves = reinterpret_cast<const b200sdf_curve *>(k_hcurves);
+		P.n_host_curves = n_curves;
+		P.n_host_segs = n_seg;
+		P.curves = reinterpret_cast<b200sdf_curve *>(s.gcurves.p);
+		P.curve_slots = curve_slots;
+		P.ojobs = reinterpret_cast<b200sdf_outline_job *>(s.ojobs.p);
+		P.frames = reinterpret_cast<b200sdf_glyph_frame *>(k_frames ? k_frames : s.frames.p);
+		P.tiles = reinterpret_cast<b200sdf_tile_job *>(s.tiles.p);
+		P.tile_cap = tile_cap;
+		P.out_bytes = out_bytes;
+		P.counters = s.counters;
+		P.cost_cap = glyph_cost_cap();
+		P.min_items = kGlyphMinItems;
+		uint8_t *d_out = reinterpret_cast<uint8_t *>(k_out ? k_out : s.out.p);
+		launch_glyph_pipeline(P, s.segs.p, d_out, s.stream, nullptr);
+		SUB_TRY(cudaGetLastError());
+		if (!k_frames)
+			SUB_TRY(cudaMemcpyAsync(frames, s.frames.p, (size_t)n_reqs * sizeof(b200sdf_glyph_frame), cudaMemcpyDeviceToHost, s.stream));
+		if (!k_out && out_bytes)
+			SUB_TRY(cudaMemcpyAsync(out, s.out.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, s.stream));
+		SUB_TRY(cudaMemcpyAsync(s.h_counters, s.counters, sizeof(BatchCounters), cudaMemcpyDeviceToHost, s.stream));
+		s.check_overflow = true;
+		if (s.t1 && s.traced_tiles)
+			cudaEventRecord(s.t1, s.stream);
+	}
+	SUB_TRY(cudaEventRecord(s.done, s.stream));
+#undef SUB_TRY
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		if (n_reqs)
+			ctx->launches += 2;
+		*ticket = ((uint64_t)s.generation << 8) | (uint64_t)si;
+	}
+	return 0;
+}
+
+int b200sdf_render_glyphs_device(b200sdf_ctx *ctx, const b200sdf_glyph_req *d_reqs, uint32_t n_reqs,
+                                 const b200sdf_glyph_part *d_parts, uint32_t n_parts, const b200sdf_curve *d_curves,
+                                 uint32_t n_curves, const b200sdf_segment *d_segs, uint32_t n_seg, uint32_t curve_slots,
+                                 uint32_t tile_cap, b200sdf_glyph_frame *d_frames, uint8_t *d_out, uint64_t out_bytes,
+                                 void *stream, void *mid_event)
+{
+	using namespace b200sdf;
+	if (!ctx)
+		return B200SDF_E_ARG;
+	if (n_reqs == 0)
+		return 0;
+	if (!d_reqs || !d_frames || (n_parts && !d_parts) || (out_bytes && !d_out))
+		return fail_arg(ctx, "render_glyphs_device: null device pointer");
+	CU_TRY(ctx, cudaSetDevice(ctx->device));
+	int rc = ensure_font_tables(ctx);
+	if (rc)
+		return rc;
+	if (tile_cap == 0)
+		tile_cap = 1;
+	// context-wide scratch: grown outside any timed loop by the first call of a given size (synchronising)
+	if ((rc = grow_plain(ctx, ctx->dv_gcurves, (size_t)std::max(1u, curve_slots) * sizeof(b200sdf_curve))) ||
+	    (rc = grow_plain(ctx, ctx->dv_ojobs, (size_t)n_reqs * sizeof(b200sdf_outline_job))) ||
+	    (rc = grow_plain(ctx, ctx->dv_tiles, (size_t)tile_cap * kTileBins * sizeof(b200sdf_tile_job))))
+		return rc;
+	if (!ctx->dv_counters)
+		CU_TRY(ctx, cudaMalloc((void **)&ctx->dv_counters, sizeof(BatchCounters)));
+	DecodeParams P;
+	P.reqs = d_reqs, P.n_reqs = n_reqs, P.parts = d_parts, P.n_parts = n_parts;
+	P.font_base = ctx->d_font_base, P.font_len = ctx->d_font_len;
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		P.n_fonts = (uint32_t)ctx->fonts.size();
+	}
+	P.host_curves = d_curves, P.n_host_curves = n_curves, P.n_host_segs = n_seg;
+	P.curves = reinterpret_cast<b200sdf_curve *>(ctx->dv_gcurves.p);
+	P.curve_slots = curve_slots;
+	P.ojobs = reinterpret_cast<b200sdf_outline_job *>(ctx->dv_ojobs.p);
+	P.frames = d_frames;
+	P.tiles = reinterpret_cast<b200sdf_tile_job *>(ctx->dv_tiles.p);
+	P.tile_cap = tile_cap;
+	P.out_bytes = out_bytes;
+	P.counters = ctx->dv_counters;
+	P.cost_cap = glyph_cost_cap();
+	P.min_items = kGlyphMinItems;
+	launch_glyph_pipeline(P, d_segs, d_out, (cudaStream_t)stream, (cudaEvent_t)mid_event);
+	CU_TRY(ctx, cudaGetLastError());
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		ctx->launches += 2;
+	}
+	return 0;
+}
+
+int b200sdf_decode_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint32_t n_reqs, const b200sdf_glyph_part *parts,
+                          uint32_t n_parts, const b200sdf_curve *curves, uint32_t n_curves, uint32_t n_seg, uint32_t curve_slots,
+                          b200sdf_glyph_frame *frames, b200sdf_outline_job *jobs_out, b200sdf_curve *curves_out,
+                          uint32_t *tiles_per_bin)
+{
+	using namespace b200sdf;
+	if (!ctx)
+		return B200SDF_E_ARG;
+	if (n_reqs == 0)
+		return 0;
+	if (!reqs || !frames || (n_parts && !parts))
+		return fail_arg(ctx, "decode_glyphs: null buffer");
+	CU_TRY(ctx, cudaSetDevice(ctx->device));
+	int rc = ensure_font_tables(ctx);
+	if (rc)
+		return rc;
+	uint64_t tile_cap64 = 0, out_bytes = 0;
+	for (uint32_t i = 0; i < n_reqs; ++i) {
+		tile_cap64 += 64; // decode only: nothing is rendered, a generous fixed allowance per glyph
+		out_bytes = std::max<uint64_t>(out_bytes, reqs[i].out_off + reqs[i].out_cap);
+	}
+	const uint32_t tile_cap = (uint32_t)std::min<uint64_t>(tile_cap64, 1u << 24);
+	if (n_curves && !curves)
+		return fail_arg(ctx, "decode_glyphs: null curve array");
+	void *d_reqs = nullptr, *d_parts = nullptr, *d_frames = nullptr, *d_curves = nullptr, *d_ojobs = nullptr, *d_tiles = nullptr, *d_ctr = nullptr;
+	void *d_hcurves = nullptr;
+	cudaError_t e = cudaSuccess;
+	auto alloc = [&](void **p, size_t n) {
+		if (e == cudaSuccess)
+			e = cudaMalloc(p, std::max<size_t>(n, 16));
+	};
+	alloc(&d_reqs, (size_t)n_reqs * sizeof(b200sdf_glyph_req));
+	alloc(&d_parts, (size_t)n_parts * sizeof(b200sdf_glyph_part));
+	alloc(&d_frames, (size_t)n_reqs * sizeof(b200sdf_glyph_frame));
+	alloc(&d_curves, (size_t)std::max(1u, curve_slots) * sizeof(b200sdf_curve));
+	alloc(&d_ojobs, (size_t)n_reqs * sizeof(b200sdf_outline_job));
+	alloc(&d_tiles, (size_t)tile_cap * kTileBins * sizeof(b200sdf_tile_job));
+	alloc(&d_ctr, sizeof(BatchCounters));
+	alloc(&d_hcurves, (size_t)n_curves * sizeof(b200sdf_curve));
+	if (e == cudaSuccess && n_curves)
+		e = cudaMemcpy(d_hcurves, curves, (size_t)n_curves * sizeof(b200sdf_curve), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(d_reqs, reqs, (size_t)n_reqs * sizeof(b200sdf_glyph_req), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess && n_parts)
+		e = cudaMemcpy(d_parts, parts, (size_t)n_parts * sizeof(b200sdf_glyph_part), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemset(d_ctr, 0, sizeof(BatchCounters));
+	if (e == cudaSuccess)
+		e = cudaMemset(d_curves, 0, (size_t)std::max(1u, curve_slots) * sizeof(b200sdf_curve));
+	if (e == cudaSuccess) {
+		DecodeParams P;
+		P.reqs = reinterpret_cast<const b200sdf_glyph_req *>(d_reqs), P.n_reqs = n_reqs;
+		P.parts = reinterpret_cast<const b200sdf_glyph_part *>(d_parts), P.n_parts = n_parts;
+		P.font_base = ctx->d_font_base, P.font_len = ctx->d_font_len;
+		{
+			std::lock_guard<std::mutex> g(ctx->mu);
+			P.n_fonts = (uint32_t)ctx->fonts.size();
+		}
+		P.host_curves = reinterpret_cast<const b200sdf_curve *>(d_hcurves), P.n_host_curves = n_curves, P.n_host_segs = n_seg;
+		P.curves = reinterpret_cast<b200sdf_curve *>(d_curves), P.curve_slots = curve_slots;
+		P.ojobs = reinterpret_cast<b200sdf_outline_job *>(d_ojobs);
+		P.frames = reinterpret_cast<b200sdf_glyph_frame *>(d_frames);
+		P.tiles = reinterpret_cast<b200sdf_tile_job *>(d_tiles), P.tile_cap = tile_cap;
+		P.out_bytes = out_bytes;
+		P.counters = reinterpret_cast<BatchCounters *>(d_ctr);
+		P.cost_cap = glyph_cost_cap(), P.min_items = kGlyphMinItems;
+		glyf_decode_kernel<<<(n_reqs + kGlyfWarps - 1) / kGlyfWarps, kGlyfThreads>>>(P);
+		e = cudaGetLastError();
+		if (e == cudaSuccess)
+			e = cudaDeviceSynchronize();
+	}
+	if (e == cudaSuccess)
+		e = cudaMemcpy(frames, d_frames, (size_t)n_reqs * sizeof(b200sdf_glyph_frame), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && jobs_out)
+		e = cudaMemcpy(jobs_out, d_ojobs, (size_t)n_reqs * sizeof(b200sdf_outline_job), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && curves_out && curve_slots)
+		e = cudaMemcpy(curves_out, d_curves, (size_t)curve_slots * sizeof(b200sdf_curve), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && tiles_per_bin) {
+		BatchCounters h;
+		e = cudaMemcpy(&h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost);
+		for (int b = 0; b < kTileBins; ++b)
+			tiles_per_bin[b] = h.bin_count[b];
+	}
+	for (void *q : {d_reqs, d_parts, d_frames, d_curves, d_ojobs, d_tiles, d_ctr, d_hcurves})
+		if (q)
+			cudaFree(q);
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		ctx->launches++;
+	}
+	if (e != cudaSuccess)
+		return fail_cuda(ctx, e, "decode_glyphs");
 	return 0;
 }
 

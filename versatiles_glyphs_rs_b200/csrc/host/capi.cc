@@ -227,7 +227,7 @@ int vgb_renderer_render_glyph(const vgb_renderer *r, const vgb_font *f, uint32_t
 {
 	std::unique_ptr<GlyphBatch> batch = r->r->new_batch();
 	if (!batch->add_glyph(*f->e->face, codepoint))
-		return 0;
+		return batch->failed() ? fail(batch->failure()) : 0;
 	std::string err;
 	if (!r->r->render_batch(*batch, &err))
 		return fail(err);
@@ -241,7 +241,9 @@ void vgb_batch_free(vgb_batch *b) { delete b; }
 void vgb_batch_clear(vgb_batch *b) { b->b->clear(); }
 int vgb_batch_add_glyph(vgb_batch *b, const vgb_font *f, uint32_t codepoint)
 {
-	return b->b->add_glyph(*f->e->face, codepoint) ? 1 : 0;
+	if (b->b->add_glyph(*f->e->face, codepoint))
+		return 1;
+	return b->b->failed() ? fail(b->b->failure()) : 0;
 }
 int vgb_batch_add_rings(vgb_batch *b, uint32_t id, int32_t x0, int32_t y0, uint32_t width, uint32_t height, const double *xy,
                         const uint32_t *ring_start, uint32_t n_rings)
@@ -307,7 +309,43 @@ const b200sdf_curve *vgb_batch_curves(const vgb_batch *b, uint32_t *n_curves)
 }
 uint64_t vgb_batch_total_segments(const vgb_batch *b) { return b->b->total_segments(); }
 uint32_t vgb_batch_fallback_glyphs(const vgb_batch *b) { return b->b->fallback_glyphs(); }
-void vgb_renderer_set_flatten(vgb_renderer *r, int on_device) { r->r->set_flatten(on_device ? Flatten::Device : Flatten::Host); }
+void vgb_renderer_set_flatten(vgb_renderer *r, int mode)
+{
+	r->r->set_flatten(mode == 2 ? Flatten::Glyf : mode ? Flatten::Device : Flatten::Host);
+}
+int vgb_renderer_flatten(const vgb_renderer *r)
+{
+	return r->r->flatten() == Flatten::Glyf ? 2 : r->r->flatten() == Flatten::Device ? 1 : 0;
+}
+int vgb_batch_finalize(const vgb_renderer *r, vgb_batch *b)
+{
+	std::string err;
+	return b->b->finalize(*r->r, &err) ? 0 : fail(err);
+}
+const b200sdf_glyph_req *vgb_batch_requests(const vgb_batch *b, uint32_t *n)
+{
+	*n = b->b->mode() == Flatten::Glyf ? b->b->job_count() : 0;
+	return b->b->reqs();
+}
+const b200sdf_glyph_part *vgb_batch_parts(const vgb_batch *b, uint32_t *n)
+{
+	*n = b->b->part_count();
+	return b->b->parts();
+}
+uint32_t vgb_batch_curve_slots(const vgb_batch *b) { return b->b->curve_slots(); }
+uint32_t vgb_batch_tile_cap(const vgb_batch *b) { return b->b->tile_cap(); }
+uint32_t vgb_batch_handed_back(const vgb_batch *b) { return b->b->handed_back(); }
+const uint8_t *vgb_batch_glyph_bitmap(const vgb_batch *b, uint32_t i, uint64_t *len)
+{
+	*len = 0;
+	if (i >= b->b->glyphs().size())
+		return nullptr;
+	const BatchGlyph &g = b->b->glyphs()[i];
+	if (!g.has_bitmap)
+		return nullptr;
+	*len = (uint64_t)g.frame.width * g.frame.height;
+	return b->b->bitmap_of(g);
+}
 const uint8_t *vgb_batch_bitmaps(const vgb_batch *b, uint64_t *bytes)
 {
 	*bytes = b->b->bitmap_bytes();
@@ -494,6 +532,10 @@ int vgb_manager_render_glyphs(const vgb_manager *m, vgb_writer *w, const vgb_ren
 		stats->wall_ns = st.wall_ns;
 		stats->submits = st.submits;
 		stats->workers = st.workers;
+		stats->handed_back = st.handed_back;
+		stats->h2d_bytes = st.h2d_bytes;
+		stats->cost_total = st.cost_total;
+		stats->cost_shard = st.cost_shard;
 	}
 	return 0;
 }

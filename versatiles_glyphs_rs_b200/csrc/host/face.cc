@@ -51,7 +51,11 @@ bool Face::table(const char tag[4], Span &out) const
 	return false;
 }
 
-Face::Face() = default;
+Face::Face()
+{
+	static std::atomic<uint64_t> next{1};
+	uid_ = next.fetch_add(1);
+}
 Face::~Face() = default;
 
 std::unique_ptr<Face> Face::parse(std::vector<uint8_t> data)
@@ -626,6 +630,104 @@ void Face::outline_impl(Span g, int depth, const Transform &t, OutlineBuilder &b
 				break;
 		}
 	}
+}
+
+// outline_impl's walk with the simple-glyph arm replaced by "remember the record": returns false as soon as a
+// component carries anything but a translation (the caller then records the whole glyph on the host).
+bool Face::parts_impl(Span g, int depth, const Transform &t, std::vector<GlyfPart> &parts) const
+{
+	if (depth >= 32 || g.len < 10)
+		return true;
+	const size_t end = g.off + g.len;
+	const int16_t n_contours = i16(g.off);
+	size_t pos = g.off + 10;
+	if (n_contours > 0) {
+		const size_t nc = (size_t)n_contours;
+		if (pos + 2 * nc + 2 > end)
+			return true; // outline_impl: no callbacks
+		const uint32_t n_points = (uint32_t)u16(pos + 2 * (nc - 1)) + 1;
+		if (n_points == 1)
+			return true;
+		if (n_points > 2048) // B200SDF_GLYF_MAX_POINTS
+			return false;
+		GlyfPart p;
+		p.off = (uint32_t)(g.off - glyf_.off);
+		p.len = (uint32_t)g.len;
+		p.ox = t.e, p.oy = t.f;
+		p.points = n_points;
+		p.xmin = i16(g.off + 2), p.ymin = i16(g.off + 4), p.xmax = i16(g.off + 6), p.ymax = i16(g.off + 8);
+		parts.push_back(p);
+	} else if (n_contours < 0) {
+		enum : uint16_t { ARG_WORDS = 0x0001, ARGS_ARE_XY = 0x0002, HAVE_SCALE = 0x0008, MORE_COMPONENTS = 0x0020, HAVE_XY_SCALE = 0x0040, HAVE_2X2 = 0x0080 };
+		for (;;) {
+			if (pos + 4 > end)
+				return true;
+			const uint16_t fl = u16(pos), child = u16(pos + 2);
+			pos += 4;
+			Transform ct;
+			if (fl & ARG_WORDS) {
+				if (pos + 4 > end)
+					return true;
+				if (fl & ARGS_ARE_XY) {
+					ct.e = (float)i16(pos);
+					ct.f = (float)i16(pos + 2);
+				}
+				pos += 4;
+			} else {
+				if (pos + 2 > end)
+					return true;
+				if (fl & ARGS_ARE_XY) {
+					ct.e = (float)(int8_t)data_[pos];
+					ct.f = (float)(int8_t)data_[pos + 1];
+				}
+				pos += 2;
+			}
+			auto f2dot14 = [&](size_t q) { return (float)i16(q) / 16384.0f; };
+			if (fl & HAVE_2X2) {
+				if (pos + 8 > end)
+					return true;
+				ct.a = f2dot14(pos), ct.b = f2dot14(pos + 2), ct.c = f2dot14(pos + 4), ct.d = f2dot14(pos + 6);
+				pos += 8;
+			} else if (fl & HAVE_XY_SCALE) {
+				if (pos + 4 > end)
+					return true;
+				ct.a = f2dot14(pos), ct.d = f2dot14(pos + 2);
+				pos += 4;
+			} else if (fl & HAVE_SCALE) {
+				if (pos + 2 > end)
+					return true;
+				ct.a = f2dot14(pos);
+				ct.d = ct.a;
+				pos += 2;
+			}
+			Span cg;
+			if (glyph_range(child, cg)) {
+				const Transform ts = Transform::combine(t, ct);
+				if (!(ts.a == 1.f && ts.b == 0.f && ts.c == 0.f && ts.d == 1.f))
+					return false;
+				if (!parts_impl(cg, depth + 1, ts, parts))
+					return false;
+			}
+			if (!(fl & MORE_COMPONENTS))
+				break;
+		}
+	}
+	return true;
+}
+
+Face::GlyfPlan Face::glyf_parts(uint16_t gid, std::vector<GlyfPart> &parts) const
+{
+	if (glyf_.len == 0 || loca_.len == 0)
+		return cff_ ? GlyfPlan::Host : GlyfPlan::None; // outline_glyph's order: glyf, then CFF
+	Span g;
+	if (!glyph_range(gid, g))
+		return GlyfPlan::None;
+	const size_t before = parts.size();
+	if (!parts_impl(g, 0, Transform(), parts)) {
+		parts.resize(before);
+		return GlyfPlan::Host;
+	}
+	return parts.size() == before ? GlyfPlan::None : GlyfPlan::Parts;
 }
 
 bool Face::outline_glyph(uint16_t gid, OutlineBuilder &builder) const

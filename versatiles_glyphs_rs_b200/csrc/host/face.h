@@ -6,6 +6,7 @@
 // the reference's fixtures use them).
 #pragma once
 
+#include <atomic>
 #include <cstdint>
 #include <memory>
 #include <optional>
@@ -45,6 +46,26 @@ class Face {
 	// name table entry (first record with that id that decodes; UTF-16BE / Mac Roman), "" if none
 	std::string name(uint16_t name_id) const;
 
+	// ---- device-side glyf decoding (csrc/glyf_kernel.cuh) ----
+	// How outline_glyph(gid) can be handed to the device: as the simple-glyph records it is made of, each only
+	// translated (appended to `parts`), or not at all (scaled / rotated components, CFF outlines, more points than the
+	// decoder holds: the caller records the outline on the host), or there is nothing to draw.
+	enum class GlyfPlan { None, Parts, Host };
+	struct GlyfPart {
+		uint32_t off, len;   // byte range inside the glyf table
+		float ox, oy;        // translation (font units)
+		uint32_t points;     // numberOfPoints of the record
+		int16_t xmin, ymin, xmax, ymax; // the record's header bounding box (not trusted: the device checks the fit)
+	};
+	GlyfPlan glyf_parts(uint16_t glyph_id, std::vector<GlyfPart> &parts) const;
+	const uint8_t *glyf_data() const { return data_.data() + glyf_.off; }
+	size_t glyf_size() const { return glyf_.len; }
+	// process-wide unique number of this face (addresses are reused once a face is freed; this is not)
+	uint64_t uid() const { return uid_; }
+	// handle of this face's glyf table on a device context, remembered per face: tag = (owner id << 32) | (handle + 1)
+	uint64_t device_tag() const { return device_tag_.load(std::memory_order_acquire); }
+	void set_device_tag(uint64_t t) const { device_tag_.store(t, std::memory_order_release); }
+
   private:
 	struct Span {
 		size_t off = 0, len = 0;
@@ -78,6 +99,9 @@ class Face {
 	template <typename F> void enumerate(const CmapSubtable &s, F &&f) const;
 	bool glyph_range(uint16_t gid, Span &out) const;
 	void outline_impl(Span glyph, int depth, const Transform &t, OutlineBuilder &b) const;
+	bool parts_impl(Span glyph, int depth, const Transform &t, std::vector<GlyfPart> &parts) const;
+	mutable std::atomic<uint64_t> device_tag_{0};
+	uint64_t uid_ = 0;
 
 	std::vector<uint8_t> data_;
 	uint16_t upm_ = 0, num_glyphs_ = 0, num_hmetrics_ = 0;

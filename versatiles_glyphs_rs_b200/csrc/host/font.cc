@@ -79,6 +79,12 @@ bool GlyphBlock::render(const std::string &font_name, const Renderer &renderer, 
 {
 	std::unique_ptr<GlyphBatch> batch = renderer.acquire_batch();
 	fill_batch(*batch);
+	if (batch->failed()) {
+		if (err)
+			*err = batch->failure();
+		renderer.release_batch(std::move(batch));
+		return false;
+	}
 	const bool ok = renderer.render_batch(*batch, err);
 	if (ok)
 		out = encode_batch(font_name, *batch);
@@ -118,6 +124,43 @@ const std::vector<GlyphBlock> &FontWrapper::blocks() const
 	if (blocks_.empty())
 		blocks_ = get_blocks();
 	return blocks_;
+}
+
+const std::vector<uint64_t> &FontWrapper::block_costs() const
+{
+	const std::vector<GlyphBlock> &table = blocks();
+	std::lock_guard<std::mutex> g(blocks_mu_);
+	if (!block_costs_.empty())
+		return block_costs_;
+	std::vector<uint64_t> costs(table.size(), 0);
+	std::vector<Face::GlyfPart> parts;
+	for (size_t b = 0; b < table.size(); ++b) {
+		uint64_t c = 64; // an empty block still costs a file
+		for (uint32_t k = 0; k < GLYPH_BLOCK_SIZE; ++k) {
+			const FontFileEntry *f = table[b].font_of((uint8_t)k);
+			if (!f)
+				continue;
+			c += 40000; // per glyph: request, decode, encode
+			const auto gid = f->face->glyph_index(table[b].start_index() + k);
+			if (!gid)
+				continue;
+			parts.clear();
+			const Face::GlyfPlan plan = f->face->glyf_parts(*gid, parts);
+			if (plan == Face::GlyfPlan::Host) {
+				c += 600000; // no header to go by: a typical glyph
+				continue;
+			}
+			const double scale = (double)GLYPH_SIZE / (double)std::max<uint16_t>(1, f->face->units_per_em());
+			for (const Face::GlyfPart &p : parts) {
+				const double w = ((double)p.xmax - (double)p.xmin) * scale + 8.0, h = ((double)p.ymax - (double)p.ymin) * scale + 8.0;
+				const double area = std::min(std::max(w, 8.0), 4096.0) * std::min(std::max(h, 8.0), 4096.0);
+				c += (uint64_t)(area * (double)p.points * 8.0); // ~8 flattened segments per point
+			}
+		}
+		costs[b] = c;
+	}
+	block_costs_ = std::move(costs);
+	return block_costs_;
 }
 
 void FontWrapper::assign_blocks(GlyphBlock *const *blocks) const

@@ -114,6 +114,7 @@ class FontWrapper {
 	{
 		files_.push_back(std::move(file));
 		blocks_.clear(); // the block table is rebuilt on next use
+		block_costs_.clear();
 	}
 	bool add_paths(const std::vector<std::string> &sources, std::string *err);
 	const std::vector<std::unique_ptr<FontFileEntry>> &files() const { return files_; }
@@ -124,10 +125,15 @@ class FontWrapper {
 	// get_blocks() as a table owned by the wrapper: a pure function of the files, so it is built when first
 	// needed after the last add_file (i.e. at load time, like the parsed cmap) and reused by every render_glyphs
 	const std::vector<GlyphBlock> &blocks() const;
+	// Estimated rendering cost of each of the 256 blocks (pixel x segment pairs plus a per-glyph constant), from the glyf
+	// headers only: what FontManager::render_glyphs balances shards with.  Like blocks(), a pure function of the
+	// files, built when first needed.
+	const std::vector<uint64_t> &block_costs() const;
 
   private:
 	std::vector<std::unique_ptr<FontFileEntry>> files_;
 	mutable std::vector<GlyphBlock> blocks_;
+	mutable std::vector<uint64_t> block_costs_;
 	mutable std::mutex blocks_mu_;
 };
 
@@ -169,6 +175,9 @@ struct RenderStats {
 	// where the host time went, nanoseconds summed over workers (wall_ns: the whole call)
 	uint64_t outline_ns = 0, submit_ns = 0, wait_ns = 0, encode_ns = 0, write_ns = 0, wall_ns = 0;
 	uint64_t submits = 0, workers = 0;
+	uint64_t handed_back = 0;               // glyphs the device decoder returned to the host recorder
+	uint64_t h2d_bytes = 0;                 // bytes of glyph requests / records / segments the device read from host memory
+	uint64_t cost_total = 0, cost_shard = 0; // estimated cost of the whole job and of this shard (0 when not sharded)
 };
 
 class FontManager {

@@ -110,7 +110,7 @@ size_t gather_items(const GlyphBatch &batch, size_t g0, size_t g1, std::vector<R
 			const b200sdf_outline_job &j = batch.jobs()[b.job];
 			it.width = m.width, it.height = m.height;
 			it.left_zz = zigzag32(m.left), it.top_zz = zigzag32(m.top);
-			it.bitmap = batch.bitmaps() + j.out_off;
+			it.bitmap = batch.bitmap_of(b);
 			it.bitmap_len = (size_t)j.width * j.height;
 		} else {
 			it.width = it.height = 0;

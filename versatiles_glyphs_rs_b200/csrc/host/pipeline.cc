@@ -139,9 +139,11 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 {
 	// glibc serves allocations >= 128 KiB (every full block's PBF) with mmap: fresh pages, i.e. ~30 page faults per
 	// file, every call.  Keep such blocks on the heap, where the pages freed after one call are reused by the next.
-	// (Process-wide malloc tuning; VGB_KEEP_MALLOC_DEFAULTS=1 leaves the allocator alone.)
+	// (Process-wide malloc tuning, therefore only on request: VGB_TUNE_MALLOC=1.)
 	static const bool malloc_tuned = [] {
-		if (std::getenv("VGB_KEEP_MALLOC_DEFAULTS"))
+		// opt-in (VGB_TUNE_MALLOC=1): a library entry point does not change process-wide allocator settings on its own
+		const char *e = std::getenv("VGB_TUNE_MALLOC");
+		if (!e || e[0] != '1')
 			return false;
 #if defined(__GLIBC__)
 		mallopt(M_MMAP_THRESHOLD, 64 << 20);
@@ -178,8 +180,40 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	std::vector<std::unique_ptr<BlockState[]>> fonts_blocks;
 	std::vector<Todo> tasks;
 	tasks.reserve(fonts_.size() * kBlocks + 64);
-	uint32_t index = 0;
 	size_t total_glyphs = 0;
+	// Shards: longest-processing-time-first over the (font, block) tasks by estimated cost (the task list
+	// is manager.rs:88-97).  Every rank computes the same assignment from the same cost tables and keeps its own part.
+	std::vector<uint16_t> owner; // owner[font * 256 + block]
+	uint64_t cost_total = 0, cost_mine = 0;
+	if (n_shards > 1) {
+		struct Item {
+			uint64_t cost;
+			uint32_t index;
+		};
+		std::vector<Item> items;
+		items.reserve(fonts_.size() * kBlocks);
+		uint32_t fi = 0;
+		for (const auto &kv : fonts_) {
+			const std::vector<uint64_t> &costs = kv.second.block_costs();
+			for (uint32_t i = 0; i < kBlocks; ++i)
+				items.push_back(Item{costs[i], fi * kBlocks + i});
+			++fi;
+		}
+		std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.cost > b.cost; });
+		std::vector<uint64_t> load(n_shards, 0);
+		owner.assign(items.size(), 0);
+		for (const Item &it : items) {
+			uint32_t best = 0;
+			for (uint32_t k = 1; k < n_shards; ++k)
+				if (load[k] < load[best])
+					best = k;
+			load[best] += it.cost;
+			owner[it.index] = (uint16_t)best;
+			cost_total += it.cost;
+		}
+		cost_mine = shard < n_shards ? load[shard] : 0;
+	}
+	uint32_t index = 0;
 	for (const auto &kv : fonts_) {
 		if (!writer.write_directory(kv.first + "/", err))
 			return false;
@@ -191,7 +225,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			bsv[i].blk = &table[i];
 		}
 		for (uint32_t i = 0; i < kBlocks; ++i) {
-			if (index++ % n_shards != shard)
+			const uint32_t task = index++;
+			if (n_shards > 1 && owner[task] != shard)
 				continue;
 			BlockState *bs = &bsv[i];
 			total_glyphs += bs->blk->len();
@@ -235,7 +270,17 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	int total_threads = 1;
 	if (parallel_) {
 		total_threads = threads > 0 ? threads : usable_cpus();
-		total_threads = std::max(1, std::min(total_threads, 33));
+		// No more threads than there is host work for: a worker should have a few hundred microseconds of glyphs to
+		// prepare and encode, or waking it costs more than it contributes (measured: 32 threads were slower than 16 on
+		// the 6480-glyph Noto merge).  VGB_GLYPHS_PER_WORKER overrides the share; the pool itself is unbounded.
+		static const size_t per_worker = [] {
+			const char *e = std::getenv("VGB_GLYPHS_PER_WORKER");
+			const long v = e ? std::atol(e) : 0;
+			return (size_t)(v >= 1 ? v : 0);
+		}();
+		const size_t share = per_worker ? per_worker : (renderer.flatten() == Flatten::Glyf ? 768 : 384);
+		const size_t useful = std::max<size_t>(1, (total_glyphs + share - 1) / share);
+		total_threads = (int)std::max<size_t>(1, std::min<size_t>((size_t)total_threads, useful + 1));
 	}
 	const bool dedicated = total_threads >= kDedicatedMin;
 	const int workers = dedicated ? total_threads - 1 : total_threads;
@@ -329,6 +374,17 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	const size_t max_outstanding =
 	    renderer.mode() == Renderer::Mode::Cuda ? std::max<size_t>(2, renderer.slots()) : (size_t)(2 * workers + 2);
 
+	// what a finished (and finalized) batch adds to the call's statistics
+	auto account = [](RenderStats &st, const GlyphBatch &b) {
+		st.glyphs += b.glyphs().size();
+		for (const BatchGlyph &g : b.glyphs())
+			st.bitmaps += g.has_bitmap ? 1 : 0;
+		st.pixels += b.pixel_count();
+		st.segments += b.total_segments();
+		st.pairs += b.pairs();
+		st.handed_back += b.handed_back();
+		st.h2d_bytes += b.upload_bytes();
+	};
 	auto work = [&](int wid) {
 		RenderStats &st = per_worker[(size_t)wid];
 		auto &ev = events[(size_t)wid];
@@ -411,6 +467,13 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				idle_spins = 0;
 				mark('e');
 				bool ok = true;
+				if (!done->parts.empty()) { // (an error path hands back batches without parts: results dropped)
+					std::string e;
+					ok = done->batch->finalize(renderer, &e);
+					if (!ok)
+						fail(e);
+					account(st, *done->batch);
+				}
 				for (const Part &p : done->parts)
 					if (ok)
 						ok = finish_part(*p.todo, *done->batch, p.g0, p.g1);
@@ -470,6 +533,16 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					cur->parts.push_back(Part{&todo, g0, cur->batch->glyphs().size()});
 				}
 				st.outline_ns += now_ns() - t0;
+				if (cur->batch->failed()) { // a glyph could not be recorded (allocation failure): the output would be incomplete
+					fail(cur->batch->failure());
+					renderer.release_batch(std::move(cur->batch));
+					{
+						std::lock_guard<std::mutex> g(qm);
+						--outstanding;
+					}
+					qcv.notify_all();
+					break;
+				}
 				if (cur->parts.empty()) {
 					renderer.release_batch(std::move(cur->batch));
 					{
@@ -479,14 +552,10 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					qcv.notify_all(); // a worker may be asleep waiting for exactly this reservation to go away
 					continue;
 				}
-				st.glyphs += cur->batch->glyphs().size();
-				st.bitmaps += cur->batch->job_count();
-				st.pixels += cur->batch->bitmap_bytes();
-				st.segments += cur->batch->total_segments();
-				st.pairs += cur->batch->pairs();
 				if (cur->batch->job_count() == 0) {
 					// nothing to rasterise (empty blocks, or only bitmap-less glyphs): no GPU round trip
 					bool ok = true;
+					account(st, *cur->batch);
 					for (const Part &p : cur->parts)
 						if (ok)
 							ok = finish_part(*p.todo, *cur->batch, p.g0, p.g1);
@@ -737,7 +806,11 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			stats->encode_ns += s.encode_ns;
 			stats->write_ns += s.write_ns;
 			stats->submits += s.submits;
+			stats->handed_back += s.handed_back;
+			stats->h2d_bytes += s.h2d_bytes;
 		}
+		stats->cost_total = cost_total;
+		stats->cost_shard = cost_mine;
 		stats->submit_ns += submit_ns.load();
 		stats->workers = (uint64_t)workers;
 		stats->wall_ns = now_ns() - t_begin;

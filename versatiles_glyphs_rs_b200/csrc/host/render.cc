@@ -299,8 +299,9 @@ bool HostBuffer::reserve(size_t bytes, size_t keep, bool exact)
 }
 
 // ---- GlyphBatch ------------------------------------------------------------------------------------
-GlyphBatch::GlyphBatch(bool pinned, Flatten mode)
-    : mode_(mode), jobs_(pinned), segs_(pinned), curves_(pinned), out_(pinned), tiles_(pinned)
+GlyphBatch::GlyphBatch(bool pinned, Flatten mode, const Renderer *owner)
+    : mode_(mode), owner_(owner), reqs_(pinned), parts_(pinned), frames_(pinned), jobs_(pinned), segs_(pinned),
+      curves_(pinned), out_(pinned), tiles_(pinned)
 {
 }
 
@@ -311,6 +312,12 @@ void GlyphBatch::clear()
 	total_seg_ = out_bytes_ = pairs_ = 0;
 	n_tiles_ = 0;
 	prepared_ = false;
+	n_parts_ = curve_slots_ = tile_cap_ = n_handed_back_ = 0;
+	pixels_ = 0;
+	finalized_ = false;
+	failed_ = false;
+	failure_ = "";
+	extra_.clear();
 }
 
 bool GlyphBatch::plan_tiles(const char **why, bool latency)
@@ -342,12 +349,41 @@ bool GlyphBatch::plan_tiles(const char **why, bool latency)
 	return false;
 }
 
+bool GlyphBatch::push_req(const b200sdf_glyph_req &r)
+{
+	// (one request per job, same index)
+	if (!reqs_.reserve(((size_t)n_jobs_ + 1) * sizeof(r), (size_t)n_jobs_ * sizeof(r)))
+		return fail_alloc();
+	reinterpret_cast<b200sdf_glyph_req *>(reqs_.data())[n_jobs_] = r;
+	return true;
+}
+
 bool GlyphBatch::push_job(const b200sdf_outline_job &j)
 {
 	if (!jobs_.reserve(((size_t)n_jobs_ + 1) * sizeof(j), (size_t)n_jobs_ * sizeof(j)))
-		return false;
+		return fail_alloc();
+	if (mode_ == Flatten::Glyf) {
+		// a glyph recorded on the host travels in a glyph-level batch as a CURVES / SEGMENTS request
+		b200sdf_glyph_req r;
+		std::memset(&r, 0, sizeof(r));
+		r.kind = j.kind;
+		r.src_off = j.src_off, r.src_cnt = j.src_cnt, r.seg_cnt = j.seg_cnt;
+		r.width = j.width, r.height = j.height, r.x0 = j.x0, r.y0 = j.y0;
+		r.scale = j.scale, r.dx = j.dx;
+		r.out_off = j.out_off;
+		r.out_cap = j.width * j.height;
+		if (j.kind == B200SDF_KIND_CURVES) {
+			r.curve_off = curve_slots_;
+			r.curve_cap = j.src_cnt;
+			curve_slots_ += j.src_cnt;
+		}
+		tile_cap_ += b200sdf_glyph_tile_bound(j.width, j.height);
+		if (!push_req(r))
+			return false;
+	}
 	reinterpret_cast<b200sdf_outline_job *>(jobs_.data())[n_jobs_++] = j;
 	out_bytes_ += (uint64_t)j.width * j.height;
+	pixels_ += (uint64_t)j.width * j.height;
 	pairs_ += (uint64_t)j.width * j.height * j.seg_cnt;
 	total_seg_ += j.seg_cnt;
 	return true;
@@ -358,7 +394,7 @@ bool GlyphBatch::append_segments(const RingSet &rings, double ox, double oy)
 {
 	const size_t n = rings.segment_count();
 	if (!segs_.reserve(((size_t)n_seg_ + n) * sizeof(b200sdf_segment), (size_t)n_seg_ * sizeof(b200sdf_segment)))
-		return false;
+		return fail_alloc();
 	b200sdf_segment *dst = reinterpret_cast<b200sdf_segment *>(segs_.data()) + n_seg_;
 	const Point *pts = rings.points();
 	for (size_t r = 0; r < rings.ring_count(); ++r) {
@@ -456,7 +492,21 @@ bool GlyphBatch::add_glyph(const Face &face, uint32_t index)
 	const double rounded = std::round(advance_float);
 	const uint32_t advance = rounded <= 0.0 ? 0u : (rounded >= 4294967295.0 ? 4294967295u : (uint32_t)rounded);
 
-	if (mode_ == Flatten::Device) {
+	if (mode_ == Flatten::Glyf) {
+		parts_tmp_.clear();
+		const Face::GlyfPlan plan = face.glyf_parts(*glyph_id, parts_tmp_);
+		if (plan == Face::GlyfPlan::None) { // no outline: rings.is_empty(), :118-120
+			BatchGlyph g;
+			g.id = index;
+			g.advance = advance;
+			glyphs_.push_back(g);
+			return true;
+		}
+		if (plan == Face::GlyfPlan::Parts)
+			return add_glyf_request(face, index, advance, advance_float, scale);
+		// Host: recorded below like in Device mode
+	}
+	if (mode_ == Flatten::Device || mode_ == Flatten::Glyf) {
 		recorder_.begin();
 		face.outline_glyph(*glyph_id, recorder_); // :109-110
 		recorder_.finish();                       // into_rings, :111
@@ -484,7 +534,7 @@ bool GlyphBatch::add_glyph(const Face &face, uint32_t index)
 			const RenderResult fr = frame_of(bbox);
 			const std::vector<b200sdf_curve> &recs = recorder_.records();
 			if (!curves_.reserve(((size_t)n_curves_ + recs.size()) * sizeof(b200sdf_curve), (size_t)n_curves_ * sizeof(b200sdf_curve)))
-				return false;
+				return fail_alloc();
 			std::memcpy(curves_.data() + (size_t)n_curves_ * sizeof(b200sdf_curve), recs.data(), recs.size() * sizeof(b200sdf_curve));
 			b200sdf_outline_job job;
 			std::memset(&job, 0, sizeof(job));
@@ -518,12 +568,140 @@ bool GlyphBatch::add_glyph(const Face &face, uint32_t index)
 	return add_flattened(index, advance, advance_float, scale);
 }
 
+// A glyph the device decodes itself: one request naming its glyf records, a bitmap slot sized from the records'
+// header boxes (the device checks that the real frame fits and hands the glyph back otherwise) and a curve slot of
+// one record per point.
+bool GlyphBatch::add_glyf_request(const Face &face, uint32_t index, uint32_t advance, double advance_float, double scale)
+{
+	uint32_t font = 0;
+	if (!owner_ || !owner_->font_handle(face, &font)) {
+		failed_ = true;
+		failure_ = "could not make the font's glyf table resident on the device";
+		return false;
+	}
+	const double dx = ((double)advance - advance_float) / 2.0;
+	BBox box;
+	uint32_t points = 0;
+	if (!parts_.reserve(((size_t)n_parts_ + parts_tmp_.size()) * sizeof(b200sdf_glyph_part), (size_t)n_parts_ * sizeof(b200sdf_glyph_part)))
+		return fail_alloc();
+	b200sdf_glyph_part *dst = reinterpret_cast<b200sdf_glyph_part *>(parts_.data()) + n_parts_;
+	for (const Face::GlyfPart &p : parts_tmp_) {
+		dst->font = font, dst->glyf_off = p.off, dst->glyf_len = p.len, dst->ox = p.ox, dst->oy = p.oy;
+		++dst;
+		points += p.points;
+		box.include_point(Point((double)p.xmin + (double)p.ox, (double)p.ymin + (double)p.oy));
+		box.include_point(Point((double)p.xmax + (double)p.ox, (double)p.ymax + (double)p.oy));
+	}
+	// the slot: frame_of the (untrusted) header box, one pixel of slack each side, 16-byte aligned start
+	double w = std::ceil(box.max.x * scale + dx) - std::floor(box.min.x * scale + dx) + 2.0 * BUFFER + 2.0;
+	double h = std::ceil(box.max.y * scale) - std::floor(box.min.y * scale) + 2.0 * BUFFER + 2.0;
+	if (!(w >= 8.0))
+		w = 8.0;
+	if (!(h >= 8.0))
+		h = 8.0;
+	if (w > 4096.0)
+		w = 4096.0; // absurd header boxes: the device hands the glyph back if the real frame is larger
+	if (h > 4096.0)
+		h = 4096.0;
+	const uint32_t wi = (uint32_t)w, hi = (uint32_t)h;
+	b200sdf_glyph_req r;
+	std::memset(&r, 0, sizeof(r));
+	r.kind = B200SDF_KIND_GLYF;
+	r.src_off = n_parts_, r.src_cnt = (uint32_t)parts_tmp_.size();
+	r.scale = scale, r.dx = dx;
+	r.out_off = (out_bytes_ + 15u) & ~(uint64_t)15u;
+	r.out_cap = wi * hi;
+	r.curve_off = curve_slots_;
+	r.curve_cap = points;
+	b200sdf_outline_job job; // host-side mirror, completed by finalize()
+	std::memset(&job, 0, sizeof(job));
+	job.kind = B200SDF_KIND_CURVES;
+	job.scale = scale, job.dx = dx;
+	job.out_off = r.out_off;
+	if (!jobs_.reserve(((size_t)n_jobs_ + 1) * sizeof(job), (size_t)n_jobs_ * sizeof(job)) || !push_req(r))
+		return fail_alloc();
+	BatchGlyph g;
+	g.id = index;
+	g.advance = advance;
+	g.pending = true;
+	g.job = n_jobs_;
+	g.face = &face;
+	reinterpret_cast<b200sdf_outline_job *>(jobs_.data())[n_jobs_++] = job;
+	n_parts_ += (uint32_t)parts_tmp_.size();
+	curve_slots_ += points;
+	tile_cap_ += b200sdf_glyph_tile_bound(wi, hi);
+	out_bytes_ = r.out_off + r.out_cap;
+	glyphs_.push_back(g);
+	return true;
+}
+
 bool GlyphBatch::ensure_output() { return out_.reserve((size_t)out_bytes_ + 16, 0); }
+bool GlyphBatch::ensure_frames() { return frames_.reserve(((size_t)n_jobs_ + 1) * sizeof(b200sdf_glyph_frame), 0); }
+
+bool GlyphBatch::finalize(const Renderer &renderer, std::string *err)
+{
+	if (mode_ != Flatten::Glyf || finalized_)
+		return true;
+	finalized_ = true;
+	b200sdf_outline_job *jv = reinterpret_cast<b200sdf_outline_job *>(jobs_.data());
+	const b200sdf_glyph_frame *fv = frames();
+	for (BatchGlyph &g : glyphs_) {
+		if (!g.pending)
+			continue;
+		g.pending = false;
+		const b200sdf_glyph_frame &f = fv[g.job];
+		b200sdf_outline_job &j = jv[g.job];
+		if (f.status == B200SDF_GLYPH_OK) {
+			j.width = f.width, j.height = f.height, j.x0 = f.x0, j.y0 = f.y0, j.seg_cnt = f.seg_cnt;
+			g.has_bitmap = true;
+			g.frame.x0 = f.x0, g.frame.y0 = f.y0;
+			g.frame.x1 = f.x0 + (int32_t)f.width, g.frame.y1 = f.y0 + (int32_t)f.height;
+			g.frame.width = f.width, g.frame.height = f.height;
+			g.frame.y1 -= GLYPH_SIZE; // renderer.rs:146
+			pixels_ += (uint64_t)f.width * f.height;
+			pairs_ += (uint64_t)f.width * f.height * f.seg_cnt;
+			total_seg_ += f.seg_cnt;
+		} else if (f.status == B200SDF_GLYPH_EMPTY) {
+			g.has_bitmap = false; // renderer.rs:118-120 / :133-137
+		} else if (f.status == B200SDF_GLYPH_NEEDS_HOST) {
+			// the closed-form device decoder does not cover this glyph: record it on the host (exact recorder or literal
+			// flattening) and render it on its own; the bitmap goes to the side buffer
+			n_handed_back_++;
+			std::unique_ptr<GlyphBatch> one(new GlyphBatch(false, Flatten::Device, owner_));
+			if (!one->add_glyph(*g.face, g.id) || one->glyphs().size() != 1) {
+				if (err)
+					*err = "could not record a glyph handed back by the device";
+				return false;
+			}
+			const BatchGlyph &o = one->glyphs()[0];
+			if (o.has_bitmap) {
+				if (!renderer.render_batch(*one, err))
+					return false;
+				const b200sdf_outline_job &oj = one->jobs()[o.job];
+				const size_t n = (size_t)oj.width * oj.height;
+				g.extra_off = (int64_t)extra_.size();
+				extra_.insert(extra_.end(), one->bitmaps() + oj.out_off, one->bitmaps() + oj.out_off + n);
+				j.width = oj.width, j.height = oj.height, j.x0 = oj.x0, j.y0 = oj.y0, j.seg_cnt = oj.seg_cnt;
+				pixels_ += n;
+				pairs_ += (uint64_t)n * oj.seg_cnt;
+				total_seg_ += oj.seg_cnt;
+			}
+			g.has_bitmap = o.has_bitmap;
+			g.frame = o.frame;
+		} else {
+			if (err)
+				*err = "the device rejected a glyph request (status " + std::to_string(f.status) + ")";
+			return false;
+		}
+	}
+	return true;
+}
 
 void GlyphBatch::capacities(size_t caps[kBuffers]) const
 {
 	caps[0] = jobs_.capacity(), caps[1] = segs_.capacity(), caps[2] = curves_.capacity(), caps[3] = out_.capacity();
 	caps[4] = tiles_.capacity();
+	caps[5] = reqs_.capacity(), caps[6] = parts_.capacity(), caps[7] = frames_.capacity();
 }
 
 void GlyphBatch::reserve_capacity(const size_t caps[kBuffers])
@@ -531,6 +709,7 @@ void GlyphBatch::reserve_capacity(const size_t caps[kBuffers])
 	// only called on an empty batch: nothing to keep
 	jobs_.reserve(caps[0], 0, true), segs_.reserve(caps[1], 0, true), curves_.reserve(caps[2], 0, true),
 	    out_.reserve(caps[3], 0, true), tiles_.reserve(caps[4], 0, true);
+	reqs_.reserve(caps[5], 0, true), parts_.reserve(caps[6], 0, true), frames_.reserve(caps[7], 0, true);
 }
 
 PbfGlyph GlyphBatch::take_glyph(size_t i) const
@@ -541,7 +720,8 @@ PbfGlyph GlyphBatch::take_glyph(size_t i) const
 	PbfGlyph g = b.frame.into_pbf_glyph(b.id, b.advance);
 	const b200sdf_outline_job &j = jobs()[b.job];
 	const size_t n = (size_t)j.width * j.height;
-	g.bitmap.assign(out_.data() + j.out_off, out_.data() + j.out_off + n);
+	const uint8_t *src = bitmap_of(b);
+	g.bitmap.assign(src, src + n);
 	return g;
 }
 
@@ -575,7 +755,43 @@ std::unique_ptr<Renderer> Renderer::new_precise(int device, uint32_t n_slots, st
 	r->mode_ = Mode::Cuda;
 	r->ctx_ = ctx;
 	r->slots_ = n_slots;
+	static std::atomic<uint64_t> next_id{1};
+	r->id_ = next_id.fetch_add(1);
+	// default: the device decodes glyf records itself (VGB_FLATTEN=device / host select the older seams: curve records
+	// recorded on the host / segments flattened on the host)
+	r->flatten_ = Flatten::Glyf;
+	if (const char *e = std::getenv("VGB_FLATTEN")) {
+		if (!std::strcmp(e, "device"))
+			r->flatten_ = Flatten::Device;
+		else if (!std::strcmp(e, "host"))
+			r->flatten_ = Flatten::Host;
+	}
 	return r;
+}
+
+bool Renderer::font_handle(const Face &face, uint32_t *handle) const
+{
+	if (mode_ != Mode::Cuda)
+		return false;
+	const uint64_t tag = face.device_tag();
+	if ((tag >> 32) == id_ && (tag & 0xffffffffu)) {
+		*handle = (uint32_t)(tag & 0xffffffffu) - 1u;
+		return true;
+	}
+	std::lock_guard<std::mutex> g(fonts_mu_);
+	for (const auto &kv : fonts_)
+		if (kv.first == face.uid()) {
+			*handle = kv.second;
+			face.set_device_tag((id_ << 32) | ((uint64_t)kv.second + 1u));
+			return true;
+		}
+	uint32_t h = 0;
+	if (b200sdf_font_upload(ctx_, face.glyf_data(), face.glyf_size(), &h) != 0)
+		return false;
+	fonts_.emplace_back(face.uid(), h);
+	face.set_device_tag((id_ << 32) | ((uint64_t)h + 1u));
+	*handle = h;
+	return true;
 }
 
 Renderer::~Renderer()
@@ -691,6 +907,14 @@ bool Renderer::prepare_batch(GlyphBatch &batch, std::string *err, bool latency) 
 	}
 	if (mode_ == Mode::Dummy)
 		return true;
+	if (batch.mode() == Flatten::Glyf) { // frames come back from the device, which also plans the tiles
+		if (!batch.ensure_frames()) {
+			if (err)
+				*err = "out of host memory for the frame buffer";
+			return false;
+		}
+		return true;
+	}
 	const char *why = "";
 	if (!batch.plan_tiles(&why, latency)) {
 		if (err)
@@ -711,6 +935,22 @@ bool Renderer::submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *er
 		// renderer_dummy.rs:3-5 — zero-filled bitmaps of the right size
 		std::memset(batch.bitmaps(), 0, (size_t)batch.bitmap_bytes());
 		*ticket = fake_latency_ns() ? fake_now_ns() + fake_latency_ns() : ~0ull; // (test hook, see poll_batch)
+		return true;
+	}
+	if (batch.mode() == Flatten::Glyf) {
+		if (!batch.ensure_frames()) {
+			if (err)
+				*err = "out of host memory for the frame buffer";
+			return false;
+		}
+		const int grc = b200sdf_submit_glyphs(ctx_, batch.reqs(), batch.job_count(), batch.parts(), batch.part_count(), batch.curves(),
+		                                      batch.curve_count(), batch.segments(), batch.segment_count(), batch.curve_slots(),
+		                                      batch.tile_cap(), batch.frames(), batch.bitmaps(), batch.bitmap_bytes(), ticket);
+		if (grc != 0) {
+			if (err)
+				*err = std::string("b200sdf_submit_glyphs: ") + b200sdf_last_error(ctx_);
+			return false;
+		}
 		return true;
 	}
 	const int rc =
@@ -768,7 +1008,7 @@ bool Renderer::poll_batch(uint64_t ticket, bool *done, std::string *err) const
 bool Renderer::render_batch(GlyphBatch &batch, std::string *err) const
 {
 	uint64_t t = 0;
-	return submit_batch(batch, &t, err) && wait_batch(t, err);
+	return submit_batch(batch, &t, err) && wait_batch(t, err) && batch.finalize(*this, err);
 }
 
 std::optional<PbfGlyph> Renderer::render_glyph(const Face &face, uint32_t index, std::string *err) const

@@ -156,21 +156,27 @@ struct BatchGlyph {
 	uint32_t id = 0;
 	uint32_t advance = 0;
 	bool has_bitmap = false; // false = PbfGlyph::empty
+	bool pending = false;    // Glyf mode: frame and has_bitmap come from the device (GlyphBatch::finalize)
 	RenderResult frame;      // y1 already rebased (renderer.rs:146)
-	uint32_t job = 0;        // index into jobs when has_bitmap
+	uint32_t job = 0;        // index into jobs when has_bitmap (or pending)
+	const Face *face = nullptr; // Glyf mode: where the glyph came from (for glyphs the device hands back)
+	int64_t extra_off = -1;  // >= 0: the bitmap lives in the batch's side buffer (glyph re-rendered by finalize)
 };
 
-// Where flattening happens for a batch.
+// Where outline decoding and flattening happen for a batch.
 enum class Flatten {
-	Device, // upload curve records, flatten on the GPU (glyphs that are not exactly representable fall back per glyph)
-	Host    // flatten on the host, upload b200sdf_segment (the literal renderer_precise seam)
+	Device, // record outlines on the host, upload curve records, flatten on the GPU (glyphs that are not exactly representable fall back per glyph)
+	Host,   // flatten on the host, upload b200sdf_segment (the literal renderer_precise seam)
+	Glyf    // send glyf record references; the GPU decodes, records, measures, plans and renders (csrc/glyf_kernel.cuh);
+	        // glyphs it cannot take (scaled components, CFF) are recorded on the host as in Device mode
 };
+class Renderer;
 
 // The flat outline buffer of one GlyphBlock (or of any group of glyphs): curve records and/or
 // segments of all glyphs back to back, one b200sdf_outline_job per bitmap, bitmaps packed back to back.
 class GlyphBatch {
   public:
-	GlyphBatch(bool pinned, Flatten mode);
+	GlyphBatch(bool pinned, Flatten mode, const Renderer *owner = nullptr);
 	void clear();
 	Flatten mode() const { return mode_; }
 	// First half of Renderer::render_glyph (renderer.rs:103-137): cmap lookup, outline, advance,
@@ -192,8 +198,42 @@ class GlyphBatch {
 	uint32_t fallback_glyphs() const { return n_fallback_; } // Device-mode glyphs that had to be flattened on the host
 	uint8_t *bitmaps() { return out_.data(); }
 	const uint8_t *bitmaps() const { return out_.data(); }
-	uint64_t bitmap_bytes() const { return out_bytes_; }
+	uint64_t bitmap_bytes() const { return out_bytes_; } // extent of the bitmap area (Glyf mode: slots, not pixels)
+	uint64_t pixel_count() const { return pixels_; }     // bitmap pixels (Glyf mode: known after finalize)
 	uint64_t pairs() const { return pairs_; }
+	// where glyph b's bitmap is (valid after the batch was rendered and, in Glyf mode, finalized)
+	const uint8_t *bitmap_of(const BatchGlyph &b) const
+	{
+		return b.extra_off >= 0 ? extra_.data() + b.extra_off : out_.data() + jobs()[b.job].out_off;
+	}
+	// ---- Glyf mode ----
+	const b200sdf_glyph_req *reqs() const { return reinterpret_cast<const b200sdf_glyph_req *>(reqs_.data()); }
+	const b200sdf_glyph_part *parts() const { return reinterpret_cast<const b200sdf_glyph_part *>(parts_.data()); }
+	b200sdf_glyph_frame *frames() { return reinterpret_cast<b200sdf_glyph_frame *>(frames_.data()); }
+	const b200sdf_glyph_frame *frames() const { return reinterpret_cast<const b200sdf_glyph_frame *>(frames_.data()); }
+	uint32_t part_count() const { return n_parts_; }
+	uint32_t curve_slots() const { return curve_slots_; }
+	uint32_t tile_cap() const { return tile_cap_; }
+	bool ensure_frames(); // allocate the frame array (after the last add)
+	// After the batch came back: take frames and bitmap presence from the device's answers; glyphs it handed back
+	// (B200SDF_GLYPH_NEEDS_HOST) are recorded on the host and rendered through `renderer` now.  false + *err on failure.
+	bool finalize(const Renderer &renderer, std::string *err);
+	bool finalized() const { return finalized_; }
+	// add_glyph answers false both for "None" (the code point has no glyph: skipped, glyph_block.rs:74-76) and when the
+	// batch could not take the glyph (allocation failure): the second case is sticky and reported here, so callers that
+	// treat false as "skip" still notice that the batch is incomplete.
+	bool failed() const { return failed_; }
+	const char *failure() const { return failure_; }
+	uint32_t handed_back() const { return n_handed_back_; }
+	// bytes of this batch the device reads from host memory (requests + parts, or job records + tile list; curve
+	// records and segments of glyphs recorded on the host)
+	uint64_t upload_bytes() const
+	{
+		const uint64_t recorded = (uint64_t)n_curves_ * sizeof(b200sdf_curve) + (uint64_t)n_seg_ * sizeof(b200sdf_segment);
+		if (mode_ == Flatten::Glyf)
+			return recorded + (uint64_t)n_jobs_ * sizeof(b200sdf_glyph_req) + (uint64_t)n_parts_ * sizeof(b200sdf_glyph_part);
+		return recorded + (uint64_t)n_jobs_ * sizeof(b200sdf_outline_job) + (uint64_t)n_tiles_ * sizeof(b200sdf_tile_job);
+	}
 	bool ensure_output(); // allocate the bitmap area (after the last add)
 	// plan the CTA work items of the recorded jobs into the batch's own (pinned) tile buffer; false + *why
 	// when a job is invalid.  After this, tiles()/tile_count() feed b200sdf_submit_planned.
@@ -202,7 +242,7 @@ class GlyphBatch {
 	const b200sdf_tile_job *tiles() const { return reinterpret_cast<const b200sdf_tile_job *>(tiles_.data()); }
 	uint32_t tile_count() const { return n_tiles_; }
 	// buffer capacities in bytes (jobs, segments, curves, bitmaps) — the pool sizes new leases from them
-	static constexpr int kBuffers = 5; // jobs, segments, curves, bitmaps, tile list
+	static constexpr int kBuffers = 8; // jobs, segments, curves, bitmaps, tile list, requests, parts, frames
 	void capacities(size_t caps[kBuffers]) const;
 	void reserve_capacity(const size_t caps[kBuffers]);
 	// PbfGlyph i with its bitmap copied out of the batch (valid after the batch was rendered)
@@ -212,7 +252,24 @@ class GlyphBatch {
 	bool append_segments(const RingSet &rings, double ox, double oy);
 	bool push_job(const b200sdf_outline_job &j);
 	bool add_flattened(uint32_t index, uint32_t advance, double advance_float, double scale);
+	bool add_glyf_request(const Face &face, uint32_t index, uint32_t advance, double advance_float, double scale);
+	bool push_req(const b200sdf_glyph_req &r);
 	Flatten mode_;
+	const Renderer *owner_ = nullptr;
+	HostBuffer reqs_, parts_, frames_;
+	std::vector<Face::GlyfPart> parts_tmp_;
+	std::vector<uint8_t> extra_;
+	uint32_t n_parts_ = 0, curve_slots_ = 0, tile_cap_ = 0, n_handed_back_ = 0;
+	uint64_t pixels_ = 0;
+	bool finalized_ = false;
+	bool failed_ = false;
+	const char *failure_ = "";
+	bool fail_alloc()
+	{
+		failed_ = true;
+		failure_ = "out of (pinned) host memory while recording a glyph";
+		return false;
+	}
 	RingSet scratch_;
 	OutlineRecorder recorder_;
 	std::vector<BatchGlyph> glyphs_;
@@ -241,7 +298,9 @@ class Renderer {
 	b200sdf_ctx *context() const { return ctx_; }
 	Flatten flatten() const { return flatten_; }
 	void set_flatten(Flatten f) { flatten_ = f; }
-	std::unique_ptr<GlyphBatch> new_batch() const { return std::make_unique<GlyphBatch>(mode_ == Mode::Cuda, flatten_); }
+	std::unique_ptr<GlyphBatch> new_batch() const { return std::make_unique<GlyphBatch>(mode_ == Mode::Cuda, flatten_, this); }
+	// handle of the face's glyf table on this renderer's device (uploaded on first use: b200sdf_font_upload); false on error
+	bool font_handle(const Face &face, uint32_t *handle) const;
 	// Batch pool: pinned buffers are expensive to allocate, so the pipeline recycles batches.
 	// in_pipeline: the batch counts towards the per-call total that sizes the pool (top_up_pool)
 	std::unique_ptr<GlyphBatch> acquire_batch(bool in_pipeline = false) const;
@@ -274,7 +333,10 @@ class Renderer {
 	Flatten flatten_ = Flatten::Device;
 	mutable std::mutex pool_mu_;
 	mutable std::vector<std::unique_ptr<GlyphBatch>> pool_;
-	mutable size_t hwm_[GlyphBatch::kBuffers] = {0, 0, 0, 0, 0}; // largest buffer capacities any batch of this renderer reached
+	mutable size_t hwm_[GlyphBatch::kBuffers] = {0, 0, 0, 0, 0, 0, 0, 0}; // largest buffer capacities any batch of this renderer reached
+	uint64_t id_ = 0; // distinguishes renderers in Face::device_tag
+	mutable std::mutex fonts_mu_;
+	mutable std::vector<std::pair<uint64_t, uint32_t>> fonts_; // Face::uid -> handle of its glyf table on ctx_
 	mutable size_t out_now_ = 0, out_max_ = 0; // batches handed out and not yet returned; the most that ever were
 	mutable size_t acq_call_ = 0, acq_max_ = 0; // batches handed out since the last top-up; the most per call
 };

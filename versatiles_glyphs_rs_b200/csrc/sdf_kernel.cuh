@@ -31,6 +31,7 @@
 #include <stdint.h>
 
 #include "../../include/b200sdf.h"
+#include "glyf_kernel.cuh"
 
 #ifndef B200SDF_MINI
 #define B200SDF_MINI 64 // segments a warp stages at a time
@@ -328,20 +329,24 @@ __device__ __forceinline__ uint32_t curves_of_32(const b200sdf_curve *__restrict
 }
 
 static_assert(kThreads == 128, "B200SDF_BOUNDS");
-__global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
-                                                             const b200sdf_curve *__restrict__ curves,
-                                                             const b200sdf_outline_job *__restrict__ ojobs,
-                                                             const b200sdf_tile_job *__restrict__ jobs,
-                                                             uint8_t *__restrict__ out)
-{
-	__shared__ __align__(128) SharedStorage sm;
 
+// mbarrier phases of a CTA that renders several tile jobs one after the other (the barriers are initialised once)
+struct BarrierPhases {
+	uint32_t curve;  // completed uses of curve_bar (CTA-uniform)
+	uint32_t raw[2]; // completed uses of this warp's two raw-segment barriers
+};
+
+// One tile job.  `rot` rotates the warps' roles (see below); the caller has initialised the mbarriers and made sure
+// (a CTA-wide barrier) that nobody still reads the shared storage of a previous job.
+__device__ __forceinline__ void render_tile(SharedStorage &sm, const b200sdf_tile_job job, const uint32_t rot,
+                                            BarrierPhases &ph, const float4 *__restrict__ segs,
+                                            const b200sdf_curve *__restrict__ curves,
+                                            const b200sdf_outline_job *__restrict__ ojobs, uint8_t *__restrict__ out)
+{
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
 	const int warp = tid >> 5;
 
-	// 32-byte job record, uniform across the CTA
-	const b200sdf_tile_job job = jobs[blockIdx.x];
 	const int W = job.width, H = job.height;
 	Rect R;
 	R.rx0 = job.tx0 * kTileW;
@@ -368,15 +373,6 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 	}
 	const bool curves_in_smem = from_curves && n_curves != 0 && n_curves <= (uint32_t)kCurveSmem;
 
-	if (tid == 0) {
-		mbar_init(&sm.curve_bar, 1);
-		fence_mbar_init();
-	}
-	if (lane == 0) {
-		mbar_init(&sm.bar[warp][0], 1);
-		mbar_init(&sm.bar[warp][1], 1);
-		fence_mbar_init();
-	}
 	for (int i = tid; i < rpix; i += kThreads) {
 		sm.delta[i] = 0;
 		sm.d2[i] = 0x7f800000u; // +inf
@@ -391,7 +387,7 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 	// A warp's scheduler (SM sub-partition) is fixed by its index, and so would be the role it plays if
 	// roles followed the index: rotate roles by the CTA index so that heavy and light roles of the CTAs
 	// resident on one SM spread over all four sub-partitions.
-	const int vw = (warp + (int)blockIdx.x) & 3;
+	const int vw = (warp + (int)rot) & 3;
 	const int n_groups = (n_items + 31) >> 5; // 1..4
 	int wslices, group, wslice;
 	if (n_groups == 1) {
@@ -445,7 +441,8 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 #endif
 
 	if (curves_in_smem) {
-		mbar_wait(&sm.curve_bar, 0);
+		mbar_wait(&sm.curve_bar, ph.curve & 1u);
+		ph.curve++;
 		gcurves = sm.src.curves;
 	}
 
@@ -653,13 +650,13 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 			// ---- stage: every lane turns up to kMini/32 segments into records ----
 #if B200SDF_ALGO == 2
 			if (!from_curves)
-				mbar_wait(&sm.bar[warp][b], (m >> 1) & 1);
+				mbar_wait(&sm.bar[warp][b], (ph.raw[b] + (m >> 1)) & 1u);
 			int nv = 0;
 			const int n_long = stage(ws, raw[b], base, n, c_lo, scatter, nv);
 #else
 			const int n_long = n;
 			if (!from_curves) {
-				mbar_wait(&sm.bar[warp][b], (m >> 1) & 1);
+				mbar_wait(&sm.bar[warp][b], (ph.raw[b] + (m >> 1)) & 1u);
 				for (int i = lane; i < n; i += 32)
 					stage_segment(raw[b][i], ws.recA[i], ws.recN[i], sm.delta, R, scatter);
 			} else {
@@ -681,6 +678,10 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 #endif
 			long_loop(ws, n_long, lslice, lslices);
 			__syncwarp(); // records are overwritten by the next staging pass
+		}
+		if (!from_curves) { // buffer b was used for passes b, b + 2, ...
+			ph.raw[0] += (n_mini + 1) >> 1;
+			ph.raw[1] += n_mini >> 1;
 		}
 	}
 
@@ -738,6 +739,73 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 			for (uint32_t k = max(lo, mis); k < min(hi, mis + nbytes); ++k)
 				gdst[k] = sm.obuf[k];
 		}
+	}
+}
+
+__device__ __forceinline__ void init_barriers(SharedStorage &sm)
+{
+	const int tid = threadIdx.x;
+	if (tid == 0) {
+		mbar_init(&sm.curve_bar, 1);
+		fence_mbar_init();
+	}
+	if ((tid & 31) == 0) {
+		mbar_init(&sm.bar[tid >> 5][0], 1);
+		mbar_init(&sm.bar[tid >> 5][1], 1);
+		fence_mbar_init();
+	}
+}
+
+// One CTA per tile job, jobs planned (and sorted, largest first) by the host.
+__global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs, const b200sdf_curve *__restrict__ curves,
+                                                const b200sdf_outline_job *__restrict__ ojobs,
+                                                const b200sdf_tile_job *__restrict__ jobs, uint8_t *__restrict__ out)
+{
+	__shared__ __align__(128) SharedStorage sm;
+	init_barriers(sm); // render_tile's first CTA-wide barrier orders this before any use
+	BarrierPhases ph;
+	ph.curve = 0, ph.raw[0] = 0, ph.raw[1] = 0;
+	render_tile(sm, jobs[blockIdx.x], blockIdx.x, ph, segs, curves, ojobs, out);
+}
+
+// Persistent form for batches planned on the device (glyf_decode_kernel): the grid is sized for the machine, not for
+// the batch — whose tile count the host never learns — and every CTA claims tile jobs from the batch's cursor until
+// the classes are exhausted, heaviest class first (what the host's largest-first sort does for the other kernel).
+__global__ void B200SDF_BOUNDS sdf_tiles_persistent_kernel(const float4 *__restrict__ segs,
+                                                           const b200sdf_curve *__restrict__ curves,
+                                                           const b200sdf_outline_job *__restrict__ ojobs,
+                                                           const b200sdf_tile_job *__restrict__ tiles, const uint32_t tile_cap,
+                                                           BatchCounters *__restrict__ ctr, uint8_t *__restrict__ out)
+{
+	__shared__ __align__(128) SharedStorage sm;
+	__shared__ uint32_t s_next;
+	init_barriers(sm);
+	BarrierPhases ph;
+	ph.curve = 0, ph.raw[0] = 0, ph.raw[1] = 0;
+	uint32_t cum[kTileBins];
+	uint32_t total = 0;
+#pragma unroll
+	for (int b = 0; b < kTileBins; ++b) {
+		total += min(ctr->bin_count[b], tile_cap);
+		cum[b] = total;
+	}
+	for (;;) {
+		__syncthreads(); // everybody is done with the previous job's shared storage (and with s_next)
+		if (threadIdx.x == 0)
+			s_next = atomicAdd(&ctr->next_tile, 1u);
+		__syncthreads();
+		const uint32_t t = s_next;
+		if (t >= total)
+			return;
+		int b = 0;
+		uint32_t first = 0;
+#pragma unroll
+		for (int k = 0; k < kTileBins - 1; ++k)
+			if (t >= cum[k]) { // cum is non-decreasing: the last hit is the class boundary below t
+				b = k + 1;
+				first = cum[k];
+			}
+		render_tile(sm, tiles[(size_t)b * tile_cap + (t - first)], t, ph, segs, curves, ojobs, out);
 	}
 }
 
