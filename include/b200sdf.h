@@ -126,7 +126,6 @@ typedef struct {
 #define B200SDF_MAX_ITEMS 64
 #endif
 #define B200SDF_MAX_DIM 16384 /* largest accepted glyph width/height in pixels */
-#define B200SDF_TILE_BINS 8   /* cost classes of device-planned tile jobs (heaviest first) */
 
 /*
  * Glyph-level input (the seam one step earlier still: Face::outline_glyph itself, reference
@@ -257,27 +256,29 @@ uint32_t b200sdf_glyph_tile_bound(uint32_t width, uint32_t height);
 /* Enqueue one batch of glyph requests: decode + frame + tile planning (one kernel), SDF (one persistent kernel).
  * frames[i] (written by the device) and the bitmaps are valid after b200sdf_wait / b200sdf_poll(ticket).
  * curves / segs: the arrays CURVES / SEGMENTS requests index (may be NULL / 0).  curve_slots = size of the device's
- * curve scratch in records (>= every request's curve_off + curve_cap); tile_cap = capacity of each of the
- * B200SDF_TILE_BINS cost classes of the device's tile list.  A tile list that turns out too short fails the
- * batch at wait / poll with B200SDF_E_ARG. */
+ * curve scratch in records (>= every request's curve_off + curve_cap); tile_cap = capacity of the device's tile
+ * list (the sum of b200sdf_glyph_tile_bound over the requests is always enough).  A tile list that turns out too
+ * short fails the batch at wait / poll with B200SDF_E_ARG.  est_cost = the caller's estimate of the batch's cost in
+ * tile x segment units (sum over glyphs of ceil(W/4) * ceil(H/4) * segments; about 8 segments per outline point):
+ * decides how finely heavy glyphs are cut (0 = never below the small-batch floor).  It affects speed only. */
 int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint32_t n_reqs, const b200sdf_glyph_part *parts,
                           uint32_t n_parts, const b200sdf_curve *curves, uint32_t n_curves, const b200sdf_segment *segs,
-                          uint32_t n_seg, uint32_t curve_slots, uint32_t tile_cap, b200sdf_glyph_frame *frames, uint8_t *out,
-                          uint64_t out_bytes, uint64_t *ticket);
+                          uint32_t n_seg, uint32_t curve_slots, uint32_t tile_cap, uint64_t est_cost, b200sdf_glyph_frame *frames,
+                          uint8_t *out, uint64_t out_bytes, uint64_t *ticket);
 /* The same over device pointers on `stream` (asynchronous, two kernel launches, scratch owned by the context);
  * mid_event (a cudaEvent_t or NULL) is recorded between the decode kernel and the SDF kernel. */
 int b200sdf_render_glyphs_device(b200sdf_ctx *ctx, const b200sdf_glyph_req *d_reqs, uint32_t n_reqs,
                                  const b200sdf_glyph_part *d_parts, uint32_t n_parts, const b200sdf_curve *d_curves,
                                  uint32_t n_curves, const b200sdf_segment *d_segs, uint32_t n_seg, uint32_t curve_slots,
-                                 uint32_t tile_cap, b200sdf_glyph_frame *d_frames, uint8_t *d_out, uint64_t out_bytes,
-                                 void *stream, void *mid_event);
+                                 uint32_t tile_cap, uint64_t est_cost, b200sdf_glyph_frame *d_frames, uint8_t *d_out,
+                                 uint64_t out_bytes, void *stream, void *mid_event);
 /* Decode only (tests, diagnostics): frames, the outline job of every request (src_off / src_cnt locate its records
- * in curves_out, which must hold curve_slots records) and the number of tile jobs planned per cost class
- * (tiles_per_bin[B200SDF_TILE_BINS], may be NULL).  Blocking. */
+ * in curves_out, which must hold curve_slots records), the number of tile jobs planned (n_tiles_out, may be NULL) and
+ * the tile jobs in the order the SDF kernel would claim them (tiles_out[tiles_cap], may be NULL).  Blocking. */
 int b200sdf_decode_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint32_t n_reqs, const b200sdf_glyph_part *parts,
                           uint32_t n_parts, const b200sdf_curve *curves, uint32_t n_curves, uint32_t n_seg, uint32_t curve_slots,
-                          b200sdf_glyph_frame *frames, b200sdf_outline_job *jobs_out, b200sdf_curve *curves_out,
-                          uint32_t *tiles_per_bin);
+                          uint64_t est_cost, b200sdf_glyph_frame *frames, b200sdf_outline_job *jobs_out, b200sdf_curve *curves_out,
+                          uint32_t *n_tiles_out, b200sdf_tile_job *tiles_out, uint32_t tiles_cap);
 
 /* ---- measurement helpers ----------------------------------------------------------------------- */
 /* Dependent-FFMA-chain microbenchmark: measured FP32 (non-tensor) peak of this device in TFLOP/s

@@ -135,6 +135,7 @@ const b200sdf_glyph_req *vgb_batch_requests(const vgb_batch *b, uint32_t *n);
 const b200sdf_glyph_part *vgb_batch_parts(const vgb_batch *b, uint32_t *n);
 uint32_t vgb_batch_curve_slots(const vgb_batch *b);
 uint32_t vgb_batch_tile_cap(const vgb_batch *b);
+uint64_t vgb_batch_est_cost(const vgb_batch *b); /* the est_cost argument of b200sdf_submit_glyphs */
 uint32_t vgb_batch_handed_back(const vgb_batch *b);
 /* bitmap of glyph i (NULL when it has none); valid after the batch was rendered */
 const uint8_t *vgb_batch_glyph_bitmap(const vgb_batch *b, uint32_t i, uint64_t *len);
@@ -188,6 +189,10 @@ int vgb_manager_render_block(const vgb_manager *m, const char *font_id, uint32_t
  * reference's --single-thread, everything on the calling thread. */
 int vgb_manager_render_glyphs(const vgb_manager *m, vgb_writer *w, const vgb_renderer *r, uint32_t shard,
                               uint32_t n_shards, int threads, vgb_stats *stats);
+/* The shard of every (font, block) task of an n_shards-way run: owner[font * 256 + block], fonts in id order
+ * (longest-processing-time-first over per-block cost estimates; SURVEY.md 8(e), task list manager.rs:88-97).
+ * loads (optional, n_shards entries): estimated cost per shard.  Returns the number of entries written or < 0. */
+int vgb_manager_shard_owners(const vgb_manager *m, uint32_t n_shards, uint16_t *owner, size_t cap, uint64_t *loads);
 int vgb_manager_write_index_json(const vgb_manager *m, vgb_writer *w);             /* manager.rs:128-131 */
 int vgb_manager_write_families_json(const vgb_manager *m, vgb_writer *w);          /* manager.rs:134-137 */
 

@@ -7,7 +7,7 @@
  * their published behaviour is restated from SURVEY.md Appendix C and anchored on the
  * reference's own call sites and golden tests (tests/test_oracle_goldens.py).
  *
- * Build: -O2 -ffp-contract=off (no FMA contraction: the reference's f64 op order is the spec).
+ * Build: -O3 -ffp-contract=off (no FMA contraction: the reference's f64 op order is the spec).
  */
 #define _POSIX_C_SOURCE 200809L
 #include "vg_oracle.h"

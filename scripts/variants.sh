@@ -5,17 +5,9 @@ set -u
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 declare -A V=(
   [base]=""
-  [pack0]="-DB200SDF_PACK=0"
-  [pack1]="-DB200SDF_PACK=1"
-  [unroll2]="-DB200SDF_UNROLL=2"
-  [mini32]="-DB200SDF_MINI=32"
-  [mini128]="-DB200SDF_MINI=128"
-  [mini128p1]="-DB200SDF_MINI=128 -DB200SDF_PACK=1"
-  [mini96]="-DB200SDF_MINI=96"
-  [t4x2]="-DB200SDF_TILE_W=4 -DB200SDF_TILE_H=2 -DB200SDF_MAX_ITEMS=128"
-  [t4x2p1]="-DB200SDF_TILE_W=4 -DB200SDF_TILE_H=2 -DB200SDF_MAX_ITEMS=128 -DB200SDF_PACK=1"
-  [t8x2]="-DB200SDF_TILE_W=8 -DB200SDF_TILE_H=2"
-  [csm128]="-DB200SDF_CURVE_SMEM=128"
+  [p8]="-DB200SDF_PERSISTENT_MIN_CTAS=8"
+  [p7]="-DB200SDF_PERSISTENT_MIN_CTAS=7"
+  [p5]="-DB200SDF_PERSISTENT_MIN_CTAS=5"
 )
 if [ "${1:-}" = "build" ]; then
   for n in "${!V[@]}"; do
@@ -27,11 +19,11 @@ else
   WL=${2:-noto}
   mkdir -p $ROOT/gpurun_out
   for n in $(ls $ROOT/build/variants); do
-    VGB200_LIBDIR=$ROOT/build/variants/$n python $ROOT/bench.py --kernel-only --steps 30 --warmup 5 --workload $WL 2>&1 | python -c "
+    VGB200_LIBDIR=$ROOT/build/variants/$n python $ROOT/bench.py --kernel-only --diag --steps 30 --warmup 5 --workload $WL 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('$n', round(d['ms_per_step'],4), 'ms  frac', round(d['roofline']['frac'],4), 'ctas', d['config']['ctas'])
+        d = json.loads(l); print('$n', round(d['ms_per_step'],4), 'ms  decode', round(d['detail']['decode_kernel_ms'],4), 'sdf', round(d['detail']['sdf_kernel_ms'],4), 'host-planned', round(d['detail']['host_planned_sdf_kernel_ms'],4), 'devplan-1cta', round(d['detail']['device_plan_in_one_cta_per_job_kernel_ms'],4))
     elif 'Error' in l or 'error' in l: print('$n', l.strip())
 " | tee -a $ROOT/gpurun_out/variants_$WL.txt
   done

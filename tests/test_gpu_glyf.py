@@ -66,7 +66,14 @@ def _compare_glyf_with_recorder(renderer, font, cps):
             rb = dc[b["src_off"] : b["src_off"] + b["src_cnt"]]
             assert ra.tobytes() == rb.tobytes(), f"curve records of job {gi} differ"
             n_rec += int(a["src_cnt"])
-        assert int(bins.sum()) >= len(glyf_curve_jobs)
+        # the claim order of the tile jobs: every glyph planned, heaviest cost class first (a factor of two per class,
+        # the lightest class open-ended)
+        assert len(bins) >= len(glyf_curve_jobs)
+        cost = bins["ntx"].astype(np.float64) * bins["nty"] * (bins["seg_cnt"].astype(np.float64) + 8.0)
+        heavy = cost > cost.max() / 100.0
+        lg = np.log2(cost[heavy])
+        assert (np.diff(lg) <= 1.001).all(), "tile jobs are not claimed in descending cost-class order"
+        assert heavy[: heavy.sum()].all()
     # end to end: both GPU paths give the same glyph metrics and the same bytes
     renderer.render_batch(g)
     renderer.render_batch(d)

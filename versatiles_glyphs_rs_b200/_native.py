@@ -151,7 +151,6 @@ class GlyphFrame(C.Structure):
 
 KIND_GLYF = 2
 GLYPH_OK, GLYPH_EMPTY, GLYPH_NEEDS_HOST, GLYPH_BAD_REQUEST = 0, 1, 2, 3
-TILE_BINS = 8
 
 
 # name -> (restype, argtypes); the single source of truth for "every symbol the headers declare"
@@ -181,12 +180,12 @@ SDF_SYMBOLS = {
     "b200sdf_font_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u32p]),
     "b200sdf_glyph_tile_bound": (C.c_uint32, [C.c_uint32, C.c_uint32]),
     "b200sdf_submit_glyphs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
-                                        C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
+                                        C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
     "b200sdf_render_glyphs_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
-                                               C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
+                                               C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                                C.c_void_p, C.c_void_p]),
     "b200sdf_decode_glyphs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
-                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, u32p]),
+                                        C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, u32p, C.c_void_p, C.c_uint32]),
     "b200sdf_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, f64p, f64p]),
     "b200sdf_launch_count": (C.c_uint64, [C.c_void_p]),
 }
@@ -234,6 +233,7 @@ HOST_SYMBOLS = {
     "vgb_batch_parts": (C.POINTER(GlyphPart), [C.c_void_p, u32p]),
     "vgb_batch_curve_slots": (C.c_uint32, [C.c_void_p]),
     "vgb_batch_tile_cap": (C.c_uint32, [C.c_void_p]),
+    "vgb_batch_est_cost": (C.c_uint64, [C.c_void_p]),
     "vgb_batch_handed_back": (C.c_uint32, [C.c_void_p]),
     "vgb_batch_glyph_bitmap": (u8p, [C.c_void_p, C.c_uint32, u64p]),
     "vgb_batch_bitmaps": (u8p, [C.c_void_p, u64p]),
@@ -266,6 +266,7 @@ HOST_SYMBOLS = {
     "vgb_manager_block_population": (C.c_int, [C.c_void_p, C.c_char_p, u32p]),
     "vgb_manager_render_block": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.POINTER(u8p), u64p]),
     "vgb_manager_render_glyphs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(Stats)]),
+    "vgb_manager_shard_owners": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint16), C.c_size_t, u64p]),
     "vgb_manager_write_index_json": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vgb_manager_write_families_json": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vgb_pbf_decode": (C.c_int32, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.POINTER(Glyph))]),

@@ -26,6 +26,9 @@ CURVE_DT = np.dtype(
 )
 assert OUTLINE_JOB_DT.itemsize == C.sizeof(N.OutlineJob) and CURVE_DT.itemsize == C.sizeof(N.Curve)
 
+TILE_JOB_DT = np.dtype([("seg_off", "<u4"), ("seg_cnt", "<u4"), ("out_off", "<u8"), ("width", "<u2"), ("height", "<u2"), ("tx0", "<u2"),
+                        ("ty0", "<u2"), ("ntx", "<u2"), ("nty", "<u2"), ("job", "<u4")])
+assert TILE_JOB_DT.itemsize == C.sizeof(N.TileJob) == 32
 GLYPH_PART_DT = np.dtype([("font", "<u4"), ("glyf_off", "<u4"), ("glyf_len", "<u4"), ("ox", "<f4"), ("oy", "<f4")])
 GLYPH_REQ_DT = np.dtype([
     ("kind", "<u4"), ("src_off", "<u4"), ("src_cnt", "<u4"), ("seg_cnt", "<u4"), ("width", "<u4"), ("height", "<u4"),
@@ -330,6 +333,10 @@ class GlyphBatch:
         return N.host.vgb_batch_tile_cap(self._h)
 
     @property
+    def est_cost(self) -> int:
+        return N.host.vgb_batch_est_cost(self._h)
+
+    @property
     def handed_back(self) -> int:
         return N.host.vgb_batch_handed_back(self._h)
 
@@ -486,6 +493,17 @@ class FontManager:
             raise B200Error(N.host_error())
         return RenderStats(*[int(getattr(st, n)) for n, _ in N.Stats._fields_])
 
+    def shard_owners(self, n_shards: int):
+        """-> (owner[font, block] uint16 array over font_ids() x 256 blocks, estimated cost per shard)."""
+        n = len(self.font_ids()) * 256
+        owner = np.zeros(n, dtype=np.uint16)
+        loads = np.zeros(max(1, n_shards), dtype=np.uint64)
+        rc = N.host.vgb_manager_shard_owners(self._h, n_shards, owner.ctypes.data_as(C.POINTER(C.c_uint16)), n,
+                                             loads.ctypes.data_as(N.u64p))
+        if rc < 0:
+            raise B200Error(N.host_error())
+        return owner.reshape(-1, 256), loads
+
     def write_index_json(self, writer: Writer):
         if N.host.vgb_manager_write_index_json(self._h, writer._h) != 0:
             raise B200Error(N.host_error())
@@ -568,24 +586,28 @@ class SdfContext:
             raise B200Error(f"b200sdf_font_upload: {rc}: {self.last_error()}")
         return h.value
 
-    def decode_glyphs(self, reqs: np.ndarray, parts: np.ndarray, curve_slots: int, curves: Optional[np.ndarray] = None, n_seg: int = 0):
-        """b200sdf_decode_glyphs -> (frames, outline jobs, curve scratch, tiles per cost class).  curves / n_seg: the
-        host-recorded arrays CURVES / SEGMENTS requests index."""
+    def decode_glyphs(self, reqs: np.ndarray, parts: np.ndarray, curve_slots: int, curves: Optional[np.ndarray] = None, n_seg: int = 0,
+                      est_cost: int = 0):
+        """b200sdf_decode_glyphs -> (frames, outline jobs, curve scratch, tile jobs in claim order).  curves / n_seg:
+        the host-recorded arrays CURVES / SEGMENTS requests index."""
         reqs = np.ascontiguousarray(reqs, dtype=GLYPH_REQ_DT)
         parts = np.ascontiguousarray(parts, dtype=GLYPH_PART_DT)
         hc = np.zeros(0, dtype=CURVE_DT) if curves is None else np.ascontiguousarray(curves, dtype=CURVE_DT)
         frames = np.zeros(len(reqs), dtype=GLYPH_FRAME_DT)
         jobs = np.zeros(len(reqs), dtype=OUTLINE_JOB_DT)
         curves = np.zeros(max(1, curve_slots), dtype=CURVE_DT)
-        bins = np.zeros(N.TILE_BINS, dtype=np.uint32)
+        n_tiles = C.c_uint32()
+        cap = max(64, 64 * len(reqs))  # decode_glyphs' own tile capacity
+        tiles = np.zeros(cap, dtype=TILE_JOB_DT)
         rc = N.sdf.b200sdf_decode_glyphs(self._h, reqs.ctypes.data, len(reqs), parts.ctypes.data, len(parts),
-                                         hc.ctypes.data if len(hc) else None, len(hc), n_seg, curve_slots, frames.ctypes.data, jobs.ctypes.data, curves.ctypes.data, bins.ctypes.data_as(N.u32p))
+                                         hc.ctypes.data if len(hc) else None, len(hc), n_seg, curve_slots, est_cost, frames.ctypes.data,
+                                         jobs.ctypes.data, curves.ctypes.data, C.byref(n_tiles), tiles.ctypes.data, cap)
         if rc != 0:
             raise B200Error(f"b200sdf_decode_glyphs: {rc}: {self.last_error()}")
-        return frames, jobs, curves[:curve_slots], bins
+        return frames, jobs, curves[:curve_slots], tiles[: min(cap, n_tiles.value)]
 
     def render_glyphs(self, reqs: np.ndarray, parts: np.ndarray, curve_slots: int, tile_cap: int, out_bytes: int,
-                      curves: Optional[np.ndarray] = None, segs: Optional[np.ndarray] = None):
+                      curves: Optional[np.ndarray] = None, segs: Optional[np.ndarray] = None, est_cost: int = 0):
         """b200sdf_submit_glyphs + b200sdf_wait over (pageable) host buffers -> (frames, bitmaps)."""
         reqs = np.ascontiguousarray(reqs, dtype=GLYPH_REQ_DT)
         parts = np.ascontiguousarray(parts, dtype=GLYPH_PART_DT)
@@ -596,7 +618,7 @@ class SdfContext:
         t = C.c_uint64()
         rc = N.sdf.b200sdf_submit_glyphs(self._h, reqs.ctypes.data, len(reqs), parts.ctypes.data, len(parts),
                                          curves.ctypes.data if len(curves) else None, len(curves),
-                                         segs.ctypes.data if len(segs) else None, len(segs), curve_slots, tile_cap,
+                                         segs.ctypes.data if len(segs) else None, len(segs), curve_slots, tile_cap, est_cost,
                                          frames.ctypes.data, out.ctypes.data, out_bytes, C.byref(t))
         if rc == 0:
             rc = N.sdf.b200sdf_wait(self._h, t.value)
@@ -605,10 +627,10 @@ class SdfContext:
         return frames[: len(reqs)], out[:out_bytes]
 
     def render_glyphs_device(self, d_reqs: int, n_reqs: int, d_parts: int, n_parts: int, d_curves: int, n_curves: int, d_segs: int,
-                             n_seg: int, curve_slots: int, tile_cap: int, d_frames: int, d_out: int, out_bytes: int, stream: int = 0,
-                             mid_event: int = 0):
+                             n_seg: int, curve_slots: int, tile_cap: int, est_cost: int, d_frames: int, d_out: int, out_bytes: int,
+                             stream: int = 0, mid_event: int = 0):
         rc = N.sdf.b200sdf_render_glyphs_device(self._h, d_reqs, n_reqs, d_parts, n_parts, d_curves, n_curves, d_segs, n_seg,
-                                                curve_slots, tile_cap, d_frames, d_out, out_bytes, stream, mid_event)
+                                                curve_slots, tile_cap, est_cost, d_frames, d_out, out_bytes, stream, mid_event)
         if rc != 0:
             raise B200Error(f"b200sdf_render_glyphs_device: {rc}: {self.last_error()}")
 

@@ -88,8 +88,9 @@ struct Slot {
 	// glyph-level submissions (b200sdf_submit_glyphs): staged copies of the request arrays when the caller's memory is
 	// not pinned, the device-written curve scratch, and the batch counters with their pinned mirror
 	DevBuf reqs, parts, frames, gcurves;
-	b200sdf::BatchCounters *counters = nullptr;   // device
-	b200sdf::BatchCounters *h_counters = nullptr; // pinned: copied back after the SDF kernel
+	b200sdf::BatchCounters *counters = nullptr; // device
+	uint32_t *h_status = nullptr;               // pinned + mapped: the batch's overflow flag, written by the SDF kernel's last CTA
+	uint32_t *d_status = nullptr;               // its device-side address
 	bool check_overflow = false;
 	void *h_tiles = nullptr; // pinned staging: tile jobs
 	size_t h_tiles_cap = 0;
@@ -687,8 +688,8 @@ void b200sdf_destroy(b200sdf_ctx *ctx)
 				cudaFree(b->p);
 		if (s.counters)
 			cudaFree(s.counters);
-		if (s.h_counters)
-			cudaFreeHost(s.h_counters);
+		if (s.h_status)
+			cudaFreeHost(s.h_status);
 		if (s.h_tiles)
 			b200sdf_free_pinned(s.h_tiles);
 		if (s.done)
@@ -855,7 +856,7 @@ namespace {
 // glyph-level batches: the device reports a tile list that was too short through the counters' mirror
 int finish_slot(b200sdf_ctx *ctx, Slot &s, cudaError_t e, const char *what)
 {
-	const bool overflow = e == cudaSuccess && s.check_overflow && s.h_counters && s.h_counters->overflow != 0;
+	const bool overflow = e == cudaSuccess && s.check_overflow && s.h_status && *(volatile uint32_t *)s.h_status != 0;
 	s.check_overflow = false;
 	report_gpu_trace(ctx, s);
 	release_slot(ctx, s, 0);
@@ -1023,34 +1024,57 @@ int b200sdf_measure_fp32_peak(b200sdf_ctx *ctx, int reps, double *tflops, double
 /* ---- glyph-level path: glyf decoding, metrics and tile planning on the device ---------------------- */
 namespace {
 
-uint32_t persistent_grid(uint32_t n_reqs)
+// the batch's tile jobs: one list of tile_cap entries per cost class
+constexpr size_t kTileScratchPerJob = sizeof(b200sdf_tile_job) * b200sdf::kTileClasses;
+void set_tile_scratch(b200sdf::DecodeParams &P, void *base, uint32_t tile_cap)
 {
-	// one wave of resident CTAs at most; small batches do not need the whole machine
-	const uint64_t want = std::max<uint64_t>(kSMs, (uint64_t)n_reqs * 2u);
-	return (uint32_t)std::min<uint64_t>((uint64_t)kSMs * B200SDF_MIN_CTAS, want);
+	P.tiles = reinterpret_cast<b200sdf_tile_job *>(base);
+	P.tile_cap = tile_cap;
 }
 
-uint32_t glyph_cost_cap()
+uint32_t persistent_grid(uint32_t n_reqs)
 {
-	static const uint32_t v = [] { // B200SDF_GLYPH_COST_CAP: tuning knob (item x segment units per tile job)
+	static const uint32_t forced = [] { // B200SDF_PERSISTENT_GRID: experiments
+		const char *e = std::getenv("B200SDF_PERSISTENT_GRID");
+		const long v = e ? std::atol(e) : 0;
+		return (uint32_t)(v > 0 ? v : 0);
+	}();
+	if (forced)
+		return forced;
+	// one wave of resident CTAs at most; small batches do not need the whole machine
+	const uint64_t want = std::max<uint64_t>(kSMs, (uint64_t)n_reqs * 2u);
+	return (uint32_t)std::min<uint64_t>((uint64_t)kSMs * B200SDF_PERSISTENT_MIN_CTAS, want);
+}
+
+// Largest tile job (item x segment units) before a glyph is cut into several rectangles: the batch's fair share per
+// resident CTA, like the host planner's items_cap — but from the caller's ESTIMATE of the batch's cost (the device has
+// not decoded anything when the launch is made).  Every rectangle repeats the staging of all the glyph's segments, so
+// small batches are not cut below kMinJobCostSmall.  B200SDF_GLYPH_COST_CAP overrides (experiments).
+uint32_t glyph_cost_cap(uint64_t est_cost)
+{
+	static const uint32_t forced = [] {
 		const char *e = std::getenv("B200SDF_GLYPH_COST_CAP");
 		const long x = e ? std::atol(e) : 0;
-		return (uint32_t)(x >= 1024 ? x : 131072);
+		return (uint32_t)(x >= 1024 ? x : 0);
 	}();
-	return v;
+	if (forced)
+		return forced;
+	const uint64_t share = est_cost / ((uint64_t)kSMs * B200SDF_PERSISTENT_MIN_CTAS);
+	return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(share, kMinJobCostSmall), 1u << 30);
 }
 constexpr uint32_t kGlyphMinItems = 8;
 
-void launch_glyph_pipeline(const b200sdf::DecodeParams &P, const void *d_segs, uint8_t *d_out, cudaStream_t stream,
-                           cudaEvent_t mid)
+// The counters are zero when this is called (zeroed when they were allocated, and again by the last CTA of every
+// persistent kernel): a batch is two launches, nothing else.
+void launch_glyph_pipeline(const b200sdf::DecodeParams &P, const void *d_segs, uint8_t *d_out, uint32_t *d_status,
+                           cudaStream_t stream, cudaEvent_t mid)
 {
 	using namespace b200sdf;
-	cudaMemsetAsync(P.counters, 0, sizeof(BatchCounters), stream);
 	glyf_decode_kernel<<<(P.n_reqs + kGlyfWarps - 1) / kGlyfWarps, kGlyfThreads, 0, stream>>>(P);
 	if (mid)
 		cudaEventRecord(mid, stream);
 	sdf_tiles_persistent_kernel<<<persistent_grid(P.n_reqs), kThreads, 0, stream>>>(
-	    reinterpret_cast<const float4 *>(d_segs), P.curves, P.ojobs, P.tiles, P.tile_cap, P.counters, d_out);
+	    reinterpret_cast<const float4 *>(d_segs), P.curves, P.ojobs, P.tiles, P.tile_cap, P.counters, d_status, d_out);
 }
 
 int ensure_font_tables(b200sdf_ctx *ctx)
@@ -1124,8 +1148,8 @@ uint32_t b200sdf_glyph_tile_bound(uint32_t width, uint32_t height)
 
 int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint32_t n_reqs, const b200sdf_glyph_part *parts,
                           uint32_t n_parts, const b200sdf_curve *curves, uint32_t n_curves, const b200sdf_segment *segs,
-                          uint32_t n_seg, uint32_t curve_slots, uint32_t tile_cap, b200sdf_glyph_frame *frames, uint8_t *out,
-                          uint64_t out_bytes, uint64_t *ticket)
+                          uint32_t n_seg, uint32_t curve_slots, uint32_t tile_cap, uint64_t est_cost, b200sdf_glyph_frame *frames,
+                          uint8_t *out, uint64_t out_bytes, uint64_t *ticket)
 {
 	using namespace b200sdf;
 	if (!ctx || !ticket)
@@ -1142,10 +1166,12 @@ int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 		return release_slot(ctx, s, rc);
 	if (!s.counters) {
 		if ((e = cudaMalloc((void **)&s.counters, sizeof(BatchCounters))) != cudaSuccess ||
-		    (e = cudaHostAlloc((void **)&s.h_counters, sizeof(BatchCounters), cudaHostAllocPortable)) != cudaSuccess)
+		    (e = cudaMemset(s.counters, 0, sizeof(BatchCounters))) != cudaSuccess ||
+		    (e = cudaHostAlloc((void **)&s.h_status, 64, cudaHostAllocPortable | cudaHostAllocMapped)) != cudaSuccess ||
+		    (e = cudaHostGetDevicePointer((void **)&s.d_status, s.h_status, 0)) != cudaSuccess)
 			return release_slot(ctx, s, fail_cuda(ctx, e, "cudaMalloc(counters)"));
-		std::memset(s.h_counters, 0, sizeof(BatchCounters));
 	}
+	*s.h_status = 0;
 	if (tile_cap == 0)
 		tile_cap = 1;
 	// what has to exist on the device: [0] segments [1] host curves [2] requests [3] parts [4] frames [5] bitmaps
@@ -1153,7 +1179,7 @@ int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 	size_t need[9] = {(size_t)n_seg * sizeof(b200sdf_segment), (size_t)n_curves * sizeof(b200sdf_curve),
 	                  (size_t)n_reqs * sizeof(b200sdf_glyph_req), (size_t)n_parts * sizeof(b200sdf_glyph_part),
 	                  (size_t)n_reqs * sizeof(b200sdf_glyph_frame), (size_t)out_bytes,
-	                  (size_t)std::max(1u, curve_slots) * sizeof(b200sdf_curve), (size_t)tile_cap * kTileBins * sizeof(b200sdf_tile_job),
+	                  (size_t)std::max(1u, curve_slots) * sizeof(b200sdf_curve), (size_t)tile_cap * kTileScratchPerJob,
 	                  (size_t)n_reqs * sizeof(b200sdf_outline_job)};
 	const bool zc = zero_copy_mode() == 1;
 	const void *k_reqs = zc && n_reqs ? pinned_registry().device_ptr(reqs, need[2]) : nullptr;
@@ -1247,20 +1273,18 @@ int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 		P.curve_slots = curve_slots;
 		P.ojobs = reinterpret_cast<b200sdf_outline_job *>(s.ojobs.p);
 		P.frames = reinterpret_cast<b200sdf_glyph_frame *>(k_frames ? k_frames : s.frames.p);
-		P.tiles = reinterpret_cast<b200sdf_tile_job *>(s.tiles.p);
-		P.tile_cap = tile_cap;
+		set_tile_scratch(P, s.tiles.p, tile_cap);
 		P.out_bytes = out_bytes;
 		P.counters = s.counters;
-		P.cost_cap = glyph_cost_cap();
+		P.cost_cap = glyph_cost_cap(est_cost);
 		P.min_items = kGlyphMinItems;
 		uint8_t *d_out = reinterpret_cast<uint8_t *>(k_out ? k_out : s.out.p);
-		launch_glyph_pipeline(P, s.segs.p, d_out, s.stream, nullptr);
+		launch_glyph_pipeline(P, s.segs.p, d_out, s.d_status, s.stream, nullptr);
 		SUB_TRY(cudaGetLastError());
 		if (!k_frames)
 			SUB_TRY(cudaMemcpyAsync(frames, s.frames.p, (size_t)n_reqs * sizeof(b200sdf_glyph_frame), cudaMemcpyDeviceToHost, s.stream));
 		if (!k_out && out_bytes)
 			SUB_TRY(cudaMemcpyAsync(out, s.out.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, s.stream));
-		SUB_TRY(cudaMemcpyAsync(s.h_counters, s.counters, sizeof(BatchCounters), cudaMemcpyDeviceToHost, s.stream));
 		s.check_overflow = true;
 		if (s.t1 && s.traced_tiles)
 			cudaEventRecord(s.t1, s.stream);
@@ -1279,8 +1303,8 @@ int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 int b200sdf_render_glyphs_device(b200sdf_ctx *ctx, const b200sdf_glyph_req *d_reqs, uint32_t n_reqs,
                                  const b200sdf_glyph_part *d_parts, uint32_t n_parts, const b200sdf_curve *d_curves,
                                  uint32_t n_curves, const b200sdf_segment *d_segs, uint32_t n_seg, uint32_t curve_slots,
-                                 uint32_t tile_cap, b200sdf_glyph_frame *d_frames, uint8_t *d_out, uint64_t out_bytes,
-                                 void *stream, void *mid_event)
+                                 uint32_t tile_cap, uint64_t est_cost, b200sdf_glyph_frame *d_frames, uint8_t *d_out,
+                                 uint64_t out_bytes, void *stream, void *mid_event)
 {
 	using namespace b200sdf;
 	if (!ctx)
@@ -1298,10 +1322,12 @@ int b200sdf_render_glyphs_device(b200sdf_ctx *ctx, const b200sdf_glyph_req *d_re
 	// context-wide scratch: grown outside any timed loop by the first call of a given size (synchronising)
 	if ((rc = grow_plain(ctx, ctx->dv_gcurves, (size_t)std::max(1u, curve_slots) * sizeof(b200sdf_curve))) ||
 	    (rc = grow_plain(ctx, ctx->dv_ojobs, (size_t)n_reqs * sizeof(b200sdf_outline_job))) ||
-	    (rc = grow_plain(ctx, ctx->dv_tiles, (size_t)tile_cap * kTileBins * sizeof(b200sdf_tile_job))))
+	    (rc = grow_plain(ctx, ctx->dv_tiles, (size_t)tile_cap * kTileScratchPerJob)))
 		return rc;
-	if (!ctx->dv_counters)
+	if (!ctx->dv_counters) {
 		CU_TRY(ctx, cudaMalloc((void **)&ctx->dv_counters, sizeof(BatchCounters)));
+		CU_TRY(ctx, cudaMemset(ctx->dv_counters, 0, sizeof(BatchCounters)));
+	}
 	DecodeParams P;
 	P.reqs = d_reqs, P.n_reqs = n_reqs, P.parts = d_parts, P.n_parts = n_parts;
 	P.font_base = ctx->d_font_base, P.font_len = ctx->d_font_len;
@@ -1314,13 +1340,12 @@ int b200sdf_render_glyphs_device(b200sdf_ctx *ctx, const b200sdf_glyph_req *d_re
 	P.curve_slots = curve_slots;
 	P.ojobs = reinterpret_cast<b200sdf_outline_job *>(ctx->dv_ojobs.p);
 	P.frames = d_frames;
-	P.tiles = reinterpret_cast<b200sdf_tile_job *>(ctx->dv_tiles.p);
-	P.tile_cap = tile_cap;
+	set_tile_scratch(P, ctx->dv_tiles.p, tile_cap);
 	P.out_bytes = out_bytes;
 	P.counters = ctx->dv_counters;
-	P.cost_cap = glyph_cost_cap();
+	P.cost_cap = glyph_cost_cap(est_cost);
 	P.min_items = kGlyphMinItems;
-	launch_glyph_pipeline(P, d_segs, d_out, (cudaStream_t)stream, (cudaEvent_t)mid_event);
+	launch_glyph_pipeline(P, d_segs, d_out, nullptr, (cudaStream_t)stream, (cudaEvent_t)mid_event);
 	CU_TRY(ctx, cudaGetLastError());
 	{
 		std::lock_guard<std::mutex> g(ctx->mu);
@@ -1331,8 +1356,8 @@ int b200sdf_render_glyphs_device(b200sdf_ctx *ctx, const b200sdf_glyph_req *d_re
 
 int b200sdf_decode_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint32_t n_reqs, const b200sdf_glyph_part *parts,
                           uint32_t n_parts, const b200sdf_curve *curves, uint32_t n_curves, uint32_t n_seg, uint32_t curve_slots,
-                          b200sdf_glyph_frame *frames, b200sdf_outline_job *jobs_out, b200sdf_curve *curves_out,
-                          uint32_t *tiles_per_bin)
+                          uint64_t est_cost, b200sdf_glyph_frame *frames, b200sdf_outline_job *jobs_out, b200sdf_curve *curves_out,
+                          uint32_t *n_tiles_out, b200sdf_tile_job *tiles_out, uint32_t tiles_cap)
 {
 	using namespace b200sdf;
 	if (!ctx)
@@ -1365,7 +1390,7 @@ int b200sdf_decode_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 	alloc(&d_frames, (size_t)n_reqs * sizeof(b200sdf_glyph_frame));
 	alloc(&d_curves, (size_t)std::max(1u, curve_slots) * sizeof(b200sdf_curve));
 	alloc(&d_ojobs, (size_t)n_reqs * sizeof(b200sdf_outline_job));
-	alloc(&d_tiles, (size_t)tile_cap * kTileBins * sizeof(b200sdf_tile_job));
+	alloc(&d_tiles, (size_t)tile_cap * kTileScratchPerJob);
 	alloc(&d_ctr, sizeof(BatchCounters));
 	alloc(&d_hcurves, (size_t)n_curves * sizeof(b200sdf_curve));
 	if (e == cudaSuccess && n_curves)
@@ -1391,10 +1416,10 @@ int b200sdf_decode_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 		P.curves = reinterpret_cast<b200sdf_curve *>(d_curves), P.curve_slots = curve_slots;
 		P.ojobs = reinterpret_cast<b200sdf_outline_job *>(d_ojobs);
 		P.frames = reinterpret_cast<b200sdf_glyph_frame *>(d_frames);
-		P.tiles = reinterpret_cast<b200sdf_tile_job *>(d_tiles), P.tile_cap = tile_cap;
+		set_tile_scratch(P, d_tiles, tile_cap);
 		P.out_bytes = out_bytes;
 		P.counters = reinterpret_cast<BatchCounters *>(d_ctr);
-		P.cost_cap = glyph_cost_cap(), P.min_items = kGlyphMinItems;
+		P.cost_cap = glyph_cost_cap(est_cost), P.min_items = kGlyphMinItems;
 		glyf_decode_kernel<<<(n_reqs + kGlyfWarps - 1) / kGlyfWarps, kGlyfThreads>>>(P);
 		e = cudaGetLastError();
 		if (e == cudaSuccess)
@@ -1406,11 +1431,20 @@ int b200sdf_decode_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 		e = cudaMemcpy(jobs_out, d_ojobs, (size_t)n_reqs * sizeof(b200sdf_outline_job), cudaMemcpyDeviceToHost);
 	if (e == cudaSuccess && curves_out && curve_slots)
 		e = cudaMemcpy(curves_out, d_curves, (size_t)curve_slots * sizeof(b200sdf_curve), cudaMemcpyDeviceToHost);
-	if (e == cudaSuccess && tiles_per_bin) {
+	if (e == cudaSuccess && (n_tiles_out || tiles_out)) {
+		// the tile jobs in the order the SDF kernel would claim them: class after class
 		BatchCounters h;
 		e = cudaMemcpy(&h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost);
-		for (int b = 0; b < kTileBins; ++b)
-			tiles_per_bin[b] = h.bin_count[b];
+		uint32_t n = 0;
+		for (int c = 0; c < kTileClasses && e == cudaSuccess; ++c) {
+			const uint32_t k = std::min(h.class_count[c], tile_cap);
+			if (tiles_out && n < tiles_cap && k)
+				e = cudaMemcpy(tiles_out + n, reinterpret_cast<b200sdf_tile_job *>(d_tiles) + (size_t)c * tile_cap,
+				               (size_t)std::min(k, tiles_cap - n) * sizeof(b200sdf_tile_job), cudaMemcpyDeviceToHost);
+			n += k;
+		}
+		if (n_tiles_out)
+			*n_tiles_out = n;
 	}
 	for (void *q : {d_reqs, d_parts, d_frames, d_curves, d_ojobs, d_tiles, d_ctr, d_hcurves})
 		if (q)

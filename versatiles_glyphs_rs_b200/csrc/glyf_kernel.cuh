@@ -28,6 +28,9 @@
 #ifndef B200SDF_GLYF_MAX_POINTS
 #define B200SDF_GLYF_MAX_POINTS 2048 // points of one simple glyph record held in shared memory per warp
 #endif
+#ifndef B200SDF_GLYF_STAGE_BYTES
+#define B200SDF_GLYF_STAGE_BYTES 1536 // glyph records up to this size are copied to shared memory before parsing
+#endif
 
 namespace b200sdf {
 
@@ -35,21 +38,28 @@ constexpr int kGlyfWarps = 4;
 constexpr int kGlyfThreads = 32 * kGlyfWarps;
 constexpr int kGlyfMaxPts = B200SDF_GLYF_MAX_POINTS;
 constexpr uint32_t kGlyfMaxDepth = 12;
-constexpr int kTileBins = B200SDF_TILE_BINS;
 
-// Device-side bookkeeping of one batch: tile counts per cost class (filled by glyf_decode_kernel, heaviest class
-// first), the cursor of the persistent SDF kernel, and an overflow flag (tile list too short).
+// Device-side bookkeeping of one batch.  glyf_decode_kernel appends every tile job to the list of its cost class
+// (class_count); the persistent SDF kernel claims them class after class, heaviest first (next_tile), and its last CTA
+// reports overflow and zeroes everything for the slot's next batch.
+constexpr int kTileClasses = 8; // class c: cost in (cap / 2^(c+1), cap / 2^c], the last one open-ended
 struct BatchCounters {
-	uint32_t bin_count[kTileBins];
+	uint32_t class_count[kTileClasses];
 	uint32_t next_tile;
 	uint32_t overflow;
-	uint32_t pad[2];
+	uint32_t done_ctas; // CTAs of the persistent kernel that have finished
+	uint32_t pad;
 };
 
+constexpr int kGlyfStageBytes = B200SDF_GLYF_STAGE_BYTES;
 struct GlyfWarpScratch {
 	int16_t px[kGlyfMaxPts];
 	int16_t py[kGlyfMaxPts];
 	uint8_t flags[kGlyfMaxPts];
+	// The record itself: parsing is a chain of dependent byte reads (header -> end points -> instruction length ->
+	// flags -> x -> y), a microsecond each from cold HBM; one coalesced copy puts the whole chain into shared memory.
+	// Larger records are parsed in place.
+	__align__(16) uint8_t bytes[kGlyfStageBytes + 32];
 };
 
 struct DecodeParams {
@@ -67,7 +77,7 @@ struct DecodeParams {
 	uint32_t curve_slots;
 	b200sdf_outline_job *ojobs;       // device scratch: one per request
 	b200sdf_glyph_frame *frames;      // result per request (pinned host memory or device mirror)
-	b200sdf_tile_job *tiles;          // kTileBins regions of tile_cap entries
+	b200sdf_tile_job *tiles;          // kTileClasses lists of tile_cap entries each
 	uint32_t tile_cap;
 	uint64_t out_bytes;
 	BatchCounters *counters;
@@ -107,7 +117,12 @@ __device__ __forceinline__ double curve_coord_dev(double s, double c, double e, 
 	return lerp_rn_g(lerp_rn_g(s, c, t), lerp_rn_g(c, e, t), t);
 }
 
-// host/render.cc OutlineRecorder::axis_extrema
+// host/render.cc OutlineRecorder::axis_extrema: the extremes of one coordinate over the grid points i / 2^k,
+// 0 < i < 2^k.  The coordinate is monotone either side of its vertex t* = (s - c) / (s - 2c + e), so the extreme grid
+// point is floor(t* 2^k) or ceil(t* 2^k); every candidate evaluated is a point of the polyline, so ANY candidate set
+// that contains those two yields the host's minimum and maximum bit for bit.  The host locates t* with an f64
+// division and looks at four neighbours; an f32 division is off by far less than one grid step (2^k <= 4096), so
+// the same four-neighbour window around the f32 estimate contains them too — without the f64 divide.
 __device__ __forceinline__ void axis_extrema_dev(double s, double c, double e, uint32_t k, double &lo, double &hi)
 {
 	const double mn = s < e ? s : e, mx = s < e ? e : s;
@@ -116,22 +131,29 @@ __device__ __forceinline__ void axis_extrema_dev(double s, double c, double e, u
 	const double a = __dadd_rn(__dsub_rn(s, __dmul_rn(c, 2.0)), e);
 	if (a == 0.0)
 		return;
-	const double ts = __ddiv_rn(__dsub_rn(s, c), a);
-	if (!(ts > 0.0 && ts < 1.0))
-		return;
-	const long long n = 1ll << k;
+	const int n = 1 << k;
+	const float x = __fdividef((float)__dsub_rn(s, c), (float)a) * (float)n; // ~ t* 2^k, |error| << 1
+	if (!(x > -1.0f && x < (float)n + 1.0f))
+		return; // vertex outside (0, 1) — cannot happen when c lies outside [s, e], kept as a guard
 	const double step = __longlong_as_double((long long)(1023 - (int)k) << 52);
-	const long long i0 = (long long)__dmul_rn(ts, (double)n);
+	const int i0 = (int)floorf(x);
 	double l = lo, h = hi;
 #pragma unroll
-	for (long long d = -1; d <= 2; ++d) {
-		long long i = i0 + d;
+	for (int d = -1; d <= 2; ++d) {
+		int i = i0 + d;
 		i = i < 1 ? 1 : (i > n - 1 ? n - 1 : i);
 		const double v = curve_coord_dev(s, c, e, __dmul_rn((double)i, step));
 		l = v < l ? v : l;
 		h = v > h ? v : h;
 	}
 	lo = l, hi = h;
+}
+
+// 0.01 * 16^j, j = 0..12 (host/render.cc kDepthThreshold: PRECISION scaled by exact powers of two)
+__device__ __forceinline__ double depth_threshold(uint32_t j)
+{
+	// 0.01 = 0x3F847AE147AE147B; multiplying by 16^j adds 4j to the exponent field
+	return __longlong_as_double(0x3F847AE147AE147Bll + ((long long)(4 * j) << 52));
 }
 
 __device__ __forceinline__ double warp_min_d(double v)
@@ -153,16 +175,18 @@ __device__ __forceinline__ double warp_max_d(double v)
 	return v;
 }
 
-// cost class of a tile job: class 0 holds the heaviest jobs (the persistent kernel starts there)
-__device__ __host__ __forceinline__ int tile_bin(uint64_t cost)
+// Cost class of a tile job: the largest-first order the host planner sorts into matters for the heavy jobs (one of
+// them is a large share of what a CTA renders in the whole kernel) and not at all for the many light ones, so a
+// factor of two per class is as good as a sort — and costs the decode kernel one atomic per job instead of a pass.
+__device__ __forceinline__ int tile_class(uint64_t cost, uint32_t cost_cap)
 {
-	int b = 0;
-	uint64_t lim = 1ull << 17; // >= 131072 units: class 0
-	while (b < kTileBins - 1 && cost < lim) {
-		++b;
+	int c = 0;
+	uint64_t lim = (uint64_t)cost_cap >> 1;
+	while (c < kTileClasses - 1 && cost <= lim) {
+		++c;
 		lim >>= 1;
 	}
-	return b;
+	return c;
 }
 
 struct GlyphAcc {
@@ -175,13 +199,24 @@ struct GlyphAcc {
 
 // One simple glyph record (g, len) translated by (ox, oy): appends the records of its kept rings at
 // curves[acc.n_rec ..] (at most `room` more) and updates acc.  Warp-collective; returns false on anomaly (acc.status set).
-__device__ __forceinline__ bool decode_simple_glyph(const uint8_t *__restrict__ g, uint32_t len, float ox, float oy,
+__device__ __forceinline__ bool decode_simple_glyph(const uint8_t *g, uint32_t len, float ox, float oy,
                                                     GlyfWarpScratch &ws, b200sdf_curve *__restrict__ curves, uint32_t room,
                                                     GlyphAcc &acc, int lane)
 {
 	// host/face.cc outline_impl, simple-glyph arm
 	if (len < 10) {
 		return true; // `g.len < 10 -> return`: no callbacks
+	}
+	if (len <= (uint32_t)kGlyfStageBytes) {
+		__syncwarp(); // the previous part's parse is over
+		const uint32_t mis = (uint32_t)((uintptr_t)g & 15u);
+		const uint4 *src = reinterpret_cast<const uint4 *>(g - mis); // font blobs are 256-byte aligned and padded by 16 bytes
+		uint4 *dst = reinterpret_cast<uint4 *>(ws.bytes);
+		const uint32_t nvec = (mis + len + 15u) >> 4;
+		for (uint32_t i = (uint32_t)lane; i < nvec; i += 32)
+			dst[i] = __ldg(src + i);
+		__syncwarp();
+		g = ws.bytes + mis;
 	}
 	const int32_t n_contours = be16s(g);
 	if (n_contours == 0)
@@ -334,106 +369,146 @@ __device__ __forceinline__ bool decode_simple_glyph(const uint8_t *__restrict__ 
 	//     i off, p on   -> nothing
 	// with start = q if q is on-curve else mid(q, p).  The ring starts at the first on-curve point (or at the midpoint
 	// of the first two points when both are off-curve): arrivals run s+1 (s+2), ..., e, s (, s+1).
-	for (uint32_t c = 0; c < nc; ++c) {
-		const uint32_t s = c ? be16(end_pts + 2 * (c - 1)) + 1 : 0;
-		const uint32_t e = be16(end_pts + 2 * c);
-		const uint32_t n = e - s + 1;
-		if (n == 1)
-			continue; // one on-curve point: a 2-point ring, dropped; one off-curve point: no callbacks
-		const uint32_t a0 = (ws.flags[s] & 1u) ? 1u : 2u; // first arrival, relative to s
-		uint32_t ring_rec = 0, ring_seg = 0;
-		double rx0 = __longlong_as_double(0x7ff0000000000000ll), ry0 = rx0;
-		double rx1 = __longlong_as_double(0xfff0000000000000ll), ry1 = rx1;
-		bool bad = false, over = false;
-		for (uint32_t j0 = 0; j0 < n; j0 += 32) {
-			const uint32_t j = j0 + (uint32_t)lane;
-			bool has = false;
-			b200sdf_curve r;
-			r.sx = r.sy = r.cx = r.cy = r.ex = r.ey = 0.f;
-			r.seg_off = 0, r.depth = 0;
-			if (j < n) {
-				uint32_t ri = a0 + j;
-				ri = ri >= n ? ri - n : ri; // a0 + j < n + 2 <= 2n
-				const uint32_t rp = ri ? ri - 1 : n - 1, rq = rp ? rp - 1 : n - 1;
-				const uint32_t i = s + ri, p = s + rp, q = s + rq;
-				const bool on_i = ws.flags[i] & 1u, on_p = ws.flags[p] & 1u, on_q = ws.flags[q] & 1u;
-				has = on_i || !on_p;
-				if (has) {
-					const float ix = (float)ws.px[i], iy = (float)ws.py[i];
-					const float pxf = (float)ws.px[p], pyf = (float)ws.py[p];
-					// (the host transforms AFTER taking midpoints of the untransformed points: same order here)
-					if (on_i && on_p) {
-						r.sx = __fadd_rn(pxf, ox), r.sy = __fadd_rn(pyf, oy);
-						r.cx = r.sx, r.cy = r.sy;
-						r.ex = __fadd_rn(ix, ox), r.ey = __fadd_rn(iy, oy);
-					} else {
-						const float qx = (float)ws.px[q], qy = (float)ws.py[q];
-						float sx = qx, sy = qy;
-						if (!on_q) { // lerp_half(q, p) = q + 0.5 (p - q)
-							sx = __fadd_rn(qx, __fmul_rn(0.5f, __fsub_rn(pxf, qx)));
-							sy = __fadd_rn(qy, __fmul_rn(0.5f, __fsub_rn(pyf, qy)));
-						}
-						float ex = ix, ey = iy;
-						if (!on_i) { // lerp_half(p, i)
-							ex = __fadd_rn(pxf, __fmul_rn(0.5f, __fsub_rn(ix, pxf)));
-							ey = __fadd_rn(pyf, __fmul_rn(0.5f, __fsub_rn(iy, pyf)));
-						}
-						r.sx = __fadd_rn(sx, ox), r.sy = __fadd_rn(sy, oy);
-						r.cx = __fadd_rn(pxf, ox), r.cy = __fadd_rn(pyf, oy);
-						r.ex = __fadd_rn(ex, ox), r.ey = __fadd_rn(ey, oy);
-						// Ring::add_quadratic_bezier's test at the root (ring.rs:128-131), depth counted against 0.01 * 16^j
-						const double ddx = __dsub_rn(__dadd_rn((double)r.sx, (double)r.ex), __dmul_rn((double)r.cx, 2.0));
-						const double ddy = __dsub_rn(__dadd_rn((double)r.sy, (double)r.ey), __dmul_rn((double)r.cy, 2.0));
-						const double v = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
-						uint32_t k = 0;
-						double thr = 0.01;
-#pragma unroll
-						for (uint32_t t = 0; t <= kGlyfMaxDepth; ++t, thr = __dmul_rn(thr, 16.0))
-							k += v > thr ? 1u : 0u;
-						bad |= k > kGlyfMaxDepth;
-						r.depth = k > kGlyfMaxDepth ? 0u : k;
-					}
-					bad |= !dyadic_ok_dev(r.sx) || !dyadic_ok_dev(r.sy) || !dyadic_ok_dev(r.cx) || !dyadic_ok_dev(r.cy) ||
-					       !dyadic_ok_dev(r.ex) || !dyadic_ok_dev(r.ey);
-					// bounding box of the flattened points: end point + the grid points next to each coordinate's vertex
-					const double exd = (double)r.ex, eyd = (double)r.ey;
-					rx0 = exd < rx0 ? exd : rx0, rx1 = exd > rx1 ? exd : rx1;
-					ry0 = eyd < ry0 ? eyd : ry0, ry1 = eyd > ry1 ? eyd : ry1;
-					if (r.depth) {
-						axis_extrema_dev((double)r.sx, (double)r.cx, exd, r.depth, rx0, rx1);
-						axis_extrema_dev((double)r.sy, (double)r.cy, eyd, r.depth, ry0, ry1);
-					}
-				}
-			}
-			const uint32_t hm = __ballot_sync(0xffffffffu, has);
-			const int nseg = has ? (1 << r.depth) : 0;
-			const int sincl = warp_incl_scan(nseg, lane);
+	//
+	// "Slot" t = the t-th arrival of the record in emission order (contour after contour, each in its rotated order);
+	// the warp takes 32 slots at a time whatever contours they belong to — a glyph of a hundred small contours is a
+	// dozen passes, not a hundred.  A ring is dropped when it ends with fewer than 4 points (ring_builder.rs:33-54):
+	// only contours of at most 4 points can be (five arrivals give at least three segments), and a window never splits
+	// such a contour, so its segment total is a few shuffles away.
+	auto contour_of = [&](uint32_t t) { // smallest c with end_pts[c] >= t
+		uint32_t lo = 0, hi = nc - 1;
+		while (lo < hi) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (be16(end_pts + 2 * mid) < t)
+				lo = mid + 1;
+			else
+				hi = mid;
+		}
+		return lo;
+	};
+	double rx0 = __longlong_as_double(0x7ff0000000000000ll), ry0 = rx0;
+	double rx1 = __longlong_as_double(0xfff0000000000000ll), ry1 = rx1;
+	bool bad = false, over = false;
+	uint32_t rec_base = acc.n_rec, seg_base = acc.n_seg, rings_kept = 0;
+	for (uint32_t t0 = 0; t0 < n_points;) {
+		uint32_t t1 = min(t0 + 32u, n_points);
+		if (t1 < n_points) { // do not split a contour that may be dropped
+			const uint32_t cl = contour_of(t1 - 1);
+			const uint32_t sl = cl ? be16(end_pts + 2 * (cl - 1)) + 1 : 0, el = be16(end_pts + 2 * cl);
+			if (el >= t1 && el - sl + 1 <= 4)
+				t1 = sl; // > t0: the contour has at most 4 slots, the window 32
+		}
+		const uint32_t t = t0 + (uint32_t)lane;
+		const bool valid = t < t1;
+		bool has = false;
+		uint32_t s = 0, e = 0, n = 1;
+		b200sdf_curve r;
+		r.sx = r.sy = r.cx = r.cy = r.ex = r.ey = 0.f;
+		r.seg_off = 0, r.depth = 0;
+		if (valid) {
+			const uint32_t c = contour_of(t);
+			s = c ? be16(end_pts + 2 * (c - 1)) + 1 : 0;
+			e = be16(end_pts + 2 * c);
+			n = e - s + 1;
+		}
+		if (valid && n >= 2) { // (one on-curve point: a 2-point ring, dropped; one off-curve point: no callbacks)
+			const uint32_t a0 = (ws.flags[s] & 1u) ? 1u : 2u; // first arrival, relative to s
+			uint32_t ri = a0 + (t - s);
+			ri = ri >= n ? ri - n : ri; // a0 + j < n + 2 <= 2n
+			const uint32_t rp = ri ? ri - 1 : n - 1, rq = rp ? rp - 1 : n - 1;
+			const uint32_t i = s + ri, p = s + rp, q = s + rq;
+			const bool on_i = ws.flags[i] & 1u, on_p = ws.flags[p] & 1u, on_q = ws.flags[q] & 1u;
+			has = on_i || !on_p;
 			if (has) {
-				const uint32_t idx = acc.n_rec + ring_rec + (uint32_t)__popc(hm & ((1u << lane) - 1u));
-				r.seg_off = acc.n_seg + ring_seg + (uint32_t)(sincl - nseg);
-				if (idx < room)
-					curves[idx] = r;
-				else
-					over = true;
+				const float ix = (float)ws.px[i], iy = (float)ws.py[i];
+				const float pxf = (float)ws.px[p], pyf = (float)ws.py[p];
+				// (the host transforms AFTER taking midpoints of the untransformed points: same order here)
+				if (on_i && on_p) {
+					r.sx = __fadd_rn(pxf, ox), r.sy = __fadd_rn(pyf, oy);
+					r.cx = r.sx, r.cy = r.sy;
+					r.ex = __fadd_rn(ix, ox), r.ey = __fadd_rn(iy, oy);
+				} else {
+					const float qx = (float)ws.px[q], qy = (float)ws.py[q];
+					float sx = qx, sy = qy;
+					if (!on_q) { // lerp_half(q, p) = q + 0.5 (p - q)
+						sx = __fadd_rn(qx, __fmul_rn(0.5f, __fsub_rn(pxf, qx)));
+						sy = __fadd_rn(qy, __fmul_rn(0.5f, __fsub_rn(pyf, qy)));
+					}
+					float ex = ix, ey = iy;
+					if (!on_i) { // lerp_half(p, i)
+						ex = __fadd_rn(pxf, __fmul_rn(0.5f, __fsub_rn(ix, pxf)));
+						ey = __fadd_rn(pyf, __fmul_rn(0.5f, __fsub_rn(iy, pyf)));
+					}
+					r.sx = __fadd_rn(sx, ox), r.sy = __fadd_rn(sy, oy);
+					r.cx = __fadd_rn(pxf, ox), r.cy = __fadd_rn(pyf, oy);
+					r.ex = __fadd_rn(ex, ox), r.ey = __fadd_rn(ey, oy);
+					// Ring::add_quadratic_bezier's test at the root (ring.rs:128-131), depth counted against 0.01 * 16^j
+					const double ddx = __dsub_rn(__dadd_rn((double)r.sx, (double)r.ex), __dmul_rn((double)r.cx, 2.0));
+					const double ddy = __dsub_rn(__dadd_rn((double)r.sy, (double)r.ey), __dmul_rn((double)r.cy, 2.0));
+					const double v = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+					uint32_t k = 0;
+#pragma unroll
+					for (uint32_t d = 0; d <= kGlyfMaxDepth; ++d)
+						k += v > depth_threshold(d) ? 1u : 0u;
+					bad |= k > kGlyfMaxDepth;
+					r.depth = k > kGlyfMaxDepth ? 0u : k;
+				}
+				bad |= !dyadic_ok_dev(r.sx) || !dyadic_ok_dev(r.sy) || !dyadic_ok_dev(r.cx) || !dyadic_ok_dev(r.cy) ||
+				       !dyadic_ok_dev(r.ex) || !dyadic_ok_dev(r.ey);
 			}
-			ring_rec += (uint32_t)__popc(hm);
-			ring_seg += (uint32_t)__shfl_sync(0xffffffffu, sincl, 31);
 		}
-		if (__any_sync(0xffffffffu, bad || over)) {
-			acc.status = B200SDF_GLYPH_NEEDS_HOST;
-			return false;
+		int nseg = has ? (1 << r.depth) : 0;
+		// segments of my contour when it is small enough to be dropped (it lies inside this window)
+		bool keep = n >= 2;
+		{
+			int tot = 0;
+			const int first = (int)(s - t0); // lane of the contour's first slot (only used when n <= 4)
+#pragma unroll
+			for (int d = 0; d < 4; ++d) {
+				const int v = __shfl_sync(0xffffffffu, nseg, (first + d) & 31);
+				tot += (s + (uint32_t)d <= e) ? v : 0;
+			}
+			if (n <= 4)
+				keep = n >= 2 && 1 + tot >= 4;
 		}
-		// ring_builder.rs:33-54 on point counts: 1 + segments points; the closing segment is explicit, so Ring::close adds none
-		if (1u + ring_seg >= 4u) {
-			acc.n_rec += ring_rec;
-			acc.n_seg += ring_seg;
-			acc.rings += 1;
-			rx0 = warp_min_d(rx0), ry0 = warp_min_d(ry0), rx1 = warp_max_d(rx1), ry1 = warp_max_d(ry1);
-			acc.bx0 = rx0 < acc.bx0 ? rx0 : acc.bx0, acc.by0 = ry0 < acc.by0 ? ry0 : acc.by0;
-			acc.bx1 = rx1 > acc.bx1 ? rx1 : acc.bx1, acc.by1 = ry1 > acc.by1 ? ry1 : acc.by1;
+		const bool emit = has && keep;
+		nseg = emit ? nseg : 0;
+		const uint32_t em = __ballot_sync(0xffffffffu, emit);
+		const int sincl = warp_incl_scan(nseg, lane);
+		if (emit) {
+			const uint32_t idx = rec_base + (uint32_t)__popc(em & ((1u << lane) - 1u));
+			r.seg_off = seg_base + (uint32_t)(sincl - nseg);
+			if (idx < room)
+				curves[idx] = r;
+			else
+				over = true;
+			// bounding box of the flattened points: end point + the grid points next to each coordinate's vertex
+			const double exd = (double)r.ex, eyd = (double)r.ey;
+			rx0 = exd < rx0 ? exd : rx0, rx1 = exd > rx1 ? exd : rx1;
+			ry0 = eyd < ry0 ? eyd : ry0, ry1 = eyd > ry1 ? eyd : ry1;
+			if (r.depth) {
+				axis_extrema_dev((double)r.sx, (double)r.cx, exd, r.depth, rx0, rx1);
+				axis_extrema_dev((double)r.sy, (double)r.cy, eyd, r.depth, ry0, ry1);
+			}
 		}
-		__syncwarp();
+		rec_base += (uint32_t)__popc(em);
+		seg_base += (uint32_t)__shfl_sync(0xffffffffu, sincl, 31);
+		rings_kept += (uint32_t)__popc(__ballot_sync(0xffffffffu, valid && t == e && keep));
+		t0 = t1;
 	}
+	if (__any_sync(0xffffffffu, bad || over)) {
+		acc.status = B200SDF_GLYPH_NEEDS_HOST;
+		return false;
+	}
+	if (rings_kept) {
+		acc.n_rec = rec_base;
+		acc.n_seg = seg_base;
+		acc.rings += rings_kept;
+		rx0 = warp_min_d(rx0), ry0 = warp_min_d(ry0), rx1 = warp_max_d(rx1), ry1 = warp_max_d(ry1);
+		acc.bx0 = rx0 < acc.bx0 ? rx0 : acc.bx0, acc.by0 = ry0 < acc.by0 ? ry0 : acc.by0;
+		acc.bx1 = rx1 > acc.bx1 ? rx1 : acc.bx1, acc.by1 = ry1 > acc.by1 ? ry1 : acc.by1;
+	}
+	__syncwarp();
 	return true;
 }
 
@@ -466,22 +541,17 @@ __device__ __forceinline__ void plan_tiles_dev(const DecodeParams &P, uint32_t s
 		t.nty = (uint16_t)min(rows_per, ny - ty);
 		t.job = job;
 		const uint64_t cost = (uint64_t)t.ntx * t.nty * (uint64_t)(seg_cnt + 8);
-		const int bin = tile_bin(cost);
-		const uint32_t at = atomicAdd(&P.counters->bin_count[bin], 1u);
+		const int cls = tile_class(cost, P.cost_cap);
+		const uint32_t at = atomicAdd(&P.counters->class_count[cls], 1u);
 		if (at < P.tile_cap)
-			P.tiles[(size_t)bin * P.tile_cap + at] = t;
+			P.tiles[(size_t)cls * P.tile_cap + at] = t;
 		else
 			atomicExch(&P.counters->overflow, 1u);
 	}
 }
 
-__global__ void __launch_bounds__(kGlyfThreads) glyf_decode_kernel(const DecodeParams P)
+__device__ __forceinline__ void decode_request(const DecodeParams &P, const uint32_t gi, GlyfWarpScratch &wscratch, const int lane)
 {
-	__shared__ GlyfWarpScratch scratch[kGlyfWarps];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t gi = blockIdx.x * kGlyfWarps + (uint32_t)warp;
-	if (gi >= P.n_reqs)
-		return;
 	const b200sdf_glyph_req rq = P.reqs[gi];
 	b200sdf_glyph_frame fr;
 	fr.x0 = rq.x0, fr.y0 = rq.y0, fr.width = 0, fr.height = 0, fr.seg_cnt = 0, fr.status = B200SDF_GLYPH_EMPTY;
@@ -508,7 +578,7 @@ __global__ void __launch_bounds__(kGlyfThreads) glyf_decode_kernel(const DecodeP
 				acc.status = B200SDF_GLYPH_BAD_REQUEST;
 				break;
 			}
-			if (!decode_simple_glyph(P.font_base[pt.font] + pt.glyf_off, pt.glyf_len, pt.ox, pt.oy, scratch[warp],
+			if (!decode_simple_glyph(P.font_base[pt.font] + pt.glyf_off, pt.glyf_len, pt.ox, pt.oy, wscratch,
 			                         P.curves + rq.curve_off, rq.curve_cap, acc, lane))
 				break;
 		}
@@ -579,6 +649,18 @@ __global__ void __launch_bounds__(kGlyfThreads) glyf_decode_kernel(const DecodeP
 	if (fr.status == B200SDF_GLYPH_OK)
 		plan_tiles_dev(P, oj.src_off, oj.seg_cnt, oj.width, oj.height, oj.out_off,
 		               oj.kind == B200SDF_KIND_SEGMENTS ? B200SDF_NO_JOB : gi, lane);
+}
+
+#ifndef B200SDF_GLYF_MIN_CTAS
+#define B200SDF_GLYF_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(kGlyfThreads, B200SDF_GLYF_MIN_CTAS) glyf_decode_kernel(const DecodeParams P)
+{
+	__shared__ GlyfWarpScratch scratch[kGlyfWarps];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t gi = blockIdx.x * kGlyfWarps + (uint32_t)warp;
+	if (gi < P.n_reqs)
+		decode_request(P, gi, scratch[warp], lane);
 }
 
 } // namespace b200sdf

@@ -334,6 +334,7 @@ const b200sdf_glyph_part *vgb_batch_parts(const vgb_batch *b, uint32_t *n)
 }
 uint32_t vgb_batch_curve_slots(const vgb_batch *b) { return b->b->curve_slots(); }
 uint32_t vgb_batch_tile_cap(const vgb_batch *b) { return b->b->tile_cap(); }
+uint64_t vgb_batch_est_cost(const vgb_batch *b) { return b->b->est_cost(); }
 uint32_t vgb_batch_handed_back(const vgb_batch *b) { return b->b->handed_back(); }
 const uint8_t *vgb_batch_glyph_bitmap(const vgb_batch *b, uint32_t i, uint64_t *len)
 {
@@ -538,6 +539,19 @@ int vgb_manager_render_glyphs(const vgb_manager *m, vgb_writer *w, const vgb_ren
 		stats->cost_shard = st.cost_shard;
 	}
 	return 0;
+}
+int vgb_manager_shard_owners(const vgb_manager *m, uint32_t n_shards, uint16_t *owner, size_t cap, uint64_t *loads)
+{
+	std::vector<uint16_t> o;
+	std::vector<uint64_t> l;
+	m->m.shard_owners(n_shards, o, &l);
+	if (cap < o.size())
+		return fail("shard_owners: buffer too small (fonts x 256 entries)");
+	std::memcpy(owner, o.data(), o.size() * sizeof(uint16_t));
+	if (loads)
+		for (size_t k = 0; k < l.size(); ++k)
+			loads[k] = l[k];
+	return (int)o.size();
 }
 int vgb_manager_write_index_json(const vgb_manager *m, vgb_writer *w)
 {

@@ -201,6 +201,10 @@ class FontManager {
 	// sharding used across GPUs (every shard still writes its own directories).
 	bool render_glyphs(Writer &writer, const Renderer &renderer, std::string *err, RenderStats *stats = nullptr,
 	                   uint32_t shard = 0, uint32_t n_shards = 1, int threads = 0) const;
+	// The shard every (font, block) task belongs to when the job is cut into n_shards: owner[font * 256 + block], fonts in
+	// id order.  Longest-processing-time-first over FontWrapper::block_costs; deterministic, so every
+	// rank of a multi-GPU run computes the same table.  loads (optional): estimated cost per shard.
+	void shard_owners(uint32_t n_shards, std::vector<uint16_t> &owner, std::vector<uint64_t> *loads = nullptr) const;
 	// manager.rs:128-131 (font ids as a JSON array)
 	bool write_index_json(Writer &writer, std::string *err) const;
 	// manager.rs:134-137 (font_families.json, index_files.rs:115-139)

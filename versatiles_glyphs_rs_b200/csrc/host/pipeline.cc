@@ -134,6 +134,40 @@ class WorkerPool {
 };
 } // namespace
 
+void FontManager::shard_owners(uint32_t n_shards, std::vector<uint16_t> &owner, std::vector<uint64_t> *loads) const
+{
+	constexpr uint32_t kBlocks = 0x10000 / GLYPH_BLOCK_SIZE;
+	struct Item {
+		uint64_t cost;
+		uint32_t index;
+	};
+	if (n_shards == 0)
+		n_shards = 1;
+	std::vector<Item> items;
+	items.reserve(fonts_.size() * kBlocks);
+	uint32_t fi = 0;
+	for (const auto &kv : fonts_) {
+		const std::vector<uint64_t> &costs = kv.second.block_costs();
+		for (uint32_t i = 0; i < kBlocks; ++i)
+			items.push_back(Item{costs[i], fi * kBlocks + i});
+		++fi;
+	}
+	// longest processing time first: heaviest task to the least loaded shard (ties: lowest task index, lowest shard)
+	std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.cost > b.cost; });
+	std::vector<uint64_t> load(n_shards, 0);
+	owner.assign(items.size(), 0);
+	for (const Item &it : items) {
+		uint32_t best = 0;
+		for (uint32_t k = 1; k < n_shards; ++k)
+			if (load[k] < load[best])
+				best = k;
+		load[best] += it.cost;
+		owner[it.index] = (uint16_t)best;
+	}
+	if (loads)
+		*loads = std::move(load);
+}
+
 bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::string *err, RenderStats *stats,
                                 uint32_t shard, uint32_t n_shards, int threads) const
 {
@@ -158,11 +192,14 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	// no worker is stuck recording 256 outlines while the others (and the GPU) run dry.  The parts of a
 	// block are encoded independently (Fontstack.glyphs entries) and the worker that finishes the last
 	// one assembles and writes the file.
-	static const size_t kPartGlyphs = [] { // tuning knob (default 64; measured 16 / 32 / 64 on C2)
+	// (When the device decodes the outlines itself a glyph costs the host a quarter of a microsecond: blocks stay whole.)
+	static const size_t kPartGlyphsEnv = [] { // tuning knob (measured 16 / 32 / 64 on C2 with host-side recording)
 		const char *e = std::getenv("VGB_PART_GLYPHS");
 		const long v = e ? std::atol(e) : 0;
-		return (size_t)(v >= 1 && v <= 256 ? v : 64);
+		return (size_t)(v >= 1 && v <= 256 ? v : 0);
 	}();
+	const bool glyf_mode = renderer.flatten() == Flatten::Glyf && renderer.mode() == Renderer::Mode::Cuda;
+	const size_t kPartGlyphs = kPartGlyphsEnv ? kPartGlyphsEnv : (glyf_mode ? 256 : 64);
 	struct BlockState {
 		const std::string *name = nullptr;
 		const GlyphBlock *blk = nullptr;
@@ -186,31 +223,10 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	std::vector<uint16_t> owner; // owner[font * 256 + block]
 	uint64_t cost_total = 0, cost_mine = 0;
 	if (n_shards > 1) {
-		struct Item {
-			uint64_t cost;
-			uint32_t index;
-		};
-		std::vector<Item> items;
-		items.reserve(fonts_.size() * kBlocks);
-		uint32_t fi = 0;
-		for (const auto &kv : fonts_) {
-			const std::vector<uint64_t> &costs = kv.second.block_costs();
-			for (uint32_t i = 0; i < kBlocks; ++i)
-				items.push_back(Item{costs[i], fi * kBlocks + i});
-			++fi;
-		}
-		std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.cost > b.cost; });
-		std::vector<uint64_t> load(n_shards, 0);
-		owner.assign(items.size(), 0);
-		for (const Item &it : items) {
-			uint32_t best = 0;
-			for (uint32_t k = 1; k < n_shards; ++k)
-				if (load[k] < load[best])
-					best = k;
-			load[best] += it.cost;
-			owner[it.index] = (uint16_t)best;
-			cost_total += it.cost;
-		}
+		std::vector<uint64_t> load;
+		shard_owners(n_shards, owner, &load);
+		for (uint64_t l : load)
+			cost_total += l;
 		cost_mine = shard < n_shards ? load[shard] : 0;
 	}
 	uint32_t index = 0;
@@ -286,17 +302,20 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	const int workers = dedicated ? total_threads - 1 : total_threads;
 	// One submission carries whole blocks until it holds about `target` glyphs: small jobs keep one
 	// block per submission (parallelism), big jobs amortise the per-submission cost.
-	static const size_t kBatchesPerWorker = [] { // tuning knob (default 4; measured 1..6 on C2)
+	static const size_t kBatchesPerWorkerEnv = [] { // tuning knob (measured 1..6 on C2)
 		const char *e = std::getenv("VGB_BATCHES_PER_WORKER");
 		const long v = e ? std::atol(e) : 0;
-		return (size_t)(v >= 1 && v <= 64 ? v : 4);
+		return (size_t)(v >= 1 && v <= 64 ? v : 0);
 	}();
+	const size_t kBatchesPerWorker = kBatchesPerWorkerEnv ? kBatchesPerWorkerEnv : (glyf_mode ? 2 : 4);
 	constexpr int kEarlyWorkers = 4;
 	static const bool kLatencyTail = [] { // VGB_LATENCY_TAIL=1: plan each worker's last batch for latency
 		const char *e = std::getenv("VGB_LATENCY_TAIL"); // (measured on C2: 1.30-1.35 ms with, 1.26-1.34 without: off)
 		return e && e[0] == '1';
 	}();
-	const size_t target = std::min<size_t>(2048, std::max<size_t>(1, total_glyphs / ((size_t)workers * kBatchesPerWorker)));
+	const size_t target = glyf_mode ? std::min<size_t>(4096, std::max<size_t>(192, (total_glyphs + (size_t)workers * kBatchesPerWorker - 1) /
+	                                                                                   ((size_t)workers * kBatchesPerWorker)))
+	                                : std::min<size_t>(2048, std::max<size_t>(1, total_glyphs / ((size_t)workers * kBatchesPerWorker)));
 	std::atomic<size_t> next{0};
 	std::atomic<size_t> glyphs_taken{0};
 	std::atomic<bool> failed{false};
@@ -519,6 +538,10 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				size_t want = std::max<size_t>(kPartGlyphs, std::min(target, left / ((size_t)workers * 2)));
 				if (n_batches == 0) // staggered openings: the workers do not all submit at the same moments
 					want = wid < kEarlyWorkers ? kPartGlyphs : std::min(target, kPartGlyphs * (size_t)(1 + wid % 4));
+				// Device-side decoding: filling a batch costs microseconds, submitting one costs the CUDA thread ~15 us and
+				// a kernel pair under a few hundred glyphs runs as long as its heaviest tile: equal, large batches.
+				if (glyf_mode)
+					want = target;
 				++n_batches;
 				while (cur->batch->glyphs().size() < want) {
 					const size_t ti = next.fetch_add(1);

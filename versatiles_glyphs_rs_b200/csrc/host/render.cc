@@ -313,7 +313,7 @@ void GlyphBatch::clear()
 	n_tiles_ = 0;
 	prepared_ = false;
 	n_parts_ = curve_slots_ = tile_cap_ = n_handed_back_ = 0;
-	pixels_ = 0;
+	pixels_ = est_cost_ = 0;
 	finalized_ = false;
 	failed_ = false;
 	failure_ = "";
@@ -378,6 +378,7 @@ bool GlyphBatch::push_job(const b200sdf_outline_job &j)
 			curve_slots_ += j.src_cnt;
 		}
 		tile_cap_ += b200sdf_glyph_tile_bound(j.width, j.height);
+		est_cost_ += (uint64_t)((j.width + 3) / 4) * ((j.height + 3) / 4) * ((uint64_t)j.seg_cnt + 8);
 		if (!push_req(r))
 			return false;
 	}
@@ -630,6 +631,7 @@ bool GlyphBatch::add_glyf_request(const Face &face, uint32_t index, uint32_t adv
 	n_parts_ += (uint32_t)parts_tmp_.size();
 	curve_slots_ += points;
 	tile_cap_ += b200sdf_glyph_tile_bound(wi, hi);
+	est_cost_ += (uint64_t)((wi + 3) / 4) * ((hi + 3) / 4) * ((uint64_t)points * 8 + 8); // ~8 flattened segments per outline point
 	out_bytes_ = r.out_off + r.out_cap;
 	glyphs_.push_back(g);
 	return true;
@@ -945,7 +947,8 @@ bool Renderer::submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *er
 		}
 		const int grc = b200sdf_submit_glyphs(ctx_, batch.reqs(), batch.job_count(), batch.parts(), batch.part_count(), batch.curves(),
 		                                      batch.curve_count(), batch.segments(), batch.segment_count(), batch.curve_slots(),
-		                                      batch.tile_cap(), batch.frames(), batch.bitmaps(), batch.bitmap_bytes(), ticket);
+		                                      batch.tile_cap(), batch.est_cost(), batch.frames(), batch.bitmaps(), batch.bitmap_bytes(),
+		                                      ticket);
 		if (grc != 0) {
 			if (err)
 				*err = std::string("b200sdf_submit_glyphs: ") + b200sdf_last_error(ctx_);

@@ -214,6 +214,7 @@ class GlyphBatch {
 	uint32_t part_count() const { return n_parts_; }
 	uint32_t curve_slots() const { return curve_slots_; }
 	uint32_t tile_cap() const { return tile_cap_; }
+	uint64_t est_cost() const { return est_cost_; } // estimated tile x segment units of the batch (b200sdf_submit_glyphs)
 	bool ensure_frames(); // allocate the frame array (after the last add)
 	// After the batch came back: take frames and bitmap presence from the device's answers; glyphs it handed back
 	// (B200SDF_GLYPH_NEEDS_HOST) are recorded on the host and rendered through `renderer` now.  false + *err on failure.
@@ -260,7 +261,7 @@ class GlyphBatch {
 	std::vector<Face::GlyfPart> parts_tmp_;
 	std::vector<uint8_t> extra_;
 	uint32_t n_parts_ = 0, curve_slots_ = 0, tile_cap_ = 0, n_handed_back_ = 0;
-	uint64_t pixels_ = 0;
+	uint64_t pixels_ = 0, est_cost_ = 0;
 	bool finalized_ = false;
 	bool failed_ = false;
 	const char *failure_ = "";

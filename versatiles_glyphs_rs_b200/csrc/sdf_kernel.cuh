@@ -46,6 +46,9 @@
 #define B200SDF_MIN_CTAS 8 // __launch_bounds__ minimum CTAs per SM: 64 registers (measured 6 / 7 / 8 with the shared-staging loop: 0.475 / 0.459 / 0.442 ms)
 #endif
 #define B200SDF_BOUNDS __launch_bounds__(128, B200SDF_MIN_CTAS)
+#ifndef B200SDF_PERSISTENT_MIN_CTAS
+#define B200SDF_PERSISTENT_MIN_CTAS 6 // resident CTAs per SM of the persistent kernel (80 registers)
+#endif
 #ifndef B200SDF_ALGO
 // 1 = every pixel x every segment through the clamped projection (11 flop per pair);
 // 2 = the same minimum split into   min over vertices  (one FFMA + half an FMNMX3 per pair)
@@ -162,6 +165,15 @@ struct SharedStorage {
 	uint64_t bar[kWarps][2];          // per-warp mbarriers of the raw double buffer
 	uint64_t curve_bar;
 	int st_nv[kWarps], st_nl[kWarps]; // shared staging: vertices / long records each warp staged this round
+	// mbarrier phases of a CTA that renders several tile jobs one after the other (the barriers are initialised once):
+	// completed uses of curve_bar, and of each warp's two raw-segment barriers.  Kept here, not in registers: the
+	// persistent kernel's loop must not carry state through the hot loops.
+	uint32_t ph_curve;
+	uint32_t ph_raw[kWarps][2];
+	// persistent kernel: the tile job claimed for the CTA's next round (claimed while the current job's epilogue runs)
+	uint32_t next_t, total;
+	uint32_t class_end[kTileClasses]; // claim index space: class c holds claims [class_end[c - 1], class_end[c])
+	b200sdf_tile_job next_job;
 };
 
 struct Rect {
@@ -330,16 +342,34 @@ __device__ __forceinline__ uint32_t curves_of_32(const b200sdf_curve *__restrict
 
 static_assert(kThreads == 128, "B200SDF_BOUNDS");
 
-// mbarrier phases of a CTA that renders several tile jobs one after the other (the barriers are initialised once)
-struct BarrierPhases {
-	uint32_t curve;  // completed uses of curve_bar (CTA-uniform)
-	uint32_t raw[2]; // completed uses of this warp's two raw-segment barriers
-};
-
 // One tile job.  `rot` rotates the warps' roles (see below); the caller has initialised the mbarriers and made sure
 // (a CTA-wide barrier) that nobody still reads the shared storage of a previous job.
-__device__ __forceinline__ void render_tile(SharedStorage &sm, const b200sdf_tile_job job, const uint32_t rot,
-                                            BarrierPhases &ph, const float4 *__restrict__ segs,
+// where claim number t lives: class after class, heaviest first
+__device__ __forceinline__ const b200sdf_tile_job *claimed_tile(const SharedStorage &sm, const b200sdf_tile_job *tiles,
+                                                               uint32_t tile_cap, uint32_t t)
+{
+	int c = 0;
+	uint32_t first = 0;
+#pragma unroll
+	for (int k = 0; k < kTileClasses - 1; ++k)
+		if (t >= sm.class_end[k]) { // non-decreasing: the last hit is the class boundary below t
+			c = k + 1;
+			first = sm.class_end[k];
+		}
+	return tiles + (size_t)c * tile_cap + (t - first);
+}
+
+// claim: persistent kernel only — the batch's cursor and its tile lists; null otherwise.
+// One copy of the tile code, called (not inlined) by both kernels: measured on C2, the call costs nothing and the
+// separately allocated function is faster than either inlined copy (0.452 -> 0.433 ms one CTA per job, 0.524 -> 0.485 ms
+// persistent); the persistent kernel additionally prefers 6 fatter CTAs per SM to 8 (0.485 -> 0.453 ms).
+#ifndef B200SDF_TILE_INLINE
+#define B200SDF_TILE_INLINE __noinline__
+#endif
+__device__ B200SDF_TILE_INLINE void render_tile(SharedStorage &sm, const b200sdf_tile_job job, const uint32_t rot,
+                                            BatchCounters *__restrict__ claim_ctr,
+                                            const b200sdf_tile_job *__restrict__ claim_tiles, const uint32_t claim_cap,
+                                            const float4 *__restrict__ segs,
                                             const b200sdf_curve *__restrict__ curves,
                                             const b200sdf_outline_job *__restrict__ ojobs, uint8_t *__restrict__ out)
 {
@@ -441,8 +471,7 @@ __device__ __forceinline__ void render_tile(SharedStorage &sm, const b200sdf_til
 #endif
 
 	if (curves_in_smem) {
-		mbar_wait(&sm.curve_bar, ph.curve & 1u);
-		ph.curve++;
+		mbar_wait(&sm.curve_bar, sm.ph_curve & 1u); // (incremented at the end of the job, after a CTA-wide barrier)
 		gcurves = sm.src.curves;
 	}
 
@@ -650,13 +679,13 @@ __device__ __forceinline__ void render_tile(SharedStorage &sm, const b200sdf_til
 			// ---- stage: every lane turns up to kMini/32 segments into records ----
 #if B200SDF_ALGO == 2
 			if (!from_curves)
-				mbar_wait(&sm.bar[warp][b], (ph.raw[b] + (m >> 1)) & 1u);
+				mbar_wait(&sm.bar[warp][b], (sm.ph_raw[warp][b] + (m >> 1)) & 1u);
 			int nv = 0;
 			const int n_long = stage(ws, raw[b], base, n, c_lo, scatter, nv);
 #else
 			const int n_long = n;
 			if (!from_curves) {
-				mbar_wait(&sm.bar[warp][b], (ph.raw[b] + (m >> 1)) & 1u);
+				mbar_wait(&sm.bar[warp][b], (sm.ph_raw[warp][b] + (m >> 1)) & 1u);
 				for (int i = lane; i < n; i += 32)
 					stage_segment(raw[b][i], ws.recA[i], ws.recN[i], sm.delta, R, scatter);
 			} else {
@@ -679,10 +708,11 @@ __device__ __forceinline__ void render_tile(SharedStorage &sm, const b200sdf_til
 			long_loop(ws, n_long, lslice, lslices);
 			__syncwarp(); // records are overwritten by the next staging pass
 		}
-		if (!from_curves) { // buffer b was used for passes b, b + 2, ...
-			ph.raw[0] += (n_mini + 1) >> 1;
-			ph.raw[1] += n_mini >> 1;
+		if (!from_curves && lane == 0) { // buffer b was used for passes b, b + 2, ... (the loop ended with a __syncwarp)
+			sm.ph_raw[warp][0] += (n_mini + 1) >> 1;
+			sm.ph_raw[warp][1] += n_mini >> 1;
 		}
+		__syncwarp();
 	}
 
 	// ---- merge slices ----
@@ -701,6 +731,14 @@ __device__ __forceinline__ void render_tile(SharedStorage &sm, const b200sdf_til
 		}
 	}
 	__syncthreads();
+	if (tid == 0 && curves_in_smem)
+		sm.ph_curve++; // every thread is past its wait on curve_bar
+	// Persistent kernel: claim the next job NOW — late enough that the greedy largest-first order still holds (a claim
+	// made at the start of a job would hand the heaviest jobs out two at a time), early enough that the atomic and the
+	// load of the job record overlap this job's epilogue.
+	uint32_t claimed = 0xffffffffu;
+	if (claim_ctr && tid == kThreads - 1)
+		claimed = atomicAdd(&claim_ctr->next_tile, 1u);
 
 	// ---- epilogue: winding prefix, quantise (renderer_precise.rs:67-79), stage in output order ----
 	// Output rows run top (largest y) to bottom; the rectangle's rows [ry0, ry0+rh) map to output
@@ -723,6 +761,11 @@ __device__ __forceinline__ void render_tile(SharedStorage &sm, const b200sdf_til
 			sm.obuf[mis + (uint32_t)((R.rh - 1 - y) * R.rw + x)] = q;
 		else
 			out[(size_t)job.out_off + (size_t)(H - 1 - (R.ry0 + y)) * (size_t)W + (size_t)(R.rx0 + x)] = q;
+	}
+	if (claim_ctr && tid == kThreads - 1) {
+		sm.next_t = claimed;
+		if (claimed < sm.total)
+			sm.next_job = *claimed_tile(sm, claim_tiles, claim_cap, claimed);
 	}
 	if (!full_width)
 		return;
@@ -747,11 +790,14 @@ __device__ __forceinline__ void init_barriers(SharedStorage &sm)
 	const int tid = threadIdx.x;
 	if (tid == 0) {
 		mbar_init(&sm.curve_bar, 1);
+		sm.ph_curve = 0;
 		fence_mbar_init();
 	}
 	if ((tid & 31) == 0) {
 		mbar_init(&sm.bar[tid >> 5][0], 1);
 		mbar_init(&sm.bar[tid >> 5][1], 1);
+		sm.ph_raw[tid >> 5][0] = 0;
+		sm.ph_raw[tid >> 5][1] = 0;
 		fence_mbar_init();
 	}
 }
@@ -763,49 +809,58 @@ __global__ void B200SDF_BOUNDS sdf_tiles_kernel(const float4 *__restrict__ segs,
 {
 	__shared__ __align__(128) SharedStorage sm;
 	init_barriers(sm); // render_tile's first CTA-wide barrier orders this before any use
-	BarrierPhases ph;
-	ph.curve = 0, ph.raw[0] = 0, ph.raw[1] = 0;
-	render_tile(sm, jobs[blockIdx.x], blockIdx.x, ph, segs, curves, ojobs, out);
+	render_tile(sm, jobs[blockIdx.x], blockIdx.x, nullptr, nullptr, 0, segs, curves, ojobs, out);
 }
 
 // Persistent form for batches planned on the device (glyf_decode_kernel): the grid is sized for the machine, not for
-// the batch — whose tile count the host never learns — and every CTA claims tile jobs from the batch's cursor until
-// the classes are exhausted, heaviest class first (what the host's largest-first sort does for the other kernel).
-__global__ void B200SDF_BOUNDS sdf_tiles_persistent_kernel(const float4 *__restrict__ segs,
-                                                           const b200sdf_curve *__restrict__ curves,
-                                                           const b200sdf_outline_job *__restrict__ ojobs,
-                                                           const b200sdf_tile_job *__restrict__ tiles, const uint32_t tile_cap,
-                                                           BatchCounters *__restrict__ ctr, uint8_t *__restrict__ out)
+// the batch — whose tile count the host never learns — and every CTA claims tile jobs from the batch's cursor, cost
+// class after cost class (heaviest first: what the host's largest-first sort does for the other kernel), until none
+// is left.  The next job is claimed while the current one's epilogue runs (render_tile).  The
+// last CTA to finish publishes the batch's overflow flag to *status_out and zeroes the counters for the slot's next
+// batch.
+__global__ void __launch_bounds__(128, B200SDF_PERSISTENT_MIN_CTAS) sdf_tiles_persistent_kernel(
+    const float4 *__restrict__ segs, const b200sdf_curve *__restrict__ curves, const b200sdf_outline_job *__restrict__ ojobs,
+    const b200sdf_tile_job *__restrict__ tiles, const uint32_t tile_cap, BatchCounters *__restrict__ ctr,
+    uint32_t *__restrict__ status_out, uint8_t *__restrict__ out)
 {
 	__shared__ __align__(128) SharedStorage sm;
-	__shared__ uint32_t s_next;
 	init_barriers(sm);
-	BarrierPhases ph;
-	ph.curve = 0, ph.raw[0] = 0, ph.raw[1] = 0;
-	uint32_t cum[kTileBins];
-	uint32_t total = 0;
+	if (threadIdx.x == 0) {
+		uint32_t run = 0;
 #pragma unroll
-	for (int b = 0; b < kTileBins; ++b) {
-		total += min(ctr->bin_count[b], tile_cap);
-		cum[b] = total;
+		for (int c = 0; c < kTileClasses; ++c) {
+			run += min(ctr->class_count[c], tile_cap);
+			sm.class_end[c] = run;
+		}
+		const uint32_t t = atomicAdd(&ctr->next_tile, 1u);
+		sm.total = run;
+		sm.next_t = t;
+		if (t < run)
+			sm.next_job = *claimed_tile(sm, tiles, tile_cap, t);
 	}
 	for (;;) {
-		__syncthreads(); // everybody is done with the previous job's shared storage (and with s_next)
-		if (threadIdx.x == 0)
-			s_next = atomicAdd(&ctr->next_tile, 1u);
-		__syncthreads();
-		const uint32_t t = s_next;
-		if (t >= total)
-			return;
-		int b = 0;
-		uint32_t first = 0;
+		__syncthreads(); // the claim is visible; everybody is done with the previous job's shared storage
+		const uint32_t t = sm.next_t;
+		if (t >= sm.total)
+			break;
+		const b200sdf_tile_job job = sm.next_job;
+		__syncthreads(); // everybody holds the job before the claiming thread may overwrite it
+		render_tile(sm, job, t, ctr, tiles, tile_cap, segs, curves, ojobs, out);
+	}
+	if (threadIdx.x == 0) {
+		__threadfence();
+		if (atomicAdd(&ctr->done_ctas, 1u) == gridDim.x - 1) {
+			// every other CTA has left its loop: nobody reads the counters any more
+			if (status_out)
+				*status_out = ctr->overflow;
 #pragma unroll
-		for (int k = 0; k < kTileBins - 1; ++k)
-			if (t >= cum[k]) { // cum is non-decreasing: the last hit is the class boundary below t
-				b = k + 1;
-				first = cum[k];
-			}
-		render_tile(sm, tiles[(size_t)b * tile_cap + (t - first)], t, ph, segs, curves, ojobs, out);
+			for (int c = 0; c < kTileClasses; ++c)
+				ctr->class_count[c] = 0;
+			ctr->next_tile = 0;
+			ctr->overflow = 0;
+			ctr->done_ctas = 0;
+			__threadfence_system();
+		}
 	}
 }
 
