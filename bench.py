@@ -313,7 +313,7 @@ class Job:
         self.reqs, self.parts = batch.requests(), batch.parts()
         self.hcurves, self.hsegs = batch.curves(), batch.segments().copy()
         self.curve_slots, self.tile_cap, self.est_cost = batch.curve_slots, batch.tile_cap, batch.est_cost
-        self.out_bytes = int(self.reqs["out_off"][-1] + self.reqs["out_cap"][-1]) if len(self.reqs) else 0
+        self.out_bytes = int((self.reqs["out_off"] + self.reqs["out_cap"]).max()) if len(self.reqs) else 0
 
         def to_dev(a):
             return torch.from_numpy(np.frombuffer(a.tobytes() or b"\0" * 16, dtype=np.uint8).copy()).to(dev)

@@ -212,6 +212,25 @@ def _font_parity(data, renderer, name, blocks):
     return px, same
 
 
+def test_first_calls_on_a_fresh_renderer_are_deterministic():
+    """The first render_glyphs calls of a renderer — slots used for the first time, pooled buffers still growing,
+    fonts being uploaded — give the same bytes as every later call.  (A device-side counter block that was zeroed on
+    the legacy default stream instead of the slot's stream once lost the last tile jobs of a slot's first batch.)"""
+    m = V.FontManager(parallel=True)
+    m.add_font_with_name("Noto Sans Regular", O.noto_paths())
+    for _ in range(3):
+        r = V.Renderer.new_precise(device=0)
+        runs = []
+        for _ in range(6):
+            w = V.Writer.new_memory()
+            m.render_glyphs(w, r)
+            runs.append({n: d for n, is_dir, d in w.entries() if not is_dir})
+        for k in range(1, len(runs)):
+            bad = [n for n in runs[0] if runs[0][n] != runs[k][n]]
+            assert not bad, (k, bad[:4])
+        del r
+
+
 def test_c3_dense_outlines_parity(renderer):
     """Synthetic dense outlines (K = 8..64 strokes, up to ~10 k segments per glyph, overlapping and
     counter-wound rings): segment staging over many chunks + winding numbers beyond 0/1."""

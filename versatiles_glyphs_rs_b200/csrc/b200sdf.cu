@@ -1085,6 +1085,7 @@ int ensure_font_tables(b200sdf_ctx *ctx)
 	CU_TRY(ctx, cudaMalloc((void **)&ctx->d_font_len, kMaxFonts * sizeof(uint64_t)));
 	CU_TRY(ctx, cudaMemset((void *)ctx->d_font_base, 0, kMaxFonts * sizeof(void *)));
 	CU_TRY(ctx, cudaMemset(ctx->d_font_len, 0, kMaxFonts * sizeof(uint64_t)));
+	CU_TRY(ctx, cudaDeviceSynchronize()); // the memsets run on the legacy default stream: done before any table entry is written or read
 	return 0;
 }
 
@@ -1119,6 +1120,7 @@ int b200sdf_font_upload(b200sdf_ctx *ctx, const uint8_t *glyf, uint64_t len, uin
 	if (len)
 		CU_TRY(ctx, cudaMemcpy(d, glyf, (size_t)len, cudaMemcpyHostToDevice));
 	CU_TRY(ctx, cudaMemset((uint8_t *)d + len, 0, 16));
+	CU_TRY(ctx, cudaStreamSynchronize(0)); // (legacy default stream: the slots' non-blocking streams do not wait for it)
 	uint32_t h;
 	{
 		std::lock_guard<std::mutex> g(ctx->mu);
@@ -1135,6 +1137,7 @@ int b200sdf_font_upload(b200sdf_ctx *ctx, const uint8_t *glyf, uint64_t len, uin
 	const void *dp = d;
 	CU_TRY(ctx, cudaMemcpy((void *)(ctx->d_font_base + h), &dp, sizeof(void *), cudaMemcpyHostToDevice));
 	CU_TRY(ctx, cudaMemcpy(ctx->d_font_len + h, &len, sizeof(uint64_t), cudaMemcpyHostToDevice));
+	CU_TRY(ctx, cudaStreamSynchronize(0));
 	*handle = h;
 	return 0;
 }
@@ -1165,8 +1168,11 @@ int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 	if (rc)
 		return release_slot(ctx, s, rc);
 	if (!s.counters) {
+		// (zeroed ON THE SLOT'S STREAM: a plain cudaMemset runs on the legacy default stream, which a non-blocking stream
+		// does not wait for — the first batch's decode kernel would count its tile jobs into counters that are wiped
+		// a moment later)
 		if ((e = cudaMalloc((void **)&s.counters, sizeof(BatchCounters))) != cudaSuccess ||
-		    (e = cudaMemset(s.counters, 0, sizeof(BatchCounters))) != cudaSuccess ||
+		    (e = cudaMemsetAsync(s.counters, 0, sizeof(BatchCounters), s.stream)) != cudaSuccess ||
 		    (e = cudaHostAlloc((void **)&s.h_status, 64, cudaHostAllocPortable | cudaHostAllocMapped)) != cudaSuccess ||
 		    (e = cudaHostGetDevicePointer((void **)&s.d_status, s.h_status, 0)) != cudaSuccess)
 			return release_slot(ctx, s, fail_cuda(ctx, e, "cudaMalloc(counters)"));
@@ -1326,7 +1332,7 @@ int b200sdf_render_glyphs_device(b200sdf_ctx *ctx, const b200sdf_glyph_req *d_re
 		return rc;
 	if (!ctx->dv_counters) {
 		CU_TRY(ctx, cudaMalloc((void **)&ctx->dv_counters, sizeof(BatchCounters)));
-		CU_TRY(ctx, cudaMemset(ctx->dv_counters, 0, sizeof(BatchCounters)));
+		CU_TRY(ctx, cudaMemsetAsync(ctx->dv_counters, 0, sizeof(BatchCounters), (cudaStream_t)stream)); // ordered before the kernels below
 	}
 	DecodeParams P;
 	P.reqs = d_reqs, P.n_reqs = n_reqs, P.parts = d_parts, P.n_parts = n_parts;

@@ -260,6 +260,7 @@ __device__ __forceinline__ bool decode_simple_glyph(const uint8_t *g, uint32_t l
 	// Whether a byte is a flag or a repeat count depends on its predecessor: count[i] = repeat_bit[i-1] & !count[i-1],
 	// i.e. a byte is a count iff the run of repeat-bit bytes ending just before it has odd length.
 	uint32_t flags_end = 0;
+	uint32_t x_bytes = 0, y_bytes = 0; // sizes of the coordinate arrays, summed while the flags are expanded
 	{
 		uint32_t k = 0, p = pos;
 		bool carry_rep = false;
@@ -291,11 +292,18 @@ __device__ __forceinline__ bool decode_simple_glyph(const uint8_t *g, uint32_t l
 				acc.status = B200SDF_GLYPH_NEEDS_HOST;
 				return false;
 			}
+			uint32_t sizes = 0; // x bytes | y bytes << 16 of the points this flag byte stands for
 			if (consumed) {
 				const uint32_t stop = min(start + (uint32_t)cnt, n_points);
 				for (uint32_t q = start; q < stop; ++q)
 					ws.flags[q] = (uint8_t)byte;
+				const uint32_t xs = (byte & 0x02u) ? 1u : ((byte & 0x10u) ? 0u : 2u);
+				const uint32_t ys = (byte & 0x04u) ? 1u : ((byte & 0x20u) ? 0u : 2u);
+				sizes = (xs | (ys << 16)) * (stop - start); // <= 2 * 2048 per half
 			}
+			sizes = __reduce_add_sync(0xffffffffu, sizes);
+			x_bytes += sizes & 0xffffu;
+			y_bytes += sizes >> 16;
 			const uint32_t total = (uint32_t)__shfl_sync(0xffffffffu, incl, 31);
 			const uint32_t cm = __ballot_sync(0xffffffffu, consumed);
 			if (k + total >= n_points) {
@@ -314,15 +322,6 @@ __device__ __forceinline__ bool decode_simple_glyph(const uint8_t *g, uint32_t l
 	__syncwarp();
 
 	// ---- coordinates: byte offsets and values by prefix sums ----------------------------------------------
-	uint32_t x_bytes = 0, y_bytes = 0;
-	for (uint32_t i0 = 0; i0 < n_points; i0 += 32) {
-		const uint32_t i = i0 + (uint32_t)lane;
-		const uint32_t f = i < n_points ? ws.flags[i] : 0x30u; // padding lanes: zero-size deltas
-		const int xs = (f & 0x02u) ? 1 : ((f & 0x10u) ? 0 : 2);
-		const int ys = (f & 0x04u) ? 1 : ((f & 0x20u) ? 0 : 2);
-		x_bytes += (uint32_t)__shfl_sync(0xffffffffu, warp_incl_scan(xs, lane), 31);
-		y_bytes += (uint32_t)__shfl_sync(0xffffffffu, warp_incl_scan(ys, lane), 31);
-	}
 	if (flags_end + x_bytes + y_bytes > len) { // truncated coordinate arrays (host: partial outline)
 		acc.status = B200SDF_GLYPH_NEEDS_HOST;
 		return false;
@@ -335,7 +334,8 @@ __device__ __forceinline__ bool decode_simple_glyph(const uint8_t *g, uint32_t l
 			const uint32_t f = i < n_points ? ws.flags[i] : 0x30u;
 			const int xs = (f & 0x02u) ? 1 : ((f & 0x10u) ? 0 : 2);
 			const int ys = (f & 0x04u) ? 1 : ((f & 0x20u) ? 0 : 2);
-			const int xi = warp_incl_scan(xs, lane), yi = warp_incl_scan(ys, lane);
+			const int both = warp_incl_scan(xs | (ys << 16), lane); // both prefix sums at once (<= 64 each)
+			const int xi = both & 0xffff, yi = both >> 16;
 			const uint8_t *xp = g + xpos + (uint32_t)(xi - xs);
 			const uint8_t *yp = g + ypos + (uint32_t)(yi - ys);
 			int32_t dx = 0, dy = 0;

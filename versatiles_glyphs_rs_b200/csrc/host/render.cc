@@ -314,6 +314,8 @@ void GlyphBatch::clear()
 	prepared_ = false;
 	n_parts_ = curve_slots_ = tile_cap_ = n_handed_back_ = 0;
 	pixels_ = est_cost_ = 0;
+	job_glyph_.clear();
+	n_heavy_ = 0;
 	finalized_ = false;
 	failed_ = false;
 	failure_ = "";
@@ -381,6 +383,7 @@ bool GlyphBatch::push_job(const b200sdf_outline_job &j)
 		est_cost_ += (uint64_t)((j.width + 3) / 4) * ((j.height + 3) / 4) * ((uint64_t)j.seg_cnt + 8);
 		if (!push_req(r))
 			return false;
+		job_glyph_.push_back((uint32_t)glyphs_.size()); // (the glyph is appended right after its job)
 	}
 	reinterpret_cast<b200sdf_outline_job *>(jobs_.data())[n_jobs_++] = j;
 	out_bytes_ += (uint64_t)j.width * j.height;
@@ -633,8 +636,26 @@ bool GlyphBatch::add_glyf_request(const Face &face, uint32_t index, uint32_t adv
 	tile_cap_ += b200sdf_glyph_tile_bound(wi, hi);
 	est_cost_ += (uint64_t)((wi + 3) / 4) * ((hi + 3) / 4) * ((uint64_t)points * 8 + 8); // ~8 flattened segments per outline point
 	out_bytes_ = r.out_off + r.out_cap;
+	job_glyph_.push_back((uint32_t)glyphs_.size());
 	glyphs_.push_back(g);
+	constexpr uint32_t kHeavyPoints = 160;
+	if (points >= kHeavyPoints)
+		move_to_front(g.job);
 	return true;
+}
+
+void GlyphBatch::move_to_front(uint32_t job)
+{
+	const uint32_t to = n_heavy_++;
+	if (job == to)
+		return;
+	b200sdf_glyph_req *rv = reinterpret_cast<b200sdf_glyph_req *>(reqs_.data());
+	b200sdf_outline_job *jv = reinterpret_cast<b200sdf_outline_job *>(jobs_.data());
+	std::swap(rv[job], rv[to]);
+	std::swap(jv[job], jv[to]);
+	std::swap(job_glyph_[job], job_glyph_[to]);
+	glyphs_[job_glyph_[job]].job = job;
+	glyphs_[job_glyph_[to]].job = to;
 }
 
 bool GlyphBatch::ensure_output() { return out_.reserve((size_t)out_bytes_ + 16, 0); }

@@ -262,6 +262,11 @@ class GlyphBatch {
 	std::vector<uint8_t> extra_;
 	uint32_t n_parts_ = 0, curve_slots_ = 0, tile_cap_ = 0, n_handed_back_ = 0;
 	uint64_t pixels_ = 0, est_cost_ = 0;
+	// Glyf mode: requests of glyphs with many outline points are kept at the front of the request array — the decode
+	// kernel takes requests in order, one warp each, and a glyph of several hundred points is that kernel's critical path
+	std::vector<uint32_t> job_glyph_; // request index -> glyph index
+	uint32_t n_heavy_ = 0;
+	void move_to_front(uint32_t job);
 	bool finalized_ = false;
 	bool failed_ = false;
 	const char *failure_ = "";

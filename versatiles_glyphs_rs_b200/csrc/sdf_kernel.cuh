@@ -829,7 +829,8 @@ __global__ void __launch_bounds__(128, B200SDF_PERSISTENT_MIN_CTAS) sdf_tiles_pe
 		uint32_t run = 0;
 #pragma unroll
 		for (int c = 0; c < kTileClasses; ++c) {
-			run += min(ctr->class_count[c], tile_cap);
+			// (read at L2, where the decode kernel's atomics left them)
+			run += min(__ldcg(&ctr->class_count[c]), tile_cap);
 			sm.class_end[c] = run;
 		}
 		const uint32_t t = atomicAdd(&ctr->next_tile, 1u);
