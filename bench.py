@@ -674,7 +674,7 @@ def main():
             assert not (c4f["status"] >= N.GLYPH_NEEDS_HOST).any()
             c4ok = c4f["status"] == N.GLYPH_OK
             c4pairs = int((c4f["width"][c4ok].astype(np.int64) * c4f["height"][c4ok] * c4f["seg_cnt"][c4ok]).sum())
-            for _ in range(3):
+            for _ in range(8):  # (pooled pinned buffers reach their steady-state size)
                 c4.manager.render_glyphs(V.Writer.new_memory(), renderer, shard=rank, n_shards=world, threads=host_threads)
             barrier()
             c4ms = []
