@@ -55,6 +55,12 @@ size_t vgb_font_codepoints(const vgb_font *f, uint32_t *out, size_t cap);  /* me
 int32_t vgb_font_outline_rings(const vgb_font *f, uint32_t glyph_id, double **xy, uint32_t **ring_start,
                                uint32_t *n_points);
 
+/* The raw outline callbacks of Face::outline_glyph (ttf_parser::OutlineBuilder, src/render/renderer.rs:109-110), before
+ * any flattening: malloc'd 7 floats per command — kind (0 move_to, 1 line_to, 2 quad_to, 3 curve_to, 4 close),
+ * x1, y1, x2, y2, x, y (unused fields 0).  Returns the number of commands; free with vgb_free.  Used by the
+ * cross-check against FreeType (tests/test_freetype_crosscheck.py). */
+int32_t vgb_font_outline_commands(const vgb_font *f, uint32_t glyph_id, float **cmds);
+
 /* ---- geometry (src/geometry/ring.rs:119-187, segment.rs:96-99) ---- */
 size_t vgb_flatten_quad(const double s[2], const double c[2], const double e[2], double tol_sq, double *out_xy, size_t cap);
 size_t vgb_flatten_cubic(const double s[2], const double c1[2], const double c2[2], const double e[2], double tol_sq,

@@ -215,6 +215,9 @@ def build_font(codepoints, strokes_for, seed=0xB200, family="Synth B200", cmap_f
     maxp = struct.pack(">IH", 0x00005000, n_glyphs)
     hm = np.zeros((n_glyphs, 2), dtype=">u2")
     hm[:, 0] = advances
+    # left side bearing = the record's xMin, as in any well-formed font (FreeType shifts an outline whose xMin differs
+    # from its lsb; ttf-parser — the reference — does not look at it)
+    hm[:, 1] = [struct.unpack(">h", g[2:4])[0] & 0xFFFF if len(g) >= 10 else 0 for g in glyf]
     hmtx = hm.tobytes()
     fam = family.encode("utf-16-be")
     name = struct.pack(">HHH", 0, 1, 6 + 12) + struct.pack(">HHHHHH", 3, 1, 0x409, 1, len(fam), 0) + fam

@@ -239,6 +239,97 @@ def test_c3_dense_outlines_parity(renderer):
     print(f"C3 dense: {px} px, {100 * same / px:.4f}% identical")
 
 
+def test_c3_full_dense_font_strided_sample(renderer):
+    """The bench's C3 itself — all 4096 dense glyphs (0.5 k .. 9 k segments each) through FontManager.render_glyphs — with
+    every 37th glyph checked against the oracle (metrics exact, bitmap within 1, >= 99.9 % identical)."""
+    data = synth_font.dense_font(4096)
+    name, fid = "Synth Dense", "synth_dense"
+    m = V.FontManager(parallel=True)
+    m.add_font_bytes_with_name(name, data)
+    w = V.Writer.new_memory()
+    st = m.render_glyphs(w, renderer)
+    assert st.glyphs == 4096 and st.bitmaps == 4096 and st.handed_back == 0
+    glyphs = {}
+    for n, is_dir, d in w.entries():
+        if not is_dir and n.endswith(".pbf"):
+            for g in V.decode_pbf(d)[2]:
+                glyphs[g.id] = g
+    assert len(glyphs) == 4096
+    ofont = O.Font(data)
+    px = same = 0
+    for cp in range(0x4E00, 0x4E00 + 4096, 37):
+        want, got = ofont.render_glyph(cp), glyphs[cp]
+        assert (got.width, got.height, got.left, got.top, got.advance) == (
+            want["width"], want["height"], want["left"], want["top"], want["advance"]), hex(cp)
+        diff = np.abs(np.frombuffer(got.bitmap, np.uint8).astype(np.int16) - want["bitmap"].astype(np.int16))
+        assert diff.max() <= 1, hex(cp)
+        px += diff.size
+        same += int((diff == 0).sum())
+    assert px > 80000 and same / px >= MIN_IDENTICAL, same / px
+    print(f"C3 full, strided sample: {px} px, {100 * same / px:.4f}% identical")
+
+
+def test_c5_recurse_directory_with_fonts_json(renderer, tmp_path):
+    """BASELINE.json configs[4]: a `recurse` input directory — fira/<file> + noto/fonts.json naming the 20 Noto files as
+    ONE font (commands/recurse.rs:104-133: a directory with a fonts.json contributes exactly what it lists) — through
+    FontManager.scan, rendered sharded 8 ways by font x GlyphBlock into a directory sink; the union of the shards is the
+    unsharded run, index.json / font_families.json are written, and every block matches the oracle."""
+    import json
+    import shutil
+
+    src = tmp_path / "fonts"
+    (src / "fira").mkdir(parents=True)
+    (src / "noto").mkdir()
+    shutil.copy(O.FIRA, src / "fira" / os.path.basename(O.FIRA))
+    names = []
+    for p in O.noto_paths():
+        shutil.copy(p, src / "noto" / os.path.basename(p))
+        names.append(os.path.basename(p))
+    (src / "noto" / "fonts.json").write_text(json.dumps([{"name": "Noto Sans Regular", "sources": names}]))
+    (src / "noto" / "README.txt").write_text("not a font")
+    m = V.FontManager(parallel=True)
+    m.scan(str(src))
+    assert m.font_ids() == ["fira_sans_regular", "noto_sans_regular"]
+    whole = V.Writer.new_memory()
+    st = m.render_glyphs(whole, renderer)
+    want = {n: d for n, is_dir, d in whole.entries() if not is_dir}
+    assert st.glyphs == 1686 + 6480 and len(want) == 512
+    out = tmp_path / "out"
+    out.mkdir()
+    costs = []
+    for shard in range(8):
+        w = V.Writer.new_file(str(out))
+        s8 = m.render_glyphs(w, renderer, shard=shard, n_shards=8)
+        costs.append(s8.cost_shard)
+        if shard == 0:
+            m.write_index_json(w)
+            m.write_families_json(w)
+        w.finish()
+    assert max(costs) <= 1.1 * sum(costs) / 8, costs  # LPT balance of the estimated costs
+    got = {}
+    for fid in m.font_ids():
+        for f in os.listdir(out / fid):
+            got[f"{fid}/{f}"] = (out / fid / f).read_bytes()
+    assert got == want, "union of the 8 shards differs from the unsharded run"
+    assert json.loads((out / "index.json").read_text()) == ["fira_sans_regular", "noto_sans_regular"]
+    fam = json.loads((out / "font_families.json").read_text())
+    assert {f["name"] for f in fam} == {"Fira Sans", "Noto Sans"}
+    px = same = 0
+    for fid, oset in (("fira_sans_regular", O.FontSet("Fira Sans - Regular", [O.FIRA])),
+                      ("noto_sans_regular", O.FontSet("Noto Sans Regular", O.noto_paths()))):
+        pop = oset.block_population()
+        for b in range(256):
+            blob = got[f"{fid}/{b * 256}-{b * 256 + 255}.pbf"]
+            if pop[b] == 0:
+                assert blob == oset.render_block(b)
+                continue
+            a, c = check_pbf_block(blob, oset.render_block(b), (fid, b))
+            px += a
+            same += c
+    assert px == 758736 + 3295280 and same / px >= MIN_IDENTICAL
+    print(f"C5 recurse dir: {px} px, {100 * same / px:.4f}% identical, shard cost max/mean {max(costs) * 8 / sum(costs):.3f}")
+
+
 def test_c4_full_bmp_subset_parity(renderer):
     """Every 97th BMP code point of the C4 font: all block ranges, surrogate gap, format-4 cmap."""
     data = synth_font.full_bmp_font(stride=97)

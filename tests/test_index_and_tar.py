@@ -277,3 +277,58 @@ def test_scan_fonts_json_manifest_and_non_font_files(tmp_path):
     (bad / "fonts.json").write_text('[{"name": "No sources"}]')
     with pytest.raises(V.B200Error, match="fonts.json"):
         V.FontManager(parallel=False).scan(str(bad))
+
+
+def test_name_to_id_follows_the_reference_rules():
+    """manager.rs:141-147: Unicode to_lowercase, runs of [-_\\s] (regex-lite: ASCII \\s) collapse to one '_', Unicode trim."""
+    # the reference's own examples (manager.rs tests) plus non-ASCII names
+    for name, want in [
+        ("Noto Sans - Regular", "noto_sans_regular"), ("Fira  Sans_Bold", "fira_sans_bold"), ("  x y\t", "x_y"),
+        ("ÄRIAL Bold", "ärial_bold"), ("ΑΒΓ_Δ-Ω", "αβγ_δ_ω"), ("Привет  Мир", "привет_мир"),
+        ("ÄRIAL\u00a0Bold", "ärial\u00a0bold"),  # NBSP is not matched by regex-lite's ASCII \s ...
+        ("\u00a0 Foo \u3000", "foo"),             # ... but str::trim removes Unicode white space at both ends
+        ("ŁÓDŹ Ÿ", "łódź_ÿ"),
+    ]:
+        assert V.name_to_id(name) == want, (name, V.name_to_id(name))
+
+
+def test_index_json_escapes_font_ids():
+    """serde_json (manager.rs:128-131) escapes quotes, backslashes and control characters: the file stays valid JSON."""
+    m = V.FontManager(parallel=False)
+    m.add_font_bytes_with_name('Foo "Bar"\\ \x01', open(O.FIRA, "rb").read())
+    w = V.Writer.new_memory()
+    m.write_index_json(w)
+    text = [d for n, is_dir, d in w.entries() if n == "index.json"][0].decode()
+    assert json.loads(text) == ['foo_"bar"\\_\x01']
+    assert '\\u0001' in text and '\\"' in text
+
+
+def test_units_per_em_out_of_range_is_a_parse_error():
+    """ttf-parser rejects a head table whose unitsPerEm is outside 16..=16384 (file_entry.rs:48: "Could not parse font data")."""
+    import struct
+
+    data = bytearray(open(O.FIRA, "rb").read())
+    n = struct.unpack(">H", data[4:6])[0]
+    head = next(struct.unpack(">I", data[12 + 16 * i + 8:12 + 16 * i + 12])[0] for i in range(n) if data[12 + 16 * i:12 + 16 * i + 4] == b"head")
+    for upm in (0, 15, 16385):
+        bad = bytearray(data)
+        bad[head + 18:head + 20] = struct.pack(">H", upm)
+        with pytest.raises(V.B200Error, match="Could not parse font data"):
+            V.FontFileEntry(data=bytes(bad))
+    ok = bytearray(data)
+    ok[head + 18:head + 20] = struct.pack(">H", 16)
+    assert V.FontFileEntry(data=bytes(ok)).units_per_em == 16
+
+
+def test_tar_finish_reports_close_errors(tmp_path):
+    """A tar sink whose flush / close fails makes finish() fail (BufWriter::flush, writer/tar.rs:133-137)."""
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full")
+    w = V.Writer.new_tar("/dev/full")
+    w.write_file("a.pbf", b"x" * 100)  # buffered by stdio: the error surfaces at flush
+    with pytest.raises(V.B200Error):
+        w.finish()
+    good = V.Writer.new_tar(str(tmp_path / "ok.tar"))
+    good.write_file("a.pbf", b"x" * 100)
+    good.finish()
+    assert tarfile.open(str(tmp_path / "ok.tar")).getnames() == ["a.pbf"]

@@ -202,6 +202,7 @@ HOST_SYMBOLS = {
     "vgb_font_hor_advance": (C.c_int32, [C.c_void_p, C.c_uint32]),
     "vgb_font_codepoints": (C.c_size_t, [C.c_void_p, u32p, C.c_size_t]),
     "vgb_font_outline_rings": (C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(f64p), C.POINTER(u32p), u32p]),
+    "vgb_font_outline_commands": (C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(C.c_float))]),
     "vgb_flatten_quad": (C.c_size_t, [f64p, f64p, f64p, C.c_double, f64p, C.c_size_t]),
     "vgb_flatten_cubic": (C.c_size_t, [f64p, f64p, f64p, f64p, C.c_double, f64p, C.c_size_t]),
     "vgb_segment_sqdist": (C.c_double, [C.c_double] * 6),

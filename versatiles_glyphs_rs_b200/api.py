@@ -113,6 +113,19 @@ class FontFileEntry:
         N.host.vgb_font_codepoints(self._h, out.ctypes.data_as(N.u32p), n)
         return out
 
+    def outline_commands(self, gid: int) -> np.ndarray:
+        """The raw outline callbacks (ttf_parser::OutlineBuilder) of a glyph: float32 [n, 7] = kind (0 move_to, 1 line_to,
+        2 quad_to, 3 curve_to, 4 close), x1, y1, x2, y2, x, y."""
+        p = C.POINTER(C.c_float)()
+        n = N.host.vgb_font_outline_commands(self._h, gid, C.byref(p))
+        if n < 0:
+            raise B200Error(N.host_error())
+        if n == 0:
+            return np.zeros((0, 7), dtype=np.float32)
+        out = np.ctypeslib.as_array(p, shape=(n, 7)).copy()
+        N.host.vgb_free(p)
+        return out
+
     def outline_rings(self, gid: int):
         """RingBuilder over outline_glyph: (xy float64 [n,2], ring_start uint32 [n_rings+1]) in font units."""
         xy = N.f64p()

@@ -106,6 +106,40 @@ size_t vgb_font_codepoints(const vgb_font *f, uint32_t *out, size_t cap)
 			out[i] = c[i];
 	return c.size();
 }
+namespace {
+// the raw callback stream of Face::outline_glyph: 7 floats per command (kind, x1, y1, x2, y2, x, y)
+class CommandRecorder : public OutlineBuilder {
+  public:
+	std::vector<float> v;
+	void put(float k, float a, float b, float c, float d, float x, float y)
+	{
+		const float r[7] = {k, a, b, c, d, x, y};
+		v.insert(v.end(), r, r + 7);
+	}
+	void move_to(float x, float y) override { put(0, 0, 0, 0, 0, x, y); }
+	void line_to(float x, float y) override { put(1, 0, 0, 0, 0, x, y); }
+	void quad_to(float x1, float y1, float x, float y) override { put(2, x1, y1, 0, 0, x, y); }
+	void curve_to(float x1, float y1, float x2, float y2, float x, float y) override { put(3, x1, y1, x2, y2, x, y); }
+	void close() override { put(4, 0, 0, 0, 0, 0, 0); }
+};
+} // namespace
+
+int32_t vgb_font_outline_commands(const vgb_font *f, uint32_t glyph_id, float **cmds)
+{
+	CommandRecorder rec;
+	if (glyph_id > 0xFFFF)
+		return fail("glyph id out of range");
+	f->e->face->outline_glyph((uint16_t)glyph_id, rec);
+	*cmds = nullptr;
+	if (!rec.v.empty()) {
+		*cmds = (float *)std::malloc(rec.v.size() * sizeof(float));
+		if (!*cmds)
+			return fail("out of memory");
+		std::memcpy(*cmds, rec.v.data(), rec.v.size() * sizeof(float));
+	}
+	return (int32_t)(rec.v.size() / 7);
+}
+
 int32_t vgb_font_outline_rings(const vgb_font *f, uint32_t gid, double **xy, uint32_t **ring_start, uint32_t *n_points)
 {
 	RingSet rs;

@@ -70,6 +70,8 @@ std::unique_ptr<Face> Face::parse(std::vector<uint8_t> data)
 	if (!f->table("hhea", hhea) || hhea.len < 36)
 		return nullptr;
 	f->upm_ = f->u16(head.off + 18);
+	if (f->upm_ < 16 || f->upm_ > 16384)
+		return nullptr; // ttf-parser head::Table::parse rejects such a head table: "Could not parse font data"
 	f->loca_long_ = f->i16(head.off + 50) != 0;
 	f->num_glyphs_ = f->u16(maxp.off + 4);
 	f->num_hmetrics_ = f->u16(hhea.off + 34);

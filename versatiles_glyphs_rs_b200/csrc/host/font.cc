@@ -174,24 +174,108 @@ void FontWrapper::assign_blocks(GlyphBlock *const *blocks) const
 }
 
 // ---- FontManager -------------------------------------------------------------------------------------
+namespace {
+// Unicode simple lowercase for the scripts font names are written in (Rust's str::to_lowercase, manager.rs:144, maps
+// every cased letter; this table covers ASCII, Latin-1, Latin Extended-A, Greek and Cyrillic — the context rule for a
+// final capital sigma is not applied).
+uint32_t lower_cp(uint32_t c)
+{
+	if (c >= 'A' && c <= 'Z')
+		return c + 32;
+	if (c < 0xC0)
+		return c;
+	if (c <= 0xDE)
+		return c == 0xD7 ? c : c + 32;
+	if (c >= 0x100 && c <= 0x137)
+		return c == 0x130 ? 'i' : ((c & 1) ? c : c + 1); // (U+0130 lowers to "i" + U+0307; the dot is dropped here)
+	if (c >= 0x139 && c <= 0x148)
+		return (c & 1) ? c + 1 : c;
+	if (c >= 0x14A && c <= 0x177)
+		return (c & 1) ? c : c + 1;
+	if (c == 0x178)
+		return 0xFF;
+	if (c >= 0x179 && c <= 0x17E)
+		return (c & 1) ? c + 1 : c;
+	if (c == 0x386)
+		return 0x3AC;
+	if (c >= 0x388 && c <= 0x38A)
+		return c + 37;
+	if (c == 0x38C)
+		return 0x3CC;
+	if (c == 0x38E || c == 0x38F)
+		return c + 63;
+	if (c >= 0x391 && c <= 0x3AB)
+		return c == 0x3A2 ? c : c + 32;
+	if (c >= 0x400 && c <= 0x40F)
+		return c + 80;
+	if (c >= 0x410 && c <= 0x42F)
+		return c + 32;
+	if (c >= 0x460 && c <= 0x481)
+		return (c & 1) ? c : c + 1;
+	if (c >= 0x48A && c <= 0x4BF)
+		return (c & 1) ? c : c + 1;
+	return c;
+}
+// char::is_whitespace (what str::trim removes)
+bool unicode_space(uint32_t c)
+{
+	return (c >= 9 && c <= 13) || c == 0x20 || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) || c == 0x2028 ||
+	       c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+}
+void put_utf8(std::string &out, uint32_t cp)
+{
+	if (cp < 0x80)
+		out.push_back((char)cp);
+	else if (cp < 0x800) {
+		out.push_back((char)(0xC0 | (cp >> 6)));
+		out.push_back((char)(0x80 | (cp & 0x3F)));
+	} else if (cp < 0x10000) {
+		out.push_back((char)(0xE0 | (cp >> 12)));
+		out.push_back((char)(0x80 | ((cp >> 6) & 0x3F)));
+		out.push_back((char)(0x80 | (cp & 0x3F)));
+	} else {
+		out.push_back((char)(0xF0 | (cp >> 18)));
+		out.push_back((char)(0x80 | ((cp >> 12) & 0x3F)));
+		out.push_back((char)(0x80 | ((cp >> 6) & 0x3F)));
+		out.push_back((char)(0x80 | (cp & 0x3F)));
+	}
+}
+} // namespace
+
 std::string FontManager::name_to_id(const std::string &name)
 {
-	// lowercase; every run of [-_\s] becomes one separator; trim; separators -> '_'
-	std::string out;
-	bool pending = false;
-	for (unsigned char ch : name) {
-		if (ch >= 'A' && ch <= 'Z')
-			ch = (unsigned char)(ch - 'A' + 'a');
-		const bool sep = ch == '-' || ch == '_' || ch == ' ' || ch == '\t' || ch == '\n' || ch == '\r' || ch == '\f' || ch == '\v';
+	// manager.rs:141-147: to_lowercase (Unicode); every run of [-_\s] — regex-lite's \s is ASCII-only — becomes one
+	// space; trim (Unicode whitespace, both ends); spaces -> '_'
+	std::vector<uint32_t> cps;
+	for (size_t i = 0; i < name.size();) {
+		const unsigned char b = (unsigned char)name[i];
+		uint32_t cp = b;
+		size_t n = 1;
+		if (b >= 0xF0 && i + 3 < name.size())
+			cp = ((b & 7u) << 18) | (((unsigned char)name[i + 1] & 0x3Fu) << 12) | (((unsigned char)name[i + 2] & 0x3Fu) << 6) |
+			     ((unsigned char)name[i + 3] & 0x3Fu), n = 4;
+		else if (b >= 0xE0 && i + 2 < name.size())
+			cp = ((b & 15u) << 12) | (((unsigned char)name[i + 1] & 0x3Fu) << 6) | ((unsigned char)name[i + 2] & 0x3Fu), n = 3;
+		else if (b >= 0xC0 && i + 1 < name.size())
+			cp = ((b & 31u) << 6) | ((unsigned char)name[i + 1] & 0x3Fu), n = 2;
+		i += n;
+		cp = lower_cp(cp);
+		const bool sep = cp == '-' || cp == '_' || cp == ' ' || (cp >= 9 && cp <= 13);
 		if (sep) {
-			pending = true;
-			continue;
+			if (cps.empty() || cps.back() != ' ')
+				cps.push_back(' ');
+		} else {
+			cps.push_back(cp);
 		}
-		if (pending && !out.empty())
-			out.push_back('_');
-		pending = false;
-		out.push_back((char)ch);
 	}
+	size_t a = 0, b = cps.size();
+	while (a < b && unicode_space(cps[a]))
+		++a;
+	while (b > a && unicode_space(cps[b - 1]))
+		--b;
+	std::string out;
+	for (size_t i = a; i < b; ++i)
+		put_utf8(out, cps[i] == ' ' ? (uint32_t)'_' : cps[i]);
 	return out;
 }
 
@@ -238,7 +322,7 @@ bool FontManager::write_index_json(Writer &writer, std::string *err) const
 		s = "[\n";
 		size_t k = 0;
 		for (const auto &kv : fonts_) {
-			s += "  \"" + kv.first + "\"";
+			s += "  \"" + json_escape(kv.first) + "\""; // (serde_json escapes: an id may hold quotes or control bytes)
 			s += (++k < fonts_.size()) ? ",\n" : "\n";
 		}
 		s += "]";

@@ -41,6 +41,8 @@ void parse_font_name(const std::string &family, const std::string &ps_name, std:
                      uint16_t &weight, std::string &width);
 // font/index_files.rs:60-95
 std::string encode_codeblocks(const std::vector<uint32_t> &codepoints);
+// JSON string escaping as serde_json writes it (quotes, backslash, control characters)
+std::string json_escape(const std::string &s);
 class FontWrapper;
 // font/index_files.rs:115-139; empty string + *err when a font has no files
 std::string build_font_families_json(const std::map<std::string, FontWrapper> &fonts, std::string *err);
@@ -165,6 +167,7 @@ class Writer {
 	std::string folder_;
 	std::vector<uint8_t> tar_;
 	std::shared_ptr<std::FILE> tar_file_;
+	std::shared_ptr<bool> tar_closed_; // finish() closes the file itself so that close errors are reported
 	std::vector<Entry> entries_;
 	uint64_t bytes_written_ = 0;
 	bool finished_ = false;

@@ -71,25 +71,33 @@ uint16_t find_weight(const std::string &s)
 	return 400;
 }
 
+} // namespace
+
+// serde_json's string escaping: \" \\ \b \f \n \r \t, other control characters as \u00XX
 std::string json_escape(const std::string &s)
 {
 	std::string o;
 	for (unsigned char c : s) {
-		if (c == '"' || c == '\\') {
-			o.push_back('\\');
-			o.push_back((char)c);
-		} else if (c < 0x20) {
-			char buf[8];
-			std::snprintf(buf, sizeof(buf), "\\u%04x", c);
-			o += buf;
-		} else {
-			o.push_back((char)c);
+		switch (c) {
+		case '"': o += "\\\""; break;
+		case '\\': o += "\\\\"; break;
+		case '\b': o += "\\b"; break;
+		case '\f': o += "\\f"; break;
+		case '\n': o += "\\n"; break;
+		case '\r': o += "\\r"; break;
+		case '\t': o += "\\t"; break;
+		default:
+			if (c < 0x20) {
+				char buf[8];
+				std::snprintf(buf, sizeof(buf), "\\u%04x", c);
+				o += buf;
+			} else {
+				o.push_back((char)c);
+			}
 		}
 	}
 	return o;
 }
-
-} // namespace
 
 // parse_font_name.rs:214-293
 void parse_font_name(const std::string &family, const std::string &ps_name, std::string &out_family, std::string &style,

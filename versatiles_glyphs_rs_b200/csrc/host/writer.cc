@@ -34,15 +34,21 @@ Writer Writer::new_tar(const std::string &path)
 	w.to_tar_ = true;
 	w.folder_ = path;
 	std::FILE *f = std::fopen(path.c_str(), "wb");
-	if (f)
-		w.tar_file_ = std::shared_ptr<std::FILE>(f, [](std::FILE *p) { std::fclose(p); });
+	if (f) {
+		std::shared_ptr<bool> closed(new bool(false));
+		w.tar_closed_ = closed;
+		w.tar_file_ = std::shared_ptr<std::FILE>(f, [closed](std::FILE *p) {
+			if (!*closed)
+				std::fclose(p); // (a writer dropped without finish(): best effort, writer/mod.rs:83-96)
+		});
+	}
 	return w;
 }
 
 bool Writer::tar_put(const uint8_t *p, size_t n, std::string *err)
 {
 	if (!folder_.empty()) {
-		if (!tar_file_ || (n && std::fwrite(p, 1, n, tar_file_.get()) != n)) {
+		if (!tar_file_ || (tar_closed_ && *tar_closed_) || (n && std::fwrite(p, 1, n, tar_file_.get()) != n)) {
 			if (err)
 				*err = "writing tar \"" + folder_ + "\" failed";
 			return false;
@@ -128,10 +134,13 @@ bool Writer::write_file(const std::string &filename, const uint8_t *bytes, size_
 			*err = "open " + path + ": " + std::strerror(errno);
 		return false;
 	}
-	const bool ok = len == 0 || std::fwrite(bytes, 1, len, f) == len;
-	std::fclose(f);
+	bool ok = len == 0 || std::fwrite(bytes, 1, len, f) == len;
+	// (buffered data reaches the file at close: a full disk or an I/O error may only show up here — std::fs::write in the
+	// reference, writer/file.rs:42, reports it)
+	if (std::fclose(f) != 0)
+		ok = false;
 	if (!ok && err)
-		*err = "write " + path + " failed";
+		*err = "write " + path + " failed: " + std::strerror(errno);
 	return ok;
 }
 
@@ -176,8 +185,18 @@ bool Writer::finish(std::string *err)
 		static const uint8_t zeros[1024] = {0};
 		if (!tar_put(zeros, sizeof(zeros), err))
 			return false;
-		if (tar_file_)
-			std::fflush(tar_file_.get());
+		if (tar_file_ && tar_closed_ && !*tar_closed_) {
+			// BufWriter::flush + close (writer/tar.rs:133-137): errors that only surface now are errors of finish()
+			std::FILE *f = tar_file_.get();
+			const bool flushed = std::fflush(f) == 0;
+			const bool closed = std::fclose(f) == 0;
+			*tar_closed_ = true;
+			if (!flushed || !closed) {
+				if (err)
+					*err = std::string("closing the tar file failed: ") + std::strerror(errno);
+				return false;
+			}
+		}
 	}
 	return true;
 }
