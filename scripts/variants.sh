@@ -5,9 +5,7 @@ set -u
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 declare -A V=(
   [base]=""
-  [p8]="-DB200SDF_PERSISTENT_MIN_CTAS=8"
-  [p7]="-DB200SDF_PERSISTENT_MIN_CTAS=7"
-  [p5]="-DB200SDF_PERSISTENT_MIN_CTAS=5"
+  [nosplit]="-DB200SDF_SPLIT_BARRIER=0"
 )
 if [ "${1:-}" = "build" ]; then
   for n in "${!V[@]}"; do

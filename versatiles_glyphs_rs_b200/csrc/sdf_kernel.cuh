@@ -46,6 +46,12 @@
 #define B200SDF_MIN_CTAS 8 // __launch_bounds__ minimum CTAs per SM: 64 registers (measured 6 / 7 / 8 with the shared-staging loop: 0.475 / 0.459 / 0.442 ms)
 #endif
 #define B200SDF_BOUNDS __launch_bounds__(128, B200SDF_MIN_CTAS)
+#ifndef B200SDF_SPLIT_BARRIER
+// shared staging: consume the warp's own list between arrive and wait of the round barrier.  Measured and left off:
+// C2 / C3 / C4 0.475 / 2.52 / 10.38 ms with it against 0.447 / 2.36 / 9.67 ms without (the duplicated inner loops cost
+// more than the overlap gains)
+#define B200SDF_SPLIT_BARRIER 0
+#endif
 #ifndef B200SDF_PERSISTENT_MIN_CTAS
 #define B200SDF_PERSISTENT_MIN_CTAS 6 // resident CTAs per SM of the persistent kernel (80 registers)
 #endif
@@ -120,6 +126,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 	                 smem_u32(dst_smem)),
 	             "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
 	             : "memory");
+}
+// named barriers (barrier 0 is __syncthreads): arrive without waiting / arrive and wait; `count` threads per phase
+__device__ __forceinline__ void named_bar_arrive(int id, int count)
+{
+	asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count)
+{
+	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 // three-input minimum (sm_100+: one FMNMX3 on the ALU pipe instead of two FMNMX)
 __device__ __forceinline__ float fmin3(float a, float b, float c)
@@ -644,6 +659,27 @@ __device__ B200SDF_TILE_INLINE void render_tile(SharedStorage &sm, const b200sdf
 				sm.st_nv[warp] = nv;
 				sm.st_nl[warp] = nl;
 			}
+#if B200SDF_SPLIT_BARRIER
+			// Split barrier (experiment, see B200SDF_SPLIT_BARRIER): announce "my list is staged", consume MY OWN list
+			// (visible to my warp already) while the slower warps finish staging theirs, and only then wait for them.
+			__syncwarp();
+			named_bar_arrive(1, 2 * kThreads);
+			if (warp_active) {
+				const int first = (cs + warp) % cstride;
+				vertex_loop(sm.warp[warp], nv, first, cstride);
+				long_loop(sm.warp[warp], nl, first, cstride);
+			}
+			named_bar_sync(1, 2 * kThreads);
+			if (warp_active) {
+#pragma unroll 1
+				for (int k = 1; k < kWarps; ++k) {
+					const int q = (warp + k) & (kWarps - 1);
+					const int first = (cs + q) % cstride; // rotate: list lengths are not multiples of the stride
+					vertex_loop(sm.warp[q], sm.st_nv[q], first, cstride);
+					long_loop(sm.warp[q], sm.st_nl[q], first, cstride);
+				}
+			}
+#else
 			__syncthreads();
 			if (warp_active) {
 #pragma unroll 1
@@ -653,6 +689,7 @@ __device__ B200SDF_TILE_INLINE void render_tile(SharedStorage &sm, const b200sdf
 					long_loop(sm.warp[q], sm.st_nl[q], first, cstride);
 				}
 			}
+#endif
 			__syncthreads(); // the lists are overwritten by the next round
 		}
 	} else
