@@ -28,10 +28,14 @@ import gc
 gc.collect()
 gc.disable()
 ms = []
-for _ in range(steps):
+for k in range(steps):
+    if os.environ.get("VGB_ALLOC_TRACE"):
+        print(f"--- step {k}", file=sys.stderr, flush=True)
     t = time.perf_counter()
     st = m.render_glyphs(V.Writer.new_memory(), r, threads=threads)
     ms.append(1e3 * (time.perf_counter() - t))
+    if os.environ.get("VGB_ALLOC_TRACE"):
+        print(f"--- step {k} took {ms[-1]:.2f} ms", file=sys.stderr, flush=True)
 knobs = {k: v for k, v in os.environ.items() if k.startswith(("VGB_", "B200SDF_"))}
 print(f"{wl} x{copies} threads={threads or 'all'} {knobs}: min/median/max {min(ms):.3f}/{statistics.median(ms):.3f}/{max(ms):.3f} ms  "
       f"workers {st.workers} submits {st.submits} req/w {st.outline_ns / 1e6 / st.workers:.3f} enc/w {st.encode_ns / 1e6 / st.workers:.3f} "

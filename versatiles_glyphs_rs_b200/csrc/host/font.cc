@@ -133,9 +133,11 @@ const std::vector<uint64_t> &FontWrapper::block_costs() const
 	if (!block_costs_.empty())
 		return block_costs_;
 	std::vector<uint64_t> costs(table.size(), 0);
+	std::vector<uint64_t> units(table.size(), 0);
 	std::vector<Face::GlyfPart> parts;
 	for (size_t b = 0; b < table.size(); ++b) {
 		uint64_t c = 64; // an empty block still costs a file
+		uint64_t u = 0;
 		for (uint32_t k = 0; k < GLYPH_BLOCK_SIZE; ++k) {
 			const FontFileEntry *f = table[b].font_of((uint8_t)k);
 			if (!f)
@@ -148,6 +150,7 @@ const std::vector<uint64_t> &FontWrapper::block_costs() const
 			const Face::GlyfPlan plan = f->face->glyf_parts(*gid, parts);
 			if (plan == Face::GlyfPlan::Host) {
 				c += 600000; // no header to go by: a typical glyph
+				u += 600000 / 16;
 				continue;
 			}
 			const double scale = (double)GLYPH_SIZE / (double)std::max<uint16_t>(1, f->face->units_per_em());
@@ -155,12 +158,21 @@ const std::vector<uint64_t> &FontWrapper::block_costs() const
 				const double w = ((double)p.xmax - (double)p.xmin) * scale + 8.0, h = ((double)p.ymax - (double)p.ymin) * scale + 8.0;
 				const double area = std::min(std::max(w, 8.0), 4096.0) * std::min(std::max(h, 8.0), 4096.0);
 				c += (uint64_t)(area * (double)p.points * 8.0); // ~8 flattened segments per point
+				u += (uint64_t)(area / 16.0 * ((double)p.points * 8.0 + 8.0));
 			}
 		}
 		costs[b] = c;
+		units[b] = u;
 	}
 	block_costs_ = std::move(costs);
+	block_units_ = std::move(units);
 	return block_costs_;
+}
+
+const std::vector<uint64_t> &FontWrapper::block_units() const
+{
+	block_costs();
+	return block_units_;
 }
 
 void FontWrapper::assign_blocks(GlyphBlock *const *blocks) const

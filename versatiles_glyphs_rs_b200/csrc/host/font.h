@@ -117,6 +117,7 @@ class FontWrapper {
 		files_.push_back(std::move(file));
 		blocks_.clear(); // the block table is rebuilt on next use
 		block_costs_.clear();
+		block_units_.clear();
 	}
 	bool add_paths(const std::vector<std::string> &sources, std::string *err);
 	const std::vector<std::unique_ptr<FontFileEntry>> &files() const { return files_; }
@@ -131,11 +132,14 @@ class FontWrapper {
 	// headers only: what FontManager::render_glyphs balances shards with.  Like blocks(), a pure function of the
 	// files, built when first needed.
 	const std::vector<uint64_t> &block_costs() const;
+	// The GPU share of those estimates in the device's own unit (4 x 4 pixel tile x segment): what a batch tells the
+	// device about the work it is part of (b200sdf_submit_glyphs est_cost)
+	const std::vector<uint64_t> &block_units() const;
 
   private:
 	std::vector<std::unique_ptr<FontFileEntry>> files_;
 	mutable std::vector<GlyphBlock> blocks_;
-	mutable std::vector<uint64_t> block_costs_;
+	mutable std::vector<uint64_t> block_costs_, block_units_;
 	mutable std::mutex blocks_mu_;
 };
 

@@ -229,6 +229,10 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			cost_total += l;
 		cost_mine = shard < n_shards ? load[shard] : 0;
 	}
+	// What the device will be rendering while any one batch of this call is in flight is (most of) the call: heavy glyphs
+	// are cut into rectangles by the call's fair share per resident CTA, not by a single batch's (every rectangle
+	// repeats the staging of all the glyph's segments — C3 in 13 batches: 6.5 ms cut per batch, 2.9 ms cut per call).
+	uint64_t call_units = 0;
 	uint32_t index = 0;
 	for (const auto &kv : fonts_) {
 		if (!writer.write_directory(kv.first + "/", err))
@@ -246,6 +250,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				continue;
 			BlockState *bs = &bsv[i];
 			total_glyphs += bs->blk->len();
+			if (glyf_mode && !bs->blk->is_empty())
+				call_units += kv.second.block_units()[i];
 			uint32_t part = 0, slot0 = 0, count = 0;
 			if (bs->blk->len() > kPartGlyphs) {
 				for (uint32_t k = 0; k < GLYPH_BLOCK_SIZE; ++k) {
@@ -527,6 +533,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				}
 				std::unique_ptr<Flight> cur(new Flight());
 				cur->batch = renderer.acquire_batch(true);
+				cur->batch->set_cost_context(call_units);
 				mark('o');
 				uint64_t t0 = now_ns();
 				// Batch size.  One thread enqueues every batch (about 10 us each), so batches are as large as the
@@ -540,8 +547,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					want = wid < kEarlyWorkers ? kPartGlyphs : std::min(target, kPartGlyphs * (size_t)(1 + wid % 4));
 				// Device-side decoding: filling a batch costs microseconds, submitting one costs the CUDA thread ~15 us and
 				// a kernel pair under a few hundred glyphs runs as long as its heaviest tile: equal, large batches.
-				if (glyf_mode)
-					want = target;
+				if (glyf_mode) // (each worker opens with a quarter-size batch: the GPU has work after tens of microseconds)
+					want = n_batches == 0 ? std::max<size_t>(192, target / 4) : target;
 				++n_batches;
 				while (cur->batch->glyphs().size() < want) {
 					const size_t ti = next.fetch_add(1);

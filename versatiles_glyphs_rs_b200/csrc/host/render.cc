@@ -313,7 +313,7 @@ void GlyphBatch::clear()
 	n_tiles_ = 0;
 	prepared_ = false;
 	n_parts_ = curve_slots_ = tile_cap_ = n_handed_back_ = 0;
-	pixels_ = est_cost_ = 0;
+	pixels_ = est_cost_ = cost_context_ = 0;
 	job_glyph_.clear();
 	n_heavy_ = 0;
 	finalized_ = false;

@@ -214,7 +214,10 @@ class GlyphBatch {
 	uint32_t part_count() const { return n_parts_; }
 	uint32_t curve_slots() const { return curve_slots_; }
 	uint32_t tile_cap() const { return tile_cap_; }
-	uint64_t est_cost() const { return est_cost_; } // estimated tile x segment units of the batch (b200sdf_submit_glyphs)
+	// estimated tile x segment units of the work the device renders together with this batch (b200sdf_submit_glyphs
+	// est_cost): the batch itself, or — when a pipeline keeps many batches of one job in flight — that job
+	uint64_t est_cost() const { return est_cost_ > cost_context_ ? est_cost_ : cost_context_; }
+	void set_cost_context(uint64_t units) { cost_context_ = units; }
 	bool ensure_frames(); // allocate the frame array (after the last add)
 	// After the batch came back: take frames and bitmap presence from the device's answers; glyphs it handed back
 	// (B200SDF_GLYPH_NEEDS_HOST) are recorded on the host and rendered through `renderer` now.  false + *err on failure.
@@ -261,7 +264,7 @@ class GlyphBatch {
 	std::vector<Face::GlyfPart> parts_tmp_;
 	std::vector<uint8_t> extra_;
 	uint32_t n_parts_ = 0, curve_slots_ = 0, tile_cap_ = 0, n_handed_back_ = 0;
-	uint64_t pixels_ = 0, est_cost_ = 0;
+	uint64_t pixels_ = 0, est_cost_ = 0, cost_context_ = 0;
 	// Glyf mode: requests of glyphs with many outline points are kept at the front of the request array — the decode
 	// kernel takes requests in order, one warp each, and a glyph of several hundred points is that kernel's critical path
 	std::vector<uint32_t> job_glyph_; // request index -> glyph index
