@@ -110,54 +110,41 @@ def config_of(label, copies, glyphs):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons of this rank's GPU, read in-process through NVML at moments the caller chooses (while
+    the timed launches are queued and running).  A polling `nvidia-smi -lms` child per rank — what round 1 used — takes
+    driver locks at random moments: with several ranks on a box it showed up as 20-40 ms outlier steps of the e2e leg."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         self.rows = []
-        self.proc = None
+        self.h = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001 — no NVML: the line reports no clocks rather than failing
+            self.h = None
 
-    def window(self, t0, t1):
-        return [r for t, r in self.rows if t0 <= t <= t1]
+    def sample(self):
+        if self.h is None:
+            return
+        try:
+            sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+            why = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.rows.append((sm, int(why)))
+        except Exception:  # noqa: BLE001
+            pass
 
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except subprocess.TimeoutExpired:
-                self.proc.kill()
-
-    @staticmethod
-    def summary(rows):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+    def summary(self):
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = sorted(n for n, bit in self.REASONS.items() if any(w & bit for _, w in self.rows))
+        return {"sm_mhz": statistics.median(r[0] for r in self.rows), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(self.rows), "how": "NVML, in-process, sampled while the timed launches were running"}
 
 
 # ---- the reference arm / CPU baseline (the only code here that touches oracle/) -------------------------
@@ -335,7 +322,7 @@ class Job:
 
         return self.np.frombuffer(self.d_frames.cpu().numpy().tobytes(), dtype=GLYPH_FRAME_DT)[: len(self.reqs)]
 
-    def time_device(self, stream, flush, steps, warmup):
+    def time_device(self, stream, flush, steps, warmup, sampler=None):
         """-> per-step (total ms, decode ms, sdf ms) lists, CUDA events on `stream`."""
         torch = self.torch
         with torch.cuda.stream(stream):
@@ -353,6 +340,8 @@ class Job:
                 self.launch(stream, em.cuda_event)
                 e1.record(stream)
                 evs.append((e0, em, e1))
+                if sampler is not None and len(evs) % 4 == 2:
+                    sampler.sample()  # (the launches are asynchronous: the GPU is busy with the queued steps)
         torch.cuda.synchronize()
         return [a.elapsed_time(c) for a, _, c in evs], [a.elapsed_time(b) for a, b, _ in evs], [b.elapsed_time(c) for _, b, c in evs]
 
@@ -441,7 +430,7 @@ def main():
     barrier()
     l0 = ctx.launch_count
     t_wall0 = time.perf_counter()
-    total_ms, decode_ms, sdf_ms = job.time_device(stream, flush, args.steps, 0)
+    total_ms, decode_ms, sdf_ms = job.time_device(stream, flush, args.steps, 0, sampler)
     barrier()
     t_wall1 = time.perf_counter()
     launches = ctx.launch_count - l0
@@ -722,8 +711,7 @@ def main():
             except Exception as e:  # noqa: BLE001 — a baseline that cannot run must not hide the measured line
                 result["cpu_baseline"] = {"value": None, "unit": "glyphs/s", "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
         barrier()
-    result["clocks"] = ClockSampler.summary(sampler.window(t_wall0, max(t_wall1, t_wall0 + 0.5, t_e2e_end)))
-    sampler.stop()
+    result["clocks"] = sampler.summary()
     if rank == 0:
         emit(result)
     if dist is not None:

@@ -1107,6 +1107,49 @@ int grow_plain(b200sdf_ctx *ctx, DevBuf &b, size_t need)
 
 } // namespace
 
+int b200sdf_reserve(b200sdf_ctx *ctx)
+{
+	using namespace b200sdf;
+	if (!ctx)
+		return B200SDF_E_ARG;
+	CU_TRY(ctx, cudaSetDevice(ctx->device));
+	size_t g[9], h[5];
+	{
+		std::lock_guard<std::mutex> lk(ctx->mu);
+		std::memcpy(g, ctx->ghwm, sizeof(g));
+		std::memcpy(h, ctx->hwm, sizeof(h));
+	}
+	for (size_t si = 0; si < ctx->slots.size(); ++si) {
+		Slot &s = ctx->slots[si];
+		{
+			std::lock_guard<std::mutex> lk(ctx->mu);
+			if (s.busy)
+				continue;
+			s.busy = true;
+		}
+		int rc = 0;
+		// glyph-level submissions: [0] segments [1] host curves [2] requests [3] parts [4] frames [5] bitmaps [6] curve
+		// scratch [7] tile lists [8] outline jobs; outline-level ones: segments, curves, jobs, tiles, bitmaps
+		const size_t want[10] = {std::max(g[0], h[0]), std::max(g[1], h[1]), g[2], g[3], g[4], std::max(g[5], h[4]), g[6], std::max(g[7], h[3]),
+		                         std::max(g[8], h[2]), 0};
+		DevBuf *bufs[9] = {&s.segs, &s.curves, &s.reqs, &s.parts, &s.frames, &s.out, &s.gcurves, &s.tiles, &s.ojobs};
+		for (int k = 0; k < 9 && rc == 0; ++k)
+			rc = grow_device(ctx, *bufs[k], want[k], s.stream);
+		if (rc == 0 && !s.counters && g[6]) {
+			cudaError_t e;
+			if ((e = cudaMalloc((void **)&s.counters, sizeof(BatchCounters))) != cudaSuccess ||
+			    (e = cudaMemsetAsync(s.counters, 0, sizeof(BatchCounters), s.stream)) != cudaSuccess ||
+			    (e = cudaHostAlloc((void **)&s.h_status, 64, cudaHostAllocPortable | cudaHostAllocMapped)) != cudaSuccess ||
+			    (e = cudaHostGetDevicePointer((void **)&s.d_status, s.h_status, 0)) != cudaSuccess)
+				rc = fail_cuda(ctx, e, "cudaMalloc(counters)");
+		}
+		release_slot(ctx, s, 0);
+		if (rc)
+			return rc;
+	}
+	return 0;
+}
+
 int b200sdf_font_upload(b200sdf_ctx *ctx, const uint8_t *glyf, uint64_t len, uint32_t *handle)
 {
 	if (!ctx || !handle || (len && !glyf))

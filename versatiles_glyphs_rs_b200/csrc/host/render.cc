@@ -890,6 +890,8 @@ void Renderer::top_up_pool() const
 		want = std::min(kPoolTopUp, want);
 		mine.swap(pool_); // size the pooled batches outside the lock
 	}
+	if (ctx_)
+		b200sdf_reserve(ctx_); // every slot's device buffers at the marks too: no device allocation in the middle of a later call
 	for (auto &b : mine)
 		if (b->mode() == flatten_)
 			b->reserve_capacity(caps);
