@@ -106,6 +106,27 @@ pub struct b200sdf_glyph_frame {
     pub status: u32,
 }
 
+/// One batch of a multi-batch submission (`b200sdf_submit_glyph_batches`); all buffers from `b200sdf_alloc_pinned`.
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct b200sdf_glyph_batch {
+    pub reqs: *const b200sdf_glyph_req,
+    pub n_reqs: u32,
+    pub parts: *const b200sdf_glyph_part,
+    pub n_parts: u32,
+    pub curves: *const b200sdf_curve,
+    pub n_curves: u32,
+    pub segs: *const b200sdf_segment,
+    pub n_seg: u32,
+    pub curve_slots: u32,
+    pub tile_cap: u32,
+    pub frames: *mut b200sdf_glyph_frame,
+    pub out: *mut u8,
+    pub out_bytes: u64,
+}
+
+pub const B200SDF_MAX_BATCHES: u32 = 16;
+
 extern "C" {
     pub fn b200sdf_abi_version() -> c_int;
     pub fn b200sdf_device_count() -> c_int;
@@ -135,4 +156,7 @@ extern "C" {
                                  n_parts: u32, curves: *const b200sdf_curve, n_curves: u32, segs: *const b200sdf_segment, n_seg: u32,
                                  curve_slots: u32, tile_cap: u32, est_cost: u64, frames: *mut b200sdf_glyph_frame, out: *mut u8,
                                  out_bytes: u64, ticket: *mut u64) -> c_int;
+    pub fn b200sdf_submit_glyph_batches(ctx: *mut b200sdf_ctx, batches: *const b200sdf_glyph_batch, n_batches: u32, est_cost: u64,
+                                        ticket: *mut u64) -> c_int;
+    pub fn b200sdf_reserve(ctx: *mut b200sdf_ctx) -> c_int;
 }

@@ -271,6 +271,28 @@ int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
                           uint32_t n_parts, const b200sdf_curve *curves, uint32_t n_curves, const b200sdf_segment *segs,
                           uint32_t n_seg, uint32_t curve_slots, uint32_t tile_cap, uint64_t est_cost, b200sdf_glyph_frame *frames,
                           uint8_t *out, uint64_t out_bytes, uint64_t *ticket);
+/* Several batches in ONE submission (one decode launch, one SDF launch, one ticket): what a pipeline does with the
+ * batches that queued up while the previous submission was being made — a kernel pair over a few hundred glyphs lasts as
+ * long as its slowest glyph and its heaviest tile, so many small submissions cost the GPU more than one large one.
+ * Every batch keeps its own arrays, frames and bitmap area.  With more than one batch all arrays must come from
+ * b200sdf_alloc_pinned (a single batch may live in pageable memory and is then staged).  At most B200SDF_MAX_BATCHES. */
+#define B200SDF_MAX_BATCHES 16
+typedef struct {
+	const b200sdf_glyph_req *reqs;
+	uint32_t n_reqs;
+	const b200sdf_glyph_part *parts;
+	uint32_t n_parts;
+	const b200sdf_curve *curves;
+	uint32_t n_curves;
+	const b200sdf_segment *segs;
+	uint32_t n_seg;
+	uint32_t curve_slots, tile_cap;
+	b200sdf_glyph_frame *frames;
+	uint8_t *out;
+	uint64_t out_bytes;
+} b200sdf_glyph_batch;
+int b200sdf_submit_glyph_batches(b200sdf_ctx *ctx, const b200sdf_glyph_batch *batches, uint32_t n_batches, uint64_t est_cost,
+                                 uint64_t *ticket);
 /* The same over device pointers on `stream` (asynchronous, two kernel launches, scratch owned by the context);
  * mid_event (a cudaEvent_t or NULL) is recorded between the decode kernel and the SDF kernel. */
 int b200sdf_render_glyphs_device(b200sdf_ctx *ctx, const b200sdf_glyph_req *d_reqs, uint32_t n_reqs,

@@ -1,18 +1,11 @@
 #!/bin/bash
 # e2e knob sweep on the GPU box (one process per setting)
 cd "$(dirname "$0")/.."
-run() { env "$@" python scripts/e2e_sweep.py ${WL:-noto} 40 ${THREADS:-8} 2>/dev/null | tail -1; }
-run A=1
-run VGB_BATCHES_PER_WORKER=1
-run VGB_BATCHES_PER_WORKER=3
-run B200SDF_PERSISTENT_GRID=296
-run B200SDF_PERSISTENT_GRID=444
-run B200SDF_PERSISTENT_GRID=592
-run B200SDF_PERSISTENT_GRID=444 VGB_BATCHES_PER_WORKER=1
-run B200SDF_PERSISTENT_GRID=592 VGB_BATCHES_PER_WORKER=1
-THREADS=4 run A=1
-THREADS=4 run VGB_BATCHES_PER_WORKER=1
-THREADS=4 run VGB_BATCHES_PER_WORKER=3
-THREADS=4 run B200SDF_PERSISTENT_GRID=444
-THREADS=6 run A=1
-THREADS=6 run VGB_BATCHES_PER_WORKER=1
+run() { echo "$@ T=${THREADS:-8}: $(env "$@" python scripts/e2e_sweep.py ${WL:-noto} 40 ${THREADS:-8} 2>/dev/null | tail -1)"; }
+for t in 4 8 16; do
+THREADS=$t run VGB_GROUP_MAX=1
+THREADS=$t run VGB_GROUP_MAX=4
+THREADS=$t run VGB_GROUP_MAX=16
+THREADS=$t run VGB_GROUP_MAX=16 VGB_BATCHES_PER_WORKER=3
+THREADS=$t run VGB_GROUP_MAX=16 VGB_BATCHES_PER_WORKER=4
+done

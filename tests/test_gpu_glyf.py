@@ -285,3 +285,37 @@ def test_glyph_level_submission_from_pageable_memory(renderer):
         assert np.array_equal(out[int(reqs["out_off"][k]) : int(reqs["out_off"][k]) + n], batch.bitmap_of(i).reshape(-1))
         seen += 1
     assert seen == int((frames["status"] == N.GLYPH_OK).sum()) > 250
+
+
+def test_several_batches_in_one_submission(renderer):
+    """b200sdf_submit_glyph_batches: 5 batches of different fonts and sizes (one of them empty) share one decode launch
+    and one SDF launch; every batch gets exactly the frames and bitmaps it gets when it is submitted alone."""
+    renderer.set_flatten("glyf")
+    ctx = V.SdfContext.of_renderer(renderer)
+    fonts = [V.FontFileEntry(path=p) for p in (O.FIRA, O.noto_paths()[0])]
+    group, alone = [], []
+    est = 0
+    for k, n in enumerate((300, 7, 0, 512, 129)):
+        font = fonts[k % 2]
+        cps = [int(c) for c in font.codepoints() if c <= 0xFFFF][40 * k : 40 * k + n]
+        batch = renderer.new_batch()
+        for cp in cps:
+            batch.add_glyph(font, cp)
+        reqs, parts = batch.requests(), batch.parts()
+        out_bytes = int((reqs["out_off"] + reqs["out_cap"]).max()) if len(reqs) else 0
+        group.append((reqs, parts, batch.curve_slots, batch.tile_cap, out_bytes))
+        est = max(est, batch.est_cost)
+        alone.append(ctx.render_glyphs(reqs, parts, batch.curve_slots, batch.tile_cap, out_bytes, est_cost=batch.est_cost))
+    together = ctx.render_glyph_batches(group, est_cost=est)
+    checked = 0
+    for (reqs, *_), (fa, oa), (fb, ob) in zip(group, alone, together):
+        assert np.array_equal(fa, fb)
+        for k in range(len(reqs)):
+            if fa[k]["status"] != N.GLYPH_OK:
+                continue
+            o, n = int(reqs["out_off"][k]), int(fa[k]["width"]) * int(fa[k]["height"])
+            assert np.array_equal(oa[o : o + n], ob[o : o + n])
+            checked += 1
+    assert checked > 800
+    with pytest.raises(V.B200Error):  # 17 batches: over B200SDF_MAX_BATCHES
+        ctx.render_glyph_batches([group[1]] * 17)

@@ -144,6 +144,14 @@ class GlyphReq(C.Structure):
     ]
 
 
+class GlyphBatchDesc(C.Structure):
+    """b200sdf_glyph_batch: one batch of a multi-batch submission"""
+    _fields_ = [("reqs", C.c_void_p), ("n_reqs", C.c_uint32), ("parts", C.c_void_p), ("n_parts", C.c_uint32),
+                ("curves", C.c_void_p), ("n_curves", C.c_uint32), ("segs", C.c_void_p), ("n_seg", C.c_uint32),
+                ("curve_slots", C.c_uint32), ("tile_cap", C.c_uint32), ("frames", C.c_void_p), ("out", C.c_void_p),
+                ("out_bytes", C.c_uint64)]
+
+
 class GlyphFrame(C.Structure):
     _fields_ = [("x0", C.c_int32), ("y0", C.c_int32), ("width", C.c_uint32), ("height", C.c_uint32),
                 ("seg_cnt", C.c_uint32), ("status", C.c_uint32)]
@@ -182,6 +190,7 @@ SDF_SYMBOLS = {
     "b200sdf_glyph_tile_bound": (C.c_uint32, [C.c_uint32, C.c_uint32]),
     "b200sdf_submit_glyphs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
+    "b200sdf_submit_glyph_batches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, u64p]),
     "b200sdf_render_glyphs_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                                C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                                C.c_void_p, C.c_void_p]),

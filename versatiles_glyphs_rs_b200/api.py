@@ -639,6 +639,47 @@ class SdfContext:
             raise B200Error(f"b200sdf_submit_glyphs: {rc}: {self.last_error()}")
         return frames[: len(reqs)], out[:out_bytes]
 
+    def render_glyph_batches(self, batches, est_cost: int = 0):
+        """b200sdf_submit_glyph_batches + b200sdf_wait: `batches` is a list of (reqs, parts, curve_slots, tile_cap, out_bytes);
+        every buffer is copied into b200sdf_alloc_pinned memory first (several batches in one submission must be
+        pinned).  -> [(frames, bitmaps)] per batch."""
+        held, views = [], []
+
+        def pinned(a: np.ndarray):
+            nbytes = max(int(a.nbytes), 64)
+            p = N.sdf.b200sdf_alloc_pinned(nbytes)
+            if not p:
+                raise B200Error("b200sdf_alloc_pinned failed")
+            held.append(p)
+            v = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p))
+            v[: a.nbytes] = a.view(np.uint8).reshape(-1)
+            return p, v
+
+        try:
+            desc = (N.GlyphBatchDesc * len(batches))()
+            for k, (reqs, parts, curve_slots, tile_cap, out_bytes) in enumerate(batches):
+                reqs = np.ascontiguousarray(reqs, dtype=GLYPH_REQ_DT)
+                parts = np.ascontiguousarray(parts, dtype=GLYPH_PART_DT)
+                d = desc[k]
+                d.reqs, _ = pinned(reqs)
+                d.parts, _ = pinned(parts)
+                d.n_reqs, d.n_parts = len(reqs), len(parts)
+                d.curve_slots, d.tile_cap = int(curve_slots), int(tile_cap)
+                d.frames, fv = pinned(np.zeros(max(1, len(reqs)), dtype=GLYPH_FRAME_DT))
+                d.out, ov = pinned(np.zeros(max(1, out_bytes), dtype=np.uint8))
+                d.out_bytes = int(out_bytes)
+                views.append((fv, ov, len(reqs), int(out_bytes)))
+            t = C.c_uint64()
+            rc = N.sdf.b200sdf_submit_glyph_batches(self._h, desc, len(batches), est_cost, C.byref(t))
+            if rc == 0:
+                rc = N.sdf.b200sdf_wait(self._h, t.value)
+            if rc != 0:
+                raise B200Error(f"b200sdf_submit_glyph_batches: {rc}: {self.last_error()}")
+            return [(fv[: n * GLYPH_FRAME_DT.itemsize].view(GLYPH_FRAME_DT).copy(), ov[:ob].copy()) for fv, ov, n, ob in views]
+        finally:
+            for p in held:
+                N.sdf.b200sdf_free_pinned(p)
+
     def render_glyphs_device(self, d_reqs: int, n_reqs: int, d_parts: int, n_parts: int, d_curves: int, n_curves: int, d_segs: int,
                              n_seg: int, curve_slots: int, tile_cap: int, est_cost: int, d_frames: int, d_out: int, out_bytes: int,
                              stream: int = 0, mid_event: int = 0):

@@ -1032,6 +1032,21 @@ void set_tile_scratch(b200sdf::DecodeParams &P, void *base, uint32_t tile_cap)
 	P.tile_cap = tile_cap;
 }
 
+void single_sub(b200sdf::DecodeParams &P, const void *reqs, uint32_t n_reqs, const void *parts, uint32_t n_parts,
+                const void *host_curves, uint32_t n_curves, uint32_t n_seg, uint32_t curve_slots, void *frames, void *out,
+                uint64_t out_bytes)
+{
+	std::memset(&P, 0, sizeof(P));
+	b200sdf::SubBatch &S = P.sub[0];
+	S.reqs = reinterpret_cast<const b200sdf_glyph_req *>(reqs), S.n_reqs = n_reqs, S.req_base = 0;
+	S.parts = reinterpret_cast<const b200sdf_glyph_part *>(parts), S.n_parts = n_parts;
+	S.host_curves = reinterpret_cast<const b200sdf_curve *>(host_curves), S.n_host_curves = n_curves, S.n_host_segs = n_seg;
+	S.frames = reinterpret_cast<b200sdf_glyph_frame *>(frames);
+	S.out_addr = (uint64_t)(uintptr_t)out, S.out_bytes = out_bytes;
+	S.seg_base = 0, S.curve_base = 0, S.curve_slots = curve_slots;
+	P.n_sub = 1, P.n_reqs = n_reqs;
+}
+
 uint32_t persistent_grid(uint32_t n_reqs)
 {
 	static const uint32_t forced = [] { // B200SDF_PERSISTENT_GRID: experiments
@@ -1066,15 +1081,15 @@ constexpr uint32_t kGlyphMinItems = 8;
 
 // The counters are zero when this is called (zeroed when they were allocated, and again by the last CTA of every
 // persistent kernel): a batch is two launches, nothing else.
-void launch_glyph_pipeline(const b200sdf::DecodeParams &P, const void *d_segs, uint8_t *d_out, uint32_t *d_status,
-                           cudaStream_t stream, cudaEvent_t mid)
+void launch_glyph_pipeline(const b200sdf::DecodeParams &P, const void *d_segs, uint32_t *d_status, cudaStream_t stream, cudaEvent_t mid)
 {
 	using namespace b200sdf;
 	glyf_decode_kernel<<<(P.n_reqs + kGlyfWarps - 1) / kGlyfWarps, kGlyfThreads, 0, stream>>>(P);
 	if (mid)
 		cudaEventRecord(mid, stream);
+	// (the tile jobs carry absolute bitmap addresses — several batches, several bitmap areas: the kernel's base is 0)
 	sdf_tiles_persistent_kernel<<<persistent_grid(P.n_reqs), kThreads, 0, stream>>>(
-	    reinterpret_cast<const float4 *>(d_segs), P.curves, P.ojobs, P.tiles, P.tile_cap, P.counters, d_status, d_out);
+	    reinterpret_cast<const float4 *>(d_segs), P.curves, P.ojobs, P.tiles, P.tile_cap, P.counters, d_status, nullptr);
 }
 
 int ensure_font_tables(b200sdf_ctx *ctx)
@@ -1192,16 +1207,24 @@ uint32_t b200sdf_glyph_tile_bound(uint32_t width, uint32_t height)
 	return std::max(1u, ((nx + kGlyphMinItems - 1) / kGlyphMinItems) * ny);
 }
 
-int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint32_t n_reqs, const b200sdf_glyph_part *parts,
-                          uint32_t n_parts, const b200sdf_curve *curves, uint32_t n_curves, const b200sdf_segment *segs,
-                          uint32_t n_seg, uint32_t curve_slots, uint32_t tile_cap, uint64_t est_cost, b200sdf_glyph_frame *frames,
-                          uint8_t *out, uint64_t out_bytes, uint64_t *ticket)
+int b200sdf_submit_glyph_batches(b200sdf_ctx *ctx, const b200sdf_glyph_batch *batches, uint32_t n_batches, uint64_t est_cost,
+                                 uint64_t *ticket)
 {
 	using namespace b200sdf;
 	if (!ctx || !ticket)
 		return B200SDF_E_ARG;
-	if ((n_reqs && (!reqs || !frames)) || (n_parts && !parts) || (n_curves && !curves) || (n_seg && !segs) || (out_bytes && !out))
-		return fail_arg(ctx, "submit_glyphs: null buffer");
+	if (n_batches == 0 || n_batches > (uint32_t)kMaxSubBatches || !batches)
+		return fail_arg(ctx, "submit_glyph_batches: between 1 and B200SDF_MAX_BATCHES batches per submission");
+	uint64_t n_reqs = 0, n_seg = 0, curve_slots = 0, tile_cap = 0;
+	for (uint32_t b = 0; b < n_batches; ++b) {
+		const b200sdf_glyph_batch &B = batches[b];
+		if ((B.n_reqs && (!B.reqs || !B.frames)) || (B.n_parts && !B.parts) || (B.n_curves && !B.curves) || (B.n_seg && !B.segs) ||
+		    (B.out_bytes && !B.out))
+			return fail_arg(ctx, "submit_glyphs: null buffer");
+		n_reqs += B.n_reqs, n_seg += B.n_seg, curve_slots += B.curve_slots, tile_cap += std::max(1u, B.tile_cap);
+	}
+	if (n_reqs > 0xffffffffull || n_seg > 0xffffffffull || curve_slots > 0xffffffffull || tile_cap > 0xffffffffull)
+		return fail_arg(ctx, "submit_glyphs: submission too large");
 	const size_t si = acquire_slot(ctx);
 	Slot &s = ctx->slots[si];
 	cudaError_t e = cudaSetDevice(ctx->device);
@@ -1221,31 +1244,49 @@ int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 			return release_slot(ctx, s, fail_cuda(ctx, e, "cudaMalloc(counters)"));
 	}
 	*s.h_status = 0;
-	if (tile_cap == 0)
-		tile_cap = 1;
-	// what has to exist on the device: [0] segments [1] host curves [2] requests [3] parts [4] frames [5] bitmaps
-	// (each only when the caller's buffer is not pinned + mapped), [6] curve scratch [7] outline jobs, tiles
-	size_t need[9] = {(size_t)n_seg * sizeof(b200sdf_segment), (size_t)n_curves * sizeof(b200sdf_curve),
-	                  (size_t)n_reqs * sizeof(b200sdf_glyph_req), (size_t)n_parts * sizeof(b200sdf_glyph_part),
-	                  (size_t)n_reqs * sizeof(b200sdf_glyph_frame), (size_t)out_bytes,
-	                  (size_t)std::max(1u, curve_slots) * sizeof(b200sdf_curve), (size_t)tile_cap * kTileScratchPerJob,
-	                  (size_t)n_reqs * sizeof(b200sdf_outline_job)};
 	const bool zc = zero_copy_mode() == 1;
-	const void *k_reqs = zc && n_reqs ? pinned_registry().device_ptr(reqs, need[2]) : nullptr;
-	const void *k_parts = zc && n_parts ? pinned_registry().device_ptr(parts, need[3]) : nullptr;
-	void *k_frames = zc && n_reqs ? pinned_registry().device_ptr(frames, need[4]) : nullptr;
-	void *k_out = zero_copy_mode() != 0 && out_bytes ? pinned_registry().device_ptr(out, need[5]) : nullptr;
-	const void *k_hcurves = zc && n_curves ? pinned_registry().device_ptr(curves, need[1]) : nullptr;
-	if (k_hcurves)
-		need[1] = 0;
-	if (k_reqs)
-		need[2] = 0;
-	if (k_parts)
-		need[3] = 0;
-	if (k_frames)
-		need[4] = 0;
-	if (k_out)
-		need[5] = 0;
+	const bool one = n_batches == 1;
+	const b200sdf_glyph_batch &B0 = batches[0];
+	// What has to exist on the device: [0] segments (always staged: the raw-segment path reads them through the TMA
+	// unit) [1] host curves [2] requests [3] parts [4] frames [5] bitmaps — each only for a single batch whose buffer
+	// is not pinned + mapped — [6] curve scratch [7] tile lists [8] outline jobs
+	size_t need[9] = {(size_t)n_seg * sizeof(b200sdf_segment), 0, 0, 0, 0, 0,
+	                  (size_t)std::max<uint64_t>(1, curve_slots) * sizeof(b200sdf_curve), (size_t)tile_cap * kTileScratchPerJob,
+	                  (size_t)n_reqs * sizeof(b200sdf_outline_job)};
+	DecodeParams P;
+	std::memset(&P, 0, sizeof(P));
+	bool staged_frames = false, staged_out = false;
+	{
+		uint32_t req_base = 0, seg_base = 0, curve_base = 0;
+		for (uint32_t b = 0; b < n_batches; ++b) {
+			const b200sdf_glyph_batch &B = batches[b];
+			SubBatch &S = P.sub[b];
+			const size_t bytes[6] = {0, (size_t)B.n_curves * sizeof(b200sdf_curve), (size_t)B.n_reqs * sizeof(b200sdf_glyph_req),
+			                         (size_t)B.n_parts * sizeof(b200sdf_glyph_part), (size_t)B.n_reqs * sizeof(b200sdf_glyph_frame),
+			                         (size_t)B.out_bytes};
+			const void *k_hc = zc && B.n_curves ? pinned_registry().device_ptr(B.curves, bytes[1]) : nullptr;
+			const void *k_rq = zc && B.n_reqs ? pinned_registry().device_ptr(B.reqs, bytes[2]) : nullptr;
+			const void *k_pt = zc && B.n_parts ? pinned_registry().device_ptr(B.parts, bytes[3]) : nullptr;
+			void *k_fr = zc && B.n_reqs ? pinned_registry().device_ptr(B.frames, bytes[4]) : nullptr;
+			void *k_out = zero_copy_mode() != 0 && B.out_bytes ? pinned_registry().device_ptr(B.out, bytes[5]) : nullptr;
+			if (!one && ((B.n_curves && !k_hc) || (B.n_reqs && (!k_rq || !k_fr)) || (B.n_parts && !k_pt) || (B.out_bytes && !k_out)))
+				return release_slot(ctx, s, fail_arg(ctx, "submit_glyph_batches: several batches in one submission need buffers from b200sdf_alloc_pinned"));
+			if (one) { // a single batch may live in pageable memory: staged copies
+				need[1] = k_hc ? 0 : bytes[1], need[2] = k_rq ? 0 : bytes[2], need[3] = k_pt ? 0 : bytes[3];
+				need[4] = k_fr ? 0 : bytes[4], need[5] = k_out ? 0 : bytes[5];
+			}
+			S.host_curves = reinterpret_cast<const b200sdf_curve *>(k_hc);
+			S.reqs = reinterpret_cast<const b200sdf_glyph_req *>(k_rq);
+			S.parts = reinterpret_cast<const b200sdf_glyph_part *>(k_pt);
+			S.frames = reinterpret_cast<b200sdf_glyph_frame *>(k_fr);
+			S.out_addr = (uint64_t)(uintptr_t)k_out;
+			S.out_bytes = B.out_bytes;
+			S.n_reqs = B.n_reqs, S.req_base = req_base;
+			S.n_parts = B.n_parts, S.n_host_curves = B.n_curves, S.n_host_segs = B.n_seg;
+			S.seg_base = seg_base, S.curve_base = curve_base, S.curve_slots = B.curve_slots;
+			req_base += B.n_reqs, seg_base += B.n_seg, curve_base += B.curve_slots;
+		}
+	}
 	{
 		std::lock_guard<std::mutex> g(ctx->mu);
 		for (int k = 0; k < 9; ++k) {
@@ -1257,8 +1298,8 @@ int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 			ctx->ghwm[k] = std::max(ctx->ghwm[k], r);
 			need[k] = ctx->ghwm[k];
 		}
+		P.n_fonts = (uint32_t)ctx->fonts.size();
 	}
-	// the tile regions are addressed as bin * tile_cap: keep the stride the caller asked for, the allocation may be larger
 	if ((rc = grow_device(ctx, s.segs, need[0], s.stream)) || (rc = grow_device(ctx, s.curves, need[1], s.stream)) ||
 	    (rc = grow_device(ctx, s.reqs, need[2], s.stream)) || (rc = grow_device(ctx, s.parts, need[3], s.stream)) ||
 	    (rc = grow_device(ctx, s.frames, need[4], s.stream)) || (rc = grow_device(ctx, s.out, need[5], s.stream)) ||
@@ -1271,19 +1312,32 @@ int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 		if (e_ != cudaSuccess)                                       \
 			return release_slot(ctx, s, fail_cuda(ctx, e_, #call));  \
 	} while (0)
-	if (n_seg)
-		SUB_TRY(cudaMemcpyAsync(s.segs.p, segs, (size_t)n_seg * sizeof(b200sdf_segment), cudaMemcpyHostToDevice, s.stream));
-	if (n_curves && !k_hcurves) {
-		SUB_TRY(cudaMemcpyAsync(s.curves.p, curves, (size_t)n_curves * sizeof(b200sdf_curve), cudaMemcpyHostToDevice, s.stream));
-		k_hcurves = s.curves.p;
-	}
-	if (n_reqs && !k_reqs) {
-		SUB_TRY(cudaMemcpyAsync(s.reqs.p, reqs, (size_t)n_reqs * sizeof(b200sdf_glyph_req), cudaMemcpyHostToDevice, s.stream));
-		k_reqs = s.reqs.p;
-	}
-	if (n_parts && !k_parts) {
-		SUB_TRY(cudaMemcpyAsync(s.parts.p, parts, (size_t)n_parts * sizeof(b200sdf_glyph_part), cudaMemcpyHostToDevice, s.stream));
-		k_parts = s.parts.p;
+	for (uint32_t b = 0; b < n_batches; ++b)
+		if (batches[b].n_seg)
+			SUB_TRY(cudaMemcpyAsync(reinterpret_cast<b200sdf_segment *>(s.segs.p) + P.sub[b].seg_base, batches[b].segs,
+			                        (size_t)batches[b].n_seg * sizeof(b200sdf_segment), cudaMemcpyHostToDevice, s.stream));
+	if (one) {
+		SubBatch &S = P.sub[0];
+		if (B0.n_curves && !S.host_curves) {
+			SUB_TRY(cudaMemcpyAsync(s.curves.p, B0.curves, (size_t)B0.n_curves * sizeof(b200sdf_curve), cudaMemcpyHostToDevice, s.stream));
+			S.host_curves = reinterpret_cast<const b200sdf_curve *>(s.curves.p);
+		}
+		if (B0.n_reqs && !S.reqs) {
+			SUB_TRY(cudaMemcpyAsync(s.reqs.p, B0.reqs, (size_t)B0.n_reqs * sizeof(b200sdf_glyph_req), cudaMemcpyHostToDevice, s.stream));
+			S.reqs = reinterpret_cast<const b200sdf_glyph_req *>(s.reqs.p);
+		}
+		if (B0.n_parts && !S.parts) {
+			SUB_TRY(cudaMemcpyAsync(s.parts.p, B0.parts, (size_t)B0.n_parts * sizeof(b200sdf_glyph_part), cudaMemcpyHostToDevice, s.stream));
+			S.parts = reinterpret_cast<const b200sdf_glyph_part *>(s.parts.p);
+		}
+		if (B0.n_reqs && !S.frames) {
+			S.frames = reinterpret_cast<b200sdf_glyph_frame *>(s.frames.p);
+			staged_frames = true;
+		}
+		if (B0.out_bytes && !S.out_addr) {
+			S.out_addr = (uint64_t)(uintptr_t)s.out.p;
+			staged_out = true;
+		}
 	}
 	static const bool gpu_trace = std::getenv("B200SDF_GPU_TRACE") != nullptr;
 	if (n_reqs) {
@@ -1301,39 +1355,25 @@ int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 				}
 			}
 			s.host_submit_ns = now_ns_mono();
-			s.traced_tiles = n_reqs;
+			s.traced_tiles = (uint32_t)n_reqs;
 			cudaEventRecord(s.t0, s.stream);
 		}
-		DecodeParams P;
-		P.reqs = reinterpret_cast<const b200sdf_glyph_req *>(k_reqs);
-		P.n_reqs = n_reqs;
-		P.parts = reinterpret_cast<const b200sdf_glyph_part *>(k_parts);
-		P.n_parts = n_parts;
+		P.n_sub = n_batches;
+		P.n_reqs = (uint32_t)n_reqs;
 		P.font_base = ctx->d_font_base;
 		P.font_len = ctx->d_font_len;
-		{
-			std::lock_guard<std::mutex> g(ctx->mu);
-			P.n_fonts = (uint32_t)ctx->fonts.size();
-		}
-		P.host_curves = reinterpret_cast<const b200sdf_curve *>(k_hcurves);
-		P.n_host_curves = n_curves;
-		P.n_host_segs = n_seg;
 		P.curves = reinterpret_cast<b200sdf_curve *>(s.gcurves.p);
-		P.curve_slots = curve_slots;
 		P.ojobs = reinterpret_cast<b200sdf_outline_job *>(s.ojobs.p);
-		P.frames = reinterpret_cast<b200sdf_glyph_frame *>(k_frames ? k_frames : s.frames.p);
-		set_tile_scratch(P, s.tiles.p, tile_cap);
-		P.out_bytes = out_bytes;
+		set_tile_scratch(P, s.tiles.p, (uint32_t)tile_cap);
 		P.counters = s.counters;
 		P.cost_cap = glyph_cost_cap(est_cost);
 		P.min_items = kGlyphMinItems;
-		uint8_t *d_out = reinterpret_cast<uint8_t *>(k_out ? k_out : s.out.p);
-		launch_glyph_pipeline(P, s.segs.p, d_out, s.d_status, s.stream, nullptr);
+		launch_glyph_pipeline(P, s.segs.p, s.d_status, s.stream, nullptr);
 		SUB_TRY(cudaGetLastError());
-		if (!k_frames)
-			SUB_TRY(cudaMemcpyAsync(frames, s.frames.p, (size_t)n_reqs * sizeof(b200sdf_glyph_frame), cudaMemcpyDeviceToHost, s.stream));
-		if (!k_out && out_bytes)
-			SUB_TRY(cudaMemcpyAsync(out, s.out.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, s.stream));
+		if (staged_frames)
+			SUB_TRY(cudaMemcpyAsync(B0.frames, s.frames.p, (size_t)B0.n_reqs * sizeof(b200sdf_glyph_frame), cudaMemcpyDeviceToHost, s.stream));
+		if (staged_out)
+			SUB_TRY(cudaMemcpyAsync(B0.out, s.out.p, (size_t)B0.out_bytes, cudaMemcpyDeviceToHost, s.stream));
 		s.check_overflow = true;
 		if (s.t1 && s.traced_tiles)
 			cudaEventRecord(s.t1, s.stream);
@@ -1347,6 +1387,18 @@ int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 		*ticket = ((uint64_t)s.generation << 8) | (uint64_t)si;
 	}
 	return 0;
+}
+
+int b200sdf_submit_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint32_t n_reqs, const b200sdf_glyph_part *parts,
+                          uint32_t n_parts, const b200sdf_curve *curves, uint32_t n_curves, const b200sdf_segment *segs,
+                          uint32_t n_seg, uint32_t curve_slots, uint32_t tile_cap, uint64_t est_cost, b200sdf_glyph_frame *frames,
+                          uint8_t *out, uint64_t out_bytes, uint64_t *ticket)
+{
+	b200sdf_glyph_batch B;
+	B.reqs = reqs, B.n_reqs = n_reqs, B.parts = parts, B.n_parts = n_parts, B.curves = curves, B.n_curves = n_curves;
+	B.segs = segs, B.n_seg = n_seg, B.curve_slots = curve_slots, B.tile_cap = tile_cap, B.frames = frames, B.out = out;
+	B.out_bytes = out_bytes;
+	return b200sdf_submit_glyph_batches(ctx, &B, 1, est_cost, ticket);
 }
 
 int b200sdf_render_glyphs_device(b200sdf_ctx *ctx, const b200sdf_glyph_req *d_reqs, uint32_t n_reqs,
@@ -1378,23 +1430,19 @@ int b200sdf_render_glyphs_device(b200sdf_ctx *ctx, const b200sdf_glyph_req *d_re
 		CU_TRY(ctx, cudaMemsetAsync(ctx->dv_counters, 0, sizeof(BatchCounters), (cudaStream_t)stream)); // ordered before the kernels below
 	}
 	DecodeParams P;
-	P.reqs = d_reqs, P.n_reqs = n_reqs, P.parts = d_parts, P.n_parts = n_parts;
+	single_sub(P, d_reqs, n_reqs, d_parts, n_parts, d_curves, n_curves, n_seg, curve_slots, d_frames, d_out, out_bytes);
 	P.font_base = ctx->d_font_base, P.font_len = ctx->d_font_len;
 	{
 		std::lock_guard<std::mutex> g(ctx->mu);
 		P.n_fonts = (uint32_t)ctx->fonts.size();
 	}
-	P.host_curves = d_curves, P.n_host_curves = n_curves, P.n_host_segs = n_seg;
 	P.curves = reinterpret_cast<b200sdf_curve *>(ctx->dv_gcurves.p);
-	P.curve_slots = curve_slots;
 	P.ojobs = reinterpret_cast<b200sdf_outline_job *>(ctx->dv_ojobs.p);
-	P.frames = d_frames;
 	set_tile_scratch(P, ctx->dv_tiles.p, tile_cap);
-	P.out_bytes = out_bytes;
 	P.counters = ctx->dv_counters;
 	P.cost_cap = glyph_cost_cap(est_cost);
 	P.min_items = kGlyphMinItems;
-	launch_glyph_pipeline(P, d_segs, d_out, nullptr, (cudaStream_t)stream, (cudaEvent_t)mid_event);
+	launch_glyph_pipeline(P, d_segs, nullptr, (cudaStream_t)stream, (cudaEvent_t)mid_event);
 	CU_TRY(ctx, cudaGetLastError());
 	{
 		std::lock_guard<std::mutex> g(ctx->mu);
@@ -1454,19 +1502,15 @@ int b200sdf_decode_glyphs(b200sdf_ctx *ctx, const b200sdf_glyph_req *reqs, uint3
 		e = cudaMemset(d_curves, 0, (size_t)std::max(1u, curve_slots) * sizeof(b200sdf_curve));
 	if (e == cudaSuccess) {
 		DecodeParams P;
-		P.reqs = reinterpret_cast<const b200sdf_glyph_req *>(d_reqs), P.n_reqs = n_reqs;
-		P.parts = reinterpret_cast<const b200sdf_glyph_part *>(d_parts), P.n_parts = n_parts;
+		single_sub(P, d_reqs, n_reqs, d_parts, n_parts, d_hcurves, n_curves, n_seg, curve_slots, d_frames, nullptr, out_bytes);
 		P.font_base = ctx->d_font_base, P.font_len = ctx->d_font_len;
 		{
 			std::lock_guard<std::mutex> g(ctx->mu);
 			P.n_fonts = (uint32_t)ctx->fonts.size();
 		}
-		P.host_curves = reinterpret_cast<const b200sdf_curve *>(d_hcurves), P.n_host_curves = n_curves, P.n_host_segs = n_seg;
-		P.curves = reinterpret_cast<b200sdf_curve *>(d_curves), P.curve_slots = curve_slots;
+		P.curves = reinterpret_cast<b200sdf_curve *>(d_curves);
 		P.ojobs = reinterpret_cast<b200sdf_outline_job *>(d_ojobs);
-		P.frames = reinterpret_cast<b200sdf_glyph_frame *>(d_frames);
 		set_tile_scratch(P, d_tiles, tile_cap);
-		P.out_bytes = out_bytes;
 		P.counters = reinterpret_cast<BatchCounters *>(d_ctr);
 		P.cost_cap = glyph_cost_cap(est_cost), P.min_items = kGlyphMinItems;
 		glyf_decode_kernel<<<(n_reqs + kGlyfWarps - 1) / kGlyfWarps, kGlyfThreads>>>(P);

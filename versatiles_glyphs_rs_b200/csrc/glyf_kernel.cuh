@@ -62,24 +62,33 @@ struct GlyfWarpScratch {
 	__align__(16) uint8_t bytes[kGlyfStageBytes + 32];
 };
 
-struct DecodeParams {
+// One caller-side batch of a submission (several queued batches of a pipeline are decoded and rendered by ONE pair of
+// launches: a kernel pair over a few hundred glyphs runs as long as its slowest glyph / heaviest tile, whatever its size)
+constexpr int kMaxSubBatches = 16;
+struct SubBatch {
 	const b200sdf_glyph_req *reqs;
-	uint32_t n_reqs;
 	const b200sdf_glyph_part *parts;
-	uint32_t n_parts;
+	const b200sdf_curve *host_curves; // records of host-recorded CURVES requests
+	b200sdf_glyph_frame *frames;      // result per request (pinned host memory or device mirror)
+	uint64_t out_addr;                // device-side address of the batch's bitmap area
+	uint64_t out_bytes;
+	uint32_t n_reqs, req_base;        // requests [req_base, req_base + n_reqs) of the submission
+	uint32_t n_parts, n_host_curves, n_host_segs;
+	uint32_t seg_base;                // where the batch's segments start in the submission's segment array
+	uint32_t curve_base, curve_slots; // the batch's part of the curve scratch
+};
+
+struct DecodeParams {
+	SubBatch sub[kMaxSubBatches];
+	uint32_t n_sub;
+	uint32_t n_reqs;                  // all batches together
 	const uint8_t *const *font_base; // device table: glyf bytes of every uploaded font
 	const uint64_t *font_len;
 	uint32_t n_fonts;
-	const b200sdf_curve *host_curves; // records of host-recorded CURVES requests
-	uint32_t n_host_curves;
-	uint32_t n_host_segs;
-	b200sdf_curve *curves;            // device scratch: every glyph's records at req.curve_off
-	uint32_t curve_slots;
-	b200sdf_outline_job *ojobs;       // device scratch: one per request
-	b200sdf_glyph_frame *frames;      // result per request (pinned host memory or device mirror)
+	b200sdf_curve *curves;            // device scratch: every glyph's records at sub.curve_base + req.curve_off
+	b200sdf_outline_job *ojobs;       // device scratch: one per request (index = request number in the submission)
 	b200sdf_tile_job *tiles;          // kTileClasses lists of tile_cap entries each
 	uint32_t tile_cap;
-	uint64_t out_bytes;
 	BatchCounters *counters;
 	uint32_t cost_cap;                // largest tile job (item x segment units) before a glyph is cut
 	uint32_t min_items;
@@ -552,16 +561,22 @@ __device__ __forceinline__ void plan_tiles_dev(const DecodeParams &P, uint32_t s
 
 __device__ __forceinline__ void decode_request(const DecodeParams &P, const uint32_t gi, GlyfWarpScratch &wscratch, const int lane)
 {
-	const b200sdf_glyph_req rq = P.reqs[gi];
+	int k = 0;
+#pragma unroll 1
+	for (int q = 1; q < (int)P.n_sub; ++q)
+		k = gi >= P.sub[q].req_base ? q : k;
+	const SubBatch &B = P.sub[k];
+	const uint32_t li = gi - B.req_base;
+	const b200sdf_glyph_req rq = B.reqs[li];
 	b200sdf_glyph_frame fr;
 	fr.x0 = rq.x0, fr.y0 = rq.y0, fr.width = 0, fr.height = 0, fr.seg_cnt = 0, fr.status = B200SDF_GLYPH_EMPTY;
 	b200sdf_outline_job oj;
 	oj.kind = B200SDF_KIND_CURVES;
-	oj.src_off = rq.curve_off, oj.src_cnt = 0, oj.seg_cnt = 0;
+	oj.src_off = B.curve_base + rq.curve_off, oj.src_cnt = 0, oj.seg_cnt = 0;
 	oj.width = oj.height = 0;
 	oj.x0 = oj.y0 = 0;
 	oj.scale = rq.scale, oj.dx = rq.dx;
-	oj.out_off = rq.out_off;
+	oj.out_off = B.out_addr + rq.out_off; // absolute: the SDF kernel's bitmap base is 0
 
 	if (rq.kind == B200SDF_KIND_GLYF) {
 		GlyphAcc acc;
@@ -569,17 +584,17 @@ __device__ __forceinline__ void decode_request(const DecodeParams &P, const uint
 		acc.bx0 = acc.by0 = __longlong_as_double(0x7ff0000000000000ll);
 		acc.bx1 = acc.by1 = __longlong_as_double(0xfff0000000000000ll);
 		acc.status = 0;
-		const bool range_ok = (uint64_t)rq.src_off + rq.src_cnt <= P.n_parts && (uint64_t)rq.curve_off + rq.curve_cap <= P.curve_slots;
+		const bool range_ok = (uint64_t)rq.src_off + rq.src_cnt <= B.n_parts && (uint64_t)rq.curve_off + rq.curve_cap <= B.curve_slots;
 		if (!range_ok)
 			acc.status = B200SDF_GLYPH_BAD_REQUEST;
 		for (uint32_t pi = 0; pi < rq.src_cnt && acc.status == 0; ++pi) {
-			const b200sdf_glyph_part pt = P.parts[rq.src_off + pi];
+			const b200sdf_glyph_part pt = B.parts[rq.src_off + pi];
 			if (pt.font >= P.n_fonts || (uint64_t)pt.glyf_off + pt.glyf_len > P.font_len[pt.font]) {
 				acc.status = B200SDF_GLYPH_BAD_REQUEST;
 				break;
 			}
 			if (!decode_simple_glyph(P.font_base[pt.font] + pt.glyf_off, pt.glyf_len, pt.ox, pt.oy, wscratch,
-			                         P.curves + rq.curve_off, rq.curve_cap, acc, lane))
+			                         P.curves + B.curve_base + rq.curve_off, rq.curve_cap, acc, lane))
 				break;
 		}
 		if (acc.status != 0) {
@@ -593,7 +608,7 @@ __device__ __forceinline__ void decode_request(const DecodeParams &P, const uint
 				const double fx0 = floor(lx) - 3.0, fy0 = floor(ly) - 3.0, fx1 = ceil(hx) + 3.0, fy1 = ceil(hy) + 3.0;
 				const double w = fx1 - fx0, h = fy1 - fy0;
 				if (!(fabs(fx0) < 1e9 && fabs(fy0) < 1e9 && w >= 1.0 && h >= 1.0 && w <= (double)B200SDF_MAX_DIM && h <= (double)B200SDF_MAX_DIM) ||
-				    (uint64_t)w * (uint64_t)h > (uint64_t)rq.out_cap || rq.out_off + (uint64_t)w * (uint64_t)h > P.out_bytes) {
+				    (uint64_t)w * (uint64_t)h > (uint64_t)rq.out_cap || rq.out_off + (uint64_t)w * (uint64_t)h > B.out_bytes) {
 					fr.status = B200SDF_GLYPH_NEEDS_HOST; // frame does not fit the slot the host reserved from the header bbox
 				} else {
 					fr.x0 = (int32_t)fx0, fr.y0 = (int32_t)fy0;
@@ -607,15 +622,15 @@ __device__ __forceinline__ void decode_request(const DecodeParams &P, const uint
 		}
 	} else if (rq.kind == B200SDF_KIND_CURVES) {
 		// host-recorded glyph (scaled composites, ...): frame and records are given; copy the records next to the others
-		const bool ok = (uint64_t)rq.src_off + rq.src_cnt <= P.n_host_curves && rq.src_cnt <= rq.curve_cap &&
-		                (uint64_t)rq.curve_off + rq.curve_cap <= P.curve_slots && rq.width >= 1 && rq.height >= 1 &&
+		const bool ok = (uint64_t)rq.src_off + rq.src_cnt <= B.n_host_curves && rq.src_cnt <= rq.curve_cap &&
+		                (uint64_t)rq.curve_off + rq.curve_cap <= B.curve_slots && rq.width >= 1 && rq.height >= 1 &&
 		                rq.width <= B200SDF_MAX_DIM && rq.height <= B200SDF_MAX_DIM &&
-		                rq.out_off + (uint64_t)rq.width * rq.height <= P.out_bytes;
+		                rq.out_off + (uint64_t)rq.width * rq.height <= B.out_bytes;
 		if (!ok) {
 			fr.status = B200SDF_GLYPH_BAD_REQUEST;
 		} else {
-			const uint4 *src = reinterpret_cast<const uint4 *>(P.host_curves + rq.src_off);
-			uint4 *dst = reinterpret_cast<uint4 *>(P.curves + rq.curve_off);
+			const uint4 *src = reinterpret_cast<const uint4 *>(B.host_curves + rq.src_off);
+			uint4 *dst = reinterpret_cast<uint4 *>(P.curves + B.curve_base + rq.curve_off);
 			for (uint32_t i = (uint32_t)lane; i < rq.src_cnt * 2u; i += 32)
 				dst[i] = src[i];
 			fr.width = rq.width, fr.height = rq.height, fr.seg_cnt = rq.seg_cnt, fr.status = B200SDF_GLYPH_OK;
@@ -623,15 +638,15 @@ __device__ __forceinline__ void decode_request(const DecodeParams &P, const uint
 			oj.seg_cnt = rq.seg_cnt;
 		}
 	} else if (rq.kind == B200SDF_KIND_SEGMENTS) {
-		const bool ok = (uint64_t)rq.src_off + rq.src_cnt <= P.n_host_segs && rq.seg_cnt == rq.src_cnt && rq.width >= 1 &&
+		const bool ok = (uint64_t)rq.src_off + rq.src_cnt <= B.n_host_segs && rq.seg_cnt == rq.src_cnt && rq.width >= 1 &&
 		                rq.height >= 1 && rq.width <= B200SDF_MAX_DIM && rq.height <= B200SDF_MAX_DIM &&
-		                rq.out_off + (uint64_t)rq.width * rq.height <= P.out_bytes;
+		                rq.out_off + (uint64_t)rq.width * rq.height <= B.out_bytes;
 		if (!ok) {
 			fr.status = B200SDF_GLYPH_BAD_REQUEST;
 		} else {
 			fr.width = rq.width, fr.height = rq.height, fr.seg_cnt = rq.seg_cnt, fr.status = B200SDF_GLYPH_OK;
 			oj.kind = B200SDF_KIND_SEGMENTS;
-			oj.src_off = rq.src_off, oj.src_cnt = rq.src_cnt, oj.seg_cnt = rq.seg_cnt;
+			oj.src_off = B.seg_base + rq.src_off, oj.src_cnt = rq.src_cnt, oj.seg_cnt = rq.seg_cnt;
 		}
 	} else {
 		fr.status = B200SDF_GLYPH_BAD_REQUEST;
@@ -644,7 +659,7 @@ __device__ __forceinline__ void decode_request(const DecodeParams &P, const uint
 	__syncwarp(); // this warp's curve records are written before any lane publishes the jobs
 	if (lane == 0) {
 		P.ojobs[gi] = oj;
-		P.frames[gi] = fr;
+		B.frames[li] = fr;
 	}
 	if (fr.status == B200SDF_GLYPH_OK)
 		plan_tiles_dev(P, oj.src_off, oj.seg_cnt, oj.width, oj.height, oj.out_off,

@@ -313,7 +313,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		const long v = e ? std::atol(e) : 0;
 		return (size_t)(v >= 1 && v <= 64 ? v : 0);
 	}();
-	const size_t kBatchesPerWorker = kBatchesPerWorkerEnv ? kBatchesPerWorkerEnv : (glyf_mode ? 2 : 4);
+	const size_t kBatchesPerWorker = kBatchesPerWorkerEnv ? kBatchesPerWorkerEnv : 4;
 	constexpr int kEarlyWorkers = 4;
 	static const bool kLatencyTail = [] { // VGB_LATENCY_TAIL=1: plan each worker's last batch for latency
 		const char *e = std::getenv("VGB_LATENCY_TAIL"); // (measured on C2: 1.30-1.35 ms with, 1.26-1.34 without: off)
@@ -347,6 +347,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		std::unique_ptr<GlyphBatch> batch;
 		std::vector<Part> parts;
 		uint64_t ticket = 0;
+		std::vector<Flight *> mates; // the other batches of the same submission (they finish together)
 	};
 	std::mutex qm;
 	std::condition_variable qcv;
@@ -671,10 +672,25 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		for (;;) {
 			Flight *f = nullptr;
 			{
+				// Everything the workers queued since the last look goes into ONE submission (glyph-level batches): a
+				// kernel pair over a few hundred glyphs runs as long as its slowest glyph and heaviest tile, so 20 small
+				// submissions cost the GPU 0.7 ms where the same glyphs in a few large ones cost 0.55
 				std::lock_guard<std::mutex> g(qm);
-				if (!submit_q.empty()) {
-					f = submit_q.front();
+				static const size_t group_max = [] {
+					const char *e = std::getenv("VGB_GROUP_MAX");
+					const long v = e ? std::atol(e) : 0;
+					return v >= 1 && v <= (long)Renderer::kMaxGroup ? (size_t)v : Renderer::kMaxGroup;
+				}();
+				const size_t take = glyf_mode ? group_max : 1;
+				size_t group_glyphs = 0; // large batches fill the GPU on their own: a submission stops growing at 4096 glyphs
+				while (!submit_q.empty() && (!f || (f->mates.size() + 1 < take && group_glyphs < 4096))) {
+					Flight *q = submit_q.front();
+					group_glyphs += q->batch->job_count();
 					submit_q.pop_front();
+					if (!f)
+						f = q;
+					else
+						f->mates.push_back(q);
 				}
 			}
 			if (f) {
@@ -682,7 +698,11 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				const uint64_t t0 = now_ns();
 				if (trace)
 					events[(size_t)workers].emplace_back('s', t0 - t_begin);
-				const bool ok = renderer.submit_batch(*f->batch, &f->ticket, &e);
+				GlyphBatch *group[Renderer::kMaxGroup];
+				group[0] = f->batch.get();
+				for (size_t k = 0; k < f->mates.size(); ++k)
+					group[k + 1] = f->mates[k]->batch.get();
+				const bool ok = renderer.submit_batches(group, f->mates.size() + 1, &f->ticket, &e);
 				submit_ns.fetch_add(now_ns() - t0, std::memory_order_relaxed);
 				if (trace)
 					events[(size_t)workers].emplace_back('S', now_ns() - t_begin);
@@ -694,8 +714,13 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					{
 						std::lock_guard<std::mutex> g(qm);
 						done_q.push_back(f);
+						for (Flight *q : f->mates) {
+							q->parts.clear();
+							done_q.push_back(q);
+						}
 					}
-					done_seq.fetch_add(1, std::memory_order_release);
+					done_seq.fetch_add(1 + f->mates.size(), std::memory_order_release);
+					f->mates.clear();
 					qcv.notify_all();
 				}
 			}
@@ -717,6 +742,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				if (!ok) {
 					fail(e);
 					q->parts.clear();
+					for (Flight *m : q->mates)
+						m->parts.clear();
 					finished = true;
 				}
 				if (!finished) {
@@ -728,6 +755,9 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					events[(size_t)workers].emplace_back('d', now_ns() - t_begin);
 				inflight.erase(inflight.begin() + (long)i);
 				finished_now.push_back(q);
+				for (Flight *m : q->mates)
+					finished_now.push_back(m);
+				q->mates.clear();
 			}
 			if (!finished_now.empty()) {
 				// hand everything that finished in this sweep over at once: one lock, one wake-up (a futex wake per
@@ -801,6 +831,9 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		while (!inflight.empty()) {
 			renderer.wait_batch(inflight.front()->ticket, nullptr);
 			done_q.push_back(inflight.front());
+			for (Flight *m : inflight.front()->mates)
+				done_q.push_back(m);
+			inflight.front()->mates.clear();
 			inflight.pop_front();
 		}
 	for (std::deque<Flight *> *q : {&submit_q, &done_q})

@@ -994,6 +994,41 @@ bool Renderer::submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *er
 	return true;
 }
 
+bool Renderer::submit_batches(GlyphBatch *const *batches, size_t n, uint64_t *ticket, std::string *err) const
+{
+	if (n == 1 || mode_ != Mode::Cuda)
+		return n == 1 && submit_batch(*batches[0], ticket, err);
+	if (n == 0 || n > kMaxGroup) {
+		if (err)
+			*err = "submit_batches: between 1 and 16 batches";
+		return false;
+	}
+	b200sdf_glyph_batch desc[kMaxGroup];
+	uint64_t est = 0;
+	for (size_t k = 0; k < n; ++k) {
+		GlyphBatch &b = *batches[k];
+		if (b.mode() != Flatten::Glyf || !b.ensure_output() || !b.ensure_frames()) {
+			if (err)
+				*err = b.mode() != Flatten::Glyf ? "submit_batches: only glyph-level batches can share a submission"
+				                                 : "out of host memory for the bitmap / frame buffer";
+			return false;
+		}
+		b200sdf_glyph_batch &d = desc[k];
+		d.reqs = b.reqs(), d.n_reqs = b.job_count(), d.parts = b.parts(), d.n_parts = b.part_count();
+		d.curves = b.curves(), d.n_curves = b.curve_count(), d.segs = b.segments(), d.n_seg = b.segment_count();
+		d.curve_slots = b.curve_slots(), d.tile_cap = b.tile_cap(), d.frames = b.frames(), d.out = b.bitmaps();
+		d.out_bytes = b.bitmap_bytes();
+		est = std::max(est, b.est_cost());
+	}
+	const int rc = b200sdf_submit_glyph_batches(ctx_, desc, (uint32_t)n, est, ticket);
+	if (rc != 0) {
+		if (err)
+			*err = std::string("b200sdf_submit_glyph_batches: ") + b200sdf_last_error(ctx_);
+		return false;
+	}
+	return true;
+}
+
 bool Renderer::wait_batch(uint64_t ticket, std::string *err) const
 {
 	if (mode_ == Mode::Dummy) {

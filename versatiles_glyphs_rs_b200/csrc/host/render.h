@@ -328,6 +328,10 @@ class Renderer {
 	// Asynchronous form: several batches in flight on the context's streams.
 	bool submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *err = nullptr) const;
 	bool wait_batch(uint64_t ticket, std::string *err = nullptr) const;
+	// Several prepared glyph-level batches in ONE submission (b200sdf_submit_glyph_batches: one decode launch, one SDF
+	// launch, one ticket for all of them); other kinds of batches, or a single one, go through submit_batch.
+	static constexpr size_t kMaxGroup = B200SDF_MAX_BATCHES;
+	bool submit_batches(GlyphBatch *const *batches, size_t n, uint64_t *ticket, std::string *err = nullptr) const;
 	// Two-step submission for pipelines with one CUDA thread: prepare_batch (any thread: sizes the bitmap
 	// buffer, validates the jobs and plans the tiles) then submit_batch (enqueue only).
 	bool prepare_batch(GlyphBatch &batch, std::string *err = nullptr, bool latency = false) const;
