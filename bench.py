@@ -12,7 +12,7 @@ pixel x segment pairs).  At N > 1 it is ONE job of N such fonts (the merge under
 rank 0 checks that the gathered files equal an unsharded run.  Per-GPU work is constant: "scaling": "weak".
 
   value      glyphs/s with glyph requests, fonts (glyf tables) and bitmaps resident in HBM: K times
-             [glyf_decode_kernel + sdf_tiles_persistent_kernel], timed with CUDA events on the launching stream, L2
+             [glyf_decode_kernel + sdf_tiles_strided_kernel], timed with CUDA events on the launching stream, L2
              flushed between steps.
   e2e        glyphs/s through the reference-facing host API (FontManager.render_glyphs: parsed fonts in host memory ->
              PBF bytes in host memory): cmap / hmtx / loca lookups, glyph requests written to pinned memory (read by the
@@ -546,14 +546,14 @@ def main():
             "glyphs_this_rank": job.n_glyphs, "bitmaps": n_bitmaps, "bitmaps_all_ranks": bitmaps_all, "pixels": pixels, "pairs": pairs,
             "segments": int(seg_cnt[okf].sum()), "curve_records": curve_records, "host_recorded_glyphs": int((job.reqs["kind"] != N.KIND_GLYF).sum()),
             "tile_jobs": n_tiles, "bitmap_checksum": checksum,
-            "value_counts": "glyphs with a bitmap, all ranks; the timed step = glyf_decode_kernel + sdf_tiles_persistent_kernel over this rank's shard",
+            "value_counts": "glyphs with a bitmap, all ranks; the timed step = glyf_decode_kernel + sdf_tiles_strided_kernel over this rank's shard",
             "decode_kernel_ms": statistics.mean(decode_ms), "sdf_kernel_ms": statistics.mean(sdf_ms), "step_ms_this_rank": statistics.mean(total_ms),
             "resident_in_hbm": "glyf tables of the fonts (uploaded when first used, outside the timed region), glyph requests, bitmaps",
             "shard_cost_estimates": [int(x) for x in job.loads], "host_planned_sdf_kernel_ms": host_planned_ms,
             "device_plan_in_one_cta_per_job_kernel_ms": device_plan_ms,
         },
         "roofline": {
-            "bound": "fp32", "kernel": "sdf_tiles_persistent_kernel", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+            "bound": "fp32", "kernel": "sdf_tiles_strided_kernel", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
             "frac": achieved_tflops / fp32_peak_tflops, "traffic": traffic, "traffic_source": traffic_source,
             "peak_source": "FFMA-chain microbenchmark in this run (b200sdf_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
             "flop_model": "3 flop x pixel x vertex (FFMA + min) + 11 flop x pixel x long segment (|d| > 0.5 px); band "

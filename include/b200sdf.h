@@ -259,7 +259,7 @@ int b200sdf_font_upload(b200sdf_ctx *ctx, const uint8_t *glyf, uint64_t len, uin
 /* Upper bound of the tile jobs the device may plan for a glyph whose frame is at most width x height:
  * tile_cap of a submission = the sum over its requests. */
 uint32_t b200sdf_glyph_tile_bound(uint32_t width, uint32_t height);
-/* Enqueue one batch of glyph requests: decode + frame + tile planning (one kernel), SDF (one persistent kernel).
+/* Enqueue one batch of glyph requests: decode + frame + tile planning (one kernel), SDF (one kernel, one CTA per tile job).
  * frames[i] (written by the device) and the bitmaps are valid after b200sdf_wait / b200sdf_poll(ticket).
  * curves / segs: the arrays CURVES / SEGMENTS requests index (may be NULL / 0).  curve_slots = size of the device's
  * curve scratch in records (>= every request's curve_off + curve_cap); tile_cap = capacity of the device's tile

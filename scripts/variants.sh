@@ -5,7 +5,13 @@ set -u
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 declare -A V=(
   [base]=""
-  [nosplit]="-DB200SDF_SPLIT_BARRIER=0"
+  [vpack0]="-DB200SDF_VPACK=0"
+  [even0]="-DB200SDF_EVEN_ROUNDS=0"
+  [old]="-DB200SDF_VPACK=0 -DB200SDF_EVEN_ROUNDS=0"
+  [ctas7]="-DB200SDF_PERSISTENT_MIN_CTAS=7"
+  [ctas5]="-DB200SDF_PERSISTENT_MIN_CTAS=5"
+  [mini32]="-DB200SDF_MINI=32"
+  [mini128]="-DB200SDF_MINI=128"
 )
 if [ "${1:-}" = "build" ]; then
   for n in "${!V[@]}"; do

@@ -1088,8 +1088,23 @@ void launch_glyph_pipeline(const b200sdf::DecodeParams &P, const void *d_segs, u
 	if (mid)
 		cudaEventRecord(mid, stream);
 	// (the tile jobs carry absolute bitmap addresses — several batches, several bitmap areas: the kernel's base is 0)
-	sdf_tiles_persistent_kernel<<<persistent_grid(P.n_reqs), kThreads, 0, stream>>>(
-	    reinterpret_cast<const float4 *>(d_segs), P.curves, P.ojobs, P.tiles, P.tile_cap, P.counters, d_status, nullptr);
+	static const int form = [] { // B200SDF_SDF_KERNEL=persistent|strided (experiments)
+		const char *e = std::getenv("B200SDF_SDF_KERNEL");
+		return e && e[0] == 'p' ? 0 : 1;
+	}();
+	static const uint32_t per_glyph = [] { // B200SDF_STRIDED_PER_GLYPH: CTAs per glyph request in the strided form's grid
+		const char *e = std::getenv("B200SDF_STRIDED_PER_GLYPH");
+		const long v = e ? std::atol(e) : 0;
+		return (uint32_t)(v > 0 ? v : 1);
+	}();
+	if (form == 0) {
+		sdf_tiles_persistent_kernel<<<persistent_grid(P.n_reqs), kThreads, 0, stream>>>(
+		    reinterpret_cast<const float4 *>(d_segs), P.curves, P.ojobs, P.tiles, P.tile_cap, P.counters, d_status, nullptr);
+	} else {
+		const uint64_t grid = std::min<uint64_t>((uint64_t)P.tile_cap, std::max<uint64_t>(kSMs, (uint64_t)P.n_reqs * per_glyph));
+		sdf_tiles_strided_kernel<<<(uint32_t)grid, kThreads, 0, stream>>>(
+		    reinterpret_cast<const float4 *>(d_segs), P.curves, P.ojobs, P.tiles, P.tile_cap, P.counters, d_status, nullptr);
+	}
 }
 
 int ensure_font_tables(b200sdf_ctx *ctx)

@@ -68,6 +68,16 @@
 #ifndef B200SDF_VUNROLL
 #define B200SDF_VUNROLL 1 // vertex-loop unroll (pairs of vertices per trip); 1 beats 2 and 4 at 64 registers
 #endif
+#ifndef B200SDF_EVEN_ROUNDS
+// shared staging: a round's segments split evenly between the four warps.  Measured and left off: C2 / C4 0.4515 / 9.566 ms
+// with it against 0.4446 / 9.506 ms without
+#define B200SDF_EVEN_ROUNDS 0
+#endif
+#ifndef B200SDF_VPACK
+// vertex loop: squared distances with FFMA2 (two pixels per instruction; 49 instead of 65 instructions per vertex pair).
+// Measured C2 / C4: 0.4446 / 9.506 ms against 0.4468 / 9.671 ms (persistent form), 0.408 against 0.426 ms (one CTA per job)
+#define B200SDF_VPACK 1
+#endif
 #ifndef B200SDF_CURVE_SMEM
 #define B200SDF_CURVE_SMEM 256 // curve records (32 B) kept in shared memory per CTA
 #endif
@@ -627,12 +637,24 @@ __device__ B200SDF_TILE_INLINE void render_tile(SharedStorage &sm, const b200sdf
 					for (int r = 0; r < kTileH; ++r) {
 						const float ya = (r & 1) ? sya[r >> 1].y : sya[r >> 1].x;
 						const float yb = (r & 1) ? syb[r >> 1].y : syb[r >> 1].x;
+#if B200SDF_VPACK
+						// two horizontally adjacent pixels per FFMA2 (the row term is a broadcast scalar operand): the
+						// squared distances take half the issue slots, which is what this loop runs out of first
+#pragma unroll
+						for (int j = 0; j < kTileW / 2; ++j) {
+							const float2 da = __ffma2_rn(paxa[j], paxa[j], make_float2(ya, ya));
+							const float2 db = __ffma2_rn(paxb[j], paxb[j], make_float2(yb, yb));
+							mn[r][2 * j] = fmin3(mn[r][2 * j], da.x, db.x);
+							mn[r][2 * j + 1] = fmin3(mn[r][2 * j + 1], da.y, db.y);
+						}
+#else
 #pragma unroll
 						for (int j = 0; j < kTileW; ++j) {
 							const float xa = (j & 1) ? paxa[j >> 1].y : paxa[j >> 1].x;
 							const float xb = (j & 1) ? paxb[j >> 1].y : paxb[j >> 1].x;
 							mn[r][j] = fmin3(mn[r][j], fmaf(xa, xa, ya), fmaf(xb, xb, yb));
 						}
+#endif
 					}
 				}
 	};
@@ -648,8 +670,17 @@ __device__ B200SDF_TILE_INLINE void render_tile(SharedStorage &sm, const b200sdf
 		const int cs = wslice * lslices + lslice;              // my position among them
 		const uint32_t per_round = 4u * (uint32_t)kMini;
 		for (uint32_t r0 = 0; r0 < S; r0 += per_round) {
+#if B200SDF_EVEN_ROUNDS
+			// the round's segments in four equal shares (a short last round is staged in one pass per warp instead of two
+			// passes by the first warps while the others wait at the barrier)
+			const uint32_t n_round = min(per_round, S - r0);
+			const uint32_t share = (n_round + 3u) >> 2;
+			const uint32_t base = r0 + (uint32_t)warp * share;
+			const int n = (uint32_t)warp * share < n_round ? (int)min(share, n_round - (uint32_t)warp * share) : 0;
+#else
 			const uint32_t base = r0 + (uint32_t)warp * (uint32_t)kMini;
 			const int n = base < S ? (int)min((uint32_t)kMini, S - base) : 0;
+#endif
 			int nv = 0, nl = 0;
 			if (n > 0) {
 				uint32_t c_lo = find_curve(gcurves, n_curves, base);
@@ -889,6 +920,60 @@ __global__ void __launch_bounds__(128, B200SDF_PERSISTENT_MIN_CTAS) sdf_tiles_pe
 		__threadfence();
 		if (atomicAdd(&ctr->done_ctas, 1u) == gridDim.x - 1) {
 			// every other CTA has left its loop: nobody reads the counters any more
+			if (status_out)
+				*status_out = ctr->overflow;
+#pragma unroll
+			for (int c = 0; c < kTileClasses; ++c)
+				ctr->class_count[c] = 0;
+			ctr->next_tile = 0;
+			ctr->overflow = 0;
+			ctr->done_ctas = 0;
+			__threadfence_system();
+		}
+	}
+}
+
+// The same tile lists, one CTA per tile job where the grid allows it: the host does not know the batch's tile count when
+// it makes the launch, so the grid is a guess (a small multiple of the glyph count).  CTA b renders claim number b; if the
+// batch has more tile jobs than the grid has CTAs the first CTAs go on with b + gridDim.x, ...; CTAs past the end leave
+// at once.  Against the persistent form: the hardware's CTA scheduler does the dynamic assignment (no cursor, no claim,
+// no job hand-over through shared memory) and the kernel fits 64 registers, 8 CTAs per SM.
+#ifndef B200SDF_STRIDED_MIN_CTAS
+#define B200SDF_STRIDED_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(128, B200SDF_STRIDED_MIN_CTAS) sdf_tiles_strided_kernel(
+    const float4 *__restrict__ segs, const b200sdf_curve *__restrict__ curves, const b200sdf_outline_job *__restrict__ ojobs,
+    const b200sdf_tile_job *__restrict__ tiles, const uint32_t tile_cap, BatchCounters *__restrict__ ctr,
+    uint32_t *__restrict__ status_out, uint8_t *__restrict__ out)
+{
+	__shared__ __align__(128) SharedStorage sm;
+	init_barriers(sm);
+	if (threadIdx.x < 32) {
+		const int lane = threadIdx.x;
+		// (read at L2, where the decode kernel's atomics left them)
+		uint32_t run = lane < kTileClasses ? min(__ldcg(&ctr->class_count[lane]), tile_cap) : 0u;
+#pragma unroll
+		for (int d = 1; d < kTileClasses; d <<= 1) {
+			const uint32_t up = __shfl_up_sync(0xffffffffu, run, d);
+			if (lane >= d)
+				run += up;
+		}
+		if (lane < kTileClasses)
+			sm.class_end[lane] = run;
+		if (lane == kTileClasses - 1)
+			sm.total = run;
+	}
+	__syncthreads();
+	const uint32_t total = sm.total;
+	for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+		const b200sdf_tile_job job = *claimed_tile(sm, tiles, tile_cap, t);
+		render_tile(sm, job, t, nullptr, nullptr, 0, segs, curves, ojobs, out);
+		__syncthreads(); // everybody is done with this job's shared storage
+	}
+	if (threadIdx.x == 0) {
+		__threadfence();
+		if (atomicAdd(&ctr->done_ctas, 1u) == gridDim.x - 1) {
+			// every other CTA has read the counts and finished: nobody reads the counters any more
 			if (status_out)
 				*status_out = ctr->overflow;
 #pragma unroll
