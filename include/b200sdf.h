@@ -136,7 +136,26 @@ typedef struct {
  * cmap, hmtx, loca and the composite tree (components that are only translated become parts; anything else is
  * recorded on the host and sent as kind CURVES / SEGMENTS in the same batch).
  */
-enum { B200SDF_KIND_GLYF = 2 };
+enum { B200SDF_KIND_GLYF = 2, B200SDF_KIND_PATH = 3 };
+
+/*
+ * kind PATH: a glyph recorded on the host whose outline has CUBIC curves (CFF fonts).  Its records live in the call's
+ * curve array like those of kind CURVES, with one more record form:
+ *   cubic head   {sx, sy = start; cx, cy = first control point; ex, ey = second control point; seg_off;
+ *                 depth = B200SDF_CURVE_CUBIC | n} — n = segments Ring::add_cubic_bezier (src/geometry/ring.rs:159-187)
+ *                 makes of this curve: the host runs the adaptive flatness test to count them (it needs the points for
+ *                 the bounding box anyway), the device repeats the subdivision literally, in f64, and writes them
+ *   cubic tail   {sx, sy = end point; depth = B200SDF_CURVE_TAIL}, directly after its head; holds no segments.
+ * The decode kernel flattens every record of such a glyph (lines, quadratics in closed form, cubics by subdivision)
+ * into origin-relative f32 segments in device memory; the SDF kernel reads them like uploaded segments, so nothing is
+ * flattened on the host and 64 bytes per cubic cross PCIe instead of 16 per segment.  In the request, curve_off /
+ * curve_cap name the glyph's slot in the submission's generated-segment area (curve_cap = seg_cnt).  A glyph whose
+ * subdivision does not come out at the host's counts is reported B200SDF_GLYPH_NEEDS_HOST.  Host buffers only:
+ * b200sdf_render_glyphs_device and b200sdf_decode_glyphs answer B200SDF_GLYPH_BAD_REQUEST.
+ */
+#define B200SDF_CURVE_CUBIC 0x80000000u
+#define B200SDF_CURVE_TAIL 0x40000000u
+#define B200SDF_CUBIC_STACK 24 /* deepest pending-halves stack of the device's subdivision (the host falls back beyond) */
 
 typedef struct {
 	uint32_t font;     /* handle from b200sdf_font_upload */

@@ -143,6 +143,8 @@ uint32_t vgb_batch_curve_slots(const vgb_batch *b);
 uint32_t vgb_batch_tile_cap(const vgb_batch *b);
 uint64_t vgb_batch_est_cost(const vgb_batch *b); /* the est_cost argument of b200sdf_submit_glyphs */
 uint32_t vgb_batch_handed_back(const vgb_batch *b);
+/* glyphs with cubic curves sent as kind PATH (flattened by the device) */
+uint32_t vgb_batch_path_glyphs(const vgb_batch *b);
 /* bitmap of glyph i (NULL when it has none); valid after the batch was rendered */
 const uint8_t *vgb_batch_glyph_bitmap(const vgb_batch *b, uint32_t i, uint64_t *len);
 

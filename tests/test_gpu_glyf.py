@@ -319,3 +319,40 @@ def test_several_batches_in_one_submission(renderer):
     assert checked > 800
     with pytest.raises(V.B200Error):  # 17 batches: over B200SDF_MAX_BATCHES
         ctx.render_glyph_batches([group[1]] * 17)
+
+
+@pytest.mark.parametrize("cid", [False, True])
+def test_cubic_outlines_are_flattened_on_the_device(renderer, cid, tmp_path):
+    """CFF glyphs (cubic curves, Ring::add_cubic_bezier ring.rs:159-187) travel as kind PATH: the host counts the leaves
+    of the adaptive subdivision, the decode kernel repeats it literally and writes the segments.  Frames, metrics and
+    every bitmap byte equal the host-flattened rendering of the same glyphs (same SDF kernel, uploaded segments)."""
+    data, cps, _ = synth_font.cff_test_font(n_glyphs=60, cid=cid)
+    path = tmp_path / "synth.otf"
+    path.write_bytes(data)
+    font = V.FontFileEntry(path=str(path))
+    got = {}
+    for mode in ("glyf", "host"):
+        renderer.set_flatten(mode)
+        batch = renderer.new_batch()
+        for cp in cps:
+            batch.add_glyph(font, cp)
+        if mode == "glyf":
+            reqs = batch.requests()
+            assert batch.path_glyphs > 40 and int((reqs["kind"] == N.KIND_PATH).sum()) == batch.path_glyphs
+            assert not (reqs["kind"] == N.KIND_SEGMENTS).any()  # nothing was flattened on the host
+        else:
+            assert batch.path_glyphs == 0
+        renderer.render_batch(batch)
+        got[mode] = [(batch.glyph_info(i), batch.bitmap_of(i).copy() if batch.glyph_info(i).has_bitmap else None)
+                     for i in range(len(batch))]
+    renderer.set_flatten("glyf")
+    assert len(got["glyf"]) == len(got["host"]) == len(cps)
+    px = 0
+    for (ga, ba), (gb, bb) in zip(got["glyf"], got["host"]):
+        assert (ga.id, ga.advance, ga.has_bitmap) == (gb.id, gb.advance, gb.has_bitmap)
+        if not ga.has_bitmap:
+            continue
+        assert (ga.x0, ga.y0, ga.bm_width, ga.bm_height) == (gb.x0, gb.y0, gb.bm_width, gb.bm_height)
+        assert np.array_equal(ba, bb)
+        px += ba.size
+    assert px > 20000

@@ -158,6 +158,8 @@ class GlyphFrame(C.Structure):
 
 
 KIND_GLYF = 2
+KIND_PATH = 3  # host-recorded outline with cubic curves, flattened by the decode kernel
+CURVE_CUBIC, CURVE_TAIL = 0x80000000, 0x40000000
 GLYPH_OK, GLYPH_EMPTY, GLYPH_NEEDS_HOST, GLYPH_BAD_REQUEST = 0, 1, 2, 3
 
 
@@ -246,6 +248,7 @@ HOST_SYMBOLS = {
     "vgb_batch_tile_cap": (C.c_uint32, [C.c_void_p]),
     "vgb_batch_est_cost": (C.c_uint64, [C.c_void_p]),
     "vgb_batch_handed_back": (C.c_uint32, [C.c_void_p]),
+    "vgb_batch_path_glyphs": (C.c_uint32, [C.c_void_p]),
     "vgb_batch_glyph_bitmap": (u8p, [C.c_void_p, C.c_uint32, u64p]),
     "vgb_batch_bitmaps": (u8p, [C.c_void_p, u64p]),
     "vgb_batch_pairs": (C.c_uint64, [C.c_void_p]),

@@ -353,6 +353,11 @@ class GlyphBatch:
     def handed_back(self) -> int:
         return N.host.vgb_batch_handed_back(self._h)
 
+    @property
+    def path_glyphs(self) -> int:
+        """glyphs with cubic curves sent as kind PATH (the device flattens them)"""
+        return N.host.vgb_batch_path_glyphs(self._h)
+
 
 class Writer:
     """reference src/writer/mod.rs:27-96 (directory sink and in-memory recorder)."""

@@ -848,6 +848,28 @@ int b200sdf_submit_planned(b200sdf_ctx *ctx, const b200sdf_curve *curves, uint32
 		return B200SDF_E_ARG;
 	if ((n_seg && !segs) || (n_curves && !curves) || (n_jobs && !jobs) || (out_bytes && !out) || (n_tiles && !tiles))
 		return fail_arg(ctx, "submit_planned: null buffer");
+	// The caller's tile list drives device writes: check every entry against the arrays it indexes (one pass, a few
+	// comparisons per tile job) instead of trusting it.
+	for (uint32_t i = 0; i < n_tiles; ++i) {
+		const b200sdf_tile_job &t = tiles[i];
+		const uint32_t items = (uint32_t)t.ntx * t.nty;
+		const uint32_t tiles_x = (t.width + B200SDF_TILE_W - 1) / B200SDF_TILE_W, tiles_y = (t.height + B200SDF_TILE_H - 1) / B200SDF_TILE_H;
+		bool ok = t.width >= 1 && t.height >= 1 && t.width <= B200SDF_MAX_DIM && t.height <= B200SDF_MAX_DIM && items >= 1 &&
+		          items <= B200SDF_MAX_ITEMS && (uint32_t)t.tx0 + t.ntx <= tiles_x && (uint32_t)t.ty0 + t.nty <= tiles_y &&
+		          t.out_off <= out_bytes && (uint64_t)t.width * t.height <= out_bytes - t.out_off;
+		if (ok && t.job == B200SDF_NO_JOB) {
+			ok = t.seg_off <= n_seg && t.seg_cnt <= n_seg - t.seg_off;
+		} else if (ok) {
+			ok = t.job < n_jobs;
+			if (ok) {
+				const b200sdf_outline_job &j = jobs[t.job];
+				ok = j.kind == B200SDF_KIND_CURVES && t.seg_off == j.src_off && j.src_off <= n_curves && j.src_cnt <= n_curves - j.src_off &&
+				     t.seg_cnt == j.seg_cnt && t.width == j.width && t.height == j.height && t.out_off == j.out_off;
+			}
+		}
+		if (!ok)
+			return fail_arg(ctx, ("submit_planned: tile job " + std::to_string(i) + " does not fit the arrays it refers to").c_str());
+	}
 	static const std::vector<Planned> none;
 	return submit_planned(ctx, none, curves, n_curves, segs, n_seg, jobs, n_jobs, out, out_bytes, ticket, tiles, n_tiles);
 }
@@ -1230,15 +1252,25 @@ int b200sdf_submit_glyph_batches(b200sdf_ctx *ctx, const b200sdf_glyph_batch *ba
 		return B200SDF_E_ARG;
 	if (n_batches == 0 || n_batches > (uint32_t)kMaxSubBatches || !batches)
 		return fail_arg(ctx, "submit_glyph_batches: between 1 and B200SDF_MAX_BATCHES batches per submission");
-	uint64_t n_reqs = 0, n_seg = 0, curve_slots = 0, tile_cap = 0;
+	uint64_t n_reqs = 0, n_seg = 0, curve_slots = 0, tile_cap = 0, gen_total = 0;
+	uint64_t gen_slots[kMaxSubBatches];
 	for (uint32_t b = 0; b < n_batches; ++b) {
 		const b200sdf_glyph_batch &B = batches[b];
 		if ((B.n_reqs && (!B.reqs || !B.frames)) || (B.n_parts && !B.parts) || (B.n_curves && !B.curves) || (B.n_seg && !B.segs) ||
 		    (B.out_bytes && !B.out))
 			return fail_arg(ctx, "submit_glyphs: null buffer");
 		n_reqs += B.n_reqs, n_seg += B.n_seg, curve_slots += B.curve_slots, tile_cap += std::max(1u, B.tile_cap);
+		// kind PATH (host-recorded outlines with cubics, only where there are host-recorded records at all): the segments
+		// the device makes of them go behind the uploaded ones; the requests say how much room that takes
+		uint64_t gen = 0;
+		if (B.n_curves)
+			for (uint32_t i = 0; i < B.n_reqs; ++i)
+				if (B.reqs[i].kind == B200SDF_KIND_PATH)
+					gen = std::max<uint64_t>(gen, (uint64_t)B.reqs[i].curve_off + B.reqs[i].curve_cap);
+		gen_slots[b] = gen;
+		gen_total += gen;
 	}
-	if (n_reqs > 0xffffffffull || n_seg > 0xffffffffull || curve_slots > 0xffffffffull || tile_cap > 0xffffffffull)
+	if (n_reqs > 0xffffffffull || n_seg + gen_total > 0xffffffffull || curve_slots > 0xffffffffull || tile_cap > 0xffffffffull)
 		return fail_arg(ctx, "submit_glyphs: submission too large");
 	const size_t si = acquire_slot(ctx);
 	Slot &s = ctx->slots[si];
@@ -1265,14 +1297,14 @@ int b200sdf_submit_glyph_batches(b200sdf_ctx *ctx, const b200sdf_glyph_batch *ba
 	// What has to exist on the device: [0] segments (always staged: the raw-segment path reads them through the TMA
 	// unit) [1] host curves [2] requests [3] parts [4] frames [5] bitmaps — each only for a single batch whose buffer
 	// is not pinned + mapped — [6] curve scratch [7] tile lists [8] outline jobs
-	size_t need[9] = {(size_t)n_seg * sizeof(b200sdf_segment), 0, 0, 0, 0, 0,
+	size_t need[9] = {(size_t)(n_seg + gen_total) * sizeof(b200sdf_segment), 0, 0, 0, 0, 0,
 	                  (size_t)std::max<uint64_t>(1, curve_slots) * sizeof(b200sdf_curve), (size_t)tile_cap * kTileScratchPerJob,
 	                  (size_t)n_reqs * sizeof(b200sdf_outline_job)};
 	DecodeParams P;
 	std::memset(&P, 0, sizeof(P));
 	bool staged_frames = false, staged_out = false;
 	{
-		uint32_t req_base = 0, seg_base = 0, curve_base = 0;
+		uint32_t req_base = 0, seg_base = 0, curve_base = 0, gen_base = (uint32_t)n_seg;
 		for (uint32_t b = 0; b < n_batches; ++b) {
 			const b200sdf_glyph_batch &B = batches[b];
 			SubBatch &S = P.sub[b];
@@ -1299,7 +1331,8 @@ int b200sdf_submit_glyph_batches(b200sdf_ctx *ctx, const b200sdf_glyph_batch *ba
 			S.n_reqs = B.n_reqs, S.req_base = req_base;
 			S.n_parts = B.n_parts, S.n_host_curves = B.n_curves, S.n_host_segs = B.n_seg;
 			S.seg_base = seg_base, S.curve_base = curve_base, S.curve_slots = B.curve_slots;
-			req_base += B.n_reqs, seg_base += B.n_seg, curve_base += B.curve_slots;
+			S.gen_base = gen_base, S.gen_slots = (uint32_t)gen_slots[b];
+			req_base += B.n_reqs, seg_base += B.n_seg, curve_base += B.curve_slots, gen_base += (uint32_t)gen_slots[b];
 		}
 	}
 	{
@@ -1377,6 +1410,7 @@ int b200sdf_submit_glyph_batches(b200sdf_ctx *ctx, const b200sdf_glyph_batch *ba
 		P.n_reqs = (uint32_t)n_reqs;
 		P.font_base = ctx->d_font_base;
 		P.font_len = ctx->d_font_len;
+		P.segs = reinterpret_cast<float4 *>(s.segs.p);
 		P.curves = reinterpret_cast<b200sdf_curve *>(s.gcurves.p);
 		P.ojobs = reinterpret_cast<b200sdf_outline_job *>(s.ojobs.p);
 		set_tile_scratch(P, s.tiles.p, (uint32_t)tile_cap);

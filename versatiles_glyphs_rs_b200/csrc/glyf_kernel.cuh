@@ -76,6 +76,7 @@ struct SubBatch {
 	uint32_t n_parts, n_host_curves, n_host_segs;
 	uint32_t seg_base;                // where the batch's segments start in the submission's segment array
 	uint32_t curve_base, curve_slots; // the batch's part of the curve scratch
+	uint32_t gen_base, gen_slots;     // the batch's part of the generated-segment area (kind PATH), in segments
 };
 
 struct DecodeParams {
@@ -85,6 +86,7 @@ struct DecodeParams {
 	const uint8_t *const *font_base; // device table: glyf bytes of every uploaded font
 	const uint64_t *font_len;
 	uint32_t n_fonts;
+	float4 *segs;                     // the submission's segment array: uploaded segments, then the generated ones
 	b200sdf_curve *curves;            // device scratch: every glyph's records at sub.curve_base + req.curve_off
 	b200sdf_outline_job *ojobs;       // device scratch: one per request (index = request number in the submission)
 	b200sdf_tile_job *tiles;          // kTileClasses lists of tile_cap entries each
@@ -559,6 +561,97 @@ __device__ __forceinline__ void plan_tiles_dev(const DecodeParams &P, uint32_t s
 	}
 }
 
+// ---- kind PATH: literal flattening of host-recorded outlines with cubic curves -------------------------------------
+// origin-relative f32 pixel coordinates of a font-unit point: p * scale, + dx (renderer.rs:122-131), - origin, narrow
+__device__ __forceinline__ float2 path_pixel(double x, double y, double scale, double dx, double ox, double oy)
+{
+	return make_float2((float)__dsub_rn(__dadd_rn(__dmul_rn(x, scale), dx), ox), (float)__dsub_rn(__dadd_rn(__dmul_rn(y, scale), 0.0), oy));
+}
+__device__ __forceinline__ double mid_rn(double a, double b) { return __dmul_rn(__dadd_rn(a, b), 0.5); } // (a + b) / 2.0, point.rs:29-31
+
+struct CubicNode {
+	double sx, sy, ax, ay, bx, by, ex, ey; // start, control 1, control 2, end
+};
+
+// Ring::add_cubic_bezier (src/geometry/ring.rs:159-187) as the reference runs it: explicit stack, right half pushed
+// first, a leaf adds its end point.  Writes segment j of the curve to dst[j] for j < cap; returns the number of leaves.
+__device__ __noinline__ uint32_t flatten_cubic_dev(const b200sdf_curve &h, const float ex, const float ey, float4 *dst, const uint32_t cap,
+                                                   const double scale, const double dx, const double ox, const double oy, bool &overflow)
+{
+	CubicNode stack[B200SDF_CUBIC_STACK];
+	int top = 0;
+	stack[top++] = CubicNode{(double)h.sx, (double)h.sy, (double)h.cx, (double)h.cy, (double)h.ex, (double)h.ey, (double)ex, (double)ey};
+	float2 prev = path_pixel((double)h.sx, (double)h.sy, scale, dx, ox, oy);
+	uint32_t n = 0;
+	while (top > 0) {
+		const CubicNode q = stack[--top];
+		const double ddx = __dsub_rn(__dadd_rn(q.bx, q.ax), __dadd_rn(q.sx, q.ex));
+		const double ddy = __dsub_rn(__dadd_rn(q.by, q.ay), __dadd_rn(q.sy, q.ey));
+		const bool flat = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) <= 0.01; // tolerance_sq, ring_builder.rs:62
+		if (flat || top + 2 > B200SDF_CUBIC_STACK) {
+			overflow |= !flat; // the host never sends a curve that needs a deeper stack: its counts would not match
+			const float2 p = path_pixel(q.ex, q.ey, scale, dx, ox, oy);
+			if (n < cap)
+				dst[n] = make_float4(prev.x, prev.y, p.x, p.y);
+			prev = p;
+			++n;
+			continue;
+		}
+		const double p01x = mid_rn(q.sx, q.ax), p01y = mid_rn(q.sy, q.ay);
+		const double p12x = mid_rn(q.ax, q.bx), p12y = mid_rn(q.ay, q.by);
+		const double p23x = mid_rn(q.bx, q.ex), p23y = mid_rn(q.by, q.ey);
+		const double p012x = mid_rn(p01x, p12x), p012y = mid_rn(p01y, p12y);
+		const double p123x = mid_rn(p12x, p23x), p123y = mid_rn(p12y, p23y);
+		const double mx = mid_rn(p012x, p123x), my = mid_rn(p012y, p123y);
+		stack[top++] = CubicNode{mx, my, p123x, p123y, p23x, p23y, q.ex, q.ey};
+		stack[top++] = CubicNode{q.sx, q.sy, p01x, p01y, p012x, p012y, mx, my};
+	}
+	return n;
+}
+
+// One lane per record: every record of the glyph becomes its segments in dst[seg_off ...].  Returns the number of
+// segments this lane wrote (or would have written); `bad` = malformed records.
+__device__ __forceinline__ uint32_t flatten_path_dev(const b200sdf_curve *recs, const uint32_t n_recs, float4 *dst, const uint32_t cap,
+                                                     const double scale, const double dx, const double ox, const double oy, const int lane,
+                                                     bool &bad)
+{
+	uint32_t made = 0;
+	for (uint32_t i = (uint32_t)lane; i < n_recs; i += 32) {
+		const b200sdf_curve r = recs[i];
+		if ((r.depth & 0xC0000000u) == B200SDF_CURVE_TAIL)
+			continue;
+		if (r.depth & B200SDF_CURVE_CUBIC) {
+			const uint32_t want = r.depth & 0x3fffffffu;
+			if (i + 1 >= n_recs || (recs[i + 1].depth & 0xC0000000u) != B200SDF_CURVE_TAIL || r.seg_off > cap || want > cap - r.seg_off) {
+				bad = true;
+				continue;
+			}
+			bool overflow = false;
+			const uint32_t n = flatten_cubic_dev(r, recs[i + 1].sx, recs[i + 1].sy, dst + r.seg_off, want, scale, dx, ox, oy, overflow);
+			bad |= overflow || n != want;
+			made += n;
+		} else {
+			const uint32_t k = r.depth;
+			if (k > kGlyfMaxDepth || r.seg_off > cap || (1u << k) > cap - r.seg_off) {
+				bad = true;
+				continue;
+			}
+			const double sx = r.sx, sy = r.sy, cx = r.cx, cy = r.cy, ex = r.ex, ey = r.ey;
+			const double step = __longlong_as_double((long long)(1023 - (int)k) << 52); // 2^-k
+			float2 prev = path_pixel(sx, sy, scale, dx, ox, oy);
+			for (uint32_t j = 1; j <= (1u << k); ++j) {
+				const double t = (double)j * step;
+				// (the same closed form as the SDF kernel's curve_point: exact for the dyadic inputs the recorder admits)
+				const float2 p = path_pixel(curve_coord_dev(sx, cx, ex, t), curve_coord_dev(sy, cy, ey, t), scale, dx, ox, oy);
+				dst[r.seg_off + j - 1] = make_float4(prev.x, prev.y, p.x, p.y);
+				prev = p;
+			}
+			made += 1u << k;
+		}
+	}
+	return made;
+}
+
 __device__ __forceinline__ void decode_request(const DecodeParams &P, const uint32_t gi, GlyfWarpScratch &wscratch, const int lane)
 {
 	int k = 0;
@@ -636,6 +729,30 @@ __device__ __forceinline__ void decode_request(const DecodeParams &P, const uint
 			fr.width = rq.width, fr.height = rq.height, fr.seg_cnt = rq.seg_cnt, fr.status = B200SDF_GLYPH_OK;
 			oj.src_cnt = rq.src_cnt;
 			oj.seg_cnt = rq.seg_cnt;
+		}
+	} else if (rq.kind == B200SDF_KIND_PATH) {
+		const bool ok = (uint64_t)rq.src_off + rq.src_cnt <= B.n_host_curves && rq.seg_cnt >= 1 && rq.seg_cnt == rq.curve_cap &&
+		                (uint64_t)rq.curve_off + rq.curve_cap <= B.gen_slots && rq.width >= 1 && rq.height >= 1 &&
+		                rq.width <= B200SDF_MAX_DIM && rq.height <= B200SDF_MAX_DIM &&
+		                rq.out_off + (uint64_t)rq.width * rq.height <= B.out_bytes;
+		if (!ok) {
+			fr.status = B200SDF_GLYPH_BAD_REQUEST;
+		} else {
+			bool bad = false;
+			float4 *dst = P.segs + B.gen_base + rq.curve_off;
+			uint32_t made = flatten_path_dev(B.host_curves + rq.src_off, rq.src_cnt, dst, rq.seg_cnt, rq.scale, rq.dx, (double)rq.x0,
+			                                 (double)rq.y0, lane, bad);
+#pragma unroll
+			for (int d = 16; d >= 1; d >>= 1)
+				made += __shfl_xor_sync(0xffffffffu, made, d);
+			bad = __any_sync(0xffffffffu, bad) || made != rq.seg_cnt;
+			if (bad) {
+				fr.status = B200SDF_GLYPH_NEEDS_HOST; // the host's counts and the device's subdivision disagree
+			} else {
+				fr.width = rq.width, fr.height = rq.height, fr.seg_cnt = rq.seg_cnt, fr.status = B200SDF_GLYPH_OK;
+				oj.kind = B200SDF_KIND_SEGMENTS;
+				oj.src_off = B.gen_base + rq.curve_off, oj.src_cnt = rq.seg_cnt, oj.seg_cnt = rq.seg_cnt;
+			}
 		}
 	} else if (rq.kind == B200SDF_KIND_SEGMENTS) {
 		const bool ok = (uint64_t)rq.src_off + rq.src_cnt <= B.n_host_segs && rq.seg_cnt == rq.src_cnt && rq.width >= 1 &&

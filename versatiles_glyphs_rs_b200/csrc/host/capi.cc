@@ -370,6 +370,7 @@ uint32_t vgb_batch_curve_slots(const vgb_batch *b) { return b->b->curve_slots();
 uint32_t vgb_batch_tile_cap(const vgb_batch *b) { return b->b->tile_cap(); }
 uint64_t vgb_batch_est_cost(const vgb_batch *b) { return b->b->est_cost(); }
 uint32_t vgb_batch_handed_back(const vgb_batch *b) { return b->b->handed_back(); }
+uint32_t vgb_batch_path_glyphs(const vgb_batch *b) { return b->b->path_glyphs(); }
 const uint8_t *vgb_batch_glyph_bitmap(const vgb_batch *b, uint32_t i, uint64_t *len)
 {
 	*len = 0;

@@ -112,6 +112,7 @@ void OutlineRecorder::begin()
 	n_seg_ = 0;
 	rings_ = 0;
 	exact_ = true;
+	has_cubic_ = false;
 }
 
 void OutlineRecorder::add_line(P a, P b)
@@ -215,10 +216,65 @@ void OutlineRecorder::quad_to(float x1, float y1, float x, float y)
 	ring_last_ = P{x, y};
 }
 
-void OutlineRecorder::curve_to(float, float, float, float, float, float)
+void OutlineRecorder::curve_to(float x1, float y1, float x2, float y2, float x, float y)
 {
-	// Cubic flattening (ring.rs:159-187) is adaptive, not uniform: flatten literally on the host.
-	exact_ = false;
+	// Cubic flattening (ring.rs:159-187) is adaptive, not uniform.  The device repeats the subdivision literally (kind
+	// PATH); here the same walk only COUNTS the leaves and collects their end points into the bounding box — nothing is
+	// stored, nothing is scaled or narrowed.  The arithmetic (f64, unfused) is the device's, operation for operation.
+	if (!allow_cubics_) {
+		exact_ = false;
+		return;
+	}
+	if (ring_points_ == 0)
+		return; // ring_builder.rs:99
+	if (!dyadic_ok(x1) || !dyadic_ok(y1) || !dyadic_ok(x2) || !dyadic_ok(y2) || !dyadic_ok(x) || !dyadic_ok(y)) {
+		exact_ = false;
+		return;
+	}
+	struct Node {
+		double sx, sy, ax, ay, bx, by, ex, ey;
+	};
+	Node stack[B200SDF_CUBIC_STACK];
+	int top = 0;
+	stack[top++] = Node{(double)ring_last_.x, (double)ring_last_.y, (double)x1, (double)y1, (double)x2, (double)y2, (double)x, (double)y};
+	uint32_t leaves = 0;
+	while (top > 0) {
+		const Node q = stack[--top];
+		const double dx = (q.bx + q.ax) - (q.sx + q.ex);
+		const double dy = (q.by + q.ay) - (q.sy + q.ey);
+		if (dx * dx + dy * dy <= PRECISION) {
+			ring_bbox_.include_point(Point(q.ex, q.ey));
+			if (++leaves > 0x00ffffffu) {
+				exact_ = false;
+				return;
+			}
+			continue;
+		}
+		if (top + 2 > B200SDF_CUBIC_STACK) { // deeper than the device's stack: let the host flatten this glyph
+			exact_ = false;
+			return;
+		}
+		const double p01x = (q.sx + q.ax) / 2.0, p01y = (q.sy + q.ay) / 2.0;
+		const double p12x = (q.ax + q.bx) / 2.0, p12y = (q.ay + q.by) / 2.0;
+		const double p23x = (q.bx + q.ex) / 2.0, p23y = (q.by + q.ey) / 2.0;
+		const double p012x = (p01x + p12x) / 2.0, p012y = (p01y + p12y) / 2.0;
+		const double p123x = (p12x + p23x) / 2.0, p123y = (p12y + p23y) / 2.0;
+		const double mx = (p012x + p123x) / 2.0, my = (p012y + p123y) / 2.0;
+		stack[top++] = Node{mx, my, p123x, p123y, p23x, p23y, q.ex, q.ey};
+		stack[top++] = Node{q.sx, q.sy, p01x, p01y, p012x, p012y, mx, my};
+	}
+	b200sdf_curve h, t;
+	h.sx = ring_last_.x, h.sy = ring_last_.y, h.cx = x1, h.cy = y1, h.ex = x2, h.ey = y2;
+	h.seg_off = 0;
+	h.depth = B200SDF_CURVE_CUBIC | leaves;
+	std::memset(&t, 0, sizeof(t));
+	t.sx = x, t.sy = y;
+	t.depth = B200SDF_CURVE_TAIL;
+	recs_.push_back(h);
+	recs_.push_back(t);
+	has_cubic_ = true;
+	ring_points_ += leaves;
+	ring_last_ = P{x, y};
 }
 
 void OutlineRecorder::close() { save_ring(); }
@@ -238,7 +294,8 @@ void OutlineRecorder::save_ring()
 		uint32_t off = n_seg_;
 		for (size_t i = ring_first_rec_; i < recs_.size(); ++i) {
 			recs_[i].seg_off = off;
-			off += 1u << recs_[i].depth;
+			const uint32_t d = recs_[i].depth;
+			off += (d & B200SDF_CURVE_TAIL) ? 0u : (d & B200SDF_CURVE_CUBIC) ? (d & 0x00ffffffu) : (1u << d);
 		}
 		n_seg_ = off;
 		bbox_.include_point(ring_bbox_.min);
@@ -313,6 +370,7 @@ void GlyphBatch::clear()
 	n_tiles_ = 0;
 	prepared_ = false;
 	n_parts_ = curve_slots_ = tile_cap_ = n_handed_back_ = 0;
+	gen_seg_slots_ = n_path_ = 0;
 	pixels_ = est_cost_ = cost_context_ = 0;
 	job_glyph_.clear();
 	n_heavy_ = 0;
@@ -378,6 +436,11 @@ bool GlyphBatch::push_job(const b200sdf_outline_job &j)
 			r.curve_off = curve_slots_;
 			r.curve_cap = j.src_cnt;
 			curve_slots_ += j.src_cnt;
+		} else if (j.kind == B200SDF_KIND_PATH) { // its slot in the generated-segment area
+			r.curve_off = gen_seg_slots_;
+			r.curve_cap = j.seg_cnt;
+			gen_seg_slots_ += j.seg_cnt;
+			n_path_++;
 		}
 		tile_cap_ += b200sdf_glyph_tile_bound(j.width, j.height);
 		est_cost_ += (uint64_t)((j.width + 3) / 4) * ((j.height + 3) / 4) * ((uint64_t)j.seg_cnt + 8);
@@ -511,6 +574,11 @@ bool GlyphBatch::add_glyph(const Face &face, uint32_t index)
 		// Host: recorded below like in Device mode
 	}
 	if (mode_ == Flatten::Device || mode_ == Flatten::Glyf) {
+		static const bool device_cubics = [] { // VGB_DEVICE_CUBICS=0: cubic outlines are flattened on the host (experiments)
+			const char *e = std::getenv("VGB_DEVICE_CUBICS");
+			return !(e && e[0] == '0');
+		}();
+		recorder_.allow_cubics(mode_ == Flatten::Glyf && device_cubics); // kind PATH exists at the glyph-level seam only
 		recorder_.begin();
 		face.outline_glyph(*glyph_id, recorder_); // :109-110
 		recorder_.finish();                       // into_rings, :111
@@ -542,7 +610,7 @@ bool GlyphBatch::add_glyph(const Face &face, uint32_t index)
 			std::memcpy(curves_.data() + (size_t)n_curves_ * sizeof(b200sdf_curve), recs.data(), recs.size() * sizeof(b200sdf_curve));
 			b200sdf_outline_job job;
 			std::memset(&job, 0, sizeof(job));
-			job.kind = B200SDF_KIND_CURVES;
+			job.kind = recorder_.has_cubic() ? (uint32_t)B200SDF_KIND_PATH : (uint32_t)B200SDF_KIND_CURVES;
 			job.src_off = n_curves_;
 			job.src_cnt = (uint32_t)recs.size();
 			job.seg_cnt = recorder_.segment_count();
@@ -669,8 +737,16 @@ bool GlyphBatch::finalize(const Renderer &renderer, std::string *err)
 	b200sdf_outline_job *jv = reinterpret_cast<b200sdf_outline_job *>(jobs_.data());
 	const b200sdf_glyph_frame *fv = frames();
 	for (BatchGlyph &g : glyphs_) {
-		if (!g.pending)
+		if (!g.pending) {
+			// recorded on the host (kinds CURVES / SEGMENTS / PATH): the frame is known, the device must have taken it
+			if (g.has_bitmap && g.extra_off < 0 && fv[g.job].status != B200SDF_GLYPH_OK) {
+				if (err)
+					*err = "the device rejected a host-recorded glyph (U+" + std::to_string(g.id) + ", status " +
+					       std::to_string(fv[g.job].status) + ")";
+				return false;
+			}
 			continue;
+		}
 		g.pending = false;
 		const b200sdf_glyph_frame &f = fv[g.job];
 		b200sdf_outline_job &j = jv[g.job];

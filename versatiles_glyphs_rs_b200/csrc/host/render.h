@@ -107,6 +107,10 @@ class OutlineRecorder : public OutlineBuilder {
 	void close() override;
 	void finish();
 
+	// Cubic curves (CFF outlines): recorded as head + tail records for the device's literal subdivision (kind PATH,
+	// include/b200sdf.h) when allowed; otherwise a cubic makes the glyph inexact (flattened on the host).
+	void allow_cubics(bool on) { allow_cubics_ = on; }
+	bool has_cubic() const { return has_cubic_; }
 	bool exact() const { return exact_; }
 	bool is_empty() const { return rings_ == 0; } // Rings::is_empty
 	const std::vector<b200sdf_curve> &records() const { return recs_; }
@@ -130,6 +134,7 @@ class OutlineRecorder : public OutlineBuilder {
 	uint32_t n_seg_ = 0;
 	size_t rings_ = 0;
 	bool exact_ = true;
+	bool allow_cubics_ = false, has_cubic_ = false;
 };
 
 // Growable host buffer, pinned when a CUDA renderer owns it.
@@ -213,6 +218,7 @@ class GlyphBatch {
 	const b200sdf_glyph_frame *frames() const { return reinterpret_cast<const b200sdf_glyph_frame *>(frames_.data()); }
 	uint32_t part_count() const { return n_parts_; }
 	uint32_t curve_slots() const { return curve_slots_; }
+	uint32_t path_glyphs() const { return n_path_; } // glyphs with cubic curves flattened by the device (kind PATH)
 	uint32_t tile_cap() const { return tile_cap_; }
 	// estimated tile x segment units of the work the device renders together with this batch (b200sdf_submit_glyphs
 	// est_cost): the batch itself, or — when a pipeline keeps many batches of one job in flight — that job
@@ -264,6 +270,7 @@ class GlyphBatch {
 	std::vector<Face::GlyfPart> parts_tmp_;
 	std::vector<uint8_t> extra_;
 	uint32_t n_parts_ = 0, curve_slots_ = 0, tile_cap_ = 0, n_handed_back_ = 0;
+	uint32_t gen_seg_slots_ = 0, n_path_ = 0; // kind PATH: room for the segments the device generates / such glyphs
 	uint64_t pixels_ = 0, est_cost_ = 0, cost_context_ = 0;
 	// Glyf mode: requests of glyphs with many outline points are kept at the front of the request array — the decode
 	// kernel takes requests in order, one warp each, and a glyph of several hundred points is that kernel's critical path

@@ -16,15 +16,22 @@
 // (warp slices), and lanes left over inside a group split a warp's segments further (lane
 // slices); slices are merged at the end with shared-memory atomicMin on the float bit patterns.
 //
-// Each WARP stages its own contiguous range of segments, 64 at a time, into a private shared
-// memory buffer — no CTA-wide barrier in the main loop:
-//   source A (raw segments): the TMA unit streams the warp's range HBM -> shared memory
-//            (cp.async.bulk + per-warp mbarrier, double buffered);
-//   source B (curve records): the glyph's curve list is bulk-copied once per CTA and each lane
-//            evaluates the end points of its segments in f64.
-// A staged segment becomes a record (negated origin and direction, direction / |direction|^2) and
-// scatters its row crossings; then the warp evaluates its pixels against the 64 records with
-// packed FP32 (FFMA2 / FADD2 / FMUL2: two horizontally adjacent pixels per instruction).
+// Two staging structures, by the source of the glyph's segments:
+//   source B (curve records — every glyph decoded or recorded as curves, i.e. the default path, B200SDF_SHARED_STAGE):
+//            the CTA works in ROUNDS of 4 x 64 segments.  The glyph's curve list is bulk-copied into shared memory once
+//            per job (TMA unit, one mbarrier); in a round warp w evaluates the end points of the w-th 64 segments in
+//            f64 — every segment is staged exactly once per CTA — and writes its own list (vertices, compacted long
+//            segments), scatters row crossings and rasterises the bands of its short segments; then a CTA-wide barrier,
+//            then EVERY warp evaluates its pixels against its share of all four lists, then a second barrier before the
+//            lists are overwritten.  Two __syncthreads per round: 20 % of the warp samples wait there (profiles/), the
+//            price of staging each segment once instead of once per item group.
+//   source A (raw segments uploaded by the caller): each warp streams its own contiguous range of segments through a
+//            private double buffer (cp.async.bulk + per-warp mbarrier) and consumes only its own list — no CTA-wide
+//            barrier in that loop.
+// A staged segment contributes its start vertex to the vertex list, its row crossings to the winding deltas, a band of
+// pixels (short segments: interior nearer than both ends) or a record of the clamped-projection loop (long segments);
+// the warp then evaluates its pixels against the vertices with packed FP32 (FADD2 / FMUL2 / FFMA2: two horizontally
+// adjacent pixels per instruction, FMNMX3 for two vertices per minimum).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -814,12 +821,30 @@ __device__ B200SDF_TILE_INLINE void render_tile(SharedStorage &sm, const b200sdf
 	const bool full_width = (R.rx0 == 0 && R.rw == W);
 	const size_t gbase = (size_t)job.out_off + (size_t)(H - R.ry0 - R.rh) * (size_t)W; // first byte (full-width case)
 	const uint32_t mis = full_width ? (uint32_t)((uintptr_t)(out + gbase) & 15u) : 0u;
+	// winding numbers = running sum of the deltas along each row, in place: one warp per row, 32 columns per shuffle scan
+	// (linear in the width; a loop over the columns left of every pixel was quadratic per row)
+	for (int y = warp; y < R.rh; y += kWarps) {
+		int *drow = &sm.delta[y * R.rw];
+		int carry = 0;
+		for (int x0 = 0; x0 < R.rw; x0 += 32) {
+			const int x = x0 + lane;
+			int v = x < R.rw ? drow[x] : 0;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int up = __shfl_up_sync(0xffffffffu, v, d);
+				if (lane >= d)
+					v += up;
+			}
+			v += carry;
+			if (x < R.rw)
+				drow[x] = v;
+			carry = __shfl_sync(0xffffffffu, v, 31);
+		}
+	}
+	__syncthreads();
 	for (int p = tid; p < rpix; p += kThreads) {
 		const int y = p / R.rw, x = p - y * R.rw;
-		int wn = 0;
-		const int *drow = &sm.delta[y * R.rw];
-		for (int k = 0; k <= x; ++k)
-			wn += drow[k];
+		const int wn = sm.delta[p];
 		const float d = sqrtf(__uint_as_float(sm.d2[p]));
 		// value = 255 - (+-d * 32 + 64), clamped, rounded half away from zero
 		float v = wn != 0 ? fmaf(d, 32.0f, 191.0f) : fmaf(d, -32.0f, 191.0f);
