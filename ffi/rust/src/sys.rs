@@ -11,6 +11,11 @@ pub const B200SDF_ABI_VERSION: c_int = 2;
 pub const B200SDF_KIND_CURVES: u32 = 0;
 pub const B200SDF_KIND_SEGMENTS: u32 = 1;
 pub const B200SDF_KIND_GLYF: u32 = 2;
+/// host-recorded outline with cubic curves: head + tail records, flattened by the decode kernel
+pub const B200SDF_KIND_PATH: u32 = 3;
+pub const B200SDF_CURVE_CUBIC: u32 = 0x8000_0000;
+pub const B200SDF_CURVE_TAIL: u32 = 0x4000_0000;
+pub const B200SDF_CUBIC_STACK: usize = 24;
 pub const B200SDF_GLYPH_OK: u32 = 0;
 pub const B200SDF_GLYPH_EMPTY: u32 = 1;
 pub const B200SDF_GLYPH_NEEDS_HOST: u32 = 2;
@@ -159,4 +164,5 @@ extern "C" {
     pub fn b200sdf_submit_glyph_batches(ctx: *mut b200sdf_ctx, batches: *const b200sdf_glyph_batch, n_batches: u32, est_cost: u64,
                                         ticket: *mut u64) -> c_int;
     pub fn b200sdf_reserve(ctx: *mut b200sdf_ctx) -> c_int;
+    pub fn b200sdf_reserve_glyphs(ctx: *mut b200sdf_ctx, n_reqs: u32, n_seg: u32, curve_slots: u32, tile_cap: u32) -> c_int;
 }

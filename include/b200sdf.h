@@ -310,6 +310,10 @@ typedef struct {
 	uint8_t *out;
 	uint64_t out_bytes;
 } b200sdf_glyph_batch;
+/* Pre-size every slot for glyph-level submissions of up to these totals (requests, uploaded + generated segments, curve
+ * slots, tile jobs), then b200sdf_reserve.  A pipeline that merges queued batches makes submissions whose size depends
+ * on timing; it names the largest one it can make, so that none of them ever grows a device buffer in mid-call. */
+int b200sdf_reserve_glyphs(b200sdf_ctx *ctx, uint32_t n_reqs, uint32_t n_seg, uint32_t curve_slots, uint32_t tile_cap);
 int b200sdf_submit_glyph_batches(b200sdf_ctx *ctx, const b200sdf_glyph_batch *batches, uint32_t n_batches, uint64_t est_cost,
                                  uint64_t *ticket);
 /* The same over device pointers on `stream` (asynchronous, two kernel launches, scratch owned by the context);

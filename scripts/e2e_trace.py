@@ -25,5 +25,6 @@ for i in range(30):
 print("steps ms:", " ".join(f"{x:.3f}" for x in ts[5:]), file=sys.stderr)
 print(f"median {sorted(ts[5:])[len(ts[5:]) // 2]:.3f} ms  workers {st.workers} submits {st.submits}", file=sys.stderr)
 os.environ["VGB_TRACE"] = "1"
-for _ in range(2):
+for k in range(2):
+    print(f"--- traced call {k}", file=sys.stderr, flush=True)
     m.render_glyphs(V.Writer.new_memory(), r, threads=threads)

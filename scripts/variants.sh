@@ -5,13 +5,11 @@ set -u
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 declare -A V=(
   [base]=""
-  [vpack0]="-DB200SDF_VPACK=0"
-  [even0]="-DB200SDF_EVEN_ROUNDS=0"
-  [old]="-DB200SDF_VPACK=0 -DB200SDF_EVEN_ROUNDS=0"
-  [ctas7]="-DB200SDF_PERSISTENT_MIN_CTAS=7"
-  [ctas5]="-DB200SDF_PERSISTENT_MIN_CTAS=5"
-  [mini32]="-DB200SDF_MINI=32"
-  [mini128]="-DB200SDF_MINI=128"
+  [mask0]="-DB200SDF_BAND_MASK=0"
+  [rowscan0]="-DB200SDF_ROW_SCAN=0"
+  [both0]="-DB200SDF_BAND_MASK=0 -DB200SDF_ROW_SCAN=0"
+  [ctas7]="-DB200SDF_STRIDED_MIN_CTAS=7"
+  [ctas6]="-DB200SDF_STRIDED_MIN_CTAS=6"
 )
 if [ "${1:-}" = "build" ]; then
   for n in "${!V[@]}"; do

@@ -728,3 +728,40 @@ def test_c4_full_font_properties(renderer):
     os.unlink(path)
     assert px > 100000 and same / px >= MIN_IDENTICAL
     print(f"C4 full: {len(runs[0])} blocks, oracle sample {px} px, {100 * same / px:.4f}% identical")
+
+
+def test_submit_planned_rejects_tile_lists_that_do_not_fit(ctx):
+    """b200sdf_submit_planned takes the caller's tile list: every entry is checked against the arrays it indexes before
+    anything is enqueued (a wrong list would otherwise be an out-of-bounds device write)."""
+    import ctypes as C
+
+    from versatiles_glyphs_rs_b200 import _native as N
+    from versatiles_glyphs_rs_b200.api import OUTLINE_JOB_DT, TILE_JOB_DT
+
+    segs = np.array([[2, 2, 9, 2], [9, 2, 9, 9], [9, 9, 2, 9], [2, 9, 2, 2]], np.float32)
+    jobs = np.zeros(1, OUTLINE_JOB_DT)
+    jobs[0]["kind"], jobs[0]["src_off"], jobs[0]["src_cnt"], jobs[0]["seg_cnt"] = N.KIND_SEGMENTS, 0, 4, 4
+    jobs[0]["width"], jobs[0]["height"], jobs[0]["out_off"] = 12, 12, 0
+    good = np.zeros(1, TILE_JOB_DT)
+    good[0]["seg_off"], good[0]["seg_cnt"], good[0]["out_off"] = 0, 4, 0
+    good[0]["width"], good[0]["height"], good[0]["tx0"], good[0]["ty0"], good[0]["ntx"], good[0]["nty"] = 12, 12, 0, 0, 3, 3
+    good[0]["job"] = 0xFFFFFFFF
+    out = np.zeros(144, np.uint8)
+
+    def submit(tiles):
+        t = C.c_uint64()
+        rc = N.sdf.b200sdf_submit_planned(ctx._h, None, 0, segs.ctypes.data, len(segs), jobs.ctypes.data, 1, tiles.ctypes.data,
+                                          len(tiles), out.ctypes.data, out.size, C.byref(t))
+        if rc == 0:
+            assert N.sdf.b200sdf_wait(ctx._h, t.value) == 0
+        return rc
+
+    assert submit(good) == 0
+    want = O.renderer_precise(0, 0, 12, 12, [[(2, 2), (9, 2), (9, 9), (2, 9), (2, 2)]])
+    assert np.abs(out.astype(int) - want.astype(int)).max() <= 1
+    for field, value in [("seg_cnt", 5), ("seg_off", 1), ("out_off", 1), ("width", 13), ("ntx", 4), ("ty0", 1), ("nty", 0),
+                         ("ntx", 65), ("job", 0), ("job", 7), ("width", 0)]:
+        bad = good.copy()
+        bad[0][field] = value
+        assert submit(bad) != 0, field
+        assert b"tile job 0" in N.sdf.b200sdf_last_error(ctx._h)

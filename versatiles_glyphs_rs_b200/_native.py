@@ -172,6 +172,7 @@ SDF_SYMBOLS = {
     "b200sdf_last_error": (C.c_char_p, [C.c_void_p]),
     "b200sdf_device": (C.c_int, [C.c_void_p]),
     "b200sdf_reserve": (C.c_int, [C.c_void_p]),
+    "b200sdf_reserve_glyphs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "b200sdf_alloc_pinned": (C.c_void_p, [C.c_size_t]),
     "b200sdf_free_pinned": (None, [C.c_void_p]),
     "b200sdf_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, u64p]),

@@ -1202,6 +1202,30 @@ int b200sdf_reserve(b200sdf_ctx *ctx)
 	return 0;
 }
 
+int b200sdf_reserve_glyphs(b200sdf_ctx *ctx, uint32_t n_reqs, uint32_t n_seg, uint32_t curve_slots, uint32_t tile_cap)
+{
+	using namespace b200sdf;
+	if (!ctx)
+		return B200SDF_E_ARG;
+	// the same sizes, rounded the same way, as b200sdf_submit_glyph_batches asks for (buffers in pinned memory are read
+	// in place: only the device scratch counts)
+	const size_t need[9] = {(size_t)n_seg * sizeof(b200sdf_segment), 0, 0, 0, 0, 0,
+	                        (size_t)std::max(1u, curve_slots) * sizeof(b200sdf_curve), (size_t)std::max(1u, tile_cap) * kTileScratchPerJob,
+	                        (size_t)n_reqs * sizeof(b200sdf_outline_job)};
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		for (int k = 0; k < 9; ++k) {
+			if (need[k] == 0)
+				continue;
+			size_t r = (size_t)64 << 10;
+			while (r < need[k])
+				r <<= 1;
+			ctx->ghwm[k] = std::max(ctx->ghwm[k], r);
+		}
+	}
+	return b200sdf_reserve(ctx);
+}
+
 int b200sdf_font_upload(b200sdf_ctx *ctx, const uint8_t *glyf, uint64_t len, uint32_t *handle)
 {
 	if (!ctx || !handle || (len && !glyf))

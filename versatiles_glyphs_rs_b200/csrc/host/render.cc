@@ -966,8 +966,25 @@ void Renderer::top_up_pool() const
 		want = std::min(kPoolTopUp, want);
 		mine.swap(pool_); // size the pooled batches outside the lock
 	}
-	if (ctx_)
-		b200sdf_reserve(ctx_); // every slot's device buffers at the marks too: no device allocation in the middle of a later call
+	if (ctx_) {
+		// every slot's device buffers at the marks too: no device allocation in the middle of a later call.  The pipeline
+		// merges whatever batches are queued into one submission (at most kMaxGroup of them, and none once it holds 4096
+		// glyphs): how large those get depends on timing, so the slots are sized for the largest one possible — as many
+		// glyphs as a submission can hold, each as heavy as the heaviest batch's average glyph.
+		GlyfMarks m;
+		{
+			std::lock_guard<std::mutex> g(pool_mu_);
+			m = glyf_marks_;
+		}
+		if (m.reqs) {
+			auto u32 = [](double v) { return (uint32_t)std::min(v + 1.0, 4294967295.0); };
+			// (a submission stops growing at 4096 glyphs: it holds less than 4096 + one batch)
+			const double reqs = (double)std::min<uint64_t>((uint64_t)kMaxGroup * m.reqs, 4096 + m.reqs);
+			b200sdf_reserve_glyphs(ctx_, u32(reqs), u32(m.segs * reqs), u32(m.curve_slots * reqs), u32(m.tile_cap * reqs));
+		} else {
+			b200sdf_reserve(ctx_);
+		}
+	}
 	for (auto &b : mine)
 		if (b->mode() == flatten_)
 			b->reserve_capacity(caps);
@@ -1044,6 +1061,7 @@ bool Renderer::submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *er
 				*err = "out of host memory for the frame buffer";
 			return false;
 		}
+		note_glyf_batch(batch);
 		const int grc = b200sdf_submit_glyphs(ctx_, batch.reqs(), batch.job_count(), batch.parts(), batch.part_count(), batch.curves(),
 		                                      batch.curve_count(), batch.segments(), batch.segment_count(), batch.curve_slots(),
 		                                      batch.tile_cap(), batch.est_cost(), batch.frames(), batch.bitmaps(), batch.bitmap_bytes(),
@@ -1068,6 +1086,16 @@ bool Renderer::submit_batch(GlyphBatch &batch, uint64_t *ticket, std::string *er
 		return false;
 	}
 	return true;
+}
+
+void Renderer::note_glyf_batch(const GlyphBatch &b) const
+{
+	std::lock_guard<std::mutex> g(pool_mu_);
+	const double n = (double)std::max<uint32_t>(1, b.job_count());
+	glyf_marks_.reqs = std::max<uint64_t>(glyf_marks_.reqs, b.job_count());
+	glyf_marks_.segs = std::max(glyf_marks_.segs, ((double)b.segment_count() + (double)b.generated_segment_slots()) / n);
+	glyf_marks_.curve_slots = std::max(glyf_marks_.curve_slots, (double)b.curve_slots() / n);
+	glyf_marks_.tile_cap = std::max(glyf_marks_.tile_cap, (double)b.tile_cap() / n);
 }
 
 bool Renderer::submit_batches(GlyphBatch *const *batches, size_t n, uint64_t *ticket, std::string *err) const
@@ -1095,6 +1123,7 @@ bool Renderer::submit_batches(GlyphBatch *const *batches, size_t n, uint64_t *ti
 		d.curve_slots = b.curve_slots(), d.tile_cap = b.tile_cap(), d.frames = b.frames(), d.out = b.bitmaps();
 		d.out_bytes = b.bitmap_bytes();
 		est = std::max(est, b.est_cost());
+		note_glyf_batch(b);
 	}
 	const int rc = b200sdf_submit_glyph_batches(ctx_, desc, (uint32_t)n, est, ticket);
 	if (rc != 0) {

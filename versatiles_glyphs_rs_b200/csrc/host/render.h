@@ -218,6 +218,7 @@ class GlyphBatch {
 	const b200sdf_glyph_frame *frames() const { return reinterpret_cast<const b200sdf_glyph_frame *>(frames_.data()); }
 	uint32_t part_count() const { return n_parts_; }
 	uint32_t curve_slots() const { return curve_slots_; }
+	uint32_t generated_segment_slots() const { return gen_seg_slots_; }
 	uint32_t path_glyphs() const { return n_path_; } // glyphs with cubic curves flattened by the device (kind PATH)
 	uint32_t tile_cap() const { return tile_cap_; }
 	// estimated tile x segment units of the work the device renders together with this batch (b200sdf_submit_glyphs
@@ -359,6 +360,14 @@ class Renderer {
 	mutable std::vector<std::pair<uint64_t, uint32_t>> fonts_; // Face::uid -> handle of its glyf table on ctx_
 	mutable size_t out_now_ = 0, out_max_ = 0; // batches handed out and not yet returned; the most that ever were
 	mutable size_t acq_call_ = 0, acq_max_ = 0; // batches handed out since the last top-up; the most per call
+	// glyph-level batches submitted so far: the largest device needs of ONE batch and the fewest glyphs a batch had — from
+	// these top_up_pool bounds the largest merged submission the pipeline can make (b200sdf_reserve_glyphs)
+	struct GlyfMarks {
+		uint64_t reqs = 0;                                // most glyph requests in one batch
+		double segs = 0.0, curve_slots = 0.0, tile_cap = 0.0; // most per request of any batch
+	};
+	mutable GlyfMarks glyf_marks_;
+	void note_glyf_batch(const GlyphBatch &b) const;
 };
 
 } // namespace vgb
