@@ -583,8 +583,10 @@ def main():
         def e2e_loop(steps, threads, make_writer):
             ms = []
             st = None
-            for _ in range(steps):
+            for k in range(steps):
                 w = make_writer()
+                if os.environ.get("VGB_ALLOC_TRACE"):
+                    print(f"--- rank {rank} step {k} of {steps}", file=sys.stderr, flush=True)
                 ts = time.perf_counter()
                 st = job.manager.render_glyphs(w, renderer, shard=rank, n_shards=world, threads=threads)
                 ms.append(1e3 * (time.perf_counter() - ts))
@@ -601,9 +603,10 @@ def main():
         barrier()
         t_e2e_end = time.perf_counter()
         e2e_s = max_over_ranks(t_loop)
+        slow = [(i, round(x, 2)) for i, x in enumerate(step_ms) if x > 1.5 * statistics.median(step_ms)]
         print(f"[bench] rank {rank}: e2e loop {1e3 * t_loop:.1f} ms, steps min/median/max "
-              f"{min(step_ms):.2f}/{statistics.median(step_ms):.2f}/{max(step_ms):.2f} ms, {st.workers} workers, {st.submits} submits",
-              file=sys.stderr)
+              f"{min(step_ms):.2f}/{statistics.median(step_ms):.2f}/{max(step_ms):.2f} ms, {st.workers} workers, {st.submits} submits"
+              + (f", steps over 1.5 x median (index, ms): {slow}" if slow else ""), file=sys.stderr)
         per_rank = gather({"rank": rank, "median_ms": statistics.median(step_ms), "max_ms": max(step_ms), "glyphs": st.glyphs,
                            "cost": st.cost_shard})
         result["e2e"] = {

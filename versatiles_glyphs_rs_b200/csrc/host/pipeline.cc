@@ -3,6 +3,7 @@
 #include "font.h"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -411,8 +412,15 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		st.handed_back += b.handed_back();
 		st.h2d_bytes += b.upload_bytes();
 	};
+	std::vector<std::array<double, 3>> task_density((size_t)workers, std::array<double, 3>{0.0, 0.0, 0.0});
+	// bytes of each batch buffer per glyph of the heaviest task (GlyphBatch::capacities order)
+	std::vector<std::array<double, GlyphBatch::kBuffers>> task_bytes((size_t)workers);
+	for (auto &a : task_bytes)
+		a.fill(0.0);
 	auto work = [&](int wid) {
 		RenderStats &st = per_worker[(size_t)wid];
+		std::array<double, 3> &dens = task_density[(size_t)wid]; // heaviest task: segments, curve slots, tile jobs per request
+		std::array<double, GlyphBatch::kBuffers> &bpg = task_bytes[(size_t)wid];
 		auto &ev = events[(size_t)wid];
 		auto mark = [&](char what) {
 			if (trace)
@@ -560,7 +568,33 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 					const Todo &todo = tasks[ti];
 					const size_t g0 = cur->batch->glyphs().size();
 					glyphs_taken.fetch_add(todo.glyphs, std::memory_order_relaxed);
+					const GlyphBatch &bb = *cur->batch;
+					const uint64_t r0 = bb.job_count(), s0 = (uint64_t)bb.segment_count() + bb.generated_segment_slots(),
+					               c0 = bb.curve_slots(), k0 = bb.tile_cap();
+					const uint64_t u0[GlyphBatch::kBuffers] = {(uint64_t)bb.job_count() * sizeof(b200sdf_outline_job),
+					                                           (uint64_t)bb.segment_count() * sizeof(b200sdf_segment),
+					                                           (uint64_t)bb.curve_count() * sizeof(b200sdf_curve), bb.bitmap_bytes(), 0,
+					                                           (uint64_t)bb.job_count() * sizeof(b200sdf_glyph_req),
+					                                           (uint64_t)bb.part_count() * sizeof(b200sdf_glyph_part),
+					                                           (uint64_t)bb.job_count() * sizeof(b200sdf_glyph_frame)};
 					todo.bs->blk->append_to_batch(*cur->batch, todo.slot0, todo.slot1);
+					if (bb.glyphs().size() > g0) {
+						const uint64_t u1[GlyphBatch::kBuffers] = {(uint64_t)bb.job_count() * sizeof(b200sdf_outline_job),
+						                                           (uint64_t)bb.segment_count() * sizeof(b200sdf_segment),
+						                                           (uint64_t)bb.curve_count() * sizeof(b200sdf_curve), bb.bitmap_bytes(), 0,
+						                                           (uint64_t)bb.job_count() * sizeof(b200sdf_glyph_req),
+						                                           (uint64_t)bb.part_count() * sizeof(b200sdf_glyph_part),
+						                                           (uint64_t)bb.job_count() * sizeof(b200sdf_glyph_frame)};
+						const double n = (double)(bb.glyphs().size() - g0);
+						for (int k = 0; k < GlyphBatch::kBuffers; ++k)
+							bpg[(size_t)k] = std::max(bpg[(size_t)k], (double)(u1[k] - u0[k]) / n);
+					}
+					if (glyf_mode && bb.job_count() > r0) { // what this task needs on the device per request: the same in every call
+						const double n = (double)(bb.job_count() - r0);
+						dens[0] = std::max(dens[0], (double)((uint64_t)bb.segment_count() + bb.generated_segment_slots() - s0) / n);
+						dens[1] = std::max(dens[1], (double)(bb.curve_slots() - c0) / n);
+						dens[2] = std::max(dens[2], (double)(bb.tile_cap() - k0) / n);
+					}
 					cur->parts.push_back(Part{&todo, g0, cur->batch->glyphs().size()});
 				}
 				st.outline_ns += now_ns() - t0;
@@ -842,6 +876,28 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				renderer.release_batch(std::move(f->batch));
 			delete f;
 		}
+	if (glyf_mode) {
+		// what the largest merged submission of a later call can need, from figures that do not depend on timing: the
+		// heaviest task's needs per request, and 4096 glyphs (where a submission stops growing) + one full batch
+		std::array<double, 3> d{0.0, 0.0, 0.0};
+		for (const auto &w : task_density)
+			for (int k = 0; k < 3; ++k)
+				d[(size_t)k] = std::max(d[(size_t)k], w[(size_t)k]);
+		renderer.note_glyf_density(d[0], d[1], d[2]);
+		renderer.set_glyf_group_bound(std::min<uint64_t>(total_glyphs, 4096 + target + kPartGlyphs));
+		// the pooled batches: no batch holds more than target + one task's glyphs, none is heavier per glyph than the
+		// heaviest task (+ 1/8, rounded to the 256 KiB steps pinned buffers grow in)
+		size_t caps[GlyphBatch::kBuffers];
+		const double max_glyphs = (double)std::min<uint64_t>(total_glyphs, target + kPartGlyphs);
+		for (int k = 0; k < GlyphBatch::kBuffers; ++k) {
+			double b = 0.0;
+			for (const auto &w : task_bytes)
+				b = std::max(b, w[(size_t)k]);
+			const double bytes = b * max_glyphs * 1.125 + 64.0;
+			caps[k] = b > 0.0 ? (((size_t)bytes + ((size_t)256 << 10) - 1) & ~(((size_t)256 << 10) - 1)) : 0;
+		}
+		renderer.raise_batch_marks(caps);
+	}
 	renderer.top_up_pool();
 	if (trace) {
 		std::fprintf(stderr, "[vgb trace] setup %.1f us, %d workers, %zu tasks, target %zu glyphs, total %.1f us\n",

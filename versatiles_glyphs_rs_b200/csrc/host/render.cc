@@ -972,14 +972,16 @@ void Renderer::top_up_pool() const
 		// glyphs): how large those get depends on timing, so the slots are sized for the largest one possible — as many
 		// glyphs as a submission can hold, each as heavy as the heaviest batch's average glyph.
 		GlyfMarks m;
+		uint64_t bound;
 		{
 			std::lock_guard<std::mutex> g(pool_mu_);
 			m = glyf_marks_;
+			bound = glyf_group_bound_;
 		}
 		if (m.reqs) {
 			auto u32 = [](double v) { return (uint32_t)std::min(v + 1.0, 4294967295.0); };
 			// (a submission stops growing at 4096 glyphs: it holds less than 4096 + one batch)
-			const double reqs = (double)std::min<uint64_t>((uint64_t)kMaxGroup * m.reqs, 4096 + m.reqs);
+			const double reqs = (double)std::max<uint64_t>(bound, std::min<uint64_t>((uint64_t)kMaxGroup * m.reqs, 4096 + m.reqs));
 			b200sdf_reserve_glyphs(ctx_, u32(reqs), u32(m.segs * reqs), u32(m.curve_slots * reqs), u32(m.tile_cap * reqs));
 		} else {
 			b200sdf_reserve(ctx_);
@@ -1096,6 +1098,27 @@ void Renderer::note_glyf_batch(const GlyphBatch &b) const
 	glyf_marks_.segs = std::max(glyf_marks_.segs, ((double)b.segment_count() + (double)b.generated_segment_slots()) / n);
 	glyf_marks_.curve_slots = std::max(glyf_marks_.curve_slots, (double)b.curve_slots() / n);
 	glyf_marks_.tile_cap = std::max(glyf_marks_.tile_cap, (double)b.tile_cap() / n);
+}
+
+void Renderer::note_glyf_density(double segs_per_req, double curve_slots_per_req, double tile_cap_per_req) const
+{
+	std::lock_guard<std::mutex> g(pool_mu_);
+	glyf_marks_.segs = std::max(glyf_marks_.segs, segs_per_req);
+	glyf_marks_.curve_slots = std::max(glyf_marks_.curve_slots, curve_slots_per_req);
+	glyf_marks_.tile_cap = std::max(glyf_marks_.tile_cap, tile_cap_per_req);
+}
+
+void Renderer::raise_batch_marks(const size_t caps[GlyphBatch::kBuffers]) const
+{
+	std::lock_guard<std::mutex> g(pool_mu_);
+	for (int i = 0; i < GlyphBatch::kBuffers; ++i)
+		hwm_[i] = std::max(hwm_[i], caps[i]);
+}
+
+void Renderer::set_glyf_group_bound(uint64_t requests) const
+{
+	std::lock_guard<std::mutex> g(pool_mu_);
+	glyf_group_bound_ = std::max(glyf_group_bound_, requests);
 }
 
 bool Renderer::submit_batches(GlyphBatch *const *batches, size_t n, uint64_t *ticket, std::string *err) const

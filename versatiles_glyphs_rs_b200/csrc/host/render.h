@@ -367,7 +367,22 @@ class Renderer {
 		double segs = 0.0, curve_slots = 0.0, tile_cap = 0.0; // most per request of any batch
 	};
 	mutable GlyfMarks glyf_marks_;
+	mutable uint64_t glyf_group_bound_ = 0; // most glyph requests one merged submission of the pipeline can hold (0: not told)
 	void note_glyf_batch(const GlyphBatch &b) const;
+
+  public:
+	// The pipeline's own, timing-independent figures for the same purpose: the heaviest TASK (a fixed range of a block's
+	// glyphs — the same in every call, unlike the batches the tasks happen to be grouped into) per request, and the
+	// most requests a merged submission can hold.
+	void note_glyf_density(double segs_per_req, double curve_slots_per_req, double tile_cap_per_req) const;
+	void set_glyf_group_bound(uint64_t requests) const;
+	// ... and for the pooled (pinned) batch buffers: capacities no batch of this job can exceed (bytes per buffer, in
+	// GlyphBatch::capacities order).  Batches differ from call to call (workers claim tasks dynamically); without this
+	// a batch a little larger than any before re-sized the whole pool in the middle of a long run (50 pinned
+	// allocations, 40 ms).
+	void raise_batch_marks(const size_t caps[GlyphBatch::kBuffers]) const;
+
+  private:
 };
 
 } // namespace vgb
