@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-strong", action="store_true", help="skip the C4 strong-scaling leg")
     ap.add_argument("--diag", action="store_true", help="also time the host-planned (sorted, one CTA per tile job) SDF kernel on the same records")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (default: min(steps, 20))")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads per rank in the e2e leg (default: the box's cores / ranks)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
     ap.add_argument("--cpu-child", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
@@ -413,7 +414,7 @@ def main():
         dist.all_gather_object(out, obj)
         return out
 
-    host_threads = max(1, len(os.sched_getaffinity(0)) // world)  # the ranks of one box share its host cores
+    host_threads = args.host_threads or max(1, len(os.sched_getaffinity(0)) // world)  # the ranks of one box share its host cores
     label, fonts = workload_fonts(args.workload, world)
     renderer = V.Renderer.new_precise(device=local_rank)
     job = Job(V, np, torch, dev, renderer, fonts, rank, world)

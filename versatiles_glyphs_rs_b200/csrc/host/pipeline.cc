@@ -401,6 +401,8 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	const size_t max_outstanding =
 	    renderer.mode() == Renderer::Mode::Cuda ? std::max<size_t>(2, renderer.slots()) : (size_t)(2 * workers + 2);
 
+	renderer.set_pool_target(max_outstanding + (size_t)workers + 2);
+
 	// what a finished (and finalized) batch adds to the call's statistics
 	auto account = [](RenderStats &st, const GlyphBatch &b) {
 		st.glyphs += b.glyphs().size();

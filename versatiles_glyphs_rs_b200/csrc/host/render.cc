@@ -963,6 +963,8 @@ void Renderer::top_up_pool() const
 		// or two more than any before do not each end with an allocation.
 		const size_t floor = std::max(out_max_ + out_max_ / 2, acq_max_ + 2);
 		want = have < floor ? std::max(2 * out_max_, acq_max_ + acq_max_ / 2) : have;
+		if (pool_target_) // the pipeline's own bound on the batches it can hold at a time: nothing else is ever needed
+			want = std::max(have, pool_target_);
 		want = std::min(kPoolTopUp, want);
 		mine.swap(pool_); // size the pooled batches outside the lock
 	}
@@ -1113,6 +1115,12 @@ void Renderer::raise_batch_marks(const size_t caps[GlyphBatch::kBuffers]) const
 	std::lock_guard<std::mutex> g(pool_mu_);
 	for (int i = 0; i < GlyphBatch::kBuffers; ++i)
 		hwm_[i] = std::max(hwm_[i], caps[i]);
+}
+
+void Renderer::set_pool_target(size_t batches) const
+{
+	std::lock_guard<std::mutex> g(pool_mu_);
+	pool_target_ = std::max(pool_target_, batches);
 }
 
 void Renderer::set_glyf_group_bound(uint64_t requests) const

@@ -367,6 +367,7 @@ class Renderer {
 		double segs = 0.0, curve_slots = 0.0, tile_cap = 0.0; // most per request of any batch
 	};
 	mutable GlyfMarks glyf_marks_;
+	mutable size_t pool_target_ = 0;
 	mutable uint64_t glyf_group_bound_ = 0; // most glyph requests one merged submission of the pipeline can hold (0: not told)
 	void note_glyf_batch(const GlyphBatch &b) const;
 
@@ -381,6 +382,9 @@ class Renderer {
 	// a batch a little larger than any before re-sized the whole pool in the middle of a long run (50 pinned
 	// allocations, 40 ms).
 	void raise_batch_marks(const size_t caps[GlyphBatch::kBuffers]) const;
+	// The most batches the pipeline can hold at one time (its back-pressure limit + one per worker): the pool is kept at
+	// that size, instead of at a multiple of what past calls happened to use.
+	void set_pool_target(size_t batches) const;
 
   private:
 };
