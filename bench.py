@@ -634,6 +634,7 @@ def main():
         few = max(3, min(8, e2e_steps))
         tmp = tempfile.mkdtemp(prefix="vgb_bench_")
         io_ms, _ = e2e_loop(few, host_threads, lambda: V.Writer.new_file(tmp))
+        e2e_loop(3, 1, V.Writer.new_memory)  # (a different thread count means different batch sizes: let the pools settle first)
         one_ms, _ = e2e_loop(few, 1, V.Writer.new_memory)
         import shutil
 
