@@ -5,11 +5,9 @@ set -u
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 declare -A V=(
   [base]=""
-  [mask0]="-DB200SDF_BAND_MASK=0"
-  [rowscan0]="-DB200SDF_ROW_SCAN=0"
-  [both0]="-DB200SDF_BAND_MASK=0 -DB200SDF_ROW_SCAN=0"
-  [ctas7]="-DB200SDF_STRIDED_MIN_CTAS=7"
-  [ctas6]="-DB200SDF_STRIDED_MIN_CTAS=6"
+  [g5]="-DB200SDF_GLYF_MIN_CTAS=5 -DB200SDF_GLYF_MAX_POINTS=1792"
+  [g6]="-DB200SDF_GLYF_MIN_CTAS=6 -DB200SDF_GLYF_MAX_POINTS=1536"
+  [g8]="-DB200SDF_GLYF_MIN_CTAS=8 -DB200SDF_GLYF_MAX_POINTS=1024"
 )
 if [ "${1:-}" = "build" ]; then
   for n in "${!V[@]}"; do

@@ -349,6 +349,14 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 		std::vector<Part> parts;
 		uint64_t ticket = 0;
 		std::vector<Flight *> mates; // the other batches of the same submission (they finish together)
+		// A finished batch is encoded PART BY PART by whichever workers are free (the batches of a merged submission
+		// come back together, at the end of a call all at once: one worker per batch left most of them idle for the
+		// call's last 0.1 ms).  next_part is claimed under the queue lock; the first claimer finalizes the batch
+		// (fin: 0 not yet, 1 in progress, 2 done, 3 failed) while the others wait for it; whoever finishes the last
+		// part gives the batch back.
+		size_t next_part = 0;
+		std::atomic<size_t> parts_left{0};
+		std::atomic<int> fin{0};
 	};
 	std::mutex qm;
 	std::condition_variable qcv;
@@ -492,35 +500,51 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			if (coop_pump)
 				worker_pump(false, nullptr);
 			Flight *done = nullptr;
+			size_t part = 0;
 			{
 				std::lock_guard<std::mutex> g(qm);
 				if (!done_q.empty()) {
 					done = done_q.front();
-					done_q.pop_front();
+					part = done->next_part++;
+					if (done->next_part >= done->parts.size()) // (also a batch without parts: an error path dropped its results)
+						done_q.pop_front();
 				}
 			}
 			if (done) {
 				idle_spins = 0;
 				mark('e');
 				bool ok = true;
-				if (!done->parts.empty()) { // (an error path hands back batches without parts: results dropped)
-					std::string e;
-					ok = done->batch->finalize(renderer, &e);
-					if (!ok)
-						fail(e);
-					account(st, *done->batch);
-				}
-				for (const Part &p : done->parts)
-					if (ok)
+				const bool empty = done->parts.empty();
+				if (!empty) {
+					int expected = 0;
+					if (done->fin.compare_exchange_strong(expected, 1, std::memory_order_acq_rel)) {
+						std::string e;
+						const bool fok = done->batch->finalize(renderer, &e);
+						if (!fok)
+							fail(e);
+						account(st, *done->batch);
+						done->fin.store(fok ? 2 : 3, std::memory_order_release);
+					} else {
+						while (done->fin.load(std::memory_order_acquire) < 2)
+							cpu_pause();
+					}
+					ok = done->fin.load(std::memory_order_acquire) == 2;
+					if (ok) {
+						const Part &p = done->parts[part];
 						ok = finish_part(*p.todo, *done->batch, p.g0, p.g1);
-				ok = ok && flush();
-				renderer.release_batch(std::move(done->batch));
-				delete done;
-				{
-					std::lock_guard<std::mutex> g(qm);
-					--outstanding;
+					}
 				}
-				qcv.notify_all();
+				ok = flush() && ok;
+				if (empty || done->parts_left.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+					// the batch's last part: give it back
+					renderer.release_batch(std::move(done->batch));
+					delete done;
+					{
+						std::lock_guard<std::mutex> g(qm);
+						--outstanding;
+					}
+					qcv.notify_all();
+				}
 				if (!ok)
 					break;
 				continue;
@@ -657,6 +681,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				mark('s');
 				{
 					std::lock_guard<std::mutex> g(qm);
+					cur->parts_left.store(cur->parts.size(), std::memory_order_relaxed); // (published by the queue lock)
 					submit_q.push_back(cur.release());
 				}
 				if (inline_pump || coop_pump)
