@@ -316,6 +316,11 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 	}();
 	const size_t kBatchesPerWorker = kBatchesPerWorkerEnv ? kBatchesPerWorkerEnv : 4;
 	constexpr int kEarlyWorkers = 4;
+	static const size_t kOpenGlyphs = [] { // glyphs in a worker's opening batch, at least (tuning knob)
+		const char *e = std::getenv("VGB_OPEN_GLYPHS");
+		const long v = e ? std::atol(e) : 0;
+		return (size_t)(v >= 1 && v <= 4096 ? v : 192);
+	}();
 	static const bool kLatencyTail = [] { // VGB_LATENCY_TAIL=1: plan each worker's last batch for latency
 		const char *e = std::getenv("VGB_LATENCY_TAIL"); // (measured on C2: 1.30-1.35 ms with, 1.26-1.34 without: off)
 		return e && e[0] == '1';
@@ -583,7 +588,7 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 				// Device-side decoding: filling a batch costs microseconds, submitting one costs the CUDA thread ~15 us and
 				// a kernel pair under a few hundred glyphs runs as long as its heaviest tile: equal, large batches.
 				if (glyf_mode) // (each worker opens with a quarter-size batch: the GPU has work after tens of microseconds)
-					want = n_batches == 0 ? std::max<size_t>(192, target / 4) : target;
+					want = n_batches == 0 ? std::max<size_t>(kOpenGlyphs, target / 4) : target;
 				++n_batches;
 				while (cur->batch->glyphs().size() < want) {
 					const size_t ti = next.fetch_add(1);
