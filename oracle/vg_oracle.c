@@ -96,6 +96,7 @@ typedef struct {
 
 typedef struct vgo_cff vgo_cff;
 static vgo_cff *cff_parse(span t);
+static vgo_cff *cff2_parse(span t, uint32_t axes);
 
 struct vgo_font {
 	uint8_t *data;
@@ -107,7 +108,8 @@ struct vgo_font {
 	span hmtx, loca, glyf, cmap;
 	cmap_sub *subs;
 	uint32_t n_subs;
-	struct vgo_cff *cff; /* parsed `CFF ` table, NULL if absent or rejected */
+	struct vgo_cff *cff;  /* parsed `CFF ` table, NULL if absent or rejected */
+	struct vgo_cff *cff2; /* parsed `CFF2` table */
 };
 
 static inline uint16_t rd16(const uint8_t *p) { return (uint16_t)((p[0] << 8) | p[1]); }
@@ -176,6 +178,13 @@ vgo_font *vgo_font_parse(const uint8_t *data, size_t len)
 	span cff;
 	if (find_table(f, "CFF ", &cff))
 		f->cff = cff_parse(cff);
+	span cff2, fvar;
+	if (find_table(f, "CFF2", &cff2)) {
+		uint32_t axes = 0;
+		if (find_table(f, "fvar", &fvar) && fvar.len >= 10)
+			axes = rd16(fvar.p + 8) < 64 ? rd16(fvar.p + 8) : 64;
+		f->cff2 = cff2_parse(cff2, axes);
+	}
 	/* cmap subtable records, in table order */
 	if (f->cmap.len >= 4) {
 		uint16_t n = rd16(f->cmap.p + 2);
@@ -204,6 +213,7 @@ void vgo_font_free(vgo_font *f)
 		return;
 	free(f->subs);
 	free(f->cff);
+	free(f->cff2);
 	free(f->data);
 	free(f);
 }
@@ -851,13 +861,22 @@ static uint32_t cff_off(const uint8_t *p, uint32_t osz)
 }
 
 /* parse_index at *pos of s; advances *pos; 0 = None */
+static int cff_read_index_w(span s, size_t *pos, cff_index *ix, int wide);
 static int cff_read_index(span s, size_t *pos, cff_index *ix)
 {
+	return cff_read_index_w(s, pos, ix, 0);
+}
+/* wide: CFF 2's parse_index::<u32> */
+static int cff_read_index_w(span s, size_t *pos, cff_index *ix, int wide)
+{
 	memset(ix, 0, sizeof(*ix));
-	if (*pos > s.len || s.len - *pos < 2)
+	const size_t cb = wide ? 4 : 2;
+	if (*pos > s.len || s.len - *pos < cb)
 		return 0;
-	uint32_t count = rd16(s.p + *pos);
-	*pos += 2;
+	uint32_t count = wide ? rd32(s.p + *pos) : rd16(s.p + *pos);
+	*pos += cb;
+	if (count == 0xffffffffu)
+		return 0;
 	if (count == 0)
 		return 1;
 	if (s.len - *pos < 1)
@@ -982,6 +1001,10 @@ struct vgo_cff {
 	int charset_format; /* -1 ISOAdobe, -2 Expert, -3 ExpertSubset, else 0 / 1 / 2 with the records in charset */
 	span charset;
 	uint32_t charset_n; /* records */
+	/* CFF 2 (cff2.rs): ItemVariationStore of the `vstore` operator; axes = the face's variation coordinates (all 0) */
+	int cff2, has_vstore;
+	uint32_t axes, region_axes, n_regions, n_vdata;
+	span vstore, vdata_offs, regions;
 };
 
 /* StandardEncoding (Adobe): code -> SID, as runs {first code, last code, first SID} */
@@ -1154,6 +1177,94 @@ static vgo_cff *cff_parse(span t)
 }
 
 /* local subroutines of a CID glyph: FDSelect → FDArray[fd] → Private → Subrs */
+/* cff2::Table::parse; axes = min(fvar axis count, 64) */
+static vgo_cff *cff2_parse(span t, uint32_t axes)
+{
+	if (t.len < 5 || t.p[0] != 2 || t.p[2] < 5)
+		return NULL;
+	size_t pos = t.p[2];
+	uint32_t tdlen = rd16(t.p + 3);
+	if (pos > t.len || t.len - pos < tdlen)
+		return NULL;
+	span td = {t.p + pos, tdlen};
+	pos += tdlen;
+	vgo_cff c;
+	memset(&c, 0, sizeof(c));
+	c.table = t, c.cff2 = 1, c.axes = axes;
+	size_t cs = 0, vs = 0, fda = 0, dpos = 0;
+	int has_vs = 0, has_fda = 0, n, op;
+	double ops[48];
+	while ((op = cff_dict_next(td, &dpos, ops, &n)) >= 0) {
+		if (op == 17) {
+			if (!cff_as_offset(ops, n, &cs))
+				return NULL;
+		} else if (op == 24)
+			has_vs = cff_as_offset(ops, n, &vs);
+		else if (op == 1236)
+			has_fda = cff_as_offset(ops, n, &fda);
+	}
+	if (cs == 0)
+		return NULL;
+	if (!cff_read_index_w(t, &pos, &c.gsubrs, 1))
+		return NULL;
+	size_t at = cs;
+	if (!cff_read_index_w(t, &at, &c.charstrings, 1))
+		return NULL;
+	if (has_vs) {
+		if (vs > t.len || t.len - vs < 2 + 8)
+			return NULL;
+		size_t base = vs + 2;
+		c.vstore.p = t.p + base, c.vstore.len = t.len - base;
+		uint32_t format = rd16(c.vstore.p), roff = rd32(c.vstore.p + 2);
+		c.n_vdata = rd16(c.vstore.p + 6);
+		if (format != 1 || c.vstore.len < 8 + (size_t)c.n_vdata * 4)
+			return NULL;
+		c.vdata_offs.p = c.vstore.p + 8, c.vdata_offs.len = (size_t)c.n_vdata * 4;
+		if ((size_t)roff + 4 > c.vstore.len)
+			return NULL;
+		c.region_axes = rd16(c.vstore.p + roff), c.n_regions = rd16(c.vstore.p + roff + 2);
+		if ((size_t)roff + 4 + (size_t)c.region_axes * c.n_regions * 6 > c.vstore.len)
+			return NULL;
+		c.regions.p = c.vstore.p + roff + 4, c.regions.len = (size_t)c.region_axes * c.n_regions * 6;
+		c.has_vstore = 1;
+	}
+	if (has_fda) {
+		cff_index fonts;
+		at = fda;
+		if (!cff_read_index_w(t, &at, &fonts, 1))
+			return NULL;
+		for (uint32_t i = 0; i < fonts.count; i++) {
+			span fd;
+			if (!cff_index_get(&fonts, i, &fd))
+				return NULL;
+			size_t pstart = 0, plen = 0, fpos = 0;
+			int has_priv = 0;
+			while ((op = cff_dict_next(fd, &fpos, ops, &n)) >= 0)
+				if (op == 18)
+					has_priv = cff_as_range(ops, n, &pstart, &plen);
+			if (!has_priv || pstart > t.len || t.len - pstart < plen)
+				return NULL;
+			/* the first Font DICT whose Private DICT names local subroutines supplies them (no FDSelect) */
+			span priv = {t.p + pstart, plen};
+			size_t ppos = 0, soff = 0;
+			int have = 0;
+			while ((op = cff_dict_next(priv, &ppos, ops, &n)) >= 0)
+				if (op == 19)
+					have = cff_as_offset(ops, n, &soff);
+			if (have) {
+				size_t lat = pstart + soff;
+				if (lat > t.len || !cff_read_index_w(t, &lat, &c.lsubrs, 1))
+					return NULL;
+				break;
+			}
+		}
+	}
+	vgo_cff *out = malloc(sizeof(c));
+	if (out)
+		*out = c;
+	return out;
+}
+
 static int cff_cid_lsubrs(const vgo_cff *c, uint32_t gid, cff_index *out)
 {
 	uint32_t fd;
@@ -1205,10 +1316,12 @@ typedef struct {
 	const vgo_cff *c;
 	ring_builder *rb;
 	uint32_t gid;
-	float st[48];
-	int n;
+	float st[513];
+	int n, max_n;
 	float x, y;
 	int moved, first_move, width_seen, endchar, seac, stems;
+	int had_vsindex, had_blend, n_scalars;
+	float scalars[64];
 	int lsubrs_ready;
 	cff_index lsubrs;
 } cs_state;
@@ -1227,6 +1340,54 @@ static void cs_rline(cs_state *s, float dx, float dy)
 {
 	s->x += dx, s->y += dy;
 	rb_line_to(s->rb, s->x, s->y);
+}
+
+/* update_scalars at all-zero coordinates (var_store.rs evaluate_region / evaluate_axis); 0 = error */
+static int cff2_scalars(const vgo_cff *c, uint32_t index, float *scalars, int *count)
+{
+	*count = 0;
+	if (!c->has_vstore || index >= c->n_vdata)
+		return 0;
+	uint32_t off = rd32(c->vdata_offs.p + (size_t)index * 4);
+	if ((size_t)off + 6 > c->vstore.len)
+		return 0;
+	uint32_t n = rd16(c->vstore.p + off + 4);
+	if ((size_t)off + 6 + (size_t)n * 2 > c->vstore.len)
+		return 0;
+	for (uint32_t k = 0; k < n; k++) {
+		uint32_t region = rd16(c->vstore.p + off + 6 + (size_t)k * 2);
+		float v = 1.0f;
+		for (uint32_t axis = 0; axis < c->axes; axis++) {
+			if (region >= c->n_regions || axis >= c->region_axes) {
+				v = 0.0f;
+				break;
+			}
+			const uint8_t *r = c->regions.p + ((size_t)region * c->region_axes + axis) * 6;
+			int start = rds16(r), peak = rds16(r + 2), end = rds16(r + 4);
+			float factor;
+			if (start > peak || peak > end)
+				factor = 1.0f;
+			else if (start < 0 && end > 0 && peak != 0)
+				factor = 1.0f;
+			else if (peak == 0)
+				factor = 1.0f;
+			else if (0 <= start || end <= 0)
+				factor = 0.0f;
+			else if (0 < peak)
+				factor = (float)(0 - start) / (float)(peak - start);
+			else
+				factor = (float)(end - 0) / (float)(end - peak);
+			if (factor == 0.0f) {
+				v = 0.0f;
+				break;
+			}
+			v *= factor;
+		}
+		if (*count == 64)
+			return 0;
+		scalars[(*count)++] = v;
+	}
+	return 1;
 }
 
 /* 1 = keep going / finished normally, 0 = error (CFFError) */
@@ -1255,10 +1416,48 @@ static int cs_exec(cs_state *s, span code, int depth)
 				int w = code.p[pc++];
 				v = (float)(op <= 250 ? (op - 247) * 256 + w + 108 : -(op - 251) * 256 - w - 108);
 			}
-			if (s->n == 48)
+			if (s->n == s->max_n)
 				return 0;
 			s->st[s->n++] = v;
 			continue;
+		}
+		if (s->c->cff2) {
+			if (op == 11 || op == 14)
+				return 0; /* no return / endchar in CFF 2 */
+			if (op == 15) { /* vsindex */
+				if (s->had_blend || s->had_vsindex || n != 1)
+					return 0;
+				double v = (double)a[0];
+				if (!(v > -2147483649.0 && v < 2147483648.0) || (int32_t)v < 0 || (int32_t)v > 65535)
+					return 0;
+				if (!cff2_scalars(s->c, (uint32_t)(int32_t)v, s->scalars, &s->n_scalars))
+					return 0;
+				s->had_vsindex = 1;
+				s->n = 0;
+				continue;
+			}
+			if (op == 16) { /* blend */
+				s->had_blend = 1;
+				if (n == 0)
+					return 0;
+				double v = (double)a[n - 1];
+				s->n = --n;
+				if (!(v > -2147483649.0 && v < 2147483648.0) || (int32_t)v < 0 || (int32_t)v > 65535)
+					return 0;
+				int cnt = (int32_t)v, k = s->n_scalars;
+				int need = cnt * (k + 1);
+				if (n < need)
+					return 0;
+				int start = n - need;
+				for (int i = cnt - 1; i >= 0; i--)
+					for (int j = 0; j < k; j++) {
+						float delta = s->st[--s->n];
+						s->st[start + i] += delta * s->scalars[k - j - 1];
+					}
+				continue;
+			}
+			if ((op == 21 || op == 22 || op == 4) && n != (op == 21 ? 2 : 1))
+				return 0; /* no width in CFF 2 */
 		}
 		switch (op) {
 		case 1: case 3: case 18: case 23: /* h/vstem(hm) */
@@ -1509,7 +1708,13 @@ static void cff_outline(const vgo_cff *c, uint32_t gid, ring_builder *rb)
 		return;
 	cs_state s;
 	memset(&s, 0, sizeof(s));
-	s.c = c, s.rb = rb, s.gid = gid, s.first_move = 1;
+	s.c = c, s.rb = rb, s.gid = gid, s.first_move = 1, s.max_n = 48;
+	if (c->cff2) {
+		s.max_n = 513;
+		s.width_seen = 1; /* no widths in CFF 2 */
+		if (!cff2_scalars(c, 0, s.scalars, &s.n_scalars))
+			return;
+	}
 	cs_exec(&s, code, 0); /* the reference ignores outline_glyph's result: what was emitted stays */
 }
 
@@ -1522,6 +1727,8 @@ int vgo_outline_rings(const vgo_font *f, uint32_t gid, vgo_rings *out)
 	if (f->glyf.len == 0 || f->loca.len == 0) { /* ttf-parser: glyf first, then cff */
 		if (f->cff)
 			cff_outline(f->cff, gid, &rb);
+		else if (f->cff2)
+			cff_outline(f->cff2, gid, &rb);
 	} else if (glyph_span(f, gid, &g))
 		outline_impl(f, g, 0, XF_ID, &rb);
 	rb_save_ring(&rb); /* into_rings — ring_builder.rs:26-29 */

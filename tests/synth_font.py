@@ -310,7 +310,7 @@ def _subr_bias(n):
     return 107 if n < 1240 else 1131 if n < 33900 else 32768
 
 
-def encode_charstring(cmds, variant=0, width=None, hints=False, call=None):
+def encode_charstring(cmds, variant=0, width=None, hints=False, call=None, endchar=True, blend_regions=0):
     """Absolute commands -> Type 2 charstring.  `variant` rotates which of the equivalent operators is used;
     `call` = (operator byte 10 / 29, biased index) is issued right after the first moveto (the subroutine
     draws a closed square relative to the current point and returns to it, see cff_test_font)."""
@@ -324,11 +324,19 @@ def encode_charstring(cmds, variant=0, width=None, hints=False, call=None):
         out += _t2_num(30) + _t2_num(40) + _t2_num(50) + _t2_num(60) + b"\x13\xe0"
     i = 0
     k = variant
+    blend_ctr = [variant]
     while i < len(cmds):
         c = cmds[i]
         k += 1
         style = (0, 0, 1, 0, 2)[k % 5]
         num = lambda v: _t2_num(v, style)
+        if blend_regions:  # CFF 2: every other operand carries variation deltas (default d1 .. dk 1 blend)
+            def num(v, _style=style, _ctr=blend_ctr):
+                _ctr[0] += 1
+                if _ctr[0] % 2:
+                    return _t2_num(v, _style)
+                deltas = b"".join(_t2_num(((_ctr[0] * 7 + r * 13) % 41) - 20) for r in range(blend_regions))
+                return _t2_num(v, _style) + deltas + _t2_num(1) + b"\x10"
         if c[0] == "M":
             dx, dy = c[1] - x, c[2] - y
             w = b"".join(stack_w)
@@ -441,7 +449,7 @@ def encode_charstring(cmds, variant=0, width=None, hints=False, call=None):
                 out += b"".join(num(a) for a in d) + b"\x08"
             x, y = c[5], c[6]
             i += 1
-    return out + b"".join(stack_w) + b"\x0e"
+    return out + b"".join(stack_w) + (b"\x0e" if endchar else b"")
 
 
 def _blob(x, y, w, h, r):
@@ -669,6 +677,158 @@ def cff_test_font(n_glyphs=40, first_cp=0x41, seed=5, cid=False, fd_select_forma
               b"name": name}
     tags = sorted(tables)
     out = struct.pack(">4sHHHH", b"OTTO", len(tags), 64, 2, len(tags) * 16 - 64)
+    offset = 12 + 16 * len(tags)
+    records, blobs = b"", b""
+    for tag in tags:
+        data = tables[tag]
+        records += tag + struct.pack(">III", _table_checksum(data), offset, len(data))
+        padded = data + b"\0" * ((-len(data)) % 4)
+        blobs += padded
+        offset += len(padded)
+    return out + records + blobs, cps, expected
+
+
+def _cff2_index(items):
+    """CFF 2 INDEX: a 32-bit count; the empty INDEX is the count alone."""
+    if not items:
+        return b"\0\0\0\0"
+    offs = [1]
+    for it in items:
+        offs.append(offs[-1] + len(it))
+    osz = 1 if offs[-1] < 256 else 2 if offs[-1] < 65536 else 4
+    return struct.pack(">IB", len(items), osz) + b"".join(o.to_bytes(osz, "big") for o in offs) + b"".join(items)
+
+
+def cff2_test_font(n_glyphs=30, first_cp=0x41, seed=11):
+    """A variable OpenType font with CFF 2 outlines (two axes).  Returns (font bytes, code points, expected) like
+    cff_test_font: expected[i] = contours of the DEFAULT instance — what a renderer that never sets variation coordinates
+    draws.  Covers: 32-bit INDEX counts, charstrings without width / endchar, `blend` (one and several operands, one and
+    two regions), `vsindex`, a region whose peaks are all 0 (its scalar is 1 at every coordinate, the default included),
+    local and global subroutines without `return`, hint operators without a width."""
+    rng = np.random.default_rng(seed)
+    specials = [
+        # (charstring, expected contours)
+        (_raw(100, 5, 1, b"\x10", 200, -7, 1, b"\x10", b"\x15", 300, 9, 1, b"\x10", b"\x06", 0, 150, -40, 60, 3, 4, 5, 6, 4, b"\x10", b"\x05"),
+         [[("M", 100, 200), ("L", 400, 200), ("L", 400, 350), ("L", 360, 410)]]),
+        # vsindex 1: two regions, both 0 at the default
+        (_raw(1, b"\x0f", 10, 20, 1, 2, 3, 4, 2, b"\x10", b"\x15", 250, 30, -30, 1, b"\x10", b"\x06", 250, b"\x07", -250, b"\x06"),
+         [[("M", 10, 20), ("L", 260, 20), ("L", 260, 270), ("L", 10, 270)]]),
+        # vsindex 2: a region with every peak 0 has scalar 1 -> its deltas apply at the default instance too
+        (_raw(2, b"\x0f", 100, 11, 1, b"\x10", 200, 22, 1, b"\x10", b"\x15", 80, 5, 1, b"\x10", 0, 0, 90, -80, 0, b"\x05"),
+         [[("M", 111, 222), ("L", 196, 222), ("L", 196, 312), ("L", 116, 312)]]),
+        # hints without width: hstemhm (odd count: the last value is dropped), hintmask with implied vstems
+        (_raw(10, 20, 30, b"\x12", 30, 40, 50, 60, b"\x13\xe0", 50, 60, b"\x15", 100, b"\x06", 100, b"\x07", -100, b"\x06"),
+         [[("M", 50, 60), ("L", 150, 60), ("L", 150, 160), ("L", 50, 160)]]),
+    ]
+    cps = list(range(first_cp, first_cp + n_glyphs + len(specials)))
+    n_all = len(cps) + 1
+
+    def tri(scale):
+        return b"".join(_t2_num(dx * scale) + _t2_num(dy * scale) + b"\x05" for dx, dy in _SUBR_RING)
+
+    local_subrs = [tri(1), tri(3)]  # (no `return`: a CFF 2 subroutine ends with its data)
+    global_subrs = [_t2_num(0 - 107) + b"\x0a", tri(2)]
+
+    def tri_contour(x, y, scale):
+        pts, out = (x, y), [("M", x, y)]
+        for dx, dy in _SUBR_RING:
+            pts = (pts[0] + dx * scale, pts[1] + dy * scale)
+            out.append(("L",) + pts)
+        return out
+
+    charstrings = [b""]  # .notdef: nothing
+    expected, advances = [], [500]
+    for gi in range(n_glyphs):
+        contours = []
+        for k in range(1 + gi % 3):
+            w, h = int(rng.integers(120, 600)), int(rng.integers(100, 500))
+            x, y = int(rng.integers(0, 1000 - w)), int(rng.integers(-200, 800 - h))
+            contours.append(_blob(x, y, w, h, int(rng.integers(20, 50))) if (gi + k) % 2 == 0 else _wave(x, y, w, h, rng))
+        if gi % 3 == 1:
+            contours += _specials(int(rng.integers(0, 500)), int(rng.integers(-150, 100)))
+        first = contours[0][0]
+        cmds = [c for ct in contours for c in ct]
+        exp = [list(ct) for ct in contours]
+        call = None
+        kind = gi % 4
+        if kind == 1:
+            call = (10, 0 - 107)
+            exp[0] = tri_contour(first[1], first[2], 1) + contours[0][1:]
+        elif kind == 2:  # global subr 0 -> local subr 0
+            call = (29, 0 - 107)
+            exp[0] = tri_contour(first[1], first[2], 1) + contours[0][1:]
+        elif kind == 3:
+            call = (29, 1 - 107)
+            exp[0] = tri_contour(first[1], first[2], 2) + contours[0][1:]
+        charstrings.append(encode_charstring(cmds, variant=gi, call=call, endchar=False, blend_regions=1 if gi % 2 else 0))
+        expected.append(exp)
+        advances.append(int(rng.integers(400, 1101)))
+    for code, exp in specials:
+        charstrings.append(code)
+        expected.append(exp)
+        advances.append(600)
+    assert n_all == len(charstrings)
+
+    # ItemVariationStore: 3 regions over 2 axes; data 0 -> [region 0], data 1 -> [0, 1], data 2 -> [2]
+    f2 = lambda v: int(round(v * 16384)) & 0xFFFF
+    region = lambda *axes: b"".join(struct.pack(">HHH", f2(a), f2(b), f2(c)) for a, b, c in axes)
+    regions = struct.pack(">HH", 2, 3) + region((0, 1, 1), (0, 0, 0)) + region((0, 0, 0), (0, 1, 1)) + region((0, 0, 0), (0, 0, 0))
+    vdata = [struct.pack(">HHH", 0, 0, len(r)) + b"".join(struct.pack(">H", x) for x in r) for r in ([0], [0, 1], [2])]
+    head_len = 8 + 4 * len(vdata)
+    offs, pos = [], head_len + len(regions)
+    for d in vdata:
+        offs.append(pos)
+        pos += len(d)
+    store = struct.pack(">HIH", 1, head_len, len(vdata)) + b"".join(struct.pack(">I", o) for o in offs) + regions + b"".join(vdata)
+    vstore = struct.pack(">H", len(store)) + store
+
+    gsubr_index = _cff2_index(global_subrs)
+    cs_index = _cff2_index(charstrings)
+    private_dict = lambda subrs_off: _dict_int5(500) + b"\x14" + _dict_int5(subrs_off) + b"\x13"
+    priv_len = len(private_dict(0))
+    font_dict = lambda off: _dict_int5(priv_len) + _dict_int5(off) + b"\x12"
+    top_dict = lambda o: _dict_int5(o["charstrings"]) + b"\x11" + _dict_int5(o["vstore"]) + b"\x18" + _dict_int5(o["fdarray"]) + b"\x0c\x24"
+    zero = {"charstrings": 0, "vstore": 0, "fdarray": 0}
+    top_len = len(top_dict(zero))
+    pos = 5 + top_len + len(gsubr_index)
+    o = {}
+    o["vstore"] = pos
+    pos += len(vstore)
+    o["charstrings"] = pos
+    pos += len(cs_index)
+    o["fdarray"] = pos
+    fdarray_len = len(_cff2_index([font_dict(0)]))
+    pos += fdarray_len
+    priv_off = pos
+    fdarray = _cff2_index([font_dict(priv_off)])
+    assert len(fdarray) == fdarray_len
+    privs = private_dict(priv_len) + _cff2_index(local_subrs)
+    cff2 = struct.pack(">BBBH", 2, 0, 5, top_len) + top_dict(o) + gsubr_index + vstore + cs_index + fdarray + privs
+
+    fixed = lambda v: struct.pack(">i", int(round(v * 65536)))
+    axis = lambda tag, lo, de, hi, name_id: tag + fixed(lo) + fixed(de) + fixed(hi) + struct.pack(">HH", 0, name_id)
+    fvar = struct.pack(">HHHHHHHH", 1, 0, 16, 2, 2, 20, 0, 4 + 2 * 4) + axis(b"wght", 100, 400, 900, 256) + axis(b"wdth", 50, 100, 200, 257)
+
+    sub = struct.pack(">HHHHHHH", 4, 16 + 16, 0, 4, 0, 0, 0) + struct.pack(">HH", cps[-1], 0xFFFF) + b"\0\0" + \
+        struct.pack(">HH", cps[0], 0xFFFF) + struct.pack(">HH", (1 - cps[0]) & 0xFFFF, 1) + b"\0\0\0\0"
+    cmap_table = struct.pack(">HH", 0, 1) + struct.pack(">HHI", 3, 1, 12) + sub
+    head = struct.pack(">IIIIHHqqhhhhHHhhh", 0x00010000, 0x00010000, 0, 0x5F0F3CF5, 0, 1000, 0, 0, 0, -200, 1000, 800,
+                       0, 8, 2, 0, 0)
+    hhea = struct.pack(">IhhhHhhhhhhhhhhhH", 0x00010000, 800, -200, 0, 1100, 0, 0, 1000, 1, 0, 0, 0, 0, 0, 0, 0, n_all)
+    maxp = struct.pack(">IH", 0x00005000, n_all)
+    hm = np.zeros((n_all, 2), dtype=">u2")
+    hm[:, 0] = advances
+    names = [(1, "Synth CFF2"), (256, "Weight"), (257, "Width")]
+    strings = [t.encode("utf-16-be") for _, t in names]
+    recs, off = b"", 0
+    for (nid, _), st in zip(names, strings):
+        recs += struct.pack(">HHHHHH", 3, 1, 0x409, nid, len(st), off)
+        off += len(st)
+    name = struct.pack(">HHH", 0, len(names), 6 + 12 * len(names)) + recs + b"".join(strings)
+    tables = {b"CFF2": cff2, b"cmap": cmap_table, b"fvar": fvar, b"head": head, b"hhea": hhea, b"hmtx": hm.tobytes(),
+              b"maxp": maxp, b"name": name}
+    tags = sorted(tables)
+    out = struct.pack(">4sHHHH", b"OTTO", len(tags), 128, 3, len(tags) * 16 - 128)
     offset = 12 + 16 * len(tags)
     records, blobs = b"", b""
     for tag in tags:

@@ -295,3 +295,36 @@ def test_cff_charstrings_match_freetype(ft, cid):
         assert np.array_equal(h, w), hex(cp)
         checked += 1
     assert checked >= 30
+
+
+def test_cff2_charstrings_match_freetype(ft):
+    """CFF 2 outlines at the default instance (host/cff.cc parse2 / blend / vsindex): same path as FreeType's
+    interpreter, operator for operator — including the glyph whose variation region has scalar 1 at the default."""
+    blob, cps, _ = synth_font.cff2_test_font()
+    font = V.FontFileEntry(data=blob)
+    face = ft.face(blob)
+    checked = 0
+    for cp in cps:
+        gid = font.glyph_index(cp)
+        have = font.outline_commands(gid)
+        want = ft_decompose(ft, face, gid)
+
+        def drawing(rows):
+            return np.array([r for r in rows if r[0] != 4], np.float32).reshape(-1, 7)
+
+        def strip_closing_lines(rows):
+            keep, start = [], None
+            for k, r in enumerate(rows):
+                if r[0] == 0:
+                    start = (r[5], r[6])
+                nxt_is_new = k + 1 == len(rows) or rows[k + 1][0] == 0
+                if r[0] == 1 and nxt_is_new and (r[5], r[6]) == start:
+                    continue
+                keep.append(r)
+            return np.array(keep, np.float32).reshape(-1, 7)
+
+        h, w = strip_closing_lines(drawing(have)), strip_closing_lines(drawing(want))
+        assert h.shape == w.shape, (hex(cp), h.shape, w.shape)
+        assert np.array_equal(h, w), hex(cp)
+        checked += 1
+    assert checked >= 30

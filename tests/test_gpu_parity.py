@@ -347,6 +347,15 @@ def test_cff_font_parity(renderer, cid):
     print(f"CFF cid={cid}: {px} px, {100 * same / px:.4f}% identical")
 
 
+def test_cff2_font_parity(renderer):
+    """CFF 2 (variable .otf at its default instance): charstrings with blend / vsindex on the host -> cubic records ->
+    subdivision in the decode kernel (kind PATH) -> SDF kernel, against the oracle's own CFF 2 interpreter and f64
+    renderer."""
+    data, cps, _ = synth_font.cff2_test_font(n_glyphs=40)
+    px, same = _font_parity(data, renderer, "Synth CFF2", [0])
+    print(f"CFF2: {px} px, {100 * same / px:.4f}% identical")
+
+
 # ---- edge cases through the raw C ABI ---------------------------------------------------------------------
 def test_empty_and_degenerate_batches(ctx):
     # empty batch

@@ -450,6 +450,76 @@ def test_cff_charstrings_known_answers_and_oracle(cid, fdsel, charset):
         os.unlink(path)
 
 
+def test_cff2_charstrings_known_answers_and_oracle():
+    """CFF 2 outlines (variable .otf; ttf-parser cff2.rs at the face's default coordinates — the reference never sets
+    any): 32-bit INDEX counts, no width / endchar / return, `blend` with one and several operands, `vsindex`, a region
+    whose scalar is 1 at the default instance, hint operators, local / global / nested subroutines.  Host and oracle
+    must both reproduce the commands the charstrings were generated from, and the dummy pipeline must agree byte for
+    byte."""
+    import synth_font
+
+    data, cps, expected = synth_font.cff2_test_font()
+    f, o = V.FontFileEntry(data=data), O.Font(data)
+    assert f.codepoints().tolist() == cps == list(o.codepoints())
+    n_rings = 0
+    for cp, contours in zip(cps, expected):
+        gid = f.glyph_index(cp)
+        assert gid == o.glyph_index(cp) == cp - cps[0] + 1
+        want = _expected_rings(contours)
+        pts, starts = f.outline_rings(gid)
+        got_o = o.outline_rings(gid)
+        assert len(want) == len(starts) - 1 == len(got_o), (hex(cp), len(want), len(starts) - 1, len(got_o))
+        for i, r in enumerate(want):
+            assert np.array_equal(pts[starts[i] : starts[i + 1]], r), (hex(cp), i)
+            assert np.array_equal(got_o[i], r), (hex(cp), i)
+        n_rings += len(want)
+    assert n_rings > len(cps)
+    assert len(f.outline_rings(0)[1]) == 1 and len(o.outline_rings(0)) == 0  # .notdef: an empty charstring
+    m = V.FontManager(parallel=False)
+    m.add_font_bytes_with_name("Synth CFF2", data)
+    path = "/tmp/_cff2_synth.otf"
+    open(path, "wb").write(data)
+    try:
+        oset = O.FontSet("Synth CFF2", [path])
+        assert m.block_population("synth_cff2").tolist() == oset.block_population()
+        assert m.render_block("synth_cff2", 0, V.Renderer.new_dummy()) == oset.render_block(0, O.MODE_DUMMY)
+    finally:
+        os.unlink(path)
+
+
+def test_cff2_malformed_inputs_do_not_crash():
+    """Truncations and byte flips of the CFF2 and fvar tables: both parsers stay in bounds and agree on what comes out."""
+    import synth_font
+
+    data, cps, _ = synth_font.cff2_test_font(n_glyphs=10)
+    n_tables = int.from_bytes(data[4:6], "big")
+    rng = np.random.default_rng(4)
+    variants = []
+    for tag in (b"CFF2", b"fvar"):
+        rec = next(12 + 16 * i for i in range(n_tables) if data[12 + 16 * i : 16 + 16 * i] == tag)
+        off, length = int.from_bytes(data[rec + 8 : rec + 12], "big"), int.from_bytes(data[rec + 12 : rec + 16], "big")
+        for cut in (3, 9, 40, length // 2, length - 7):
+            b = bytearray(data)
+            b[rec + 12 : rec + 16] = max(0, min(cut, length)).to_bytes(4, "big")
+            variants.append(bytes(b))
+        for _ in range(120 if tag == b"CFF2" else 20):
+            b = bytearray(data)
+            for _ in range(int(rng.integers(1, 4))):
+                b[off + int(rng.integers(0, length))] = int(rng.integers(0, 256))
+            variants.append(bytes(b))
+    agreed = 0
+    for v in variants:
+        f, o = V.FontFileEntry(data=v), O.Font(v)
+        for gid in range(0, len(cps) + 1):
+            pts, starts = f.outline_rings(gid)
+            got_o = o.outline_rings(gid)
+            assert len(starts) - 1 == len(got_o)
+            for i, r in enumerate(got_o):
+                assert np.array_equal(pts[starts[i] : starts[i + 1]], r, equal_nan=True)
+            agreed += 1
+    assert agreed > 1000
+
+
 def test_cff_malformed_inputs_do_not_crash():
     """Truncations and byte flips of the CFF table: both parsers must stay in bounds and agree on what comes out
     (a rejected table = a face without outlines; a charstring error keeps the callbacks made before it)."""

@@ -71,12 +71,12 @@ uint32_t read_offset(const uint8_t *p, uint8_t size)
 	return v;
 }
 
-// parse_index::<u16>: false = None.  count 0 is the empty INDEX (two bytes).
-bool parse_index(Cursor &c, Index &out)
+// parse_index::<u16> (CFF 1) / parse_index::<u32> (CFF 2: `wide`): false = None.  count 0 is the empty INDEX.
+bool parse_index(Cursor &c, Index &out, bool wide = false)
 {
 	out = Index();
-	const uint16_t count = c.u16();
-	if (!c.ok)
+	const uint32_t count = wide ? c.u32() : c.u16();
+	if (!c.ok || count == 0xffffffffu)
 		return false;
 	if (count == 0)
 		return true;
@@ -288,6 +288,7 @@ bool encoding_well_formed(Bytes t, size_t off)
 
 constexpr int kStackLimit = 10;   // subroutine nesting
 constexpr int kMaxArguments = 48; // Type 2 argument stack
+constexpr int kMaxArguments2 = 513; // CFF 2 argument stack
 
 } // namespace
 
@@ -400,6 +401,161 @@ std::unique_ptr<CffTable> CffTable::parse(const uint8_t *data, size_t len)
 	return t;
 }
 
+// ---- CFF 2 (cff2.rs): variable-font outlines at the face's variation coordinates — which the reference never sets,
+// so every coordinate is 0 and the blend scalars are those of the default instance ------------------------------------
+std::unique_ptr<CffTable> CffTable::parse2(const uint8_t *data, size_t len, uint16_t axis_count)
+{
+	std::unique_ptr<CffTable> t(new CffTable());
+	t->table_.p = data, t->table_.len = len;
+	t->cff2_ = true;
+	t->axis_count_ = axis_count;
+	Cursor c(t->table_);
+	const uint8_t major = c.u8();
+	c.skip(1); // minor
+	const uint8_t header_size = c.u8();
+	const uint16_t top_dict_length = c.u16();
+	if (!c.ok || major != 2 || header_size < 5)
+		return nullptr;
+	c.skip(header_size - 5u);
+	const Bytes top_dict = c.take(top_dict_length);
+	if (!c.ok)
+		return nullptr;
+	size_t char_strings_off = 0, vstore_off = 0, fd_array_off = 0;
+	bool has_vstore = false, has_fd_array = false;
+	{
+		Dict d(top_dict);
+		for (int op = d.next(); op >= 0; op = d.next()) {
+			switch (op) {
+			case 17:
+				if (!d.offset(char_strings_off))
+					return nullptr;
+				break;
+			case 24: has_vstore = d.offset(vstore_off); break;
+			case 1236: has_fd_array = d.offset(fd_array_off); break;
+			default: break;
+			}
+		}
+	}
+	if (char_strings_off == 0)
+		return nullptr;
+	if (!parse_index(c, t->global_subrs_, true))
+		return nullptr;
+	{
+		Cursor cs(t->table_, char_strings_off);
+		if (!cs.ok || !parse_index(cs, t->char_strings_, true))
+			return nullptr;
+	}
+	if (has_vstore) {
+		// a u16 length, then an ItemVariationStore (var_store.rs): format 1, the region list, the data subtables
+		Cursor vs(t->table_, vstore_off);
+		vs.skip(2);
+		const size_t base = vs.pos;
+		const uint16_t format = vs.u16();
+		const uint32_t regions_off = vs.u32();
+		const uint16_t n_data = vs.u16();
+		if (!vs.ok || format != 1)
+			return nullptr;
+		t->var_data_offsets_ = vs.take((size_t)n_data * 4);
+		if (!vs.ok)
+			return nullptr;
+		t->var_store_ = Bytes{t->table_.p + base, t->table_.len - base};
+		Cursor rs(t->var_store_, regions_off);
+		t->region_axes_ = rs.u16();
+		const uint16_t n_regions = rs.u16();
+		t->regions_ = rs.take((size_t)t->region_axes_ * n_regions * 6);
+		if (!rs.ok)
+			return nullptr;
+		t->n_regions_ = n_regions;
+		t->has_var_store_ = true;
+	}
+	if (has_fd_array) {
+		// (no FDSelect in ttf-parser's CFF 2: the first Font DICT whose Private DICT has local subroutines supplies them)
+		Cursor fa(t->table_, fd_array_off);
+		Index fonts;
+		if (!fa.ok || !parse_index(fa, fonts, true))
+			return nullptr;
+		for (uint32_t i = 0; i < fonts.count; ++i) {
+			Bytes fd;
+			if (!fonts.get(i, fd))
+				return nullptr;
+			size_t priv_start = 0, priv_end = 0;
+			bool has_priv = false;
+			Dict d(fd);
+			for (int op = d.next(); op >= 0; op = d.next())
+				if (op == 18)
+					has_priv = d.range(priv_start, priv_end);
+			if (!has_priv)
+				return nullptr;
+			Bytes priv;
+			if (!sub(t->table_, priv_start, priv_end, priv))
+				return nullptr;
+			size_t subrs_off;
+			if (private_subrs_offset(priv, subrs_off)) {
+				Cursor ls(t->table_, priv_start + subrs_off);
+				if (!ls.ok || !parse_index(ls, t->local_subrs_, true))
+					return nullptr;
+				break;
+			}
+		}
+	}
+	return t;
+}
+
+// CharStringParserContext::update_scalars at all-zero coordinates: one scalar per region of ItemVariationData[index]
+// (RegionList::evaluate_region / evaluate_axis, var_store.rs).  false = InvalidItemVariationDataIndex / too many regions.
+bool CffTable::blend_scalars(uint16_t index, float *scalars, int &count) const
+{
+	count = 0;
+	if (!has_var_store_)
+		return false; // (the default store has no data subtables: every index is invalid)
+	if ((size_t)index * 4 + 4 > var_data_offsets_.len)
+		return false;
+	const uint32_t off = read_offset(var_data_offsets_.p + (size_t)index * 4, 4);
+	Cursor d(var_store_, off);
+	d.skip(4); // item count, short delta count
+	const uint16_t n = d.u16();
+	if (!d.ok)
+		return false;
+	for (uint16_t k = 0; k < n; ++k) {
+		const uint16_t region = d.u16();
+		if (!d.ok)
+			return false;
+		float v = 1.0f;
+		for (uint16_t axis = 0; axis < axis_count_; ++axis) {
+			// RegionList::get(index, axis): None -> the region evaluates to 0
+			if (region >= n_regions_ || axis >= region_axes_) {
+				v = 0.0f;
+				break;
+			}
+			const uint8_t *r = regions_.p + ((size_t)region * region_axes_ + axis) * 6;
+			const int16_t start = (int16_t)((r[0] << 8) | r[1]), peak = (int16_t)((r[2] << 8) | r[3]), end = (int16_t)((r[4] << 8) | r[5]);
+			// evaluate_axis(coord = 0)
+			float factor;
+			if (start > peak || peak > end)
+				factor = 1.0f;
+			else if (start < 0 && end > 0 && peak != 0)
+				factor = 1.0f;
+			else if (peak == 0)
+				factor = 1.0f;
+			else if (0 <= start || end <= 0)
+				factor = 0.0f;
+			else if (0 < peak)
+				factor = (float)(0 - start) / (float)(peak - start);
+			else
+				factor = (float)(end - 0) / (float)(end - peak);
+			if (factor == 0.0f) {
+				v = 0.0f;
+				break;
+			}
+			v *= factor;
+		}
+		if (count == 64)
+			return false; // BlendRegionsLimitReached
+		scalars[count++] = v;
+	}
+	return true;
+}
+
 // seac_code_to_glyph_id: StandardEncoding code -> SID -> glyph through the charset
 bool CffTable::seac_glyph(float code, uint16_t &glyph_id) const
 {
@@ -502,7 +658,12 @@ bool CffTable::cid_local_subrs(uint16_t glyph_id, Index &out) const
 struct CffTable::Interp {
 	OutlineBuilder &b;
 	uint16_t glyph_id;
-	float stack[kMaxArguments];
+	float stack[kMaxArguments2];
+	int max_len = kMaxArguments;
+	// CFF 2: blend scalars of the current ItemVariationData, `vsindex` / `blend` seen
+	bool cff2 = false, had_vsindex = false, had_blend = false;
+	float scalars[64];
+	int n_scalars = 0;
 	int len = 0;
 	float x = 0.f, y = 0.f;
 	bool has_move_to = false, is_first_move_to = true;
@@ -514,7 +675,7 @@ struct CffTable::Interp {
 	Interp(OutlineBuilder &bb, uint16_t g) : b(bb), glyph_id(g) {}
 	bool push(float v)
 	{
-		if (len == kMaxArguments)
+		if (len == max_len)
 			return false;
 		stack[len++] = v;
 		return true;
@@ -553,6 +714,8 @@ struct CffTable::Interp {
 	{
 		const int want = op == 21 ? 2 : 1;
 		int i = 0;
+		if (cff2 && len != want) // CFF 2 charstrings carry no width
+			return false;
 		if (len == want + 1) { // one argument too many: the first is the width (also inside a seac component)
 			have_width = true;
 			i = 1;
@@ -751,6 +914,39 @@ bool CffTable::run(Interp &in, Bytes code, int depth) const
 	Cursor s(code);
 	while (!s.at_end()) {
 		const uint8_t op = s.u8();
+		if (cff2_ && (op == 11 || op == 14))
+			return false; // `return` and `endchar` do not exist in CFF 2
+		if (cff2_ && op == 15) { // vsindex: once, before the first blend
+			if (in.had_blend || in.had_vsindex || in.len != 1)
+				return false;
+			const float v = in.pop();
+			if (!(v > -2147483904.f && v < 2147483648.f) || (int32_t)v < 0 || (int32_t)v > 65535)
+				return false;
+			if (!blend_scalars((uint16_t)(int32_t)v, in.scalars, in.n_scalars))
+				return false;
+			in.had_vsindex = true;
+			in.len = 0;
+			continue;
+		}
+		if (cff2_ && op == 16) { // blend: n defaults followed by n * k deltas, k = regions of the current variation data
+			in.had_blend = true;
+			if (in.len == 0)
+				return false;
+			const float nv = in.pop();
+			if (!(nv > -2147483904.f && nv < 2147483648.f) || (int32_t)nv < 0 || (int32_t)nv > 65535)
+				return false;
+			const int n = (int32_t)nv, k = in.n_scalars;
+			const int need = n * (k + 1);
+			if (in.len < need)
+				return false;
+			const int start = in.len - need;
+			for (int i = n - 1; i >= 0; --i)
+				for (int j = 0; j < k; ++j) {
+					const float delta = in.pop();
+					in.stack[start + i] += delta * in.scalars[k - j - 1];
+				}
+			continue;
+		}
 		switch (op) {
 		case 0: case 2: case 9: case 13: case 15: case 16: case 17:
 			return false; // reserved
@@ -925,6 +1121,16 @@ bool CffTable::outline(uint16_t glyph_id, OutlineBuilder &builder) const
 	if (!char_strings_.get(glyph_id, code))
 		return false;
 	Interp in(builder, glyph_id);
+	if (cff2_) {
+		in.cff2 = true;
+		in.max_len = kMaxArguments2;
+		in.have_width = true; // (no width anywhere: an odd stem count just drops its last value)
+		if (!blend_scalars(0, in.scalars, in.n_scalars)) // "load scalars at default index"
+			return false;
+		if (!run(in, code, 0))
+			return false;
+		return in.drew; // ZeroBBox
+	}
 	if (!run(in, code, 0))
 		return false;
 	return in.has_endchar && in.drew; // MissingEndChar; ZeroBBox (the box changes with the first move_to)

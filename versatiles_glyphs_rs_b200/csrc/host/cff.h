@@ -19,6 +19,8 @@ class CffTable {
   public:
 	// nullptr where cff::Table::parse returns None (the face then has no CFF outlines at all)
 	static std::unique_ptr<CffTable> parse(const uint8_t *data, size_t len);
+	// the same for a `CFF2` table (cff2::Table::parse); axis_count = the face's variation coordinates (fvar axes, all 0)
+	static std::unique_ptr<CffTable> parse2(const uint8_t *data, size_t len, uint16_t axis_count);
 	// false where Table::outline returns Err (callbacks may already have been made)
 	bool outline(uint16_t glyph_id, OutlineBuilder &builder) const;
 	uint32_t number_of_glyphs() const { return char_strings_.count; }
@@ -41,6 +43,7 @@ class CffTable {
 	bool run(Interp &in, Bytes code, int depth) const;
 	bool cid_local_subrs(uint16_t glyph_id, Index &out) const;
 	bool seac_glyph(float code, uint16_t &glyph_id) const;
+	bool blend_scalars(uint16_t index, float *scalars, int &count) const;
 
 	Bytes table_;
 	Index global_subrs_, char_strings_, local_subrs_, fd_array_;
@@ -51,6 +54,10 @@ class CffTable {
 	int charset_kind_ = 0;
 	Bytes charset_;
 	uint32_t charset_records_ = 0;
+	// CFF 2: ItemVariationStore (regions x axes of start / peak / end, data subtables -> region indices)
+	bool cff2_ = false, has_var_store_ = false;
+	uint16_t axis_count_ = 0, region_axes_ = 0, n_regions_ = 0;
+	Bytes var_store_, var_data_offsets_, regions_;
 };
 
 } // namespace vgb

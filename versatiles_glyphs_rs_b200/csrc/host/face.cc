@@ -82,6 +82,14 @@ std::unique_ptr<Face> Face::parse(std::vector<uint8_t> data)
 	Span cff;
 	if (f->table("CFF ", cff))
 		f->cff_ = CffTable::parse(f->data_.data() + cff.off, cff.len);
+	Span cff2, fvar;
+	if (f->table("CFF2", cff2)) {
+		// the face's variation coordinates: one per fvar axis (at most 64), all 0 — the reference never sets any
+		uint16_t axes = 0;
+		if (f->table("fvar", fvar) && fvar.len >= 10)
+			axes = std::min<uint16_t>(f->u16(fvar.off + 8), 64);
+		f->cff2_ = CffTable::parse2(f->data_.data() + cff2.off, cff2.len, axes);
+	}
 	if (f->table("cmap", f->cmap_) && f->cmap_.len >= 4) {
 		const uint16_t n = f->u16(f->cmap_.off + 2);
 		for (uint16_t i = 0; i < n; ++i) {
@@ -720,7 +728,7 @@ bool Face::parts_impl(Span g, int depth, const Transform &t, std::vector<GlyfPar
 Face::GlyfPlan Face::glyf_parts(uint16_t gid, std::vector<GlyfPart> &parts) const
 {
 	if (glyf_.len == 0 || loca_.len == 0)
-		return cff_ ? GlyfPlan::Host : GlyfPlan::None; // outline_glyph's order: glyf, then CFF
+		return cff_ || cff2_ ? GlyfPlan::Host : GlyfPlan::None; // outline_glyph's order: glyf, then CFF, then CFF2
 	Span g;
 	if (!glyph_range(gid, g))
 		return GlyfPlan::None;
@@ -736,7 +744,7 @@ bool Face::outline_glyph(uint16_t gid, OutlineBuilder &builder) const
 {
 	// ttf-parser's order (lib.rs, Face::outline_glyph): a face with glyf + loca never looks at `CFF `
 	if (glyf_.len == 0 || loca_.len == 0)
-		return cff_ ? cff_->outline(gid, builder) : false;
+		return cff_ ? cff_->outline(gid, builder) : (cff2_ ? cff2_->outline(gid, builder) : false);
 	Span g;
 	if (!glyph_range(gid, g))
 		return false;

@@ -108,7 +108,7 @@ class Face {
 	bool loca_long_ = false;
 	Span hmtx_, loca_, glyf_, cmap_, name_;
 	std::vector<CmapSubtable> subtables_;
-	std::unique_ptr<CffTable> cff_;
+	std::unique_ptr<CffTable> cff_, cff2_;
 	Face();
 };
 
