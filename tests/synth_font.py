@@ -838,3 +838,50 @@ def cff2_test_font(n_glyphs=30, first_cp=0x41, seed=11):
         blobs += padded
         offset += len(padded)
     return out + records + blobs, cps, expected
+
+
+def replace_table(blob: bytes, tag: bytes, new: bytes) -> bytes:
+    """The sfnt `blob` with table `tag` replaced by `new` (directory and offsets rebuilt, checksums recomputed)."""
+    n = int.from_bytes(blob[4:6], "big")
+    tables = {}
+    for i in range(n):
+        rec = 12 + 16 * i
+        t = blob[rec : rec + 4]
+        off, length = int.from_bytes(blob[rec + 8 : rec + 12], "big"), int.from_bytes(blob[rec + 12 : rec + 16], "big")
+        tables[t] = blob[off : off + length]
+    assert tag in tables
+    tables[tag] = new
+    tags = sorted(tables)
+    out = blob[:12]
+    offset = 12 + 16 * len(tags)
+    records, blobs = b"", b""
+    for t in tags:
+        data = tables[t]
+        records += t + struct.pack(">III", _table_checksum(data), offset, len(data))
+        padded = data + b"\0" * ((-len(data)) % 4)
+        blobs += padded
+        offset += len(padded)
+    return out + records + blobs
+
+
+def with_variation_selectors(blob: bytes, sequences) -> bytes:
+    """The font with a cmap format 14 subtable (platform 0, encoding 5) put IN FRONT of its existing subtable:
+    sequences = [(variation selector, [(base code point, glyph id)])] as non-default UVS mappings."""
+    n = int.from_bytes(blob[4:6], "big")
+    rec = next(12 + 16 * i for i in range(n) if blob[12 + 16 * i : 16 + 16 * i] == b"cmap")
+    off, length = int.from_bytes(blob[rec + 8 : rec + 12], "big"), int.from_bytes(blob[rec + 12 : rec + 16], "big")
+    cmap = blob[off : off + length]
+    assert int.from_bytes(cmap[2:4], "big") == 1
+    platform, encoding, sub_off = struct.unpack(">HHI", cmap[4:12])
+    old_sub = cmap[sub_off:]
+    header_len = 10 + 11 * len(sequences)
+    tables, pos = b"", header_len
+    records = b""
+    for vs, maps in sequences:
+        t = struct.pack(">I", len(maps)) + b"".join(cp.to_bytes(3, "big") + struct.pack(">H", g) for cp, g in maps)
+        records += vs.to_bytes(3, "big") + struct.pack(">II", 0, pos)
+        tables += t
+        pos += len(t)
+    f14 = struct.pack(">HII", 14, header_len + len(tables), len(sequences)) + records + tables
+    new = struct.pack(">HH", 0, 2) + struct.pack(">HHI", 0, 5, 20) + struct.pack(">HHI", platform, encoding, 20 + len(f14)) + f14 + old_sub
+    return replace_table(blob, b"cmap", new)

@@ -328,3 +328,14 @@ def test_cff2_charstrings_match_freetype(ft):
         assert np.array_equal(h, w), hex(cp)
         checked += 1
     assert checked >= 30
+
+
+def test_cmap_with_variation_selector_subtable_matches_freetype(ft):
+    """cmap format 14 in front of the Unicode subtable: plain lookups are FreeType's (which also ignores it for them)."""
+    cps = [0x41, 0x42, 0x43, 0x50] + list(range(0x4E00, 0x4E08))
+    plain = synth_font.build_font(cps, lambda cp: 3, seed=9, family="UVS Test", cmap_format=12)
+    blob = synth_font.with_variation_selectors(plain, [(0xFE00, [(0x41, 2), (0x4E00, 3)])])
+    font = V.FontFileEntry(data=blob)
+    face = ft.face(blob)
+    for cp in cps + [0x20, 0xFE00, 0x4E09]:
+        assert ft.ft.FT_Get_Char_Index(face, cp) == (font.glyph_index(cp) or 0), hex(cp)

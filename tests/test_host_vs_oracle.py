@@ -450,6 +450,32 @@ def test_cff_charstrings_known_answers_and_oracle(cid, fdsel, charset):
         os.unlink(path)
 
 
+def test_cmap_format_14_subtable_is_skipped_like_ttf_parser_does():
+    """A cmap with a format 14 (Unicode variation sequences) subtable in front of the usual one: ttf-parser's
+    `Face::glyph_index` asks every Unicode subtable in turn and format 14 answers None for a plain code point; its
+    `codepoints` callback enumerates nothing for format 14.  So lookups and the code point set are those of the font
+    without the subtable — host and oracle — and the variation selectors themselves are not code points of the font."""
+    import synth_font
+
+    cps = [0x41, 0x42, 0x43, 0x50] + list(range(0x4E00, 0x4E08))
+    plain = synth_font.build_font(cps, lambda cp: 3, seed=9, family="UVS Test", cmap_format=12)
+    data = synth_font.with_variation_selectors(plain, [(0xFE00, [(0x41, 2), (0x4E00, 3)]), (0xE0100, [(0x4E01, 4)])])
+    f0, f, o = V.FontFileEntry(data=plain), V.FontFileEntry(data=data), O.Font(data)
+    assert f.codepoints().tolist() == f0.codepoints().tolist() == sorted(cps) == list(o.codepoints())
+    for cp in cps + [0x20, 0xFE00, 0xE0100, 0x4E09]:
+        assert f.glyph_index(cp) == f0.glyph_index(cp) == o.glyph_index(cp), hex(cp)
+    m = V.FontManager(parallel=False)
+    m.add_font_bytes_with_name("UVS Test", data)
+    path = "/tmp/_cmap_14.ttf"
+    open(path, "wb").write(data)
+    try:
+        oset = O.FontSet("UVS Test", [path])
+        assert m.block_population("uvs_test").tolist() == oset.block_population()
+        assert m.render_block("uvs_test", 0, V.Renderer.new_dummy()) == oset.render_block(0, O.MODE_DUMMY)
+    finally:
+        os.unlink(path)
+
+
 def test_cff2_charstrings_known_answers_and_oracle():
     """CFF 2 outlines (variable .otf; ttf-parser cff2.rs at the face's default coordinates — the reference never sets
     any): 32-bit INDEX counts, no width / endchar / return, `blend` with one and several operands, `vsindex`, a region
