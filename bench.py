@@ -549,6 +549,8 @@ def main():
             "tile_jobs": n_tiles, "bitmap_checksum": checksum,
             "value_counts": "glyphs with a bitmap, all ranks; the timed step = glyf_decode_kernel + sdf_tiles_strided_kernel over this rank's shard",
             "decode_kernel_ms": statistics.mean(decode_ms), "sdf_kernel_ms": statistics.mean(sdf_ms), "step_ms_this_rank": statistics.mean(total_ms),
+            "step_ms_best_median_this_rank": [min(total_ms), statistics.median(total_ms)],
+            "pixels_per_s_this_rank": pixels / (statistics.mean(total_ms) * 1e-3),
             "resident_in_hbm": "glyf tables of the fonts (uploaded when first used, outside the timed region), glyph requests, bitmaps",
             "shard_cost_estimates": [int(x) for x in job.loads], "host_planned_sdf_kernel_ms": host_planned_ms,
             "device_plan_in_one_cta_per_job_kernel_ms": device_plan_ms,
