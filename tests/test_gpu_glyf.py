@@ -356,3 +356,91 @@ def test_cubic_outlines_are_flattened_on_the_device(renderer, cid, tmp_path):
         assert np.array_equal(ba, bb)
         px += ba.size
     assert px > 20000
+
+
+def test_path_requests_equal_uploaded_segments_for_random_outlines(renderer):
+    """Kind PATH at the C ABI, without a font: random closed outlines of lines, quadratics and cubics (integer font
+    units; some cubics with control points far outside, i.e. ten levels of subdivision; large coordinates at
+    upm 16384).  The decode kernel's flattening must give exactly the segments the reference's flattening gives
+    (oracle, f64, literal stack): the bitmap of every PATH request equals the bitmap of the same glyph sent as
+    uploaded segments, byte for byte, and the reference's leaf counts are accepted."""
+    import ctypes as C
+
+    from versatiles_glyphs_rs_b200.api import CURVE_DT, GLYPH_REQ_DT
+
+    rng = np.random.default_rng(17)
+    ctx = V.SdfContext.of_renderer(renderer)
+    recs, segs, reqs = [], [], []
+    out_off = gen_off = tile_cap = 0
+    n_cubic_leaves = 0
+    for g in range(120):
+        upm, span = (1000, 1000) if g % 3 else (16384, 30000)
+        scale, dx = 24.0 / upm, float(rng.uniform(-0.25, 0.25))
+        k = int(rng.integers(3, 7))
+        anchors = rng.integers(-span // 8, span, size=(k, 2)).astype(np.float64)
+        first_rec, seg_off, pts = len(recs), 0, [anchors[0]]
+        for i in range(k):
+            s, e = anchors[i], anchors[(i + 1) % k]
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                recs.append((s[0], s[1], s[0], s[1], e[0], e[1], seg_off, 0))
+                pts.append(e)
+                seg_off += 1
+            elif kind == 1:
+                c = rng.integers(-span // 8, span, size=2).astype(np.float64)
+                p = O.flatten_quad(s, c, e)
+                depth = int(np.log2(len(p)))
+                assert 1 << depth == len(p) and depth <= 12
+                recs.append((s[0], s[1], c[0], c[1], e[0], e[1], seg_off, depth))
+                pts.extend(p)
+                seg_off += len(p)
+            else:
+                far = span * (4 if g % 5 == 0 else 1)
+                c1, c2 = (rng.integers(-far, far, size=2).astype(np.float64) for _ in range(2))
+                p = O.flatten_cubic(s, c1, c2, e)
+                assert 1 <= len(p) < 4096
+                recs.append((s[0], s[1], c1[0], c1[1], c2[0], c2[1], seg_off, N.CURVE_CUBIC | len(p)))
+                recs.append((e[0], e[1], 0, 0, 0, 0, 0, N.CURVE_TAIL))
+                pts.extend(p)
+                seg_off += len(p)
+                n_cubic_leaves += len(p)
+        pts = np.array(pts)
+        px, py = pts[:, 0] * scale + dx, pts[:, 1] * scale + 0.0
+        x0, y0 = int(np.floor(px.min())) - 3, int(np.floor(py.min())) - 3
+        w, h = int(np.ceil(px.max())) + 3 - x0, int(np.ceil(py.max())) + 3 - y0
+        fx, fy = (px - x0).astype(np.float32), (py - y0).astype(np.float32)
+        first_seg = sum(len(sg) for sg in segs)
+        segs.append(np.stack([fx[:-1], fy[:-1], fx[1:], fy[1:]], axis=1))
+        assert len(segs[-1]) == seg_off
+        for kind, src_off, src_cnt in ((N.KIND_PATH, first_rec, len(recs) - first_rec), (N.KIND_SEGMENTS, first_seg, seg_off)):
+            r = np.zeros(1, GLYPH_REQ_DT)[0]
+            r["kind"], r["src_off"], r["src_cnt"], r["seg_cnt"] = kind, src_off, src_cnt, seg_off
+            r["width"], r["height"], r["x0"], r["y0"], r["scale"], r["dx"] = w, h, x0, y0, scale, dx
+            r["out_off"], r["out_cap"] = out_off, w * h
+            if kind == N.KIND_PATH:
+                r["curve_off"], r["curve_cap"] = gen_off, seg_off
+                gen_off += seg_off
+            out_off += (w * h + 15) & ~15
+            tile_cap += N.sdf.b200sdf_glyph_tile_bound(w, h)
+            reqs.append(r)
+    reqs = np.array(reqs, GLYPH_REQ_DT)
+    curves = np.array(recs, dtype=CURVE_DT)
+    frames, out = ctx.render_glyphs(reqs, np.zeros(0, V.api.GLYPH_PART_DT), 1, tile_cap, out_off, curves=curves,
+                                    segs=np.concatenate(segs), est_cost=0)
+    assert (frames["status"] == N.GLYPH_OK).all(), frames["status"]
+    assert n_cubic_leaves > 2000
+    px = 0
+    for a, b in zip(reqs[0::2], reqs[1::2]):
+        n = int(a["width"]) * int(a["height"])
+        assert np.array_equal(out[int(a["out_off"]) : int(a["out_off"]) + n], out[int(b["out_off"]) : int(b["out_off"]) + n])
+        px += n
+    assert px > 100000
+    # a leaf count that is not the subdivision's: the device notices and hands the glyph back
+    bad = curves.copy()
+    k = int(np.nonzero(bad["depth"] & N.CURVE_CUBIC)[0][0])
+    bad["depth"][k] += 1
+    frames, _ = ctx.render_glyphs(reqs, np.zeros(0, V.api.GLYPH_PART_DT), 1, tile_cap, out_off, curves=bad, segs=np.concatenate(segs))
+    hit = next(i for i in range(0, len(reqs), 2) if reqs["src_off"][i] <= k < reqs["src_off"][i] + reqs["src_cnt"][i])
+    assert frames["status"][hit] == N.GLYPH_NEEDS_HOST
+    assert (np.delete(frames["status"], hit) == N.GLYPH_OK).all()
+    assert N.sdf.b200sdf_reserve_glyphs(ctx._h, 4096, 1 << 16, 1 << 16, 1 << 14) == 0
