@@ -112,6 +112,38 @@ impl CudaRenderer {
     }
 }
 
+impl CudaRenderer {
+    /// Several batches in ONE submission (one decode launch, one SDF launch, one ticket): what a pipeline does with the
+    /// batches that queued up while the previous submission was being made.  With more than one batch every array must
+    /// live in memory from `b200sdf_alloc_pinned` (the library refuses pageable arrays here), so this is for hosts that
+    /// build their batches in pinned buffers, as csrc/host/pipeline.cc does.
+    pub fn submit_group(&self, batches: &mut [&mut GlyphBatch]) -> Result<u64> {
+        let mut descs = Vec::with_capacity(batches.len());
+        let mut est = 0u64;
+        for b in batches.iter_mut() {
+            b.frames.resize(b.reqs.len() + 1, sys::b200sdf_glyph_frame::default());
+            b.out.resize(b.out_bytes as usize + 16, 0);
+            est = est.max(b.est_cost);
+            descs.push(sys::b200sdf_glyph_batch {
+                reqs: b.reqs.as_ptr(), n_reqs: b.reqs.len() as u32, parts: b.parts.as_ptr(), n_parts: b.parts.len() as u32,
+                curves: std::ptr::null(), n_curves: 0, segs: std::ptr::null(), n_seg: 0, curve_slots: b.curve_slots,
+                tile_cap: b.tile_cap.max(1), frames: b.frames.as_mut_ptr(), out: b.out.as_mut_ptr(), out_bytes: b.out_bytes,
+            });
+        }
+        let mut ticket = 0u64;
+        let rc = unsafe { sys::b200sdf_submit_glyph_batches(self.ctx.0, descs.as_ptr(), descs.len() as u32, est, &mut ticket) };
+        check(self.ctx.0, rc, "b200sdf_submit_glyph_batches")?;
+        Ok(ticket)
+    }
+
+    /// Size every slot's device scratch for submissions of up to these totals, once, so that a long run never allocates
+    /// device memory in mid-flight (`b200sdf_reserve_glyphs`).
+    pub fn reserve(&self, glyphs: u32, segments: u32, curve_slots: u32, tile_jobs: u32) -> Result<()> {
+        check(self.ctx.0, unsafe { sys::b200sdf_reserve_glyphs(self.ctx.0, glyphs, segments, curve_slots, tile_jobs) },
+              "b200sdf_reserve_glyphs")
+    }
+}
+
 struct Pending {
     id: u32,
     advance: u32,
