@@ -1102,7 +1102,7 @@ uint32_t glyph_cost_cap(uint64_t est_cost)
 constexpr uint32_t kGlyphMinItems = 8;
 
 // The counters are zero when this is called (zeroed when they were allocated, and again by the last CTA of every
-// persistent kernel): a batch is two launches, nothing else.
+// SDF kernel): a batch is two launches, nothing else.
 void launch_glyph_pipeline(const b200sdf::DecodeParams &P, const void *d_segs, uint32_t *d_status, cudaStream_t stream, cudaEvent_t mid)
 {
 	using namespace b200sdf;

@@ -40,14 +40,15 @@ constexpr int kGlyfMaxPts = B200SDF_GLYF_MAX_POINTS;
 constexpr uint32_t kGlyfMaxDepth = 12;
 
 // Device-side bookkeeping of one batch.  glyf_decode_kernel appends every tile job to the list of its cost class
-// (class_count); the persistent SDF kernel claims them class after class, heaviest first (next_tile), and its last CTA
-// reports overflow and zeroes everything for the slot's next batch.
+// (class_count); the SDF kernel takes them class after class, heaviest first — CTA b the b-th one (strided form), or by
+// claiming from next_tile (persistent form) — and its last CTA reports overflow and zeroes everything for the slot's
+// next batch.
 constexpr int kTileClasses = 8; // class c: cost in (cap / 2^(c+1), cap / 2^c], the last one open-ended
 struct BatchCounters {
 	uint32_t class_count[kTileClasses];
 	uint32_t next_tile;
 	uint32_t overflow;
-	uint32_t done_ctas; // CTAs of the persistent kernel that have finished
+	uint32_t done_ctas; // CTAs of the SDF kernel that have finished
 	uint32_t pad;
 };
 
