@@ -1217,6 +1217,10 @@ int b200sdf_reserve_glyphs(b200sdf_ctx *ctx, uint32_t n_reqs, uint32_t n_seg, ui
 		for (int k = 0; k < 9; ++k) {
 			if (need[k] == 0)
 				continue;
+			// (a bound, not a need: a font with absurd header boxes can make it astronomical — beyond 256 MiB per buffer
+			// and slot the buffer is left to grow when a submission really needs it)
+			if (need[k] > ((size_t)256 << 20))
+				continue;
 			size_t r = (size_t)64 << 10;
 			while (r < need[k])
 				r <<= 1;

@@ -1113,8 +1113,11 @@ void Renderer::note_glyf_density(double segs_per_req, double curve_slots_per_req
 void Renderer::raise_batch_marks(const size_t caps[GlyphBatch::kBuffers]) const
 {
 	std::lock_guard<std::mutex> g(pool_mu_);
+	// (bounds, not needs: a font with absurd header boxes makes them astronomical — past 64 MiB per buffer the pool
+	// keeps growing with what batches really use, as it does without this call)
 	for (int i = 0; i < GlyphBatch::kBuffers; ++i)
-		hwm_[i] = std::max(hwm_[i], caps[i]);
+		if (caps[i] <= ((size_t)64 << 20))
+			hwm_[i] = std::max(hwm_[i], caps[i]);
 }
 
 void Renderer::set_pool_target(size_t batches) const
