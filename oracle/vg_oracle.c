@@ -287,9 +287,50 @@ static int32_t fmt12_lookup(span d, uint32_t cp)
 	return -1;
 }
 
+/* cmap format 2 (ttf-parser 0.25.1 cmap/format2.rs): number of subheaders, 0 = the subtable does not parse */
+static uint32_t fmt2_subheaders(span d)
+{
+	if (d.len < 518)
+		return 0;
+	uint32_t max_key = 0;
+	for (uint32_t k = 0; k < 256; k++) {
+		uint32_t key = rd16(d.p + 6 + 2 * k);
+		if (key > max_key)
+			max_key = key;
+	}
+	uint32_t n = max_key / 8 + 1;
+	return 518 + (size_t)n * 8 > d.len ? 0 : n;
+}
+
+static int32_t fmt2_lookup(span d, uint32_t cp)
+{
+	uint32_t n_sub = fmt2_subheaders(d);
+	if (cp > 0xFFFF || n_sub == 0)
+		return -1;
+	uint32_t high = cp >> 8, low = cp & 0xFF;
+	uint32_t i = cp < 0xFF ? 0 : rd16(d.p + 6 + 2 * high) / 8u;
+	if (i >= n_sub)
+		return -1;
+	const uint8_t *sh = d.p + 518 + (size_t)i * 8;
+	uint32_t first = rd16(sh), count = rd16(sh + 2), range_offset = rd16(sh + 6);
+	int32_t delta = rds16(sh + 4);
+	if (first + count > 0xFFFF || low < first || low >= first + count)
+		return -1;
+	size_t pos = (size_t)518 + 8 * ((size_t)i + 1) - 2 + range_offset + 2 * (size_t)(low - first);
+	if (pos + 2 > d.len)
+		return -1;
+	int32_t glyph = rd16(d.p + pos);
+	if (glyph == 0)
+		return -1;
+	int32_t v = (glyph + delta) % 65536;
+	return v < 0 ? -1 : v;
+}
+
 static int32_t sub_lookup(const cmap_sub *s, uint32_t cp)
 {
 	switch (s->format) {
+	case 2:
+		return fmt2_lookup(s->data, cp);
 	case 4:
 		return fmt4_lookup(s->data, cp);
 	case 12:
@@ -398,6 +439,34 @@ size_t vgo_font_codepoints(const vgo_font *f, uint32_t *out, size_t cap)
 				for (uint32_t cp = st; cp <= en && cp >= st; cp++)
 					if (sub_lookup(s, cp) >= 0)
 						uvec_push(&cps, cp);
+			}
+		} else if (s->format == 2) {
+			uint32_t n_sub = fmt2_subheaders(s->data);
+			int stop = n_sub == 0;
+			for (uint32_t fb = 0; fb < 256 && !stop; fb++) {
+				uint32_t i = rd16(s->data.p + 6 + 2 * fb) / 8u;
+				if (i >= n_sub)
+					break;
+				const uint8_t *sh = s->data.p + 518 + (size_t)i * 8;
+				uint32_t first = rd16(sh), count = rd16(sh + 2);
+				if (i == 0) {
+					if (first + count > 0xFFFF)
+						break;
+					if (fb >= first && fb < first + count && sub_lookup(s, fb) >= 0)
+						uvec_push(&cps, fb);
+				} else {
+					uint32_t b = first + (fb << 8);
+					if (b > 0xFFFF)
+						break;
+					for (uint32_t k = 0; k < count; k++) {
+						if (b + k > 0xFFFF) {
+							stop = 1;
+							break;
+						}
+						if (sub_lookup(s, b + k) >= 0)
+							uvec_push(&cps, b + k);
+					}
+				}
 			}
 		} else if (s->format == 0) {
 			for (uint32_t cp = 0; cp < 256; cp++)

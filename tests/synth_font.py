@@ -885,3 +885,22 @@ def with_variation_selectors(blob: bytes, sequences) -> bytes:
     f14 = struct.pack(">HII", 14, header_len + len(tables), len(sequences)) + records + tables
     new = struct.pack(">HH", 0, 2) + struct.pack(">HHI", 0, 5, 20) + struct.pack(">HHI", platform, encoding, 20 + len(f14)) + f14 + old_sub
     return replace_table(blob, b"cmap", new)
+
+
+def with_cmap_format2(blob: bytes, single, double) -> bytes:
+    """The font with its cmap replaced by ONE format 2 subtable (platform 0, encoding 3).  single = (first code, [glyph
+    ids]) for one-byte codes; double = [(lead byte, first low byte, id delta, [stored glyph ids])]."""
+    subs = [(single[0], 0, list(single[1]))] + [(lo, d, list(g)) for _, lo, d, g in double]
+    keys = [0] * 256
+    for k, (lead, _, _, _) in enumerate(double):
+        keys[lead] = 8 * (k + 1)
+    n_sub = len(subs)
+    array_start = 518 + 8 * n_sub
+    headers, array = b"", []
+    for i, (first, delta, glyphs) in enumerate(subs):
+        field = 518 + 8 * i + 6
+        headers += struct.pack(">HHhH", first, len(glyphs), delta, array_start + 2 * len(array) - field)
+        array += glyphs
+    body = b"".join(struct.pack(">H", k) for k in keys) + headers + b"".join(struct.pack(">H", g) for g in array)
+    sub = struct.pack(">HHH", 2, 6 + len(body), 0) + body
+    return replace_table(blob, b"cmap", struct.pack(">HH", 0, 1) + struct.pack(">HHI", 0, 3, 12) + sub)

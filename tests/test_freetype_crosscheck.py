@@ -339,3 +339,15 @@ def test_cmap_with_variation_selector_subtable_matches_freetype(ft):
     face = ft.face(blob)
     for cp in cps + [0x20, 0xFE00, 0x4E09]:
         assert ft.ft.FT_Get_Char_Index(face, cp) == (font.glyph_index(cp) or 0), hex(cp)
+
+
+def test_cmap_format_2_matches_freetype(ft):
+    """cmap format 2: the mapped one-byte and two-byte codes (and plainly unmapped ones) resolve as in FreeType."""
+    cps = list(range(0x4E00, 0x4E10))
+    base = synth_font.build_font(cps, lambda cp: 3, seed=5, family="Cmap2 Test")
+    blob = synth_font.with_cmap_format2(base, (0x41, [1, 2, 0, 4, 5]),
+                                        [(0x4E, 0x00, 5, [1, 2, 3, 4, 0, 6, 7, 8]), (0x81, 0x40, -2, [12, 13, 14, 2])])
+    font = V.FontFileEntry(data=blob)
+    face = ft.face(blob)
+    for cp in [0x41, 0x42, 0x43, 0x44, 0x45, 0x46, 0x20] + list(range(0x4E00, 0x4E09)) + list(range(0x8140, 0x8145)) + [0x9000]:
+        assert ft.ft.FT_Get_Char_Index(face, cp) == (font.glyph_index(cp) or 0), hex(cp)

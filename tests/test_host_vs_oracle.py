@@ -450,6 +450,47 @@ def test_cff_charstrings_known_answers_and_oracle(cid, fdsel, charset):
         os.unlink(path)
 
 
+def test_cmap_format_2_known_answers_and_oracle():
+    """cmap format 2 (high-byte mapping through table) under a Unicode platform id: one-byte codes through subheader 0,
+    two-byte codes through the lead byte's subheader, idDelta (negative too), stored glyph 0 = unmapped; the code point
+    set is what ttf-parser's `codepoints` enumerates, filtered by `glyph_index` (metadata.rs:104-118)."""
+    import synth_font
+
+    cps = list(range(0x4E00, 0x4E10))  # 16 glyphs, ids 1..16, whatever the base font's own cmap says
+    base = synth_font.build_font(cps, lambda cp: 3, seed=5, family="Cmap2 Test")
+    data = synth_font.with_cmap_format2(base, (0x41, [1, 2, 0, 4, 5]),
+                                        [(0x4E, 0x00, 5, [1, 2, 3, 4, 0, 6, 7, 8]), (0x81, 0x40, -2, [12, 13, 14, 2])])
+    expect = {0x41: 1, 0x42: 2, 0x44: 4, 0x45: 5}
+    expect.update({0x4E00 + k: g + 5 for k, g in enumerate([1, 2, 3, 4, 0, 6, 7, 8]) if g})
+    expect.update({0x8140 + k: g - 2 for k, g in enumerate([12, 13, 14, 2]) if g})
+    f, o = V.FontFileEntry(data=data), O.Font(data)
+    for cp in list(expect) + [0x20, 0x40, 0x43, 0x46, 0x4E04, 0x4E08, 0x813F, 0x8144, 0x9000, 0x1F600]:
+        assert f.glyph_index(cp) == expect.get(cp), hex(cp)
+        assert o.glyph_index(cp) == expect.get(cp), hex(cp)
+    assert f.codepoints().tolist() == sorted(expect) == list(o.codepoints())
+    m = V.FontManager(parallel=False)
+    m.add_font_bytes_with_name("Cmap2 Test", data)
+    path = "/tmp/_cmap_2.ttf"
+    open(path, "wb").write(data)
+    try:
+        oset = O.FontSet("Cmap2 Test", [path])
+        assert m.block_population("cmap2_test").tolist() == oset.block_population()
+        for b in (0, 0x4E, 0x81):
+            assert m.render_block("cmap2_test", b, V.Renderer.new_dummy()) == oset.render_block(b, O.MODE_DUMMY), b
+    finally:
+        os.unlink(path)
+    # truncations: both parsers answer nothing rather than reading past the table
+    for cut in (100, 517, 530, len(data)):
+        n = int.from_bytes(data[4:6], "big")
+        rec = next(12 + 16 * i for i in range(n) if data[12 + 16 * i : 16 + 16 * i] == b"cmap")
+        b = bytearray(data)
+        b[rec + 12 : rec + 16] = min(cut, int.from_bytes(data[rec + 12 : rec + 16], "big")).to_bytes(4, "big")
+        ft, ot = V.FontFileEntry(data=bytes(b)), O.Font(bytes(b))
+        assert ft.codepoints().tolist() == list(ot.codepoints())
+        for cp in list(expect)[:6]:
+            assert ft.glyph_index(cp) == ot.glyph_index(cp)
+
+
 def test_cmap_format_14_subtable_is_skipped_like_ttf_parser_does():
     """A cmap with a format 14 (Unicode variation sequences) subtable in front of the usual one: ttf-parser's
     `Face::glyph_index` asks every Unicode subtable in turn and format 14 answers None for a plain code point; its

@@ -160,6 +160,39 @@ std::optional<uint16_t> Face::lookup(const CmapSubtable &s, uint32_t cp) const
 			return std::nullopt;
 		return (uint16_t)(v + delta);
 	}
+	case 2: { // high-byte mapping through table (ttf-parser cmap/format2.rs; legacy CJK encodings)
+		if (cp > 0xFFFF || len < 518)
+			return std::nullopt;
+		uint32_t max_key = 0;
+		for (uint32_t k = 0; k < 256; ++k)
+			max_key = std::max<uint32_t>(max_key, u16(base + 6 + 2 * k));
+		const uint32_t n_sub = max_key / 8 + 1; // the subheader array is as long as the largest key says
+		if (518 + (size_t)n_sub * 8 > len)
+			return std::nullopt; // Subtable2::parse fails: the subtable answers nothing
+		const uint32_t high = cp >> 8, low = cp & 0xFF;
+		const uint32_t i = cp < 0xFF ? 0u : u16(base + 6 + 2 * high) / 8u; // "subheader 0 is for single-byte codes"
+		if (i >= n_sub)
+			return std::nullopt;
+		const size_t sh = base + 518 + (size_t)i * 8;
+		const uint32_t first = u16(sh), count = u16(sh + 2);
+		const int32_t delta = (int16_t)u16(sh + 4);
+		const uint32_t range_offset = u16(sh + 6);
+		if (first + count > 0xFFFF) // checked_add on u16
+			return std::nullopt;
+		if (low < first || low >= first + count)
+			return std::nullopt;
+		// idRangeOffset counts from its own position to the glyphIndexArray element of firstCode
+		const size_t pos = (size_t)518 + 8 * ((size_t)i + 1) - 2 + range_offset + 2 * (size_t)(low - first);
+		if (pos + 2 > len)
+			return std::nullopt;
+		const int32_t glyph = u16(base + pos);
+		if (glyph == 0)
+			return std::nullopt;
+		const int32_t v = (glyph + delta) % 65536; // (negative stays negative: u16::try_from fails)
+		if (v < 0)
+			return std::nullopt;
+		return (uint16_t)v;
+	}
 	case 6: {
 		if (len < 10)
 			return std::nullopt;
@@ -249,6 +282,39 @@ template <typename F> void Face::enumerate(const CmapSubtable &s, F &&f) const
 				break; // terminator segment
 			for (uint32_t cp = sc; cp <= ec; ++cp)
 				f(cp);
+		}
+		break;
+	}
+	case 2: { // format2.rs codepoints_inner: every code of every subheader's range; stops at the first malformed entry
+		if (len < 518)
+			return;
+		uint32_t max_key = 0;
+		for (uint32_t k = 0; k < 256; ++k)
+			max_key = std::max<uint32_t>(max_key, u16(base + 6 + 2 * k));
+		const uint32_t n_sub = max_key / 8 + 1;
+		if (518 + (size_t)n_sub * 8 > len)
+			return;
+		for (uint32_t first_byte = 0; first_byte < 256; ++first_byte) {
+			const uint32_t i = u16(base + 6 + 2 * first_byte) / 8u;
+			if (i >= n_sub)
+				return;
+			const size_t sh = base + 518 + (size_t)i * 8;
+			const uint32_t first = u16(sh), count = u16(sh + 2);
+			if (i == 0) {
+				if (first + count > 0xFFFF)
+					return;
+				if (first_byte >= first && first_byte < first + count)
+					f(first_byte);
+			} else {
+				const uint32_t b = first + (first_byte << 8);
+				if (b > 0xFFFF)
+					return;
+				for (uint32_t k = 0; k < count; ++k) {
+					if (b + k > 0xFFFF)
+						return;
+					f(b + k);
+				}
+			}
 		}
 		break;
 	}
