@@ -598,6 +598,7 @@ def main():
         e2e_loop(e2e_warmup, host_threads, V.Writer.new_memory)
         gc.collect()
         gc.disable()  # a generational collection of the interpreter's heap (torch, numpy, ...) is a 50 ms pause between steps
+        e2e_loop(2, host_threads, V.Writer.new_memory)  # (untimed: the collection above let the worker threads go to sleep)
         barrier()
         t0 = time.perf_counter()
         step_ms, st = e2e_loop(e2e_steps, host_threads, V.Writer.new_memory)
