@@ -8,6 +8,7 @@
 //   Writer         = writer/mod.rs:27-96          directory / in-memory sink
 #pragma once
 
+#include <atomic>
 #include <array>
 #include <cstdio>
 #include <cstdint>
@@ -162,7 +163,11 @@ class Writer {
 		std::vector<uint8_t> bytes;
 	};
 	const std::vector<Entry> &entries() const { return entries_; } // memory writer only
-	uint64_t bytes_written() const { return bytes_written_; }
+	uint64_t bytes_written() const { return __atomic_load_n(&bytes_written_, __ATOMIC_RELAXED); }
+	// The directory sink writes every file on its own (open, write, close): calls for different files need no lock
+	// between them.  (The reference serialises every write behind one mutex, manager.rs:108-111; the tar stream and the
+	// in-memory list do need it.)
+	bool concurrent_files() const { return to_disk_ && !to_tar_; }
 
   private:
 	bool tar_header(const std::string &path, uint64_t size, uint64_t mode, char typeflag, std::string *err);
@@ -173,7 +178,7 @@ class Writer {
 	std::shared_ptr<std::FILE> tar_file_;
 	std::shared_ptr<bool> tar_closed_; // finish() closes the file itself so that close errors are reported
 	std::vector<Entry> entries_;
-	uint64_t bytes_written_ = 0;
+	uint64_t bytes_written_ = 0; // (updated with atomic adds: directory-sink writes run side by side; the class stays movable)
 	bool finished_ = false;
 };
 

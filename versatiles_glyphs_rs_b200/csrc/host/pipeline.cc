@@ -476,7 +476,11 @@ bool FontManager::render_glyphs(Writer &writer, const Renderer &renderer, std::s
 			const uint64_t t0 = now_ns();
 			std::string e;
 			bool ok = true;
-			{
+			if (writer.concurrent_files()) { // files in a directory: every worker writes its own, side by side
+				for (auto &f : pending)
+					if (ok)
+						ok = writer.write_file(f.first, std::move(f.second), &e);
+			} else {
 				std::lock_guard<std::mutex> g(writer_mutex);
 				for (auto &f : pending)
 					if (ok)

@@ -112,7 +112,7 @@ static bool mkdirs(const std::string &path, std::string *err)
 
 bool Writer::write_file(const std::string &filename, const uint8_t *bytes, size_t len, std::string *err)
 {
-	bytes_written_ += len;
+	__atomic_fetch_add(&bytes_written_, (uint64_t)len, __ATOMIC_RELAXED);
 	if (to_tar_) { // writer/tar.rs:101-120
 		static const uint8_t zeros[512] = {0};
 		if (!tar_header(filename, len, 0644, '0', err) || !tar_put(bytes, len, err))
@@ -148,7 +148,7 @@ bool Writer::write_file(const std::string &filename, std::vector<uint8_t> &&byte
 {
 	if (to_disk_ || to_tar_)
 		return write_file(filename, bytes.data(), bytes.size(), err);
-	bytes_written_ += bytes.size();
+	__atomic_fetch_add(&bytes_written_, (uint64_t)bytes.size(), __ATOMIC_RELAXED);
 	Entry e;
 	e.name = filename;
 	e.bytes = std::move(bytes);
